@@ -1,0 +1,186 @@
+/* tt_b200.h -- C ABI of libtt_b200.so: the B200 (sm_100a) two-tower hot path.
+ *
+ * This is the drop-in boundary.  The reference (k0r1g/two-towers) is pure Python/PyTorch;
+ * its "FFI" for this path is the set of ATen calls made by its registered classes.  Each
+ * entry point below names the reference call site (file:line under /root/reference) it
+ * replaces.  The host-side mirror of the reference's registries (two_towers_b200/*.py) binds
+ * these symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  All data pointers are DEVICE pointers
+ *     on the current CUDA device unless the name ends in _host.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); nothing
+ *     allocates, synchronises or spawns threads.  Workspaces are caller-allocated; query
+ *     their size with the matching *_workspace() function (bytes, 256-B aligned base needed).
+ *   - return value: TT_OK (0) or a negative TT_ERR_*; tt_last_error() gives the message for
+ *     the calling thread.  There is NO CPU fallback: without an sm_100 device every compute
+ *     entry point returns TT_ERR_ARCH.
+ *   - matrices are row-major and contiguous; `ids` are token ids of `id_bytes` in {4, 8}
+ *     (int32 / int64; the reference uses int64, dataset.py:274-277).
+ *   - precision: TT_PREC_FP32 = CUDA-core fp32 FFMA (parity mode, rel 1e-5);
+ *                TT_PREC_BF16 = bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM
+ *                (performance mode, rel 2e-2).
+ *   - all reductions use a fixed order: results are bitwise reproducible run to run.
+ */
+#ifndef TT_B200_H
+#define TT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_ABI_VERSION 1
+
+enum { TT_OK = 0, TT_ERR_INVALID = -1, TT_ERR_CUDA = -2, TT_ERR_ARCH = -3, TT_ERR_WORKSPACE = -4,
+       TT_ERR_UNSUPPORTED = -5 };
+enum { TT_PREC_FP32 = 0, TT_PREC_BF16 = 1 };
+
+/* ---- library -------------------------------------------------------------------------- */
+int tt_abi_version(void);
+const char* tt_last_error(void);
+/* TT_OK iff `device` exists and is compute capability 10.x (B200).  Cached per device. */
+int tt_require_sm100(int device);
+/* Number of kernel launches issued by this library in the calling process so far. */
+int64_t tt_launch_count(void);
+
+/* ---- K1: token-id gather + masked mean pool ----------------------------------------------
+ * tt_embed_gather     : LookupEmbedding.forward, twotower/embeddings.py:33-40 (W[ids]).
+ * tt_embed_pool_fwd   : MeanPoolingTower.forward twotower/encoders.py:62,67,72 (and :125-138):
+ *                       mask=(ids>0); pooled = sum_l W[ids]*mask / (sum mask + 1e-9).
+ *                       Never materialises [rows,L,E].  inv_len[r] = 1/(count_r + 1e-9).
+ *                       pooled_bf16 (nullable) receives a bf16 copy for the tensor-core path.
+ * tt_embed_pool_bwd   : autograd of the above -> ATen embedding_dense_backward
+ *                       (loss.backward(), twotower/train.py:138).  Deterministic: small tables
+ *                       use a pooling-matrix GEMM with fixed split order, large tables a
+ *                       stable radix sort of (id,row) + ordered segment reduction.
+ *                       d_table [V,E] is OVERWRITTEN (row 0 = 0, untouched rows = 0).
+ */
+int tt_embed_gather(const void* ids, int id_bytes, const float* table, int64_t n_tokens,
+                    int64_t V, int E, float* out, void* stream);
+int tt_embed_pool_fwd(const void* ids, int id_bytes, const float* table, int64_t rows, int L,
+                      int64_t V, int E, float* pooled, float* inv_len, void* pooled_bf16,
+                      void* stream);
+size_t tt_embed_pool_bwd_workspace(int64_t rows, int L, int64_t V, int E);
+int tt_embed_pool_bwd(const void* ids, int id_bytes, const float* inv_len, const float* d_pooled,
+                      int64_t rows, int L, int64_t V, int E, float* d_table,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3: tower MLP  Linear(E,H) -> ReLU -> Linear(H,H) -> L2 normalise ---------------------
+ * Replaces MeanPoolingTower.feed_forward + F.normalize, twotower/encoders.py:38-42,77.
+ * Weights are nn.Linear layout: w1 [H,E], b1 [H], w2 [H,H], b2 [H].
+ * Saved for backward (caller-allocated): h1 [R,H] (post-ReLU), z [R,H] (pre-normalise).
+ * y [R,H] has unit rows: y = z / max(||z||, 1e-12).  y_bf16 (nullable): bf16 copy of y.
+ * tt_mlp_bwd: given dy, produces dx [R,E] (nullable), dw1, db1, dw2, db2 (OVERWRITTEN).
+ */
+size_t tt_mlp_workspace(int64_t R, int E, int H, int precision);
+int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+               int64_t R, int E, int H, float* h1, float* z, float* y, void* y_bf16,
+               int precision, void* workspace, size_t workspace_bytes, void* stream);
+int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2,
+               const float* h1, const float* z, int64_t R, int E, int H,
+               float* dx, float* dw1, float* db1, float* dw2, float* db2,
+               int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3': avg_pool tower projection  Linear(E,H) -> Dropout(p) -> LayerNorm(H) -> normalise -
+ * Replaces AveragePoolingTower.projection + F.normalize, twotower/encoders.py:100-104,144-150.
+ * has_projection == 0 (H == E): y = normalise(x) only (w,b,gamma,beta ignored).
+ * Dropout: p == 0 or training == 0 -> identity (the parity-tested mode); otherwise a
+ * counter-based keep-mask from (seed, element index), recomputed in backward.
+ * Saved: a [R,H] (post-dropout pre-LN), stats [R,2] (mean, rstd), z [R,H] (LN output).
+ */
+size_t tt_proj_ln_workspace(int64_t R, int E, int H);
+int tt_proj_ln_fwd(const float* x, const float* w, const float* b, const float* gamma,
+                   const float* beta, int64_t R, int E, int H, int has_projection,
+                   float dropout_p, int training, uint64_t seed,
+                   float* a, float* stats, float* z, float* y,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int tt_proj_ln_bwd(const float* dy, const float* x, const float* w, const float* gamma,
+                   const float* a, const float* stats, const float* z,
+                   int64_t R, int E, int H, int has_projection,
+                   float dropout_p, int training, uint64_t seed,
+                   float* dx, float* dw, float* db, float* dgamma, float* dbeta,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4: in-batch sampled-softmax loss, fused similarity GEMM + online logsumexp CE --------
+ * Replaces in_batch_sampled_softmax_loss, twotower/losses.py:107-116: S = Q D^T; S/temperature;
+ * labels = arange; cross_entropy(mean).  The [Bq,Bd] logits never reach HBM.
+ *   q [Bq,H], d [Bd,H]; row i's positive is column i + label_offset (0 == the reference;
+ *   rank*B_local with all-gathered D gives global in-batch negatives).
+ *   loss (device scalar) = loss_scale * sum_i (lse_i - logit_ii); pass loss_scale = 1/Bq for
+ *   the reference's mean.  lse [Bq] is saved for backward.  pos_mean (nullable device scalar)
+ *   = mean_i S_ii (the train.py:145-147 monitoring value, free here).
+ * tt_inbatch_ce_bwd: dq = g*loss_scale/temp * (P - I) D ; dd = g*loss_scale/temp * (P - I)^T Q,
+ *   g read from device scalar grad_out (nullable == 1).  dq / dd nullable.
+ * q_bf16/d_bf16 (nullable): bf16 copies of q/d used by TT_PREC_BF16 (else converted inside).
+ */
+size_t tt_inbatch_ce_workspace(int64_t Bq, int64_t Bd, int H, int precision);
+int tt_inbatch_ce_fwd(const float* q, const float* d, const void* q_bf16, const void* d_bf16,
+                      int64_t Bq, int64_t Bd, int H, float inv_temperature, int64_t label_offset,
+                      float loss_scale, float* loss, float* lse, float* pos_mean,
+                      int precision, void* workspace, size_t workspace_bytes, void* stream);
+int tt_inbatch_ce_bwd(const float* q, const float* d, const void* q_bf16, const void* d_bf16,
+                      const float* lse, int64_t Bq, int64_t Bd, int H, float inv_temperature,
+                      int64_t label_offset, float loss_scale, const float* grad_out,
+                      float* dq, float* dd,
+                      int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5/K6: row-paired cosine losses ------------------------------------------------------
+ * tt_triplet_*   : contrastive_triplet_loss, twotower/losses.py:28-35:
+ *                  mean(relu(margin - cos(q,p) + cos(q,n))), cosine eps 1e-8.
+ *                  sims: 3*B floats saved -- [B,2] (cos_qp, cos_qn) followed by [B] row
+ *                  losses; pos_mean/neg_mean nullable device scalars (train.py:145-151
+ *                  monitoring).
+ * tt_multineg_*  : multiple_negatives_loss, twotower/losses.py:65-83: cos(q,[p;negs])/temp,
+ *                  CE vs label 0.  negs [B,N,H], N <= 63; probs: B*(N+1)+B floats saved --
+ *                  [B,N+1] softmax followed by [B] row losses.
+ */
+int tt_triplet_fwd(const float* q, const float* p, const float* n, int64_t B, int H, float margin,
+                   float* loss, float* sims, float* pos_mean, float* neg_mean, void* stream);
+int tt_triplet_bwd(const float* q, const float* p, const float* n, const float* sims,
+                   int64_t B, int H, float margin, const float* grad_out,
+                   float* dq, float* dp, float* dn, void* stream);
+int tt_multineg_fwd(const float* q, const float* p, const float* negs, int64_t B, int N, int H,
+                    float inv_temperature, float* loss, float* probs, void* stream);
+int tt_multineg_bwd(const float* q, const float* p, const float* negs, const float* probs,
+                    int64_t B, int N, int H, float inv_temperature, const float* grad_out,
+                    float* dq, float* dp, float* dnegs, void* stream);
+
+/* ---- K7: brute-force scan + top-k ---------------------------------------------------------
+ * Replaces TwoTowerSearch.search scoring + torch.topk, inference/search/two_tower.py:98-105.
+ *   index [N,H] fp32 (index_bf16 == 0) or bf16 (== 1), contiguous (what index_documents
+ *   writes, two_tower.py:69).  queries [nq,H] fp32.  cosine == 0: raw dot products (valid for
+ *   the unit rows both towers emit); cosine == 1: divide by max(||q||,1e-8)*max(||d||,1e-8)
+ *   exactly like F.cosine_similarity.
+ *   out_scores [nq,k] fp32 and out_ids [nq,k] int64 (global id = row + id_offset), sorted by
+ *   descending score, ties -> LOWER id first; k <= min(N, TT_TOPK_MAX).
+ * tt_topk_merge: merge R sorted candidate lists per query (the sharded / multi-GPU step):
+ *   scores [R,nq,k], ids [R,nq,k] -> [nq,k], same ordering rule.
+ */
+#define TT_TOPK_MAX 1024
+size_t tt_topk_scan_workspace(int64_t N, int H, int nq, int k);
+int tt_topk_scan(const void* index, int index_bf16, const float* queries, int64_t N, int H,
+                 int nq, int k, int cosine, int64_t id_offset,
+                 float* out_scores, int64_t* out_ids,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int tt_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k,
+                  float* out_scores, int64_t* out_ids, void* stream);
+/* fp32 -> bf16 row copy used by index_documents when the index is kept in bf16. */
+int tt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- optimizer: torch.optim.AdamW(model.parameters(), lr), train.py:359 ------
+ * One fused AdamW step over a flat fp32 parameter buffer (ATen _single_tensor_adamw
+ * semantics, amsgrad off).  step_count: device int64 holding the number of steps already
+ * taken; the kernel uses step_count+1 for bias correction and tt_adamw_step increments it
+ * (graph-capturable: no host state).  param_bf16 (nullable): refreshed bf16 shadow.
+ */
+int tt_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                  int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int64_t* step_count, void* param_bf16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_B200_H */

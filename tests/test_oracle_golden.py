@@ -169,3 +169,32 @@ def test_adamw_and_train_steps(golden_dir):
         for k in names:
             p[k], m[k], v[k] = O.adamw_step(p[k], grads[k].astype(np.float32), m[k], v[k], step + 1)
             close(p[k], g[f"step{step}_{k}"], rtol=1e-5, atol=1e-6)
+
+
+def test_torch_port_matches_reference_training(golden_dir):
+    """oracle/torch_port.py (the CPU baseline that bench.py times) reproduces the reference's 3 steps."""
+    import torch
+    from oracle import torch_port as P
+    g = np.load(os.path.join(golden_dir, "train_triplet_3steps.npz"))
+    V, E = g["init_embedding"].shape
+    H = g["init_w1"].shape[0]
+    model = P.PortTwoTower(V, E, H, tied=True)
+    model.query_tower.load_state_dict({
+        "embedding.weight": torch.tensor(g["init_embedding"]),
+        "feed_forward.0.weight": torch.tensor(g["init_w1"]), "feed_forward.0.bias": torch.tensor(g["init_b1"]),
+        "feed_forward.2.weight": torch.tensor(g["init_w2"]), "feed_forward.2.bias": torch.tensor(g["init_b2"])})
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    for step in range(3):
+        loss, _, _ = P.train_step(model, opt, "triplet", torch.tensor(g[f"step{step}_q_ids"]),
+                                  torch.tensor(g[f"step{step}_d_ids"]), torch.tensor(g[f"step{step}_n_ids"]))
+        close(loss, g[f"step{step}_loss"], rtol=1e-6)
+        close(model.query_tower.feed_forward[2].weight.detach().numpy(), g[f"step{step}_w2"], rtol=1e-6)
+
+
+def test_torch_port_search_matches_reference(golden_dir):
+    import torch
+    from oracle import torch_port as P
+    g = np.load(os.path.join(golden_dir, "search_topk.npz"))
+    v, i = P.search(torch.tensor(g["Q"][1:2]), torch.tensor(g["D"]), 100)
+    np.testing.assert_array_equal(v.numpy(), g["topk_values"][1])
+    np.testing.assert_array_equal(i.numpy(), g["topk_indices"][1])

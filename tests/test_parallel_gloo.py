@@ -1,0 +1,133 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in two_towers_b200/parallel.py.
+
+The collectives, offsets, scaling and merge plumbing are the product code under test; the
+per-rank numerical kernels are replaced by a CPU stand-in built on the oracle (tests may use
+oracle/), because the CUDA kernels cannot run here.  Equivalence target: the
+2-rank result equals the single-process reference result on the concatenated batch / index.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class OracleKernels:
+    """CPU stand-in with the same call signatures as two_towers_b200.ops."""
+
+    @staticmethod
+    def inbatch_ce_fwd(q, d, temperature, label_offset=0, loss_scale=None, precision=None, **_):
+        from oracle import two_tower_oracle as O
+        qn, dn = q.numpy().astype(np.float64), d.numpy().astype(np.float64)
+        loss, lse = O.in_batch_loss(qn, dn, temperature, label_offset)
+        scale = 1.0 / qn.shape[0] if loss_scale is None else loss_scale
+        return torch.tensor(loss * qn.shape[0] * scale), torch.tensor(lse), None
+
+    @staticmethod
+    def inbatch_ce_bwd(q, d, lse, temperature, label_offset=0, loss_scale=None, grad_out=None, need_dq=True,
+                       need_dd=True, precision=None, **_):
+        qn, dn = q.numpy().astype(np.float64), d.numpy().astype(np.float64)
+        G = np.exp(qn @ dn.T / temperature - lse.numpy()[:, None])
+        for i in range(qn.shape[0]):
+            j = i + label_offset
+            if 0 <= j < dn.shape[0]:
+                G[i, j] -= 1.0
+        scale = 1.0 / qn.shape[0] if loss_scale is None else loss_scale
+        G *= scale / temperature * (1.0 if grad_out is None else float(grad_out))
+        return (torch.tensor(G @ dn) if need_dq else None), (torch.tensor(G.T @ qn) if need_dd else None)
+
+    @staticmethod
+    def topk_scan(index, queries, k, cosine=True, id_offset=0, **_):
+        from oracle import two_tower_oracle as O
+        s = O.search_scores(queries.numpy(), index.numpy()) if cosine else queries.numpy() @ index.numpy().T
+        v, i = O.topk_lower_index(s, k)
+        return torch.tensor(v), torch.tensor(i + id_offset)
+
+    @staticmethod
+    def topk_merge(all_s, all_i):
+        R, nq, k = all_s.shape
+        s = all_s.permute(1, 0, 2).reshape(nq, R * k).numpy()
+        i = all_i.permute(1, 0, 2).reshape(nq, R * k).numpy()
+        out_s, out_i = np.empty((nq, k), np.float32), np.empty((nq, k), np.int64)
+        for q in range(nq):
+            valid = i[q] >= 0
+            order = sorted(np.nonzero(valid)[0], key=lambda j: (-s[q, j], i[q, j]))[:k]
+            out_s[q], out_i[q] = s[q, order], i[q, order]
+        return torch.tensor(out_s), torch.tensor(out_i)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q_out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import two_tower_oracle as O
+        from two_towers_b200 import parallel
+        K = OracleKernels
+        g = np.random.default_rng(0)
+        B, H, t = 6, 16, 0.1
+        Q = O.normalize(g.standard_normal((world * B, H)))
+        D = O.normalize(g.standard_normal((world * B, H)))
+        ql, dl = torch.tensor(Q[rank * B:(rank + 1) * B]), torch.tensor(D[rank * B:(rank + 1) * B])
+        # ---- training: global in-batch negatives ------------------------------------------
+        loss, lse, d_glob = parallel.global_inbatch_fwd(ql, dl, t, K)
+        assert d_glob.shape == (world * B, H) and np.allclose(d_glob.numpy(), D)
+        total = loss.clone().double()
+        dist.all_reduce(total)
+        ref_loss, ref_lse = O.in_batch_loss(Q, D, t)
+        np.testing.assert_allclose(total.item(), ref_loss, rtol=1e-10)
+        np.testing.assert_allclose(lse.numpy(), ref_lse[rank * B:(rank + 1) * B], rtol=1e-10)
+        dq, dd = parallel.global_inbatch_bwd(ql, dl, d_glob, lse, t, K)
+        ref_dq, ref_dd = O.in_batch_loss_bwd(Q, D, t)
+        np.testing.assert_allclose(dq.numpy(), ref_dq[rank * B:(rank + 1) * B], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(dd.numpy(), ref_dd[rank * B:(rank + 1) * B], rtol=1e-9, atol=1e-12)
+        # flat-gradient all-reduce
+        flat = torch.full((5,), float(rank + 1))
+        parallel.allreduce_sum_(flat)
+        assert torch.all(flat == sum(range(1, world + 1)))
+        # ---- search: row-sharded index, uneven shards, planted ties, shard smaller than k -----
+        for N, k in ((101, 10), (7, 5), (3, 3)):
+            idx = O.normalize(g.standard_normal((N, H))).astype(np.float32)
+            if N > 60:
+                idx[60] = idx[3]                       # tie across shards -> lower global id first
+            qs = O.normalize(g.standard_normal((3, H))).astype(np.float32)
+            qs[0] = idx[3] if N > 3 else qs[0]
+            lo, hi = parallel.shard_bounds(N, rank, world)
+            s, i = parallel.sharded_topk(torch.tensor(idx[lo:hi]), torch.tensor(qs), k, lo, K)
+            rs, ri = O.topk_lower_index(O.search_scores(qs, idx), k)
+            np.testing.assert_array_equal(i.numpy(), ri)
+            np.testing.assert_allclose(s.numpy(), rs, rtol=1e-6)
+            if N > 60:
+                assert list(i[0, :2].numpy()) == [3, 60]
+        q_out.put((rank, "ok"))
+    except Exception as e:                                     # pragma: no cover
+        import traceback
+        q_out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_global_negatives_and_sharded_search():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(30)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"

@@ -1,0 +1,85 @@
+"""ctypes binding of ``libtt_b200.so`` (the C ABI declared in ``include/tt_b200.h``).
+
+The library is built in-tree by ``two_towers_b200/csrc/Makefile`` (``__graft_entry__.build()``).
+There is NO fallback: if the shared object is missing, or a compute entry point is called
+without an sm_100 device, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtt_b200.so")
+
+TT_PREC_FP32 = 0
+TT_PREC_BF16 = 1
+TT_TOPK_MAX = 1024
+
+_vp, _i, _i64, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
+
+# name -> (restype, argtypes); mirrors include/tt_b200.h one to one
+SIGNATURES = {
+    "tt_abi_version": (_i, []),
+    "tt_last_error": (C.c_char_p, []),
+    "tt_require_sm100": (_i, [_i]),
+    "tt_launch_count": (_i64, []),
+    "tt_embed_gather": (_i, [_vp, _i, _vp, _i64, _i64, _i, _vp, _vp]),
+    "tt_embed_pool_fwd": (_i, [_vp, _i, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp, _vp]),
+    "tt_embed_pool_bwd_workspace": (_sz, [_i64, _i, _i64, _i]),
+    "tt_embed_pool_bwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _i64, _i, _vp, _vp, _sz, _vp]),
+    "tt_mlp_workspace": (_sz, [_i64, _i, _i, _i]),
+    "tt_mlp_fwd": (_i, [_vp] * 5 + [_i64, _i, _i] + [_vp] * 4 + [_i, _vp, _sz, _vp]),
+    "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 5 + [_i, _vp, _sz, _vp]),
+    "tt_proj_ln_workspace": (_sz, [_i64, _i, _i]),
+    "tt_proj_ln_fwd": (_i, [_vp] * 5 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 4 + [_vp, _sz, _vp]),
+    "tt_proj_ln_bwd": (_i, [_vp] * 7 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 5 + [_vp, _sz, _vp]),
+    "tt_inbatch_ce_workspace": (_sz, [_i64, _i64, _i, _i]),
+    "tt_inbatch_ce_fwd": (_i, [_vp] * 4 + [_i64, _i64, _i, _f, _i64, _f] + [_vp] * 3 + [_i, _vp, _sz, _vp]),
+    "tt_inbatch_ce_bwd": (_i, [_vp] * 5 + [_i64, _i64, _i, _f, _i64, _f] + [_vp] * 3 + [_i, _vp, _sz, _vp]),
+    "tt_triplet_fwd": (_i, [_vp] * 3 + [_i64, _i, _f] + [_vp] * 4 + [_vp]),
+    "tt_triplet_bwd": (_i, [_vp] * 4 + [_i64, _i, _f] + [_vp] * 4 + [_vp]),
+    "tt_multineg_fwd": (_i, [_vp] * 3 + [_i64, _i, _i, _f] + [_vp] * 2 + [_vp]),
+    "tt_multineg_bwd": (_i, [_vp] * 4 + [_i64, _i, _i, _f] + [_vp] * 4 + [_vp]),
+    "tt_topk_scan_workspace": (_sz, [_i64, _i, _i, _i]),
+    "tt_topk_scan": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "tt_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "tt_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "tt_adamw_step": (_i, [_vp] * 4 + [_i64, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libtt_b200.so (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"two_towers_b200: {LIB_PATH} is missing -- build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C two_towers_b200/csrc`). "
+            "There is no CPU / PyTorch fallback for the hot path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError == ABI mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.tt_abi_version() != 1:
+        raise RuntimeError(f"two_towers_b200: ABI version {lib.tt_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().tt_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(load().tt_launch_count())

@@ -1,0 +1,435 @@
+// embed_pool.cu -- K1 fused token-id gather + masked mean pool (fwd) and K2 its deterministic
+// backward (dense embedding gradient).
+//
+// Reference: twotower/encoders.py:62,67,72 (mask = ids>0; W[ids]*mask; sum/(count+1e-9)) over
+// nn.Embedding (twotower/embeddings.py:30,40); backward = ATen embedding_dense_backward
+// reached from loss.backward() (twotower/train.py:138).
+//
+// fwd: one warp per batch row.  A row of the table is E floats; lanes are split into
+//   32/TPT token-groups of TPT lanes (TPT = lanes needed to cover E/4 float4 chunks), so small
+//   E (char tower, E=64 -> 16 lanes) gathers two tokens per warp instruction and large E
+//   (E=300 -> 75 chunks) gives every lane up to 3 independent 128-bit loads per token.  The
+//   [rows,L,E] tensor the reference materialises (twice) never exists.
+// bwd, small tables (V <= 1024): build the pooling matrix P[r,v] = count(r,v) * inv_len[r]
+//   (integer smem histogram -> exact, order-free) and compute dW = P^T * dPooled with the
+//   fixed-order split-K GEMM.
+// bwd, large tables: stable radix sort of (id, row) pairs, then a chunked segmented reduction
+//   in sorted order: every vocabulary row has exactly one writer and a fixed summation order,
+//   so dW is bitwise reproducible (atomics would not be).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "sgemm.cuh"
+
+namespace tt {
+
+template <typename IdT>
+__device__ __forceinline__ int64_t load_id(const IdT* p) { return (int64_t)__ldg(p); }
+
+// ---------------------------------------------------------------------------------------
+// K1 forward
+// ---------------------------------------------------------------------------------------
+template <typename IdT, int NACC, bool VEC>
+__global__ void __launch_bounds__(256)
+embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ table, int64_t rows,
+                      int L, int64_t V, int E, int tpt, float* __restrict__ pooled,
+                      float* __restrict__ inv_len, __nv_bfloat16* __restrict__ pooled_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int groups = 32 / tpt;
+  const int sub = lane % tpt, grp = lane / tpt;
+  const IdT* rid = ids + row * L;
+
+  if (VEC) {
+    const int chunks = E >> 2;
+    // column blocks of tpt*NACC float4 chunks (one pass for E <= 128*NACC)
+    int count = 0;
+    for (int cbase = 0; cbase < chunks; cbase += tpt * NACC) {
+      float4 acc[NACC];
+#pragma unroll
+      for (int j = 0; j < NACC; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cnt = 0;
+      int t = grp;
+      // 4 tokens in flight per group: ids first, then all row loads, then the adds
+      for (; t + 3 * groups < L; t += 4 * groups) {
+        int64_t id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) id[u] = load_id(rid + t + u * groups);
+        float4 v[4][NACC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool ok = id[u] > 0 && id[u] < V;
+          cnt += ok;
+          const float4* src = reinterpret_cast<const float4*>(table + (ok ? id[u] : 0) * E);
+#pragma unroll
+          for (int j = 0; j < NACC; ++j) {
+            int c = cbase + sub + j * tpt;
+            v[u][j] = (ok && c < chunks) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < NACC; ++j) {
+            acc[j].x += v[u][j].x; acc[j].y += v[u][j].y; acc[j].z += v[u][j].z; acc[j].w += v[u][j].w;
+          }
+      }
+      for (; t < L; t += groups) {
+        int64_t id = load_id(rid + t);
+        const bool ok = id > 0 && id < V;
+        cnt += ok;
+        if (ok) {
+          const float4* src = reinterpret_cast<const float4*>(table + id * E);
+#pragma unroll
+          for (int j = 0; j < NACC; ++j) {
+            int c = cbase + sub + j * tpt;
+            if (c < chunks) {
+              float4 v = __ldg(src + c);
+              acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+            }
+          }
+        }
+      }
+      // combine the token groups (lanes with equal `sub`), fixed xor-tree order
+      for (int o = tpt; o < 32; o <<= 1) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+          acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o);
+          acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
+          acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o);
+          acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+      count = cnt;
+      const float denom = (float)cnt + 1e-9f;           // encoders.py:72
+      if (grp == 0) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+          int c = cbase + sub + j * tpt;
+          if (c < chunks) {
+            float4 o = make_float4(acc[j].x / denom, acc[j].y / denom, acc[j].z / denom, acc[j].w / denom);
+            *reinterpret_cast<float4*>(pooled + row * E + 4 * c) = o;
+            if (pooled_bf16) {
+              uint2 pk = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+              *reinterpret_cast<uint2*>(pooled_bf16 + row * E + 4 * c) = pk;
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0 && inv_len) inv_len[row] = 1.0f / ((float)count + 1e-9f);
+  } else {
+    // scalar path (E not a multiple of 4 or unaligned table): lane-strided columns
+    int cnt = 0;
+    for (int t = 0; t < L; ++t) {
+      int64_t id = load_id(rid + t);
+      cnt += (id > 0 && id < V);
+    }
+    const float denom = (float)cnt + 1e-9f;
+    for (int e = lane; e < E; e += 32) {
+      float s = 0.f;
+      for (int t = 0; t < L; ++t) {
+        int64_t id = load_id(rid + t);
+        if (id > 0 && id < V) s += __ldg(table + id * E + e);
+      }
+      float o = s / denom;
+      pooled[row * E + e] = o;
+      if (pooled_bf16) pooled_bf16[row * E + e] = __float2bfloat16(o);
+    }
+    if (lane == 0 && inv_len) inv_len[row] = 1.0f / denom;
+  }
+}
+
+// plain gather (API compatibility with LookupEmbedding.forward -> [B,L,E])
+template <typename IdT>
+__global__ void embed_gather_kernel(const IdT* __restrict__ ids, const float* __restrict__ table,
+                                    int64_t n_tokens, int64_t V, int E, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t = warp; t < n_tokens; t += nwarps) {
+    int64_t id = load_id(ids + t);
+    const bool ok = id >= 0 && id < V;
+    for (int e = lane; e < E; e += 32) out[t * E + e] = ok ? __ldg(table + id * E + e) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 backward, small tables: pooling matrix + GEMM
+// ---------------------------------------------------------------------------------------
+template <typename IdT>
+__global__ void __launch_bounds__(256)
+pool_matrix_kernel(const IdT* __restrict__ ids, const float* __restrict__ inv_len, int64_t rows,
+                   int L, int V, float* __restrict__ P) {
+  extern __shared__ int hist[];                       // [warps][V]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int* h = hist + w * V;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
+  if (row >= rows) return;
+  for (int v = lane; v < V; v += 32) h[v] = 0;
+  __syncwarp();
+  for (int t = lane; t < L; t += 32) {
+    int64_t id = load_id(ids + row * L + t);
+    if (id > 0 && id < V) atomicAdd(&h[(int)id], 1);   // integer: exact, order-independent
+  }
+  __syncwarp();
+  const float il = inv_len[row];
+  for (int v = lane; v < V; v += 32) P[row * V + v] = (float)h[v] * il;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 backward, large tables: sort + ordered segmented reduction
+// ---------------------------------------------------------------------------------------
+template <typename IdT>
+__global__ void make_keys_kernel(const IdT* __restrict__ ids, int64_t n_tokens, int L, int64_t V,
+                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_tokens;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t id = load_id(ids + t);
+    keys[t] = (id > 0 && id < V) ? (uint32_t)id : (uint32_t)V;   // masked tokens sort last
+    vals[t] = (uint32_t)(t / L);                                 // owning batch row
+  }
+}
+
+constexpr int kSegChunk = 64;     // sorted tokens per warp
+
+// One warp per chunk of kSegChunk sorted tokens.  Segments that START inside the chunk are
+// written straight to dW (sole writer).  The leading run that continues a segment begun in an
+// earlier chunk goes to carry[chunk]; seg_fixup adds carries in chunk order.
+__global__ void __launch_bounds__(256)
+seg_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                  const float* __restrict__ inv_len, const float* __restrict__ g, int64_t n_tokens,
+                  int64_t V, int E, float* __restrict__ dW, float* __restrict__ carry) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t p0 = chunk * kSegChunk;
+  if (p0 >= n_tokens) return;
+  const int64_t p1 = (p0 + kSegChunk < n_tokens) ? p0 + kSegChunk : n_tokens;
+  for (int ebase = 0; ebase < E; ebase += 128) {          // 4 columns per lane per pass
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t cur = keys[p0];
+    bool continued = (p0 > 0) && (keys[p0 - 1] == cur);
+    for (int64_t p = p0; p <= p1; ++p) {
+      uint32_t k = (p < p1) ? keys[p] : 0xffffffffu;
+      if (k != cur) {                                     // flush finished run
+        if (cur < (uint32_t)V) {
+          float* dst = continued ? carry + chunk * E : dW + (int64_t)cur * E;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            int e = ebase + lane + 32 * j;
+            if (e < E) dst[e] = acc[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = 0.f;
+        cur = k;
+        continued = false;
+        if (p == p1) break;
+      }
+      const uint32_t r = vals[p];
+      const float s = inv_len[r];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int e = ebase + lane + 32 * j;
+        if (e < E) acc[j] = fmaf(__ldg(g + (int64_t)r * E + e), s, acc[j]);
+      }
+    }
+  }
+}
+
+// One warp per chunk whose LAST run continues into later chunks and STARTED in this chunk (or
+// at token 0): walk the following chunks in order, adding their carries.
+__global__ void __launch_bounds__(256)
+seg_fixup_kernel(const uint32_t* __restrict__ keys, int64_t n_tokens, int64_t V, int E,
+                 float* __restrict__ dW, const float* __restrict__ carry) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t p0 = chunk * kSegChunk;
+  if (p0 >= n_tokens) return;
+  const int64_t p1 = (p0 + kSegChunk < n_tokens) ? p0 + kSegChunk : n_tokens;
+  if (p1 >= n_tokens) return;                             // nothing after this chunk
+  const uint32_t key = keys[p1 - 1];
+  if (key >= (uint32_t)V || keys[p1] != key) return;      // last run ends here
+  // the run must have started in this chunk, otherwise an earlier chunk owns the fix-up
+  if (keys[p0] == key && p0 > 0 && keys[p0 - 1] == key) return;
+  for (int64_t c = chunk + 1; c * kSegChunk < n_tokens; ++c) {
+    const int64_t q0 = c * kSegChunk;
+    if (keys[q0] != key) break;
+    for (int e = lane; e < E; e += 32) dW[(int64_t)key * E + e] += carry[c * E + e];
+    const int64_t q1 = (q0 + kSegChunk < n_tokens) ? q0 + kSegChunk : n_tokens;
+    if (keys[q1 - 1] != key) break;                       // run ended inside chunk c
+  }
+}
+
+constexpr int64_t kSmallVocab = 1024;
+
+struct BwdPlan {
+  bool small;
+  int splits;
+  size_t p_bytes, partial_bytes;                 // small path
+  size_t keys_bytes, carry_bytes, cub_bytes;     // sort path
+  size_t total;
+};
+
+static BwdPlan plan_bwd(int64_t rows, int L, int64_t V, int E) {
+  BwdPlan p{};
+  p.small = (V <= kSmallVocab);
+  if (p.small) {
+    p.splits = sgemm_pick_splits((int)V, E, (int)rows);
+    p.p_bytes = align_up((size_t)rows * V * sizeof(float));
+    p.partial_bytes = align_up(sgemm_partial_bytes((int)V, E, p.splits));
+    p.total = p.p_bytes + p.partial_bytes;
+  } else {
+    const int64_t n = rows * L;
+    p.keys_bytes = align_up((size_t)n * sizeof(uint32_t));
+    p.carry_bytes = align_up((size_t)ceil_div(n, kSegChunk) * E * sizeof(float));
+    size_t cub = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 32);
+    p.cub_bytes = align_up(cub);
+    p.total = 4 * p.keys_bytes + p.carry_bytes + p.cub_bytes;
+  }
+  p.total += 256;
+  return p;
+}
+
+template <typename IdT>
+static int embed_pool_fwd_t(const IdT* ids, const float* table, int64_t rows, int L, int64_t V, int E,
+                            float* pooled, float* inv_len, __nv_bfloat16* pooled_bf16, cudaStream_t s) {
+  const int warps = 8;
+  const unsigned grid = (unsigned)ceil_div(rows, warps);
+  const bool vec = (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(table) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(pooled) & 15) == 0) &&
+                   (pooled_bf16 == nullptr || (reinterpret_cast<uintptr_t>(pooled_bf16) & 7) == 0);
+  if (!vec) {
+    embed_pool_fwd_kernel<IdT, 1, false><<<grid, warps * 32, 0, s>>>(ids, table, rows, L, V, E, 32,
+                                                                       pooled, inv_len, pooled_bf16);
+  } else {
+    const int chunks = E / 4;
+    int tpt = 1;
+    while (tpt < chunks && tpt < 32) tpt <<= 1;
+    const int per_lane = (int)ceil_div(chunks, tpt);
+    if (per_lane <= 1)
+      embed_pool_fwd_kernel<IdT, 1, true><<<grid, warps * 32, 0, s>>>(ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16);
+    else if (per_lane == 2)
+      embed_pool_fwd_kernel<IdT, 2, true><<<grid, warps * 32, 0, s>>>(ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16);
+    else
+      embed_pool_fwd_kernel<IdT, 3, true><<<grid, warps * 32, 0, s>>>(ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16);
+  }
+  TT_LAUNCH_CHECK("embed_pool_fwd_kernel");
+  return TT_OK;
+}
+
+template <typename IdT>
+static int embed_pool_bwd_t(const IdT* ids, const float* inv_len, const float* d_pooled, int64_t rows,
+                            int L, int64_t V, int E, float* d_table, void* ws, size_t ws_bytes,
+                            cudaStream_t s) {
+  const BwdPlan plan = plan_bwd(rows, L, V, E);
+  if (ws == nullptr || ws_bytes < plan.total) {
+    set_error("embed_pool_bwd: workspace too small (%zu < %zu)", ws_bytes, plan.total);
+    return TT_ERR_WORKSPACE;
+  }
+  Workspace w(ws, ws_bytes);
+  if (plan.small) {
+    float* P = w.take<float>((size_t)rows * V);
+    float* partial = plan.splits > 1 ? w.take<float>((size_t)plan.splits * V * E) : nullptr;
+    const int warps = 8;
+    pool_matrix_kernel<IdT><<<(unsigned)ceil_div(rows, warps), warps * 32, warps * V * sizeof(int), s>>>(
+        ids, inv_len, rows, L, (int)V, P);
+    TT_LAUNCH_CHECK("pool_matrix_kernel");
+    SgemmArgs a{};
+    a.M = (int)V; a.N = E; a.K = (int)rows;
+    a.A = P; a.lda = (int)V; a.transA = 1;           // P^T
+    a.B = d_pooled; a.ldb = E; a.transB = 0;
+    a.C = d_table; a.ldc = E;
+    a.splits = plan.splits; a.partial = partial;
+    return sgemm(a, s);                               // row 0 of P is all-zero -> dW[0] = 0
+  }
+  const int64_t n = rows * L;
+  TT_CHECK_ARG(n < (int64_t)1 << 31, "embed_pool_bwd: too many tokens (%lld)", (long long)n);
+  uint32_t* keys_in = w.take<uint32_t>(n);
+  uint32_t* vals_in = w.take<uint32_t>(n);
+  uint32_t* keys = w.take<uint32_t>(n);
+  uint32_t* vals = w.take<uint32_t>(n);
+  float* carry = w.take<float>((size_t)ceil_div(n, kSegChunk) * E);
+  void* cub_ws = w.take<char>(plan.cub_bytes);
+  size_t cub_bytes = plan.cub_bytes;
+  TT_CUDA(cudaMemsetAsync(d_table, 0, (size_t)V * E * sizeof(float), s));
+  make_keys_kernel<IdT><<<(unsigned)(ceil_div(n, 256) < 8 * kNumSMs ? ceil_div(n, 256) : 8 * kNumSMs), 256, 0, s>>>(
+      ids, n, L, V, keys_in, vals_in);
+  TT_LAUNCH_CHECK("make_keys_kernel");
+  int end_bit = 1;
+  while (((int64_t)1 << end_bit) <= V && end_bit < 32) ++end_bit;
+  TT_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_in, keys, vals_in, vals, (int)n, 0,
+                                          end_bit, s));      // stable -> fixed order
+  count_launch(3);
+  const int warps = 8;
+  const unsigned grid = (unsigned)ceil_div(ceil_div(n, kSegChunk), warps);
+  seg_reduce_kernel<<<grid, warps * 32, 0, s>>>(keys, vals, inv_len, d_pooled, n, V, E, d_table, carry);
+  TT_LAUNCH_CHECK("seg_reduce_kernel");
+  seg_fixup_kernel<<<grid, warps * 32, 0, s>>>(keys, n, V, E, d_table, carry);
+  TT_LAUNCH_CHECK("seg_fixup_kernel");
+  return TT_OK;
+}
+
+}  // namespace tt
+
+extern "C" {
+
+int tt_embed_gather(const void* ids, int id_bytes, const float* table, int64_t n_tokens, int64_t V,
+                    int E, float* out, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(ids && table && out && n_tokens >= 0 && V > 0 && E > 0, "embed_gather: bad arguments");
+  TT_CHECK_ARG(id_bytes == 4 || id_bytes == 8, "embed_gather: id_bytes must be 4 or 8");
+  if (n_tokens == 0) return TT_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned grid = (unsigned)(tt::ceil_div(n_tokens, 8) < 16 * tt::kNumSMs ? tt::ceil_div(n_tokens, 8) : 16 * tt::kNumSMs);
+  if (id_bytes == 8)
+    tt::embed_gather_kernel<int64_t><<<grid, 256, 0, s>>>((const int64_t*)ids, table, n_tokens, V, E, out);
+  else
+    tt::embed_gather_kernel<int32_t><<<grid, 256, 0, s>>>((const int32_t*)ids, table, n_tokens, V, E, out);
+  TT_LAUNCH_CHECK("embed_gather_kernel");
+  return TT_OK;
+}
+
+int tt_embed_pool_fwd(const void* ids, int id_bytes, const float* table, int64_t rows, int L, int64_t V,
+                      int E, float* pooled, float* inv_len, void* pooled_bf16, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(ids && table && pooled && rows >= 0 && L > 0 && V > 0 && E > 0, "embed_pool_fwd: bad arguments");
+  TT_CHECK_ARG(id_bytes == 4 || id_bytes == 8, "embed_pool_fwd: id_bytes must be 4 or 8");
+  if (rows == 0) return TT_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (id_bytes == 8)
+    return tt::embed_pool_fwd_t<int64_t>((const int64_t*)ids, table, rows, L, V, E, pooled, inv_len,
+                                         (__nv_bfloat16*)pooled_bf16, s);
+  return tt::embed_pool_fwd_t<int32_t>((const int32_t*)ids, table, rows, L, V, E, pooled, inv_len,
+                                       (__nv_bfloat16*)pooled_bf16, s);
+}
+
+size_t tt_embed_pool_bwd_workspace(int64_t rows, int L, int64_t V, int E) {
+  if (rows <= 0 || L <= 0 || V <= 0 || E <= 0) return 256;
+  return tt::plan_bwd(rows, L, V, E).total;
+}
+
+int tt_embed_pool_bwd(const void* ids, int id_bytes, const float* inv_len, const float* d_pooled,
+                      int64_t rows, int L, int64_t V, int E, float* d_table, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(ids && inv_len && d_pooled && d_table && rows >= 0 && L > 0 && V > 0 && E > 0,
+               "embed_pool_bwd: bad arguments");
+  TT_CHECK_ARG(id_bytes == 4 || id_bytes == 8, "embed_pool_bwd: id_bytes must be 4 or 8");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rows == 0) {
+    TT_CUDA(cudaMemsetAsync(d_table, 0, (size_t)V * E * sizeof(float), s));
+    return TT_OK;
+  }
+  if (id_bytes == 8)
+    return tt::embed_pool_bwd_t<int64_t>((const int64_t*)ids, inv_len, d_pooled, rows, L, V, E, d_table,
+                                         workspace, workspace_bytes, s);
+  return tt::embed_pool_bwd_t<int32_t>((const int32_t*)ids, inv_len, d_pooled, rows, L, V, E, d_table,
+                                       workspace, workspace_bytes, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// tensor_core.cuh -- entry points of the TT_PREC_BF16 path (tcgen05 / TMEM / TMA kernels,
+// implemented in tc_*.cu).  Called by the C-ABI functions in tower.cu / inbatch_ce.cu.
+#pragma once
+#include "common.cuh"
+
+namespace tt {
+
+// tower MLP on tcgen05 (tc_mlp.cu)
+size_t tc_mlp_workspace(int64_t R, int E, int H);
+int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+               int64_t R, int E, int H, float* h1, float* z, float* y, __nv_bfloat16* y_bf16,
+               void* ws, size_t ws_bytes, cudaStream_t s);
+int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1,
+               const float* z, int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2,
+               float* db2, void* ws, size_t ws_bytes, cudaStream_t s);
+
+// fused similarity GEMM + online-LSE cross entropy on tcgen05 (tc_inbatch.cu)
+size_t tc_inbatch_workspace(int64_t Bq, int64_t Bd, int H);
+int tc_inbatch_fwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16,
+                   int64_t Bq, int64_t Bd, int H, float inv_temp, int64_t label_offset, float loss_scale,
+                   float* loss, float* lse, float* pos_mean, void* ws, size_t ws_bytes, cudaStream_t s);
+int tc_inbatch_bwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16,
+                   const float* lse, int64_t Bq, int64_t Bd, int H, float inv_temp, int64_t label_offset,
+                   float loss_scale, const float* grad_out, float* dq, float* dd, void* ws, size_t ws_bytes,
+                   cudaStream_t s);
+
+// shared by both precisions (inbatch_ce.cu): lse/loss finalisation from per-split (max,sum)
+int inbatch_finalize(const float* part_ml, const float* pos_logit, int nsplit, int64_t Bq, float inv_temp,
+                     float loss_scale, float* lse, float* loss, float* pos_mean, float* scratch,
+                     cudaStream_t s);
+
+}  // namespace tt

@@ -1,0 +1,113 @@
+"""Multi-GPU pieces (one process per GPU, ``torch.distributed`` / NCCL over NVLink).
+
+The reference has no distributed code at all; the path shards naturally in two
+places and only these use a collective:
+
+* training with global in-batch negatives: all-gather of the document embeddings before the
+  fused loss kernel (``label_offset = rank * B_local``), all-gather of (Q, lse) for the dD
+  pass, one all-reduce of the flat gradient buffer;
+* search: row-sharded index, local top-k, all-gather of k candidates per rank, merge kernel.
+
+The numerical work is delegated to a ``kernels`` namespace (default: ``two_towers_b200.ops``,
+i.e. the CUDA library).  The world_size-2 ``gloo`` CPU tests inject a CPU stand-in namespace
+to exercise exactly this host logic without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
+    """[B_local, ...] -> [world * B_local, ...] (rank-major), no autograd."""
+    rank, ws = world(group)
+    if ws == 1:
+        return x
+    out = torch.empty((ws * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def global_inbatch_fwd(q_local, d_local, temperature: float, kernels, group=None, precision=None):
+    """Forward of the global-negatives in-batch loss on this rank's rows.
+
+    Returns (loss_local_contribution, lse_local, d_global).  The *global* loss is the SUM of
+    loss_local_contribution over ranks (each already scaled by 1/B_global), which equals the
+    reference ``in_batch_sampled_softmax_loss`` on the concatenated batch.
+    """
+    rank, ws = world(group)
+    B_local = q_local.shape[0]
+    d_global = all_gather_rows(d_local, group)
+    loss, lse, _ = kernels.inbatch_ce_fwd(q_local, d_global, temperature, label_offset=rank * B_local,
+                                          loss_scale=1.0 / (ws * B_local), precision=precision)
+    return loss, lse, d_global
+
+
+def global_inbatch_bwd(q_local, d_local, d_global, lse_local, temperature: float, kernels, group=None,
+                       precision=None, grad_out=None):
+    """Backward: dq for local queries (vs all docs) and dd for local docs (vs all queries).
+
+    dd uses the all-gather(Q, lse) + local recompute variant: same bytes on the wire as the
+    forward, no fp32 reduce-scatter, and deterministic.
+    """
+    rank, ws = world(group)
+    B_local = q_local.shape[0]
+    scale = 1.0 / (ws * B_local)
+    dq, _ = kernels.inbatch_ce_bwd(q_local, d_global, lse_local, temperature, label_offset=rank * B_local,
+                                   loss_scale=scale, grad_out=grad_out, need_dq=True, need_dd=False,
+                                   precision=precision)
+    q_global = all_gather_rows(q_local, group)
+    lse_global = all_gather_rows(lse_local, group)
+    _, dd = kernels.inbatch_ce_bwd(q_global, d_local, lse_global, temperature, label_offset=-rank * B_local,
+                                   loss_scale=scale, grad_out=grad_out, need_dq=False, need_dd=True,
+                                   precision=precision)
+    return dq, dd
+
+
+def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    _, ws = world(group)
+    if ws > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+def shard_bounds(n: int, rank: int, ws: int) -> Tuple[int, int]:
+    """Contiguous row range [lo, hi) of shard `rank` (rows split as evenly as possible)."""
+    base, rem = divmod(n, ws)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sharded_topk(index_shard: torch.Tensor, queries: torch.Tensor, k: int, id_offset: int, kernels, group=None,
+                 cosine: bool = True):
+    """Local scan + top-k on this rank's rows, all-gather the k candidates, merge.
+
+    Every rank returns the same (scores [nq,k], global ids [nq,k]).  Shards smaller than k pad
+    their lists with (-inf, -1), which the merge kernel ignores.
+    """
+    _, ws = world(group)
+    nq = queries.shape[0]
+    n_local = index_shard.shape[0]
+    k_local = min(k, n_local)
+    if k_local > 0:
+        s, i = kernels.topk_scan(index_shard, queries, k_local, cosine=cosine, id_offset=id_offset)
+    else:
+        s = torch.empty(nq, 0, dtype=torch.float32, device=queries.device)
+        i = torch.empty(nq, 0, dtype=torch.int64, device=queries.device)
+    if ws == 1 and k_local == k:
+        return s, i
+    if k_local < k:
+        pad_s = torch.full((nq, k - k_local), float("-inf"), dtype=torch.float32, device=s.device)
+        pad_i = torch.full((nq, k - k_local), -1, dtype=torch.int64, device=s.device)
+        s, i = torch.cat([s, pad_s], 1), torch.cat([i, pad_i], 1)
+    all_s = all_gather_rows(s.unsqueeze(0), group)          # [R,nq,k]
+    all_i = all_gather_rows(i.unsqueeze(0), group)
+    return kernels.topk_merge(all_s, all_i)

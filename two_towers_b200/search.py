@@ -1,0 +1,150 @@
+"""Brute-force two-tower retrieval behind the reference's ``BaseSearch`` interface.
+
+Reference: ``BaseSearch`` ABC inference/search/base.py:8-54; ``TwoTowerSearch``
+inference/search/two_tower.py:15-155.  Same constructor, attributes (``document_embeddings``,
+``documents``), result schema (``{"document", "score"}`` sorted by descending score),
+exceptions (``ValueError`` before indexing) and pickle format; the work is done by
+  * index_documents: large-batch tokenise -> one H2D copy per batch -> document tower writing
+    into ONE preallocated contiguous [N,H] fp32 (or bf16) matrix (reference: batches of 32 +
+    torch.cat, two_tower.py:48-69);
+  * search: query tower -> fused scan + exact top-k kernel (reference: F.cosine_similarity over
+    a broadcast [1,N,H] + torch.topk, two_tower.py:98-105).
+With a process group the index is row-sharded across ranks and candidates are merged with an
+all-gather.
+"""
+from __future__ import annotations
+
+import pickle
+from abc import ABC, abstractmethod
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import ops, parallel
+
+
+class BaseSearch(ABC):
+    """inference/search/base.py:8-54"""
+
+    @abstractmethod
+    def index_documents(self, documents: List[str]) -> None:
+        ...
+
+    @abstractmethod
+    def search(self, query: str, top_k: int = 5) -> List[Dict[str, Union[str, float]]]:
+        ...
+
+    def save_index(self, filepath: str) -> None:
+        raise NotImplementedError("This search implementation does not support saving indices")
+
+    def load_index(self, filepath: str) -> None:
+        raise NotImplementedError("This search implementation does not support loading indices")
+
+
+class TwoTowerSearch(BaseSearch):
+    def __init__(self, model, tokenizer, device="cuda", index_dtype: str = "fp32", max_len: int = 64,
+                 encode_batch_size: int = 8192, cosine: bool = True, process_group=None, kernels=None):
+        if index_dtype not in ("fp32", "bf16"):
+            raise ValueError("index_dtype must be 'fp32' or 'bf16'")
+        self.model = model
+        self.tokenizer = tokenizer
+        self.device = device
+        self.index_dtype = index_dtype
+        self.max_len = max_len
+        self.encode_batch_size = encode_batch_size
+        self.cosine = cosine
+        self.group = process_group
+        self.kernels = kernels if kernels is not None else ops
+        self.document_embeddings: Optional[torch.Tensor] = None      # this rank's rows
+        self.documents: Optional[Sequence[str]] = None
+        self.row_offset = 0                                          # global id of local row 0
+        self.num_documents = 0
+        self.model = self.model.to(self.device)
+
+    # ------------------------------------------------------------------ indexing
+    def _encode(self, texts: Sequence[str], tower) -> torch.Tensor:
+        ids = self.tokenizer.encode_batch(texts, self.max_len, pin_memory=str(self.device).startswith("cuda"))
+        ids = ids.to(self.device, non_blocking=True)
+        with torch.no_grad():
+            return tower(ids)
+
+    def index_documents(self, documents: List[str]) -> None:
+        self.documents = documents
+        self.model.eval()
+        n = len(documents)
+        rank, ws = parallel.world(self.group) if self.group is not None or ws_initialized() else (0, 1)
+        lo, hi = parallel.shard_bounds(n, rank, ws)
+        self.row_offset, self.num_documents = lo, n
+        hidden = self.model.document_tower.hidden_dim
+        dtype = torch.float32 if self.index_dtype == "fp32" else torch.bfloat16
+        mat = torch.empty(hi - lo, hidden, dtype=dtype, device=self.device)
+        bs = self.encode_batch_size
+        for i in range(lo, hi, bs):
+            j = min(i + bs, hi)
+            emb = self._encode(documents[i:j], self.model.document_tower)
+            if dtype == torch.float32:
+                mat[i - lo:j - lo].copy_(emb)
+            else:
+                self.kernels.cast_bf16(emb, mat[i - lo:j - lo])
+        self.document_embeddings = mat
+
+    def set_index(self, embeddings: torch.Tensor, documents: Sequence[str], row_offset: int = 0,
+                  num_documents: Optional[int] = None) -> None:
+        """Install a pre-computed [N,H] matrix (fp32 or bf16, this rank's rows) -- used for large
+        synthetic indices where `documents` is a lazy sequence."""
+        if embeddings.dim() != 2 or not embeddings.is_contiguous():
+            raise ValueError("embeddings must be a contiguous [N,H] matrix")
+        self.document_embeddings = embeddings
+        self.documents = documents
+        self.row_offset = row_offset
+        self.num_documents = len(documents) if num_documents is None else num_documents
+        self.index_dtype = "bf16" if embeddings.dtype == torch.bfloat16 else "fp32"
+
+    # ------------------------------------------------------------------ search
+    def _topk(self, q_emb: torch.Tensor, k: int):
+        if self.group is not None or ws_initialized():
+            return parallel.sharded_topk(self.document_embeddings, q_emb, k, self.row_offset, self.kernels,
+                                         self.group, self.cosine)
+        return self.kernels.topk_scan(self.document_embeddings, q_emb, k, cosine=self.cosine,
+                                      id_offset=self.row_offset)
+
+    def search_batch(self, queries: Sequence[str], top_k: int = 5) -> List[List[Dict[str, Union[str, float]]]]:
+        if self.document_embeddings is None:
+            raise ValueError("No documents indexed. Call index_documents() first.")
+        self.model.eval()
+        k = min(top_k, self.num_documents)
+        q_emb = self._encode(list(queries), self.model.query_tower)
+        scores, ids = self._topk(q_emb, k)
+        scores, ids = scores.cpu().tolist(), ids.cpu().tolist()
+        return [[{"document": self.documents[i], "score": s} for s, i in zip(srow, irow)]
+                for srow, irow in zip(scores, ids)]
+
+    def search(self, query: str, top_k: int = 5) -> List[Dict[str, Union[str, float]]]:
+        return self.search_batch([query], top_k)[0]
+
+    # ------------------------------------------------------------------ persistence (two_tower.py:117-155)
+    def save_index(self, filepath: str) -> None:
+        if self.document_embeddings is None or self.documents is None:
+            raise ValueError("No index to save. Call index_documents() first.")
+        emb = self.document_embeddings
+        emb = emb.float().cpu().numpy() if torch.is_tensor(emb) else emb
+        with open(filepath, "wb") as f:
+            pickle.dump({"embeddings": emb, "documents": self.documents}, f)
+
+    def load_index(self, filepath: str) -> None:
+        with open(filepath, "rb") as f:
+            data = pickle.load(f)
+        emb = data["embeddings"]
+        emb = torch.tensor(emb, device=self.device) if isinstance(emb, np.ndarray) else emb.to(self.device)
+        emb = emb.contiguous()
+        if self.index_dtype == "bf16" and emb.dtype == torch.float32:
+            emb = self.kernels.cast_bf16(emb)
+        self.document_embeddings = emb
+        self.documents = data["documents"]
+        self.row_offset, self.num_documents = 0, len(self.documents)
+
+
+def ws_initialized() -> bool:
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1

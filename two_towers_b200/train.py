@@ -1,0 +1,268 @@
+"""Fused training step: forward + loss + backward + AdamW as one CUDA-graph replay.
+
+Reference: the body of ``train_epoch``'s batch loop, twotower/train.py:107-154 --
+``.to(device)`` x3 (:107-109), ``model(q, pos, neg)`` (:120), ``loss_fn`` (:133),
+``zero_grad / backward / step`` (:137-139), monitoring cosines + ``.item()`` x3 (:144-154).
+The reference launches ~100 eager ATen kernels per step and synchronises the host three
+times; here the same arithmetic is ~12 hand-written kernels captured in one CUDA graph,
+all parameters / gradients / Adam moments live in flat buffers (one optimizer launch), no
+gradient zeroing is needed (every gradient is overwritten by its single producer) and the
+monitoring values are by-products of the loss kernels read back asynchronously.
+
+Data parallel (one process per GPU): rows are sharded; in-batch negatives become GLOBAL
+negatives through an all-gather of the document embeddings (``parallel.global_inbatch_*``),
+and the flat gradient buffer is all-reduced once per step.
+
+The modules of ``two_towers_b200.encoders`` also work under plain ``loss.backward()`` +
+``torch.optim.AdamW`` exactly like the reference loop; this class is the fast path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops, parallel
+from ._lib import check
+from .encoders import AveragePoolingTower, MeanPoolingTower, TwoTower
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class FusedTrainer:
+    def __init__(self, model: TwoTower, loss: str = "in_batch", temperature: float = 0.1, margin: float = 0.2,
+                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
+                 batch_size: int = 256, max_len: int = 64, precision=None, process_group=None,
+                 global_negatives: bool = True, use_cuda_graph: bool = True, id_dtype=torch.int64):
+        if loss not in ("in_batch", "triplet"):
+            raise ValueError("FusedTrainer supports loss 'in_batch' or 'triplet'")
+        self.model = model
+        self.loss_name = loss
+        self.temperature, self.margin = float(temperature), float(margin)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
+        self.B, self.L = int(batch_size), int(max_len)
+        self.prec = ops.resolve_precision(precision)
+        self.group = process_group
+        self.rank, self.world = parallel.world(process_group)
+        self.global_negatives = bool(global_negatives) and self.world > 1 and loss == "in_batch"
+        self.use_graph = use_cuda_graph
+        self.lib = _lib.load()
+
+        qt, dt = model.query_tower, model.document_tower
+        self.tied = qt is dt
+        self.passes = 2 if loss == "in_batch" else 3
+        table = qt.embedding.embedding.weight
+        if not table.is_cuda:
+            raise RuntimeError("FusedTrainer: model must live on a CUDA (B200) device; there is no CPU fallback")
+        self.dev = table.device
+        self.table = table
+        self.V, self.E = table.shape
+        self.H = qt.hidden_dim
+        self.train_table = bool(table.requires_grad)
+        B, L, P = self.B, self.L, self.passes
+        R = P * B
+        # row groups: (tower, first row, row count)
+        self.groups = [(qt, 0, R)] if self.tied else [(qt, 0, B), (dt, B, (P - 1) * B)]
+
+        # ---- flat parameter / gradient / moment buffers --------------------------------------
+        params = [p for p in model.parameters() if p.requires_grad]
+        pad = lambda n: (n + 63) // 64 * 64          # every view starts 256-byte aligned
+        total = sum(pad(p.numel()) for p in params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.step_count = torch.zeros((), dtype=torch.int64, device=self.dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                # keep 16-byte alignment of every view (vector loads in the kernels)
+                self.flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + n].view(p.shape)
+                p.grad = self.flat_grad[off:off + n].view(p.shape)
+                off += pad(n)
+        self.n_params = total
+
+        # ---- static activations -------------------------------------------------------------
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.ids = torch.zeros(R, L, dtype=id_dtype, device=self.dev)
+        self.pooled = torch.empty(R, self.E, **f32)
+        self.inv_len = torch.empty(R, **f32)
+        self.y = torch.empty(R, self.H, **f32)
+        self.dy = torch.empty(R, self.H, **f32)
+        self.dpooled = torch.empty(R, self.E, **f32)
+        self.saved: List[Dict[str, torch.Tensor]] = []
+        for tower, r0, nr in self.groups:
+            if isinstance(tower, MeanPoolingTower):
+                self.saved.append(dict(h1=torch.empty(nr, self.H, **f32), z=torch.empty(nr, self.H, **f32)))
+            elif isinstance(tower, AveragePoolingTower):
+                if tower.has_projection:
+                    self.saved.append(dict(a=torch.empty(nr, self.H, **f32), stats=torch.empty(nr, 2, **f32),
+                                           z=torch.empty(nr, self.H, **f32)))
+                else:
+                    self.saved.append({})
+            else:
+                raise TypeError(f"FusedTrainer: unsupported tower {type(tower).__name__}")
+        bf = self.prec == _lib.TT_PREC_BF16
+        self.pooled_bf16 = torch.empty(R, self.E, dtype=torch.bfloat16, device=self.dev) if bf else None
+        self.y_bf16 = torch.empty(R, self.H, dtype=torch.bfloat16, device=self.dev) if bf else None
+        self.loss = torch.zeros((), **f32)
+        self.lse = torch.empty(B, **f32)
+        self.pos_mean = torch.zeros((), **f32)
+        self.neg_mean = torch.zeros((), **f32)
+        self.sims = torch.empty(3 * B, **f32)
+        self.grad_scale = torch.full((), 1.0 / self.world, **f32)
+        lib = self.lib
+        nb = max(lib.tt_mlp_workspace(R, self.E, self.H, self.prec), lib.tt_proj_ln_workspace(R, self.E, self.H),
+                 lib.tt_embed_pool_bwd_workspace(R, L, self.V, self.E),
+                 lib.tt_inbatch_ce_workspace(B * self.world, B * self.world, self.H, self.prec))
+        self.ws = torch.empty(int(nb), dtype=torch.uint8, device=self.dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._pinned_ids = None
+        self.steps_done = 0
+
+    # ---------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _tower_fwd(self, gi: int):
+        tower, r0, nr = self.groups[gi]
+        lib, s, sv = self.lib, self._stream(), self.saved[gi]
+        x, y = self.pooled[r0:r0 + nr], self.y[r0:r0 + nr]
+        yb = self.y_bf16[r0:r0 + nr] if self.y_bf16 is not None else None
+        if isinstance(tower, MeanPoolingTower):
+            l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
+            check(lib.tt_mlp_fwd(_p(x), _p(l1.weight), _p(l1.bias), _p(l2.weight), _p(l2.bias), nr, self.E, self.H,
+                                 _p(sv["h1"]), _p(sv["z"]), _p(y), _p(yb), self.prec, _p(self.ws), self.ws.numel(), s),
+                  "tt_mlp_fwd")
+        elif tower.has_projection:
+            lin, ln = tower.projection[0], tower.projection[2]
+            check(lib.tt_proj_ln_fwd(_p(x), _p(lin.weight), _p(lin.bias), _p(ln.weight), _p(ln.bias), nr, self.E,
+                                     self.H, 1, 0.0, 0, 0, _p(sv["a"]), _p(sv["stats"]), _p(sv["z"]), _p(y),
+                                     _p(self.ws), self.ws.numel(), s), "tt_proj_ln_fwd")
+        else:
+            check(lib.tt_proj_ln_fwd(_p(x), None, None, None, None, nr, self.E, self.H, 0, 0.0, 0, 0, None, None,
+                                     None, _p(y), None, 0, s), "tt_proj_ln_fwd")
+
+    def _tower_bwd(self, gi: int):
+        tower, r0, nr = self.groups[gi]
+        lib, s, sv = self.lib, self._stream(), self.saved[gi]
+        x, dy = self.pooled[r0:r0 + nr], self.dy[r0:r0 + nr]
+        dx = self.dpooled[r0:r0 + nr] if self.train_table else None
+        if isinstance(tower, MeanPoolingTower):
+            l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
+            check(lib.tt_mlp_bwd(_p(dy), _p(x), _p(l1.weight), _p(l2.weight), _p(sv["h1"]), _p(sv["z"]), nr, self.E,
+                                 self.H, _p(dx), _p(l1.weight.grad), _p(l1.bias.grad), _p(l2.weight.grad),
+                                 _p(l2.bias.grad), self.prec, _p(self.ws), self.ws.numel(), s), "tt_mlp_bwd")
+        elif tower.has_projection:
+            lin, ln = tower.projection[0], tower.projection[2]
+            check(lib.tt_proj_ln_bwd(_p(dy), _p(x), _p(lin.weight), _p(ln.weight), _p(sv["a"]), _p(sv["stats"]),
+                                     _p(sv["z"]), nr, self.E, self.H, 1, 0.0, 0, 0, _p(dx), _p(lin.weight.grad),
+                                     _p(lin.bias.grad), _p(ln.weight.grad), _p(ln.bias.grad), _p(self.ws),
+                                     self.ws.numel(), s), "tt_proj_ln_bwd")
+        elif dx is not None:
+            check(lib.tt_proj_ln_bwd(_p(dy), _p(x), None, None, None, None, None, nr, self.E, self.H, 0, 0.0, 0, 0,
+                                     _p(dx), None, None, None, None, None, 0, s), "tt_proj_ln_bwd")
+
+    def _step_impl(self):
+        lib, B, H, P = self.lib, self.B, self.H, self.passes
+        R = P * B
+        idb = 8 if self.ids.dtype == torch.int64 else 4
+        s = self._stream()
+        check(lib.tt_embed_pool_fwd(_p(self.ids), idb, _p(self.table), R, self.L, self.V, self.E, _p(self.pooled),
+                                    _p(self.inv_len), _p(self.pooled_bf16), s), "tt_embed_pool_fwd")
+        for gi in range(len(self.groups)):
+            self._tower_fwd(gi)
+        q, d = self.y[:B], self.y[B:2 * B]
+        dq, dd = self.dy[:B], self.dy[B:2 * B]
+        if self.loss_name == "in_batch":
+            inv_t = 1.0 / self.temperature
+            if self.global_negatives:
+                loss, lse, d_glob = parallel.global_inbatch_fwd(q, d, self.temperature, ops, self.group, self.prec)
+                self.loss.copy_(loss)
+                g_dq, g_dd = parallel.global_inbatch_bwd(q, d, d_glob, lse, self.temperature, ops, self.group, self.prec)
+                dq.copy_(g_dq)
+                dd.copy_(g_dd)
+            else:
+                scale = 1.0 / (B * self.world)
+                qb = self.y_bf16[:B] if self.y_bf16 is not None else None
+                db = self.y_bf16[B:2 * B] if self.y_bf16 is not None else None
+                check(lib.tt_inbatch_ce_fwd(_p(q), _p(d), _p(qb), _p(db), B, B, H, inv_t, 0, scale, _p(self.loss),
+                                            _p(self.lse), _p(self.pos_mean), self.prec, _p(self.ws), self.ws.numel(), s),
+                      "tt_inbatch_ce_fwd")
+                check(lib.tt_inbatch_ce_bwd(_p(q), _p(d), _p(qb), _p(db), _p(self.lse), B, B, H, inv_t, 0, scale, None,
+                                            _p(dq), _p(dd), self.prec, _p(self.ws), self.ws.numel(), s),
+                      "tt_inbatch_ce_bwd")
+        else:
+            n, dn = self.y[2 * B:3 * B], self.dy[2 * B:3 * B]
+            check(lib.tt_triplet_fwd(_p(q), _p(d), _p(n), B, H, self.margin, _p(self.loss), _p(self.sims),
+                                     _p(self.pos_mean), _p(self.neg_mean), s), "tt_triplet_fwd")
+            check(lib.tt_triplet_bwd(_p(q), _p(d), _p(n), _p(self.sims), B, H, self.margin,
+                                     _p(self.grad_scale) if self.world > 1 else None, _p(dq), _p(dd), _p(dn), s),
+                  "tt_triplet_bwd")
+        for gi in range(len(self.groups)):
+            self._tower_bwd(gi)
+        if self.train_table:
+            check(lib.tt_embed_pool_bwd(_p(self.ids), idb, _p(self.inv_len), _p(self.dpooled), R, self.L, self.V,
+                                        self.E, _p(self.table.grad), _p(self.ws), self.ws.numel(), s),
+                  "tt_embed_pool_bwd")
+        if self.world > 1:
+            parallel.allreduce_sum_(self.flat_grad, self.group)
+        check(lib.tt_adamw_step(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                _p(self.step_count), None, s), "tt_adamw_step")
+
+    # ---------------------------------------------------------------------------------------
+    def load_batch(self, q_ids: torch.Tensor, d_ids: torch.Tensor, n_ids: Optional[torch.Tensor] = None):
+        """Copy a batch of token ids (host or device, [B,L]) into the static input buffer."""
+        B = self.B
+        parts = [q_ids, d_ids] + ([n_ids] if self.passes == 3 else [])
+        if self.passes == 3 and n_ids is None:
+            raise ValueError("triplet loss needs negative ids")
+        for i, t in enumerate(parts):
+            if tuple(t.shape) != (B, self.L):
+                raise ValueError(f"expected ids of shape {(B, self.L)}, got {tuple(t.shape)}")
+            self.ids[i * B:(i + 1) * B].copy_(t, non_blocking=True)
+
+    def run(self) -> torch.Tensor:
+        """One optimizer step on the batch currently in the static buffer; returns the loss (device scalar)."""
+        if not self.use_graph:
+            self._step_impl()
+        elif self.graph is None:
+            # warm-up outside capture (module loading, workspace sizing, NCCL communicators) ...
+            st = {k: v.clone() for k, v in (("flat", self.flat), ("m", self.exp_avg), ("v", self.exp_avg_sq),
+                                            ("t", self.step_count))}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._step_impl()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            # ... restore the state the warm-up step changed, then capture and replay once
+            self.flat.copy_(st["flat"]); self.exp_avg.copy_(st["m"]); self.exp_avg_sq.copy_(st["v"])
+            self.step_count.copy_(st["t"])
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_impl()
+            self.graph = g
+            g.replay()
+        else:
+            self.graph.replay()
+        self.steps_done += 1
+        return self.loss
+
+    def step(self, q_ids, d_ids, n_ids=None) -> torch.Tensor:
+        self.load_batch(q_ids, d_ids, n_ids)
+        return self.run()
+
+    def kernels_per_step(self) -> int:
+        """Launches of libtt_b200 kernels in one step (measured on an eager step)."""
+        before = _lib.launch_count()
+        self._step_impl()
+        n = _lib.launch_count() - before
+        return n

@@ -172,12 +172,13 @@ int tt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /* ---- optimizer: torch.optim.AdamW(model.parameters(), lr), train.py:359 ------
  * One fused AdamW step over a flat fp32 parameter buffer (ATen _single_tensor_adamw
- * semantics, amsgrad off).  step_count: device int64 holding the number of steps already
+ * semantics and operation order, amsgrad off; hyper-parameters are doubles, rounded to fp32
+ * exactly where torch rounds them).  step_count: device int64 holding the number of steps already
  * taken; the kernel uses step_count+1 for bias correction and tt_adamw_step increments it
  * (graph-capturable: no host state).  param_bf16 (nullable): refreshed bf16 shadow.
  */
 int tt_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                  int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
                   int64_t* step_count, void* param_bf16, void* stream);
 
 #ifdef __cplusplus

@@ -396,7 +396,7 @@ def test_adamw_matches_oracle():
         g = rng.standard_normal(n).astype(np.float32)
         tt.ops.adamw_step(tp, cu(g), tm, tv, step)
         p, m, v = O.adamw_step(p.astype(np.float64), g.astype(np.float64), m.astype(np.float64), v.astype(np.float64), t)
-        close(tp, p, rtol=2e-6); close(tm, m, rtol=2e-6); close(tv, v, rtol=2e-6)
+        close(tp, p, rtol=5e-6); close(tm, m, rtol=5e-6); close(tv, v, rtol=5e-6)
         p, m, v = p.astype(np.float32), m.astype(np.float32), v.astype(np.float32)
     assert step.item() == 5
 

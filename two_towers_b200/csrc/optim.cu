@@ -11,26 +11,30 @@ namespace tt {
 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             int64_t n, float lr, float beta1, float beta2, float eps, float wd,
+             int64_t n, double lr, double beta1, double beta2, double eps, double wd,
              const int64_t* __restrict__ step_count, __nv_bfloat16* __restrict__ p_bf16) {
-  __shared__ float s_step_size, s_inv_sqrt_bc2;
+  // scalars are formed in double (as Python does in torch.optim) and rounded to fp32 once
+  __shared__ float s_neg_step_size, s_sqrt_bc2;
   if (threadIdx.x == 0) {
     const double t = (double)(*step_count + 1);
-    const double bc1 = 1.0 - pow((double)beta1, t);
-    const double bc2 = 1.0 - pow((double)beta2, t);
-    s_step_size = (float)((double)lr / bc1);
-    s_inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    const double bc1 = 1.0 - pow(beta1, t);
+    const double bc2 = 1.0 - pow(beta2, t);
+    s_neg_step_size = (float)(-(lr / bc1));
+    s_sqrt_bc2 = (float)sqrt(bc2);
   }
   __syncthreads();
-  const float step_size = s_step_size, inv_sqrt_bc2 = s_inv_sqrt_bc2;
-  const float decay = 1.0f - lr * wd;
+  const float neg_step_size = s_neg_step_size, sqrt_bc2 = s_sqrt_bc2;
+  const float decay = (float)(1.0 - lr * wd);
+  const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), epsf = (float)eps;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i];
-    float pi = p[i] * decay;
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    pi -= step_size * (mi / denom);
+    float pi = p[i] * decay;                                   // param.mul_(1 - lr*wd)
+    float mi = m[i];
+    mi = (w1 < 0.5f) ? mi + w1 * (gi - mi) : gi - (gi - mi) * (1.0f - w1);   // exp_avg.lerp_(grad, 1-beta1)
+    float vi = v[i] * b2;                                      // exp_avg_sq.mul_(beta2)
+    vi = vi + (w2 * gi) * gi;                                  //   .addcmul_(grad, grad, value=1-beta2)
+    const float denom = sqrtf(vi) / sqrt_bc2 + epsf;           // sqrt / bias_correction2_sqrt + eps
+    pi = pi + neg_step_size * (mi / denom);                    // addcdiv_(exp_avg, denom, value=-step_size)
     p[i] = pi; m[i] = mi; v[i] = vi;
     if (p_bf16) p_bf16[i] = __float2bfloat16(pi);
   }
@@ -41,7 +45,7 @@ __global__ void step_inc_kernel(int64_t* step_count) { *step_count += 1; }
 }  // namespace tt
 
 extern "C" int tt_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                             float lr, float beta1, float beta2, float eps, float weight_decay,
+                             double lr, double beta1, double beta2, double eps, double weight_decay,
                              int64_t* step_count, void* param_bf16, void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step_count && n >= 0, "adamw_step: bad arguments");

@@ -125,8 +125,7 @@ __device__ __forceinline__ float group8_sum(float v) {
   return v;
 }
 
-constexpr int kScanThreads = 512;
-constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanThreads = 512;            // upper bound; large k launches fewer warps so the buffers fit
 
 // CPL = 16-byte chunks per lane (row = 8 lanes x CPL chunks), NQ queries per pass.
 template <int CPL, int NQ, bool BF16, bool COSINE>
@@ -139,6 +138,7 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   u64* sm = reinterpret_cast<u64*>(smem_raw);              // [NQ][warps][cap]
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kScanWarps = blockDim.x >> 5;
   const int sub = lane & 7, grp = lane >> 3;
   const int chunks_per_row = H / EPC;
 
@@ -208,9 +208,9 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
     tk[n].prune(lane);
     __syncthreads();
     u64* region = sm + (size_t)n * kScanWarps * cap;
-    bitonic_desc<true>(region, kScanWarps * cap, threadIdx.x, kScanThreads);
+    bitonic_desc<true>(region, kScanWarps * cap, threadIdx.x, blockDim.x);
     u64* out = cand + ((size_t)(q0 + n) * gridDim.x + blockIdx.x) * k;
-    for (int i = threadIdx.x; i < k; i += kScanThreads) out[i] = region[i];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = region[i];
     __syncthreads();
   }
 }
@@ -223,6 +223,7 @@ scan_topk_generic_kernel(const void* __restrict__ index, const float* __restrict
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* sm = reinterpret_cast<u64*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kScanWarps = blockDim.x >> 5;
   const float* qp = queries + (int64_t)q0 * H;
   float qinv = 1.0f;
   if (COSINE) {
@@ -246,9 +247,9 @@ scan_topk_generic_kernel(const void* __restrict__ index, const float* __restrict
   }
   tk.prune(lane);
   __syncthreads();
-  bitonic_desc<true>(sm, kScanWarps * cap, threadIdx.x, kScanThreads);
+  bitonic_desc<true>(sm, kScanWarps * cap, threadIdx.x, blockDim.x);
   u64* out = cand + ((size_t)q0 * gridDim.x + blockIdx.x) * k;
-  for (int i = threadIdx.x; i < k; i += kScanThreads) out[i] = sm[i];
+  for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = sm[i];
 }
 
 // ---- merge: one block per query; radix-select the k-th largest key, sort the survivors --------
@@ -330,16 +331,19 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
     dst[i] = __float2bfloat16(src[i]);
 }
 
-struct ScanPlan { int cap; int grid; size_t smem_per_q; size_t cand_bytes; size_t total; };
+struct ScanPlan { int cap; int grid; int warps; size_t smem_per_q; size_t cand_bytes; size_t total; };
 static ScanPlan plan_scan(int64_t N, int nq, int k) {
   ScanPlan p{};
   int cap = 256;
   while (cap < 2 * k) cap <<= 1;
   p.cap = cap;
+  int warps = kScanThreads / 32;
+  while (warps > 1 && (size_t)warps * cap * sizeof(u64) > 160 * 1024) warps >>= 1;   // k=1024 -> 8 warps
+  p.warps = warps;
   int64_t quads = (N + 3) / 4;
-  int64_t g = ceil_div(quads, kScanWarps);
+  int64_t g = ceil_div(quads, warps);
   p.grid = (int)(g < kNumSMs ? (g < 1 ? 1 : g) : kNumSMs);
-  p.smem_per_q = (size_t)kScanWarps * cap * sizeof(u64);
+  p.smem_per_q = (size_t)warps * cap * sizeof(u64);
   p.cand_bytes = align_up((size_t)nq * p.grid * k * sizeof(u64));
   p.total = p.cand_bytes + 256;
   return p;
@@ -355,14 +359,14 @@ static int launch_scan(const void* index, const float* queries, int64_t N, int H
   if (kTwoFits && 2 * plan.smem_per_q <= 200 * 1024) {
     TT_CUDA(cudaFuncSetAttribute(scan_topk_kernel<CPL, 2, BF16, COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * plan.smem_per_q)));
     for (; q + 2 <= nq; q += 2) {
-      scan_topk_kernel<CPL, 2, BF16, COS><<<plan.grid, kScanThreads, 2 * plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand);
+      scan_topk_kernel<CPL, 2, BF16, COS><<<plan.grid, plan.warps * 32, 2 * plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand);
       TT_LAUNCH_CHECK("scan_topk_kernel");
     }
   }
   if (q < nq) {
     TT_CUDA(cudaFuncSetAttribute(scan_topk_kernel<CPL, 1, BF16, COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_q));
     for (; q < nq; ++q) {
-      scan_topk_kernel<CPL, 1, BF16, COS><<<plan.grid, kScanThreads, plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand);
+      scan_topk_kernel<CPL, 1, BF16, COS><<<plan.grid, plan.warps * 32, plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand);
       TT_LAUNCH_CHECK("scan_topk_kernel");
     }
   }
@@ -386,7 +390,7 @@ static int dispatch_scan(const void* index, const float* queries, int64_t N, int
   }
   TT_CUDA(cudaFuncSetAttribute(scan_topk_generic_kernel<BF16, COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_q));
   for (int q = 0; q < nq; ++q) {
-    scan_topk_generic_kernel<BF16, COS><<<plan.grid, kScanThreads, plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand);
+    scan_topk_generic_kernel<BF16, COS><<<plan.grid, plan.warps * 32, plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand);
     TT_LAUNCH_CHECK("scan_topk_generic_kernel");
   }
   return TT_OK;

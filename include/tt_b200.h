@@ -181,6 +181,14 @@ int tt_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
                   int64_t* step_count, void* param_bf16, void* stream);
 
+/* ---- self-test hook -------------------------------------------------------------------------
+ * C[M,N] (fp32) = A * B on the tcgen05 tensor cores; used by the GPU tests to pin the UMMA / TMA
+ * descriptor encodings for both operand majors.  a_mn_major: A stored [K,M] (else [M,K]);
+ * b_mn_major: B stored [K,N] (else [N,K]); bf16 operands.  splits > 1 needs partial[splits*M*N].
+ */
+int tt_selftest_tc_gemm(const void* a_bf16, int a_mn_major, const void* b_bf16, int b_mn_major,
+                        int M, int N, int K, float* c, int splits, float* partial, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

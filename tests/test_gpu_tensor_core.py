@@ -1,0 +1,151 @@
+"""GPU tests of the TT_PREC_BF16 path: hand-written tcgen05 / TMEM / TMA kernels.
+
+Tolerance: BASELINE.json north_star -- bf16 mode rel 2e-2 (checked as max|a-b| <= 2e-2 * max|b|).
+The self-test GEMM pins the UMMA shared-memory descriptors (both operand majors), the TMA
+tensor maps / 128B swizzle, the instruction descriptor and the TMEM load mapping against an
+fp64 matmul of the same bf16-rounded operands (tolerance 1e-4: only fp32 accumulation order).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import two_tower_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF16_RTOL = 2e-2
+
+
+def close(a, b, rtol, what=""):
+    a = a.detach().float().cpu().numpy().astype(np.float64) if torch.is_tensor(a) else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(float(np.abs(b).max()), 1e-30)
+    err = float(np.abs(a - b).max())
+    assert np.isfinite(a).all(), f"{what}: non-finite output"
+    assert err <= rtol * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.2e})"
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,splits", [(128, 64, 64, 1), (128, 128, 256, 1), (256, 256, 64, 1), (300, 200, 136, 1),
+                                          (8192, 256, 64, 1), (256, 256, 8192, 8), (256, 64, 8192, 16), (77, 40, 72, 1)])
+def test_tc_gemm_selftest(a_mn, b_mn, M, N, K, splits):
+    import two_towers_b200 as tt
+    if M % 8 or N % 8 or K % 8:
+        # TMA needs 16-byte row pitch: MN-major operands need M/N % 8 == 0, K-major need K % 8 == 0
+        if (a_mn and M % 8) or (b_mn and N % 8) or ((not a_mn or not b_mn) and K % 8):
+            pytest.skip("row pitch not 16-byte aligned for this major")
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    B = torch.randn(N, K, device=DEV, generator=g).bfloat16()
+    ref = (A.double() @ B.double().T).cpu().numpy()
+    a_store = A.t().contiguous() if a_mn else A.contiguous()          # [K,M] or [M,K]
+    b_store = B.t().contiguous() if b_mn else B.contiguous()          # [K,N] or [N,K]
+    C = tt.ops.selftest_tc_gemm(a_store, bool(a_mn), b_store, bool(b_mn), M, N, K, splits)
+    close(C, ref, 1e-4, f"gemm a_mn={a_mn} b_mn={b_mn}")
+
+
+def _mlp_case(R, E, H, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((R, E)).astype(np.float32) * 0.3
+    w1 = (rng.standard_normal((H, E)) / np.sqrt(E)).astype(np.float32)
+    b1 = (rng.standard_normal(H) * 0.1).astype(np.float32)
+    w2 = (rng.standard_normal((H, H)) / np.sqrt(H)).astype(np.float32)
+    b2 = (rng.standard_normal(H) * 0.1).astype(np.float32)
+    dy = rng.standard_normal((R, H)).astype(np.float32)
+    return x, w1, b1, w2, b2, dy
+
+
+@pytest.mark.parametrize("R,E,H", [(128, 64, 256), (8192, 64, 256), (300, 16, 32), (1000, 304, 256), (130, 64, 128)])
+def test_mlp_bf16_vs_oracle(R, E, H):
+    import two_towers_b200 as tt
+    x, w1, b1, w2, b2, dy = _mlp_case(R, E, H, R + E + H)
+    t = lambda a: torch.tensor(a, device=DEV)
+    y, h1, z, yb = tt.ops.mlp_fwd(t(x), t(w1), t(b1), t(w2), t(b2), precision="bf16", want_bf16=True)
+    f = np.float64
+    a1 = x.astype(f) @ w1.astype(f).T + b1
+    rh1 = np.maximum(a1, 0)
+    rz = rh1 @ w2.astype(f).T + b2
+    ry = O.normalize(rz)
+    close(h1, rh1, BF16_RTOL, "h1"); close(z, rz, BF16_RTOL, "z"); close(y, ry, BF16_RTOL, "y"); close(yb, ry, BF16_RTOL, "y_bf16")
+    dx, dw1, db1, dw2, db2 = tt.ops.mlp_bwd(t(dy), t(x), t(w1), t(w2), h1, z, True, precision="bf16")
+    dz = O.normalize_bwd(dy.astype(f), rz)
+    close(dw2, dz.T @ rh1, BF16_RTOL, "dw2"); close(db2, dz.sum(0), BF16_RTOL, "db2")
+    da1 = (dz @ w2.astype(f)) * (a1 > 0)
+    close(dw1, da1.T @ x.astype(f), BF16_RTOL, "dw1"); close(db1, da1.sum(0), BF16_RTOL, "db1")
+    close(dx, da1 @ w1.astype(f), BF16_RTOL, "dx")
+    # determinism
+    dx2, dw1b, _, dw2b, _ = tt.ops.mlp_bwd(t(dy), t(x), t(w1), t(w2), h1, z, True, precision="bf16")
+    assert torch.equal(dx, dx2) and torch.equal(dw1, dw1b) and torch.equal(dw2, dw2b)
+
+
+@pytest.mark.parametrize("Bq,Bd,H,off,temp", [(128, 128, 256, 0, 0.1), (64, 64, 64, 0, 0.1), (100, 257, 64, 57, 0.05),
+                                              (257, 300, 128, 3, 1.0), (1024, 1024, 256, 0, 0.1), (4096, 4096, 256, 0, 0.1),
+                                              (96, 768, 256, 96 * 3, 0.1), (200, 200, 192, 0, 0.1), (50, 50, 24, 0, 0.1)])
+def test_inbatch_ce_bf16_vs_oracle(Bq, Bd, H, off, temp):
+    import two_towers_b200 as tt
+    rng = np.random.default_rng(Bq + Bd + H)
+    q = O.normalize(rng.standard_normal((Bq, H))).astype(np.float32)
+    d = O.normalize(rng.standard_normal((Bd, H))).astype(np.float32)
+    # make positives meaningful: d_pos correlated with q
+    idx = np.arange(Bq) + off
+    d[idx] = O.normalize(d[idx] + 2.0 * q).astype(np.float32)
+    tq, td = torch.tensor(q, device=DEV), torch.tensor(d, device=DEV)
+    loss, lse, pm = tt.ops.inbatch_ce_fwd(tq, td, temp, off, precision="bf16", want_pos_mean=True)
+    q64, d64 = q.astype(np.float64), d.astype(np.float64)
+    rl, rlse = O.in_batch_loss(q64, d64, temp, off)
+    # logits carry bf16 operand rounding (~4e-3 abs on |S|<=1) amplified by 1/temp
+    assert abs(loss.item() - rl) <= BF16_RTOL * max(abs(rl), 1.0), (loss.item(), rl)
+    assert np.abs(lse.cpu().numpy() - rlse).max() <= BF16_RTOL * max(np.abs(rlse).max(), 1.0)
+    gout = torch.tensor(0.5, device=DEV)
+    dq, dd = tt.ops.inbatch_ce_bwd(tq, td, lse, temp, off, grad_out=gout, precision="bf16")
+    rdq, rdd = O.in_batch_loss_bwd(q64, d64, temp, off, grad=0.5)
+    close(dq, rdq, 3e-2, "dq"); close(dd, rdd, 3e-2, "dd")
+    dq2, dd2 = tt.ops.inbatch_ce_bwd(tq, td, lse, temp, off, grad_out=gout, precision="bf16")
+    assert torch.equal(dq, dq2) and torch.equal(dd, dd2)
+
+
+def test_inbatch_bf16_full_size_known_answers():
+    import two_towers_b200 as tt
+    B, H = 4096, 256
+    q = torch.nn.functional.normalize(torch.randn(B, H, device=DEV), dim=-1)
+    v = torch.nn.functional.normalize(torch.randn(1, H, device=DEV), dim=-1)
+    d_same = v.expand(B, H).contiguous()
+    loss, lse, _ = tt.ops.inbatch_ce_fwd(q, d_same, 0.1, precision="bf16")
+    assert abs(loss.item() - np.log(B)) < 1e-3                       # uniform softmax, exact up to rounding
+    dq, dd = tt.ops.inbatch_ce_bwd(q, d_same, lse, 0.1, precision="bf16")
+    assert dq.abs().max().item() < 1e-5
+    d = torch.nn.functional.normalize(torch.randn(B, H, device=DEV), dim=-1)
+    full, lse_full, _ = tt.ops.inbatch_ce_fwd(q, d, 0.1, precision="bf16")
+    ref, _, _ = tt.ops.inbatch_ce_fwd(q, d, 0.1, precision="fp32")
+    assert abs(full.item() - ref.item()) < BF16_RTOL * ref.item()
+    parts = [tt.ops.inbatch_ce_fwd(q[r * 1024:(r + 1) * 1024].contiguous(), d, 0.1, label_offset=r * 1024,
+                                   precision="bf16")[0].item() for r in range(4)]
+    assert abs(np.mean(parts) - full.item()) < 1e-4 * abs(full.item())
+    dq, dd = tt.ops.inbatch_ce_bwd(q, d, lse_full, 0.1, precision="bf16")
+    rq, rd = tt.ops.inbatch_ce_bwd(q, d, tt.ops.inbatch_ce_fwd(q, d, 0.1, precision="fp32")[1], 0.1, precision="fp32")
+    close(dq, rq.cpu().numpy(), 3e-2, "dq vs fp32 kernel"); close(dd, rd.cpu().numpy(), 3e-2, "dd vs fp32 kernel")
+
+
+def test_fused_trainer_bf16_tracks_fp32():
+    """Same batch, same init: one bf16 tensor-core step stays within 2e-2 of the fp32 step."""
+    import copy
+    import two_towers_b200 as tt
+    torch.manual_seed(0)
+    emb = tt.embeddings.build("lookup", 128, embedding_dim=64)
+    m32 = tt.build_two_tower("mean", emb, hidden_dim=256, tied_weights=True).to(DEV)
+    m16 = copy.deepcopy(m32)
+    g = torch.Generator().manual_seed(3)
+    B, L = 1024, 64
+    q = torch.randint(0, 128, (B, L), generator=g); d = torch.randint(0, 128, (B, L), generator=g)
+    t32 = tt.FusedTrainer(m32, loss="in_batch", batch_size=B, max_len=L, precision="fp32", use_cuda_graph=False)
+    t16 = tt.FusedTrainer(m16, loss="in_batch", batch_size=B, max_len=L, precision="bf16", use_cuda_graph=True)
+    l32, l16 = t32.step(q, d).item(), t16.step(q, d).item()
+    assert abs(l32 - l16) <= BF16_RTOL * abs(l32)
+    close(t16.flat_grad, t32.flat_grad.cpu().numpy(), 5e-2, "flat grads")
+    first = l16
+    for _ in range(30):
+        last = t16.step(q, d).item()
+    assert np.isfinite(last) and last < first

@@ -294,6 +294,12 @@ __global__ void split_sum_kernel(const float* __restrict__ partial, int nsplit, 
   }
 }
 
+int split_sum(const float* partial, int nsplit, int64_t n, float* out, cudaStream_t s) {
+  split_sum_kernel<<<(unsigned)(ceil_div(n, 256) < 8 * kNumSMs ? ceil_div(n, 256) : 8 * kNumSMs), 256, 0, s>>>(partial, nsplit, n, out);
+  TT_LAUNCH_CHECK("split_sum_kernel");
+  return TT_OK;
+}
+
 static int pick_split(int64_t Bx, int64_t By) {
   const int64_t xt = ceil_div(Bx, CE_T), yt = ceil_div(By, CE_T);
   int64_t s = ceil_div(2 * kNumSMs, xt);
@@ -335,12 +341,52 @@ static int launch_bwd(const float* X, const float* Y, const float* lse, int64_t 
   float* dst = nsplit > 1 ? partial : out;
   ce_bwd_kernel<VEC, COL><<<grid, 256, kCeBwdSmem, s>>>(X, Y, lse, Bx, By, H, inv_temp, off, per, grad_out, coef, dst);
   TT_LAUNCH_CHECK("ce_bwd_kernel");
-  if (nsplit > 1) {
-    const int64_t n = Bx * H;
-    split_sum_kernel<<<(unsigned)(ceil_div(n, 256) < 8 * kNumSMs ? ceil_div(n, 256) : 8 * kNumSMs), 256, 0, s>>>(partial, nsplit, n, out);
-    TT_LAUNCH_CHECK("split_sum_kernel");
-  }
+  if (nsplit > 1) return split_sum(partial, nsplit, Bx * H, out, s);
   return TT_OK;
+}
+
+size_t inbatch_ce_fp32_workspace(int64_t Bq, int64_t Bd, int H) { return plan_ce(Bq, Bd, H).total; }
+
+int inbatch_ce_fwd_fp32(const float* q, const float* d, int64_t Bq, int64_t Bd, int H, float inv_temperature,
+                        int64_t label_offset, float loss_scale, float* loss, float* lse, float* pos_mean,
+                        void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  const CePlan plan = plan_ce(Bq, Bd, H);
+  if (workspace == nullptr || workspace_bytes < plan.total) { set_error("inbatch_ce_fwd: workspace too small"); return TT_ERR_WORKSPACE; }
+  Workspace w(workspace, workspace_bytes);
+  float* part_ml = w.take<float>(plan.ml_bytes / sizeof(float));
+  float* pos = w.take<float>(Bq);
+  const int yt = (int)ceil_div(Bd, CE_T);
+  const int per = (int)ceil_div(yt, plan.ns_f);
+  dim3 grid((unsigned)ceil_div(Bq, CE_T), (unsigned)plan.ns_f);
+  const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+  if (vec) ce_fwd_kernel<true><<<grid, 256, 0, s>>>(q, d, Bq, Bd, H, inv_temperature, label_offset, per, part_ml, pos);
+  else     ce_fwd_kernel<false><<<grid, 256, 0, s>>>(q, d, Bq, Bd, H, inv_temperature, label_offset, per, part_ml, pos);
+  TT_LAUNCH_CHECK("ce_fwd_kernel");
+  return inbatch_finalize(part_ml, pos, plan.ns_f, Bq, inv_temperature, loss_scale, lse, loss, pos_mean, nullptr, s);
+}
+
+int inbatch_ce_bwd_fp32(const float* q, const float* d, const float* lse, int64_t Bq, int64_t Bd, int H,
+                        float inv_temperature, int64_t label_offset, float loss_scale, const float* grad_out,
+                        float* dq, float* dd, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  const CePlan plan = plan_ce(Bq, Bd, H);
+  if (workspace == nullptr || workspace_bytes < plan.total) { set_error("inbatch_ce_bwd: workspace too small"); return TT_ERR_WORKSPACE; }
+  Workspace w(workspace, workspace_bytes);
+  (void)w.take<float>(plan.ml_bytes / sizeof(float));
+  (void)w.take<float>(Bq);
+  float* partial = plan.bwd_bytes ? w.take<float>(plan.bwd_bytes / sizeof(float)) : nullptr;
+  const float coef = loss_scale * inv_temperature;
+  const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+  int rc = TT_OK;
+  if (dq) {
+    rc = vec ? launch_bwd<true, false>(q, d, lse, Bq, Bd, H, inv_temperature, label_offset, plan.ns_q, grad_out, coef, dq, partial, s)
+             : launch_bwd<false, false>(q, d, lse, Bq, Bd, H, inv_temperature, label_offset, plan.ns_q, grad_out, coef, dq, partial, s);
+    if (rc) return rc;
+  }
+  if (dd) {
+    rc = vec ? launch_bwd<true, true>(d, q, lse, Bd, Bq, H, inv_temperature, label_offset, plan.ns_d, grad_out, coef, dd, partial, s)
+             : launch_bwd<false, true>(d, q, lse, Bd, Bq, H, inv_temperature, label_offset, plan.ns_d, grad_out, coef, dd, partial, s);
+  }
+  return rc;
 }
 
 }  // namespace tt
@@ -350,10 +396,7 @@ extern "C" {
 size_t tt_inbatch_ce_workspace(int64_t Bq, int64_t Bd, int H, int precision) {
   if (Bq <= 0 || Bd <= 0 || H <= 0) return 256;
   size_t fp32 = tt::plan_ce(Bq, Bd, H).total;
-  if (precision == TT_PREC_BF16) {
-    size_t tc = tt::tc_inbatch_workspace(Bq, Bd, H);
-    return tc > fp32 ? tc : fp32;
-  }
+  if (precision == TT_PREC_BF16) return tt::tc_inbatch_workspace(Bq, Bd, H);
   return fp32;
 }
 
@@ -372,19 +415,8 @@ int tt_inbatch_ce_fwd(const float* q, const float* d, const void* q_bf16, const 
                               inv_temperature, label_offset, loss_scale, loss, lse, pos_mean, workspace,
                               workspace_bytes, s);
   TT_CHECK_ARG(precision == TT_PREC_FP32, "inbatch_ce_fwd: unknown precision %d", precision);
-  const tt::CePlan plan = tt::plan_ce(Bq, Bd, H);
-  if (workspace == nullptr || workspace_bytes < plan.total) { tt::set_error("inbatch_ce_fwd: workspace too small"); return TT_ERR_WORKSPACE; }
-  tt::Workspace w(workspace, workspace_bytes);
-  float* part_ml = w.take<float>(plan.ml_bytes / sizeof(float));
-  float* pos = w.take<float>(Bq);
-  const int yt = (int)tt::ceil_div(Bd, tt::CE_T);
-  const int per = (int)tt::ceil_div(yt, plan.ns_f);
-  dim3 grid((unsigned)tt::ceil_div(Bq, tt::CE_T), (unsigned)plan.ns_f);
-  const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
-  if (vec) tt::ce_fwd_kernel<true><<<grid, 256, 0, s>>>(q, d, Bq, Bd, H, inv_temperature, label_offset, per, part_ml, pos);
-  else     tt::ce_fwd_kernel<false><<<grid, 256, 0, s>>>(q, d, Bq, Bd, H, inv_temperature, label_offset, per, part_ml, pos);
-  TT_LAUNCH_CHECK("ce_fwd_kernel");
-  return tt::inbatch_finalize(part_ml, pos, plan.ns_f, Bq, inv_temperature, loss_scale, lse, loss, pos_mean, nullptr, s);
+  return tt::inbatch_ce_fwd_fp32(q, d, Bq, Bd, H, inv_temperature, label_offset, loss_scale, loss, lse, pos_mean,
+                                 workspace, workspace_bytes, s);
 }
 
 int tt_inbatch_ce_bwd(const float* q, const float* d, const void* q_bf16, const void* d_bf16, const float* lse,
@@ -399,25 +431,8 @@ int tt_inbatch_ce_bwd(const float* q, const float* d, const void* q_bf16, const 
                               inv_temperature, label_offset, loss_scale, grad_out, dq, dd, workspace,
                               workspace_bytes, s);
   TT_CHECK_ARG(precision == TT_PREC_FP32, "inbatch_ce_bwd: unknown precision %d", precision);
-  const tt::CePlan plan = tt::plan_ce(Bq, Bd, H);
-  if (workspace == nullptr || workspace_bytes < plan.total) { tt::set_error("inbatch_ce_bwd: workspace too small"); return TT_ERR_WORKSPACE; }
-  tt::Workspace w(workspace, workspace_bytes);
-  (void)w.take<float>(plan.ml_bytes / sizeof(float));
-  (void)w.take<float>(Bq);
-  float* partial = plan.bwd_bytes ? w.take<float>(plan.bwd_bytes / sizeof(float)) : nullptr;
-  const float coef = loss_scale * inv_temperature;
-  const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
-  int rc = TT_OK;
-  if (dq) {
-    rc = vec ? tt::launch_bwd<true, false>(q, d, lse, Bq, Bd, H, inv_temperature, label_offset, plan.ns_q, grad_out, coef, dq, partial, s)
-             : tt::launch_bwd<false, false>(q, d, lse, Bq, Bd, H, inv_temperature, label_offset, plan.ns_q, grad_out, coef, dq, partial, s);
-    if (rc) return rc;
-  }
-  if (dd) {
-    rc = vec ? tt::launch_bwd<true, true>(d, q, lse, Bd, Bq, H, inv_temperature, label_offset, plan.ns_d, grad_out, coef, dd, partial, s)
-             : tt::launch_bwd<false, true>(d, q, lse, Bd, Bq, H, inv_temperature, label_offset, plan.ns_d, grad_out, coef, dd, partial, s);
-  }
-  return rc;
+  return tt::inbatch_ce_bwd_fp32(q, d, lse, Bq, Bd, H, inv_temperature, label_offset, loss_scale, grad_out, dq, dd,
+                                 workspace, workspace_bytes, s);
 }
 
 }  // extern "C"

@@ -180,12 +180,15 @@ int sgemm(const SgemmArgs& a, cudaStream_t stream) {
     launch_cfg<64, 64, 16, 4, 4>(a, kchunk, grid, stream);
   }
   TT_LAUNCH_CHECK("sgemm_kernel");
-  if (a.splits > 1) {
-    size_t total = (size_t)a.M * a.N;
-    int blocks = (int)(ceil_div((int64_t)total, 256) < 4 * kNumSMs ? ceil_div((int64_t)total, 256) : 4 * kNumSMs);
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(a);
-    TT_LAUNCH_CHECK("splitk_reduce_kernel");
-  }
+  if (a.splits > 1) return splitk_reduce(a, stream);
+  return TT_OK;
+}
+
+int splitk_reduce(const SgemmArgs& a, cudaStream_t stream) {
+  size_t total = (size_t)a.M * a.N;
+  int blocks = (int)(ceil_div((int64_t)total, 256) < 4 * kNumSMs ? ceil_div((int64_t)total, 256) : 4 * kNumSMs);
+  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(a);
+  TT_LAUNCH_CHECK("splitk_reduce_kernel");
   return TT_OK;
 }
 

@@ -31,6 +31,8 @@ inline size_t sgemm_partial_bytes(int M, int N, int splits) {
 // heuristic split-K factor so that the grid covers the 148 SMs
 int sgemm_pick_splits(int M, int N, int K);
 int sgemm(const SgemmArgs& a, cudaStream_t stream);
+// fixed-order sum of a.partial[0..splits) + epilogue -> a.C (used by the fp32 and the tcgen05 GEMMs)
+int splitk_reduce(const SgemmArgs& a, cudaStream_t stream);
 
 // column sums: out[n] = sum_m X[m,n]  (bias gradients), fixed-order two-stage reduction.
 // partial must hold colsum_partial_rows(M) * N floats.

@@ -1,0 +1,463 @@
+// tc_gemm.cu -- bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM,
+// operands staged by TMA into 128B-swizzled shared memory) and the tower MLP built on it
+// (TT_PREC_BF16 path of K3).
+//
+//   C[M,N] = epilogue( A * B )   A: [M,K] (K-major) or stored [K,M] (MN-major)
+//                                B: [N,K] (K-major, nn.Linear weight layout) or stored [K,N] (MN-major)
+//   epilogue: + bias[n] -> relu -> * (mask[m,n] > 0); fp32 and/or bf16 output; or raw split-K partials.
+//
+// One CTA = one 128 x BN output tile (x one K split).  Warp roles (192 threads):
+//   warp 0  TMA producer   : 4-stage ring of {A 128x64, B BNx64} bf16 tiles, mbarrier expect_tx
+//   warp 1  MMA issuer     : one lane issues 4 x tcgen05.mma (K=16) per stage, tcgen05.commit
+//                            frees the stage and finally signals the accumulator
+//   warps 2-5 epilogue     : tcgen05.ld 32 lanes x 32 columns -> registers -> global
+// Both operand majors are supported because the backward GEMMs (dW = dY^T X, dX = dY W) consume
+// the same row-major activations with the roles of the axes swapped; no transposes are
+// materialised.
+#include "tc_common.cuh"
+#include "sgemm.cuh"
+#include "tensor_core.cuh"
+
+namespace tt {
+namespace tc {
+
+// ---------------------------------------------------------------------------------------
+// host: tensor map encode through the runtime's driver entry point
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || p == nullptr) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return TT_ERR_CUDA; }
+  if ((cols * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA operand needs 16-byte aligned base and row pitch (cols=%llu)", (unsigned long long)cols);
+    return TT_ERR_UNSUPPORTED;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows); return TT_ERR_CUDA; }
+  return TT_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------
+struct GemmParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int kblocks_per_split;      // 64-wide K blocks handled by one blockIdx.z
+  float* C;                   // fp32 output [M,ldc] (nullable) or split partials [z][M][N]
+  __nv_bfloat16* Cb;          // bf16 output [M,ldc] (nullable)
+  int ldc;
+  const float* bias;
+  int act;
+  const float* mask;
+  int ldmask;
+  int splits;
+};
+
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 192;
+constexpr int BM = 128, BK = 64;
+constexpr uint32_t kATile = BM * BK * 2;                         // 16 KB
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  constexpr uint32_t kBTile = BN * BK * 2;
+  constexpr uint32_t kStageBytes = kATile + kBTile;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // carve: [stages x (A,B)] [full barriers][empty barriers][tmem_full][tmem slot]
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* acc_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb_beg = blockIdx.z * p.kblocks_per_split;
+  const int kb_end = min(total_kb, kb_beg + p.kblocks_per_split);
+  const int nkb = max(0, kb_end - kb_beg);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kStages, k0 = (kb_beg + i) * BK;
+        mbar_wait(&empty_bar[s], ((i / kStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+        uint8_t* a = tiles + s * kStageBytes;
+        uint8_t* b = a + kATile;
+        if (!p.a_mn) tma_load_2d(a, &tmA, &full_bar[s], k0, m0);
+        else { tma_load_2d(a, &tmA, &full_bar[s], m0, k0); tma_load_2d(a + 8192, &tmA, &full_bar[s], m0 + 64, k0); }
+        if (!p.b_mn) tma_load_2d(b, &tmB, &full_bar[s], k0, n0);
+        else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kStages;
+        mbar_wait(&full_bar[s], (i / kStages) & 1);
+        tc_fence_after();
+        const uint32_t a = smem_u32(tiles + s * kStageBytes), b = a + kATile;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = p.a_mn ? umma_desc_mnmajor(a, k, 8192u) : umma_desc_kmajor(a, k);
+          const uint64_t db = p.b_mn ? umma_desc_mnmajor(b, k, 8192u) : umma_desc_kmajor(b, k);
+          umma_bf16(tmem_acc, da, db, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);            // stage reusable once these MMAs have read it
+      }
+      umma_commit(acc_bar);                    // accumulator complete
+    }
+  } else {
+    // epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
+    const int quarter = warp & 3;
+    const int row = m0 + quarter * 32 + lane;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const bool split = p.splits > 1;
+    float* outp = split ? p.C + (size_t)blockIdx.z * p.M * p.N : p.C;
+    const int ldo = split ? p.N : p.ldc;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      if (nkb > 0) {
+        tmem_ld_x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (row < p.M) {
+        const int cbase = n0 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int col = cbase + j + u;
+            float x = __uint_as_float(r[j + u]);
+            if (!split && col < p.N) {
+              if (p.bias) x += p.bias[col];
+              if (p.act == 1) x = fmaxf(x, 0.f);
+              if (p.mask) x = (p.mask[(size_t)row * p.ldmask + col] > 0.f) ? x : 0.f;
+            }
+            v[u] = x;
+          }
+          const int col = cbase + j;
+          if (col + 3 < p.N && (ldo & 3) == 0) {
+            if (outp) *reinterpret_cast<float4*>(outp + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+            if (!split && p.Cb) {
+              uint2 pk = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+              *reinterpret_cast<uint2*>(p.Cb + (size_t)row * p.ldc + col) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (col + u < p.N) {
+                if (outp) outp[(size_t)row * ldo + col + u] = v[u];
+                if (!split && p.Cb) p.Cb[(size_t)row * p.ldc + col + u] = __float2bfloat16(v[u]);
+              }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_acc, BN);
+}
+
+template <int BN>
+static constexpr size_t gemm_smem_bytes() {
+  return 1024 + kStages * (kATile + BN * BK * 2) + (2 * kStages + 1) * 8 + 16;
+}
+
+struct TcGemm {
+  int M, N, K;
+  const __nv_bfloat16* A; int a_mn;      // a_mn ? stored [K,M] : stored [M,K]
+  const __nv_bfloat16* B; int b_mn;      // b_mn ? stored [K,N] : stored [N,K]
+  float* C = nullptr; __nv_bfloat16* Cb = nullptr; int ldc = 0;
+  const float* bias = nullptr; int act = 0; const float* mask = nullptr; int ldmask = 0;
+  int splits = 1; float* partial = nullptr;
+};
+
+template <int BN>
+static int launch_gemm(const TcGemm& g, cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!g.a_mn) rc = make_tmap_bf16(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM);
+  else         rc = make_tmap_bf16(&tmA, g.A, (uint64_t)g.K, (uint64_t)g.M, 64);
+  if (rc) return rc;
+  if (!g.b_mn) rc = make_tmap_bf16(&tmB, g.B, (uint64_t)g.N, (uint64_t)g.K, BN);
+  else         rc = make_tmap_bf16(&tmB, g.B, (uint64_t)g.K, (uint64_t)g.N, 64);
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.a_mn = g.a_mn; p.b_mn = g.b_mn;
+  const int total_kb = (g.K + BK - 1) / BK;
+  p.kblocks_per_split = (total_kb + g.splits - 1) / g.splits;
+  p.splits = g.splits;
+  p.C = g.splits > 1 ? g.partial : g.C;
+  p.Cb = g.Cb; p.ldc = g.ldc; p.bias = g.bias; p.act = g.act; p.mask = g.mask; p.ldmask = g.ldmask;
+  constexpr size_t smem = gemm_smem_bytes<BN>();
+  TT_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), (unsigned)g.splits);
+  tc_gemm_kernel<BN><<<grid, kGemmThreads, smem, s>>>(tmA, tmB, p);
+  TT_LAUNCH_CHECK("tc_gemm_kernel");
+  if (g.splits > 1) {
+    // fixed-order reduction + epilogue (shared with the fp32 path)
+    SgemmArgs a{};
+    a.M = g.M; a.N = g.N; a.K = g.K; a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.act = g.act;
+    a.mask = g.mask; a.ldmask = g.ldmask; a.splits = g.splits; a.partial = g.partial;
+    return splitk_reduce(a, s);
+  }
+  return TT_OK;
+}
+
+int tc_gemm(const TcGemm& g, cudaStream_t s) {
+  TT_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "tc_gemm: bad shape");
+  TT_CHECK_ARG(g.splits == 1 || (g.partial && g.C && !g.Cb), "tc_gemm: split-K needs partial + fp32 output only");
+  if (g.N <= 64) return launch_gemm<64>(g, s);
+  if (g.N <= 128) return launch_gemm<128>(g, s);
+  return launch_gemm<256>(g, s);
+}
+
+static int pick_splits(int M, int N, int K) {
+  const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int64_t tiles = ceil_div(M, BM) * ceil_div(N, bn);
+  const int total_kb = (K + BK - 1) / BK;
+  if (tiles >= kNumSMs / 2 || total_kb <= 4) return 1;
+  int64_t want = ceil_div(kNumSMs, tiles);
+  int64_t maxs = total_kb / 4;              // >= 4 k-blocks (256 of K) per split
+  if (want > maxs) want = maxs;
+  if (want > 64) want = 64;
+  return (int)(want < 1 ? 1 : want);
+}
+
+// ---------------------------------------------------------------------------------------
+// small elementwise helpers of the bf16 path
+// ---------------------------------------------------------------------------------------
+__global__ void cast2_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ ab, int64_t na,
+                             const float* __restrict__ b, __nv_bfloat16* __restrict__ bb, int64_t nb,
+                             const float* __restrict__ c, __nv_bfloat16* __restrict__ cb, int64_t nc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < na; i += stride) ab[i] = __float2bfloat16(a[i]);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += stride) bb[i] = __float2bfloat16(b[i]);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc; i += stride) cb[i] = __float2bfloat16(c[i]);
+}
+
+static int cast3(const float* a, __nv_bfloat16* ab, int64_t na, const float* b, __nv_bfloat16* bb, int64_t nb,
+                 const float* c, __nv_bfloat16* cb, int64_t nc, cudaStream_t s) {
+  int64_t n = na > nb ? na : nb;
+  if (nc > n) n = nc;
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  cast2_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, ab, na, b, bb, nb, c, cb, nc);
+  TT_LAUNCH_CHECK("cast2_kernel");
+  return TT_OK;
+}
+
+int cast3_public(const float* a, __nv_bfloat16* ab, int64_t na, const float* b, __nv_bfloat16* bb, int64_t nb, cudaStream_t s) {
+  return cast3(a, ab, na, b, bb, nb, nullptr, nullptr, 0, s);
+}
+
+// y = z / max(|z|,1e-12) (fp32 + bf16)
+__global__ void __launch_bounds__(256)
+l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __restrict__ y, __nv_bfloat16* __restrict__ yb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float* zr = z + row * H;
+  float ss = 0.f;
+  for (int e = lane; e < H; e += 32) { float v = zr[e]; ss = fmaf(v, v, ss); }
+  const float denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  for (int e = lane; e < H; e += 32) {
+    const float o = zr[e] / denom;
+    y[row * H + e] = o;
+    if (yb) yb[row * H + e] = __float2bfloat16(o);
+  }
+}
+// dz = (dy - y (y.dy)) / |z|  -> fp32 + bf16
+__global__ void __launch_bounds__(256)
+l2norm_bwd_bf16_kernel(const float* __restrict__ dy, const float* __restrict__ z, int64_t R, int H,
+                       float* __restrict__ dz, __nv_bfloat16* __restrict__ dzb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float* zr = z + row * H; const float* gr = dy + row * H;
+  float ss = 0.f, dot = 0.f;
+  for (int e = lane; e < H; e += 32) { float v = zr[e]; ss = fmaf(v, v, ss); dot = fmaf(v, gr[e], dot); }
+  ss = warp_sum(ss); dot = warp_sum(dot);
+  const float n = sqrtf(ss), denom = fmaxf(n, 1e-12f);
+  const float inner = (n > 1e-12f) ? dot / (denom * denom) : 0.f;
+  for (int e = lane; e < H; e += 32) {
+    const float o = (gr[e] - zr[e] * inner) / denom;
+    dz[row * H + e] = o;
+    dzb[row * H + e] = __float2bfloat16(o);
+  }
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------
+// tower MLP on the tensor cores
+// ---------------------------------------------------------------------------------------
+struct TcMlpPlan {
+  int s_dw2, s_dw1;
+  size_t xb, w1b, w2b, h1b, act_f, act_b, partial, colsum, total;
+};
+static TcMlpPlan plan_tc_mlp(int64_t R, int E, int H) {
+  TcMlpPlan p{};
+  p.s_dw2 = tc::pick_splits(H, H, (int)R);
+  p.s_dw1 = tc::pick_splits(H, E, (int)R);
+  p.xb = align_up((size_t)R * E * 2);
+  p.w1b = align_up((size_t)H * E * 2);
+  p.w2b = align_up((size_t)H * H * 2);
+  p.h1b = align_up((size_t)R * H * 2);
+  p.act_f = align_up((size_t)R * H * 4);
+  p.act_b = align_up((size_t)R * H * 2);
+  size_t pa = p.s_dw2 > 1 ? (size_t)p.s_dw2 * H * H * 4 : 0;
+  size_t pb = p.s_dw1 > 1 ? (size_t)p.s_dw1 * H * E * 4 : 0;
+  p.partial = align_up(pa > pb ? pa : pb);
+  p.colsum = align_up((size_t)colsum_partial_rows(R) * H * 4);
+  // bwd: xb, w1b, w2b, h1b, dz (f32+bf16), da1 (f32+bf16), partial, colsum
+  p.total = p.xb + p.w1b + p.w2b + p.h1b + 2 * p.act_f + 2 * p.act_b + p.partial + p.colsum + 1024;
+  return p;
+}
+
+size_t tc_mlp_workspace(int64_t R, int E, int H) { return plan_tc_mlp(R, E, H).total; }
+
+static bool tc_mlp_supported(int E, int H) { return (E % 8 == 0) && (H % 8 == 0); }
+
+int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t R, int E,
+               int H, float* h1, float* z, float* y, __nv_bfloat16* y_bf16, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0 (E=%d H=%d)", E, H); return TT_ERR_UNSUPPORTED; }
+  const TcMlpPlan plan = plan_tc_mlp(R, E, H);
+  if (ws == nullptr || ws_bytes < plan.total) { set_error("tc_mlp_fwd: workspace too small (%zu < %zu)", ws_bytes, plan.total); return TT_ERR_WORKSPACE; }
+  Workspace w(ws, ws_bytes);
+  __nv_bfloat16* xb = w.take<__nv_bfloat16>((size_t)R * E);
+  __nv_bfloat16* w1b = w.take<__nv_bfloat16>((size_t)H * E);
+  __nv_bfloat16* w2b = w.take<__nv_bfloat16>((size_t)H * H);
+  __nv_bfloat16* h1b = w.take<__nv_bfloat16>((size_t)R * H);
+  int rc = tc::cast3(x, xb, R * E, w1, w1b, (int64_t)H * E, w2, w2b, (int64_t)H * H, s);
+  if (rc) return rc;
+  tc::TcGemm g{};
+  g.M = (int)R; g.N = H; g.K = E; g.A = xb; g.a_mn = 0; g.B = w1b; g.b_mn = 0;
+  g.C = h1; g.Cb = h1b; g.ldc = H; g.bias = b1; g.act = 1;
+  rc = tc::tc_gemm(g, s); if (rc) return rc;
+  g = tc::TcGemm{};
+  g.M = (int)R; g.N = H; g.K = H; g.A = h1b; g.a_mn = 0; g.B = w2b; g.b_mn = 0;
+  g.C = z; g.ldc = H; g.bias = b2;
+  rc = tc::tc_gemm(g, s); if (rc) return rc;
+  tc::l2norm_fwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(z, R, H, y, y_bf16);
+  TT_LAUNCH_CHECK("l2norm_fwd_bf16_kernel");
+  return TT_OK;
+}
+
+int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1, const float* z,
+               int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2, float* db2, void* ws,
+               size_t ws_bytes, cudaStream_t s) {
+  if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0"); return TT_ERR_UNSUPPORTED; }
+  const TcMlpPlan plan = plan_tc_mlp(R, E, H);
+  if (ws == nullptr || ws_bytes < plan.total) { set_error("tc_mlp_bwd: workspace too small (%zu < %zu)", ws_bytes, plan.total); return TT_ERR_WORKSPACE; }
+  Workspace w(ws, ws_bytes);
+  __nv_bfloat16* xb = w.take<__nv_bfloat16>((size_t)R * E);
+  __nv_bfloat16* w1b = w.take<__nv_bfloat16>((size_t)H * E);
+  __nv_bfloat16* w2b = w.take<__nv_bfloat16>((size_t)H * H);
+  __nv_bfloat16* h1b = w.take<__nv_bfloat16>((size_t)R * H);
+  float* dz = w.take<float>((size_t)R * H);
+  float* da1 = w.take<float>((size_t)R * H);
+  __nv_bfloat16* dzb = w.take<__nv_bfloat16>((size_t)R * H);
+  __nv_bfloat16* da1b = w.take<__nv_bfloat16>((size_t)R * H);
+  float* partial = plan.partial ? w.take<float>(plan.partial / 4) : nullptr;
+  float* cpart = w.take<float>(plan.colsum / 4);
+  int rc = tc::cast3(x, xb, R * E, w1, w1b, (int64_t)H * E, w2, w2b, (int64_t)H * H, s); if (rc) return rc;
+  rc = tc::cast3(h1, h1b, R * H, nullptr, nullptr, 0, nullptr, nullptr, 0, s); if (rc) return rc;
+  tc::l2norm_bwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(dy, z, R, H, dz, dzb);
+  TT_LAUNCH_CHECK("l2norm_bwd_bf16_kernel");
+  tc::TcGemm g{};
+  // dw2[H,H] = dz^T h1 : A = dz stored [K=R, M=H] (MN-major), B = h1 stored [K=R, N=H] (MN-major)
+  g.M = H; g.N = H; g.K = (int)R; g.A = dzb; g.a_mn = 1; g.B = h1b; g.b_mn = 1; g.C = dw2; g.ldc = H;
+  g.splits = plan.s_dw2; g.partial = partial;
+  rc = tc::tc_gemm(g, s); if (rc) return rc;
+  rc = colsum(dz, R, H, H, db2, cpart, s); if (rc) return rc;
+  // da1[R,H] = (dz w2) * (h1 > 0) : A = dz [M=R,K=H] K-major, B = w2 stored [K=H_out, N=H_in] (MN-major)
+  g = tc::TcGemm{};
+  g.M = (int)R; g.N = H; g.K = H; g.A = dzb; g.a_mn = 0; g.B = w2b; g.b_mn = 1; g.C = da1; g.Cb = da1b; g.ldc = H;
+  g.mask = h1; g.ldmask = H;
+  rc = tc::tc_gemm(g, s); if (rc) return rc;
+  // dw1[H,E] = da1^T x
+  g = tc::TcGemm{};
+  g.M = H; g.N = E; g.K = (int)R; g.A = da1b; g.a_mn = 1; g.B = xb; g.b_mn = 1; g.C = dw1; g.ldc = E;
+  g.splits = plan.s_dw1; g.partial = partial;
+  rc = tc::tc_gemm(g, s); if (rc) return rc;
+  rc = colsum(da1, R, H, H, db1, cpart, s); if (rc) return rc;
+  if (dx) {
+    // dx[R,E] = da1 w1 : A = da1 K-major, B = w1 stored [K=H, N=E] (MN-major)
+    g = tc::TcGemm{};
+    g.M = (int)R; g.N = E; g.K = H; g.A = da1b; g.a_mn = 0; g.B = w1b; g.b_mn = 1; g.C = dx; g.ldc = E;
+    rc = tc::tc_gemm(g, s); if (rc) return rc;
+  }
+  return TT_OK;
+}
+
+// self-test hook used by the GPU test-suite: C = A * B on the tensor cores with either operand major
+int tc_gemm_selftest(const __nv_bfloat16* A, int a_mn, const __nv_bfloat16* B, int b_mn, int M, int N, int K,
+                     float* C, int splits, float* partial, cudaStream_t s) {
+  tc::TcGemm g{};
+  g.M = M; g.N = N; g.K = K; g.A = A; g.a_mn = a_mn; g.B = B; g.b_mn = b_mn; g.C = C; g.ldc = N;
+  g.splits = splits; g.partial = partial;
+  return tc::tc_gemm(g, s);
+}
+
+}  // namespace tt
+
+extern "C" int tt_selftest_tc_gemm(const void* a_bf16, int a_mn_major, const void* b_bf16, int b_mn_major, int M, int N,
+                                   int K, float* c, int splits, float* partial, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(a_bf16 && b_bf16 && c && M > 0 && N > 0 && K > 0 && splits >= 1, "selftest_tc_gemm: bad arguments");
+  return tt::tc_gemm_selftest((const __nv_bfloat16*)a_bf16, a_mn_major, (const __nv_bfloat16*)b_bf16, b_mn_major, M, N, K,
+                              c, splits, partial, static_cast<cudaStream_t>(stream));
+}

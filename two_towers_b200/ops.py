@@ -493,3 +493,16 @@ class MultiNegLossFn(torch.autograd.Function):
         q, p, negs, probs = ctx.saved_tensors
         dq, dp, dnegs = multineg_bwd(q, p, negs, probs, ctx.temperature, g.contiguous())
         return dq, dp, dnegs, None
+
+
+# --------------------------------------------------------------------------------------
+# tensor-core self-test hook (tests only)
+# --------------------------------------------------------------------------------------
+def selftest_tc_gemm(a_bf16: torch.Tensor, a_mn_major: bool, b_bf16: torch.Tensor, b_mn_major: bool, M: int, N: int,
+                     K: int, splits: int = 1) -> torch.Tensor:
+    _need_cuda(a_bf16, b_bf16)
+    c = torch.empty(M, N, dtype=torch.float32, device=a_bf16.device)
+    partial = torch.empty(splits * M * N, dtype=torch.float32, device=a_bf16.device) if splits > 1 else None
+    check(_lib_().tt_selftest_tc_gemm(_p(a_bf16.contiguous()), int(a_mn_major), _p(b_bf16.contiguous()), int(b_mn_major),
+                                      M, N, K, _p(c), splits, _p(partial), _stream()), "tt_selftest_tc_gemm")
+    return c

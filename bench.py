@@ -258,12 +258,18 @@ def kernel_roofline(tt, tr, dev):
     prec = "bf16" if tr.prec == 1 else "fp32"
     loss, lse, _ = tt.ops.inbatch_ce_fwd(q, d, 0.1, precision=prec)
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    # capture the op in a CUDA graph so the CUDA-event interval holds device time only (no host launch gaps)
+    tt.ops.inbatch_ce_bwd(q, d, lse, 0.1, precision=prec)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        tt.ops.inbatch_ce_bwd(q, d, lse, 0.1, precision=prec)
     times = []
-    for i in range(8):
+    for i in range(10):
         flush_l2(flush)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        tt.ops.inbatch_ce_bwd(q, d, lse, 0.1, precision=prec)
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:

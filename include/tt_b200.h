@@ -74,14 +74,22 @@ int tt_embed_pool_bwd(const void* ids, int id_bytes, const float* inv_len, const
  * Saved for backward (caller-allocated): h1 [R,H] (post-ReLU), z [R,H] (pre-normalise).
  * y [R,H] has unit rows: y = z / max(||z||, 1e-12).  y_bf16 (nullable): bf16 copy of y.
  * tt_mlp_bwd: given dy, produces dx [R,E] (nullable), dw1, db1, dw2, db2 (OVERWRITTEN).
+ * bf16 operand shadows (TT_PREC_BF16 only, all nullable -- missing ones are produced inside the call):
+ *   x_bf16 [R,E], w1_bf16 [H,E], w2_bf16 [H,H] (e.g. the shadow tt_adamw_step maintains),
+ *   h1_bf16 [R,H] written by fwd and read by bwd.
+ * dy_parts > 1 (TT_PREC_BF16): dy is given as dy_parts slices, dy_part_stride elements apart, that are summed
+ *   in slice order inside the first backward kernel (see tt_inbatch_ce_bwd_parts); pass 1, 0 otherwise.
  */
 size_t tt_mlp_workspace(int64_t R, int E, int H, int precision);
 int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                int64_t R, int E, int H, float* h1, float* z, float* y, void* y_bf16,
+               const void* x_bf16, const void* w1_bf16, const void* w2_bf16, void* h1_bf16,
                int precision, void* workspace, size_t workspace_bytes, void* stream);
 int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2,
                const float* h1, const float* z, int64_t R, int E, int H,
                float* dx, float* dw1, float* db1, float* dw2, float* db2,
+               const void* x_bf16, const void* w1_bf16, const void* w2_bf16, const void* h1_bf16,
+               int dy_parts, int64_t dy_part_stride,
                int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K3': avg_pool tower projection  Linear(E,H) -> Dropout(p) -> LayerNorm(H) -> normalise -
@@ -126,6 +134,18 @@ int tt_inbatch_ce_bwd(const float* q, const float* d, const void* q_bf16, const 
                       int64_t label_offset, float loss_scale, const float* grad_out,
                       float* dq, float* dd,
                       int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Partial-slice backward (TT_PREC_BF16, bf16 operands, H % 64 == 0, H <= 256): ONE launch computes both
+ * gradients; the Y range is split over n = tt_inbatch_ce_bwd_nparts() CTAs per row tile and slice s of
+ * dq/dd is written at dq_parts + s*dq_part_stride (dd likewise).  The true gradient is the sum of the
+ * slices in slice order -- tt_mlp_bwd(dy_parts = n) consumes them directly, so no reduction kernel and no
+ * extra pass over [B,H] is needed.  A null dq_parts / dd_parts skips that gradient.
+ */
+int tt_inbatch_ce_bwd_nparts(int64_t Bq, int64_t Bd, int H, int precision);
+int tt_inbatch_ce_bwd_parts(const void* q_bf16, const void* d_bf16, const float* lse, int64_t Bq, int64_t Bd,
+                            int H, float inv_temperature, int64_t label_offset, float loss_scale,
+                            const float* grad_out, float* dq_parts, int64_t dq_part_stride,
+                            float* dd_parts, int64_t dd_part_stride, void* stream);
 
 /* ---- K5/K6: row-paired cosine losses ------------------------------------------------------
  * tt_triplet_*   : contrastive_triplet_loss, twotower/losses.py:28-35:
@@ -173,9 +193,9 @@ int tt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* ---- optimizer: torch.optim.AdamW(model.parameters(), lr), train.py:359 ------
  * One fused AdamW step over a flat fp32 parameter buffer (ATen _single_tensor_adamw
  * semantics and operation order, amsgrad off; hyper-parameters are doubles, rounded to fp32
- * exactly where torch rounds them).  step_count: device int64 holding the number of steps already
- * taken; the kernel uses step_count+1 for bias correction and tt_adamw_step increments it
- * (graph-capturable: no host state).  param_bf16 (nullable): refreshed bf16 shadow.
+ * exactly where torch rounds them).  step_count: device int64[2], zero-initialised by the caller:
+ * [0] = number of steps already taken (the kernel uses [0]+1 for bias correction and the last block
+ * to finish increments it -- graph-capturable, no host state), [1] = scratch arrival ticket.  param_bf16 (nullable): refreshed bf16 shadow.
  */
 int tt_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                   int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,

@@ -29,14 +29,16 @@ SIGNATURES = {
     "tt_embed_pool_bwd_workspace": (_sz, [_i64, _i, _i64, _i]),
     "tt_embed_pool_bwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _i64, _i, _vp, _vp, _sz, _vp]),
     "tt_mlp_workspace": (_sz, [_i64, _i, _i, _i]),
-    "tt_mlp_fwd": (_i, [_vp] * 5 + [_i64, _i, _i] + [_vp] * 4 + [_i, _vp, _sz, _vp]),
-    "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 5 + [_i, _vp, _sz, _vp]),
+    "tt_mlp_fwd": (_i, [_vp] * 5 + [_i64, _i, _i] + [_vp] * 8 + [_i, _vp, _sz, _vp]),
+    "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 9 + [_i, _i64] + [_i, _vp, _sz, _vp]),
     "tt_proj_ln_workspace": (_sz, [_i64, _i, _i]),
     "tt_proj_ln_fwd": (_i, [_vp] * 5 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 4 + [_vp, _sz, _vp]),
     "tt_proj_ln_bwd": (_i, [_vp] * 7 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 5 + [_vp, _sz, _vp]),
     "tt_inbatch_ce_workspace": (_sz, [_i64, _i64, _i, _i]),
     "tt_inbatch_ce_fwd": (_i, [_vp] * 4 + [_i64, _i64, _i, _f, _i64, _f] + [_vp] * 3 + [_i, _vp, _sz, _vp]),
     "tt_inbatch_ce_bwd": (_i, [_vp] * 5 + [_i64, _i64, _i, _f, _i64, _f] + [_vp] * 3 + [_i, _vp, _sz, _vp]),
+    "tt_inbatch_ce_bwd_nparts": (_i, [_i64, _i64, _i, _i]),
+    "tt_inbatch_ce_bwd_parts": (_i, [_vp] * 3 + [_i64, _i64, _i, _f, _i64, _f] + [_vp, _vp, _i64, _vp, _i64, _vp]),
     "tt_triplet_fwd": (_i, [_vp] * 3 + [_i64, _i, _f] + [_vp] * 4 + [_vp]),
     "tt_triplet_bwd": (_i, [_vp] * 4 + [_i64, _i, _f] + [_vp] * 4 + [_vp]),
     "tt_multineg_fwd": (_i, [_vp] * 3 + [_i64, _i, _i, _f] + [_vp] * 2 + [_vp]),

@@ -50,45 +50,38 @@ embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ tab
 #pragma unroll
       for (int j = 0; j < NACC; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       int cnt = 0;
-      int t = grp;
-      // 4 tokens in flight per group: ids first, then all row loads, then the adds
-      for (; t + 3 * groups < L; t += 4 * groups) {
-        int64_t id[4];
+      // ids are read 32 tokens at a time with ONE coalesced load per lane and handed to the token
+      // groups by shuffle, so the gather loads below do not wait on a per-token id load.
+      for (int tb = 0; tb < L; tb += 32) {
+        const int64_t my_id = (tb + lane < L) ? load_id(rid + tb + lane) : 0;
+        const int my_row = (my_id > 0 && my_id < V) ? (int)my_id : -1;       // -1 == masked token
+        cnt += __popc(__ballot_sync(0xffffffffu, my_row >= 0));
+        const int nb = min(32, L - tb);
+        for (int tbase = 0; tbase < nb; tbase += 4 * groups) {     // warp-uniform trip count (shuffles inside)
+          const int t0 = tbase + grp;
+          int trow[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) id[u] = load_id(rid + t + u * groups);
-        float4 v[4][NACC];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool ok = id[u] > 0 && id[u] < V;
-          cnt += ok;
-          const float4* src = reinterpret_cast<const float4*>(table + (ok ? id[u] : 0) * E);
-#pragma unroll
-          for (int j = 0; j < NACC; ++j) {
-            int c = cbase + sub + j * tpt;
-            v[u][j] = (ok && c < chunks) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < 4; ++u) {
+            const int t = t0 + u * groups;
+            const int r = __shfl_sync(0xffffffffu, my_row, t & 31);
+            trow[u] = (t < nb) ? r : -1;
           }
-        }
+          float4 v[4][NACC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 4; ++u) {
+            const float4* src = reinterpret_cast<const float4*>(table + (int64_t)(trow[u] < 0 ? 0 : trow[u]) * E);
 #pragma unroll
-          for (int j = 0; j < NACC; ++j) {
-            acc[j].x += v[u][j].x; acc[j].y += v[u][j].y; acc[j].z += v[u][j].z; acc[j].w += v[u][j].w;
-          }
-      }
-      for (; t < L; t += groups) {
-        int64_t id = load_id(rid + t);
-        const bool ok = id > 0 && id < V;
-        cnt += ok;
-        if (ok) {
-          const float4* src = reinterpret_cast<const float4*>(table + id * E);
-#pragma unroll
-          for (int j = 0; j < NACC; ++j) {
-            int c = cbase + sub + j * tpt;
-            if (c < chunks) {
-              float4 v = __ldg(src + c);
-              acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+            for (int j = 0; j < NACC; ++j) {
+              const int c = cbase + sub + j * tpt;
+              v[u][j] = (trow[u] >= 0 && c < chunks) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) {
+              acc[j].x += v[u][j].x; acc[j].y += v[u][j].y; acc[j].z += v[u][j].z; acc[j].w += v[u][j].w;
+            }
         }
       }
       // combine the token groups (lanes with equal `sub`), fixed xor-tree order
@@ -100,7 +93,6 @@ embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ tab
           acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o);
           acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
         }
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       }
       count = cnt;
       const float denom = (float)cnt + 1e-9f;           // encoders.py:72

@@ -435,4 +435,20 @@ int tt_inbatch_ce_bwd(const float* q, const float* d, const void* q_bf16, const 
                                  workspace, workspace_bytes, s);
 }
 
+int tt_inbatch_ce_bwd_nparts(int64_t Bq, int64_t Bd, int H, int precision) {
+  if (precision != TT_PREC_BF16 || Bq <= 0 || Bd <= 0 || H <= 0) return 1;
+  return tt::tc_inbatch_bwd_nparts(Bq, Bd, H);
+}
+
+int tt_inbatch_ce_bwd_parts(const void* q_bf16, const void* d_bf16, const float* lse, int64_t Bq, int64_t Bd, int H,
+                            float inv_temperature, int64_t label_offset, float loss_scale, const float* grad_out,
+                            float* dq_parts, int64_t dq_part_stride, float* dd_parts, int64_t dd_part_stride,
+                            void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(q_bf16 && d_bf16 && lse && Bq > 0 && Bd > 0 && H > 0 && (dq_parts || dd_parts), "inbatch_ce_bwd_parts: bad arguments");
+  return tt::tc_inbatch_bwd_parts((const __nv_bfloat16*)q_bf16, (const __nv_bfloat16*)d_bf16, lse, Bq, Bd, H,
+                                  inv_temperature, label_offset, loss_scale, grad_out, dq_parts, dq_part_stride,
+                                  dd_parts, dd_part_stride, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

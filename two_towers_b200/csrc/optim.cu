@@ -12,7 +12,7 @@ namespace tt {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              int64_t n, double lr, double beta1, double beta2, double eps, double wd,
-             const int64_t* __restrict__ step_count, __nv_bfloat16* __restrict__ p_bf16) {
+             int64_t* step_count, __nv_bfloat16* __restrict__ p_bf16) {
   // scalars are formed in double (as Python does in torch.optim) and rounded to fp32 once
   __shared__ float s_neg_step_size, s_sqrt_bc2;
   if (threadIdx.x == 0) {
@@ -38,9 +38,18 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     p[i] = pi; m[i] = mi; v[i] = vi;
     if (p_bf16) p_bf16[i] = __float2bfloat16(pi);
   }
+  // every block has read step_count[0] above; the LAST block to arrive advances the counter, so the
+  // increment needs no extra launch and the whole optimizer step is one graph node.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(step_count + 1), 1ull);
+    if (t == (unsigned long long)gridDim.x - 1ull) {
+      step_count[1] = 0;
+      step_count[0] += 1;
+    }
+  }
 }
-
-__global__ void step_inc_kernel(int64_t* step_count) { *step_count += 1; }
 
 }  // namespace tt
 
@@ -50,14 +59,10 @@ extern "C" int tt_adamw_step(float* param, const float* grad, float* exp_avg, fl
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step_count && n >= 0, "adamw_step: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (n > 0) {
-    int64_t blocks = tt::ceil_div(n, 256);
-    if (blocks > 8 * tt::kNumSMs) blocks = 8 * tt::kNumSMs;
-    tt::adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                      weight_decay, step_count, (__nv_bfloat16*)param_bf16);
-    TT_LAUNCH_CHECK("adamw_kernel");
-  }
-  tt::step_inc_kernel<<<1, 1, 0, s>>>(step_count);
-  TT_LAUNCH_CHECK("step_inc_kernel");
+  int64_t blocks = tt::ceil_div(n > 0 ? n : 1, 256);
+  if (blocks > 8 * tt::kNumSMs) blocks = 8 * tt::kNumSMs;
+  tt::adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                    weight_decay, step_count, (__nv_bfloat16*)param_bf16);
+  TT_LAUNCH_CHECK("adamw_kernel");
   return TT_OK;
 }

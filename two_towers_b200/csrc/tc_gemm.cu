@@ -75,6 +75,7 @@ struct GemmParams {
   const float* mask;
   int ldmask;
   int splits;
+  float* colsum_part;         // nullable [ceil(M/32), N]: per-32-row column sums of the epilogue output (bias grads)
 };
 
 constexpr int kStages = 4;
@@ -94,6 +95,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* acc_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint8_t* stage_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 127) & ~(uintptr_t)127);   // 4 x [32][36] fp32 epilogue staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -151,14 +153,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(acc_bar);                    // accumulator complete
     }
   } else {
-    // epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
+    // epilogue warps 2..5 -> TMEM lane quarters (warp % 4).  Each thread holds one accumulator row;
+    // a 32x32 chunk is transposed through a warp-private shared-memory tile so that global stores
+    // (and the bias / mask loads) are coalesced: lane == column, 128 contiguous bytes per row.
     const int quarter = warp & 3;
-    const int row = m0 + quarter * 32 + lane;
+    float (*T)[36] = reinterpret_cast<float (*)[36]>(stage_tiles + (warp - 2) * (32 * 36 * 4));
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     const bool split = p.splits > 1;
     float* outp = split ? p.C + (size_t)blockIdx.z * p.M * p.N : p.C;
     const int ldo = split ? p.N : p.ldc;
+    const int row0 = m0 + quarter * 32;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -169,39 +174,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (row < p.M) {
-        const int cbase = n0 + c * 32;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int col = cbase + j + u;
-            float x = __uint_as_float(r[j + u]);
-            if (!split && col < p.N) {
-              if (p.bias) x += p.bias[col];
-              if (p.act == 1) x = fmaxf(x, 0.f);
-              if (p.mask) x = (p.mask[(size_t)row * p.ldmask + col] > 0.f) ? x : 0.f;
-            }
-            v[u] = x;
-          }
-          const int col = cbase + j;
-          if (col + 3 < p.N && (ldo & 3) == 0) {
-            if (outp) *reinterpret_cast<float4*>(outp + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
-            if (!split && p.Cb) {
-              uint2 pk = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-              *reinterpret_cast<uint2*>(p.Cb + (size_t)row * p.ldc + col) = pk;
-            }
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (col + u < p.N) {
-                if (outp) outp[(size_t)row * ldo + col + u] = v[u];
-                if (!split && p.Cb) p.Cb[(size_t)row * p.ldc + col + u] = __float2bfloat16(v[u]);
-              }
-          }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(&T[lane][j]) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      __syncwarp();
+      const int col = n0 + c * 32 + lane;
+      const bool col_ok = col < p.N;
+      const float bias_v = (!split && p.bias && col_ok) ? p.bias[col] : 0.f;
+      const int nrows = min(32, p.M - row0);
+      float csum = 0.f;
+      for (int rr = 0; rr < nrows; ++rr) {
+        const int grow = row0 + rr;
+        float v = T[rr][lane];
+        if (!split) {
+          v += bias_v;
+          if (p.act == 1) v = fmaxf(v, 0.f);
+          if (p.mask && col_ok) v = (p.mask[(size_t)grow * p.ldmask + col] > 0.f) ? v : 0.f;
+        }
+        csum += v;
+        if (col_ok) {
+          if (outp) outp[(size_t)grow * ldo + col] = v;
+          if (!split && p.Cb) p.Cb[(size_t)grow * p.ldc + col] = __float2bfloat16(v);
         }
       }
+      if (p.colsum_part && col_ok && nrows > 0) p.colsum_part[(size_t)(row0 >> 5) * p.N + col] = csum;
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -211,7 +209,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <int BN>
 static constexpr size_t gemm_smem_bytes() {
-  return 1024 + kStages * (kATile + BN * BK * 2) + (2 * kStages + 1) * 8 + 16;
+  return 1024 + kStages * (kATile + BN * BK * 2) + (2 * kStages + 1) * 8 + 16 + 128 + 4 * 32 * 36 * 4;
 }
 
 struct TcGemm {
@@ -221,6 +219,8 @@ struct TcGemm {
   float* C = nullptr; __nv_bfloat16* Cb = nullptr; int ldc = 0;
   const float* bias = nullptr; int act = 0; const float* mask = nullptr; int ldmask = 0;
   int splits = 1; float* partial = nullptr;
+  bool defer_reduce = false;             // split-K: leave the partials, the caller reduces them later
+  float* colsum_part = nullptr;          // [ceil(M/32), N] column-sum partials of the output
 };
 
 template <int BN>
@@ -240,12 +240,13 @@ static int launch_gemm(const TcGemm& g, cudaStream_t s) {
   p.splits = g.splits;
   p.C = g.splits > 1 ? g.partial : g.C;
   p.Cb = g.Cb; p.ldc = g.ldc; p.bias = g.bias; p.act = g.act; p.mask = g.mask; p.ldmask = g.ldmask;
+  p.colsum_part = g.colsum_part;
   constexpr size_t smem = gemm_smem_bytes<BN>();
   TT_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), (unsigned)g.splits);
   tc_gemm_kernel<BN><<<grid, kGemmThreads, smem, s>>>(tmA, tmB, p);
   TT_LAUNCH_CHECK("tc_gemm_kernel");
-  if (g.splits > 1) {
+  if (g.splits > 1 && !g.defer_reduce) {
     // fixed-order reduction + epilogue (shared with the fp32 path)
     SgemmArgs a{};
     a.M = g.M; a.N = g.N; a.K = g.K; a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.act = g.act;
@@ -259,12 +260,11 @@ int tc_gemm(const TcGemm& g, cudaStream_t s) {
   TT_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "tc_gemm: bad shape");
   TT_CHECK_ARG(g.splits == 1 || (g.partial && g.C && !g.Cb), "tc_gemm: split-K needs partial + fp32 output only");
   if (g.N <= 64) return launch_gemm<64>(g, s);
-  if (g.N <= 128) return launch_gemm<128>(g, s);
-  return launch_gemm<256>(g, s);
+  return launch_gemm<128>(g, s);            // 128-wide tiles: twice the CTAs of 256-wide ones for N = 256
 }
 
 static int pick_splits(int M, int N, int K) {
-  const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int bn = N <= 64 ? 64 : 128;
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, bn);
   const int total_kb = (K + BK - 1) / BK;
   if (tiles >= kNumSMs / 2 || total_kb <= 4) return 1;
@@ -319,6 +319,83 @@ l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __r
     if (yb) yb[row * H + e] = __float2bfloat16(o);
   }
 }
+// Gradient finalisation: up to 4 independent fixed-order reductions  out[i] = sum_p part[p*n + i]  in one launch
+// (split-K partials of dW1/dW2 and the per-block column sums that become db1/db2).
+struct ReduceJobs {
+  const float* part[4];
+  float* out[4];
+  int nparts[4];
+  int64_t n[4];
+  int njobs;
+};
+__global__ void __launch_bounds__(256) reduce_jobs_kernel(ReduceJobs j) {
+  const int job = blockIdx.y;
+  if (job >= j.njobs) return;
+  const float* part = j.part[job];
+  const int64_t n = j.n[job];
+  const int np = j.nparts[job];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int p = 0; p < np; ++p) v += part[(int64_t)p * n + i];
+    j.out[job][i] = v;
+  }
+}
+
+constexpr int kNormRowsPerBlock = 64;
+// dz = (dy - y (y.dy)) / |z|  -> fp32 + bf16; also per-block column sums of dz (-> db2), H <= 512
+__global__ void __launch_bounds__(256)
+l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_stride, const float* __restrict__ z,
+                         int64_t R, int H, float* __restrict__ dz, __nv_bfloat16* __restrict__ dzb,
+                         float* __restrict__ colsum_part) {
+  __shared__ float s_part[8][512];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float cs[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) cs[k] = 0.f;
+  for (int i = 0; i < kNormRowsPerBlock / 8; ++i) {
+    const int64_t row = (int64_t)blockIdx.x * kNormRowsPerBlock + warp * (kNormRowsPerBlock / 8) + i;
+    if (row >= R) break;
+    const float* zr = z + row * H; const float* gr = dy + row * H;
+    // dy may arrive as `dy_parts` split slices (the loss kernel's per-split partial gradients): sum them in order
+    float g[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int e = lane + 32 * k;
+      float t = 0.f;
+      if (e < H) for (int pp = 0; pp < dy_parts; ++pp) t += gr[(int64_t)pp * dy_stride + e];
+      g[k] = t;
+    }
+    float ss = 0.f, dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int e = lane + 32 * k;
+      if (e < H) { float v = zr[e]; ss = fmaf(v, v, ss); dot = fmaf(v, g[k], dot); }
+    }
+    ss = warp_sum(ss); dot = warp_sum(dot);
+    const float n = sqrtf(ss), denom = fmaxf(n, 1e-12f);
+    const float inner = (n > 1e-12f) ? dot / (denom * denom) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int e = lane + 32 * k;
+      if (e < H) {
+        const float o = (g[k] - zr[e] * inner) / denom;
+        dz[row * H + e] = o;
+        dzb[row * H + e] = __float2bfloat16(o);
+        cs[k] += o;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) if (lane + 32 * k < H) s_part[warp][lane + 32 * k] = cs[k];
+  __syncthreads();
+  for (int e = threadIdx.x; e < H; e += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[w][e];
+    colsum_part[(size_t)blockIdx.x * H + e] = t;
+  }
+}
+
 // dz = (dy - y (y.dy)) / |z|  -> fp32 + bf16
 __global__ void __launch_bounds__(256)
 l2norm_bwd_bf16_kernel(const float* __restrict__ dy, const float* __restrict__ z, int64_t R, int H,
@@ -346,7 +423,7 @@ l2norm_bwd_bf16_kernel(const float* __restrict__ dy, const float* __restrict__ z
 // ---------------------------------------------------------------------------------------
 struct TcMlpPlan {
   int s_dw2, s_dw1;
-  size_t xb, w1b, w2b, h1b, act_f, act_b, partial, colsum, total;
+  size_t xb, w1b, w2b, h1b, act_f, act_b, partial, partial2, cs1, cs2, colsum, total;
 };
 static TcMlpPlan plan_tc_mlp(int64_t R, int E, int H) {
   TcMlpPlan p{};
@@ -358,12 +435,14 @@ static TcMlpPlan plan_tc_mlp(int64_t R, int E, int H) {
   p.h1b = align_up((size_t)R * H * 2);
   p.act_f = align_up((size_t)R * H * 4);
   p.act_b = align_up((size_t)R * H * 2);
-  size_t pa = p.s_dw2 > 1 ? (size_t)p.s_dw2 * H * H * 4 : 0;
-  size_t pb = p.s_dw1 > 1 ? (size_t)p.s_dw1 * H * E * 4 : 0;
-  p.partial = align_up(pa > pb ? pa : pb);
+  p.partial = align_up(p.s_dw2 > 1 ? (size_t)p.s_dw2 * H * H * 4 : 0);
+  p.partial2 = align_up(p.s_dw1 > 1 ? (size_t)p.s_dw1 * H * E * 4 : 0);
+  p.cs1 = align_up((size_t)ceil_div(R, 32) * H * 4);                        // da1 column-sum partials (GEMM epilogue)
+  p.cs2 = align_up((size_t)ceil_div(R, tc::kNormRowsPerBlock) * H * 4);     // dz column-sum partials (normalise bwd)
   p.colsum = align_up((size_t)colsum_partial_rows(R) * H * 4);
-  // bwd: xb, w1b, w2b, h1b, dz (f32+bf16), da1 (f32+bf16), partial, colsum
-  p.total = p.xb + p.w1b + p.w2b + p.h1b + 2 * p.act_f + 2 * p.act_b + p.partial + p.colsum + 1024;
+  // bwd: xb, w1b, w2b, h1b, dz (f32+bf16), da1 (f32+bf16), split partials x2, column-sum partials x2
+  p.total = p.xb + p.w1b + p.w2b + p.h1b + 2 * p.act_f + 2 * p.act_b + p.partial + p.partial2 + p.cs1 + p.cs2 +
+            p.colsum + 1024;
   return p;
 }
 
@@ -372,7 +451,9 @@ size_t tc_mlp_workspace(int64_t R, int E, int H) { return plan_tc_mlp(R, E, H).t
 static bool tc_mlp_supported(int E, int H) { return (E % 8 == 0) && (H % 8 == 0); }
 
 int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t R, int E,
-               int H, float* h1, float* z, float* y, __nv_bfloat16* y_bf16, void* ws, size_t ws_bytes, cudaStream_t s) {
+               int H, float* h1, float* z, float* y, __nv_bfloat16* y_bf16, const __nv_bfloat16* x_bf16,
+               const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16, __nv_bfloat16* h1_bf16, void* ws,
+               size_t ws_bytes, cudaStream_t s) {
   if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0 (E=%d H=%d)", E, H); return TT_ERR_UNSUPPORTED; }
   const TcMlpPlan plan = plan_tc_mlp(R, E, H);
   if (ws == nullptr || ws_bytes < plan.total) { set_error("tc_mlp_fwd: workspace too small (%zu < %zu)", ws_bytes, plan.total); return TT_ERR_WORKSPACE; }
@@ -381,14 +462,22 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
   __nv_bfloat16* w1b = w.take<__nv_bfloat16>((size_t)H * E);
   __nv_bfloat16* w2b = w.take<__nv_bfloat16>((size_t)H * H);
   __nv_bfloat16* h1b = w.take<__nv_bfloat16>((size_t)R * H);
-  int rc = tc::cast3(x, xb, R * E, w1, w1b, (int64_t)H * E, w2, w2b, (int64_t)H * H, s);
-  if (rc) return rc;
+  int rc = TT_OK;
+  if (!x_bf16 || !w1_bf16 || !w2_bf16) {       // only the operands without a caller-provided shadow are converted
+    rc = tc::cast3(x_bf16 ? nullptr : x, xb, x_bf16 ? 0 : R * E, w1_bf16 ? nullptr : w1, w1b, w1_bf16 ? 0 : (int64_t)H * E,
+                   w2_bf16 ? nullptr : w2, w2b, w2_bf16 ? 0 : (int64_t)H * H, s);
+    if (rc) return rc;
+  }
+  const __nv_bfloat16* xa = x_bf16 ? x_bf16 : xb;
+  const __nv_bfloat16* w1a = w1_bf16 ? w1_bf16 : w1b;
+  const __nv_bfloat16* w2a = w2_bf16 ? w2_bf16 : w2b;
+  if (h1_bf16) h1b = h1_bf16;
   tc::TcGemm g{};
-  g.M = (int)R; g.N = H; g.K = E; g.A = xb; g.a_mn = 0; g.B = w1b; g.b_mn = 0;
+  g.M = (int)R; g.N = H; g.K = E; g.A = xa; g.a_mn = 0; g.B = w1a; g.b_mn = 0;
   g.C = h1; g.Cb = h1b; g.ldc = H; g.bias = b1; g.act = 1;
   rc = tc::tc_gemm(g, s); if (rc) return rc;
   g = tc::TcGemm{};
-  g.M = (int)R; g.N = H; g.K = H; g.A = h1b; g.a_mn = 0; g.B = w2b; g.b_mn = 0;
+  g.M = (int)R; g.N = H; g.K = H; g.A = h1b; g.a_mn = 0; g.B = w2a; g.b_mn = 0;
   g.C = z; g.ldc = H; g.bias = b2;
   rc = tc::tc_gemm(g, s); if (rc) return rc;
   tc::l2norm_fwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(z, R, H, y, y_bf16);
@@ -397,9 +486,13 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
 }
 
 int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1, const float* z,
-               int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2, float* db2, void* ws,
-               size_t ws_bytes, cudaStream_t s) {
+               int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2, float* db2,
+               const __nv_bfloat16* x_bf16, const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16,
+               const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride, void* ws, size_t ws_bytes,
+               cudaStream_t s) {
   if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0"); return TT_ERR_UNSUPPORTED; }
+  if (dy_parts < 1) dy_parts = 1;
+  if (dy_parts > 1 && H > 512) { set_error("tc_mlp_bwd: split dy needs H <= 512"); return TT_ERR_UNSUPPORTED; }
   const TcMlpPlan plan = plan_tc_mlp(R, E, H);
   if (ws == nullptr || ws_bytes < plan.total) { set_error("tc_mlp_bwd: workspace too small (%zu < %zu)", ws_bytes, plan.total); return TT_ERR_WORKSPACE; }
   Workspace w(ws, ws_bytes);
@@ -412,34 +505,65 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   __nv_bfloat16* dzb = w.take<__nv_bfloat16>((size_t)R * H);
   __nv_bfloat16* da1b = w.take<__nv_bfloat16>((size_t)R * H);
   float* partial = plan.partial ? w.take<float>(plan.partial / 4) : nullptr;
+  float* partial2 = plan.partial2 ? w.take<float>(plan.partial2 / 4) : nullptr;
+  float* cs1 = w.take<float>(plan.cs1 / 4);
+  float* cs2 = w.take<float>(plan.cs2 / 4);
   float* cpart = w.take<float>(plan.colsum / 4);
-  int rc = tc::cast3(x, xb, R * E, w1, w1b, (int64_t)H * E, w2, w2b, (int64_t)H * H, s); if (rc) return rc;
-  rc = tc::cast3(h1, h1b, R * H, nullptr, nullptr, 0, nullptr, nullptr, 0, s); if (rc) return rc;
-  tc::l2norm_bwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(dy, z, R, H, dz, dzb);
-  TT_LAUNCH_CHECK("l2norm_bwd_bf16_kernel");
+  int rc = TT_OK;
+  if (!x_bf16 || !w1_bf16 || !w2_bf16) {
+    rc = tc::cast3(x_bf16 ? nullptr : x, xb, x_bf16 ? 0 : R * E, w1_bf16 ? nullptr : w1, w1b, w1_bf16 ? 0 : (int64_t)H * E,
+                   w2_bf16 ? nullptr : w2, w2b, w2_bf16 ? 0 : (int64_t)H * H, s);
+    if (rc) return rc;
+  }
+  if (!h1_bf16) { rc = tc::cast3(h1, h1b, R * H, nullptr, nullptr, 0, nullptr, nullptr, 0, s); if (rc) return rc; }
+  const __nv_bfloat16* xa = x_bf16 ? x_bf16 : xb;
+  const __nv_bfloat16* w1a = w1_bf16 ? w1_bf16 : w1b;
+  const __nv_bfloat16* w2a = w2_bf16 ? w2_bf16 : w2b;
+  const __nv_bfloat16* h1a = h1_bf16 ? h1_bf16 : h1b;
+  const bool fused_cs = H <= 512;
+  const int nblk2 = (int)ceil_div(R, tc::kNormRowsPerBlock);
+  if (fused_cs) {
+    tc::l2norm_bwd_colsum_kernel<<<(unsigned)nblk2, 256, 0, s>>>(dy, dy_parts, dy_part_stride, z, R, H, dz, dzb, cs2);
+    TT_LAUNCH_CHECK("l2norm_bwd_colsum_kernel");
+  } else {
+    tc::l2norm_bwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(dy, z, R, H, dz, dzb);
+    TT_LAUNCH_CHECK("l2norm_bwd_bf16_kernel");
+    rc = colsum(dz, R, H, H, db2, cpart, s); if (rc) return rc;
+  }
   tc::TcGemm g{};
   // dw2[H,H] = dz^T h1 : A = dz stored [K=R, M=H] (MN-major), B = h1 stored [K=R, N=H] (MN-major)
-  g.M = H; g.N = H; g.K = (int)R; g.A = dzb; g.a_mn = 1; g.B = h1b; g.b_mn = 1; g.C = dw2; g.ldc = H;
-  g.splits = plan.s_dw2; g.partial = partial;
+  g.M = H; g.N = H; g.K = (int)R; g.A = dzb; g.a_mn = 1; g.B = h1a; g.b_mn = 1; g.C = dw2; g.ldc = H;
+  g.splits = plan.s_dw2; g.partial = partial; g.defer_reduce = true;
   rc = tc::tc_gemm(g, s); if (rc) return rc;
-  rc = colsum(dz, R, H, H, db2, cpart, s); if (rc) return rc;
   // da1[R,H] = (dz w2) * (h1 > 0) : A = dz [M=R,K=H] K-major, B = w2 stored [K=H_out, N=H_in] (MN-major)
   g = tc::TcGemm{};
-  g.M = (int)R; g.N = H; g.K = H; g.A = dzb; g.a_mn = 0; g.B = w2b; g.b_mn = 1; g.C = da1; g.Cb = da1b; g.ldc = H;
-  g.mask = h1; g.ldmask = H;
+  g.M = (int)R; g.N = H; g.K = H; g.A = dzb; g.a_mn = 0; g.B = w2a; g.b_mn = 1; g.C = da1; g.Cb = da1b; g.ldc = H;
+  g.mask = h1; g.ldmask = H; g.colsum_part = cs1;
   rc = tc::tc_gemm(g, s); if (rc) return rc;
   // dw1[H,E] = da1^T x
   g = tc::TcGemm{};
-  g.M = H; g.N = E; g.K = (int)R; g.A = da1b; g.a_mn = 1; g.B = xb; g.b_mn = 1; g.C = dw1; g.ldc = E;
-  g.splits = plan.s_dw1; g.partial = partial;
+  g.M = H; g.N = E; g.K = (int)R; g.A = da1b; g.a_mn = 1; g.B = xa; g.b_mn = 1; g.C = dw1; g.ldc = E;
+  g.splits = plan.s_dw1; g.partial = partial2; g.defer_reduce = true;
   rc = tc::tc_gemm(g, s); if (rc) return rc;
-  rc = colsum(da1, R, H, H, db1, cpart, s); if (rc) return rc;
   if (dx) {
     // dx[R,E] = da1 w1 : A = da1 K-major, B = w1 stored [K=H, N=E] (MN-major)
     g = tc::TcGemm{};
-    g.M = (int)R; g.N = E; g.K = H; g.A = da1b; g.a_mn = 0; g.B = w1b; g.b_mn = 1; g.C = dx; g.ldc = E;
+    g.M = (int)R; g.N = E; g.K = H; g.A = da1b; g.a_mn = 0; g.B = w1a; g.b_mn = 1; g.C = dx; g.ldc = E;
     rc = tc::tc_gemm(g, s); if (rc) return rc;
   }
+  // one launch finishes every reduction of this call in a fixed order: dW2, dW1 split-K partials, db1, db2
+  tc::ReduceJobs jobs{};
+  int nj = 0;
+  auto add = [&](const float* part, int np, int64_t n, float* out) {
+    jobs.part[nj] = part; jobs.nparts[nj] = np; jobs.n[nj] = n; jobs.out[nj] = out; ++nj;
+  };
+  if (plan.s_dw2 > 1) add(partial, plan.s_dw2, (int64_t)H * H, dw2);
+  if (plan.s_dw1 > 1) add(partial2, plan.s_dw1, (int64_t)H * E, dw1);
+  add(cs1, (int)ceil_div(R, 32), H, db1);
+  if (fused_cs) add(cs2, nblk2, H, db2);
+  jobs.njobs = nj;
+  tc::reduce_jobs_kernel<<<dim3(64, nj), 256, 0, s>>>(jobs);
+  TT_LAUNCH_CHECK("reduce_jobs_kernel");
   return TT_OK;
 }
 

@@ -38,6 +38,12 @@ constexpr int CE_BN = 64;           // Y rows per tile (UMMA N of the S product,
 constexpr int CE_THREADS = 192;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2, inputs are bounded (<= 0 after max-subtraction)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
@@ -48,7 +54,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  int64_t Bd, int H, float inv_temp, int64_t label_offset, int tiles_per_split,
                  float* __restrict__ part_ml, float* __restrict__ pos_logit) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // stays in the shared address space
   const int kq = H / 64;                                  // 64-wide K blocks
   const uint32_t q_bytes = (uint32_t)CE_BM * H * 2, d_bytes = (uint32_t)CE_BN * H * 2;
   uint8_t* q_tile = base;
@@ -96,18 +102,20 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(CE_BM, CE_BN, 0, 0);
+      const uint64_t dq0 = umma_desc_kmajor(smem_u32(q_tile), 0);
+      const uint64_t dd0 = umma_desc_kmajor(smem_u32(d_tiles), 0);
       mbar_wait(q_bar, 0);
       for (int i = 0; i < nt; ++i) {
         const int s = i % FWD_STAGES, b = i & 1;
         mbar_wait(&d_full[s], (i / FWD_STAGES) & 1);
         mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t qa = smem_u32(q_tile), da = smem_u32(d_tiles + s * d_bytes);
+        const uint64_t dd = dd0 + (uint64_t)((s * d_bytes) >> 4);
         for (int kb = 0; kb < kq; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_s + b * CE_BN, umma_desc_kmajor(qa + kb * (CE_BM * 128), k),
-                      umma_desc_kmajor(da + kb * (CE_BN * 128), k), idesc, (kb | k) != 0);
+            umma_bf16(tmem_s + b * CE_BN, dq0 + (uint64_t)(kb * (CE_BM * 128 / 16) + k * 2),
+                      dd + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc, (kb | k) != 0);
         umma_commit(&d_empty[s]);
         umma_commit(&s_full[b]);
       }
@@ -131,25 +139,36 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);             // TMEM buffer may be overwritten
+      if (y0 + CE_BN > Bd) {                               // ragged last tile: padded columns -> -inf
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (y0 + j >= Bd) r0[j] = 0xff800000u;
+          if (y0 + 32 + j >= Bd) r1[j] = 0xff800000u;
+        }
+      }
+      const int64_t pj = pcol - y0;                        // this row's positive column inside the tile
+      if (pj >= 0 && pj < CE_BN && row < Bq) {
+        float pv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j == (int)pj) pv = __uint_as_float(r0[j]);
+          if (j + 32 == (int)pj) pv = __uint_as_float(r1[j]);
+        }
+        pos_logit[row] = pv * inv_temp;
+      }
       float tmax = -CUDART_INF_F;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float v0 = (y0 + j < Bd) ? __uint_as_float(r0[j]) : -CUDART_INF_F;
-        float v1 = (y0 + 32 + j < Bd) ? __uint_as_float(r1[j]) : -CUDART_INF_F;
-        r0[j] = __float_as_uint(v0); r1[j] = __float_as_uint(v1);
-        tmax = fmaxf(tmax, fmaxf(v0, v1));
-        if (y0 + j == pcol && row < Bq) pos_logit[row] = v0 * inv_temp;
-        if (y0 + 32 + j == pcol && row < Bq) pos_logit[row] = v1 * inv_temp;
-      }
+      for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])));
       const float mnew = fmaxf(m, tmax);
       const float mc = mnew * c;
-      float sum = 0.f;
+      float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        sum += exp2f(fmaf(__uint_as_float(r0[j]), c, -mc));
-        sum += exp2f(fmaf(__uint_as_float(r1[j]), c, -mc));
+        sum0 += fast_exp2(fmaf(__uint_as_float(r0[j]), c, -mc));
+        sum1 += fast_exp2(fmaf(__uint_as_float(r1[j]), c, -mc));
       }
-      l = l * exp2f((m - mnew) * c) + sum;
+      const float sum = sum0 + sum1;
+      l = l * fast_exp2((m - mnew) * c) + sum;
       m = mnew;
     }
     if (row < Bq && nt > 0) {
@@ -163,17 +182,30 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------
-// backward
+// backward: dQ and dD passes in ONE launch (blockIdx.z selects the pass)
 // ---------------------------------------------------------------------------------------
 constexpr int BWD_STAGES = 3;
 
-template <bool COL_LSE>
-__global__ void __launch_bounds__(CE_THREADS, 1)
-tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                 const float* __restrict__ lse, int64_t Bx, int64_t By, int H, float inv_temp, int64_t label_offset,
-                 int tiles_per_split, const float* __restrict__ grad_out, float coef, float* __restrict__ out) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+struct BwdParams {
+  const float* lse;            // [Bq] row logsumexp of the logits (natural log)
+  int64_t Bq, Bd;
+  int H;
+  float inv_temp;
+  int64_t label_offset;
+  int tiles_per_split[2];      // Y tiles handled by one split, per pass
+  const float* grad_out;       // nullable device scalar
+  float coef;                  // loss_scale / temperature
+  float* out[2];               // pass outputs: [nsplit][Bx][H] partials (slice stride below) or the final tensor
+  int64_t part_stride[2];      // elements between consecutive split slices
+};
+
+// X rows = this CTA's 128 output rows, Y = streamed 64-row tiles.
+//   COL == false: X = Q, Y = D, lse indexed by X row,  positive at col == row + off   (dQ)
+//   COL == true : X = D, Y = Q, lse indexed by Y row,  positive at row == col + off   (dD)
+template <bool COL>
+__device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtensorMap* tmY, const BwdParams& p,
+                                            int64_t Bx, int64_t By, int tiles_per_split, float* out, uint8_t* base) {
+  const int H = p.H;
   const int kq = H / 64;
   const uint32_t x_bytes = (uint32_t)CE_BM * H * 2, y_bytes = (uint32_t)CE_BN * H * 2;
   constexpr uint32_t p_bytes = CE_BM * CE_BN * 2;         // 16 KB, K-major 128 rows x 64
@@ -199,7 +231,7 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int nt = max(0, t_end - t_beg);
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(tmX); tma_prefetch_desc(tmY);
     mbar_init(x_bar, 1);
     for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
@@ -220,31 +252,35 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(x_bar, x_bytes);
-      for (int kb = 0; kb < kq; ++kb) tma_load_2d(x_tile + kb * (CE_BM * 128), &tmX, x_bar, kb * 64, (int)x0);
+      for (int kb = 0; kb < kq; ++kb) tma_load_2d(x_tile + kb * (CE_BM * 128), tmX, x_bar, kb * 64, (int)x0);
       for (int i = 0; i < nt; ++i) {
         const int s = i % BWD_STAGES;
         mbar_wait(&y_empty[s], ((i / BWD_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&y_full[s], y_bytes);
         uint8_t* yt = y_tiles + s * y_bytes;
-        for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (CE_BN * 128), &tmY, &y_full[s], kb * 64, (t_beg + i) * CE_BN);
+        for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (CE_BN * 128), tmY, &y_full[s], kb * 64, (t_beg + i) * CE_BN);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && nt > 0) {
       const uint32_t idesc_s = umma_idesc_bf16(CE_BM, CE_BN, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(CE_BM, H, 0, 1);     // B = Y tile read MN-major
-      const uint32_t xa = smem_u32(x_tile);
+      // descriptors differ only in the (address >> 4) field: build once, then add small constants
+      const uint64_t dx0 = umma_desc_kmajor(smem_u32(x_tile), 0);
+      const uint64_t dp0 = umma_desc_kmajor(smem_u32(p_tiles), 0);
+      const uint64_t dyk0 = umma_desc_kmajor(smem_u32(y_tiles), 0);
+      const uint64_t dym0 = umma_desc_mnmajor(smem_u32(y_tiles), 0, CE_BN * 128);
       auto issue_s = [&](int i) {
         const int s = i % BWD_STAGES, b = i & 1;
         mbar_wait(&y_full[s], (i / BWD_STAGES) & 1);
         mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t ya = smem_u32(y_tiles + s * y_bytes);
+        const uint64_t dy = dyk0 + (uint64_t)((s * y_bytes) >> 4);
         for (int kb = 0; kb < kq; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_s + b * CE_BN, umma_desc_kmajor(xa + kb * (CE_BM * 128), k),
-                      umma_desc_kmajor(ya + kb * (CE_BN * 128), k), idesc_s, (kb | k) != 0);
+            umma_bf16(tmem_s + b * CE_BN, dx0 + (uint64_t)(kb * (CE_BM * 128 / 16) + k * 2),
+                      dy + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc_s, (kb | k) != 0);
         umma_commit(&s_full[b]);
       };
       mbar_wait(x_bar, 0);
@@ -254,10 +290,11 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int s = i % BWD_STAGES, b = i & 1;
         mbar_wait(&p_full[b], (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t pa = smem_u32(p_tiles + b * p_bytes), ya = smem_u32(y_tiles + s * y_bytes);
+        const uint64_t dp = dp0 + (uint64_t)((b * p_bytes) >> 4);
+        const uint64_t dy = dym0 + (uint64_t)((s * y_bytes) >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_o, umma_desc_kmajor(pa, k), umma_desc_mnmajor(ya, k, CE_BN * 128), idesc_o, (i | k) != 0);
+          umma_bf16(tmem_o, dp + (uint64_t)(k * 2), dy + (uint64_t)(k * (2048 / 16)), idesc_o, (i | k) != 0);
         umma_commit(&p_empty[b]);
         umma_commit(&y_empty[s]);
       }
@@ -267,11 +304,18 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int quarter = warp & 3;
     const int lrow = quarter * 32 + lane;                  // row inside the tile == TMEM lane
     const int64_t row = x0 + lrow;
-    const float c = inv_temp * kLog2e;
-    const float row_lse = (!COL_LSE && row < Bx) ? lse[row] * kLog2e : 0.f;
+    const float c = p.inv_temp * kLog2e;
+    const float row_lse = (!COL && row < Bx) ? p.lse[row] * kLog2e : 0.f;
+    // Y tiles that can hold a positive of one of this CTA's rows (CTA-uniform band)
+    const int64_t band_lo = COL ? x0 - p.label_offset : x0 + p.label_offset;
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
       const int64_t y0 = (int64_t)(t_beg + i) * CE_BN;
+      float cl0 = 0.f, cl1 = 0.f;                           // column lse (COL mode): lane holds columns lane, lane+32
+      if (COL) {
+        cl0 = (y0 + lane < By) ? __ldg(p.lse + y0 + lane) * kLog2e : CUDART_INF_F;
+        cl1 = (y0 + 32 + lane < By) ? __ldg(p.lse + y0 + 32 + lane) * kLog2e : CUDART_INF_F;
+      }
       mbar_wait(&s_full[b], (i >> 1) & 1);
       tc_fence_after();
       uint32_t r0[32], r1[32];
@@ -282,45 +326,49 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);
-      // P = exp2(S*c - lse*log2e) - [positive]; packed to bf16 pairs in place
-      uint32_t pk[32];
+      // P = exp2(S*c - lse*log2e); ragged columns get lse = +inf -> P = 0 (row mode: masked below)
+      float pv[64];
 #pragma unroll
-      for (int j = 0; j < 64; j += 2) {
-        float pv[2];
+      for (int j = 0; j < 32; ++j) {
+        const float l0 = COL ? __shfl_sync(0xffffffffu, cl0, j) : row_lse;
+        const float l1 = COL ? __shfl_sync(0xffffffffu, cl1, j) : row_lse;
+        pv[j] = fast_exp2(fmaf(__uint_as_float(r0[j]), c, -l0));
+        pv[32 + j] = fast_exp2(fmaf(__uint_as_float(r1[j]), c, -l1));
+      }
+      if (!COL && y0 + CE_BN > By) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int jj = j + u;
-          const int64_t col = y0 + jj;
-          const float sv = __uint_as_float(jj < 32 ? r0[jj] : r1[jj - 32]);
-          float p = 0.f;
-          if (col < By && row < Bx) {
-            const float lv = COL_LSE ? __ldg(lse + col) * kLog2e : row_lse;
-            p = exp2f(fmaf(sv, c, -lv));
-            const bool pos = COL_LSE ? (row == col + label_offset) : (col == row + label_offset);
-            if (pos) p -= 1.0f;
-          }
-          pv[u] = p;
+        for (int j = 0; j < 64; ++j)
+          if (y0 + j >= By) pv[j] = 0.f;
+      }
+      if (y0 + CE_BN > band_lo && y0 < band_lo + CE_BM) {   // tile intersects the diagonal band
+        const int64_t pj = (COL ? row - p.label_offset : row + p.label_offset) - y0;
+        if (pj >= 0 && pj < CE_BN && y0 + pj < By) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) pv[j] -= (j == (int)pj) ? 1.0f : 0.0f;     // select, keeps pv[] in registers
         }
-        pk[j >> 1] = pack_bf16x2(pv[0], pv[1]);
       }
       mbar_wait(&p_empty[b], ((i >> 1) & 1) ^ 1);          // O-GEMM(i-2) has finished reading this P buffer
       uint8_t* prow = p_tiles + b * p_bytes + lrow * 128;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {                      // 8 x 16-byte chunks, 128B swizzle: chunk ^= row & 7
-        uint4 v = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        uint4 v = make_uint4(pack_bf16x2(pv[8 * ch + 0], pv[8 * ch + 1]), pack_bf16x2(pv[8 * ch + 2], pv[8 * ch + 3]),
+                             pack_bf16x2(pv[8 * ch + 4], pv[8 * ch + 5]), pack_bf16x2(pv[8 * ch + 6], pv[8 * ch + 7]));
         *reinterpret_cast<uint4*>(prow + ((ch ^ (lrow & 7)) << 4)) = v;
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
     }
-    // final: O (TMEM) -> global, scaled by grad * loss_scale / temperature
-    const float scale = coef * (grad_out ? *grad_out : 1.0f);
-    float* o = out + (int64_t)blockIdx.y * Bx * H;
+    // final: O (TMEM) -> registers -> warp-private smem transpose -> 128-byte coalesced global stores
+    const float scale = p.coef * (p.grad_out ? *p.grad_out : 1.0f);
     if (nt > 0) {
       mbar_wait(o_full, 0);
       tc_fence_after();
     }
+    float* T = reinterpret_cast<float*>(p_tiles + (warp - 2) * (32 * 36 * 4));      // [32][36], P buffers are free now
+    const int64_t row0 = x0 + quarter * 32;
+    const int nrows = (int)min((int64_t)32, Bx - row0);
+    float* orow = out + row0 * H + lane;
     for (int cb = 0; cb < H / 32; ++cb) {
       uint32_t r[32];
       if (nt > 0) {
@@ -330,14 +378,18 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (row < Bx) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v = make_float4(__uint_as_float(r[j]) * scale, __uint_as_float(r[j + 1]) * scale,
-                                 __uint_as_float(r[j + 2]) * scale, __uint_as_float(r[j + 3]) * scale);
-          *reinterpret_cast<float4*>(o + row * H + cb * 32 + j) = v;
-        }
-      }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(&T[lane * 36 + j]) = make_float4(__uint_as_float(r[j]) * scale, __uint_as_float(r[j + 1]) * scale,
+                                                                    __uint_as_float(r[j + 2]) * scale, __uint_as_float(r[j + 3]) * scale);
+      __syncwarp();
+      float v[32];
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) v[rr] = T[rr * 36 + lane];
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr)
+        if (rr < nrows) orow[(int64_t)rr * H + cb * 32] = v[rr];
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -345,14 +397,27 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+__global__ void __launch_bounds__(CE_THREADS, 1)
+tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmQ64,
+                 const __grid_constant__ CUtensorMap tmD128, const __grid_constant__ CUtensorMap tmD64, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  const int pass = blockIdx.z;
+  const int64_t Bx = pass == 0 ? p.Bq : p.Bd, By = pass == 0 ? p.Bd : p.Bq;
+  if ((int64_t)blockIdx.x * CE_BM >= Bx || p.out[pass] == nullptr) return;   // CTA-uniform: nothing to do for this pass
+  float* out = p.out[pass] + (int64_t)blockIdx.y * p.part_stride[pass];
+  if (pass == 0) ce_bwd_body<false>(&tmQ128, &tmD64, p, Bx, By, p.tiles_per_split[0], out, base);
+  else           ce_bwd_body<true>(&tmD128, &tmQ64, p, Bx, By, p.tiles_per_split[1], out, base);
+}
+
 static size_t fwd_smem(int H) { return 1024 + (size_t)CE_BM * H * 2 + FWD_STAGES * (size_t)CE_BN * H * 2 + 16 * 8 + 16; }
 static size_t bwd_smem(int H) {
   return 1024 + (size_t)CE_BM * H * 2 + BWD_STAGES * (size_t)CE_BN * H * 2 + 2 * (size_t)CE_BM * CE_BN * 2 + 20 * 8 + 16;
 }
 
-static int pick_split(int64_t Bx, int64_t By) {
-  const int64_t xt = ceil_div(Bx, CE_BM), yt = ceil_div(By, CE_BN);
-  int64_t s = kNumSMs / xt;                 // one wave
+static int pick_split(int64_t xtiles, int64_t By) {
+  const int64_t yt = ceil_div(By, CE_BN);
+  int64_t s = kNumSMs / (xtiles > 0 ? xtiles : 1);                     // one wave
   if (s > yt) s = yt;
   if (s > 32) s = 32;
   if (s < 1) s = 1;
@@ -364,18 +429,24 @@ static int pick_split(int64_t Bx, int64_t By) {
 
 static bool tc_ce_supported(int H) { return H % 64 == 0 && H >= 64 && H <= 256; }
 
-struct TcCePlan { int ns_f, ns_q, ns_d; size_t qb, db, ml, pos, partial, total; };
+// splits: forward uses its own; backward uses ONE split count for both passes (they share a launch)
+static int fwd_splits(int64_t Bq, int64_t Bd) { return tc::pick_split(ceil_div(Bq, tc::CE_BM), Bd); }
+static int bwd_splits(int64_t Bq, int64_t Bd) {
+  const int64_t xt = ceil_div(Bq, tc::CE_BM) + ceil_div(Bd, tc::CE_BM);
+  const int a = tc::pick_split(xt, Bd), b = tc::pick_split(xt, Bq);
+  return a < b ? a : b;
+}
+
+struct TcCePlan { int ns_f, ns_b; size_t qb, db, ml, pos, partial, total; };
 static TcCePlan plan_tc_ce(int64_t Bq, int64_t Bd, int H) {
   TcCePlan p{};
-  p.ns_f = tc::pick_split(Bq, Bd);
-  p.ns_q = tc::pick_split(Bq, Bd);
-  p.ns_d = tc::pick_split(Bd, Bq);
+  p.ns_f = fwd_splits(Bq, Bd);
+  p.ns_b = bwd_splits(Bq, Bd);
   p.qb = align_up((size_t)Bq * H * 2);
   p.db = align_up((size_t)Bd * H * 2);
   p.ml = align_up((size_t)p.ns_f * Bq * 2 * 4);
   p.pos = align_up((size_t)Bq * 4);
-  size_t a = p.ns_q > 1 ? (size_t)p.ns_q * Bq * H * 4 : 0, b = p.ns_d > 1 ? (size_t)p.ns_d * Bd * H * 4 : 0;
-  p.partial = align_up(a > b ? a : b);
+  p.partial = align_up(p.ns_b > 1 ? (size_t)p.ns_b * (Bq + Bd) * H * 4 : 0);
   p.total = p.qb + p.db + p.ml + p.pos + p.partial + 1024;
   return p;
 }
@@ -386,6 +457,8 @@ size_t tc_inbatch_workspace(int64_t Bq, int64_t Bd, int H) {
   size_t t = plan_tc_ce(Bq, Bd, H).total;
   return t > f ? t : f;
 }
+
+int tc_inbatch_bwd_nparts(int64_t Bq, int64_t Bd, int H) { return tc_ce_supported(H) ? bwd_splits(Bq, Bd) : 1; }
 
 namespace tc {
 int cast3_public(const float* a, __nv_bfloat16* ab, int64_t na, const float* b, __nv_bfloat16* bb, int64_t nb, cudaStream_t s);
@@ -423,23 +496,49 @@ int tc_inbatch_fwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, 
   return inbatch_finalize(part_ml, pos, plan.ns_f, Bq, inv_temp, loss_scale, lse, loss, pos_mean, nullptr, s);
 }
 
-template <bool COL>
-static int launch_tc_bwd(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* lse, int64_t Bx, int64_t By, int H,
-                         float inv_temp, int64_t off, int nsplit, const float* grad_out, float coef, float* out,
-                         float* partial, cudaStream_t s) {
-  CUtensorMap tmX, tmY;
-  int rc = tc::make_tmap_bf16(&tmX, X, (uint64_t)Bx, (uint64_t)H, tc::CE_BM); if (rc) return rc;
-  rc = tc::make_tmap_bf16(&tmY, Y, (uint64_t)By, (uint64_t)H, tc::CE_BN); if (rc) return rc;
-  const int yt = (int)ceil_div(By, tc::CE_BN);
-  const int per = (int)ceil_div(yt, nsplit);
+// One launch for both gradients.  out_q / out_d receive nsplit slices (stride_q / stride_d elements apart);
+// a nullptr output skips that pass.  nsplit must equal tc_inbatch_bwd_nparts().
+static int launch_tc_bwd(const __nv_bfloat16* qa, const __nv_bfloat16* da, const float* lse, int64_t Bq, int64_t Bd, int H,
+                         float inv_temp, int64_t off, int nsplit, const float* grad_out, float coef, float* out_q,
+                         int64_t stride_q, float* out_d, int64_t stride_d, cudaStream_t s) {
+  CUtensorMap tmQ128, tmQ64, tmD128, tmD64;
+  int rc = tc::make_tmap_bf16(&tmQ128, qa, (uint64_t)Bq, (uint64_t)H, tc::CE_BM); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmQ64, qa, (uint64_t)Bq, (uint64_t)H, tc::CE_BN); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmD128, da, (uint64_t)Bd, (uint64_t)H, tc::CE_BM); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmD64, da, (uint64_t)Bd, (uint64_t)H, tc::CE_BN); if (rc) return rc;
+  tc::BwdParams p{};
+  p.lse = lse; p.Bq = Bq; p.Bd = Bd; p.H = H; p.inv_temp = inv_temp; p.label_offset = off;
+  p.tiles_per_split[0] = (int)ceil_div(ceil_div(Bd, tc::CE_BN), nsplit);
+  p.tiles_per_split[1] = (int)ceil_div(ceil_div(Bq, tc::CE_BN), nsplit);
+  p.grad_out = grad_out; p.coef = coef;
+  p.out[0] = out_q; p.out[1] = out_d; p.part_stride[0] = stride_q; p.part_stride[1] = stride_d;
   const size_t smem = tc::bwd_smem(H);
-  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel<COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(Bx, tc::CE_BM), (unsigned)nsplit);
-  float* dst = nsplit > 1 ? partial : out;
-  tc::tc_ce_bwd_kernel<COL><<<grid, tc::CE_THREADS, smem, s>>>(tmX, tmY, lse, Bx, By, H, inv_temp, off, per, grad_out, coef, dst);
+  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t xq = ceil_div(Bq, tc::CE_BM), xd = ceil_div(Bd, tc::CE_BM);
+  // pass 0 = dQ, pass 1 = dD; a missing output shrinks the grid to the other pass
+  if (out_q && out_d) {
+    dim3 grid((unsigned)(xq > xd ? xq : xd), (unsigned)nsplit, 2);
+    tc::tc_ce_bwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ128, tmQ64, tmD128, tmD64, p);
+  } else if (out_q) {
+    dim3 grid((unsigned)xq, (unsigned)nsplit, 1);
+    tc::tc_ce_bwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ128, tmQ64, tmD128, tmD64, p);
+  } else {
+    // only dD: run it as "pass 0" of a swapped problem is not possible (lse orientation), so launch z=2 and let pass 0 exit
+    p.Bq = Bq; p.out[0] = nullptr;
+    dim3 grid((unsigned)xd, (unsigned)nsplit, 2);
+    tc::tc_ce_bwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ128, tmQ64, tmD128, tmD64, p);
+  }
   TT_LAUNCH_CHECK("tc_ce_bwd_kernel");
-  if (nsplit > 1) return split_sum(partial, nsplit, Bx * H, out, s);
   return TT_OK;
+}
+
+// Partial-slice variant used by the fused trainer: the consumer (normalise-backward) sums the slices.
+int tc_inbatch_bwd_parts(const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16, const float* lse, int64_t Bq, int64_t Bd,
+                         int H, float inv_temp, int64_t label_offset, float loss_scale, const float* grad_out,
+                         float* dq_parts, int64_t stride_q, float* dd_parts, int64_t stride_d, cudaStream_t s) {
+  if (!tc_ce_supported(H) || !q_bf16 || !d_bf16) { set_error("tc_inbatch_bwd_parts: needs bf16 operands and H %% 64 == 0, H <= 256"); return TT_ERR_UNSUPPORTED; }
+  return launch_tc_bwd(q_bf16, d_bf16, lse, Bq, Bd, H, inv_temp, label_offset, bwd_splits(Bq, Bd), grad_out,
+                       loss_scale * inv_temp, dq_parts, stride_q, dd_parts, stride_d, s);
 }
 
 int tc_inbatch_bwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16,
@@ -464,14 +563,15 @@ int tc_inbatch_bwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, 
   const __nv_bfloat16* qa = q_bf16 ? q_bf16 : qb;
   const __nv_bfloat16* da = d_bf16 ? d_bf16 : db;
   const float coef = loss_scale * inv_temp;
-  if (dq) {
-    rc = launch_tc_bwd<false>(qa, da, lse, Bq, Bd, H, inv_temp, label_offset, plan.ns_q, grad_out, coef, dq, partial, s);
-    if (rc) return rc;
-  }
-  if (dd) {
-    rc = launch_tc_bwd<true>(da, qa, lse, Bd, Bq, H, inv_temp, label_offset, plan.ns_d, grad_out, coef, dd, partial, s);
-    if (rc) return rc;
-  }
+  const int ns = plan.ns_b;
+  if (ns == 1) return launch_tc_bwd(qa, da, lse, Bq, Bd, H, inv_temp, label_offset, 1, grad_out, coef, dq, 0, dd, 0, s);
+  float* pq = partial;                                   // [ns][Bq][H]
+  float* pd = partial + (size_t)ns * Bq * H;             // [ns][Bd][H]
+  rc = launch_tc_bwd(qa, da, lse, Bq, Bd, H, inv_temp, label_offset, ns, grad_out, coef, dq ? pq : nullptr, Bq * H,
+                     dd ? pd : nullptr, Bd * H, s);
+  if (rc) return rc;
+  if (dq) { rc = split_sum(pq, ns, Bq * H, dq, s); if (rc) return rc; }
+  if (dd) { rc = split_sum(pd, ns, Bd * H, dd, s); if (rc) return rc; }
   return TT_OK;
 }
 

@@ -9,10 +9,13 @@ namespace tt {
 size_t tc_mlp_workspace(int64_t R, int E, int H);
 int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                int64_t R, int E, int H, float* h1, float* z, float* y, __nv_bfloat16* y_bf16,
-               void* ws, size_t ws_bytes, cudaStream_t s);
+               const __nv_bfloat16* x_bf16, const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16,
+               __nv_bfloat16* h1_bf16, void* ws, size_t ws_bytes, cudaStream_t s);
 int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1,
                const float* z, int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2,
-               float* db2, void* ws, size_t ws_bytes, cudaStream_t s);
+               float* db2, const __nv_bfloat16* x_bf16, const __nv_bfloat16* w1_bf16,
+               const __nv_bfloat16* w2_bf16, const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride,
+               void* ws, size_t ws_bytes, cudaStream_t s);
 
 // fused similarity GEMM + online-LSE cross entropy on tcgen05 (tc_inbatch.cu)
 size_t tc_inbatch_workspace(int64_t Bq, int64_t Bd, int H);
@@ -23,6 +26,12 @@ int tc_inbatch_bwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, 
                    const float* lse, int64_t Bq, int64_t Bd, int H, float inv_temp, int64_t label_offset,
                    float loss_scale, const float* grad_out, float* dq, float* dd, void* ws, size_t ws_bytes,
                    cudaStream_t s);
+
+// partial-slice backward for the fused trainer: both gradients in one launch, slices summed by the consumer
+int tc_inbatch_bwd_nparts(int64_t Bq, int64_t Bd, int H);
+int tc_inbatch_bwd_parts(const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16, const float* lse, int64_t Bq, int64_t Bd,
+                         int H, float inv_temp, int64_t label_offset, float loss_scale, const float* grad_out,
+                         float* dq_parts, int64_t stride_q, float* dd_parts, int64_t stride_d, cudaStream_t s);
 
 // shared by both precisions (inbatch_ce.cu): lse/loss finalisation from per-split (max,sum)
 int inbatch_finalize(const float* part_ml, const float* pos_logit, int nsplit, int64_t Bq, float inv_temp,

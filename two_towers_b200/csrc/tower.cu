@@ -252,7 +252,8 @@ size_t tt_mlp_workspace(int64_t R, int E, int H, int precision) {
 }
 
 int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
-               int64_t R, int E, int H, float* h1, float* z, float* y, void* y_bf16, int precision,
+               int64_t R, int E, int H, float* h1, float* z, float* y, void* y_bf16, const void* x_bf16,
+               const void* w1_bf16, const void* w2_bf16, void* h1_bf16, int precision,
                void* workspace, size_t workspace_bytes, void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(x && w1 && b1 && w2 && b2 && h1 && z && y && R >= 0 && E > 0 && H > 0, "mlp_fwd: bad arguments");
@@ -260,21 +261,28 @@ int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
   if (R == 0) return TT_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == TT_PREC_BF16)
-    return tt::tc_mlp_fwd(x, w1, b1, w2, b2, R, E, H, h1, z, y, (__nv_bfloat16*)y_bf16, workspace, workspace_bytes, s);
+    return tt::tc_mlp_fwd(x, w1, b1, w2, b2, R, E, H, h1, z, y, (__nv_bfloat16*)y_bf16, (const __nv_bfloat16*)x_bf16,
+                          (const __nv_bfloat16*)w1_bf16, (const __nv_bfloat16*)w2_bf16, (__nv_bfloat16*)h1_bf16,
+                          workspace, workspace_bytes, s);
   TT_CHECK_ARG(precision == TT_PREC_FP32, "mlp_fwd: unknown precision %d", precision);
   return tt::mlp_fwd_fp32(x, w1, b1, w2, b2, R, E, H, h1, z, y, (__nv_bfloat16*)y_bf16, workspace, workspace_bytes, s);
 }
 
 int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1,
                const float* z, int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2,
-               float* db2, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+               float* db2, const void* x_bf16, const void* w1_bf16, const void* w2_bf16, const void* h1_bf16,
+               int dy_parts, int64_t dy_part_stride, int precision, void* workspace, size_t workspace_bytes,
+               void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(dy && x && w1 && w2 && h1 && z && dw1 && db1 && dw2 && db2 && R > 0 && E > 0 && H > 0,
                "mlp_bwd: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == TT_PREC_BF16)
-    return tt::tc_mlp_bwd(dy, x, w1, w2, h1, z, R, E, H, dx, dw1, db1, dw2, db2, workspace, workspace_bytes, s);
+    return tt::tc_mlp_bwd(dy, x, w1, w2, h1, z, R, E, H, dx, dw1, db1, dw2, db2, (const __nv_bfloat16*)x_bf16,
+                          (const __nv_bfloat16*)w1_bf16, (const __nv_bfloat16*)w2_bf16, (const __nv_bfloat16*)h1_bf16,
+                          dy_parts, dy_part_stride, workspace, workspace_bytes, s);
   TT_CHECK_ARG(precision == TT_PREC_FP32, "mlp_bwd: unknown precision %d", precision);
+  TT_CHECK_ARG(dy_parts <= 1, "mlp_bwd: split dy slices are a TT_PREC_BF16 feature");
   return tt::mlp_bwd_fp32(dy, x, w1, w2, h1, z, R, E, H, dx, dw1, db1, dw2, db2, workspace, workspace_bytes, s);
 }
 

@@ -76,11 +76,13 @@ class FusedTrainer:
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.dev)
-        self.step_count = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self.step_count = torch.zeros(2, dtype=torch.int64, device=self.dev)      # [steps taken, ticket]
         off = 0
+        self.offsets = {}
         with torch.no_grad():
             for p in params:
                 n = p.numel()
+                self.offsets[id(p)] = off
                 # keep 16-byte alignment of every view (vector loads in the kernels)
                 self.flat[off:off + n].copy_(p.data.reshape(-1))
                 p.data = self.flat[off:off + n].view(p.shape)
@@ -94,7 +96,15 @@ class FusedTrainer:
         self.pooled = torch.empty(R, self.E, **f32)
         self.inv_len = torch.empty(R, **f32)
         self.y = torch.empty(R, self.H, **f32)
-        self.dy = torch.empty(R, self.H, **f32)
+        # the tensor-core loss backward leaves its per-split partial gradients as slices [parts, R, H]; the
+        # tower backward sums them while it reads dy (no reduction kernel, no extra pass)
+        self.dy_parts = 1
+        if (self.prec == _lib.TT_PREC_BF16 and loss == "in_batch" and not self.global_negatives and
+                all(isinstance(t, MeanPoolingTower) for t, _, _ in self.groups)):
+            self.dy_parts = int(self.lib.tt_inbatch_ce_bwd_nparts(B, B, self.H, self.prec))
+        self.dy_part_stride = R * self.H if self.dy_parts > 1 else 0
+        self.dy_all = torch.empty(self.dy_parts, R, self.H, **f32)
+        self.dy = self.dy_all[0]
         self.dpooled = torch.empty(R, self.E, **f32)
         self.saved: List[Dict[str, torch.Tensor]] = []
         for tower, r0, nr in self.groups:
@@ -111,6 +121,11 @@ class FusedTrainer:
         bf = self.prec == _lib.TT_PREC_BF16
         self.pooled_bf16 = torch.empty(R, self.E, dtype=torch.bfloat16, device=self.dev) if bf else None
         self.y_bf16 = torch.empty(R, self.H, dtype=torch.bfloat16, device=self.dev) if bf else None
+        # bf16 shadow of the flat parameter buffer, refreshed by the AdamW kernel -> the tensor-core GEMMs
+        # read weights without any per-step conversion kernel
+        self.flat_bf16 = ops.cast_bf16(self.flat) if bf else None
+        self.h1_bf16 = [torch.empty(nr, self.H, dtype=torch.bfloat16, device=self.dev) if bf else None
+                        for _, _, nr in self.groups]
         self.loss = torch.zeros((), **f32)
         self.lse = torch.empty(B, **f32)
         self.pos_mean = torch.zeros((), **f32)
@@ -130,16 +145,25 @@ class FusedTrainer:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def _shadow(self, param):
+        """bf16 view of `param` inside the flat shadow buffer (None in fp32 mode / frozen params)."""
+        if self.flat_bf16 is None or id(param) not in self.offsets:
+            return None
+        off = self.offsets[id(param)]
+        return self.flat_bf16[off:off + param.numel()]
+
     def _tower_fwd(self, gi: int):
         tower, r0, nr = self.groups[gi]
         lib, s, sv = self.lib, self._stream(), self.saved[gi]
         x, y = self.pooled[r0:r0 + nr], self.y[r0:r0 + nr]
         yb = self.y_bf16[r0:r0 + nr] if self.y_bf16 is not None else None
+        xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
             check(lib.tt_mlp_fwd(_p(x), _p(l1.weight), _p(l1.bias), _p(l2.weight), _p(l2.bias), nr, self.E, self.H,
-                                 _p(sv["h1"]), _p(sv["z"]), _p(y), _p(yb), self.prec, _p(self.ws), self.ws.numel(), s),
-                  "tt_mlp_fwd")
+                                 _p(sv["h1"]), _p(sv["z"]), _p(y), _p(yb), _p(xb), _p(self._shadow(l1.weight)),
+                                 _p(self._shadow(l2.weight)), _p(self.h1_bf16[gi]), self.prec, _p(self.ws),
+                                 self.ws.numel(), s), "tt_mlp_fwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
             check(lib.tt_proj_ln_fwd(_p(x), _p(lin.weight), _p(lin.bias), _p(ln.weight), _p(ln.bias), nr, self.E,
@@ -152,13 +176,16 @@ class FusedTrainer:
     def _tower_bwd(self, gi: int):
         tower, r0, nr = self.groups[gi]
         lib, s, sv = self.lib, self._stream(), self.saved[gi]
-        x, dy = self.pooled[r0:r0 + nr], self.dy[r0:r0 + nr]
+        x, dy = self.pooled[r0:r0 + nr], self.dy[r0:r0 + nr]          # slice 0; further slices dy_part_stride apart
         dx = self.dpooled[r0:r0 + nr] if self.train_table else None
+        xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
             check(lib.tt_mlp_bwd(_p(dy), _p(x), _p(l1.weight), _p(l2.weight), _p(sv["h1"]), _p(sv["z"]), nr, self.E,
                                  self.H, _p(dx), _p(l1.weight.grad), _p(l1.bias.grad), _p(l2.weight.grad),
-                                 _p(l2.bias.grad), self.prec, _p(self.ws), self.ws.numel(), s), "tt_mlp_bwd")
+                                 _p(l2.bias.grad), _p(xb), _p(self._shadow(l1.weight)), _p(self._shadow(l2.weight)),
+                                 _p(self.h1_bf16[gi]), self.dy_parts, self.dy_part_stride, self.prec, _p(self.ws),
+                                 self.ws.numel(), s), "tt_mlp_bwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
             check(lib.tt_proj_ln_bwd(_p(dy), _p(x), _p(lin.weight), _p(ln.weight), _p(sv["a"]), _p(sv["stats"]),
@@ -195,9 +222,14 @@ class FusedTrainer:
                 check(lib.tt_inbatch_ce_fwd(_p(q), _p(d), _p(qb), _p(db), B, B, H, inv_t, 0, scale, _p(self.loss),
                                             _p(self.lse), _p(self.pos_mean), self.prec, _p(self.ws), self.ws.numel(), s),
                       "tt_inbatch_ce_fwd")
-                check(lib.tt_inbatch_ce_bwd(_p(q), _p(d), _p(qb), _p(db), _p(self.lse), B, B, H, inv_t, 0, scale, None,
-                                            _p(dq), _p(dd), self.prec, _p(self.ws), self.ws.numel(), s),
-                      "tt_inbatch_ce_bwd")
+                if self.dy_parts > 1:
+                    check(lib.tt_inbatch_ce_bwd_parts(_p(qb), _p(db), _p(self.lse), B, B, H, inv_t, 0, scale, None,
+                                                      _p(dq), self.dy_part_stride, _p(dd), self.dy_part_stride, s),
+                          "tt_inbatch_ce_bwd_parts")
+                else:
+                    check(lib.tt_inbatch_ce_bwd(_p(q), _p(d), _p(qb), _p(db), _p(self.lse), B, B, H, inv_t, 0, scale,
+                                                None, _p(dq), _p(dd), self.prec, _p(self.ws), self.ws.numel(), s),
+                          "tt_inbatch_ce_bwd")
         else:
             n, dn = self.y[2 * B:3 * B], self.dy[2 * B:3 * B]
             check(lib.tt_triplet_fwd(_p(q), _p(d), _p(n), B, H, self.margin, _p(self.loss), _p(self.sims),
@@ -215,7 +247,7 @@ class FusedTrainer:
             parallel.allreduce_sum_(self.flat_grad, self.group)
         check(lib.tt_adamw_step(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
                                 self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                _p(self.step_count), None, s), "tt_adamw_step")
+                                _p(self.step_count), _p(self.flat_bf16), s), "tt_adamw_step")
 
     # ---------------------------------------------------------------------------------------
     def load_batch(self, q_ids: torch.Tensor, d_ids: torch.Tensor, n_ids: Optional[torch.Tensor] = None):
@@ -246,6 +278,8 @@ class FusedTrainer:
             # ... restore the state the warm-up step changed, then capture and replay once
             self.flat.copy_(st["flat"]); self.exp_avg.copy_(st["m"]); self.exp_avg_sq.copy_(st["v"])
             self.step_count.copy_(st["t"])
+            if self.flat_bf16 is not None:
+                ops.cast_bf16(self.flat, self.flat_bf16)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step_impl()

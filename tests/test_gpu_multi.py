@@ -1,0 +1,99 @@
+"""2-GPU NCCL tests (skipped unless >= 2 CUDA devices): the real kernels under the real collectives.
+
+Equivalence targets: the 2-rank data-parallel step with global in-batch negatives equals the
+single-process oracle on the concatenated batch; the row-sharded search equals the unsharded one.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q_out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import two_towers_b200 as tt
+        from oracle import two_tower_oracle as O
+        from two_towers_b200 import parallel
+        # ---- global in-batch negatives: loss / dq / dd vs the oracle on the concatenated batch -------------
+        g = np.random.default_rng(0)
+        B, H, t = 192, 256, 0.1
+        Q = O.normalize(g.standard_normal((world * B, H))).astype(np.float32)
+        D = O.normalize(g.standard_normal((world * B, H))).astype(np.float32)
+        ql = torch.tensor(Q[rank * B:(rank + 1) * B], device=dev)
+        dl = torch.tensor(D[rank * B:(rank + 1) * B], device=dev)
+        for prec, tol in (("fp32", 2e-5), ("bf16", 3e-2)):
+            loss, lse, dglob = parallel.global_inbatch_fwd(ql, dl, t, tt.ops, precision=prec)
+            total = loss.clone()
+            dist.all_reduce(total)
+            rl, rlse = O.in_batch_loss(Q.astype(np.float64), D.astype(np.float64), t)
+            assert abs(total.item() - rl) <= tol * abs(rl), (prec, total.item(), rl)
+            dq, dd = parallel.global_inbatch_bwd(ql, dl, dglob, lse, t, tt.ops, precision=prec)
+            rdq, rdd = O.in_batch_loss_bwd(Q.astype(np.float64), D.astype(np.float64), t)
+            for a, b in ((dq, rdq), (dd, rdd)):
+                b = b[rank * B:(rank + 1) * B]
+                err = np.abs(a.cpu().numpy() - b).max()
+                assert err <= tol * np.abs(b).max() + 1e-9, (prec, err, np.abs(b).max())
+        # ---- fused trainer, 2 ranks, global negatives: finite, decreasing, identical weights on both ranks --
+        torch.manual_seed(0)
+        emb = tt.embeddings.build("lookup", 128, embedding_dim=64)
+        model = tt.build_two_tower("mean", emb, hidden_dim=256, tied_weights=True).to(dev)
+        gq = torch.Generator().manual_seed(100 + rank)
+        q_ids = torch.randint(1, 128, (256, 64), generator=gq)
+        d_ids = torch.randint(1, 128, (256, 64), generator=gq)
+        tr = tt.FusedTrainer(model, loss="in_batch", batch_size=256, max_len=64, precision="bf16",
+                             process_group=dist.group.WORLD, global_negatives=True)
+        first = tr.step(q_ids, d_ids).item()
+        for _ in range(10):
+            last = tr.step(q_ids, d_ids).item()
+        assert np.isfinite(first) and np.isfinite(last) and last < first
+        chk = tr.flat.double().sum().reshape(1)
+        both = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(both, chk)
+        assert both[0].item() == both[1].item()              # ranks stay bit-identical after the all-reduce
+        # ---- sharded search == unsharded ---------------------------------------------------------------------
+        N, k = 100_003, 50
+        idx = O.normalize(g.standard_normal((N, H))).astype(np.float32)
+        idx[70_000] = idx[3]
+        qs = O.normalize(g.standard_normal((3, H))).astype(np.float32); qs[0] = idx[3]
+        lo, hi = parallel.shard_bounds(N, rank, world)
+        s, i = parallel.sharded_topk(torch.tensor(idx[lo:hi], device=dev), torch.tensor(qs, device=dev), k, lo, tt.ops, cosine=False)
+        fs, fi = tt.ops.topk_scan(torch.tensor(idx, device=dev), torch.tensor(qs, device=dev), k, cosine=False)
+        assert torch.equal(i, fi) and torch.equal(s, fs)
+        assert i[0, :2].tolist() == [3, 70_000]
+        q_out.put((rank, "ok"))
+    except Exception:
+        import traceback
+        q_out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_nccl_equivalence():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"

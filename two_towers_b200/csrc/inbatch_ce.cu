@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "tensor_core.cuh"
+#include "reduce.cuh"
 
 namespace tt {
 
@@ -153,12 +154,21 @@ ce_finalize_kernel(const float* __restrict__ part_ml, const float* __restrict__ 
   __shared__ float s_loss[1024], s_pos[1024];
   float tl = 0.f, tp = 0.f;
   for (int64_t row = threadIdx.x; row < Bq; row += 1024) {
-    float M = -CUDART_INF_F;
-    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, part_ml[((int64_t)s * Bq + row) * 2]);
-    float Lsum = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-      const float ms = part_ml[((int64_t)s * Bq + row) * 2], ls = part_ml[((int64_t)s * Bq + row) * 2 + 1];
-      Lsum += ls * expf(ms - M);
+    // (max, sum) pairs of all splits: loads issued back to back (8 in flight), then combined in split order
+    float M = -CUDART_INF_F, Lsum = 0.f;
+    for (int s0 = 0; s0 < nsplit; s0 += 8) {
+      float2 ml[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        ml[u] = (s0 + u < nsplit) ? __ldg(reinterpret_cast<const float2*>(part_ml) + (int64_t)(s0 + u) * Bq + row)
+                                  : make_float2(-CUDART_INF_F, 0.f);
+      float Mn = M;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) Mn = fmaxf(Mn, ml[u].x);
+      Lsum *= expf(M - Mn);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) Lsum += ml[u].y * expf(ml[u].x - Mn);
+      M = Mn;
     }
     const float v = M + logf(Lsum);
     lse[row] = v;
@@ -286,18 +296,11 @@ ce_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Y, const fl
   }
 }
 
-__global__ void split_sum_kernel(const float* __restrict__ partial, int nsplit, int64_t n, float* __restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    for (int s = 0; s < nsplit; ++s) v += partial[(int64_t)s * n + i];
-    out[i] = v;
-  }
-}
-
 int split_sum(const float* partial, int nsplit, int64_t n, float* out, cudaStream_t s) {
-  split_sum_kernel<<<(unsigned)(ceil_div(n, 256) < 8 * kNumSMs ? ceil_div(n, 256) : 8 * kNumSMs), 256, 0, s>>>(partial, nsplit, n, out);
-  TT_LAUNCH_CHECK("split_sum_kernel");
-  return TT_OK;
+  ReduceJobs jobs{};
+  jobs.job[0] = make_job(partial, nsplit, n, n, out);
+  jobs.njobs = 1;
+  return reduce_parts(jobs, s);
 }
 
 static int pick_split(int64_t Bx, int64_t By) {

@@ -1,5 +1,6 @@
 // sgemm.cu -- fp32 FFMA GEMM (register-blocked, smem double-buffered) + fixed-order split-K.
 #include "sgemm.cuh"
+#include "reduce.cuh"
 
 namespace tt {
 
@@ -124,20 +125,6 @@ sgemm_kernel(SgemmArgs a, int kchunk) {
   }
 }
 
-__global__ void splitk_reduce_kernel(SgemmArgs a) {
-  const size_t total = (size_t)a.M * a.N;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    int gm = (int)(idx / a.N), gn = (int)(idx % a.N);
-    float v = 0.f;
-    for (int z = 0; z < a.splits; ++z) v += a.partial[(size_t)z * total + idx];   // fixed order
-    if (a.bias) v += a.bias[gn];
-    if (a.act == 1) v = fmaxf(v, 0.f);
-    if (a.mask) v = (a.mask[(size_t)gm * a.ldmask + gn] > 0.f) ? v : 0.f;
-    a.C[(size_t)gm * a.ldc + gn] = v;
-  }
-}
-
 int sgemm_pick_splits(int M, int N, int K) {
   const bool big = (M >= 128 && N >= 128);
   const int bm = big ? 128 : 64, bn = big ? 128 : 64;
@@ -185,11 +172,12 @@ int sgemm(const SgemmArgs& a, cudaStream_t stream) {
 }
 
 int splitk_reduce(const SgemmArgs& a, cudaStream_t stream) {
-  size_t total = (size_t)a.M * a.N;
-  int blocks = (int)(ceil_div((int64_t)total, 256) < 4 * kNumSMs ? ceil_div((int64_t)total, 256) : 4 * kNumSMs);
-  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(a);
-  TT_LAUNCH_CHECK("splitk_reduce_kernel");
-  return TT_OK;
+  ReduceJobs jobs{};
+  ReduceJob& j = jobs.job[0];
+  j = make_job(a.partial, a.splits, (int64_t)a.M * a.N, (int64_t)a.M * a.N, a.C);
+  j.bias = a.bias; j.act = a.act; j.mask = a.mask; j.ldmask = a.ldmask; j.ncols = a.N; j.ldo = a.ldc;
+  jobs.njobs = 1;
+  return reduce_parts(jobs, stream);
 }
 
 // ---------------------------------------------------------------------------------------

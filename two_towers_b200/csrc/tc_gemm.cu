@@ -17,6 +17,7 @@
 #include "tc_common.cuh"
 #include "sgemm.cuh"
 #include "tensor_core.cuh"
+#include "reduce.cuh"
 
 namespace tt {
 namespace tc {
@@ -90,12 +91,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t kStageBytes = kATile + kBTile;
   extern __shared__ __align__(1024) uint8_t smem[];
   // carve: [stages x (A,B)] [full barriers][empty barriers][tmem_full][tmem slot]
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);       // stays in the shared address space
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* acc_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-  uint8_t* stage_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 127) & ~(uintptr_t)127);   // 4 x [32][36] fp32 epilogue staging
+  uint8_t* stage_tiles = reinterpret_cast<uint8_t*>(tmem_slot) + 128 - (((2 * kStages + 1) * 8) & 127);   // 128-B aligned: 4 x [32][36] fp32 staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -183,19 +184,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool col_ok = col < p.N;
       const float bias_v = (!split && p.bias && col_ok) ? p.bias[col] : 0.f;
       const int nrows = min(32, p.M - row0);
-      float csum = 0.f;
-      for (int rr = 0; rr < nrows; ++rr) {
-        const int grow = row0 + rr;
-        float v = T[rr][lane];
-        if (!split) {
-          v += bias_v;
-          if (p.act == 1) v = fmaxf(v, 0.f);
-          if (p.mask && col_ok) v = (p.mask[(size_t)grow * p.ldmask + col] > 0.f) ? v : 0.f;
+      // all shared / mask loads first (independent), then the math, then the stores: no load waits on a store
+      float v[32];
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) v[rr] = T[rr][lane];
+      if (!split) {
+        if (p.mask) {
+          float mk[32];
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr)
+            mk[rr] = (rr < nrows && col_ok) ? __ldg(p.mask + (size_t)(row0 + rr) * p.ldmask + col) : 1.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            float x = v[rr] + bias_v;
+            if (p.act == 1) x = fmaxf(x, 0.f);
+            v[rr] = mk[rr] > 0.f ? x : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            float x = v[rr] + bias_v;
+            if (p.act == 1) x = fmaxf(x, 0.f);
+            v[rr] = x;
+          }
         }
-        csum += v;
-        if (col_ok) {
-          if (outp) outp[(size_t)grow * ldo + col] = v;
-          if (!split && p.Cb) p.Cb[(size_t)grow * p.ldc + col] = __float2bfloat16(v);
+      }
+      float csum = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        if (rr < nrows) {
+          csum += v[rr];
+          if (col_ok) {
+            if (outp) outp[(size_t)(row0 + rr) * ldo + col] = v[rr];
+            if (!split && p.Cb) p.Cb[(size_t)(row0 + rr) * p.ldc + col] = __float2bfloat16(v[rr]);
+          }
         }
       }
       if (p.colsum_part && col_ok && nrows > 0) p.colsum_part[(size_t)(row0 >> 5) * p.N + col] = csum;
@@ -319,29 +341,7 @@ l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __r
     if (yb) yb[row * H + e] = __float2bfloat16(o);
   }
 }
-// Gradient finalisation: up to 4 independent fixed-order reductions  out[i] = sum_p part[p*n + i]  in one launch
-// (split-K partials of dW1/dW2 and the per-block column sums that become db1/db2).
-struct ReduceJobs {
-  const float* part[4];
-  float* out[4];
-  int nparts[4];
-  int64_t n[4];
-  int njobs;
-};
-__global__ void __launch_bounds__(256) reduce_jobs_kernel(ReduceJobs j) {
-  const int job = blockIdx.y;
-  if (job >= j.njobs) return;
-  const float* part = j.part[job];
-  const int64_t n = j.n[job];
-  const int np = j.nparts[job];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    for (int p = 0; p < np; ++p) v += part[(int64_t)p * n + i];
-    j.out[job][i] = v;
-  }
-}
-
-constexpr int kNormRowsPerBlock = 64;
+constexpr int kNormRowsPerBlock = 32;
 // dz = (dy - y (y.dy)) / |z|  -> fp32 + bf16; also per-block column sums of dz (-> db2), H <= 512
 __global__ void __launch_bounds__(256)
 l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_stride, const float* __restrict__ z,
@@ -356,20 +356,27 @@ l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_
     const int64_t row = (int64_t)blockIdx.x * kNormRowsPerBlock + warp * (kNormRowsPerBlock / 8) + i;
     if (row >= R) break;
     const float* zr = z + row * H; const float* gr = dy + row * H;
-    // dy may arrive as `dy_parts` split slices (the loss kernel's per-split partial gradients): sum them in order
-    float g[16];
+    // dy may arrive as `dy_parts` split slices (the loss kernel's per-split partial gradients): summed in slice
+    // order; every slice's loads are issued together (independent, up to 16 in flight per lane)
+    float g[16], zv[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const int e = lane + 32 * k;
-      float t = 0.f;
-      if (e < H) for (int pp = 0; pp < dy_parts; ++pp) t += gr[(int64_t)pp * dy_stride + e];
-      g[k] = t;
+      zv[k] = (e < H) ? zr[e] : 0.f;
+      g[k] = (e < H) ? gr[e] : 0.f;
+    }
+    for (int pp = 1; pp < dy_parts; ++pp) {
+      float t[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { const int e = lane + 32 * k; t[k] = (e < H) ? gr[(int64_t)pp * dy_stride + e] : 0.f; }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) g[k] += t[k];
     }
     float ss = 0.f, dot = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const int e = lane + 32 * k;
-      if (e < H) { float v = zr[e]; ss = fmaf(v, v, ss); dot = fmaf(v, g[k], dot); }
+      if (e < H) { float v = zv[k]; ss = fmaf(v, v, ss); dot = fmaf(v, g[k], dot); }
     }
     ss = warp_sum(ss); dot = warp_sum(dot);
     const float n = sqrtf(ss), denom = fmaxf(n, 1e-12f);
@@ -378,7 +385,7 @@ l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_
     for (int k = 0; k < 16; ++k) {
       const int e = lane + 32 * k;
       if (e < H) {
-        const float o = (g[k] - zr[e] * inner) / denom;
+        const float o = (g[k] - zv[k] * inner) / denom;
         dz[row * H + e] = o;
         dzb[row * H + e] = __float2bfloat16(o);
         cs[k] += o;
@@ -552,19 +559,14 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
     rc = tc::tc_gemm(g, s); if (rc) return rc;
   }
   // one launch finishes every reduction of this call in a fixed order: dW2, dW1 split-K partials, db1, db2
-  tc::ReduceJobs jobs{};
+  ReduceJobs jobs{};
   int nj = 0;
-  auto add = [&](const float* part, int np, int64_t n, float* out) {
-    jobs.part[nj] = part; jobs.nparts[nj] = np; jobs.n[nj] = n; jobs.out[nj] = out; ++nj;
-  };
-  if (plan.s_dw2 > 1) add(partial, plan.s_dw2, (int64_t)H * H, dw2);
-  if (plan.s_dw1 > 1) add(partial2, plan.s_dw1, (int64_t)H * E, dw1);
-  add(cs1, (int)ceil_div(R, 32), H, db1);
-  if (fused_cs) add(cs2, nblk2, H, db2);
+  if (plan.s_dw2 > 1) jobs.job[nj++] = make_job(partial, plan.s_dw2, (int64_t)H * H, (int64_t)H * H, dw2);
+  if (plan.s_dw1 > 1) jobs.job[nj++] = make_job(partial2, plan.s_dw1, (int64_t)H * E, (int64_t)H * E, dw1);
+  jobs.job[nj++] = make_job(cs1, (int)ceil_div(R, 32), H, H, db1);
+  if (fused_cs) jobs.job[nj++] = make_job(cs2, nblk2, H, H, db2);
   jobs.njobs = nj;
-  tc::reduce_jobs_kernel<<<dim3(64, nj), 256, 0, s>>>(jobs);
-  TT_LAUNCH_CHECK("reduce_jobs_kernel");
-  return TT_OK;
+  return reduce_parts(jobs, s);
 }
 
 // self-test hook used by the GPU test-suite: C = A * B on the tensor cores with either operand major

@@ -184,7 +184,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // ---------------------------------------------------------------------------------------
 // backward: dQ and dD passes in ONE launch (blockIdx.z selects the pass)
 // ---------------------------------------------------------------------------------------
-constexpr int BWD_STAGES = 3;
+constexpr int BWD_STAGES = 4;          // X 64 KB + 4 x 32 KB Y + 2 x 16 KB P = 224 KB: a full tile of slack for the TMA latency
 
 struct BwdParams {
   const float* lse;            // [Bq] row logsumexp of the logits (natural log)

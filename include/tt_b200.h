@@ -73,6 +73,9 @@ int tt_embed_pool_bwd(const void* ids, int id_bytes, const float* inv_len, const
  * Weights are nn.Linear layout: w1 [H,E], b1 [H], w2 [H,H], b2 [H].
  * Saved for backward (caller-allocated): h1 [R,H] (post-ReLU), z [R,H] (pre-normalise).
  * y [R,H] has unit rows: y = z / max(||z||, 1e-12).  y_bf16 (nullable): bf16 copy of y.
+ * TT_PREC_BF16: y may be null when y_bf16 is given; h1 is opaque saved state (it holds the hidden activation as
+ * R*H bf16 values unless a separate h1_bf16 buffer is passed); E % 64 == 0, H % 64 == 0, H <= 256 runs the whole
+ * forward as ONE kernel (both weight matrices resident in shared memory).
  * tt_mlp_bwd: given dy, produces dx [R,E] (nullable), dw1, db1, dw2, db2 (OVERWRITTEN).
  * bf16 operand shadows (TT_PREC_BF16 only, all nullable -- missing ones are produced inside the call):
  *   x_bf16 [R,E], w1_bf16 [H,E], w2_bf16 [H,H] (e.g. the shadow tt_adamw_step maintains),

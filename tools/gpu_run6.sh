@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out
+mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tensor_core.py -q --timeout 600 -p no:cacheprovider > $O/pytest_all.log 2>&1; echo "exit $?" >> $O/pytest_all.log
+timeout 600 python tools/time_ops.py --precision bf16 > $O/time_ops_bf16.log 2>&1; echo "exit $?" >> $O/time_ops_bf16.log
+timeout 900 python bench.py --steps 30 --warmup 5 --precision bf16 --no-search --no-cpu-baseline > $O/bench_bf16_c.log 2>&1; echo "exit $?" >> $O/bench_bf16_c.log
+tail -3 $O/pytest_all.log; cat $O/time_ops_bf16.log; tail -c 300 $O/bench_bf16_c.log

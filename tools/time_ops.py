@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Per-op device time of the fused train step at the BASELINE shape: each C-ABI call is captured in its own
+CUDA graph and replayed between L2 flushes with CUDA events around it (no host launch gaps, no profiler)."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import two_towers_b200 as tt
+from two_towers_b200 import _lib
+from two_towers_b200.train import _p
+
+
+def timed(fn, flush, reps=12):
+    fn(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    ts = []
+    for i in range(reps):
+        flush.add_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+    return float(np.median(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--B", type=int, default=4096)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    emb = tt.embeddings.build("lookup", 128, embedding_dim=64)
+    model = tt.build_two_tower("mean", emb, hidden_dim=256, tied_weights=True).to(dev)
+    tr = tt.FusedTrainer(model, loss="in_batch", batch_size=a.B, max_len=64, precision=a.precision, use_cuda_graph=False)
+    g = torch.Generator().manual_seed(1)
+    q = torch.randint(1, 128, (a.B, 64), generator=g); d = torch.randint(1, 128, (a.B, 64), generator=g)
+    tr.step(q, d); torch.cuda.synchronize()
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    lib, B, H, R = tr.lib, tr.B, tr.H, 2 * tr.B
+    s = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    from two_towers_b200._lib import check
+    qb = tr.y_bf16[:B] if tr.y_bf16 is not None else None
+    db = tr.y_bf16[B:2 * B] if tr.y_bf16 is not None else None
+    qf, df = tr.y[:B], tr.y[B:2 * B]
+    ops = {
+        "embed_pool_fwd": lambda: check(lib.tt_embed_pool_fwd(_p(tr.ids), 8, _p(tr.table), R, tr.L, tr.V, tr.E, _p(tr.pooled), _p(tr.inv_len), _p(tr.pooled_bf16), s()), "x"),
+        "tower_fwd": lambda: tr._tower_fwd(0),
+        "ce_fwd": lambda: check(lib.tt_inbatch_ce_fwd(_p(qf), _p(df), _p(qb), _p(db), B, B, H, 10.0, 0, 1.0 / B, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), tr.prec, _p(tr.ws), tr.ws.numel(), s()), "x"),
+        "ce_bwd": (lambda: check(lib.tt_inbatch_ce_bwd_parts(_p(qb), _p(db), _p(tr.lse), B, B, H, 10.0, 0, 1.0 / B, None, _p(tr.dy[:B]), tr.dy_part_stride, _p(tr.dy[B:2 * B]), tr.dy_part_stride, s()), "x"))
+                  if tr.dy_parts > 1 else
+                  (lambda: check(lib.tt_inbatch_ce_bwd(_p(qf), _p(df), _p(qb), _p(db), _p(tr.lse), B, B, H, 10.0, 0, 1.0 / B, None, _p(tr.dy[:B]), _p(tr.dy[B:2 * B]), tr.prec, _p(tr.ws), tr.ws.numel(), s()), "x")),
+        "tower_bwd": lambda: tr._tower_bwd(0),
+        "embed_pool_bwd": lambda: check(lib.tt_embed_pool_bwd(_p(tr.ids), 8, _p(tr.inv_len), _p(tr.dpooled), R, tr.L, tr.V, tr.E, _p(tr.table.grad), _p(tr.ws), tr.ws.numel(), s()), "x"),
+        "adamw": lambda: check(lib.tt_adamw_step(_p(tr.flat), _p(tr.flat_grad), _p(tr.exp_avg), _p(tr.exp_avg_sq), tr.n_params, 1e-3, 0.9, 0.999, 1e-8, 0.01, _p(tr.step_count), _p(tr.flat_bf16), s()), "x"),
+        "whole_step": lambda: tr._step_impl(),
+    }
+    total = 0.0
+    for name, fn in ops.items():
+        before = _lib.launch_count()
+        fn()
+        nl = _lib.launch_count() - before
+        t = timed(fn, flush)
+        if name != "whole_step":
+            total += t
+        print(f"{name:16s} {t:9.1f} us   ({nl} launches)")
+    print(f"{'sum of ops':16s} {total:9.1f} us")
+
+
+if __name__ == "__main__":
+    main()

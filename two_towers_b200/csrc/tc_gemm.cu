@@ -73,7 +73,7 @@ struct GemmParams {
   int ldc;
   const float* bias;
   int act;
-  const float* mask;
+  const __nv_bfloat16* mask;  // nullable bf16 [M,ldmask]: out = mask > 0 ? acc : 0 (only without bias / act)
   int ldmask;
   int splits;
   float* colsum_part;         // nullable [ceil(M/32), N]: per-32-row column sums of the epilogue output (bias grads)
@@ -167,6 +167,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row0 = m0 + quarter * 32;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
+      // ReLU-gate mask for this thread's accumulator row (32 bf16 = 64 contiguous bytes, two full sectors):
+      // issued before the TMEM load so its latency overlaps the accumulator read
+      uint4 mk[4];
+      const bool use_mask = !split && p.mask != nullptr;
+      if (use_mask) {
+        const int grow = row0 + lane;
+        const bool ok = grow < p.M && (n0 + c * 32 + 32 <= p.N) && ((p.ldmask & 7) == 0);
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (size_t)(ok ? grow : 0) * p.ldmask + n0 + c * 32);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mk[u] = ok ? __ldg(mp + u) : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        if (!ok && grow < p.M) {                               // ragged / unaligned tail: element-wise
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int c0 = n0 + c * 32 + j;
+            const uint32_t lo = (c0 < p.N) ? (uint32_t)__bfloat16_as_ushort(p.mask[(size_t)grow * p.ldmask + c0]) : 0x3f80u;
+            const uint32_t hi = (c0 + 1 < p.N) ? (uint32_t)__bfloat16_as_ushort(p.mask[(size_t)grow * p.ldmask + c0 + 1]) : 0x3f80u;
+            w[j >> 1] = lo | (hi << 16);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mk[u] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+        }
+      }
       uint32_t r[32];
       if (nkb > 0) {
         tmem_ld_x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
@@ -174,6 +197,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (use_mask) {
+        const uint32_t* mw = reinterpret_cast<const uint32_t*>(mk);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+          const uint32_t w = mw[j >> 1];
+          if (!((w & 0x8000u) == 0 && (w & 0x7fffu) != 0)) r[j] = 0u;
+          if (!((w & 0x80000000u) == 0 && (w & 0x7fff0000u) != 0)) r[j + 1] = 0u;
+        }
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
@@ -184,39 +217,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool col_ok = col < p.N;
       const float bias_v = (!split && p.bias && col_ok) ? p.bias[col] : 0.f;
       const int nrows = min(32, p.M - row0);
-      // all shared / mask loads first (independent), then the math, then the stores: no load waits on a store
-      float v[32];
-#pragma unroll
-      for (int rr = 0; rr < 32; ++rr) v[rr] = T[rr][lane];
-      if (!split) {
-        if (p.mask) {
-          float mk[32];
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr)
-            mk[rr] = (rr < nrows && col_ok) ? __ldg(p.mask + (size_t)(row0 + rr) * p.ldmask + col) : 1.f;
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            float x = v[rr] + bias_v;
-            if (p.act == 1) x = fmaxf(x, 0.f);
-            v[rr] = mk[rr] > 0.f ? x : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            float x = v[rr] + bias_v;
-            if (p.act == 1) x = fmaxf(x, 0.f);
-            v[rr] = x;
-          }
-        }
-      }
+      // 8 rows at a time: shared loads of a batch issued together, then the math, then 128-byte coalesced stores
       float csum = 0.f;
+#pragma unroll 1
+      for (int rb = 0; rb < 32; rb += 8) {
+        if (rb >= nrows) break;
+        float v[8];
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        if (rr < nrows) {
-          csum += v[rr];
-          if (col_ok) {
-            if (outp) outp[(size_t)(row0 + rr) * ldo + col] = v[rr];
-            if (!split && p.Cb) p.Cb[(size_t)(row0 + rr) * p.ldc + col] = __float2bfloat16(v[rr]);
+        for (int u = 0; u < 8; ++u) v[u] = T[rb + u][lane];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (!split) {
+            float x = v[u] + bias_v;
+            if (p.act == 1) x = fmaxf(x, 0.f);
+            v[u] = x;
+          }
+          if (rb + u < nrows) {
+            csum += v[u];
+            if (col_ok) {
+              if (outp) outp[(size_t)(row0 + rb + u) * ldo + col] = v[u];
+              if (!split && p.Cb) p.Cb[(size_t)(row0 + rb + u) * p.ldc + col] = __float2bfloat16(v[u]);
+            }
           }
         }
       }
@@ -239,7 +260,7 @@ struct TcGemm {
   const __nv_bfloat16* A; int a_mn;      // a_mn ? stored [K,M] : stored [M,K]
   const __nv_bfloat16* B; int b_mn;      // b_mn ? stored [K,N] : stored [N,K]
   float* C = nullptr; __nv_bfloat16* Cb = nullptr; int ldc = 0;
-  const float* bias = nullptr; int act = 0; const float* mask = nullptr; int ldmask = 0;
+  const float* bias = nullptr; int act = 0; const __nv_bfloat16* mask = nullptr; int ldmask = 0;
   int splits = 1; float* partial = nullptr;
   bool defer_reduce = false;             // split-K: leave the partials, the caller reduces them later
   float* colsum_part = nullptr;          // [ceil(M/32), N] column-sum partials of the output
@@ -272,7 +293,7 @@ static int launch_gemm(const TcGemm& g, cudaStream_t s) {
     // fixed-order reduction + epilogue (shared with the fp32 path)
     SgemmArgs a{};
     a.M = g.M; a.N = g.N; a.K = g.K; a.C = g.C; a.ldc = g.ldc; a.bias = g.bias; a.act = g.act;
-    a.mask = g.mask; a.ldmask = g.ldmask; a.splits = g.splits; a.partial = g.partial;
+    a.splits = g.splits; a.partial = g.partial;
     return splitk_reduce(a, s);
   }
   return TT_OK;
@@ -280,7 +301,8 @@ static int launch_gemm(const TcGemm& g, cudaStream_t s) {
 
 int tc_gemm(const TcGemm& g, cudaStream_t s) {
   TT_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "tc_gemm: bad shape");
-  TT_CHECK_ARG(g.splits == 1 || (g.partial && g.C && !g.Cb), "tc_gemm: split-K needs partial + fp32 output only");
+  TT_CHECK_ARG(g.splits == 1 || (g.partial && g.C && !g.Cb && !g.mask), "tc_gemm: split-K needs partial + fp32 output only");
+  TT_CHECK_ARG(!g.mask || (!g.bias && g.act == 0), "tc_gemm: the gate mask is applied to the raw accumulator (no bias / act)");
   if (g.N <= 64) return launch_gemm<64>(g, s);
   return launch_gemm<128>(g, s);            // 128-wide tiles: twice the CTAs of 256-wide ones for N = 256
 }
@@ -337,7 +359,7 @@ l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __r
   const float denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
   for (int e = lane; e < H; e += 32) {
     const float o = zr[e] / denom;
-    y[row * H + e] = o;
+    if (y) y[row * H + e] = o;
     if (yb) yb[row * H + e] = __float2bfloat16(o);
   }
 }
@@ -386,7 +408,7 @@ l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_
       const int e = lane + 32 * k;
       if (e < H) {
         const float o = (g[k] - zv[k] * inner) / denom;
-        dz[row * H + e] = o;
+        if (dz) dz[row * H + e] = o;
         dzb[row * H + e] = __float2bfloat16(o);
         cs[k] += o;
       }
@@ -478,10 +500,14 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
   const __nv_bfloat16* xa = x_bf16 ? x_bf16 : xb;
   const __nv_bfloat16* w1a = w1_bf16 ? w1_bf16 : w1b;
   const __nv_bfloat16* w2a = w2_bf16 ? w2_bf16 : w2b;
-  if (h1_bf16) h1b = h1_bf16;
+  // saved hidden activation: bf16.  Without a caller-owned shadow it is stored in the (4-byte per element,
+  // so large enough) h1 buffer itself -- TT_PREC_BF16 treats h1 as opaque saved state.
+  h1b = h1_bf16 ? h1_bf16 : reinterpret_cast<__nv_bfloat16*>(h1);
+  if (tc_mlp_fused_supported(E, H))
+    return tc_mlp_fwd_fused(xa, w1a, b1, w2a, b2, R, E, H, h1b, z, y, y_bf16, s);
   tc::TcGemm g{};
   g.M = (int)R; g.N = H; g.K = E; g.A = xa; g.a_mn = 0; g.B = w1a; g.b_mn = 0;
-  g.C = h1; g.Cb = h1b; g.ldc = H; g.bias = b1; g.act = 1;
+  g.C = nullptr; g.Cb = h1b; g.ldc = H; g.bias = b1; g.act = 1;
   rc = tc::tc_gemm(g, s); if (rc) return rc;
   g = tc::TcGemm{};
   g.M = (int)R; g.N = H; g.K = H; g.A = h1b; g.a_mn = 0; g.B = w2a; g.b_mn = 0;
@@ -522,15 +548,14 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
                    w2_bf16 ? nullptr : w2, w2b, w2_bf16 ? 0 : (int64_t)H * H, s);
     if (rc) return rc;
   }
-  if (!h1_bf16) { rc = tc::cast3(h1, h1b, R * H, nullptr, nullptr, 0, nullptr, nullptr, 0, s); if (rc) return rc; }
   const __nv_bfloat16* xa = x_bf16 ? x_bf16 : xb;
   const __nv_bfloat16* w1a = w1_bf16 ? w1_bf16 : w1b;
   const __nv_bfloat16* w2a = w2_bf16 ? w2_bf16 : w2b;
-  const __nv_bfloat16* h1a = h1_bf16 ? h1_bf16 : h1b;
+  const __nv_bfloat16* h1a = h1_bf16 ? h1_bf16 : reinterpret_cast<const __nv_bfloat16*>(h1);   // see tc_mlp_fwd
   const bool fused_cs = H <= 512;
   const int nblk2 = (int)ceil_div(R, tc::kNormRowsPerBlock);
   if (fused_cs) {
-    tc::l2norm_bwd_colsum_kernel<<<(unsigned)nblk2, 256, 0, s>>>(dy, dy_parts, dy_part_stride, z, R, H, dz, dzb, cs2);
+    tc::l2norm_bwd_colsum_kernel<<<(unsigned)nblk2, 256, 0, s>>>(dy, dy_parts, dy_part_stride, z, R, H, nullptr, dzb, cs2);   // fp32 dz is not needed: db2 comes from cs2
     TT_LAUNCH_CHECK("l2norm_bwd_colsum_kernel");
   } else {
     tc::l2norm_bwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(dy, z, R, H, dz, dzb);
@@ -544,8 +569,8 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   rc = tc::tc_gemm(g, s); if (rc) return rc;
   // da1[R,H] = (dz w2) * (h1 > 0) : A = dz [M=R,K=H] K-major, B = w2 stored [K=H_out, N=H_in] (MN-major)
   g = tc::TcGemm{};
-  g.M = (int)R; g.N = H; g.K = H; g.A = dzb; g.a_mn = 0; g.B = w2a; g.b_mn = 1; g.C = da1; g.Cb = da1b; g.ldc = H;
-  g.mask = h1; g.ldmask = H; g.colsum_part = cs1;
+  g.M = (int)R; g.N = H; g.K = H; g.A = dzb; g.a_mn = 0; g.B = w2a; g.b_mn = 1; g.C = nullptr; g.Cb = da1b; g.ldc = H;
+  g.mask = h1a; g.ldmask = H; g.colsum_part = cs1;      // fp32 da1 is never needed: db1 comes from the column-sum partials
   rc = tc::tc_gemm(g, s); if (rc) return rc;
   // dw1[H,E] = da1^T x
   g = tc::TcGemm{};

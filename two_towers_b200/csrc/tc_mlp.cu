@@ -1,0 +1,238 @@
+// tc_mlp.cu -- the whole tower MLP forward as ONE tcgen05 kernel (TT_PREC_BF16, K3):
+//
+//     y = normalize( relu(x W1^T + b1) W2^T + b2 )        twotower/encoders.py:38-42,77
+//
+// One CTA owns 128 rows.  Both weight matrices live in shared memory, the hidden activation never
+// leaves the SM:
+//   TMA   : x tile [128,E] + W1 [H,E]  ->  GEMM 1 (tcgen05.mma, fp32 accumulator in TMEM columns [0,H))
+//   warps : TMEM -> +b1 -> ReLU -> bf16 -> 128B-swizzled smem tile (the A operand of GEMM 2) and -> global h1
+//   TMA   : W2 [H,H] (k-block 0 re-uses the x/W1 bytes once GEMM 1 has retired)  ->  GEMM 2 (TMEM columns [256,256+H))
+//   warps : TMEM -> +b2 -> row sum of squares -> z (fp32, saved for backward), y (bf16 and optional fp32)
+// Every epilogue thread owns one TMEM lane == one row, so the row L2 norm is a private register reduction.
+// Compared with the unfused path (GEMM, GEMM, normalise) this is 1 launch instead of 3 and the
+// [R,H] hidden / pre-normalise tensors are written once and never re-read in the forward.
+#include <math_constants.h>
+
+#include "tc_common.cuh"
+#include "tensor_core.cuh"
+
+namespace tt {
+namespace tc {
+
+constexpr int MLP_BM = 128;
+constexpr int MLP_THREADS = 192;
+
+struct MlpFwdParams {
+  int64_t R;
+  int E, H;
+  const float* b1;
+  const float* b2;
+  __nv_bfloat16* h1b;     // [R,H]
+  float* z;               // [R,H] nullable
+  float* y;               // [R,H] nullable
+  __nv_bfloat16* yb;      // [R,H] nullable
+};
+
+__global__ void __launch_bounds__(MLP_THREADS, 1)
+tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                  const __grid_constant__ CUtensorMap tmW2, const MlpFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  const int E = p.E, H = p.H;
+  const int kE = E / 64, kH = H / 64;
+  const uint32_t x_bytes = (uint32_t)kE * MLP_BM * 128;            // x tile, kE k-blocks of [128 rows x 128 B]
+  const uint32_t w1_bytes = (uint32_t)kE * H * 128;                // W1, kE k-blocks of [H rows x 128 B]
+  const uint32_t w2_blk = (uint32_t)H * 128;                       // one W2 k-block [H rows x 128 B]
+  const uint32_t a_bytes = x_bytes + w1_bytes;                     // region A (>= w2_blk, checked on the host)
+  uint8_t* x_tile = base;
+  uint8_t* w1_tile = base + x_bytes;
+  uint8_t* w2_rest = base + a_bytes;                               // W2 k-blocks 1..kH-1
+  uint8_t* h1_tile = w2_rest + (uint32_t)(kH - 1) * w2_blk;        // [128 x H] bf16, kH k-blocks of 16 KB
+  uint8_t* after = h1_tile + (uint32_t)kH * MLP_BM * 128;
+  float* bias_s = reinterpret_cast<float*>(after);                 // b1[H], b2[H]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after + 2 * H * sizeof(float));
+  uint64_t* bar_x = bars;        // x + W1 landed
+  uint64_t* bar_w2a = bars + 1;  // W2 k-block 0 landed
+  uint64_t* bar_w2b = bars + 2;  // W2 k-blocks 1.. landed
+  uint64_t* bar_g1 = bars + 3;   // GEMM 1 retired (region A reusable)
+  uint64_t* bar_acc1 = bars + 4; // accumulator 1 ready
+  uint64_t* bar_h1 = bars + 5;   // hidden tile written (4 warps)
+  uint64_t* bar_acc2 = bars + 6; // accumulator 2 ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * MLP_BM;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    mbar_init(bar_x, 1); mbar_init(bar_w2a, 1); mbar_init(bar_w2b, 1); mbar_init(bar_g1, 1);
+    mbar_init(bar_acc1, 1); mbar_init(bar_h1, 4); mbar_init(bar_acc2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp >= 2) {                                                 // biases -> smem (read as broadcasts later)
+    for (int i = threadIdx.x - 64; i < H; i += 128) { bias_s[i] = p.b1[i]; bias_s[H + i] = p.b2[i]; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a1 = tmem_base, tmem_a2 = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_x, a_bytes);
+      for (int kb = 0; kb < kE; ++kb) tma_load_2d(x_tile + kb * (MLP_BM * 128), &tmX, bar_x, kb * 64, (int)m0);
+      for (int kb = 0; kb < kE; ++kb) tma_load_2d(w1_tile + (uint32_t)kb * w2_blk, &tmW1, bar_x, kb * 64, 0);
+      if (kH > 1) {
+        mbar_arrive_expect_tx(bar_w2b, (uint32_t)(kH - 1) * w2_blk);
+        for (int kb = 1; kb < kH; ++kb) tma_load_2d(w2_rest + (uint32_t)(kb - 1) * w2_blk, &tmW2, bar_w2b, kb * 64, 0);
+      }
+      mbar_wait(bar_g1, 0);                                        // GEMM 1 has finished reading x / W1
+      mbar_arrive_expect_tx(bar_w2a, w2_blk);
+      tma_load_2d(base, &tmW2, bar_w2a, 0, 0);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(MLP_BM, H, 0, 0);
+      const uint64_t dx = umma_desc_kmajor(smem_u32(x_tile), 0);
+      const uint64_t dw1 = umma_desc_kmajor(smem_u32(w1_tile), 0);
+      mbar_wait(bar_x, 0);
+      tc_fence_after();
+      for (int kb = 0; kb < kE; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_a1, dx + (uint64_t)(kb * (MLP_BM * 128 / 16) + k * 2),
+                    dw1 + (uint64_t)(kb * (w2_blk >> 4) + k * 2), idesc, (kb | k) != 0);
+      umma_commit(bar_g1);
+      umma_commit(bar_acc1);
+      const uint64_t dh = umma_desc_kmajor(smem_u32(h1_tile), 0);
+      const uint64_t dw2a = umma_desc_kmajor(smem_u32(base), 0);
+      const uint64_t dw2b = umma_desc_kmajor(smem_u32(w2_rest), 0);
+      mbar_wait(bar_h1, 0);
+      mbar_wait(bar_w2a, 0);
+      if (kH > 1) mbar_wait(bar_w2b, 0);
+      tc_fence_after();
+      for (int kb = 0; kb < kH; ++kb) {
+        const uint64_t dw = kb == 0 ? dw2a : dw2b + (uint64_t)((kb - 1) * (w2_blk >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_a2, dh + (uint64_t)(kb * (MLP_BM * 128 / 16) + k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+      }
+      umma_commit(bar_acc2);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int lrow = quarter * 32 + lane;
+    const int64_t row = m0 + lrow;
+    const bool row_ok = row < p.R;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    // ---- epilogue 1: hidden = relu(acc1 + b1) -> bf16 -> smem A tile + global h1 ------------------------------
+    mbar_wait(bar_acc1, 0);
+    tc_fence_after();
+    for (int c = 0; c < H / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem_a1 + lane_addr + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float a = fmaxf(__uint_as_float(r[j]) + bias_s[c * 32 + j], 0.f);
+        const float b = fmaxf(__uint_as_float(r[j + 1]) + bias_s[c * 32 + j + 1], 0.f);
+        pk[j >> 1] = pack_bf16x2(a, b);
+      }
+      uint8_t* hrow = h1_tile + (uint32_t)(c >> 1) * (MLP_BM * 128) + lrow * 128;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ch = (c & 1) * 4 + u;
+        const uint4 v = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        *reinterpret_cast<uint4*>(hrow + ((ch ^ (lrow & 7)) << 4)) = v;
+        if (row_ok) *reinterpret_cast<uint4*>(p.h1b + row * H + c * 32 + u * 8) = v;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_h1);
+    // ---- epilogue 2: z = acc2 + b2; y = z / max(|z|, 1e-12) --------------------------------------------------
+    mbar_wait(bar_acc2, 0);
+    tc_fence_after();
+    float ss = 0.f;
+    for (int c = 0; c < H / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem_a2 + lane_addr + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float v = __uint_as_float(r[j]) + bias_s[H + c * 32 + j];
+        ss = fmaf(v, v, ss);
+      }
+    }
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = 0; c < H / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem_a2 + lane_addr + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      if (row_ok) {
+        float zv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) zv[j] = __uint_as_float(r[j]) + bias_s[H + c * 32 + j];
+        if (p.z) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(p.z + row * H + c * 32 + j) = make_float4(zv[j], zv[j + 1], zv[j + 2], zv[j + 3]);
+        }
+        if (p.y) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(p.y + row * H + c * 32 + j) =
+                make_float4(zv[j] * inv, zv[j + 1] * inv, zv[j + 2] * inv, zv[j + 3] * inv);
+        }
+        if (p.yb) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint4 v = make_uint4(pack_bf16x2(zv[8 * u] * inv, zv[8 * u + 1] * inv), pack_bf16x2(zv[8 * u + 2] * inv, zv[8 * u + 3] * inv),
+                                       pack_bf16x2(zv[8 * u + 4] * inv, zv[8 * u + 5] * inv), pack_bf16x2(zv[8 * u + 6] * inv, zv[8 * u + 7] * inv));
+            *reinterpret_cast<uint4*>(p.yb + row * H + c * 32 + u * 8) = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static size_t mlp_fused_smem(int E, int H) {
+  const int kE = E / 64, kH = H / 64;
+  return 1024 + (size_t)kE * MLP_BM * 128 + (size_t)kE * H * 128 + (size_t)(kH - 1) * H * 128 + (size_t)kH * MLP_BM * 128 +
+         2 * (size_t)H * 4 + 8 * 8 + 16;
+}
+
+}  // namespace tc
+
+// shapes the fused kernel tiles: k-blocks of 64, W2 k-block 0 must fit in the x/W1 bytes, 227 KB of shared memory
+bool tc_mlp_fused_supported(int E, int H) {
+  if (E % 64 != 0 || H % 64 != 0 || E < 64 || H < 64 || H > 256) return false;
+  const int kE = E / 64;
+  if ((size_t)kE * tc::MLP_BM * 128 + (size_t)kE * H * 128 < (size_t)H * 128) return false;
+  return tc::mlp_fused_smem(E, H) <= 227 * 1024;
+}
+
+int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const float* b1, const __nv_bfloat16* w2b,
+                     const float* b2, int64_t R, int E, int H, __nv_bfloat16* h1b, float* z, float* y,
+                     __nv_bfloat16* yb, cudaStream_t s) {
+  CUtensorMap tmX, tmW1, tmW2;
+  int rc = tc::make_tmap_bf16(&tmX, xb, (uint64_t)R, (uint64_t)E, tc::MLP_BM); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmW1, w1b, (uint64_t)H, (uint64_t)E, (uint32_t)H); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmW2, w2b, (uint64_t)H, (uint64_t)H, (uint32_t)H); if (rc) return rc;
+  tc::MlpFwdParams p{};
+  p.R = R; p.E = E; p.H = H; p.b1 = b1; p.b2 = b2; p.h1b = h1b; p.z = z; p.y = y; p.yb = yb;
+  const size_t smem = tc::mlp_fused_smem(E, H);
+  TT_CUDA(cudaFuncSetAttribute(tc::tc_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::tc_mlp_fwd_kernel<<<(unsigned)ceil_div(R, tc::MLP_BM), tc::MLP_THREADS, smem, s>>>(tmX, tmW1, tmW2, p);
+  TT_LAUNCH_CHECK("tc_mlp_fwd_kernel");
+  return TT_OK;
+}
+
+}  // namespace tt

@@ -17,6 +17,12 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
                const __nv_bfloat16* w2_bf16, const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride,
                void* ws, size_t ws_bytes, cudaStream_t s);
 
+// whole-MLP forward in one kernel (tc_mlp.cu)
+bool tc_mlp_fused_supported(int E, int H);
+int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const float* b1, const __nv_bfloat16* w2b,
+                     const float* b2, int64_t R, int E, int H, __nv_bfloat16* h1b, float* z, float* y,
+                     __nv_bfloat16* yb, cudaStream_t s);
+
 // fused similarity GEMM + online-LSE cross entropy on tcgen05 (tc_inbatch.cu)
 size_t tc_inbatch_workspace(int64_t Bq, int64_t Bd, int H);
 int tc_inbatch_fwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16,

@@ -256,7 +256,8 @@ int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
                const void* w1_bf16, const void* w2_bf16, void* h1_bf16, int precision,
                void* workspace, size_t workspace_bytes, void* stream) {
   TT_REQUIRE_DEVICE();
-  TT_CHECK_ARG(x && w1 && b1 && w2 && b2 && h1 && z && y && R >= 0 && E > 0 && H > 0, "mlp_fwd: bad arguments");
+  TT_CHECK_ARG(x && w1 && b1 && w2 && b2 && h1 && z && R >= 0 && E > 0 && H > 0, "mlp_fwd: bad arguments");
+  TT_CHECK_ARG(y || (precision == TT_PREC_BF16 && y_bf16), "mlp_fwd: y may be null only in TT_PREC_BF16 with y_bf16 given");
   TT_CHECK_ARG(R < (1ll << 31), "mlp_fwd: R too large");
   if (R == 0) return TT_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -160,8 +160,9 @@ class FusedTrainer:
         xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
+            y_ptr = None if (self.dy_parts > 1 and yb is not None) else y      # fp32 y unused on the pure bf16 path
             check(lib.tt_mlp_fwd(_p(x), _p(l1.weight), _p(l1.bias), _p(l2.weight), _p(l2.bias), nr, self.E, self.H,
-                                 _p(sv["h1"]), _p(sv["z"]), _p(y), _p(yb), _p(xb), _p(self._shadow(l1.weight)),
+                                 _p(sv["h1"]), _p(sv["z"]), _p(y_ptr), _p(yb), _p(xb), _p(self._shadow(l1.weight)),
                                  _p(self._shadow(l2.weight)), _p(self.h1_bf16[gi]), self.prec, _p(self.ws),
                                  self.ws.numel(), s), "tt_mlp_fwd")
         elif tower.has_projection:

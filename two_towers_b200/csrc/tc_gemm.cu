@@ -76,6 +76,7 @@ struct GemmParams {
   const __nv_bfloat16* mask;  // nullable bf16 [M,ldmask]: out = mask > 0 ? acc : 0 (only without bias / act)
   int ldmask;
   int splits;
+  int tiles_m, tiles_n, nblocks;   // block decomposition of this problem inside a (possibly shared) launch
   float* colsum_part;         // nullable [ceil(M/32), N]: per-32-row column sums of the epilogue output (bias grads)
 };
 
@@ -84,9 +85,18 @@ constexpr int kGemmThreads = 192;
 constexpr int BM = 128, BK = 64;
 constexpr uint32_t kATile = BM * BK * 2;                         // 16 KB
 
+// Up to two independent GEMM problems share one launch (e.g. {dW2 = dz^T h1, da1 = dz W2} in the tower
+// backward): CTAs [0, p0.nblocks) work on problem 0, the rest on problem 1.
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0, const GemmParams p0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const GemmParams p1) {
+  const bool second = (int)blockIdx.x >= p0.nblocks;
+  const GemmParams& p = second ? p1 : p0;
+  const CUtensorMap& tmA = second ? tmA1 : tmA0;
+  const CUtensorMap& tmB = second ? tmB1 : tmB0;
+  const int lin = (int)blockIdx.x - (second ? p0.nblocks : 0);
+  const int bx = lin % p.tiles_n, by = (lin / p.tiles_n) % p.tiles_m, bz = lin / (p.tiles_n * p.tiles_m);
   constexpr uint32_t kBTile = BN * BK * 2;
   constexpr uint32_t kStageBytes = kATile + kBTile;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -99,9 +109,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* stage_tiles = reinterpret_cast<uint8_t*>(tmem_slot) + 128 - (((2 * kStages + 1) * 8) & 127);   // 128-B aligned: 4 x [32][36] fp32 staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = by * BM, n0 = bx * BN;
   const int total_kb = (p.K + BK - 1) / BK;
-  const int kb_beg = blockIdx.z * p.kblocks_per_split;
+  const int kb_beg = bz * p.kblocks_per_split;
   const int kb_end = min(total_kb, kb_beg + p.kblocks_per_split);
   const int nkb = max(0, kb_end - kb_beg);
 
@@ -162,7 +172,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     const bool split = p.splits > 1;
-    float* outp = split ? p.C + (size_t)blockIdx.z * p.M * p.N : p.C;
+    float* outp = split ? p.C + (size_t)bz * p.M * p.N : p.C;
     const int ldo = split ? p.N : p.ldc;
     const int row0 = m0 + quarter * 32;
 #pragma unroll 1
@@ -267,14 +277,13 @@ struct TcGemm {
 };
 
 template <int BN>
-static int launch_gemm(const TcGemm& g, cudaStream_t s) {
-  CUtensorMap tmA, tmB;
+static int fill_problem(const TcGemm& g, CUtensorMap* tmA, CUtensorMap* tmB, GemmParams* pp) {
   int rc;
-  if (!g.a_mn) rc = make_tmap_bf16(&tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM);
-  else         rc = make_tmap_bf16(&tmA, g.A, (uint64_t)g.K, (uint64_t)g.M, 64);
+  if (!g.a_mn) rc = make_tmap_bf16(tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM);
+  else         rc = make_tmap_bf16(tmA, g.A, (uint64_t)g.K, (uint64_t)g.M, 64);
   if (rc) return rc;
-  if (!g.b_mn) rc = make_tmap_bf16(&tmB, g.B, (uint64_t)g.N, (uint64_t)g.K, BN);
-  else         rc = make_tmap_bf16(&tmB, g.B, (uint64_t)g.K, (uint64_t)g.N, 64);
+  if (!g.b_mn) rc = make_tmap_bf16(tmB, g.B, (uint64_t)g.N, (uint64_t)g.K, BN);
+  else         rc = make_tmap_bf16(tmB, g.B, (uint64_t)g.K, (uint64_t)g.N, 64);
   if (rc) return rc;
   GemmParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.a_mn = g.a_mn; p.b_mn = g.b_mn;
@@ -284,11 +293,13 @@ static int launch_gemm(const TcGemm& g, cudaStream_t s) {
   p.C = g.splits > 1 ? g.partial : g.C;
   p.Cb = g.Cb; p.ldc = g.ldc; p.bias = g.bias; p.act = g.act; p.mask = g.mask; p.ldmask = g.ldmask;
   p.colsum_part = g.colsum_part;
-  constexpr size_t smem = gemm_smem_bytes<BN>();
-  TT_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(g.N, BN), (unsigned)ceil_div(g.M, BM), (unsigned)g.splits);
-  tc_gemm_kernel<BN><<<grid, kGemmThreads, smem, s>>>(tmA, tmB, p);
-  TT_LAUNCH_CHECK("tc_gemm_kernel");
+  p.tiles_n = (int)ceil_div(g.N, BN); p.tiles_m = (int)ceil_div(g.M, BM);
+  p.nblocks = p.tiles_n * p.tiles_m * g.splits;
+  *pp = p;
+  return TT_OK;
+}
+
+static int finish_problem(const TcGemm& g, cudaStream_t s) {
   if (g.splits > 1 && !g.defer_reduce) {
     // fixed-order reduction + epilogue (shared with the fp32 path)
     SgemmArgs a{};
@@ -299,12 +310,44 @@ static int launch_gemm(const TcGemm& g, cudaStream_t s) {
   return TT_OK;
 }
 
-int tc_gemm(const TcGemm& g, cudaStream_t s) {
+// g1 may be null (single problem).  Both problems must use the same tile width BN.
+template <int BN>
+static int launch_gemm_pair(const TcGemm& g0, const TcGemm* g1, cudaStream_t s) {
+  CUtensorMap tmA0, tmB0, tmA1, tmB1;
+  GemmParams p0{}, p1{};
+  int rc = fill_problem<BN>(g0, &tmA0, &tmB0, &p0); if (rc) return rc;
+  if (g1) { rc = fill_problem<BN>(*g1, &tmA1, &tmB1, &p1); if (rc) return rc; }
+  else { tmA1 = tmA0; tmB1 = tmB0; p1 = p0; p1.nblocks = 0; }
+  constexpr size_t smem = gemm_smem_bytes<BN>();
+  TT_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_gemm_kernel<BN><<<(unsigned)(p0.nblocks + p1.nblocks), kGemmThreads, smem, s>>>(tmA0, tmB0, p0, tmA1, tmB1, p1);
+  TT_LAUNCH_CHECK("tc_gemm_kernel");
+  rc = finish_problem(g0, s); if (rc) return rc;
+  if (g1) { rc = finish_problem(*g1, s); if (rc) return rc; }
+  return TT_OK;
+}
+
+static int check_problem(const TcGemm& g) {
   TT_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "tc_gemm: bad shape");
   TT_CHECK_ARG(g.splits == 1 || (g.partial && g.C && !g.Cb && !g.mask), "tc_gemm: split-K needs partial + fp32 output only");
   TT_CHECK_ARG(!g.mask || (!g.bias && g.act == 0), "tc_gemm: the gate mask is applied to the raw accumulator (no bias / act)");
-  if (g.N <= 64) return launch_gemm<64>(g, s);
-  return launch_gemm<128>(g, s);            // 128-wide tiles: twice the CTAs of 256-wide ones for N = 256
+  return TT_OK;
+}
+
+int tc_gemm(const TcGemm& g, cudaStream_t s) {
+  int rc = check_problem(g); if (rc) return rc;
+  if (g.N <= 64) return launch_gemm_pair<64>(g, nullptr, s);
+  return launch_gemm_pair<128>(g, nullptr, s);            // 128-wide tiles: twice the CTAs of 256-wide ones for N = 256
+}
+
+// two independent problems in one launch (same tile-width class)
+int tc_gemm2(const TcGemm& g0, const TcGemm& g1, cudaStream_t s) {
+  int rc = check_problem(g0); if (rc) return rc;
+  rc = check_problem(g1); if (rc) return rc;
+  const bool n0 = g0.N <= 64, n1 = g1.N <= 64;
+  if (n0 != n1) { rc = tc_gemm(g0, s); if (rc) return rc; return tc_gemm(g1, s); }
+  if (n0) return launch_gemm_pair<64>(g0, &g1, s);
+  return launch_gemm_pair<128>(g0, &g1, s);
 }
 
 static int pick_splits(int M, int N, int K) {
@@ -562,26 +605,22 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
     TT_LAUNCH_CHECK("l2norm_bwd_bf16_kernel");
     rc = colsum(dz, R, H, H, db2, cpart, s); if (rc) return rc;
   }
-  tc::TcGemm g{};
-  // dw2[H,H] = dz^T h1 : A = dz stored [K=R, M=H] (MN-major), B = h1 stored [K=R, N=H] (MN-major)
-  g.M = H; g.N = H; g.K = (int)R; g.A = dzb; g.a_mn = 1; g.B = h1a; g.b_mn = 1; g.C = dw2; g.ldc = H;
-  g.splits = plan.s_dw2; g.partial = partial; g.defer_reduce = true;
-  rc = tc::tc_gemm(g, s); if (rc) return rc;
-  // da1[R,H] = (dz w2) * (h1 > 0) : A = dz [M=R,K=H] K-major, B = w2 stored [K=H_out, N=H_in] (MN-major)
-  g = tc::TcGemm{};
-  g.M = (int)R; g.N = H; g.K = H; g.A = dzb; g.a_mn = 0; g.B = w2a; g.b_mn = 1; g.C = nullptr; g.Cb = da1b; g.ldc = H;
-  g.mask = h1a; g.ldmask = H; g.colsum_part = cs1;      // fp32 da1 is never needed: db1 comes from the column-sum partials
-  rc = tc::tc_gemm(g, s); if (rc) return rc;
-  // dw1[H,E] = da1^T x
-  g = tc::TcGemm{};
-  g.M = H; g.N = E; g.K = (int)R; g.A = da1b; g.a_mn = 1; g.B = xa; g.b_mn = 1; g.C = dw1; g.ldc = E;
-  g.splits = plan.s_dw1; g.partial = partial2; g.defer_reduce = true;
-  rc = tc::tc_gemm(g, s); if (rc) return rc;
+  // launch 1: { dw2[H,H] = dz^T h1 (split-K partials),  da1[R,H] = (dz w2) * (h1 > 0) } -- independent, one grid
+  tc::TcGemm gw2{}, ga1{};
+  gw2.M = H; gw2.N = H; gw2.K = (int)R; gw2.A = dzb; gw2.a_mn = 1; gw2.B = h1a; gw2.b_mn = 1; gw2.C = dw2; gw2.ldc = H;
+  gw2.splits = plan.s_dw2; gw2.partial = partial; gw2.defer_reduce = true;
+  ga1.M = (int)R; ga1.N = H; ga1.K = H; ga1.A = dzb; ga1.a_mn = 0; ga1.B = w2a; ga1.b_mn = 1; ga1.C = nullptr; ga1.Cb = da1b;
+  ga1.ldc = H; ga1.mask = h1a; ga1.ldmask = H; ga1.colsum_part = cs1;   // fp32 da1 never needed: db1 comes from cs1
+  rc = tc::tc_gemm2(ga1, gw2, s); if (rc) return rc;
+  // launch 2: { dw1[H,E] = da1^T x (split-K partials),  dx[R,E] = da1 w1 }
+  tc::TcGemm gw1{}, gdx{};
+  gw1.M = H; gw1.N = E; gw1.K = (int)R; gw1.A = da1b; gw1.a_mn = 1; gw1.B = xa; gw1.b_mn = 1; gw1.C = dw1; gw1.ldc = E;
+  gw1.splits = plan.s_dw1; gw1.partial = partial2; gw1.defer_reduce = true;
   if (dx) {
-    // dx[R,E] = da1 w1 : A = da1 K-major, B = w1 stored [K=H, N=E] (MN-major)
-    g = tc::TcGemm{};
-    g.M = (int)R; g.N = E; g.K = H; g.A = da1b; g.a_mn = 0; g.B = w1a; g.b_mn = 1; g.C = dx; g.ldc = E;
-    rc = tc::tc_gemm(g, s); if (rc) return rc;
+    gdx.M = (int)R; gdx.N = E; gdx.K = H; gdx.A = da1b; gdx.a_mn = 0; gdx.B = w1a; gdx.b_mn = 1; gdx.C = dx; gdx.ldc = E;
+    rc = tc::tc_gemm2(gdx, gw1, s); if (rc) return rc;
+  } else {
+    rc = tc::tc_gemm(gw1, s); if (rc) return rc;
   }
   // one launch finishes every reduction of this call in a fixed order: dW2, dW1 split-K partials, db1, db2
   ReduceJobs jobs{};

@@ -16,6 +16,7 @@
 // Each output row has one owner CTA per split and splits are summed in split order:
 // bitwise-reproducible gradients.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 #include "tensor_core.cuh"
@@ -197,6 +198,7 @@ struct BwdParams {
   float coef;                  // loss_scale / temperature
   float* out[2];               // pass outputs: [nsplit][Bx][H] partials (slice stride below) or the final tensor
   int64_t part_stride[2];      // elements between consecutive split slices
+  long long* dbg;              // optional timeline buffer (TT_CE_DEBUG=1): [role 0..1][tile][8] clock64 stamps of CTA (0,0,0)
 };
 
 // X rows = this CTA's 128 output rows, Y = streamed 64-row tiles.
@@ -229,6 +231,8 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   const int t_beg = blockIdx.y * tiles_per_split;
   const int t_end = min(ntiles, t_beg + tiles_per_split);
   const int nt = max(0, t_end - t_beg);
+  long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg : nullptr;
+#define TT_STAMP(role, tile, slot) do { if (dbg) dbg[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(tmX); tma_prefetch_desc(tmY);
@@ -272,8 +276,11 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       const uint64_t dym0 = umma_desc_mnmajor(smem_u32(y_tiles), 0, CE_BN * 128);
       auto issue_s = [&](int i) {
         const int s = i % BWD_STAGES, b = i & 1;
+        TT_STAMP(0, i, 0);
         mbar_wait(&y_full[s], (i / BWD_STAGES) & 1);
+        TT_STAMP(0, i, 1);
         mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
+        TT_STAMP(0, i, 2);
         tc_fence_after();
         const uint64_t dy = dyk0 + (uint64_t)((s * y_bytes) >> 4);
         for (int kb = 0; kb < kq; ++kb)
@@ -282,13 +289,16 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
             umma_bf16(tmem_s + b * CE_BN, dx0 + (uint64_t)(kb * (CE_BM * 128 / 16) + k * 2),
                       dy + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc_s, (kb | k) != 0);
         umma_commit(&s_full[b]);
+        TT_STAMP(0, i, 3);
       };
       mbar_wait(x_bar, 0);
       issue_s(0);
       for (int i = 0; i < nt; ++i) {
         if (i + 1 < nt) issue_s(i + 1);
         const int s = i % BWD_STAGES, b = i & 1;
+        TT_STAMP(0, i, 4);
         mbar_wait(&p_full[b], (i >> 1) & 1);
+        TT_STAMP(0, i, 5);
         tc_fence_after();
         const uint64_t dp = dp0 + (uint64_t)((b * p_bytes) >> 4);
         const uint64_t dy = dym0 + (uint64_t)((s * y_bytes) >> 4);
@@ -297,6 +307,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
           umma_bf16(tmem_o, dp + (uint64_t)(k * 2), dy + (uint64_t)(k * (2048 / 16)), idesc_o, (i | k) != 0);
         umma_commit(&p_empty[b]);
         umma_commit(&y_empty[s]);
+        TT_STAMP(0, i, 6);
       }
       umma_commit(o_full);
     }
@@ -316,7 +327,9 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         cl0 = (y0 + lane < By) ? __ldg(p.lse + y0 + lane) * kLog2e : CUDART_INF_F;
         cl1 = (y0 + 32 + lane < By) ? __ldg(p.lse + y0 + 32 + lane) * kLog2e : CUDART_INF_F;
       }
+      if (threadIdx.x == 64) TT_STAMP(1, i, 0);
       mbar_wait(&s_full[b], (i >> 1) & 1);
+      if (threadIdx.x == 64) TT_STAMP(1, i, 1);
       tc_fence_after();
       uint32_t r0[32], r1[32];
       const uint32_t ta = tmem_s + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * CE_BN);
@@ -326,6 +339,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);
+      if (threadIdx.x == 64) TT_STAMP(1, i, 2);
       // P = exp2(S*c - lse*log2e); ragged columns get lse = +inf -> P = 0 (row mode: masked below)
       float pv[64];
 #pragma unroll
@@ -347,7 +361,9 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
           for (int j = 0; j < 64; ++j) pv[j] -= (j == (int)pj) ? 1.0f : 0.0f;     // select, keeps pv[] in registers
         }
       }
+      if (threadIdx.x == 64) TT_STAMP(1, i, 3);
       mbar_wait(&p_empty[b], ((i >> 1) & 1) ^ 1);          // O-GEMM(i-2) has finished reading this P buffer
+      if (threadIdx.x == 64) TT_STAMP(1, i, 4);
       uint8_t* prow = p_tiles + b * p_bytes + lrow * 128;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {                      // 8 x 16-byte chunks, 128B swizzle: chunk ^= row & 7
@@ -358,6 +374,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
+      if (threadIdx.x == 64) TT_STAMP(1, i, 5);
     }
     // final: O (TMEM) -> registers -> warp-private smem transpose -> 128-byte coalesced global stores
     const float scale = p.coef * (p.grad_out ? *p.grad_out : 1.0f);
@@ -514,6 +531,9 @@ static int launch_tc_bwd(const __nv_bfloat16* qa, const __nv_bfloat16* da, const
   p.out[0] = out_q; p.out[1] = out_d; p.part_stride[0] = stride_q; p.part_stride[1] = stride_d;
   const size_t smem = tc::bwd_smem(H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
+  long long* dbg_dev = nullptr;
+  if (dbg_on) { cudaMalloc(&dbg_dev, 2 * 64 * 8 * sizeof(long long)); cudaMemset(dbg_dev, 0, 2 * 64 * 8 * sizeof(long long)); p.dbg = dbg_dev; }
   const int64_t xq = ceil_div(Bq, tc::CE_BM), xd = ceil_div(Bd, tc::CE_BM);
   // pass 0 = dQ, pass 1 = dD; a missing output shrinks the grid to the other pass
   if (out_q && out_d) {
@@ -529,6 +549,22 @@ static int launch_tc_bwd(const __nv_bfloat16* qa, const __nv_bfloat16* da, const
     tc::tc_ce_bwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ128, tmQ64, tmD128, tmD64, p);
   }
   TT_LAUNCH_CHECK("tc_ce_bwd_kernel");
+  if (dbg_on) {                                              // developer aid: per-tile timeline of CTA (0,0,0)
+    static long long host[2 * 64 * 8];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(host, dbg_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaFree(dbg_dev);
+    const long long t0 = host[0];
+    const int ntl = p.tiles_per_split[0] < 64 ? p.tiles_per_split[0] : 64;
+    printf("[tt ce_bwd timeline, cycles since first stamp] tile: MMA{s_issue_begin,y_full,s_empty,s_issued,o_wait,p_full,o_issued} EPI{begin,s_full,loaded,computed,p_empty,p_written}\n");
+    for (int t = 0; t < ntl; ++t) {
+      printf("  %2d: MMA", t);
+      for (int k = 0; k < 7; ++k) printf(" %6lld", host[(0 * 64 + t) * 8 + k] ? host[(0 * 64 + t) * 8 + k] - t0 : -1);
+      printf("   EPI");
+      for (int k = 0; k < 6; ++k) printf(" %6lld", host[(1 * 64 + t) * 8 + k] ? host[(1 * 64 + t) * 8 + k] - t0 : -1);
+      printf("\n");
+    }
+  }
   return TT_OK;
 }
 

@@ -80,7 +80,10 @@ def _worker(rank, world, port, q_out):
         import traceback
         q_out.put((rank, traceback.format_exc()))
     finally:
-        dist.destroy_process_group()
+        # results are already in the queue: leave without the (occasionally slow) NCCL / CUDA-graph teardown
+        torch.cuda.synchronize()
+        q_out.close(); q_out.join_thread()
+        os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -94,6 +97,8 @@ def test_two_gpu_nccl_equivalence():
         p.start()
     results = [q.get(timeout=600) for _ in procs]
     for p in procs:
-        p.join(60)
+        p.join(30)
+        if p.is_alive():
+            p.kill()
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}:\n{msg}"

@@ -52,23 +52,26 @@ embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ tab
       int cnt = 0;
       // ids are read 32 tokens at a time with ONE coalesced load per lane and handed to the token
       // groups by shuffle, so the gather loads below do not wait on a per-token id load.
+      constexpr int TOK = NACC == 1 ? 16 : (NACC == 2 ? 8 : 4);      // tokens in flight per group (16 LDG.128 per lane)
+      int64_t next_id = (lane < L) ? load_id(rid + lane) : 0;
       for (int tb = 0; tb < L; tb += 32) {
-        const int64_t my_id = (tb + lane < L) ? load_id(rid + tb + lane) : 0;
+        const int64_t my_id = next_id;
+        if (tb + 32 < L) next_id = (tb + 32 + lane < L) ? load_id(rid + tb + 32 + lane) : 0;   // prefetch the next id block
         const int my_row = (my_id > 0 && my_id < V) ? (int)my_id : -1;       // -1 == masked token
         cnt += __popc(__ballot_sync(0xffffffffu, my_row >= 0));
         const int nb = min(32, L - tb);
-        for (int tbase = 0; tbase < nb; tbase += 4 * groups) {     // warp-uniform trip count (shuffles inside)
+        for (int tbase = 0; tbase < nb; tbase += TOK * groups) {     // warp-uniform trip count (shuffles inside)
           const int t0 = tbase + grp;
-          int trow[4];
+          int trow[TOK];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < TOK; ++u) {
             const int t = t0 + u * groups;
             const int r = __shfl_sync(0xffffffffu, my_row, t & 31);
             trow[u] = (t < nb) ? r : -1;
           }
-          float4 v[4][NACC];
+          float4 v[TOK][NACC];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < TOK; ++u) {
             const float4* src = reinterpret_cast<const float4*>(table + (int64_t)(trow[u] < 0 ? 0 : trow[u]) * E);
 #pragma unroll
             for (int j = 0; j < NACC; ++j) {
@@ -77,7 +80,7 @@ embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ tab
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < TOK; ++u)
 #pragma unroll
             for (int j = 0; j < NACC; ++j) {
               acc[j].x += v[u][j].x; acc[j].y += v[u][j].y; acc[j].z += v[u][j].z; acc[j].w += v[u][j].w;

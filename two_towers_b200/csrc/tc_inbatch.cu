@@ -66,7 +66,8 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* d_empty = d_full + FWD_STAGES;
   uint64_t* s_full = d_empty + FWD_STAGES;                // [2]
   uint64_t* s_empty = s_full + 2;                         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+  uint64_t* q_ready = s_empty + 2;                        // Q tile copied into TMEM (4 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t x0 = (int64_t)blockIdx.x * CE_BM;
@@ -80,13 +81,15 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(q_bar, 1);
     for (int s = 0; s < FWD_STAGES; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4); }
+    mbar_init(q_ready, 4);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_s = *tmem_slot;
+  const uint32_t tmem_s = *tmem_slot;                     // columns [0,128): two S buffers
+  const uint32_t tmem_q = tmem_s + 128;                   // columns [128, 128 + H/2): Q tile (TMEM A operand)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -103,9 +106,9 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(CE_BM, CE_BN, 0, 0);
-      const uint64_t dq0 = umma_desc_kmajor(smem_u32(q_tile), 0);
       const uint64_t dd0 = umma_desc_kmajor(smem_u32(d_tiles), 0);
-      mbar_wait(q_bar, 0);
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
       for (int i = 0; i < nt; ++i) {
         const int s = i % FWD_STAGES, b = i & 1;
         mbar_wait(&d_full[s], (i / FWD_STAGES) & 1);
@@ -115,8 +118,8 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int kb = 0; kb < kq; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_s + b * CE_BN, dq0 + (uint64_t)(kb * (CE_BM * 128 / 16) + k * 2),
-                      dd + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc, (kb | k) != 0);
+            umma_bf16_ts(tmem_s + b * CE_BN, tmem_q + (uint32_t)(kb * 32 + k * 8),
+                         dd + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc, (kb | k) != 0);
         umma_commit(&d_empty[s]);
         umma_commit(&s_full[b]);
       }
@@ -126,6 +129,25 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int64_t row = x0 + quarter * 32 + lane;
     const int64_t pcol = row + label_offset;
     const float c = inv_temp * kLog2e;
+    // Q tile: smem (TMA, 128B swizzle) -> registers -> TMEM, so every S product reads A from tensor memory
+    {
+      const int lrow = quarter * 32 + lane;
+      mbar_wait(q_bar, 0);
+      for (int kb = 0; kb < kq; ++kb) {
+        uint32_t xr[32];
+        const uint8_t* xrow = q_tile + kb * (CE_BM * 128) + lrow * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint4 v = *reinterpret_cast<const uint4*>(xrow + ((ch ^ (lrow & 7)) << 4));
+          xr[4 * ch] = v.x; xr[4 * ch + 1] = v.y; xr[4 * ch + 2] = v.z; xr[4 * ch + 3] = v.w;
+        }
+        tmem_st_x32(tmem_q + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kb * 32), xr);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);
+    }
     float m = -CUDART_INF_F, l = 0.f;
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
@@ -179,7 +201,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_s, 128);
+  if (warp == 1) tmem_dealloc(tmem_s, 256);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -223,7 +245,8 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   uint64_t* p_full = s_empty + 2;                         // [2]
   uint64_t* p_empty = p_full + 2;                         // [2]
   uint64_t* o_full = p_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* x_ready = o_full + 1;                         // X tile copied into TMEM (4 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t x0 = (int64_t)blockIdx.x * CE_BM;
@@ -243,6 +266,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1);
     }
     mbar_init(o_full, 1);
+    mbar_init(x_ready, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -252,6 +276,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base;                      // columns [0, H)
   const uint32_t tmem_s = tmem_base + 256;                // columns [256, 384): two S buffers
+  const uint32_t tmem_x = tmem_base + 384;                // columns [384, 384 + H/2): the X tile as the TMEM A operand
 
   if (warp == 0) {
     if (lane == 0) {
@@ -270,7 +295,6 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       const uint32_t idesc_s = umma_idesc_bf16(CE_BM, CE_BN, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(CE_BM, H, 0, 1);     // B = Y tile read MN-major
       // descriptors differ only in the (address >> 4) field: build once, then add small constants
-      const uint64_t dx0 = umma_desc_kmajor(smem_u32(x_tile), 0);
       const uint64_t dp0 = umma_desc_kmajor(smem_u32(p_tiles), 0);
       const uint64_t dyk0 = umma_desc_kmajor(smem_u32(y_tiles), 0);
       const uint64_t dym0 = umma_desc_mnmajor(smem_u32(y_tiles), 0, CE_BN * 128);
@@ -286,12 +310,13 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         for (int kb = 0; kb < kq; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_s + b * CE_BN, dx0 + (uint64_t)(kb * (CE_BM * 128 / 16) + k * 2),
-                      dy + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc_s, (kb | k) != 0);
+            umma_bf16_ts(tmem_s + b * CE_BN, tmem_x + (uint32_t)(kb * 32 + k * 8),
+                         dy + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc_s, (kb | k) != 0);
         umma_commit(&s_full[b]);
         TT_STAMP(0, i, 3);
       };
-      mbar_wait(x_bar, 0);
+      mbar_wait(x_ready, 0);
+      tc_fence_after();
       issue_s(0);
       for (int i = 0; i < nt; ++i) {
         if (i + 1 < nt) issue_s(i + 1);
@@ -317,6 +342,24 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     const int64_t row = x0 + lrow;
     const float c = p.inv_temp * kLog2e;
     const float row_lse = (!COL && row < Bx) ? p.lse[row] * kLog2e : 0.f;
+    // X tile: shared memory (TMA, 128B swizzle) -> registers -> TMEM.  Every S = X Y^T product of this CTA then
+    // reads its A operand from tensor memory; with A in smem the 128x16 slice re-read per MMA saturates the
+    // shared-memory port and the N=64 product runs at half rate (measured 66 vs 32 cycles per tcgen05.mma).
+    mbar_wait(x_bar, 0);
+    for (int kb = 0; kb < kq; ++kb) {
+      uint32_t xr[32];
+      const uint8_t* xrow = x_tile + kb * (CE_BM * 128) + lrow * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xrow + ((ch ^ (lrow & 7)) << 4));
+        xr[4 * ch] = v.x; xr[4 * ch + 1] = v.y; xr[4 * ch + 2] = v.z; xr[4 * ch + 3] = v.w;
+      }
+      tmem_st_x32(tmem_x + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kb * 32), xr);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(x_ready);
     // Y tiles that can hold a positive of one of this CTA's rows (CTA-uniform band)
     const int64_t band_lo = COL ? x0 - p.label_offset : x0 + p.label_offset;
     for (int i = 0; i < nt; ++i) {
@@ -427,9 +470,9 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_consta
   else           ce_bwd_body<true>(&tmD128, &tmQ64, p, Bx, By, p.tiles_per_split[1], out, base);
 }
 
-static size_t fwd_smem(int H) { return 1024 + (size_t)CE_BM * H * 2 + FWD_STAGES * (size_t)CE_BN * H * 2 + 16 * 8 + 16; }
+static size_t fwd_smem(int H) { return 1024 + (size_t)CE_BM * H * 2 + FWD_STAGES * (size_t)CE_BN * H * 2 + 20 * 8 + 16; }
 static size_t bwd_smem(int H) {
-  return 1024 + (size_t)CE_BM * H * 2 + BWD_STAGES * (size_t)CE_BN * H * 2 + 2 * (size_t)CE_BM * CE_BN * 2 + 20 * 8 + 16;
+  return 1024 + (size_t)CE_BM * H * 2 + BWD_STAGES * (size_t)CE_BN * H * 2 + 2 * (size_t)CE_BM * CE_BN * 2 + 24 * 8 + 16;
 }
 
 static int pick_split(int64_t xtiles, int64_t By) {

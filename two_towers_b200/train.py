@@ -138,7 +138,8 @@ class FusedTrainer:
                  lib.tt_inbatch_ce_workspace(B * self.world, B * self.world, self.H, self.prec))
         self.ws = torch.empty(int(nb), dtype=torch.uint8, device=self.dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self._pinned_ids = None
+        self._stage = None
+        self._staged = False
         self.steps_done = 0
 
     # ---------------------------------------------------------------------------------------
@@ -262,6 +263,38 @@ class FusedTrainer:
                 raise ValueError(f"expected ids of shape {(B, self.L)}, got {tuple(t.shape)}")
             self.ids[i * B:(i + 1) * B].copy_(t, non_blocking=True)
 
+    # ---- input pipelining: the next batch's host->device copy overlaps the current step ------------------
+    def prefetch(self, q_ids: torch.Tensor, d_ids: torch.Tensor, n_ids: Optional[torch.Tensor] = None) -> None:
+        """Start copying the NEXT batch (pinned host or device tensors, [B,L]) into a staging buffer on a
+        separate copy stream.  `step()` with no arguments then consumes it.  One batch may be in flight."""
+        if self._stage is None:
+            self._stage = torch.empty_like(self.ids)
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._copy_done = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream())
+        B = self.B
+        parts = [q_ids, d_ids] + ([n_ids] if self.passes == 3 else [])
+        if self.passes == 3 and n_ids is None:
+            raise ValueError("triplet loss needs negative ids")
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free)          # previous consumer has read the staging buffer
+            for i, t in enumerate(parts):
+                if tuple(t.shape) != (B, self.L):
+                    raise ValueError(f"expected ids of shape {(B, self.L)}, got {tuple(t.shape)}")
+                self._stage[i * B:(i + 1) * B].copy_(t, non_blocking=True)
+            self._copy_done.record(self._copy_stream)
+        self._staged = True
+
+    def _consume_prefetched(self) -> None:
+        if not self._staged:
+            raise RuntimeError("step() without arguments needs a prefetch() first")
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._copy_done)
+        self.ids.copy_(self._stage, non_blocking=True)              # device-to-device into the graph's static buffer
+        self._stage_free.record(cur)
+        self._staged = False
+
     def run(self) -> torch.Tensor:
         """One optimizer step on the batch currently in the static buffer; returns the loss (device scalar)."""
         if not self.use_graph:
@@ -291,8 +324,12 @@ class FusedTrainer:
         self.steps_done += 1
         return self.loss
 
-    def step(self, q_ids, d_ids, n_ids=None) -> torch.Tensor:
-        self.load_batch(q_ids, d_ids, n_ids)
+    def step(self, q_ids=None, d_ids=None, n_ids=None) -> torch.Tensor:
+        """One optimizer step.  With ids: copy them in and run.  Without: consume the batch started by prefetch()."""
+        if q_ids is None:
+            self._consume_prefetched()
+        else:
+            self.load_batch(q_ids, d_ids, n_ids)
         return self.run()
 
     def kernels_per_step(self) -> int:

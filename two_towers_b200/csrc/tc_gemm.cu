@@ -129,13 +129,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t tmem_acc = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % kStages, k0 = (kb_beg + i) * BK;
-        mbar_wait(&empty_bar[s], ((i / kStages) & 1) ^ 1);
+    for (int i = 0; i < nkb; ++i) {                       // whole warp, uniform control flow; one lane issues
+      const int s = i % kStages, k0 = (kb_beg + i) * BK;
+      mbar_wait(&empty_bar[s], ((i / kStages) & 1) ^ 1);
+      uint8_t* a = tiles + s * kStageBytes;
+      uint8_t* b = a + kATile;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        uint8_t* a = tiles + s * kStageBytes;
-        uint8_t* b = a + kATile;
         if (!p.a_mn) tma_load_2d(a, &tmA, &full_bar[s], k0, m0);
         else { tma_load_2d(a, &tmA, &full_bar[s], m0, k0); tma_load_2d(a + 8192, &tmA, &full_bar[s], m0 + 64, k0); }
         if (!p.b_mn) tma_load_2d(b, &tmB, &full_bar[s], k0, n0);
@@ -144,25 +144,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int j = 0; j < BN / 64; ++j) tma_load_2d(b + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, k0);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % kStages;
-        mbar_wait(&full_bar[s], (i / kStages) & 1);
-        tc_fence_after();
-        const uint32_t a = smem_u32(tiles + s * kStageBytes), b = a + kATile;
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % kStages;
+      mbar_wait(&full_bar[s], (i / kStages) & 1);
+      tc_fence_after();
+      const uint32_t a = smem_u32(tiles + s * kStageBytes), b = a + kATile;
+      const uint64_t da0 = p.a_mn ? umma_desc_mnmajor(a, 0, 8192u) : umma_desc_kmajor(a, 0);
+      const uint64_t db0 = p.b_mn ? umma_desc_mnmajor(b, 0, 8192u) : umma_desc_kmajor(b, 0);
+      const uint64_t sa = p.a_mn ? 128u : 2u, sb = p.b_mn ? 128u : 2u;     // (bytes per k16 step) >> 4
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = p.a_mn ? umma_desc_mnmajor(a, k, 8192u) : umma_desc_kmajor(a, k);
-          const uint64_t db = p.b_mn ? umma_desc_mnmajor(b, k, 8192u) : umma_desc_kmajor(b, k);
-          umma_bf16(tmem_acc, da, db, idesc, (i | k) != 0);
-        }
-        umma_commit(&empty_bar[s]);            // stage reusable once these MMAs have read it
+      for (int k = 0; k < BK / 16; ++k) {
+        if (elect_one()) umma_bf16(tmem_acc, da0 + sa * k, db0 + sb * k, idesc, (i | k) != 0);
       }
-      umma_commit(acc_bar);                    // accumulator complete
+      if (elect_one()) umma_commit(&empty_bar[s]);        // stage reusable once these MMAs have read it
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(acc_bar);                // accumulator complete
+    __syncwarp();
   } else {
     // epilogue warps 2..5 -> TMEM lane quarters (warp % 4).  Each thread holds one accumulator row;
     // a 32x32 chunk is transposed through a warp-private shared-memory tile so that global stores

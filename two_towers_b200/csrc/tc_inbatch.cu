@@ -92,37 +92,41 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_q = tmem_s + 128;                   // columns [128, 128 + H/2): Q tile (TMEM A operand)
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_bar, q_bytes);
       for (int kb = 0; kb < kq; ++kb) tma_load_2d(q_tile + kb * (CE_BM * 128), &tmQ, q_bar, kb * 64, (int)x0);
-      for (int i = 0; i < nt; ++i) {
-        const int s = i % FWD_STAGES;
-        mbar_wait(&d_empty[s], ((i / FWD_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int i = 0; i < nt; ++i) {                        // whole warp, uniform control flow; one lane issues
+      const int s = i % FWD_STAGES;
+      mbar_wait(&d_empty[s], ((i / FWD_STAGES) & 1) ^ 1);
+      uint8_t* dt = d_tiles + s * d_bytes;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&d_full[s], d_bytes);
-        uint8_t* dt = d_tiles + s * d_bytes;
         for (int kb = 0; kb < kq; ++kb) tma_load_2d(dt + kb * (CE_BN * 128), &tmD, &d_full[s], kb * 64, (t_beg + i) * CE_BN);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(CE_BM, CE_BN, 0, 0);
-      const uint64_t dd0 = umma_desc_kmajor(smem_u32(d_tiles), 0);
-      mbar_wait(q_ready, 0);
+    const uint32_t idesc = umma_idesc_bf16(CE_BM, CE_BN, 0, 0);
+    const uint64_t dd0 = umma_desc_kmajor(smem_u32(d_tiles), 0);
+    mbar_wait(q_ready, 0);
+    tc_fence_after();
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % FWD_STAGES, b = i & 1;
+      mbar_wait(&d_full[s], (i / FWD_STAGES) & 1);
+      mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
       tc_fence_after();
-      for (int i = 0; i < nt; ++i) {
-        const int s = i % FWD_STAGES, b = i & 1;
-        mbar_wait(&d_full[s], (i / FWD_STAGES) & 1);
-        mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t dd = dd0 + (uint64_t)((s * d_bytes) >> 4);
-        for (int kb = 0; kb < kq; ++kb)
+      const uint64_t dd = dd0 + (uint64_t)((s * d_bytes) >> 4);
+      for (int kb = 0; kb < kq; ++kb)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k) {
+          if (elect_one())
             umma_bf16_ts(tmem_s + b * CE_BN, tmem_q + (uint32_t)(kb * 32 + k * 8),
                          dd + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc, (kb | k) != 0);
-        umma_commit(&d_empty[s]);
-        umma_commit(&s_full[b]);
-      }
+        }
+      if (elect_one()) { umma_commit(&d_empty[s]); umma_commit(&s_full[b]); }
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
@@ -279,41 +283,49 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   const uint32_t tmem_x = tmem_base + 384;                // columns [384, 384 + H/2): the X tile as the TMEM A operand
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(x_bar, x_bytes);
       for (int kb = 0; kb < kq; ++kb) tma_load_2d(x_tile + kb * (CE_BM * 128), tmX, x_bar, kb * 64, (int)x0);
-      for (int i = 0; i < nt; ++i) {
-        const int s = i % BWD_STAGES;
-        mbar_wait(&y_empty[s], ((i / BWD_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int i = 0; i < nt; ++i) {                        // whole warp, uniform control flow; one lane issues
+      const int s = i % BWD_STAGES;
+      mbar_wait(&y_empty[s], ((i / BWD_STAGES) & 1) ^ 1);
+      uint8_t* yt = y_tiles + s * y_bytes;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&y_full[s], y_bytes);
-        uint8_t* yt = y_tiles + s * y_bytes;
         for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (CE_BN * 128), tmY, &y_full[s], kb * 64, (t_beg + i) * CE_BN);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0 && nt > 0) {
+    if (nt > 0) {
+      // whole warp in uniform control flow: descriptors live in uniform registers, only the tcgen05
+      // instructions are predicated on the elected lane
       const uint32_t idesc_s = umma_idesc_bf16(CE_BM, CE_BN, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(CE_BM, H, 0, 1);     // B = Y tile read MN-major
-      // descriptors differ only in the (address >> 4) field: build once, then add small constants
       const uint64_t dp0 = umma_desc_kmajor(smem_u32(p_tiles), 0);
       const uint64_t dyk0 = umma_desc_kmajor(smem_u32(y_tiles), 0);
       const uint64_t dym0 = umma_desc_mnmajor(smem_u32(y_tiles), 0, CE_BN * 128);
       auto issue_s = [&](int i) {
         const int s = i % BWD_STAGES, b = i & 1;
-        TT_STAMP(0, i, 0);
+        if (lane == 0) TT_STAMP(0, i, 0);
         mbar_wait(&y_full[s], (i / BWD_STAGES) & 1);
-        TT_STAMP(0, i, 1);
+        if (lane == 0) TT_STAMP(0, i, 1);
         mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
-        TT_STAMP(0, i, 2);
+        if (lane == 0) TT_STAMP(0, i, 2);
         tc_fence_after();
         const uint64_t dy = dyk0 + (uint64_t)((s * y_bytes) >> 4);
         for (int kb = 0; kb < kq; ++kb)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ts(tmem_s + b * CE_BN, tmem_x + (uint32_t)(kb * 32 + k * 8),
-                         dy + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc_s, (kb | k) != 0);
-        umma_commit(&s_full[b]);
-        TT_STAMP(0, i, 3);
+          for (int k = 0; k < 4; ++k) {
+            if (elect_one())
+              umma_bf16_ts(tmem_s + b * CE_BN, tmem_x + (uint32_t)(kb * 32 + k * 8),
+                           dy + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc_s, (kb | k) != 0);
+          }
+        if (elect_one()) umma_commit(&s_full[b]);
+        __syncwarp();
+        if (lane == 0) TT_STAMP(0, i, 3);
       };
       mbar_wait(x_ready, 0);
       tc_fence_after();
@@ -321,20 +333,22 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       for (int i = 0; i < nt; ++i) {
         if (i + 1 < nt) issue_s(i + 1);
         const int s = i % BWD_STAGES, b = i & 1;
-        TT_STAMP(0, i, 4);
+        if (lane == 0) TT_STAMP(0, i, 4);
         mbar_wait(&p_full[b], (i >> 1) & 1);
-        TT_STAMP(0, i, 5);
+        if (lane == 0) TT_STAMP(0, i, 5);
         tc_fence_after();
         const uint64_t dp = dp0 + (uint64_t)((b * p_bytes) >> 4);
         const uint64_t dy = dym0 + (uint64_t)((s * y_bytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_o, dp + (uint64_t)(k * 2), dy + (uint64_t)(k * (2048 / 16)), idesc_o, (i | k) != 0);
-        umma_commit(&p_empty[b]);
-        umma_commit(&y_empty[s]);
-        TT_STAMP(0, i, 6);
+        for (int k = 0; k < 4; ++k) {
+          if (elect_one()) umma_bf16(tmem_o, dp + (uint64_t)(k * 2), dy + (uint64_t)(k * (2048 / 16)), idesc_o, (i | k) != 0);
+        }
+        if (elect_one()) { umma_commit(&p_empty[b]); umma_commit(&y_empty[s]); }
+        __syncwarp();
+        if (lane == 0) TT_STAMP(0, i, 6);
       }
-      umma_commit(o_full);
+      if (elect_one()) umma_commit(o_full);
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;

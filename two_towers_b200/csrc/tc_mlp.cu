@@ -80,7 +80,7 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t tmem_a1 = tmem_base, tmem_a2 = tmem_base + 256;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_x, a_bytes);
       for (int kb = 0; kb < kE; ++kb) tma_load_2d(x_tile + kb * (MLP_BM * 128), &tmX, bar_x, kb * 64, (int)m0);
       for (int kb = 0; kb < kE; ++kb) tma_load_2d(w1_tile + (uint32_t)kb * w2_blk, &tmW1, bar_x, kb * 64, 0);
@@ -88,39 +88,47 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_arrive_expect_tx(bar_w2b, (uint32_t)(kH - 1) * w2_blk);
         for (int kb = 1; kb < kH; ++kb) tma_load_2d(w2_rest + (uint32_t)(kb - 1) * w2_blk, &tmW2, bar_w2b, kb * 64, 0);
       }
-      mbar_wait(bar_g1, 0);                                        // GEMM 1 has finished reading x / W1
+    }
+    __syncwarp();
+    mbar_wait(bar_g1, 0);                                        // GEMM 1 has finished reading x / W1
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_w2a, w2_blk);
       tma_load_2d(base, &tmW2, bar_w2a, 0, 0);
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(MLP_BM, H, 0, 0);
-      const uint64_t dx = umma_desc_kmajor(smem_u32(x_tile), 0);
-      const uint64_t dw1 = umma_desc_kmajor(smem_u32(w1_tile), 0);
-      mbar_wait(bar_x, 0);
-      tc_fence_after();
-      for (int kb = 0; kb < kE; ++kb)
+    // whole warp in uniform control flow; only the tcgen05 instructions are predicated on the elected lane
+    const uint32_t idesc = umma_idesc_bf16(MLP_BM, H, 0, 0);
+    const uint64_t dx = umma_desc_kmajor(smem_u32(x_tile), 0);
+    const uint64_t dw1 = umma_desc_kmajor(smem_u32(w1_tile), 0);
+    mbar_wait(bar_x, 0);
+    tc_fence_after();
+    for (int kb = 0; kb < kE; ++kb)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k) {
+        if (elect_one())
           umma_bf16(tmem_a1, dx + (uint64_t)(kb * (MLP_BM * 128 / 16) + k * 2),
                     dw1 + (uint64_t)(kb * (w2_blk >> 4) + k * 2), idesc, (kb | k) != 0);
-      umma_commit(bar_g1);
-      umma_commit(bar_acc1);
-      const uint64_t dh = umma_desc_kmajor(smem_u32(h1_tile), 0);
-      const uint64_t dw2a = umma_desc_kmajor(smem_u32(base), 0);
-      const uint64_t dw2b = umma_desc_kmajor(smem_u32(w2_rest), 0);
-      mbar_wait(bar_h1, 0);
-      mbar_wait(bar_w2a, 0);
-      if (kH > 1) mbar_wait(bar_w2b, 0);
-      tc_fence_after();
-      for (int kb = 0; kb < kH; ++kb) {
-        const uint64_t dw = kb == 0 ? dw2a : dw2b + (uint64_t)((kb - 1) * (w2_blk >> 4));
+      }
+    if (elect_one()) { umma_commit(bar_g1); umma_commit(bar_acc1); }
+    __syncwarp();
+    const uint64_t dh = umma_desc_kmajor(smem_u32(h1_tile), 0);
+    const uint64_t dw2a = umma_desc_kmajor(smem_u32(base), 0);
+    const uint64_t dw2b = umma_desc_kmajor(smem_u32(w2_rest), 0);
+    mbar_wait(bar_h1, 0);
+    mbar_wait(bar_w2a, 0);
+    if (kH > 1) mbar_wait(bar_w2b, 0);
+    tc_fence_after();
+    for (int kb = 0; kb < kH; ++kb) {
+      const uint64_t dw = kb == 0 ? dw2a : dw2b + (uint64_t)((kb - 1) * (w2_blk >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 4; ++k) {
+        if (elect_one())
           umma_bf16(tmem_a2, dh + (uint64_t)(kb * (MLP_BM * 128 / 16) + k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0);
       }
-      umma_commit(bar_acc2);
     }
+    if (elect_one()) umma_commit(bar_acc2);
+    __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int lrow = quarter * 32 + lane;

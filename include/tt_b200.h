@@ -145,6 +145,32 @@ int tt_inbatch_ce_bwd(const float* q, const float* d, const void* q_bf16, const 
  * extra pass over [B,H] is needed.  A null dq_parts / dd_parts skips that gradient.
  */
 int tt_inbatch_ce_bwd_nparts(int64_t Bq, int64_t Bd, int H, int precision);
+
+/* General forms for data-parallel training with GLOBAL in-batch negatives (bf16 operands).  The "all" operand may be
+ * the raw output of an all-gather of per-rank [Q_r | D_r] blocks: logical row g of the gathered matrix lives at
+ * physical row (g / blk) * blk_stride + g % blk + blk_off of a buffer with buf_rows rows (blk % 64 == 0), so no
+ * re-packing copy is needed between the collective and the kernel.
+ *   tt_inbatch_ce_fwd_ex : local queries [Bq,H] vs gathered documents (Bd logical rows); label_offset = rank*Bq.
+ *   tt_ce_pass_t         : one gradient pass -- rows X get gradients from all logical rows of Y.
+ *       q pass: x = local queries,   y = gathered documents, lse = local row lse [x_rows],  positive col = row + off
+ *       d pass: x = local documents, y = gathered queries,   lse = gathered lse [y_rows],   positive at row == col + off
+ *   tt_inbatch_ce_bwd_parts_ex : both passes in ONE launch; slice s of each output at out_parts + s*part_stride.
+ */
+typedef struct {
+  const void* x_bf16; int64_t x_rows;
+  const void* y_bf16; int64_t y_rows;
+  int64_t y_buf_rows, y_blk, y_blk_stride, y_blk_off;
+  const float* lse; int64_t label_offset;
+  float* out_parts; int64_t part_stride;
+} tt_ce_pass_t;
+size_t tt_inbatch_ce_fwd_ex_workspace(int64_t Bq, int64_t Bd);
+int tt_inbatch_ce_fwd_ex(const void* q_bf16, int64_t Bq, const void* d_bf16, int64_t Bd, int64_t d_buf_rows,
+                         int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off, int H, float inv_temperature,
+                         int64_t label_offset, float loss_scale, float* loss, float* lse, float* pos_mean,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int tt_inbatch_ce_bwd_nparts_ex(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_rows, int64_t d_y_rows, int H);
+int tt_inbatch_ce_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temperature,
+                               float loss_scale, const float* grad_out, int nparts, void* stream);
 int tt_inbatch_ce_bwd_parts(const void* q_bf16, const void* d_bf16, const float* lse, int64_t Bq, int64_t Bd,
                             int H, float inv_temperature, int64_t label_offset, float loss_scale,
                             const float* grad_out, float* dq_parts, int64_t dq_part_stride,
@@ -180,7 +206,8 @@ int tt_multineg_bwd(const float* q, const float* p, const float* negs, const flo
  *   out_scores [nq,k] fp32 and out_ids [nq,k] int64 (global id = row + id_offset), sorted by
  *   descending score, ties -> LOWER id first; k <= min(N, TT_TOPK_MAX).
  * tt_topk_merge: merge R sorted candidate lists per query (the sharded / multi-GPU step):
- *   scores [R,nq,k], ids [R,nq,k] -> [nq,k], same ordering rule.
+ *   list r = scores + r*score_rank_stride, ids + r*id_rank_stride (elements; 0 = dense [R,nq,k]) -> [nq,k], same
+ *   ordering rule.  Strides let the merge read (score,id) records straight out of ONE all-gathered byte buffer.
  */
 #define TT_TOPK_MAX 1024
 size_t tt_topk_scan_workspace(int64_t N, int H, int nq, int k);
@@ -189,6 +216,7 @@ int tt_topk_scan(const void* index, int index_bf16, const float* queries, int64_
                  float* out_scores, int64_t* out_ids,
                  void* workspace, size_t workspace_bytes, void* stream);
 int tt_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k,
+                  int64_t score_rank_stride, int64_t id_rank_stride,
                   float* out_scores, int64_t* out_ids, void* stream);
 /* fp32 -> bf16 row copy used by index_documents when the index is kept in bf16. */
 int tt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -45,11 +45,25 @@ SIGNATURES = {
     "tt_multineg_bwd": (_i, [_vp] * 4 + [_i64, _i, _i, _f] + [_vp] * 4 + [_vp]),
     "tt_topk_scan_workspace": (_sz, [_i64, _i, _i, _i]),
     "tt_topk_scan": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
-    "tt_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "tt_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _i64, _i64, _vp, _vp, _vp]),
     "tt_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "tt_selftest_tc_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "tt_adamw_step": (_i, [_vp] * 4 + [_i64] + [C.c_double] * 5 + [_vp, _vp, _vp]),
 }
+
+class CePass(C.Structure):
+    """tt_ce_pass_t (include/tt_b200.h)"""
+    _fields_ = [("x_bf16", _vp), ("x_rows", _i64), ("y_bf16", _vp), ("y_rows", _i64), ("y_buf_rows", _i64),
+                ("y_blk", _i64), ("y_blk_stride", _i64), ("y_blk_off", _i64), ("lse", _vp), ("label_offset", _i64),
+                ("out_parts", _vp), ("part_stride", _i64)]
+
+
+SIGNATURES.update({
+    "tt_inbatch_ce_fwd_ex_workspace": (_sz, [_i64, _i64]),
+    "tt_inbatch_ce_fwd_ex": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i, _f, _i64, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tt_inbatch_ce_bwd_nparts_ex": (_i, [_i64, _i64, _i64, _i64, _i]),
+    "tt_inbatch_ce_bwd_parts_ex": (_i, [C.POINTER(CePass), C.POINTER(CePass), _i, _f, _f, _vp, _i, _vp]),
+})
 
 _lib = None
 

@@ -454,4 +454,43 @@ int tt_inbatch_ce_bwd_parts(const void* q_bf16, const void* d_bf16, const float*
                                   dd_parts, dd_part_stride, static_cast<cudaStream_t>(stream));
 }
 
+size_t tt_inbatch_ce_fwd_ex_workspace(int64_t Bq, int64_t Bd) {
+  if (Bq <= 0 || Bd <= 0) return 256;
+  return tt::tc_inbatch_fwd_ex_workspace(Bq, Bd);
+}
+
+int tt_inbatch_ce_fwd_ex(const void* q_bf16, int64_t Bq, const void* d_bf16, int64_t Bd, int64_t d_buf_rows, int64_t d_blk,
+                         int64_t d_blk_stride, int64_t d_blk_off, int H, float inv_temperature, int64_t label_offset,
+                         float loss_scale, float* loss, float* lse, float* pos_mean, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(q_bf16 && d_bf16 && loss && lse && Bq > 0 && Bd > 0 && H > 0 && d_buf_rows >= 1 && d_blk >= 1,
+               "inbatch_ce_fwd_ex: bad arguments");
+  TT_CHECK_ARG(H % 64 == 0 && H <= 256 && d_blk % 64 == 0, "inbatch_ce_fwd_ex: needs H %% 64 == 0, H <= 256, d_blk %% 64 == 0");
+  TT_CHECK_ARG(label_offset >= 0 && Bq + label_offset <= Bd, "inbatch_ce_fwd_ex: positives out of range");
+  const size_t need = tt::tc_inbatch_fwd_ex_workspace(Bq, Bd);
+  if (workspace == nullptr || workspace_bytes < need) { tt::set_error("inbatch_ce_fwd_ex: workspace too small"); return TT_ERR_WORKSPACE; }
+  tt::Workspace w(workspace, workspace_bytes);
+  float* pos = w.take<float>(Bq);
+  float* part_ml = w.take<float>((need - 256 - tt::align_up((size_t)Bq * 4)) / 4);
+  return tt::tc_inbatch_fwd_ex((const __nv_bfloat16*)q_bf16, Bq, (const __nv_bfloat16*)d_bf16, Bd, d_buf_rows, d_blk,
+                               d_blk_stride, d_blk_off, H, inv_temperature, label_offset, loss_scale, loss, lse, pos_mean,
+                               part_ml, pos, static_cast<cudaStream_t>(stream));
+}
+
+int tt_inbatch_ce_bwd_nparts_ex(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_rows, int64_t d_y_rows, int H) {
+  if (q_x_rows <= 0 || q_y_rows <= 0 || d_x_rows <= 0 || d_y_rows <= 0 || H <= 0) return 1;
+  return tt::tc_inbatch_bwd_nparts2(q_x_rows, q_y_rows, d_x_rows, d_y_rows, H);
+}
+
+int tt_inbatch_ce_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temperature,
+                               float loss_scale, const float* grad_out, int nparts, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(q_pass && d_pass && H > 0 && nparts >= 1, "inbatch_ce_bwd_parts_ex: bad arguments");
+  TT_CHECK_ARG(q_pass->x_bf16 && q_pass->y_bf16 && d_pass->x_bf16 && d_pass->y_bf16 && q_pass->lse && d_pass->lse,
+               "inbatch_ce_bwd_parts_ex: null operand");
+  return tt::tc_inbatch_bwd_parts_ex(q_pass, d_pass, H, inv_temperature, loss_scale, grad_out, nparts,
+                                     static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

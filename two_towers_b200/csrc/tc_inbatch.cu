@@ -53,6 +53,7 @@ constexpr int FWD_STAGES = 4;
 __global__ void __launch_bounds__(CE_THREADS, 1)
 tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmD, int64_t Bq,
                  int64_t Bd, int H, float inv_temp, int64_t label_offset, int tiles_per_split,
+                 int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off,
                  float* __restrict__ part_ml, float* __restrict__ pos_logit) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // stays in the shared address space
@@ -103,7 +104,9 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint8_t* dt = d_tiles + s * d_bytes;
       if (elect_one()) {
         mbar_arrive_expect_tx(&d_full[s], d_bytes);
-        for (int kb = 0; kb < kq; ++kb) tma_load_2d(dt + kb * (CE_BN * 128), &tmD, &d_full[s], kb * 64, (t_beg + i) * CE_BN);
+        const int64_t g = (int64_t)(t_beg + i) * CE_BN;                       // logical D row -> physical row of the (gathered) buffer
+        const int yc = (int)((g / d_blk) * d_blk_stride + (g % d_blk) + d_blk_off);
+        for (int kb = 0; kb < kq; ++kb) tma_load_2d(dt + kb * (CE_BN * 128), &tmD, &d_full[s], kb * 64, yc);
       }
       __syncwarp();
     }
@@ -214,16 +217,19 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 constexpr int BWD_STAGES = 4;          // X 64 KB + 4 x 32 KB Y + 2 x 16 KB P = 224 KB: a full tile of slack for the TMA latency
 
 struct BwdParams {
-  const float* lse;            // [Bq] row logsumexp of the logits (natural log)
-  int64_t Bq, Bd;
+  // index 0: dQ pass (X = queries, Y = documents, lse indexed by X row, positive at col == row + off)
+  // index 1: dD pass (X = documents, Y = queries, lse indexed by Y row, positive at row == col + off)
+  const float* lse[2];         // natural-log logsumexp of the logits
+  int64_t Bx[2], By[2];        // gradient rows / logical rows scored against
+  int64_t label_offset[2];
+  int64_t y_blk[2], y_blk_stride[2], y_blk_off[2];   // logical Y row g -> physical (g / blk) * stride + g % blk + off
+  int tiles_per_split[2];      // Y tiles handled by one split
+  float* out[2];               // [nsplit] slices (part_stride elements apart) or the final tensor
+  int64_t part_stride[2];
   int H;
   float inv_temp;
-  int64_t label_offset;
-  int tiles_per_split[2];      // Y tiles handled by one split, per pass
   const float* grad_out;       // nullable device scalar
   float coef;                  // loss_scale / temperature
-  float* out[2];               // pass outputs: [nsplit][Bx][H] partials (slice stride below) or the final tensor
-  int64_t part_stride[2];      // elements between consecutive split slices
   long long* dbg;              // optional timeline buffer (TT_CE_DEBUG=1): [role 0..1][tile][8] clock64 stamps of CTA (0,0,0)
 };
 
@@ -232,7 +238,12 @@ struct BwdParams {
 //   COL == true : X = D, Y = Q, lse indexed by Y row,  positive at row == col + off   (dD)
 template <bool COL>
 __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtensorMap* tmY, const BwdParams& p,
-                                            int64_t Bx, int64_t By, int tiles_per_split, float* out, uint8_t* base) {
+                                            uint8_t* base) {
+  constexpr int PASS = COL ? 1 : 0;
+  const int64_t Bx = p.Bx[PASS], By = p.By[PASS], label_offset = p.label_offset[PASS];
+  const int tiles_per_split = p.tiles_per_split[PASS];
+  const float* __restrict__ lse = p.lse[PASS];
+  float* out = p.out[PASS] + (int64_t)blockIdx.y * p.part_stride[PASS];
   const int H = p.H;
   const int kq = H / 64;
   const uint32_t x_bytes = (uint32_t)CE_BM * H * 2, y_bytes = (uint32_t)CE_BN * H * 2;
@@ -294,7 +305,9 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       uint8_t* yt = y_tiles + s * y_bytes;
       if (elect_one()) {
         mbar_arrive_expect_tx(&y_full[s], y_bytes);
-        for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (CE_BN * 128), tmY, &y_full[s], kb * 64, (t_beg + i) * CE_BN);
+        const int64_t g = (int64_t)(t_beg + i) * CE_BN;
+        const int yc = (int)((g / p.y_blk[PASS]) * p.y_blk_stride[PASS] + (g % p.y_blk[PASS]) + p.y_blk_off[PASS]);
+        for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (CE_BN * 128), tmY, &y_full[s], kb * 64, yc);
       }
       __syncwarp();
     }
@@ -355,7 +368,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     const int lrow = quarter * 32 + lane;                  // row inside the tile == TMEM lane
     const int64_t row = x0 + lrow;
     const float c = p.inv_temp * kLog2e;
-    const float row_lse = (!COL && row < Bx) ? p.lse[row] * kLog2e : 0.f;
+    const float row_lse = (!COL && row < Bx) ? lse[row] * kLog2e : 0.f;
     // X tile: shared memory (TMA, 128B swizzle) -> registers -> TMEM.  Every S = X Y^T product of this CTA then
     // reads its A operand from tensor memory; with A in smem the 128x16 slice re-read per MMA saturates the
     // shared-memory port and the N=64 product runs at half rate (measured 66 vs 32 cycles per tcgen05.mma).
@@ -375,14 +388,14 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     __syncwarp();
     if (lane == 0) mbar_arrive(x_ready);
     // Y tiles that can hold a positive of one of this CTA's rows (CTA-uniform band)
-    const int64_t band_lo = COL ? x0 - p.label_offset : x0 + p.label_offset;
+    const int64_t band_lo = COL ? x0 - label_offset : x0 + label_offset;
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
       const int64_t y0 = (int64_t)(t_beg + i) * CE_BN;
       float cl0 = 0.f, cl1 = 0.f;                           // column lse (COL mode): lane holds columns lane, lane+32
       if (COL) {
-        cl0 = (y0 + lane < By) ? __ldg(p.lse + y0 + lane) * kLog2e : CUDART_INF_F;
-        cl1 = (y0 + 32 + lane < By) ? __ldg(p.lse + y0 + 32 + lane) * kLog2e : CUDART_INF_F;
+        cl0 = (y0 + lane < By) ? __ldg(lse + y0 + lane) * kLog2e : CUDART_INF_F;
+        cl1 = (y0 + 32 + lane < By) ? __ldg(lse + y0 + 32 + lane) * kLog2e : CUDART_INF_F;
       }
       if (threadIdx.x == 64) TT_STAMP(1, i, 0);
       mbar_wait(&s_full[b], (i >> 1) & 1);
@@ -412,7 +425,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
           if (y0 + j >= By) pv[j] = 0.f;
       }
       if (y0 + CE_BN > band_lo && y0 < band_lo + CE_BM) {   // tile intersects the diagonal band
-        const int64_t pj = (COL ? row - p.label_offset : row + p.label_offset) - y0;
+        const int64_t pj = (COL ? row - label_offset : row + label_offset) - y0;
         if (pj >= 0 && pj < CE_BN && y0 + pj < By) {
 #pragma unroll
           for (int j = 0; j < 64; ++j) pv[j] -= (j == (int)pj) ? 1.0f : 0.0f;     // select, keeps pv[] in registers
@@ -472,16 +485,14 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
 }
 
 __global__ void __launch_bounds__(CE_THREADS, 1)
-tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmQ64,
-                 const __grid_constant__ CUtensorMap tmD128, const __grid_constant__ CUtensorMap tmD64, const BwdParams p) {
+tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmY0,
+                 const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmY1, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   const int pass = blockIdx.z;
-  const int64_t Bx = pass == 0 ? p.Bq : p.Bd, By = pass == 0 ? p.Bd : p.Bq;
-  if ((int64_t)blockIdx.x * CE_BM >= Bx || p.out[pass] == nullptr) return;   // CTA-uniform: nothing to do for this pass
-  float* out = p.out[pass] + (int64_t)blockIdx.y * p.part_stride[pass];
-  if (pass == 0) ce_bwd_body<false>(&tmQ128, &tmD64, p, Bx, By, p.tiles_per_split[0], out, base);
-  else           ce_bwd_body<true>(&tmD128, &tmQ64, p, Bx, By, p.tiles_per_split[1], out, base);
+  if ((int64_t)blockIdx.x * CE_BM >= p.Bx[pass] || p.out[pass] == nullptr) return;   // CTA-uniform: nothing to do for this pass
+  if (pass == 0) ce_bwd_body<false>(&tmX0, &tmY0, p, base);
+  else           ce_bwd_body<true>(&tmX1, &tmY1, p, base);
 }
 
 static size_t fwd_smem(int H) { return 1024 + (size_t)CE_BM * H * 2 + FWD_STAGES * (size_t)CE_BN * H * 2 + 20 * 8 + 16; }
@@ -505,11 +516,12 @@ static bool tc_ce_supported(int H) { return H % 64 == 0 && H >= 64 && H <= 256; 
 
 // splits: forward uses its own; backward uses ONE split count for both passes (they share a launch)
 static int fwd_splits(int64_t Bq, int64_t Bd) { return tc::pick_split(ceil_div(Bq, tc::CE_BM), Bd); }
-static int bwd_splits(int64_t Bq, int64_t Bd) {
-  const int64_t xt = ceil_div(Bq, tc::CE_BM) + ceil_div(Bd, tc::CE_BM);
-  const int a = tc::pick_split(xt, Bd), b = tc::pick_split(xt, Bq);
+static int bwd_splits2(int64_t Bx0, int64_t By0, int64_t Bx1, int64_t By1) {
+  const int64_t xt = ceil_div(Bx0, tc::CE_BM) + ceil_div(Bx1, tc::CE_BM);
+  const int a = tc::pick_split(xt, By0), b = tc::pick_split(xt, By1);
   return a < b ? a : b;
 }
+static int bwd_splits(int64_t Bq, int64_t Bd) { return bwd_splits2(Bq, Bd, Bd, Bq); }
 
 struct TcCePlan { int ns_f, ns_b; size_t qb, db, ml, pos, partial, total; };
 static TcCePlan plan_tc_ce(int64_t Bq, int64_t Bd, int H) {
@@ -532,10 +544,28 @@ size_t tc_inbatch_workspace(int64_t Bq, int64_t Bd, int H) {
   return t > f ? t : f;
 }
 
-int tc_inbatch_bwd_nparts(int64_t Bq, int64_t Bd, int H) { return tc_ce_supported(H) ? bwd_splits(Bq, Bd) : 1; }
-
 namespace tc {
 int cast3_public(const float* a, __nv_bfloat16* ab, int64_t na, const float* b, __nv_bfloat16* bb, int64_t nb, cudaStream_t s);
+}
+
+// forward on bf16 operands; D may be a block-interleaved (all-gathered) buffer: logical row g lives at physical
+// row (g / d_blk) * d_blk_stride + g % d_blk + d_blk_off of a buffer with d_buf_rows rows.
+int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* da, int64_t Bd, int64_t d_buf_rows,
+                      int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off, int H, float inv_temp, int64_t label_offset,
+                      float loss_scale, float* loss, float* lse, float* pos_mean, float* part_ml, float* pos, cudaStream_t s) {
+  CUtensorMap tmQ, tmD;
+  int rc = tc::make_tmap_bf16(&tmQ, qa, (uint64_t)Bq, (uint64_t)H, tc::CE_BM); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmD, da, (uint64_t)d_buf_rows, (uint64_t)H, tc::CE_BN); if (rc) return rc;
+  const int ns = fwd_splits(Bq, Bd);
+  const int yt = (int)ceil_div(Bd, tc::CE_BN);
+  const int per = (int)ceil_div(yt, ns);
+  const size_t smem = tc::fwd_smem(H);
+  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div(Bq, tc::CE_BM), (unsigned)ns);
+  tc::tc_ce_fwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ, tmD, Bq, Bd, H, inv_temp, label_offset, per, d_blk, d_blk_stride,
+                                                         d_blk_off, part_ml, pos);
+  TT_LAUNCH_CHECK("tc_ce_fwd_kernel");
+  return inbatch_finalize(part_ml, pos, ns, Bq, inv_temp, loss_scale, lse, loss, pos_mean, nullptr, s);
 }
 
 int tc_inbatch_fwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16, int64_t Bq,
@@ -550,61 +580,51 @@ int tc_inbatch_fwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, 
   __nv_bfloat16* db = w.take<__nv_bfloat16>((size_t)Bd * H);
   float* part_ml = w.take<float>(plan.ml / 4);
   float* pos = w.take<float>(Bq);
-  int rc;
   if (!q_bf16 || !d_bf16) {
-    rc = tc::cast3_public(q_bf16 ? nullptr : q, qb, q_bf16 ? 0 : Bq * H, d_bf16 ? nullptr : d, db, d_bf16 ? 0 : Bd * H, s);
+    int rc = tc::cast3_public(q_bf16 ? nullptr : q, qb, q_bf16 ? 0 : Bq * H, d_bf16 ? nullptr : d, db, d_bf16 ? 0 : Bd * H, s);
     if (rc) return rc;
   }
-  const __nv_bfloat16* qa = q_bf16 ? q_bf16 : qb;
-  const __nv_bfloat16* da = d_bf16 ? d_bf16 : db;
-  CUtensorMap tmQ, tmD;
-  rc = tc::make_tmap_bf16(&tmQ, qa, (uint64_t)Bq, (uint64_t)H, tc::CE_BM); if (rc) return rc;
-  rc = tc::make_tmap_bf16(&tmD, da, (uint64_t)Bd, (uint64_t)H, tc::CE_BN); if (rc) return rc;
-  const int yt = (int)ceil_div(Bd, tc::CE_BN);
-  const int per = (int)ceil_div(yt, plan.ns_f);
-  const size_t smem = tc::fwd_smem(H);
-  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(Bq, tc::CE_BM), (unsigned)plan.ns_f);
-  tc::tc_ce_fwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ, tmD, Bq, Bd, H, inv_temp, label_offset, per, part_ml, pos);
-  TT_LAUNCH_CHECK("tc_ce_fwd_kernel");
-  return inbatch_finalize(part_ml, pos, plan.ns_f, Bq, inv_temp, loss_scale, lse, loss, pos_mean, nullptr, s);
+  return tc_inbatch_fwd_ex(q_bf16 ? q_bf16 : qb, Bq, d_bf16 ? d_bf16 : db, Bd, Bd, Bd > 0 ? Bd : 1, 0, 0, H, inv_temp,
+                           label_offset, loss_scale, loss, lse, pos_mean, part_ml, pos, s);
 }
 
-// One launch for both gradients.  out_q / out_d receive nsplit slices (stride_q / stride_d elements apart);
-// a nullptr output skips that pass.  nsplit must equal tc_inbatch_bwd_nparts().
-static int launch_tc_bwd(const __nv_bfloat16* qa, const __nv_bfloat16* da, const float* lse, int64_t Bq, int64_t Bd, int H,
-                         float inv_temp, int64_t off, int nsplit, const float* grad_out, float coef, float* out_q,
-                         int64_t stride_q, float* out_d, int64_t stride_d, cudaStream_t s) {
-  CUtensorMap tmQ128, tmQ64, tmD128, tmD64;
-  int rc = tc::make_tmap_bf16(&tmQ128, qa, (uint64_t)Bq, (uint64_t)H, tc::CE_BM); if (rc) return rc;
-  rc = tc::make_tmap_bf16(&tmQ64, qa, (uint64_t)Bq, (uint64_t)H, tc::CE_BN); if (rc) return rc;
-  rc = tc::make_tmap_bf16(&tmD128, da, (uint64_t)Bd, (uint64_t)H, tc::CE_BM); if (rc) return rc;
-  rc = tc::make_tmap_bf16(&tmD64, da, (uint64_t)Bd, (uint64_t)H, tc::CE_BN); if (rc) return rc;
+size_t tc_inbatch_fwd_ex_workspace(int64_t Bq, int64_t Bd) {
+  return align_up((size_t)fwd_splits(Bq, Bd) * Bq * 2 * 4) + align_up((size_t)Bq * 4) + 256;
+}
+
+// ---- backward: both gradient passes in ONE launch ---------------------------------------------------------------
+struct CePass {                  // rows X receive gradients from all (logical) rows of Y
+  const __nv_bfloat16* x; int64_t Bx;
+  const __nv_bfloat16* y; int64_t By, y_buf_rows, y_blk, y_blk_stride, y_blk_off;
+  const float* lse; int64_t label_offset;
+  float* out; int64_t part_stride;
+};
+
+static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_temp, int nsplit, const float* grad_out,
+                         float coef, cudaStream_t s) {
+  CUtensorMap tmX0, tmY0, tmX1, tmY1;
+  int rc = tc::make_tmap_bf16(&tmX0, pq.x, (uint64_t)pq.Bx, (uint64_t)H, tc::CE_BM); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmY0, pq.y, (uint64_t)pq.y_buf_rows, (uint64_t)H, tc::CE_BN); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmX1, pd.x, (uint64_t)pd.Bx, (uint64_t)H, tc::CE_BM); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmY1, pd.y, (uint64_t)pd.y_buf_rows, (uint64_t)H, tc::CE_BN); if (rc) return rc;
   tc::BwdParams p{};
-  p.lse = lse; p.Bq = Bq; p.Bd = Bd; p.H = H; p.inv_temp = inv_temp; p.label_offset = off;
-  p.tiles_per_split[0] = (int)ceil_div(ceil_div(Bd, tc::CE_BN), nsplit);
-  p.tiles_per_split[1] = (int)ceil_div(ceil_div(Bq, tc::CE_BN), nsplit);
-  p.grad_out = grad_out; p.coef = coef;
-  p.out[0] = out_q; p.out[1] = out_d; p.part_stride[0] = stride_q; p.part_stride[1] = stride_d;
+  const CePass* ps[2] = {&pq, &pd};
+  for (int k = 0; k < 2; ++k) {
+    p.lse[k] = ps[k]->lse; p.Bx[k] = ps[k]->Bx; p.By[k] = ps[k]->By; p.label_offset[k] = ps[k]->label_offset;
+    p.y_blk[k] = ps[k]->y_blk > 0 ? ps[k]->y_blk : 1; p.y_blk_stride[k] = ps[k]->y_blk_stride; p.y_blk_off[k] = ps[k]->y_blk_off;
+    p.tiles_per_split[k] = (int)ceil_div(ceil_div(ps[k]->By, tc::CE_BN), nsplit);
+    p.out[k] = ps[k]->out; p.part_stride[k] = ps[k]->part_stride;
+  }
+  p.H = H; p.inv_temp = inv_temp; p.grad_out = grad_out; p.coef = coef;
   const size_t smem = tc::bwd_smem(H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
   long long* dbg_dev = nullptr;
   if (dbg_on) { cudaMalloc(&dbg_dev, 2 * 64 * 8 * sizeof(long long)); cudaMemset(dbg_dev, 0, 2 * 64 * 8 * sizeof(long long)); p.dbg = dbg_dev; }
-  const int64_t xq = ceil_div(Bq, tc::CE_BM), xd = ceil_div(Bd, tc::CE_BM);
-  // pass 0 = dQ, pass 1 = dD; a missing output shrinks the grid to the other pass
-  if (out_q && out_d) {
-    dim3 grid((unsigned)(xq > xd ? xq : xd), (unsigned)nsplit, 2);
-    tc::tc_ce_bwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ128, tmQ64, tmD128, tmD64, p);
-  } else if (out_q) {
-    dim3 grid((unsigned)xq, (unsigned)nsplit, 1);
-    tc::tc_ce_bwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ128, tmQ64, tmD128, tmD64, p);
-  } else {
-    // only dD: run it as "pass 0" of a swapped problem is not possible (lse orientation), so launch z=2 and let pass 0 exit
-    p.Bq = Bq; p.out[0] = nullptr;
-    dim3 grid((unsigned)xd, (unsigned)nsplit, 2);
-    tc::tc_ce_bwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ128, tmQ64, tmD128, tmD64, p);
-  }
+  const int64_t x0 = pq.out ? ceil_div(pq.Bx, tc::CE_BM) : 0, x1 = pd.out ? ceil_div(pd.Bx, tc::CE_BM) : 0;
+  const int nz = pd.out ? 2 : 1;                         // pass 1 absent -> only z = 0 is launched
+  dim3 grid((unsigned)(x0 > x1 ? x0 : x1), (unsigned)nsplit, (unsigned)nz);
+  tc::tc_ce_bwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmX0, tmY0, tmX1, tmY1, p);
   TT_LAUNCH_CHECK("tc_ce_bwd_kernel");
   if (dbg_on) {                                              // developer aid: per-tile timeline of CTA (0,0,0)
     static long long host[2 * 64 * 8];
@@ -625,13 +645,45 @@ static int launch_tc_bwd(const __nv_bfloat16* qa, const __nv_bfloat16* da, const
   return TT_OK;
 }
 
+static CePass plain_pass(const __nv_bfloat16* x, int64_t Bx, const __nv_bfloat16* y, int64_t By, const float* lse, int64_t off,
+                         float* out, int64_t stride) {
+  CePass c{};
+  c.x = x; c.Bx = Bx; c.y = y; c.By = By; c.y_buf_rows = By; c.y_blk = By > 0 ? By : 1; c.y_blk_stride = 0; c.y_blk_off = 0;
+  c.lse = lse; c.label_offset = off; c.out = out; c.part_stride = stride;
+  return c;
+}
+
+int tc_inbatch_bwd_nparts(int64_t Bq, int64_t Bd, int H) { return tc_ce_supported(H) ? bwd_splits(Bq, Bd) : 1; }
+int tc_inbatch_bwd_nparts2(int64_t Bx0, int64_t By0, int64_t Bx1, int64_t By1, int H) {
+  return tc_ce_supported(H) ? bwd_splits2(Bx0, By0, Bx1, By1) : 1;
+}
+
 // Partial-slice variant used by the fused trainer: the consumer (normalise-backward) sums the slices.
 int tc_inbatch_bwd_parts(const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16, const float* lse, int64_t Bq, int64_t Bd,
                          int H, float inv_temp, int64_t label_offset, float loss_scale, const float* grad_out,
                          float* dq_parts, int64_t stride_q, float* dd_parts, int64_t stride_d, cudaStream_t s) {
   if (!tc_ce_supported(H) || !q_bf16 || !d_bf16) { set_error("tc_inbatch_bwd_parts: needs bf16 operands and H %% 64 == 0, H <= 256"); return TT_ERR_UNSUPPORTED; }
-  return launch_tc_bwd(q_bf16, d_bf16, lse, Bq, Bd, H, inv_temp, label_offset, bwd_splits(Bq, Bd), grad_out,
-                       loss_scale * inv_temp, dq_parts, stride_q, dd_parts, stride_d, s);
+  const CePass pq = plain_pass(q_bf16, Bq, d_bf16, Bd, lse, label_offset, dq_parts, stride_q);
+  const CePass pd = plain_pass(d_bf16, Bd, q_bf16, Bq, lse, label_offset, dd_parts, stride_d);
+  return launch_tc_bwd(pq, pd, H, inv_temp, bwd_splits(Bq, Bd), grad_out, loss_scale * inv_temp, s);
+}
+
+// General two-pass form (data-parallel training with global negatives): every field of tt_ce_pass_t is honoured.
+int tc_inbatch_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temp, float loss_scale,
+                            const float* grad_out, int nparts, cudaStream_t s) {
+  if (!tc_ce_supported(H)) { set_error("tc_inbatch_bwd_parts_ex: needs H %% 64 == 0, H <= 256"); return TT_ERR_UNSUPPORTED; }
+  auto conv = [](const tt_ce_pass_t* t) {
+    CePass c{};
+    c.x = (const __nv_bfloat16*)t->x_bf16; c.Bx = t->x_rows; c.y = (const __nv_bfloat16*)t->y_bf16; c.By = t->y_rows;
+    c.y_buf_rows = t->y_buf_rows; c.y_blk = t->y_blk; c.y_blk_stride = t->y_blk_stride; c.y_blk_off = t->y_blk_off;
+    c.lse = t->lse; c.label_offset = t->label_offset; c.out = t->out_parts; c.part_stride = t->part_stride;
+    return c;
+  };
+  const CePass pq = conv(q_pass), pd = conv(d_pass);
+  const int want = bwd_splits2(pq.Bx, pq.By, pd.Bx, pd.By);
+  if (nparts != want) { set_error("tc_inbatch_bwd_parts_ex: nparts %d != %d (query tt_inbatch_ce_bwd_nparts_ex)", nparts, want); return TT_ERR_INVALID; }
+  if (pq.y_blk % tc::CE_BN != 0 || pd.y_blk % tc::CE_BN != 0) { set_error("tc_inbatch_bwd_parts_ex: y_blk must be a multiple of %d", tc::CE_BN); return TT_ERR_UNSUPPORTED; }
+  return launch_tc_bwd(pq, pd, H, inv_temp, nparts, grad_out, loss_scale * inv_temp, s);
 }
 
 int tc_inbatch_bwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16,
@@ -657,14 +709,16 @@ int tc_inbatch_bwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, 
   const __nv_bfloat16* da = d_bf16 ? d_bf16 : db;
   const float coef = loss_scale * inv_temp;
   const int ns = plan.ns_b;
-  if (ns == 1) return launch_tc_bwd(qa, da, lse, Bq, Bd, H, inv_temp, label_offset, 1, grad_out, coef, dq, 0, dd, 0, s);
-  float* pq = partial;                                   // [ns][Bq][H]
-  float* pd = partial + (size_t)ns * Bq * H;             // [ns][Bd][H]
-  rc = launch_tc_bwd(qa, da, lse, Bq, Bd, H, inv_temp, label_offset, ns, grad_out, coef, dq ? pq : nullptr, Bq * H,
-                     dd ? pd : nullptr, Bd * H, s);
+  float* pq_buf = ns > 1 ? partial : dq;                                   // [ns][Bq][H]
+  float* pd_buf = ns > 1 ? partial + (size_t)ns * Bq * H : dd;             // [ns][Bd][H]
+  const CePass pq = plain_pass(qa, Bq, da, Bd, lse, label_offset, dq ? pq_buf : nullptr, Bq * H);
+  const CePass pd = plain_pass(da, Bd, qa, Bq, lse, label_offset, dd ? pd_buf : nullptr, Bd * H);
+  rc = launch_tc_bwd(pq, pd, H, inv_temp, ns, grad_out, coef, s);
   if (rc) return rc;
-  if (dq) { rc = split_sum(pq, ns, Bq * H, dq, s); if (rc) return rc; }
-  if (dd) { rc = split_sum(pd, ns, Bd * H, dd, s); if (rc) return rc; }
+  if (ns > 1) {
+    if (dq) { rc = split_sum(pq_buf, ns, Bq * H, dq, s); if (rc) return rc; }
+    if (dd) { rc = split_sum(pd_buf, ns, Bd * H, dd, s); if (rc) return rc; }
+  }
   return TT_OK;
 }
 

@@ -39,6 +39,14 @@ int tc_inbatch_bwd_parts(const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf1
                          int H, float inv_temp, int64_t label_offset, float loss_scale, const float* grad_out,
                          float* dq_parts, int64_t stride_q, float* dd_parts, int64_t stride_d, cudaStream_t s);
 
+int tc_inbatch_bwd_nparts2(int64_t Bx0, int64_t By0, int64_t Bx1, int64_t By1, int H);
+int tc_inbatch_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temp, float loss_scale,
+                            const float* grad_out, int nparts, cudaStream_t s);
+size_t tc_inbatch_fwd_ex_workspace(int64_t Bq, int64_t Bd);
+int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* da, int64_t Bd, int64_t d_buf_rows,
+                      int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off, int H, float inv_temp, int64_t label_offset,
+                      float loss_scale, float* loss, float* lse, float* pos_mean, float* part_ml, float* pos, cudaStream_t s);
+
 // shared by both precisions (inbatch_ce.cu): lse/loss finalisation from per-split (max,sum)
 int inbatch_finalize(const float* part_ml, const float* pos_logit, int nsplit, int64_t Bq, float inv_temp,
                      float loss_scale, float* lse, float* loss, float* pos_mean, float* scratch,

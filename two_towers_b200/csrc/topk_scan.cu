@@ -257,14 +257,13 @@ struct RawKeys {
   const u64* keys; int64_t per_query;
   __device__ __forceinline__ u64 get(int q, int64_t i) const { return keys[(int64_t)q * per_query + i]; }
 };
-struct ScoreIdKeys {            // [R, nq, k] layout
-  const float* scores; const int64_t* ids; int R, nq, k;
+struct ScoreIdKeys {            // R lists of [nq, k]; list r starts at r * rank_stride elements
+  const float* scores; const int64_t* ids; int R, nq, k; int64_t score_stride, id_stride;
   __device__ __forceinline__ u64 get(int q, int64_t i) const {
     const int64_t r = i / k, j = i % k;
-    const int64_t o = (r * nq + q) * k + j;
-    const int64_t id = ids[o];
+    const int64_t id = ids[r * id_stride + (int64_t)q * k + j];
     if (id < 0) return 0ull;
-    return make_key(scores[o], (uint32_t)id);
+    return make_key(scores[r * score_stride + (int64_t)q * k + j], (uint32_t)id);
   }
 };
 
@@ -429,12 +428,13 @@ int tt_topk_scan(const void* index, int index_bf16, const float* queries, int64_
   return TT_OK;
 }
 
-int tt_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k, float* out_scores,
-                  int64_t* out_ids, void* stream) {
+int tt_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k, int64_t score_rank_stride,
+                  int64_t id_rank_stride, float* out_scores, int64_t* out_ids, void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(scores && ids && out_scores && out_ids && R > 0 && nq > 0 && k > 0 && k <= TT_TOPK_MAX, "topk_merge: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  tt::ScoreIdKeys src{scores, ids, R, nq, k};
+  tt::ScoreIdKeys src{scores, ids, R, nq, k, score_rank_stride > 0 ? score_rank_stride : (int64_t)nq * k,
+                      id_rank_stride > 0 ? id_rank_stride : (int64_t)nq * k};
   tt::merge_topk_kernel<tt::ScoreIdKeys><<<nq, tt::kMergeThreads, 0, s>>>(src, (int64_t)R * k, k, 0, out_scores, out_ids);
   TT_LAUNCH_CHECK("merge_topk_kernel");
   return TT_OK;

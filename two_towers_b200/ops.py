@@ -348,7 +348,33 @@ def topk_merge(scores: torch.Tensor, ids: torch.Tensor):
     R, nq, k = scores.shape
     out_s = torch.empty(nq, k, dtype=torch.float32, device=scores.device)
     out_i = torch.empty(nq, k, dtype=torch.int64, device=scores.device)
-    check(_lib_().tt_topk_merge(_p(scores), _p(ids), R, nq, k, _p(out_s), _p(out_i), _stream()), "tt_topk_merge")
+    check(_lib_().tt_topk_merge(_p(scores), _p(ids), R, nq, k, 0, 0, _p(out_s), _p(out_i), _stream()), "tt_topk_merge")
+    return out_s, out_i
+
+
+def packed_topk_buffer(nq: int, k: int, device, ranks: int = 1):
+    """One byte buffer per rank holding [nq,k] fp32 scores followed by [nq,k] int64 ids (8-byte aligned), so the
+    sharded search needs ONE all-gather.  Returns (buffer [ranks, nbytes] uint8, nbytes, id byte offset)."""
+    sbytes = (nq * k * 4 + 7) // 8 * 8
+    nbytes = sbytes + nq * k * 8
+    return torch.empty(ranks, nbytes, dtype=torch.uint8, device=device), nbytes, sbytes
+
+
+def packed_views(buf_row: torch.Tensor, nq: int, k: int, id_off: int):
+    s = buf_row[:nq * k * 4].view(torch.float32).view(nq, k)
+    i = buf_row[id_off:id_off + nq * k * 8].view(torch.int64).view(nq, k)
+    return s, i
+
+
+def topk_merge_packed(buf: torch.Tensor, nq: int, k: int, id_off: int):
+    """Merge R packed candidate records (see packed_topk_buffer) -> ([nq,k], [nq,k])."""
+    _need_cuda(buf)
+    R, nbytes = buf.shape
+    out_s = torch.empty(nq, k, dtype=torch.float32, device=buf.device)
+    out_i = torch.empty(nq, k, dtype=torch.int64, device=buf.device)
+    base = buf.data_ptr()
+    check(_lib_().tt_topk_merge(C.c_void_p(base), C.c_void_p(base + id_off), R, nq, k, nbytes // 4, nbytes // 8,
+                                _p(out_s), _p(out_i), _stream()), "tt_topk_merge")
     return out_s, out_i
 
 

@@ -97,13 +97,29 @@ def sharded_topk(index_shard: torch.Tensor, queries: torch.Tensor, k: int, id_of
     nq = queries.shape[0]
     n_local = index_shard.shape[0]
     k_local = min(k, n_local)
+    if ws == 1 and k_local == k:
+        return kernels.topk_scan(index_shard, queries, k_local, cosine=cosine, id_offset=id_offset)
+    packed = hasattr(kernels, "packed_topk_buffer")
+    if packed:
+        # (score, id) records of this rank go straight into one byte buffer -> ONE all-gather -> merge kernel
+        mine, nbytes, id_off = kernels.packed_topk_buffer(nq, k, queries.device)
+        s_view, i_view = kernels.packed_views(mine[0], nq, k, id_off)
+        if k_local < k:
+            s_view.fill_(float("-inf"))
+            i_view.fill_(-1)
+        if k_local == k:
+            kernels.topk_scan(index_shard, queries, k, cosine=cosine, id_offset=id_offset, out=(s_view, i_view))
+        elif k_local > 0:
+            s, i = kernels.topk_scan(index_shard, queries, k_local, cosine=cosine, id_offset=id_offset)
+            s_view[:, :k_local].copy_(s)
+            i_view[:, :k_local].copy_(i)
+        everyone = all_gather_rows(mine, group)                 # [R, nbytes]
+        return kernels.topk_merge_packed(everyone, nq, k, id_off)
     if k_local > 0:
         s, i = kernels.topk_scan(index_shard, queries, k_local, cosine=cosine, id_offset=id_offset)
     else:
         s = torch.empty(nq, 0, dtype=torch.float32, device=queries.device)
         i = torch.empty(nq, 0, dtype=torch.int64, device=queries.device)
-    if ws == 1 and k_local == k:
-        return s, i
     if k_local < k:
         pad_s = torch.full((nq, k - k_local), float("-inf"), dtype=torch.float32, device=s.device)
         pad_i = torch.full((nq, k - k_local), -1, dtype=torch.int64, device=s.device)

@@ -99,9 +99,18 @@ class FusedTrainer:
         # the tensor-core loss backward leaves its per-split partial gradients as slices [parts, R, H]; the
         # tower backward sums them while it reads dy (no reduction kernel, no extra pass)
         self.dy_parts = 1
-        if (self.prec == _lib.TT_PREC_BF16 and loss == "in_batch" and not self.global_negatives and
-                all(isinstance(t, MeanPoolingTower) for t, _, _ in self.groups)):
+        fast = (self.prec == _lib.TT_PREC_BF16 and loss == "in_batch" and self.H % 64 == 0 and self.H <= 256 and
+                all(isinstance(t, MeanPoolingTower) for t, _, _ in self.groups))
+        self.global_fast = bool(fast and self.global_negatives and B % 64 == 0)
+        if fast and not self.global_negatives:
             self.dy_parts = int(self.lib.tt_inbatch_ce_bwd_nparts(B, B, self.H, self.prec))
+        elif self.global_fast:
+            Bg = B * self.world
+            self.dy_parts = int(self.lib.tt_inbatch_ce_bwd_nparts_ex(B, Bg, B, Bg, self.H))
+            # one all-gather moves [Q_r | D_r] (bf16) of every rank; the loss kernels index it block-wise in place
+            self.yg_bf16 = torch.empty(self.world * 2 * B, self.H, dtype=torch.bfloat16, device=self.dev)
+            self.lse_g = torch.empty(Bg, **f32)
+            self.ce_ws = torch.empty(int(self.lib.tt_inbatch_ce_fwd_ex_workspace(B, Bg)), dtype=torch.uint8, device=self.dev)
         self.dy_part_stride = R * self.H if self.dy_parts > 1 else 0
         self.dy_all = torch.empty(self.dy_parts, R, self.H, **f32)
         self.dy = self.dy_all[0]
@@ -161,7 +170,7 @@ class FusedTrainer:
         xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
-            y_ptr = None if (self.dy_parts > 1 and yb is not None) else y      # fp32 y unused on the pure bf16 path
+            y_ptr = None if ((self.dy_parts > 1 or self.global_fast) and yb is not None) else y   # fp32 y unused on the pure bf16 path
             check(lib.tt_mlp_fwd(_p(x), _p(l1.weight), _p(l1.bias), _p(l2.weight), _p(l2.bias), nr, self.E, self.H,
                                  _p(sv["h1"]), _p(sv["z"]), _p(y_ptr), _p(yb), _p(xb), _p(self._shadow(l1.weight)),
                                  _p(self._shadow(l2.weight)), _p(self.h1_bf16[gi]), self.prec, _p(self.ws),
@@ -211,7 +220,9 @@ class FusedTrainer:
         dq, dd = self.dy[:B], self.dy[B:2 * B]
         if self.loss_name == "in_batch":
             inv_t = 1.0 / self.temperature
-            if self.global_negatives:
+            if self.global_fast:
+                self._global_inbatch_fast(s, inv_t)
+            elif self.global_negatives:
                 loss, lse, d_glob = parallel.global_inbatch_fwd(q, d, self.temperature, ops, self.group, self.prec)
                 self.loss.copy_(loss)
                 g_dq, g_dd = parallel.global_inbatch_bwd(q, d, d_glob, lse, self.temperature, ops, self.group, self.prec)
@@ -250,6 +261,25 @@ class FusedTrainer:
         check(lib.tt_adamw_step(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
                                 self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                 _p(self.step_count), _p(self.flat_bf16), s), "tt_adamw_step")
+
+    def _global_inbatch_fast(self, s, inv_t):
+        """Global in-batch negatives on the tensor-core path: 2 all-gathers (bf16 [Q|D], fp32 lse), the loss kernels
+        read the gathered buffer in place (block-interleaved rows), both gradients come from ONE launch as slices."""
+        lib, B, H, W = self.lib, self.B, self.H, self.world
+        Bg = B * W
+        dist.all_gather_into_tensor(self.yg_bf16, self.y_bf16[:2 * B], group=self.group)
+        scale = 1.0 / Bg
+        check(lib.tt_inbatch_ce_fwd_ex(_p(self.y_bf16[:B]), B, _p(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, B, H, inv_t,
+                                       self.rank * B, scale, _p(self.loss), _p(self.lse), _p(self.pos_mean),
+                                       _p(self.ce_ws), self.ce_ws.numel(), s), "tt_inbatch_ce_fwd_ex")
+        dist.all_gather_into_tensor(self.lse_g, self.lse, group=self.group)
+        vp = lambda t: None if t is None else t.data_ptr()
+        qp = _lib.CePass(vp(self.y_bf16[:B]), B, vp(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, B, vp(self.lse), self.rank * B,
+                         vp(self.dy[:B]), self.dy_part_stride)
+        dp = _lib.CePass(vp(self.y_bf16[B:2 * B]), B, vp(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, 0, vp(self.lse_g),
+                         -self.rank * B, vp(self.dy[B:2 * B]), self.dy_part_stride)
+        check(lib.tt_inbatch_ce_bwd_parts_ex(C.byref(qp), C.byref(dp), H, inv_t, scale, None, self.dy_parts, s),
+              "tt_inbatch_ce_bwd_parts_ex")
 
     # ---------------------------------------------------------------------------------------
     def load_batch(self, q_ids: torch.Tensor, d_ids: torch.Tensor, n_ids: Optional[torch.Tensor] = None):

@@ -466,7 +466,7 @@ int tt_inbatch_ce_fwd_ex(const void* q_bf16, int64_t Bq, const void* d_bf16, int
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(q_bf16 && d_bf16 && loss && lse && Bq > 0 && Bd > 0 && H > 0 && d_buf_rows >= 1 && d_blk >= 1,
                "inbatch_ce_fwd_ex: bad arguments");
-  TT_CHECK_ARG(H % 64 == 0 && H <= 256 && d_blk % 64 == 0, "inbatch_ce_fwd_ex: needs H %% 64 == 0, H <= 256, d_blk %% 64 == 0");
+  TT_CHECK_ARG(H % 64 == 0 && H <= 256 && (d_blk % 128 == 0 || d_blk >= Bd), "inbatch_ce_fwd_ex: needs H %% 64 == 0, H <= 256, d_blk %% 128 == 0");
   TT_CHECK_ARG(label_offset >= 0 && Bq + label_offset <= Bd, "inbatch_ce_fwd_ex: positives out of range");
   const size_t need = tt::tc_inbatch_fwd_ex_workspace(Bq, Bd);
   if (workspace == nullptr || workspace_bytes < need) { tt::set_error("inbatch_ce_fwd_ex: workspace too small"); return TT_ERR_WORKSPACE; }

@@ -48,7 +48,11 @@ __device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2, inputs a
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
-constexpr int FWD_STAGES = 4;
+// D tiles are 128 rows: one tcgen05.mma covers N = 128 (a 128x64x16 instruction was measured at ~66 cycles, the
+// same as a 128x128x16 one, so 64-wide tiles run the tensor pipe at half rate).  The Q tile is staged through the
+// third D stage into TMEM once and then read from there by every MMA (TS mode).
+constexpr int FWD_BN = 128;
+constexpr int FWD_STAGES = 3;
 
 __global__ void __launch_bounds__(CE_THREADS, 1)
 tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmD, int64_t Bq,
@@ -58,9 +62,9 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // stays in the shared address space
   const int kq = H / 64;                                  // 64-wide K blocks
-  const uint32_t q_bytes = (uint32_t)CE_BM * H * 2, d_bytes = (uint32_t)CE_BN * H * 2;
-  uint8_t* q_tile = base;
-  uint8_t* d_tiles = base + q_bytes;
+  const uint32_t d_bytes = (uint32_t)FWD_BN * H * 2;      // == Q tile bytes (both are 128 rows)
+  uint8_t* d_tiles = base;
+  uint8_t* q_tile = base + (FWD_STAGES - 1) * d_bytes;    // Q borrows the last stage until it sits in TMEM
   uint64_t* bars = reinterpret_cast<uint64_t*>(d_tiles + FWD_STAGES * d_bytes);
   uint64_t* q_bar = bars;
   uint64_t* d_full = bars + 1;
@@ -72,7 +76,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t x0 = (int64_t)blockIdx.x * CE_BM;
-  const int ntiles = (int)ceil_div(Bd, CE_BN);
+  const int ntiles = (int)ceil_div(Bd, FWD_BN);
   const int t_beg = blockIdx.y * tiles_per_split;
   const int t_end = min(ntiles, t_beg + tiles_per_split);
   const int nt = max(0, t_end - t_beg);
@@ -85,33 +89,34 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(q_ready, 4);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_s = *tmem_slot;                     // columns [0,128): two S buffers
-  const uint32_t tmem_q = tmem_s + 128;                   // columns [128, 128 + H/2): Q tile (TMEM A operand)
+  const uint32_t tmem_s = *tmem_slot;                     // columns [0,256): two S buffers of 128
+  const uint32_t tmem_q = tmem_s + 256;                   // columns [256, 256 + H/2): Q tile (TMEM A operand)
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_bar, q_bytes);
+      mbar_arrive_expect_tx(q_bar, d_bytes);
       for (int kb = 0; kb < kq; ++kb) tma_load_2d(q_tile + kb * (CE_BM * 128), &tmQ, q_bar, kb * 64, (int)x0);
     }
     __syncwarp();
     for (int i = 0; i < nt; ++i) {                        // whole warp, uniform control flow; one lane issues
       const int s = i % FWD_STAGES;
+      if (i == FWD_STAGES - 1) mbar_wait(q_ready, 0);     // the stage Q borrowed is free once Q lives in TMEM
       mbar_wait(&d_empty[s], ((i / FWD_STAGES) & 1) ^ 1);
       uint8_t* dt = d_tiles + s * d_bytes;
+      const int64_t g = (int64_t)(t_beg + i) * FWD_BN;    // logical D row -> physical row of the (gathered) buffer
+      const int yc = (int)((g / d_blk) * d_blk_stride + (g % d_blk) + d_blk_off);
       if (elect_one()) {
         mbar_arrive_expect_tx(&d_full[s], d_bytes);
-        const int64_t g = (int64_t)(t_beg + i) * CE_BN;                       // logical D row -> physical row of the (gathered) buffer
-        const int yc = (int)((g / d_blk) * d_blk_stride + (g % d_blk) + d_blk_off);
-        for (int kb = 0; kb < kq; ++kb) tma_load_2d(dt + kb * (CE_BN * 128), &tmD, &d_full[s], kb * 64, yc);
+        for (int kb = 0; kb < kq; ++kb) tma_load_2d(dt + kb * (FWD_BN * 128), &tmD, &d_full[s], kb * 64, yc);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_bf16(CE_BM, CE_BN, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(CE_BM, FWD_BN, 0, 0);
     const uint64_t dd0 = umma_desc_kmajor(smem_u32(d_tiles), 0);
     mbar_wait(q_ready, 0);
     tc_fence_after();
@@ -125,80 +130,82 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (elect_one())
-            umma_bf16_ts(tmem_s + b * CE_BN, tmem_q + (uint32_t)(kb * 32 + k * 8),
-                         dd + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc, (kb | k) != 0);
+            umma_bf16_ts(tmem_s + b * FWD_BN, tmem_q + (uint32_t)(kb * 32 + k * 8),
+                         dd + (uint64_t)(kb * (FWD_BN * 128 / 16) + k * 2), idesc, (kb | k) != 0);
         }
       if (elect_one()) { umma_commit(&d_empty[s]); umma_commit(&s_full[b]); }
       __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
-    const int64_t row = x0 + quarter * 32 + lane;
+    const int lrow = quarter * 32 + lane;
+    const int64_t row = x0 + lrow;
     const int64_t pcol = row + label_offset;
     const float c = inv_temp * kLog2e;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     // Q tile: smem (TMA, 128B swizzle) -> registers -> TMEM, so every S product reads A from tensor memory
-    {
-      const int lrow = quarter * 32 + lane;
-      mbar_wait(q_bar, 0);
-      for (int kb = 0; kb < kq; ++kb) {
-        uint32_t xr[32];
-        const uint8_t* xrow = q_tile + kb * (CE_BM * 128) + lrow * 128;
+    mbar_wait(q_bar, 0);
+    for (int kb = 0; kb < kq; ++kb) {
+      uint32_t xr[32];
+      const uint8_t* xrow = q_tile + kb * (CE_BM * 128) + lrow * 128;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const uint4 v = *reinterpret_cast<const uint4*>(xrow + ((ch ^ (lrow & 7)) << 4));
-          xr[4 * ch] = v.x; xr[4 * ch + 1] = v.y; xr[4 * ch + 2] = v.z; xr[4 * ch + 3] = v.w;
-        }
-        tmem_st_x32(tmem_q + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kb * 32), xr);
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xrow + ((ch ^ (lrow & 7)) << 4));
+        xr[4 * ch] = v.x; xr[4 * ch + 1] = v.y; xr[4 * ch + 2] = v.z; xr[4 * ch + 3] = v.w;
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(q_ready);
+      tmem_st_x32(tmem_q + lane_addr + (uint32_t)(kb * 32), xr);
     }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(q_ready);
     float m = -CUDART_INF_F, l = 0.f;
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
-      const int64_t y0 = (int64_t)(t_beg + i) * CE_BN;
+      const int64_t y0 = (int64_t)(t_beg + i) * FWD_BN;
       mbar_wait(&s_full[b], (i >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      const uint32_t ta = tmem_s + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * CE_BN);
-      tmem_ld_x32(ta, r0);
-      tmem_ld_x32(ta + 32, r1);
+      uint32_t r[4][32];
+      const uint32_t ta = tmem_s + lane_addr + (uint32_t)(b * FWD_BN);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) tmem_ld_x32(ta + 32 * h, r[h]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);             // TMEM buffer may be overwritten
-      if (y0 + CE_BN > Bd) {                               // ragged last tile: padded columns -> -inf
+      if (y0 + FWD_BN > Bd) {                              // ragged last tile: padded columns -> -inf
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (y0 + j >= Bd) r0[j] = 0xff800000u;
-          if (y0 + 32 + j >= Bd) r1[j] = 0xff800000u;
-        }
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (y0 + 32 * h + j >= Bd) r[h][j] = 0xff800000u;
       }
       const int64_t pj = pcol - y0;                        // this row's positive column inside the tile
-      if (pj >= 0 && pj < CE_BN && row < Bq) {
+      if (pj >= 0 && pj < FWD_BN && row < Bq) {
         float pv = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j == (int)pj) pv = __uint_as_float(r0[j]);
-          if (j + 32 == (int)pj) pv = __uint_as_float(r1[j]);
-        }
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv = (32 * h + j == (int)pj) ? __uint_as_float(r[h][j]) : pv;
         pos_logit[row] = pv * inv_temp;
       }
-      float tmax = -CUDART_INF_F;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])));
-      const float mnew = fmaxf(m, tmax);
-      const float mc = mnew * c;
-      float sum0 = 0.f, sum1 = 0.f;
+      float t0 = -CUDART_INF_F, t1 = -CUDART_INF_F;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        sum0 += fast_exp2(fmaf(__uint_as_float(r0[j]), c, -mc));
-        sum1 += fast_exp2(fmaf(__uint_as_float(r1[j]), c, -mc));
+        t0 = fmaxf(t0, fmaxf(__uint_as_float(r[0][j]), __uint_as_float(r[1][j])));
+        t1 = fmaxf(t1, fmaxf(__uint_as_float(r[2][j]), __uint_as_float(r[3][j])));
       }
-      const float sum = sum0 + sum1;
-      l = l * fast_exp2((m - mnew) * c) + sum;
+      const float mnew = fmaxf(m, fmaxf(t0, t1));
+      const float mc = mnew * c;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        s0 += fast_exp2(fmaf(__uint_as_float(r[0][j]), c, -mc));
+        s1 += fast_exp2(fmaf(__uint_as_float(r[1][j]), c, -mc));
+        s2 += fast_exp2(fmaf(__uint_as_float(r[2][j]), c, -mc));
+        s3 += fast_exp2(fmaf(__uint_as_float(r[3][j]), c, -mc));
+      }
+      l = l * fast_exp2((m - mnew) * c) + ((s0 + s1) + (s2 + s3));
       m = mnew;
     }
     if (row < Bq && nt > 0) {
@@ -208,7 +215,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_s, 256);
+  if (warp == 1) tmem_dealloc(tmem_s, 512);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -495,13 +502,13 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
   else           ce_bwd_body<true>(&tmX1, &tmY1, p, base);
 }
 
-static size_t fwd_smem(int H) { return 1024 + (size_t)CE_BM * H * 2 + FWD_STAGES * (size_t)CE_BN * H * 2 + 20 * 8 + 16; }
+static size_t fwd_smem(int H) { return 1024 + FWD_STAGES * (size_t)FWD_BN * H * 2 + 20 * 8 + 16; }
 static size_t bwd_smem(int H) {
   return 1024 + (size_t)CE_BM * H * 2 + BWD_STAGES * (size_t)CE_BN * H * 2 + 2 * (size_t)CE_BM * CE_BN * 2 + 24 * 8 + 16;
 }
 
-static int pick_split(int64_t xtiles, int64_t By) {
-  const int64_t yt = ceil_div(By, CE_BN);
+static int pick_split(int64_t xtiles, int64_t By, int bn = CE_BN) {
+  const int64_t yt = ceil_div(By, bn);
   int64_t s = kNumSMs / (xtiles > 0 ? xtiles : 1);                     // one wave
   if (s > yt) s = yt;
   if (s > 32) s = 32;
@@ -515,7 +522,7 @@ static int pick_split(int64_t xtiles, int64_t By) {
 static bool tc_ce_supported(int H) { return H % 64 == 0 && H >= 64 && H <= 256; }
 
 // splits: forward uses its own; backward uses ONE split count for both passes (they share a launch)
-static int fwd_splits(int64_t Bq, int64_t Bd) { return tc::pick_split(ceil_div(Bq, tc::CE_BM), Bd); }
+static int fwd_splits(int64_t Bq, int64_t Bd) { return tc::pick_split(ceil_div(Bq, tc::CE_BM), Bd, tc::FWD_BN); }
 static int bwd_splits2(int64_t Bx0, int64_t By0, int64_t Bx1, int64_t By1) {
   const int64_t xt = ceil_div(Bx0, tc::CE_BM) + ceil_div(Bx1, tc::CE_BM);
   const int a = tc::pick_split(xt, By0), b = tc::pick_split(xt, By1);
@@ -555,9 +562,9 @@ int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* 
                       float loss_scale, float* loss, float* lse, float* pos_mean, float* part_ml, float* pos, cudaStream_t s) {
   CUtensorMap tmQ, tmD;
   int rc = tc::make_tmap_bf16(&tmQ, qa, (uint64_t)Bq, (uint64_t)H, tc::CE_BM); if (rc) return rc;
-  rc = tc::make_tmap_bf16(&tmD, da, (uint64_t)d_buf_rows, (uint64_t)H, tc::CE_BN); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmD, da, (uint64_t)d_buf_rows, (uint64_t)H, tc::FWD_BN); if (rc) return rc;
   const int ns = fwd_splits(Bq, Bd);
-  const int yt = (int)ceil_div(Bd, tc::CE_BN);
+  const int yt = (int)ceil_div(Bd, tc::FWD_BN);
   const int per = (int)ceil_div(yt, ns);
   const size_t smem = tc::fwd_smem(H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

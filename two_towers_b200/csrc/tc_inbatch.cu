@@ -221,7 +221,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // ---------------------------------------------------------------------------------------
 // backward: dQ and dD passes in ONE launch (blockIdx.z selects the pass)
 // ---------------------------------------------------------------------------------------
-constexpr int BWD_STAGES = 4;          // X 64 KB + 4 x 32 KB Y + 2 x 16 KB P = 224 KB: a full tile of slack for the TMA latency
+constexpr int BWD_STAGES = 3;          // 3 x 64 KB Y stages (X staged through the last one) + 32 KB P = 224 KB
 
 struct BwdParams {
   // index 0: dQ pass (X = queries, Y = documents, lse indexed by X row, positive at col == row + off)
@@ -240,9 +240,15 @@ struct BwdParams {
   long long* dbg;              // optional timeline buffer (TT_CE_DEBUG=1): [role 0..1][tile][8] clock64 stamps of CTA (0,0,0)
 };
 
-// X rows = this CTA's 128 output rows, Y = streamed 64-row tiles.
+// X rows = this CTA's 128 output rows, Y = streamed 128-row tiles.
 //   COL == false: X = Q, Y = D, lse indexed by X row,  positive at col == row + off   (dQ)
 //   COL == true : X = D, Y = Q, lse indexed by Y row,  positive at row == col + off   (dD)
+// Shared memory: 3 Y stages x 64 KB (the X tile is staged through the last one into TMEM) + one 32 KB P tile.
+// Tensor memory: O [0,256) | S [256,384) | X [384,512).
+// Tensor pipe order  S(0) S(1) O(0) S(2) O(1) ...: S(i+1) runs while the warps turn S(i) into P(i); every
+// tcgen05.mma has N >= 128 (a 128x64x16 instruction was measured at the same ~66 cycles as 128x128x16).
+constexpr int BWD_BN = 128;
+
 template <bool COL>
 __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtensorMap* tmY, const BwdParams& p,
                                             uint8_t* base) {
@@ -253,26 +259,26 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   float* out = p.out[PASS] + (int64_t)blockIdx.y * p.part_stride[PASS];
   const int H = p.H;
   const int kq = H / 64;
-  const uint32_t x_bytes = (uint32_t)CE_BM * H * 2, y_bytes = (uint32_t)CE_BN * H * 2;
-  constexpr uint32_t p_bytes = CE_BM * CE_BN * 2;         // 16 KB, K-major 128 rows x 64
-  uint8_t* x_tile = base;
-  uint8_t* y_tiles = x_tile + x_bytes;
-  uint8_t* p_tiles = y_tiles + BWD_STAGES * y_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_tiles + 2 * p_bytes);
+  const uint32_t y_bytes = (uint32_t)BWD_BN * H * 2;      // == X tile bytes (both are 128 rows)
+  constexpr uint32_t p_bytes = CE_BM * BWD_BN * 2;        // 32 KB: K-major, 2 k-blocks of [128 rows x 128 B]
+  uint8_t* y_tiles = base;
+  uint8_t* x_tile = base + (BWD_STAGES - 1) * y_bytes;    // X borrows the last Y stage until it sits in TMEM
+  uint8_t* p_tile = y_tiles + BWD_STAGES * y_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_tile + p_bytes);
   uint64_t* x_bar = bars;
   uint64_t* y_full = bars + 1;
   uint64_t* y_empty = y_full + BWD_STAGES;
-  uint64_t* s_full = y_empty + BWD_STAGES;                // [2]
-  uint64_t* s_empty = s_full + 2;                         // [2]
-  uint64_t* p_full = s_empty + 2;                         // [2]
-  uint64_t* p_empty = p_full + 2;                         // [2]
-  uint64_t* o_full = p_empty + 2;
+  uint64_t* s_full = y_empty + BWD_STAGES;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_empty + 1;
+  uint64_t* p_empty = p_full + 1;
+  uint64_t* o_full = p_empty + 1;
   uint64_t* x_ready = o_full + 1;                         // X tile copied into TMEM (4 epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t x0 = (int64_t)blockIdx.x * CE_BM;
-  const int ntiles = (int)ceil_div(By, CE_BN);
+  const int ntiles = (int)ceil_div(By, BWD_BN);
   const int t_beg = blockIdx.y * tiles_per_split;
   const int t_end = min(ntiles, t_beg + tiles_per_split);
   const int nt = max(0, t_end - t_beg);
@@ -283,10 +289,8 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     tma_prefetch_desc(tmX); tma_prefetch_desc(tmY);
     mbar_init(x_bar, 1);
     for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4);
-      mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1);
-    }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4);
+    mbar_init(p_full, 4); mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     mbar_init(x_ready, 4);
     fence_barrier_init();
@@ -297,24 +301,25 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base;                      // columns [0, H)
-  const uint32_t tmem_s = tmem_base + 256;                // columns [256, 384): two S buffers
-  const uint32_t tmem_x = tmem_base + 384;                // columns [384, 384 + H/2): the X tile as the TMEM A operand
+  const uint32_t tmem_s = tmem_base + 256;                // columns [256, 384): S tile
+  const uint32_t tmem_x = tmem_base + 384;                // columns [384, 384 + H/2): X tile (TMEM A operand)
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(x_bar, x_bytes);
+      mbar_arrive_expect_tx(x_bar, y_bytes);
       for (int kb = 0; kb < kq; ++kb) tma_load_2d(x_tile + kb * (CE_BM * 128), tmX, x_bar, kb * 64, (int)x0);
     }
     __syncwarp();
     for (int i = 0; i < nt; ++i) {                        // whole warp, uniform control flow; one lane issues
       const int s = i % BWD_STAGES;
+      if (i == BWD_STAGES - 1) mbar_wait(x_ready, 0);     // the stage X borrowed is free once X lives in TMEM
       mbar_wait(&y_empty[s], ((i / BWD_STAGES) & 1) ^ 1);
       uint8_t* yt = y_tiles + s * y_bytes;
+      const int64_t g = (int64_t)(t_beg + i) * BWD_BN;
+      const int yc = (int)((g / p.y_blk[PASS]) * p.y_blk_stride[PASS] + (g % p.y_blk[PASS]) + p.y_blk_off[PASS]);
       if (elect_one()) {
         mbar_arrive_expect_tx(&y_full[s], y_bytes);
-        const int64_t g = (int64_t)(t_beg + i) * CE_BN;
-        const int yc = (int)((g / p.y_blk[PASS]) * p.y_blk_stride[PASS] + (g % p.y_blk[PASS]) + p.y_blk_off[PASS]);
-        for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (CE_BN * 128), tmY, &y_full[s], kb * 64, yc);
+        for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (BWD_BN * 128), tmY, &y_full[s], kb * 64, yc);
       }
       __syncwarp();
     }
@@ -322,17 +327,17 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     if (nt > 0) {
       // whole warp in uniform control flow: descriptors live in uniform registers, only the tcgen05
       // instructions are predicated on the elected lane
-      const uint32_t idesc_s = umma_idesc_bf16(CE_BM, CE_BN, 0, 0);
+      const uint32_t idesc_s = umma_idesc_bf16(CE_BM, BWD_BN, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(CE_BM, H, 0, 1);     // B = Y tile read MN-major
-      const uint64_t dp0 = umma_desc_kmajor(smem_u32(p_tiles), 0);
+      const uint64_t dp0 = umma_desc_kmajor(smem_u32(p_tile), 0);
       const uint64_t dyk0 = umma_desc_kmajor(smem_u32(y_tiles), 0);
-      const uint64_t dym0 = umma_desc_mnmajor(smem_u32(y_tiles), 0, CE_BN * 128);
+      const uint64_t dym0 = umma_desc_mnmajor(smem_u32(y_tiles), 0, BWD_BN * 128);
       auto issue_s = [&](int i) {
-        const int s = i % BWD_STAGES, b = i & 1;
+        const int s = i % BWD_STAGES;
         if (lane == 0) TT_STAMP(0, i, 0);
         mbar_wait(&y_full[s], (i / BWD_STAGES) & 1);
         if (lane == 0) TT_STAMP(0, i, 1);
-        mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
+        mbar_wait(s_empty, (i & 1) ^ 1);
         if (lane == 0) TT_STAMP(0, i, 2);
         tc_fence_after();
         const uint64_t dy = dyk0 + (uint64_t)((s * y_bytes) >> 4);
@@ -340,33 +345,38 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (elect_one())
-              umma_bf16_ts(tmem_s + b * CE_BN, tmem_x + (uint32_t)(kb * 32 + k * 8),
-                           dy + (uint64_t)(kb * (CE_BN * 128 / 16) + k * 2), idesc_s, (kb | k) != 0);
+              umma_bf16_ts(tmem_s, tmem_x + (uint32_t)(kb * 32 + k * 8),
+                           dy + (uint64_t)(kb * (BWD_BN * 128 / 16) + k * 2), idesc_s, (kb | k) != 0);
           }
-        if (elect_one()) umma_commit(&s_full[b]);
+        if (elect_one()) umma_commit(s_full);
         __syncwarp();
         if (lane == 0) TT_STAMP(0, i, 3);
+      };
+      auto issue_o = [&](int i) {
+        const int s = i % BWD_STAGES;
+        if (lane == 0) TT_STAMP(0, i, 4);
+        mbar_wait(p_full, i & 1);
+        if (lane == 0) TT_STAMP(0, i, 5);
+        tc_fence_after();
+        const uint64_t dy = dym0 + (uint64_t)((s * y_bytes) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < BWD_BN / 16; ++kk) {         // K = 128 Y rows: 2 P k-blocks x 4 slices
+          if (elect_one())
+            umma_bf16(tmem_o, dp0 + (uint64_t)((kk >> 2) * (CE_BM * 128 / 16) + (kk & 3) * 2),
+                      dy + (uint64_t)(kk * (2048 / 16)), idesc_o, (i | kk) != 0);
+        }
+        if (elect_one()) { umma_commit(p_empty); umma_commit(&y_empty[s]); }
+        __syncwarp();
+        if (lane == 0) TT_STAMP(0, i, 6);
       };
       mbar_wait(x_ready, 0);
       tc_fence_after();
       issue_s(0);
-      for (int i = 0; i < nt; ++i) {
-        if (i + 1 < nt) issue_s(i + 1);
-        const int s = i % BWD_STAGES, b = i & 1;
-        if (lane == 0) TT_STAMP(0, i, 4);
-        mbar_wait(&p_full[b], (i >> 1) & 1);
-        if (lane == 0) TT_STAMP(0, i, 5);
-        tc_fence_after();
-        const uint64_t dp = dp0 + (uint64_t)((b * p_bytes) >> 4);
-        const uint64_t dy = dym0 + (uint64_t)((s * y_bytes) >> 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (elect_one()) umma_bf16(tmem_o, dp + (uint64_t)(k * 2), dy + (uint64_t)(k * (2048 / 16)), idesc_o, (i | k) != 0);
-        }
-        if (elect_one()) { umma_commit(&p_empty[b]); umma_commit(&y_empty[s]); }
-        __syncwarp();
-        if (lane == 0) TT_STAMP(0, i, 6);
+      for (int i = 1; i < nt; ++i) {
+        issue_s(i);
+        issue_o(i - 1);
       }
+      issue_o(nt - 1);
       if (elect_one()) umma_commit(o_full);
       __syncwarp();
     }
@@ -374,11 +384,10 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     const int quarter = warp & 3;
     const int lrow = quarter * 32 + lane;                  // row inside the tile == TMEM lane
     const int64_t row = x0 + lrow;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float c = p.inv_temp * kLog2e;
     const float row_lse = (!COL && row < Bx) ? lse[row] * kLog2e : 0.f;
-    // X tile: shared memory (TMA, 128B swizzle) -> registers -> TMEM.  Every S = X Y^T product of this CTA then
-    // reads its A operand from tensor memory; with A in smem the 128x16 slice re-read per MMA saturates the
-    // shared-memory port and the N=64 product runs at half rate (measured 66 vs 32 cycles per tcgen05.mma).
+    // X tile: shared memory (TMA, 128B swizzle) -> registers -> TMEM (the TS-mode A operand of every S product)
     mbar_wait(x_bar, 0);
     for (int kb = 0; kb < kq; ++kb) {
       uint32_t xr[32];
@@ -388,7 +397,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         const uint4 v = *reinterpret_cast<const uint4*>(xrow + ((ch ^ (lrow & 7)) << 4));
         xr[4 * ch] = v.x; xr[4 * ch + 1] = v.y; xr[4 * ch + 2] = v.z; xr[4 * ch + 3] = v.w;
       }
-      tmem_st_x32(tmem_x + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kb * 32), xr);
+      tmem_st_x32(tmem_x + lane_addr + (uint32_t)(kb * 32), xr);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -397,60 +406,65 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     // Y tiles that can hold a positive of one of this CTA's rows (CTA-uniform band)
     const int64_t band_lo = COL ? x0 - label_offset : x0 + label_offset;
     for (int i = 0; i < nt; ++i) {
-      const int b = i & 1;
-      const int64_t y0 = (int64_t)(t_beg + i) * CE_BN;
-      float cl0 = 0.f, cl1 = 0.f;                           // column lse (COL mode): lane holds columns lane, lane+32
+      const int64_t y0 = (int64_t)(t_beg + i) * BWD_BN;
+      float cl[4] = {0.f, 0.f, 0.f, 0.f};                   // column lse (COL mode): lane holds columns lane + 32 h
       if (COL) {
-        cl0 = (y0 + lane < By) ? __ldg(lse + y0 + lane) * kLog2e : CUDART_INF_F;
-        cl1 = (y0 + 32 + lane < By) ? __ldg(lse + y0 + 32 + lane) * kLog2e : CUDART_INF_F;
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          cl[h] = (y0 + 32 * h + lane < By) ? __ldg(lse + y0 + 32 * h + lane) * kLog2e : CUDART_INF_F;
       }
       if (threadIdx.x == 64) TT_STAMP(1, i, 0);
-      mbar_wait(&s_full[b], (i >> 1) & 1);
+      mbar_wait(s_full, i & 1);
       if (threadIdx.x == 64) TT_STAMP(1, i, 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      const uint32_t ta = tmem_s + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * CE_BN);
-      tmem_ld_x32(ta, r0);
-      tmem_ld_x32(ta + 32, r1);
+      uint32_t r[4][32];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) tmem_ld_x32(tmem_s + lane_addr + 32 * h, r[h]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);
+      if (lane == 0) mbar_arrive(s_empty);                 // S(i+1) may overwrite the accumulator
       if (threadIdx.x == 64) TT_STAMP(1, i, 2);
-      // P = exp2(S*c - lse*log2e); ragged columns get lse = +inf -> P = 0 (row mode: masked below)
-      float pv[64];
+      // P = exp2(S*c - lse*log2e) (ragged columns: lse = +inf in COL mode, masked below otherwise), in place
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float l0 = COL ? __shfl_sync(0xffffffffu, cl0, j) : row_lse;
-        const float l1 = COL ? __shfl_sync(0xffffffffu, cl1, j) : row_lse;
-        pv[j] = fast_exp2(fmaf(__uint_as_float(r0[j]), c, -l0));
-        pv[32 + j] = fast_exp2(fmaf(__uint_as_float(r1[j]), c, -l1));
-      }
-      if (!COL && y0 + CE_BN > By) {
+      for (int h = 0; h < 4; ++h)
 #pragma unroll
-        for (int j = 0; j < 64; ++j)
-          if (y0 + j >= By) pv[j] = 0.f;
+        for (int j = 0; j < 32; ++j) {
+          const float lv = COL ? __shfl_sync(0xffffffffu, cl[h], j) : row_lse;
+          r[h][j] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j]), c, -lv)));
+        }
+      if (!COL && y0 + BWD_BN > By) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (y0 + 32 * h + j >= By) r[h][j] = 0u;
       }
-      if (y0 + CE_BN > band_lo && y0 < band_lo + CE_BM) {   // tile intersects the diagonal band
+      if (y0 + BWD_BN > band_lo && y0 < band_lo + CE_BM) {  // tile intersects the diagonal band
         const int64_t pj = (COL ? row - label_offset : row + label_offset) - y0;
-        if (pj >= 0 && pj < CE_BN && y0 + pj < By) {
+        if (pj >= 0 && pj < BWD_BN && y0 + pj < By) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) pv[j] -= (j == (int)pj) ? 1.0f : 0.0f;     // select, keeps pv[] in registers
+          for (int h = 0; h < 4; ++h)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              r[h][j] = __float_as_uint(__uint_as_float(r[h][j]) - ((32 * h + j == (int)pj) ? 1.0f : 0.0f));
         }
       }
       if (threadIdx.x == 64) TT_STAMP(1, i, 3);
-      mbar_wait(&p_empty[b], ((i >> 1) & 1) ^ 1);          // O-GEMM(i-2) has finished reading this P buffer
+      mbar_wait(p_empty, (i & 1) ^ 1);                     // O(i-1) has finished reading the P tile
       if (threadIdx.x == 64) TT_STAMP(1, i, 4);
-      uint8_t* prow = p_tiles + b * p_bytes + lrow * 128;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {                      // 8 x 16-byte chunks, 128B swizzle: chunk ^= row & 7
-        uint4 v = make_uint4(pack_bf16x2(pv[8 * ch + 0], pv[8 * ch + 1]), pack_bf16x2(pv[8 * ch + 2], pv[8 * ch + 3]),
-                             pack_bf16x2(pv[8 * ch + 4], pv[8 * ch + 5]), pack_bf16x2(pv[8 * ch + 6], pv[8 * ch + 7]));
-        *reinterpret_cast<uint4*>(prow + ((ch ^ (lrow & 7)) << 4)) = v;
+      for (int ch = 0; ch < 16; ++ch) {                     // 16 x 16-byte chunks: k-block ch/8, 128B swizzle inside
+        const int h = ch >> 2, j0 = (ch & 3) * 8;
+        const uint4 v = make_uint4(pack_bf16x2(__uint_as_float(r[h][j0 + 0]), __uint_as_float(r[h][j0 + 1])),
+                                   pack_bf16x2(__uint_as_float(r[h][j0 + 2]), __uint_as_float(r[h][j0 + 3])),
+                                   pack_bf16x2(__uint_as_float(r[h][j0 + 4]), __uint_as_float(r[h][j0 + 5])),
+                                   pack_bf16x2(__uint_as_float(r[h][j0 + 6]), __uint_as_float(r[h][j0 + 7])));
+        *reinterpret_cast<uint4*>(p_tile + (ch >> 3) * (CE_BM * 128) + lrow * 128 + (((ch & 7) ^ (lrow & 7)) << 4)) = v;
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (lane == 0) mbar_arrive(p_full);
       if (threadIdx.x == 64) TT_STAMP(1, i, 5);
     }
     // final: O (TMEM) -> registers -> warp-private smem transpose -> 128-byte coalesced global stores
@@ -459,23 +473,23 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       mbar_wait(o_full, 0);
       tc_fence_after();
     }
-    float* T = reinterpret_cast<float*>(p_tiles + (warp - 2) * (32 * 36 * 4));      // [32][36], P buffers are free now
+    float* T = reinterpret_cast<float*>(p_tile + (warp - 2) * (32 * 36 * 4));       // [32][36], the P tile is free now
     const int64_t row0 = x0 + quarter * 32;
     const int nrows = (int)min((int64_t)32, Bx - row0);
     float* orow = out + row0 * H + lane;
     for (int cb = 0; cb < H / 32; ++cb) {
-      uint32_t r[32];
+      uint32_t q[32];
       if (nt > 0) {
-        tmem_ld_x32(tmem_o + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cb * 32), r);
+        tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
+        for (int j = 0; j < 32; ++j) q[j] = 0u;
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(&T[lane * 36 + j]) = make_float4(__uint_as_float(r[j]) * scale, __uint_as_float(r[j + 1]) * scale,
-                                                                    __uint_as_float(r[j + 2]) * scale, __uint_as_float(r[j + 3]) * scale);
+        *reinterpret_cast<float4*>(&T[lane * 36 + j]) = make_float4(__uint_as_float(q[j]) * scale, __uint_as_float(q[j + 1]) * scale,
+                                                                    __uint_as_float(q[j + 2]) * scale, __uint_as_float(q[j + 3]) * scale);
       __syncwarp();
       float v[32];
 #pragma unroll
@@ -504,7 +518,7 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
 
 static size_t fwd_smem(int H) { return 1024 + FWD_STAGES * (size_t)FWD_BN * H * 2 + 20 * 8 + 16; }
 static size_t bwd_smem(int H) {
-  return 1024 + (size_t)CE_BM * H * 2 + BWD_STAGES * (size_t)CE_BN * H * 2 + 2 * (size_t)CE_BM * CE_BN * 2 + 24 * 8 + 16;
+  return 1024 + BWD_STAGES * (size_t)BWD_BN * H * 2 + (size_t)CE_BM * BWD_BN * 2 + 24 * 8 + 16;
 }
 
 static int pick_split(int64_t xtiles, int64_t By, int bn = CE_BN) {
@@ -525,7 +539,7 @@ static bool tc_ce_supported(int H) { return H % 64 == 0 && H >= 64 && H <= 256; 
 static int fwd_splits(int64_t Bq, int64_t Bd) { return tc::pick_split(ceil_div(Bq, tc::CE_BM), Bd, tc::FWD_BN); }
 static int bwd_splits2(int64_t Bx0, int64_t By0, int64_t Bx1, int64_t By1) {
   const int64_t xt = ceil_div(Bx0, tc::CE_BM) + ceil_div(Bx1, tc::CE_BM);
-  const int a = tc::pick_split(xt, By0), b = tc::pick_split(xt, By1);
+  const int a = tc::pick_split(xt, By0, tc::BWD_BN), b = tc::pick_split(xt, By1, tc::BWD_BN);
   return a < b ? a : b;
 }
 static int bwd_splits(int64_t Bq, int64_t Bd) { return bwd_splits2(Bq, Bd, Bd, Bq); }
@@ -611,15 +625,15 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
                          float coef, cudaStream_t s) {
   CUtensorMap tmX0, tmY0, tmX1, tmY1;
   int rc = tc::make_tmap_bf16(&tmX0, pq.x, (uint64_t)pq.Bx, (uint64_t)H, tc::CE_BM); if (rc) return rc;
-  rc = tc::make_tmap_bf16(&tmY0, pq.y, (uint64_t)pq.y_buf_rows, (uint64_t)H, tc::CE_BN); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmY0, pq.y, (uint64_t)pq.y_buf_rows, (uint64_t)H, tc::BWD_BN); if (rc) return rc;
   rc = tc::make_tmap_bf16(&tmX1, pd.x, (uint64_t)pd.Bx, (uint64_t)H, tc::CE_BM); if (rc) return rc;
-  rc = tc::make_tmap_bf16(&tmY1, pd.y, (uint64_t)pd.y_buf_rows, (uint64_t)H, tc::CE_BN); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmY1, pd.y, (uint64_t)pd.y_buf_rows, (uint64_t)H, tc::BWD_BN); if (rc) return rc;
   tc::BwdParams p{};
   const CePass* ps[2] = {&pq, &pd};
   for (int k = 0; k < 2; ++k) {
     p.lse[k] = ps[k]->lse; p.Bx[k] = ps[k]->Bx; p.By[k] = ps[k]->By; p.label_offset[k] = ps[k]->label_offset;
     p.y_blk[k] = ps[k]->y_blk > 0 ? ps[k]->y_blk : 1; p.y_blk_stride[k] = ps[k]->y_blk_stride; p.y_blk_off[k] = ps[k]->y_blk_off;
-    p.tiles_per_split[k] = (int)ceil_div(ceil_div(ps[k]->By, tc::CE_BN), nsplit);
+    p.tiles_per_split[k] = (int)ceil_div(ceil_div(ps[k]->By, tc::BWD_BN), nsplit);
     p.out[k] = ps[k]->out; p.part_stride[k] = ps[k]->part_stride;
   }
   p.H = H; p.inv_temp = inv_temp; p.grad_out = grad_out; p.coef = coef;
@@ -689,7 +703,7 @@ int tc_inbatch_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pa
   const CePass pq = conv(q_pass), pd = conv(d_pass);
   const int want = bwd_splits2(pq.Bx, pq.By, pd.Bx, pd.By);
   if (nparts != want) { set_error("tc_inbatch_bwd_parts_ex: nparts %d != %d (query tt_inbatch_ce_bwd_nparts_ex)", nparts, want); return TT_ERR_INVALID; }
-  if (pq.y_blk % tc::CE_BN != 0 || pd.y_blk % tc::CE_BN != 0) { set_error("tc_inbatch_bwd_parts_ex: y_blk must be a multiple of %d", tc::CE_BN); return TT_ERR_UNSUPPORTED; }
+  if (pq.y_blk % tc::BWD_BN != 0 || pd.y_blk % tc::BWD_BN != 0) { set_error("tc_inbatch_bwd_parts_ex: y_blk must be a multiple of %d", tc::BWD_BN); return TT_ERR_UNSUPPORTED; }
   return launch_tc_bwd(pq, pd, H, inv_temp, nparts, grad_out, loss_scale * inv_temp, s);
 }
 

@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out
+mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tensor_core.py -q --timeout 600 -p no:cacheprovider -x > $O/pytest_all.log 2>&1; echo "exit $?" >> $O/pytest_all.log
+bash tools/gpu_run7.sh > /dev/null 2>&1
+timeout 300 python tools/time_ops.py --precision bf16 > $O/time_ops_bf16.log 2>&1; echo "exit $?" >> $O/time_ops_bf16.log
+tail -3 $O/pytest_all.log; grep -A200 "per-CTA" $O/ce_timeline.log | awk 'NR%8==2' | tail -18; cat $O/time_ops_bf16.log

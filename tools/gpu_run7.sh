@@ -2,7 +2,7 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-TT_CE_DEBUG=1 timeout 300 python - > $O/ce_timeline.log 2>&1 <<'PY'
+TT_CE_DEBUG=${CE_PASS:-0} timeout 300 python - > $O/ce_timeline.log 2>&1 <<'PY'
 import torch, two_towers_b200 as tt
 B,H=4096,256
 q=torch.nn.functional.normalize(torch.randn(B,H,device='cuda'),dim=-1); d=torch.nn.functional.normalize(torch.randn(B,H,device='cuda'),dim=-1)

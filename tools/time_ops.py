@@ -15,6 +15,11 @@ from two_towers_b200 import _lib
 from two_towers_b200.train import _p
 
 
+FLUSH_MODE = "write"
+FLUSH_BUF2 = None
+FLUSH_SINK = []
+
+
 def timed(fn, flush, reps=12):
     fn(); torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
@@ -23,6 +28,9 @@ def timed(fn, flush, reps=12):
     ts = []
     for i in range(reps):
         flush.add_(1)
+        if FLUSH_MODE == "write_read":          # read a second buffer: dirty lines are written back, L2 is cold AND clean
+            FLUSH_SINK.append(float(0) if FLUSH_BUF2 is None else 0.0)
+            torch.sum(FLUSH_BUF2, dtype=torch.float32)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); g.replay(); e1.record()
         torch.cuda.synchronize()
@@ -35,8 +43,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--B", type=int, default=4096)
+    ap.add_argument("--flush", default="write", choices=["write", "write_read"])
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
+    global FLUSH_MODE, FLUSH_BUF2
+    FLUSH_MODE = a.flush
+    if a.flush == "write_read":
+        FLUSH_BUF2 = torch.ones(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     torch.manual_seed(0)
     emb = tt.embeddings.build("lookup", 128, embedding_dim=64)
     model = tt.build_two_tower("mean", emb, hidden_dim=256, tied_weights=True).to(dev)
@@ -73,6 +86,23 @@ def main():
             total += t
         print(f"{name:16s} {t:9.1f} us   ({nl} launches)")
     print(f"{'sum of ops':16s} {total:9.1f} us")
+    # cumulative prefixes of the step in ONE graph: the differences are each op's cost inside the pipeline
+    # (launch gaps included, the single-graph replay floor cancelled)
+    names = [n for n in ops if n != "whole_step"]
+    prev = 0.0
+    for k in range(1, len(names) + 1):
+        def prefix(k=k):
+            for n in names[:k]:
+                ops[n]()
+        t = timed(prefix, flush, reps=16)
+        print(f"prefix..{names[k - 1]:16s} {t:9.1f} us   (+{t - prev:6.1f})")
+        prev = t
+    # launch-boundary cost: 32 back-to-back AdamW launches over a tiny slice
+    def chain():
+        for _ in range(32):
+            check(lib.tt_adamw_step(_p(tr.flat), _p(tr.flat_grad), _p(tr.exp_avg), _p(tr.exp_avg_sq), 1024, 1e-3, 0.9, 0.999, 1e-8, 0.01, _p(tr.step_count), _p(tr.flat_bf16), s()), "x")
+    t = timed(chain, flush, reps=16)
+    print(f"32 tiny launches {t:9.1f} us   ({t / 32:.2f} us per boundary, TT_PDL={os.environ.get('TT_PDL', '1')})")
 
 
 if __name__ == "__main__":

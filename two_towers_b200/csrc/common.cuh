@@ -69,8 +69,35 @@ struct Workspace {
 
 constexpr int kNumSMs = 148;    // B200: 2 dies x 74 SMs
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Kernels on the training path call pdl_trigger() as their first instruction and pdl_wait() before their
+// first access to global memory produced by the previous kernel.  Launched with the programmatic-stream-
+// serialization attribute, kernel N+1 is scheduled as soon as every CTA of kernel N has started, so its launch
+// latency and prologue (barrier init, TMEM allocation, tensor-map prefetch) overlap the tail of kernel N.
+// Dependents launch only after ALL CTAs of the primary have triggered, so no primary CTA can be starved.
+bool pdl_enabled();             // env TT_PDL=0 switches the attribute off (plain stream order)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl && pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    na = 1;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- device helpers --------------------------------------------------------------------
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256)
 embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ table, int64_t rows,
                       int L, int64_t V, int E, int tpt, float* __restrict__ pooled,
                       float* __restrict__ inv_len, __nv_bfloat16* __restrict__ pooled_bf16) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -159,6 +161,8 @@ __global__ void __launch_bounds__(256)
 pool_matrix_kernel(const IdT* __restrict__ ids, const float* __restrict__ inv_len, int64_t rows,
                    int L, int V, float* __restrict__ P) {
   extern __shared__ int hist[];                       // [warps][V]
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int* h = hist + w * V;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
@@ -299,19 +303,19 @@ static int embed_pool_fwd_t(const IdT* ids, const float* table, int64_t rows, in
                    ((reinterpret_cast<uintptr_t>(pooled) & 15) == 0) &&
                    (pooled_bf16 == nullptr || (reinterpret_cast<uintptr_t>(pooled_bf16) & 7) == 0);
   if (!vec) {
-    embed_pool_fwd_kernel<IdT, 1, false><<<grid, warps * 32, 0, s>>>(ids, table, rows, L, V, E, 32,
-                                                                       pooled, inv_len, pooled_bf16);
+    TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 1, false>, dim3(grid), dim3(warps * 32), 0, s, true, ids, table, rows, L, V, E, 32,
+                          pooled, inv_len, pooled_bf16));
   } else {
     const int chunks = E / 4;
     int tpt = 1;
     while (tpt < chunks && tpt < 32) tpt <<= 1;
     const int per_lane = (int)ceil_div(chunks, tpt);
     if (per_lane <= 1)
-      embed_pool_fwd_kernel<IdT, 1, true><<<grid, warps * 32, 0, s>>>(ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16);
+      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 1, true>, dim3(grid), dim3(warps * 32), 0, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16));
     else if (per_lane == 2)
-      embed_pool_fwd_kernel<IdT, 2, true><<<grid, warps * 32, 0, s>>>(ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16);
+      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 2, true>, dim3(grid), dim3(warps * 32), 0, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16));
     else
-      embed_pool_fwd_kernel<IdT, 3, true><<<grid, warps * 32, 0, s>>>(ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16);
+      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 3, true>, dim3(grid), dim3(warps * 32), 0, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16));
   }
   TT_LAUNCH_CHECK("embed_pool_fwd_kernel");
   return TT_OK;
@@ -331,8 +335,8 @@ static int embed_pool_bwd_t(const IdT* ids, const float* inv_len, const float* d
     float* P = w.take<float>((size_t)rows * V);
     float* partial = plan.splits > 1 ? w.take<float>((size_t)plan.splits * V * E) : nullptr;
     const int warps = 8;
-    pool_matrix_kernel<IdT><<<(unsigned)ceil_div(rows, warps), warps * 32, warps * V * sizeof(int), s>>>(
-        ids, inv_len, rows, L, (int)V, P);
+    TT_CUDA(launch_kernel(pool_matrix_kernel<IdT>, dim3((unsigned)ceil_div(rows, warps)), dim3(warps * 32), warps * V * sizeof(int), s, true,
+                          ids, inv_len, rows, L, (int)V, P));
     TT_LAUNCH_CHECK("pool_matrix_kernel");
     SgemmArgs a{};
     a.M = (int)V; a.N = E; a.K = (int)rows;

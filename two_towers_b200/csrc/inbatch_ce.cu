@@ -152,6 +152,8 @@ ce_finalize_kernel(const float* __restrict__ part_ml, const float* __restrict__ 
                    int64_t Bq, float inv_temp, float loss_scale, float* __restrict__ lse,
                    float* __restrict__ loss, float* __restrict__ pos_mean) {
   __shared__ float s_loss[1024], s_pos[1024];
+  pdl_trigger();
+  pdl_wait();
   float tl = 0.f, tp = 0.f;
   for (int64_t row = threadIdx.x; row < Bq; row += 1024) {
     // (max, sum) pairs of all splits: loads issued back to back (8 in flight), then combined in split order
@@ -190,7 +192,7 @@ ce_finalize_kernel(const float* __restrict__ part_ml, const float* __restrict__ 
 int inbatch_finalize(const float* part_ml, const float* pos_logit, int nsplit, int64_t Bq, float inv_temp,
                      float loss_scale, float* lse, float* loss, float* pos_mean, float* /*scratch*/,
                      cudaStream_t s) {
-  ce_finalize_kernel<<<1, 1024, 0, s>>>(part_ml, pos_logit, nsplit, Bq, inv_temp, loss_scale, lse, loss, pos_mean);
+  TT_CUDA(launch_kernel(ce_finalize_kernel, dim3(1), dim3(1024), 0, s, true, part_ml, pos_logit, nsplit, Bq, inv_temp, loss_scale, lse, loss, pos_mean));
   TT_LAUNCH_CHECK("ce_finalize_kernel");
   return TT_OK;
 }

@@ -15,6 +15,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
              int64_t* step_count, __nv_bfloat16* __restrict__ p_bf16) {
   // scalars are formed in double (as Python does in torch.optim) and rounded to fp32 once
   __shared__ float s_neg_step_size, s_sqrt_bc2;
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0) {
     const double t = (double)(*step_count + 1);
     const double bc1 = 1.0 - pow(beta1, t);
@@ -61,8 +63,8 @@ extern "C" int tt_adamw_step(float* param, const float* grad, float* exp_avg, fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int64_t blocks = tt::ceil_div(n > 0 ? n : 1, 256);
   if (blocks > 8 * tt::kNumSMs) blocks = 8 * tt::kNumSMs;
-  tt::adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                    weight_decay, step_count, (__nv_bfloat16*)param_bf16);
+  TT_CUDA(tt::launch_kernel(tt::adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, s, true, param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                            beta2, eps, weight_decay, step_count, (__nv_bfloat16*)param_bf16));
   TT_LAUNCH_CHECK("adamw_kernel");
   return TT_OK;
 }

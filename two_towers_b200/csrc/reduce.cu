@@ -4,6 +4,8 @@ namespace tt {
 
 __global__ void __launch_bounds__(256) reduce_parts_kernel(const ReduceJobs jobs) {
   __shared__ float s_tot[8][32];
+  pdl_trigger();
+  pdl_wait();
   const ReduceJob& j = jobs.job[blockIdx.y];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 32 + lane;
@@ -43,7 +45,7 @@ int reduce_parts(const ReduceJobs& jobs, cudaStream_t s) {
   int64_t nmax = 0;
   for (int k = 0; k < jobs.njobs; ++k) nmax = jobs.job[k].n > nmax ? jobs.job[k].n : nmax;
   dim3 grid((unsigned)ceil_div(nmax, 32), (unsigned)jobs.njobs);
-  reduce_parts_kernel<<<grid, 256, 0, s>>>(jobs);
+  TT_CUDA(launch_kernel(reduce_parts_kernel, grid, dim3(256), 0, s, true, jobs));
   TT_LAUNCH_CHECK("reduce_parts_kernel");
   return TT_OK;
 }

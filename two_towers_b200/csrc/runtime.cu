@@ -1,5 +1,6 @@
 // runtime.cu -- library plumbing: error strings, device gate, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -24,6 +25,11 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("TT_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 // cached per-device verdict: 0 unknown, 1 ok, -1 not sm_100
 static std::atomic<int> g_dev_ok[64];

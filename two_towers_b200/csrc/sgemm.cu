@@ -17,6 +17,8 @@ sgemm_kernel(SgemmArgs a, int kchunk) {
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
 
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int tx = tid % TXN, ty = tid / TXN;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -142,11 +144,11 @@ template <int BM, int BN, int BK, int TM, int TN>
 static void launch_cfg(const SgemmArgs& a, int kchunk, dim3 grid, cudaStream_t s) {
   constexpr int NT = (BM / TM) * (BN / TN);
   if (a.transA) {
-    if (a.transB) sgemm_kernel<BM, BN, BK, TM, TN, true, true><<<grid, NT, 0, s>>>(a, kchunk);
-    else          sgemm_kernel<BM, BN, BK, TM, TN, true, false><<<grid, NT, 0, s>>>(a, kchunk);
+    if (a.transB) (void)launch_kernel(sgemm_kernel<BM, BN, BK, TM, TN, true, true>, grid, dim3(NT), 0, s, true, a, kchunk);
+    else          (void)launch_kernel(sgemm_kernel<BM, BN, BK, TM, TN, true, false>, grid, dim3(NT), 0, s, true, a, kchunk);
   } else {
-    if (a.transB) sgemm_kernel<BM, BN, BK, TM, TN, false, true><<<grid, NT, 0, s>>>(a, kchunk);
-    else          sgemm_kernel<BM, BN, BK, TM, TN, false, false><<<grid, NT, 0, s>>>(a, kchunk);
+    if (a.transB) (void)launch_kernel(sgemm_kernel<BM, BN, BK, TM, TN, false, true>, grid, dim3(NT), 0, s, true, a, kchunk);
+    else          (void)launch_kernel(sgemm_kernel<BM, BN, BK, TM, TN, false, false>, grid, dim3(NT), 0, s, true, a, kchunk);
   }
 }
 

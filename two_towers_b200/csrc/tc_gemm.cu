@@ -14,6 +14,9 @@
 // Both operand majors are supported because the backward GEMMs (dW = dY^T X, dX = dY W) consume
 // the same row-major activations with the roles of the axes swapped; no transposes are
 // materialised.
+#include <stdlib.h>
+#include <vector>
+
 #include "tc_common.cuh"
 #include "sgemm.cuh"
 #include "tensor_core.cuh"
@@ -78,19 +81,26 @@ struct GemmParams {
   int splits;
   int tiles_m, tiles_n, nblocks;   // block decomposition of this problem inside a (possibly shared) launch
   float* colsum_part;         // nullable [ceil(M/32), N]: per-32-row column sums of the epilogue output (bias grads)
+  long long* dbg;             // developer aid (TT_GEMM_DEBUG=1): [cta][4] %globaltimer stamps
 };
 
-constexpr int kStages = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kStages = 3;                 // 3 x 32 KB: two CTAs fit one SM and overlap each other's prologue / epilogue
+constexpr int kGemmThreads = 192;         // TMA warp, MMA warp, 4 epilogue warps (one per TMEM lane quarter)
 constexpr int BM = 128, BK = 64;
 constexpr uint32_t kATile = BM * BK * 2;                         // 16 KB
 
 // Up to two independent GEMM problems share one launch (e.g. {dW2 = dz^T h1, da1 = dz W2} in the tower
 // backward): CTAs [0, p0.nblocks) work on problem 0, the rest on problem 1.
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0, const GemmParams p0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const GemmParams p1) {
+  pdl_trigger();
+  long long* cta_dbg = p0.dbg ? p0.dbg + 4 * blockIdx.x : nullptr;
+  long long* fine = (p0.dbg && (blockIdx.x == 0 || (int)blockIdx.x == p0.nblocks)) ? p0.dbg + 4 * (gridDim.x + (blockIdx.x ? 64 : 0)) : nullptr;
+#define TT_FINE(c, slot) do { if (fine && threadIdx.x == 64) fine[(c) * 8 + (slot)] = clock64(); } while (0)
+#define TT_GEMM_STAMP(slot) do { if (cta_dbg && threadIdx.x == 64) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); cta_dbg[slot] = t_; } } while (0)
+  TT_GEMM_STAMP(0);
   const bool second = (int)blockIdx.x >= p0.nblocks;
   const GemmParams& p = second ? p1 : p0;
   const CUtensorMap& tmA = second ? tmA1 : tmA0;
@@ -106,7 +116,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* acc_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-  uint8_t* stage_tiles = reinterpret_cast<uint8_t*>(tmem_slot) + 128 - (((2 * kStages + 1) * 8) & 127);   // 128-B aligned: 4 x [32][36] fp32 staging
+  uint8_t* stage_tiles = tiles;   // 4 x [32][36] fp32 epilogue staging: reuses pipeline stage 0 (idle once the accumulator is complete)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = by * BM, n0 = bx * BN;
@@ -127,6 +137,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  pdl_wait();                                             // everything above overlapped the previous kernel's tail
+  TT_GEMM_STAMP(1);
 
   if (warp == 0) {
     for (int i = 0; i < nkb; ++i) {                       // whole warp, uniform control flow; one lane issues
@@ -171,19 +183,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // (and the bias / mask loads) are coalesced: lane == column, 128 contiguous bytes per row.
     const int quarter = warp & 3;
     float (*T)[36] = reinterpret_cast<float (*)[36]>(stage_tiles + (warp - 2) * (32 * 36 * 4));
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
     const bool split = p.splits > 1;
     float* outp = split ? p.C + (size_t)bz * p.M * p.N : p.C;
     const int ldo = split ? p.N : p.ldc;
     const int row0 = m0 + quarter * 32;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      // ReLU-gate mask for this thread's accumulator row (32 bf16 = 64 contiguous bytes, two full sectors):
-      // issued before the TMEM load so its latency overlaps the accumulator read
-      uint4 mk[4];
-      const bool use_mask = !split && p.mask != nullptr;
-      if (use_mask) {
+    // everything the loop needs, in registers (p is a run-time choice between two parameter blocks)
+    const int N = p.N;
+    const float* bias = split ? nullptr : p.bias;
+    const bool has_bias = bias != nullptr, relu = !split && p.act == 1;
+    __nv_bfloat16* Cb = split ? nullptr : p.Cb;
+    const int ldcb = p.ldc;
+    float* csp = p.colsum_part;
+    const bool vec_ok = (N & 3) == 0 && (ldo & 3) == 0 && (ldcb & 3) == 0 && (reinterpret_cast<uintptr_t>(outp) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(Cb) & 7) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(csp) & 15) == 0;
+    // ReLU-gate mask for this thread's accumulator row (32 bf16 = 64 contiguous bytes, two full sectors), fetched
+    // one chunk ahead: the first before the accumulator is even complete, the next while a chunk is processed
+    const bool use_mask = !split && p.mask != nullptr;
+    uint4 mk_next[4];
+    auto load_mask = [&](int c, uint4* mk) {
+      if (use_mask && c < BN / 32) {
         const int grow = row0 + lane;
         const bool ok = grow < p.M && (n0 + c * 32 + 32 <= p.N) && ((p.ldmask & 7) == 0);
         const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (size_t)(ok ? grow : 0) * p.ldmask + n0 + c * 32);
@@ -202,10 +221,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int u = 0; u < 4; ++u) mk[u] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
         }
       }
+    };
+    load_mask(0, mk_next);
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    TT_GEMM_STAMP(2);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      TT_FINE(c, 0);
+      uint4 mk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mk[u] = mk_next[u];
+      load_mask(c + 1, mk_next);
       uint32_t r[32];
       if (nkb > 0) {
         tmem_ld_x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
+        TT_FINE(c, 1);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
@@ -215,9 +247,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-          const uint32_t w = mw[j >> 1];
-          if (!((w & 0x8000u) == 0 && (w & 0x7fffu) != 0)) r[j] = 0u;
-          if (!((w & 0x80000000u) == 0 && (w & 0x7fff0000u) != 0)) r[j + 1] = 0u;
+          const uint32_t w = mw[j >> 1];                      // bf16 > 0  <=>  its bits, as a signed integer, are > 0
+          r[j] = (int)(w << 16) > 0 ? r[j] : 0u;
+          r[j + 1] = (int)(w & 0xffff0000u) > 0 ? r[j + 1] : 0u;
         }
       }
 #pragma unroll
@@ -225,11 +257,67 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         *reinterpret_cast<float4*>(&T[lane][j]) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
       __syncwarp();
+      TT_FINE(c, 2);
+      const int nrows = min(32, p.M - row0);
+      if (vec_ok) {
+        // fast path: lane -> 4 consecutive columns of row (4 k + lane / 8); one instruction stores 4 rows x 128 B.
+        // Straight-line code: with a single epilogue warp per scheduler, instruction-level parallelism is all there is.
+        const int cq = (lane & 7) * 4, rq = lane >> 3;
+        const int col0 = n0 + c * 32 + cq;
+        const bool cok = col0 < N;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias && cok) bv = *reinterpret_cast<const float4*>(bias + col0);
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* o32 = outp ? outp + (size_t)(row0 + rq) * ldo + col0 : nullptr;
+        __nv_bfloat16* o16 = Cb ? Cb + (size_t)(row0 + rq) * ldcb + col0 : nullptr;
+        if (nrows == 32 && n0 + c * 32 + 32 <= N) {         // whole chunk in range (warp-uniform): no predicates at all
+          float4 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const float4*>(&T[4 * k + rq][cq]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            v[k].x += bv.x; v[k].y += bv.y; v[k].z += bv.z; v[k].w += bv.w;
+            if (relu) { v[k].x = fmaxf(v[k].x, 0.f); v[k].y = fmaxf(v[k].y, 0.f); v[k].z = fmaxf(v[k].z, 0.f); v[k].w = fmaxf(v[k].w, 0.f); }
+            cs.x += v[k].x; cs.y += v[k].y; cs.z += v[k].z; cs.w += v[k].w;
+          }
+          if (o32) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(o32 + (size_t)(4 * k) * ldo) = v[k];
+          }
+          if (o16) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<uint2*>(o16 + (size_t)(4 * k) * ldcb) = make_uint2(pack_bf16x2(v[k].x, v[k].y), pack_bf16x2(v[k].z, v[k].w));
+          }
+        } else
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4 v = *reinterpret_cast<const float4*>(&T[4 * k + rq][cq]);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          const bool ok = cok && (4 * k + rq < nrows);
+          if (ok) {
+            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+            if (o32) *reinterpret_cast<float4*>(o32 + (size_t)(4 * k) * ldo) = v;
+            if (o16) *reinterpret_cast<uint2*>(o16 + (size_t)(4 * k) * ldcb) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+          }
+        }
+        if (csp) {                                         // 32-row column sums: fold the 4 row groups (lanes +8, +16)
+#pragma unroll
+          for (int d = 8; d <= 16; d <<= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, d); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, d);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, d); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, d);
+          }
+          if (rq == 0 && cok && nrows > 0) *reinterpret_cast<float4*>(csp + (size_t)(row0 >> 5) * N + col0) = cs;
+        }
+        __syncwarp();
+        TT_FINE(c, 7);
+        continue;
+      }
       const int col = n0 + c * 32 + lane;
       const bool col_ok = col < p.N;
       const float bias_v = (!split && p.bias && col_ok) ? p.bias[col] : 0.f;
-      const int nrows = min(32, p.M - row0);
-      // 8 rows at a time: shared loads of a batch issued together, then the math, then 128-byte coalesced stores
+      // generic path (unaligned leading dimensions): 8 rows at a time, 128-byte coalesced scalar stores
       float csum = 0.f;
 #pragma unroll 1
       for (int rb = 0; rb < 32; rb += 8) {
@@ -255,16 +343,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       if (p.colsum_part && col_ok && nrows > 0) p.colsum_part[(size_t)(row0 >> 5) * p.N + col] = csum;
       __syncwarp();
+      TT_FINE(c, 7);
     }
   }
   tc_fence_before();
   __syncthreads();
+  TT_GEMM_STAMP(3);
   if (warp == 1) tmem_dealloc(tmem_acc, BN);
 }
 
 template <int BN>
 static constexpr size_t gemm_smem_bytes() {
-  return 1024 + kStages * (kATile + BN * BK * 2) + (2 * kStages + 1) * 8 + 16 + 128 + 4 * 32 * 36 * 4;
+  return 1024 + kStages * (kATile + BN * BK * 2) + (2 * kStages + 1) * 8 + 16;
 }
 
 struct TcGemm {
@@ -322,8 +412,34 @@ static int launch_gemm_pair(const TcGemm& g0, const TcGemm* g1, cudaStream_t s) 
   else { tmA1 = tmA0; tmB1 = tmB0; p1 = p0; p1.nblocks = 0; }
   constexpr size_t smem = gemm_smem_bytes<BN>();
   TT_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_gemm_kernel<BN><<<(unsigned)(p0.nblocks + p1.nblocks), kGemmThreads, smem, s>>>(tmA0, tmB0, p0, tmA1, tmB1, p1);
+  TT_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  static const bool dbg_on = getenv("TT_GEMM_DEBUG") != nullptr;
+  const int ncta = p0.nblocks + p1.nblocks;
+  long long* dbg_dev = nullptr;
+  const size_t dbg_n = (size_t)ncta * 4 + 128;
+  if (dbg_on) { cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p0.dbg = dbg_dev; }
+  TT_CUDA(launch_kernel(tc_gemm_kernel<BN>, dim3((unsigned)(p0.nblocks + p1.nblocks)), dim3(kGemmThreads), smem, s, true, tmA0, tmB0, p0,
+                        tmA1, tmB1, p1));
   TT_LAUNCH_CHECK("tc_gemm_kernel");
+  if (dbg_on) {
+    std::vector<long long> h(dbg_n);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dbg_dev);
+    long long g0 = 0;
+    for (int i = 0; i < ncta; ++i) if (h[4 * i] && (!g0 || h[4 * i] < g0)) g0 = h[4 * i];
+    printf("[tt tc_gemm<%d> per-CTA ns] problems {M %d N %d K %d splits %d : %d ctas} {M %d N %d K %d splits %d : %d ctas}\n", BN, p0.M, p0.N, p0.K,
+           p0.splits, p0.nblocks, p1.M, p1.N, p1.K, p1.splits, p1.nblocks);
+    for (int i = 0; i < ncta; i += (ncta > 64 ? 7 : 1))
+      printf("  cta %3d: start %6lld  ready %6lld  acc %6lld  end %6lld\n", i, h[4 * i] - g0, h[4 * i + 1] - g0, h[4 * i + 2] - g0, h[4 * i + 3] - g0);
+    long long mx = 0; for (int i = 0; i < ncta; ++i) if (h[4 * i + 3] - g0 > mx) mx = h[4 * i + 3] - g0;
+    printf("  last end %lld ns\n", mx);
+    for (int pr = 0; pr < 2; ++pr) {
+      const long long* f = h.data() + (size_t)ncta * 4 + pr * 64;
+      printf("  problem %d first CTA, epilogue cycles per 32-col chunk {begin, tmem, staged, lds0, lds1, lds2, lds3, end}:\n", pr);
+      for (int c = 0; c < BN / 32; ++c) { printf("    c%d:", c); for (int k = 0; k < 8; ++k) printf(" %6lld", f[c * 8 + k] ? f[c * 8 + k] - f[0] : -1); printf("\n"); }
+    }
+  }
   rc = finish_problem(g0, s); if (rc) return rc;
   if (g1) { rc = finish_problem(*g1, s); if (rc) return rc; }
   return TT_OK;
@@ -415,6 +531,8 @@ l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_
                          int64_t R, int H, float* __restrict__ dz, __nv_bfloat16* __restrict__ dzb,
                          float* __restrict__ colsum_part) {
   __shared__ float s_part[8][512];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float cs[16];
 #pragma unroll
@@ -600,7 +718,8 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   const bool fused_cs = H <= 512;
   const int nblk2 = (int)ceil_div(R, tc::kNormRowsPerBlock);
   if (fused_cs) {
-    tc::l2norm_bwd_colsum_kernel<<<(unsigned)nblk2, 256, 0, s>>>(dy, dy_parts, dy_part_stride, z, R, H, nullptr, dzb, cs2);   // fp32 dz is not needed: db2 comes from cs2
+    TT_CUDA(launch_kernel(tc::l2norm_bwd_colsum_kernel, dim3((unsigned)nblk2), dim3(256), 0, s, true, dy, dy_parts, dy_part_stride, z, R, H,
+                          (float*)nullptr, dzb, cs2));   // fp32 dz is not needed: db2 comes from cs2
     TT_LAUNCH_CHECK("l2norm_bwd_colsum_kernel");
   } else {
     tc::l2norm_bwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(dy, z, R, H, dz, dzb);

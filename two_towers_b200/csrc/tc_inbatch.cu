@@ -18,6 +18,8 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "tc_common.cuh"
 #include "tensor_core.cuh"
 
@@ -60,6 +62,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off,
                  float* __restrict__ part_ml, float* __restrict__ pos_logit) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // stays in the shared address space
   const int kq = H / 64;                                  // 64-wide K blocks
   const uint32_t d_bytes = (uint32_t)FWD_BN * H * 2;      // == Q tile bytes (both are 128 rows)
@@ -93,6 +96,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                             // prologue overlapped the previous kernel's tail
   const uint32_t tmem_s = *tmem_slot;                     // columns [0,256): two S buffers of 128
   const uint32_t tmem_q = tmem_s + 256;                   // columns [256, 256 + H/2): Q tile (TMEM A operand)
 
@@ -237,6 +241,7 @@ struct BwdParams {
   float inv_temp;
   const float* grad_out;       // nullable device scalar
   float coef;                  // loss_scale / temperature
+  int dbg_pass;                // pass whose CTA (0,0) is stamped (TT_CE_DEBUG=<pass>)
   long long* dbg;              // optional timeline buffer (TT_CE_DEBUG=1): [role 0..1][tile][8] clock64 stamps of CTA (0,0,0)
 };
 
@@ -275,6 +280,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   uint64_t* o_full = p_empty + 1;
   uint64_t* x_ready = o_full + 1;                         // X tile copied into TMEM (4 epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
+  float* col_lse = reinterpret_cast<float*>(tmem_slot + 6);   // [2][128] column lse of the current / next Y tile (COL)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t x0 = (int64_t)blockIdx.x * CE_BM;
@@ -282,8 +288,12 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   const int t_beg = blockIdx.y * tiles_per_split;
   const int t_end = min(ntiles, t_beg + tiles_per_split);
   const int nt = max(0, t_end - t_beg);
-  long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg : nullptr;
+  long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (int)blockIdx.z == p.dbg_pass) ? p.dbg : nullptr;
 #define TT_STAMP(role, tile, slot) do { if (dbg) dbg[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); } while (0)
+  // per-CTA wall-clock stamps (ns): kernel entry, X resident in TMEM, main loop done, outputs stored
+  long long* cta_dbg = p.dbg ? p.dbg + 2 * 64 * 8 + 4 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+#define TT_CTA_STAMP(slot) do { if (cta_dbg && threadIdx.x == 64) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); cta_dbg[slot] = t_; } } while (0)
+  TT_CTA_STAMP(0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(tmX); tma_prefetch_desc(tmY);
@@ -299,6 +309,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                             // prologue overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base;                      // columns [0, H)
   const uint32_t tmem_s = tmem_base + 256;                // columns [256, 384): S tile
@@ -403,15 +414,21 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(x_ready);
+    TT_CTA_STAMP(1);
     // Y tiles that can hold a positive of one of this CTA's rows (CTA-uniform band)
     const int64_t band_lo = COL ? x0 - label_offset : x0 + label_offset;
+    auto load_col_lse = [&](int i) {                        // this thread's column of Y tile i (COL mode)
+      const int64_t gc = (int64_t)(t_beg + i) * BWD_BN + threadIdx.x - 64;
+      return (i < nt && gc < By) ? __ldg(lse + gc) * kLog2e : CUDART_INF_F;
+    };
+    float next_cl = COL ? load_col_lse(0) : 0.f;
     for (int i = 0; i < nt; ++i) {
       const int64_t y0 = (int64_t)(t_beg + i) * BWD_BN;
-      float cl[4] = {0.f, 0.f, 0.f, 0.f};                   // column lse (COL mode): lane holds columns lane + 32 h
-      if (COL) {
-#pragma unroll
-        for (int h = 0; h < 4; ++h)
-          cl[h] = (y0 + 32 * h + lane < By) ? __ldg(lse + y0 + 32 * h + lane) * kLog2e : CUDART_INF_F;
+      const float4* cl4 = reinterpret_cast<const float4*>(col_lse + (i & 1) * BWD_BN);
+      if (COL) {                                            // column lse -> smem; read back as broadcasts
+        col_lse[(i & 1) * BWD_BN + threadIdx.x - 64] = next_cl;
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+        next_cl = load_col_lse(i + 1);                      // latency hides behind this tile's work
       }
       if (threadIdx.x == 64) TT_STAMP(1, i, 0);
       mbar_wait(s_full, i & 1);
@@ -429,9 +446,13 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
 #pragma unroll
       for (int h = 0; h < 4; ++h)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float lv = COL ? __shfl_sync(0xffffffffu, cl[h], j) : row_lse;
-          r[h][j] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j]), c, -lv)));
+        for (int j = 0; j < 32; j += 4) {
+          float4 lv = make_float4(row_lse, row_lse, row_lse, row_lse);
+          if (COL) lv = cl4[(32 * h + j) >> 2];
+          r[h][j + 0] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 0]), c, -lv.x)));
+          r[h][j + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 1]), c, -lv.y)));
+          r[h][j + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 2]), c, -lv.z)));
+          r[h][j + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 3]), c, -lv.w)));
         }
       if (!COL && y0 + BWD_BN > By) {
 #pragma unroll
@@ -473,6 +494,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       mbar_wait(o_full, 0);
       tc_fence_after();
     }
+    TT_CTA_STAMP(2);
     float* T = reinterpret_cast<float*>(p_tile + (warp - 2) * (32 * 36 * 4));       // [32][36], the P tile is free now
     const int64_t row0 = x0 + quarter * 32;
     const int nrows = (int)min((int64_t)32, Bx - row0);
@@ -486,19 +508,24 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
 #pragma unroll
         for (int j = 0; j < 32; ++j) q[j] = 0u;
       }
+      if (threadIdx.x == 64) TT_STAMP(1, 32 + cb, 0);
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(&T[lane * 36 + j]) = make_float4(__uint_as_float(q[j]) * scale, __uint_as_float(q[j + 1]) * scale,
                                                                     __uint_as_float(q[j + 2]) * scale, __uint_as_float(q[j + 3]) * scale);
       __syncwarp();
+      if (threadIdx.x == 64) TT_STAMP(1, 32 + cb, 1);
       float v[32];
 #pragma unroll
       for (int rr = 0; rr < 32; ++rr) v[rr] = T[rr * 36 + lane];
+      if (threadIdx.x == 64) TT_STAMP(1, 32 + cb, 2);
 #pragma unroll
       for (int rr = 0; rr < 32; ++rr)
         if (rr < nrows) orow[(int64_t)rr * H + cb * 32] = v[rr];
       __syncwarp();
+      if (threadIdx.x == 64) TT_STAMP(1, 32 + cb, 3);
     }
+    TT_CTA_STAMP(3);
   }
   tc_fence_before();
   __syncthreads();
@@ -509,6 +536,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
 tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmY0,
                  const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmY1, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   const int pass = blockIdx.z;
   if ((int64_t)blockIdx.x * CE_BM >= p.Bx[pass] || p.out[pass] == nullptr) return;   // CTA-uniform: nothing to do for this pass
@@ -518,7 +546,7 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
 
 static size_t fwd_smem(int H) { return 1024 + FWD_STAGES * (size_t)FWD_BN * H * 2 + 20 * 8 + 16; }
 static size_t bwd_smem(int H) {
-  return 1024 + BWD_STAGES * (size_t)BWD_BN * H * 2 + (size_t)CE_BM * BWD_BN * 2 + 24 * 8 + 16;
+  return 1024 + BWD_STAGES * (size_t)BWD_BN * H * 2 + (size_t)CE_BM * BWD_BN * 2 + 24 * 8 + 16 + 2 * BWD_BN * 4;
 }
 
 static int pick_split(int64_t xtiles, int64_t By, int bn = CE_BN) {
@@ -583,8 +611,8 @@ int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* 
   const size_t smem = tc::fwd_smem(H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(Bq, tc::CE_BM), (unsigned)ns);
-  tc::tc_ce_fwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmQ, tmD, Bq, Bd, H, inv_temp, label_offset, per, d_blk, d_blk_stride,
-                                                         d_blk_off, part_ml, pos);
+  TT_CUDA(launch_kernel(tc::tc_ce_fwd_kernel, grid, dim3(tc::CE_THREADS), smem, s, true, tmQ, tmD, Bq, Bd, H, inv_temp, label_offset, per,
+                        d_blk, d_blk_stride, d_blk_off, part_ml, pos));
   TT_LAUNCH_CHECK("tc_ce_fwd_kernel");
   return inbatch_finalize(part_ml, pos, ns, Bq, inv_temp, loss_scale, lse, loss, pos_mean, nullptr, s);
 }
@@ -641,18 +669,21 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
   TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
   long long* dbg_dev = nullptr;
-  if (dbg_on) { cudaMalloc(&dbg_dev, 2 * 64 * 8 * sizeof(long long)); cudaMemset(dbg_dev, 0, 2 * 64 * 8 * sizeof(long long)); p.dbg = dbg_dev; }
   const int64_t x0 = pq.out ? ceil_div(pq.Bx, tc::CE_BM) : 0, x1 = pd.out ? ceil_div(pd.Bx, tc::CE_BM) : 0;
   const int nz = pd.out ? 2 : 1;                         // pass 1 absent -> only z = 0 is launched
   dim3 grid((unsigned)(x0 > x1 ? x0 : x1), (unsigned)nsplit, (unsigned)nz);
-  tc::tc_ce_bwd_kernel<<<grid, tc::CE_THREADS, smem, s>>>(tmX0, tmY0, tmX1, tmY1, p);
+  const size_t ncta = (size_t)grid.x * grid.y * grid.z, dbg_n = 2 * 64 * 8 + 4 * ncta;
+  if (dbg_on) { p.dbg_pass = atoi(getenv("TT_CE_DEBUG")) == 1 ? 1 : 0; cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p.dbg = dbg_dev; }
+  TT_CUDA(launch_kernel(tc::tc_ce_bwd_kernel, grid, dim3(tc::CE_THREADS), smem, s, true, tmX0, tmY0, tmX1, tmY1, p));
   TT_LAUNCH_CHECK("tc_ce_bwd_kernel");
   if (dbg_on) {                                              // developer aid: per-tile timeline of CTA (0,0,0)
-    static long long host[2 * 64 * 8];
+    std::vector<long long> hostv(dbg_n);
+    long long* host = hostv.data();
     cudaStreamSynchronize(s);
-    cudaMemcpy(host, dbg_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    cudaMemcpy(host, dbg_dev, dbg_n * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(dbg_dev);
-    const long long t0 = host[0];
+    long long t0 = host[0];
+    for (int k = 0; k < 8; ++k) if (host[64 * 8 + k] && host[64 * 8 + k] < t0) t0 = host[64 * 8 + k];
     const int ntl = p.tiles_per_split[0] < 64 ? p.tiles_per_split[0] : 64;
     printf("[tt ce_bwd timeline, cycles since first stamp] tile: MMA{s_issue_begin,y_full,s_empty,s_issued,o_wait,p_full,o_issued} EPI{begin,s_full,loaded,computed,p_empty,p_written}\n");
     for (int t = 0; t < ntl; ++t) {
@@ -662,6 +693,18 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
       for (int k = 0; k < 6; ++k) printf(" %6lld", host[(1 * 64 + t) * 8 + k] ? host[(1 * 64 + t) * 8 + k] - t0 : -1);
       printf("\n");
     }
+    printf("[tt ce_bwd O store, cycles] cb: tmem_loaded staged read stored\n");
+    for (int cb = 0; cb < H / 32; ++cb) {
+      printf("  %2d:", cb);
+      for (int k = 0; k < 4; ++k) printf(" %6lld", host[(1 * 64 + 32 + cb) * 8 + k] - t0);
+      printf("\n");
+    }
+    const long long* c = host + 2 * 64 * 8;
+    long long g0 = 0;
+    for (size_t i = 0; i < ncta; ++i) if (c[4 * i] && (!g0 || c[4 * i] < g0)) g0 = c[4 * i];
+    printf("[tt ce_bwd per-CTA, ns since first CTA start] cta: start x_ready loop_done stored\n");
+    for (size_t i = 0; i < ncta; ++i)
+      printf("  cta %3zu: %6lld %6lld %6lld %6lld\n", i, c[4 * i] - g0, c[4 * i + 1] - g0, c[4 * i + 2] - g0, c[4 * i + 3] - g0);
   }
   return TT_OK;
 }

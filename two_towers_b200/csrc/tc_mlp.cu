@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1)
 tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const MlpFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   const int E = p.E, H = p.H;
   const int kE = E / 64, kH = H / 64;
@@ -70,6 +71,7 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_wait();                                                      // barrier init / TMEM alloc overlapped the previous kernel
   if (warp >= 2) {                                                 // biases -> smem (read as broadcasts later)
     for (int i = threadIdx.x - 64; i < H; i += 128) { bias_s[i] = p.b1[i]; bias_s[H + i] = p.b2[i]; }
   }
@@ -238,7 +240,7 @@ int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const fl
   p.R = R; p.E = E; p.H = H; p.b1 = b1; p.b2 = b2; p.h1b = h1b; p.z = z; p.y = y; p.yb = yb;
   const size_t smem = tc::mlp_fused_smem(E, H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::tc_mlp_fwd_kernel<<<(unsigned)ceil_div(R, tc::MLP_BM), tc::MLP_THREADS, smem, s>>>(tmX, tmW1, tmW2, p);
+  TT_CUDA(launch_kernel(tc::tc_mlp_fwd_kernel, dim3((unsigned)ceil_div(R, tc::MLP_BM)), dim3(tc::MLP_THREADS), smem, s, true, tmX, tmW1, tmW2, p));
   TT_LAUNCH_CHECK("tc_mlp_fwd_kernel");
   return TT_OK;
 }

@@ -167,7 +167,11 @@ size_t tt_inbatch_ce_fwd_ex_workspace(int64_t Bq, int64_t Bd);
 int tt_inbatch_ce_fwd_ex(const void* q_bf16, int64_t Bq, const void* d_bf16, int64_t Bd, int64_t d_buf_rows,
                          int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off, int H, float inv_temperature,
                          int64_t label_offset, float loss_scale, float* loss, float* lse, float* pos_mean,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         void* workspace, size_t workspace_bytes, void* sync_scratch, void* stream);
+/* sync_scratch (nullable): tt_inbatch_ce_sync_bytes(Bq) bytes the caller keeps for the life of the call site, zero-filled
+ * once before first use; every call re-arms it for the next one (do not share it between concurrent calls).  With it the loss / lse finalisation runs inside the
+ * same launch (the last CTA of each row tile merges its splits, fixed order); without it a second launch does. */
+size_t tt_inbatch_ce_sync_bytes(int64_t Bq);
 int tt_inbatch_ce_bwd_nparts_ex(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_rows, int64_t d_y_rows, int H);
 int tt_inbatch_ce_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temperature,
                                float loss_scale, const float* grad_out, int nparts, void* stream);

@@ -113,6 +113,36 @@ def test_inbatch_ce_bf16_vs_oracle(Bq, Bd, H, off, temp):
     assert torch.equal(dq, dq2) and torch.equal(dd, dd2)
 
 
+@pytest.mark.parametrize("Bq,Bd,H,off", [(4096, 4096, 256, 0), (1024, 4096, 256, 2048), (300, 900, 128, 17), (128, 128, 64, 0)])
+def test_inbatch_fwd_in_kernel_finalisation(Bq, Bd, H, off):
+    """tt_inbatch_ce_fwd_ex with the self-zeroing sync scratch (lse / loss finished by the last CTA of each row tile)
+    must agree with the two-launch form, be repeatable bit for bit, and re-arm its ticket counters."""
+    import ctypes as C
+    import two_towers_b200 as tt
+    from two_towers_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(Bq + Bd)
+    q = tt.ops.cast_bf16(torch.nn.functional.normalize(torch.randn(Bq, H, device=DEV), dim=-1))
+    d = tt.ops.cast_bf16(torch.nn.functional.normalize(torch.randn(Bd, H, device=DEV), dim=-1))
+    ws = torch.empty(int(lib.tt_inbatch_ce_fwd_ex_workspace(Bq, Bd)), dtype=torch.uint8, device=DEV)
+    sync = torch.zeros(int(lib.tt_inbatch_ce_sync_bytes(Bq)), dtype=torch.uint8, device=DEV)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for use_sync in (False, True, True):
+        loss = torch.zeros((), device=DEV); lse = torch.zeros(Bq, device=DEV); pm = torch.zeros((), device=DEV)
+        _lib.check(lib.tt_inbatch_ce_fwd_ex(q.data_ptr(), Bq, d.data_ptr(), Bd, Bd, Bd, 0, 0, H, 10.0, off, 1.0 / Bq,
+                                            loss.data_ptr(), lse.data_ptr(), pm.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            sync.data_ptr() if use_sync else None, s), "fwd_ex")
+        torch.cuda.synchronize()
+        outs.append((loss.item(), lse.clone(), pm.item()))
+        ncount = 4 * ((Bq + 127) // 128 + 1)                  # the ticket counters (head of the scratch) re-arm themselves
+        assert int(sync[:ncount].to(torch.int32).abs().sum().item()) == 0
+    (l0, lse0, p0), (l1, lse1, p1), (l2, lse2, p2) = outs
+    assert abs(l0 - l1) <= 2e-6 * max(1.0, abs(l0)) and abs(p0 - p1) <= 2e-6 * max(1.0, abs(p0))
+    assert (lse0 - lse1).abs().max().item() <= 4e-6 * max(1.0, lse0.abs().max().item())
+    assert l1 == l2 and p1 == p2 and torch.equal(lse1, lse2)
+
+
 def test_inbatch_bf16_full_size_known_answers():
     import two_towers_b200 as tt
     B, H = 4096, 256

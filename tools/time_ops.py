@@ -20,7 +20,7 @@ FLUSH_BUF2 = None
 FLUSH_SINK = []
 
 
-def timed(fn, flush, reps=12):
+def timed(fn, flush, reps=43):
     fn(); torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
@@ -36,7 +36,7 @@ def timed(fn, flush, reps=12):
         torch.cuda.synchronize()
         if i >= 3:
             ts.append(e0.elapsed_time(e1) * 1e3)
-    return float(np.median(ts))
+    return float(np.mean(ts))             # event resolution is 2.048 us: the mean over 40 replays resolves finer steps
 
 
 def main():
@@ -67,7 +67,8 @@ def main():
     ops = {
         "embed_pool_fwd": lambda: check(lib.tt_embed_pool_fwd(_p(tr.ids), 8, _p(tr.table), R, tr.L, tr.V, tr.E, _p(tr.pooled), _p(tr.inv_len), _p(tr.pooled_bf16), s()), "x"),
         "tower_fwd": lambda: tr._tower_fwd(0),
-        "ce_fwd": lambda: check(lib.tt_inbatch_ce_fwd(_p(qf), _p(df), _p(qb), _p(db), B, B, H, 10.0, 0, 1.0 / B, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), tr.prec, _p(tr.ws), tr.ws.numel(), s()), "x"),
+        "ce_fwd": (lambda: check(lib.tt_inbatch_ce_fwd_ex(_p(qb), B, _p(db), B, B, B, 0, 0, H, 10.0, 0, 1.0 / B, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), _p(tr.ce_ws), tr.ce_ws.numel(), _p(tr.ce_sync), s()), "x"))
+                  if getattr(tr, "local_fast", False) else lambda: check(lib.tt_inbatch_ce_fwd(_p(qf), _p(df), _p(qb), _p(db), B, B, H, 10.0, 0, 1.0 / B, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), tr.prec, _p(tr.ws), tr.ws.numel(), s()), "x"),
         "ce_bwd": (lambda: check(lib.tt_inbatch_ce_bwd_parts(_p(qb), _p(db), _p(tr.lse), B, B, H, 10.0, 0, 1.0 / B, None, _p(tr.dy[:B]), tr.dy_part_stride, _p(tr.dy[B:2 * B]), tr.dy_part_stride, s()), "x"))
                   if tr.dy_parts > 1 else
                   (lambda: check(lib.tt_inbatch_ce_bwd(_p(qf), _p(df), _p(qb), _p(db), _p(tr.lse), B, B, H, 10.0, 0, 1.0 / B, None, _p(tr.dy[:B]), _p(tr.dy[B:2 * B]), tr.prec, _p(tr.ws), tr.ws.numel(), s()), "x")),
@@ -94,14 +95,14 @@ def main():
         def prefix(k=k):
             for n in names[:k]:
                 ops[n]()
-        t = timed(prefix, flush, reps=16)
+        t = timed(prefix, flush)
         print(f"prefix..{names[k - 1]:16s} {t:9.1f} us   (+{t - prev:6.1f})")
         prev = t
     # launch-boundary cost: 32 back-to-back AdamW launches over a tiny slice
     def chain():
         for _ in range(32):
             check(lib.tt_adamw_step(_p(tr.flat), _p(tr.flat_grad), _p(tr.exp_avg), _p(tr.exp_avg_sq), 1024, 1e-3, 0.9, 0.999, 1e-8, 0.01, _p(tr.step_count), _p(tr.flat_bf16), s()), "x")
-    t = timed(chain, flush, reps=16)
+    t = timed(chain, flush)
     print(f"32 tiny launches {t:9.1f} us   ({t / 32:.2f} us per boundary, TT_PDL={os.environ.get('TT_PDL', '1')})")
 
 

@@ -60,7 +60,8 @@ class CePass(C.Structure):
 
 SIGNATURES.update({
     "tt_inbatch_ce_fwd_ex_workspace": (_sz, [_i64, _i64]),
-    "tt_inbatch_ce_fwd_ex": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i, _f, _i64, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tt_inbatch_ce_fwd_ex": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i, _f, _i64, _f, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "tt_inbatch_ce_sync_bytes": (_sz, [_i64]),
     "tt_inbatch_ce_bwd_nparts_ex": (_i, [_i64, _i64, _i64, _i64, _i]),
     "tt_inbatch_ce_bwd_parts_ex": (_i, [C.POINTER(CePass), C.POINTER(CePass), _i, _f, _f, _vp, _i, _vp]),
 })

@@ -464,7 +464,7 @@ size_t tt_inbatch_ce_fwd_ex_workspace(int64_t Bq, int64_t Bd) {
 int tt_inbatch_ce_fwd_ex(const void* q_bf16, int64_t Bq, const void* d_bf16, int64_t Bd, int64_t d_buf_rows, int64_t d_blk,
                          int64_t d_blk_stride, int64_t d_blk_off, int H, float inv_temperature, int64_t label_offset,
                          float loss_scale, float* loss, float* lse, float* pos_mean, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+                         size_t workspace_bytes, void* sync_scratch, void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(q_bf16 && d_bf16 && loss && lse && Bq > 0 && Bd > 0 && H > 0 && d_buf_rows >= 1 && d_blk >= 1,
                "inbatch_ce_fwd_ex: bad arguments");
@@ -477,8 +477,10 @@ int tt_inbatch_ce_fwd_ex(const void* q_bf16, int64_t Bq, const void* d_bf16, int
   float* part_ml = w.take<float>((need - 256 - tt::align_up((size_t)Bq * 4)) / 4);
   return tt::tc_inbatch_fwd_ex((const __nv_bfloat16*)q_bf16, Bq, (const __nv_bfloat16*)d_bf16, Bd, d_buf_rows, d_blk,
                                d_blk_stride, d_blk_off, H, inv_temperature, label_offset, loss_scale, loss, lse, pos_mean,
-                               part_ml, pos, static_cast<cudaStream_t>(stream));
+                               part_ml, pos, sync_scratch, static_cast<cudaStream_t>(stream));
 }
+
+size_t tt_inbatch_ce_sync_bytes(int64_t Bq) { return Bq > 0 ? tt::tc_inbatch_fwd_sync_bytes(Bq) : 16; }
 
 int tt_inbatch_ce_bwd_nparts_ex(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_rows, int64_t d_y_rows, int H) {
   if (q_x_rows <= 0 || q_y_rows <= 0 || d_x_rows <= 0 || d_y_rows <= 0 || H <= 0) return 1;

@@ -3,10 +3,10 @@
 //
 //   out[i] = epilogue( sum_p part[p * stride + i] ),  i < n
 //
-// Fixed summation order (bitwise reproducible): a block owns 32 consecutive outputs; its 8 warps each
-// sum the slices p = w, w+8, w+16, ... (independent, coalesced 128-byte loads, 4 in flight per thread --
-// a naive one-thread-per-output loop serialises on every load), then warp 0 adds the 8 warp totals in
-// warp order.
+// Fixed summation order (bitwise reproducible): a block owns 32 (or, for large aligned jobs, 128) consecutive
+// outputs; its 8 warps each sum the slices p = w, w+8, w+16, ... (independent, coalesced loads, 4 in flight per
+// thread -- a naive one-thread-per-output loop serialises on every load), then the warp totals are added in
+// warp order.  All jobs of a call share one flat grid (no empty blocks).
 #pragma once
 #include "common.cuh"
 
@@ -25,10 +25,12 @@ struct ReduceJob {
   const float* mask;     // [n / ncols, ldmask] : out *= (mask > 0)
   int ldmask;
   int ldo;               // output row pitch when ncols > 0 (else contiguous)
+  int vec;               // set by reduce_parts: 128-output blocks with 16-byte loads
 };
 struct ReduceJobs {
   ReduceJob job[4];
   int njobs;
+  int unit_base[5];      // set by reduce_parts: first block of each job in the flat grid
 };
 
 int reduce_parts(const ReduceJobs& jobs, cudaStream_t s);

@@ -474,7 +474,7 @@ static int pick_splits(int M, int N, int K) {
   const int total_kb = (K + BK - 1) / BK;
   if (tiles >= kNumSMs / 2 || total_kb <= 4) return 1;
   int64_t want = ceil_div(kNumSMs, tiles);
-  int64_t maxs = total_kb / 4;              // >= 4 k-blocks (256 of K) per split
+  int64_t maxs = total_kb / 8;              // >= 8 k-blocks (512 of K) per split: halves the partial-slice traffic
   if (want > maxs) want = maxs;
   if (want > 64) want = 64;
   return (int)(want < 1 ? 1 : want);

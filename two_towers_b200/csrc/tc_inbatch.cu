@@ -56,11 +56,21 @@ __device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2, inputs a
 constexpr int FWD_BN = 128;
 constexpr int FWD_STAGES = 3;
 
+// In-kernel finalisation (optional): the last CTA of a row tile to finish merges that tile's per-split (max, sum)
+// pairs into lse and a per-tile loss partial; the last row tile to finish adds the tile partials in tile order.
+// Fixed orders everywhere, so the result does not depend on which CTA happens to be last.
+struct FwdFinalize {
+  unsigned* counters;          // [row tiles + 1], zero on entry, zero again on exit (null: finalise in a second launch)
+  float* tile_sums;            // [row tiles][2]: sum(lse - pos), sum(pos)
+  float* lse; float* loss; float* pos_mean;
+  float loss_scale;
+};
+
 __global__ void __launch_bounds__(CE_THREADS, 1)
 tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmD, int64_t Bq,
                  int64_t Bd, int H, float inv_temp, int64_t label_offset, int tiles_per_split,
                  int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off,
-                 float* __restrict__ part_ml, float* __restrict__ pos_logit) {
+                 float* __restrict__ part_ml, float* __restrict__ pos_logit, const FwdFinalize fin) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // stays in the shared address space
@@ -212,14 +222,66 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       l = l * fast_exp2((m - mnew) * c) + ((s0 + s1) + (s2 + s3));
       m = mnew;
     }
-    if (row < Bq && nt > 0) {
-      part_ml[((int64_t)blockIdx.y * Bq + row) * 2 + 0] = m * inv_temp;
+    if (row < Bq) {                                          // a split without tiles contributes (-inf, 0)
+      part_ml[((int64_t)blockIdx.y * Bq + row) * 2 + 0] = nt > 0 ? m * inv_temp : -CUDART_INF_F;
       part_ml[((int64_t)blockIdx.y * Bq + row) * 2 + 1] = l;
     }
+    if (fin.counters) __threadfence();                       // partials visible before this CTA takes its ticket
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_s, 512);
+  if (fin.counters == nullptr) return;
+
+  // ---- finalisation by whichever CTA of this row tile finishes last ----
+  __shared__ unsigned s_ticket;
+  __shared__ float s_red[2][4];
+  if (threadIdx.x == 0) { s_ticket = atomicAdd(&fin.counters[blockIdx.x], 1u); __threadfence(); }
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  if (warp >= 2) {
+    const int lrow = (warp & 3) * 32 + lane;
+    const int64_t row = x0 + lrow;
+    float dl = 0.f, dp = 0.f;
+    if (row < Bq) {
+      float M = -CUDART_INF_F, L = 0.f;
+      for (int sp = 0; sp < (int)gridDim.y; ++sp) {            // split order
+        const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_ml) + (int64_t)sp * Bq + row);
+        const float Mn = fmaxf(M, ml.x);
+        L = L * expf(M - Mn) + ml.y * expf(ml.x - Mn);
+        M = Mn;
+      }
+      const float v = M + logf(L);
+      const float pl = __ldcg(pos_logit + row);
+      fin.lse[row] = v;
+      dl = v - pl; dp = pl;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { dl += __shfl_xor_sync(0xffffffffu, dl, o); dp += __shfl_xor_sync(0xffffffffu, dp, o); }
+    if (lane == 0) { s_red[0][warp & 3] = dl; s_red[1][warp & 3] = dp; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fin.tile_sums[2 * blockIdx.x + 0] = (s_red[0][0] + s_red[0][1]) + (s_red[0][2] + s_red[0][3]);
+    fin.tile_sums[2 * blockIdx.x + 1] = (s_red[1][0] + s_red[1][1]) + (s_red[1][2] + s_red[1][3]);
+    fin.counters[blockIdx.x] = 0u;                           // leave the scratch zeroed for the next launch
+    __threadfence();
+    s_ticket = atomicAdd(&fin.counters[gridDim.x], 1u);
+    __threadfence();
+  }
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  if (warp == 0) {                                          // last row tile: tile partials in tile order
+    float tl = 0.f, tp = 0.f;
+    for (int t = lane; t < (int)gridDim.x; t += 32) { tl += __ldcg(fin.tile_sums + 2 * t); tp += __ldcg(fin.tile_sums + 2 * t + 1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { tl += __shfl_xor_sync(0xffffffffu, tl, o); tp += __shfl_xor_sync(0xffffffffu, tp, o); }
+    if (lane == 0) {
+      *fin.loss = tl * fin.loss_scale;
+      if (fin.pos_mean) *fin.pos_mean = tp / (inv_temp * (float)Bq);
+      fin.counters[gridDim.x] = 0u;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -601,7 +663,8 @@ int cast3_public(const float* a, __nv_bfloat16* ab, int64_t na, const float* b, 
 // row (g / d_blk) * d_blk_stride + g % d_blk + d_blk_off of a buffer with d_buf_rows rows.
 int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* da, int64_t Bd, int64_t d_buf_rows,
                       int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off, int H, float inv_temp, int64_t label_offset,
-                      float loss_scale, float* loss, float* lse, float* pos_mean, float* part_ml, float* pos, cudaStream_t s) {
+                      float loss_scale, float* loss, float* lse, float* pos_mean, float* part_ml, float* pos, void* sync_scratch,
+                      cudaStream_t s) {
   CUtensorMap tmQ, tmD;
   int rc = tc::make_tmap_bf16(&tmQ, qa, (uint64_t)Bq, (uint64_t)H, tc::CE_BM); if (rc) return rc;
   rc = tc::make_tmap_bf16(&tmD, da, (uint64_t)d_buf_rows, (uint64_t)H, tc::FWD_BN); if (rc) return rc;
@@ -611,10 +674,22 @@ int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* 
   const size_t smem = tc::fwd_smem(H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(Bq, tc::CE_BM), (unsigned)ns);
+  tc::FwdFinalize fin{};
+  if (sync_scratch) {
+    fin.counters = static_cast<unsigned*>(sync_scratch);
+    fin.tile_sums = reinterpret_cast<float*>(static_cast<char*>(sync_scratch) + align_up((size_t)(grid.x + 1) * 4, 16));
+    fin.lse = lse; fin.loss = loss; fin.pos_mean = pos_mean; fin.loss_scale = loss_scale;
+  }
   TT_CUDA(launch_kernel(tc::tc_ce_fwd_kernel, grid, dim3(tc::CE_THREADS), smem, s, true, tmQ, tmD, Bq, Bd, H, inv_temp, label_offset, per,
-                        d_blk, d_blk_stride, d_blk_off, part_ml, pos));
+                        d_blk, d_blk_stride, d_blk_off, part_ml, pos, fin));
   TT_LAUNCH_CHECK("tc_ce_fwd_kernel");
+  if (sync_scratch) return TT_OK;
   return inbatch_finalize(part_ml, pos, ns, Bq, inv_temp, loss_scale, lse, loss, pos_mean, nullptr, s);
+}
+
+size_t tc_inbatch_fwd_sync_bytes(int64_t Bq) {
+  const size_t tiles = (size_t)ceil_div(Bq, tc::CE_BM);
+  return align_up((tiles + 1) * 4, 16) + tiles * 2 * 4;
 }
 
 int tc_inbatch_fwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, const __nv_bfloat16* d_bf16, int64_t Bq,
@@ -634,7 +709,7 @@ int tc_inbatch_fwd(const float* q, const float* d, const __nv_bfloat16* q_bf16, 
     if (rc) return rc;
   }
   return tc_inbatch_fwd_ex(q_bf16 ? q_bf16 : qb, Bq, d_bf16 ? d_bf16 : db, Bd, Bd, Bd > 0 ? Bd : 1, 0, 0, H, inv_temp,
-                           label_offset, loss_scale, loss, lse, pos_mean, part_ml, pos, s);
+                           label_offset, loss_scale, loss, lse, pos_mean, part_ml, pos, nullptr, s);
 }
 
 size_t tc_inbatch_fwd_ex_workspace(int64_t Bq, int64_t Bd) {

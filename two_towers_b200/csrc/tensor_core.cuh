@@ -45,7 +45,9 @@ int tc_inbatch_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pa
 size_t tc_inbatch_fwd_ex_workspace(int64_t Bq, int64_t Bd);
 int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* da, int64_t Bd, int64_t d_buf_rows,
                       int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off, int H, float inv_temp, int64_t label_offset,
-                      float loss_scale, float* loss, float* lse, float* pos_mean, float* part_ml, float* pos, cudaStream_t s);
+                      float loss_scale, float* loss, float* lse, float* pos_mean, float* part_ml, float* pos, void* sync_scratch,
+                      cudaStream_t s);
+size_t tc_inbatch_fwd_sync_bytes(int64_t Bq);
 
 // shared by both precisions (inbatch_ce.cu): lse/loss finalisation from per-split (max,sum)
 int inbatch_finalize(const float* part_ml, const float* pos_logit, int nsplit, int64_t Bq, float inv_temp,

@@ -102,8 +102,13 @@ class FusedTrainer:
         fast = (self.prec == _lib.TT_PREC_BF16 and loss == "in_batch" and self.H % 64 == 0 and self.H <= 256 and
                 all(isinstance(t, MeanPoolingTower) for t, _, _ in self.groups))
         self.global_fast = bool(fast and self.global_negatives and B % 64 == 0)
-        if fast and not self.global_negatives:
+        self.local_fast = bool(fast and not self.global_negatives)
+        if fast:
+            # persistent, self-zeroing scratch: lets the loss forward finish lse / loss inside its own launch
+            self.ce_sync = torch.zeros(int(self.lib.tt_inbatch_ce_sync_bytes(B)), dtype=torch.uint8, device=self.dev)
+        if self.local_fast:
             self.dy_parts = int(self.lib.tt_inbatch_ce_bwd_nparts(B, B, self.H, self.prec))
+            self.ce_ws = torch.empty(int(self.lib.tt_inbatch_ce_fwd_ex_workspace(B, B)), dtype=torch.uint8, device=self.dev)
         elif self.global_fast:
             Bg = B * self.world
             self.dy_parts = int(self.lib.tt_inbatch_ce_bwd_nparts_ex(B, Bg, B, Bg, self.H))
@@ -232,9 +237,14 @@ class FusedTrainer:
                 scale = 1.0 / (B * self.world)
                 qb = self.y_bf16[:B] if self.y_bf16 is not None else None
                 db = self.y_bf16[B:2 * B] if self.y_bf16 is not None else None
-                check(lib.tt_inbatch_ce_fwd(_p(q), _p(d), _p(qb), _p(db), B, B, H, inv_t, 0, scale, _p(self.loss),
-                                            _p(self.lse), _p(self.pos_mean), self.prec, _p(self.ws), self.ws.numel(), s),
-                      "tt_inbatch_ce_fwd")
+                if self.local_fast:
+                    check(lib.tt_inbatch_ce_fwd_ex(_p(qb), B, _p(db), B, B, B, 0, 0, H, inv_t, 0, scale, _p(self.loss),
+                                                   _p(self.lse), _p(self.pos_mean), _p(self.ce_ws), self.ce_ws.numel(),
+                                                   _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
+                else:
+                    check(lib.tt_inbatch_ce_fwd(_p(q), _p(d), _p(qb), _p(db), B, B, H, inv_t, 0, scale, _p(self.loss),
+                                                _p(self.lse), _p(self.pos_mean), self.prec, _p(self.ws), self.ws.numel(), s),
+                          "tt_inbatch_ce_fwd")
                 if self.dy_parts > 1:
                     check(lib.tt_inbatch_ce_bwd_parts(_p(qb), _p(db), _p(self.lse), B, B, H, inv_t, 0, scale, None,
                                                       _p(dq), self.dy_part_stride, _p(dd), self.dy_part_stride, s),
@@ -271,7 +281,7 @@ class FusedTrainer:
         scale = 1.0 / Bg
         check(lib.tt_inbatch_ce_fwd_ex(_p(self.y_bf16[:B]), B, _p(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, B, H, inv_t,
                                        self.rank * B, scale, _p(self.loss), _p(self.lse), _p(self.pos_mean),
-                                       _p(self.ce_ws), self.ce_ws.numel(), s), "tt_inbatch_ce_fwd_ex")
+                                       _p(self.ce_ws), self.ce_ws.numel(), _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
         dist.all_gather_into_tensor(self.lse_g, self.lse, group=self.group)
         vp = lambda t: None if t is None else t.data_ptr()
         qp = _lib.CePass(vp(self.y_bf16[:B]), B, vp(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, B, vp(self.lse), self.rank * B,

@@ -52,6 +52,9 @@ int64_t tt_launch_count(void);
  *                       mask=(ids>0); pooled = sum_l W[ids]*mask / (sum mask + 1e-9).
  *                       Never materialises [rows,L,E].  inv_len[r] = 1/(count_r + 1e-9).
  *                       pooled_bf16 (nullable) receives a bf16 copy for the tensor-core path.
+ *                       pool_bf16 (nullable, V <= 1024): the pooling matrix P [rows,V] in bf16,
+ *                       P[r,v] = count_r(v) / (count_r + 1e-9), so that pooled = P * table; consumed by
+ *                       tt_mlp_bwd(embed = ...) which then needs neither dx nor tt_embed_pool_bwd.
  * tt_embed_pool_bwd   : autograd of the above -> ATen embedding_dense_backward
  *                       (loss.backward(), twotower/train.py:138).  Deterministic: small tables
  *                       use a pooling-matrix GEMM with fixed split order, large tables a
@@ -62,7 +65,7 @@ int tt_embed_gather(const void* ids, int id_bytes, const float* table, int64_t n
                     int64_t V, int E, float* out, void* stream);
 int tt_embed_pool_fwd(const void* ids, int id_bytes, const float* table, int64_t rows, int L,
                       int64_t V, int E, float* pooled, float* inv_len, void* pooled_bf16,
-                      void* stream);
+                      void* pool_bf16, void* stream);
 size_t tt_embed_pool_bwd_workspace(int64_t rows, int L, int64_t V, int E);
 int tt_embed_pool_bwd(const void* ids, int id_bytes, const float* inv_len, const float* d_pooled,
                       int64_t rows, int L, int64_t V, int E, float* d_table,
@@ -82,7 +85,20 @@ int tt_embed_pool_bwd(const void* ids, int id_bytes, const float* inv_len, const
  *   h1_bf16 [R,H] written by fwd and read by bwd.
  * dy_parts > 1 (TT_PREC_BF16): dy is given as dy_parts slices, dy_part_stride elements apart, that are summed
  *   in slice order inside the first backward kernel (see tt_inbatch_ce_bwd_parts); pass 1, 0 otherwise.
+ * embed (TT_PREC_BF16, nullable): x is the mean-pooled lookup embedding x = P * table (P from tt_embed_pool_fwd).
+ *   The backward then forms M = P^T da1 [V,H] once on the tensor cores and finishes with two tiny products,
+ *   dw1 = M^T table and d_table = M w1 (+= when accumulate != 0), instead of computing dx [R,E], dw1 = da1^T x and
+ *   the separate embedding backward; dx must be null.  workspace: tt_mlp_embed_workspace(V, H, R) bytes.
  */
+typedef struct {
+  const void* pool_bf16;      /* P [R,V] bf16 */
+  int64_t V;
+  const float* table;         /* [V,E] */
+  float* d_table;             /* [V,E] */
+  int accumulate;             /* 0: d_table is overwritten, else added to (second tower sharing the table) */
+  void* workspace; size_t workspace_bytes;
+} tt_mlp_embed_t;
+size_t tt_mlp_embed_workspace(int64_t V, int H, int64_t R);
 size_t tt_mlp_workspace(int64_t R, int E, int H, int precision);
 int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                int64_t R, int E, int H, float* h1, float* z, float* y, void* y_bf16,
@@ -92,7 +108,7 @@ int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
                const float* h1, const float* z, int64_t R, int E, int H,
                float* dx, float* dw1, float* db1, float* dw2, float* db2,
                const void* x_bf16, const void* w1_bf16, const void* w2_bf16, const void* h1_bf16,
-               int dy_parts, int64_t dy_part_stride,
+               int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed,
                int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K3': avg_pool tower projection  Linear(E,H) -> Dropout(p) -> LayerNorm(H) -> normalise -

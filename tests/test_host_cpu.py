@@ -40,7 +40,7 @@ def test_no_gpu_fails_loudly_no_fallback():
     lib = _lib.load()
     buf = (ctypes.c_float * 16)()
     rc = lib.tt_embed_pool_fwd(ctypes.addressof(buf), 8, ctypes.addressof(buf), 1, 1, 2, 4,
-                               ctypes.addressof(buf), ctypes.addressof(buf), None, None)
+                               ctypes.addressof(buf), ctypes.addressof(buf), None, None, None)
     assert rc == -3 and "no CPU fallback" in _lib.last_error()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.embed_pool_fwd(torch.zeros(2, 3, dtype=torch.int64), torch.zeros(4, 4))

@@ -65,7 +65,7 @@ def main():
     db = tr.y_bf16[B:2 * B] if tr.y_bf16 is not None else None
     qf, df = tr.y[:B], tr.y[B:2 * B]
     ops = {
-        "embed_pool_fwd": lambda: check(lib.tt_embed_pool_fwd(_p(tr.ids), 8, _p(tr.table), R, tr.L, tr.V, tr.E, _p(tr.pooled), _p(tr.inv_len), _p(tr.pooled_bf16), s()), "x"),
+        "embed_pool_fwd": lambda: check(lib.tt_embed_pool_fwd(_p(tr.ids), 8, _p(tr.table), R, tr.L, tr.V, tr.E, _p(tr.pooled), _p(tr.inv_len), _p(tr.pooled_bf16), _p(tr.pool_bf16), s()), "x"),
         "tower_fwd": lambda: tr._tower_fwd(0),
         "ce_fwd": (lambda: check(lib.tt_inbatch_ce_fwd_ex(_p(qb), B, _p(db), B, B, B, 0, 0, H, 10.0, 0, 1.0 / B, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), _p(tr.ce_ws), tr.ce_ws.numel(), _p(tr.ce_sync), s()), "x"))
                   if getattr(tr, "local_fast", False) else lambda: check(lib.tt_inbatch_ce_fwd(_p(qf), _p(df), _p(qb), _p(db), B, B, H, 10.0, 0, 1.0 / B, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), tr.prec, _p(tr.ws), tr.ws.numel(), s()), "x"),
@@ -77,6 +77,8 @@ def main():
         "adamw": lambda: check(lib.tt_adamw_step(_p(tr.flat), _p(tr.flat_grad), _p(tr.exp_avg), _p(tr.exp_avg_sq), tr.n_params, 1e-3, 0.9, 0.999, 1e-8, 0.01, _p(tr.step_count), _p(tr.flat_bf16), s()), "x"),
         "whole_step": lambda: tr._step_impl(),
     }
+    if tr.embed_fused:
+        del ops["embed_pool_bwd"]            # folded into the tower backward (tt_mlp_embed_t)
     total = 0.0
     for name, fn in ops.items():
         before = _lib.launch_count()

@@ -25,12 +25,13 @@ SIGNATURES = {
     "tt_require_sm100": (_i, [_i]),
     "tt_launch_count": (_i64, []),
     "tt_embed_gather": (_i, [_vp, _i, _vp, _i64, _i64, _i, _vp, _vp]),
-    "tt_embed_pool_fwd": (_i, [_vp, _i, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp, _vp]),
+    "tt_embed_pool_fwd": (_i, [_vp, _i, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "tt_embed_pool_bwd_workspace": (_sz, [_i64, _i, _i64, _i]),
     "tt_embed_pool_bwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _i64, _i, _vp, _vp, _sz, _vp]),
     "tt_mlp_workspace": (_sz, [_i64, _i, _i, _i]),
     "tt_mlp_fwd": (_i, [_vp] * 5 + [_i64, _i, _i] + [_vp] * 8 + [_i, _vp, _sz, _vp]),
-    "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 9 + [_i, _i64] + [_i, _vp, _sz, _vp]),
+    "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 9 + [_i, _i64, _vp] + [_i, _vp, _sz, _vp]),
+    "tt_mlp_embed_workspace": (_sz, [_i64, _i, _i64]),
     "tt_proj_ln_workspace": (_sz, [_i64, _i, _i]),
     "tt_proj_ln_fwd": (_i, [_vp] * 5 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 4 + [_vp, _sz, _vp]),
     "tt_proj_ln_bwd": (_i, [_vp] * 7 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 5 + [_vp, _sz, _vp]),
@@ -50,6 +51,12 @@ SIGNATURES = {
     "tt_selftest_tc_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "tt_adamw_step": (_i, [_vp] * 4 + [_i64] + [C.c_double] * 5 + [_vp, _vp, _vp]),
 }
+
+class MlpEmbed(C.Structure):
+    """tt_mlp_embed_t (include/tt_b200.h)"""
+    _fields_ = [("pool_bf16", _vp), ("V", _i64), ("table", _vp), ("d_table", _vp), ("accumulate", _i),
+                ("workspace", _vp), ("workspace_bytes", _sz)]
+
 
 class CePass(C.Structure):
     """tt_ce_pass_t (include/tt_b200.h)"""

@@ -33,12 +33,19 @@ template <typename IdT, int NACC, bool VEC>
 __global__ void __launch_bounds__(256)
 embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ table, int64_t rows,
                       int L, int64_t V, int E, int tpt, float* __restrict__ pooled,
-                      float* __restrict__ inv_len, __nv_bfloat16* __restrict__ pooled_bf16) {
+                      float* __restrict__ inv_len, __nv_bfloat16* __restrict__ pooled_bf16,
+                      __nv_bfloat16* __restrict__ pool_bf16) {
+  extern __shared__ int fwd_hist[];                    // [warps][V] token histogram (only with pool_bf16)
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  int* hist = fwd_hist + (threadIdx.x >> 5) * (int)V;
+  if (pool_bf16) {
+    for (int v = lane; v < (int)V; v += 32) hist[v] = 0;
+    __syncwarp();
+  }
   const int groups = 32 / tpt;
   const int sub = lane % tpt, grp = lane / tpt;
   const IdT* rid = ids + row * L;
@@ -61,6 +68,7 @@ embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ tab
         if (tb + 32 < L) next_id = (tb + 32 + lane < L) ? load_id(rid + tb + 32 + lane) : 0;   // prefetch the next id block
         const int my_row = (my_id > 0 && my_id < V) ? (int)my_id : -1;       // -1 == masked token
         cnt += __popc(__ballot_sync(0xffffffffu, my_row >= 0));
+        if (pool_bf16 && cbase == 0 && my_row >= 0) atomicAdd(&hist[my_row], 1);   // integer counts: order-free, exact
         const int nb = min(32, L - tb);
         for (int tbase = 0; tbase < nb; tbase += TOK * groups) {     // warp-uniform trip count (shuffles inside)
           const int t0 = tbase + grp;
@@ -117,6 +125,11 @@ embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ tab
       }
     }
     if (lane == 0 && inv_len) inv_len[row] = 1.0f / ((float)count + 1e-9f);
+    if (pool_bf16) {                                     // P[row, v] = count(row, v) / len(row)  (the pooling matrix, bf16)
+      __syncwarp();
+      const float il = 1.0f / ((float)count + 1e-9f);
+      for (int v = lane; v < (int)V; v += 32) pool_bf16[row * V + v] = __float2bfloat16((float)hist[v] * il);
+    }
   } else {
     // scalar path (E not a multiple of 4 or unaligned table): lane-strided columns
     int cnt = 0;
@@ -136,6 +149,14 @@ embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ tab
       if (pooled_bf16) pooled_bf16[row * E + e] = __float2bfloat16(o);
     }
     if (lane == 0 && inv_len) inv_len[row] = 1.0f / denom;
+    if (pool_bf16) {
+      for (int t = lane; t < L; t += 32) {
+        const int64_t id = load_id(rid + t);
+        if (id > 0 && id < V) atomicAdd(&hist[id], 1);
+      }
+      __syncwarp();
+      for (int v = lane; v < (int)V; v += 32) pool_bf16[row * V + v] = __float2bfloat16((float)hist[v] / denom);
+    }
   }
 }
 
@@ -296,26 +317,29 @@ static BwdPlan plan_bwd(int64_t rows, int L, int64_t V, int E) {
 
 template <typename IdT>
 static int embed_pool_fwd_t(const IdT* ids, const float* table, int64_t rows, int L, int64_t V, int E,
-                            float* pooled, float* inv_len, __nv_bfloat16* pooled_bf16, cudaStream_t s) {
+                            float* pooled, float* inv_len, __nv_bfloat16* pooled_bf16, __nv_bfloat16* pool_bf16,
+                            cudaStream_t s) {
   const int warps = 8;
   const unsigned grid = (unsigned)ceil_div(rows, warps);
+  if (pool_bf16 && V > kSmallVocab) { set_error("embed_pool_fwd: the pooling-matrix output needs V <= %d", kSmallVocab); return TT_ERR_UNSUPPORTED; }
+  const size_t hsm = pool_bf16 ? (size_t)warps * V * sizeof(int) : 0;
   const bool vec = (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(table) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(pooled) & 15) == 0) &&
                    (pooled_bf16 == nullptr || (reinterpret_cast<uintptr_t>(pooled_bf16) & 7) == 0);
   if (!vec) {
-    TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 1, false>, dim3(grid), dim3(warps * 32), 0, s, true, ids, table, rows, L, V, E, 32,
-                          pooled, inv_len, pooled_bf16));
+    TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 1, false>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, 32,
+                          pooled, inv_len, pooled_bf16, pool_bf16));
   } else {
     const int chunks = E / 4;
     int tpt = 1;
     while (tpt < chunks && tpt < 32) tpt <<= 1;
     const int per_lane = (int)ceil_div(chunks, tpt);
     if (per_lane <= 1)
-      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 1, true>, dim3(grid), dim3(warps * 32), 0, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16));
+      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 1, true>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16, pool_bf16));
     else if (per_lane == 2)
-      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 2, true>, dim3(grid), dim3(warps * 32), 0, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16));
+      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 2, true>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16, pool_bf16));
     else
-      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 3, true>, dim3(grid), dim3(warps * 32), 0, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16));
+      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 3, true>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16, pool_bf16));
   }
   TT_LAUNCH_CHECK("embed_pool_fwd_kernel");
   return TT_OK;
@@ -394,7 +418,7 @@ int tt_embed_gather(const void* ids, int id_bytes, const float* table, int64_t n
 }
 
 int tt_embed_pool_fwd(const void* ids, int id_bytes, const float* table, int64_t rows, int L, int64_t V,
-                      int E, float* pooled, float* inv_len, void* pooled_bf16, void* stream) {
+                      int E, float* pooled, float* inv_len, void* pooled_bf16, void* pool_bf16, void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(ids && table && pooled && rows >= 0 && L > 0 && V > 0 && E > 0, "embed_pool_fwd: bad arguments");
   TT_CHECK_ARG(id_bytes == 4 || id_bytes == 8, "embed_pool_fwd: id_bytes must be 4 or 8");
@@ -402,9 +426,9 @@ int tt_embed_pool_fwd(const void* ids, int id_bytes, const float* table, int64_t
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (id_bytes == 8)
     return tt::embed_pool_fwd_t<int64_t>((const int64_t*)ids, table, rows, L, V, E, pooled, inv_len,
-                                         (__nv_bfloat16*)pooled_bf16, s);
+                                         (__nv_bfloat16*)pooled_bf16, (__nv_bfloat16*)pool_bf16, s);
   return tt::embed_pool_fwd_t<int32_t>((const int32_t*)ids, table, rows, L, V, E, pooled, inv_len,
-                                       (__nv_bfloat16*)pooled_bf16, s);
+                                       (__nv_bfloat16*)pooled_bf16, (__nv_bfloat16*)pool_bf16, s);
 }
 
 size_t tt_embed_pool_bwd_workspace(int64_t rows, int L, int64_t V, int E) {

@@ -43,6 +43,13 @@ __global__ void __launch_bounds__(256) reduce_parts_kernel(const ReduceJobs jobs
     if (i < j.n) {
       const float* base = j.part + i;
       int p = w;
+      for (; p + 56 < j.nparts; p += 64) {                       // 8 independent loads in flight
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = __ldg(base + (int64_t)(p + 8 * u) * j.stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += t[u];
+      }
       for (; p + 24 < j.nparts; p += 32) {                       // 4 independent loads in flight
         const float a = __ldg(base + (int64_t)p * j.stride), b = __ldg(base + (int64_t)(p + 8) * j.stride);
         const float c = __ldg(base + (int64_t)(p + 16) * j.stride), d = __ldg(base + (int64_t)(p + 24) * j.stride);

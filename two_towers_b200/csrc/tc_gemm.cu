@@ -524,66 +524,131 @@ l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __r
     if (yb) yb[row * H + e] = __float2bfloat16(o);
   }
 }
+// Tail of the embedding-fused tower backward: with M = P^T da1 [V,H] (fp32),
+//   dw1[h,e]     = sum_v M[v,h] table[v,e]        (== da1^T x   for x = P table)
+//   d_table[v,e] = sum_h M[v,h] w1[h,e]           (== P^T dx    for dx = da1 w1)
+// one thread per output, fixed summation order; consecutive threads take consecutive e (coalesced table / w1 reads,
+// M is a warp-wide broadcast).
+__global__ void __launch_bounds__(64)
+embed_finish_kernel(const float* __restrict__ M, const float* __restrict__ table, const float* __restrict__ w1, int V,
+                    int H, int E, float* __restrict__ dw1, float* __restrict__ d_table, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n1 = (int64_t)H * E;
+  if (i < n1) {
+    const int h = (int)(i / E), e = (int)(i % E);
+    // 16 independent load pairs are issued before any of them is used: the loop is latency-, not bandwidth-bound
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int v = 0;
+    for (; v + 16 <= V; v += 16) {
+      float m[16], t[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) { m[u] = __ldg(M + (size_t)(v + u) * H + h); t[u] = __ldg(table + (size_t)(v + u) * E + e); }
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) {
+        a0 = fmaf(m[u], t[u], a0); a1 = fmaf(m[u + 1], t[u + 1], a1); a2 = fmaf(m[u + 2], t[u + 2], a2); a3 = fmaf(m[u + 3], t[u + 3], a3);
+      }
+    }
+    for (; v < V; ++v) a0 = fmaf(M[(size_t)v * H + h], table[(size_t)v * E + e], a0);
+    dw1[i] = (a0 + a1) + (a2 + a3);
+  } else if (i < n1 + (int64_t)V * E) {
+    const int64_t j = i - n1;
+    const int v = (int)(j / E), e = (int)(j % E);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* mr = M + (size_t)v * H;
+    int h = 0;
+    for (; h + 16 <= H; h += 16) {
+      float4 m4[4];
+      float t[16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m4[u] = __ldg(reinterpret_cast<const float4*>(mr + h) + u);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t[u] = __ldg(w1 + (size_t)(h + u) * E + e);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a0 = fmaf(m4[u].x, t[4 * u], a0); a1 = fmaf(m4[u].y, t[4 * u + 1], a1);
+        a2 = fmaf(m4[u].z, t[4 * u + 2], a2); a3 = fmaf(m4[u].w, t[4 * u + 3], a3);
+      }
+    }
+    for (; h < H; ++h) a0 = fmaf(mr[h], w1[(size_t)h * E + e], a0);
+    float r = (a0 + a1) + (a2 + a3);
+    if (v == 0) r = 0.f;                                  // padding row: never looked up (ids > 0), gradient 0 like the reference
+    d_table[j] = accumulate ? d_table[j] + r : r;
+  }
+}
+
 constexpr int kNormRowsPerBlock = 32;
-// dz = (dy - y (y.dy)) / |z|  -> fp32 + bf16; also per-block column sums of dz (-> db2), H <= 512
-__global__ void __launch_bounds__(256)
+// dz = (dy - y (y.dy)) / |z|  -> fp32 + bf16; also per-block column sums of dz (-> db2), H <= 32 * KMAX <= 512.
+// 16 warps x 2 rows: both rows of a warp are loaded together, so a block pays one memory round trip, not four.
+template <int KMAX>
+__global__ void __launch_bounds__(512)
 l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_stride, const float* __restrict__ z,
                          int64_t R, int H, float* __restrict__ dz, __nv_bfloat16* __restrict__ dzb,
                          float* __restrict__ colsum_part) {
-  __shared__ float s_part[8][512];
+  __shared__ float s_part[16][32 * KMAX];
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float cs[16];
+  const int64_t row0 = (int64_t)blockIdx.x * kNormRowsPerBlock + warp * 2;
+  float g[2][KMAX], zv[2][KMAX];
+  // dy may arrive as `dy_parts` split slices (the loss kernel's per-split partial gradients): summed in slice order
 #pragma unroll
-  for (int k = 0; k < 16; ++k) cs[k] = 0.f;
-  for (int i = 0; i < kNormRowsPerBlock / 8; ++i) {
-    const int64_t row = (int64_t)blockIdx.x * kNormRowsPerBlock + warp * (kNormRowsPerBlock / 8) + i;
-    if (row >= R) break;
-    const float* zr = z + row * H; const float* gr = dy + row * H;
-    // dy may arrive as `dy_parts` split slices (the loss kernel's per-split partial gradients): summed in slice
-    // order; every slice's loads are issued together (independent, up to 16 in flight per lane)
-    float g[16], zv[16];
+  for (int i = 0; i < 2; ++i) {
+    const bool ok = row0 + i < R;
+    const float* zr = z + (row0 + i) * H; const float* gr = dy + (row0 + i) * H;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < KMAX; ++k) {
       const int e = lane + 32 * k;
-      zv[k] = (e < H) ? zr[e] : 0.f;
-      g[k] = (e < H) ? gr[e] : 0.f;
+      zv[i][k] = (ok && e < H) ? zr[e] : 0.f;
+      g[i][k] = (ok && e < H) ? gr[e] : 0.f;
     }
-    for (int pp = 1; pp < dy_parts; ++pp) {
-      float t[16];
+  }
+  for (int pp = 1; pp < dy_parts; ++pp) {
+    float t[2][KMAX];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) { const int e = lane + 32 * k; t[k] = (e < H) ? gr[(int64_t)pp * dy_stride + e] : 0.f; }
+    for (int i = 0; i < 2; ++i) {
+      const bool ok = row0 + i < R;
+      const float* gr = dy + (row0 + i) * H + (int64_t)pp * dy_stride;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) g[k] += t[k];
+      for (int k = 0; k < KMAX; ++k) { const int e = lane + 32 * k; t[i][k] = (ok && e < H) ? gr[e] : 0.f; }
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) g[i][k] += t[i][k];
+  }
+  float cs[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) cs[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
     float ss = 0.f, dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int e = lane + 32 * k;
-      if (e < H) { float v = zv[k]; ss = fmaf(v, v, ss); dot = fmaf(v, g[k], dot); }
-    }
+    for (int k = 0; k < KMAX; ++k) { const float v = zv[i][k]; ss = fmaf(v, v, ss); dot = fmaf(v, g[i][k], dot); }
     ss = warp_sum(ss); dot = warp_sum(dot);
     const float n = sqrtf(ss), denom = fmaxf(n, 1e-12f);
     const float inner = (n > 1e-12f) ? dot / (denom * denom) : 0.f;
+    if (row0 + i < R) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int e = lane + 32 * k;
-      if (e < H) {
-        const float o = (g[k] - zv[k] * inner) / denom;
-        if (dz) dz[row * H + e] = o;
-        dzb[row * H + e] = __float2bfloat16(o);
-        cs[k] += o;
+      for (int k = 0; k < KMAX; ++k) {
+        const int e = lane + 32 * k;
+        if (e < H) {
+          const float o = (g[i][k] - zv[i][k] * inner) / denom;
+          if (dz) dz[(row0 + i) * H + e] = o;
+          dzb[(row0 + i) * H + e] = __float2bfloat16(o);
+          cs[k] += o;
+        }
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < 16; ++k) if (lane + 32 * k < H) s_part[warp][lane + 32 * k] = cs[k];
+  for (int k = 0; k < KMAX; ++k) s_part[warp][lane + 32 * k] = cs[k];
   __syncthreads();
-  for (int e = threadIdx.x; e < H; e += 256) {
+  for (int e = threadIdx.x; e < H; e += 512) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += s_part[w][e];
+    for (int w = 0; w < 16; ++w) t += s_part[w][e];
     colsum_part[(size_t)blockIdx.x * H + e] = t;
   }
 }
@@ -684,9 +749,10 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
 int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1, const float* z,
                int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2, float* db2,
                const __nv_bfloat16* x_bf16, const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16,
-               const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride, void* ws, size_t ws_bytes,
-               cudaStream_t s) {
+               const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed, void* ws,
+               size_t ws_bytes, cudaStream_t s) {
   if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0"); return TT_ERR_UNSUPPORTED; }
+  if (embed && (embed->V % 8 != 0 || E % 4 != 0)) { set_error("tc_mlp_bwd: embed needs V %% 8 == 0 and E %% 4 == 0"); return TT_ERR_UNSUPPORTED; }
   if (dy_parts < 1) dy_parts = 1;
   if (dy_parts > 1 && H > 512) { set_error("tc_mlp_bwd: split dy needs H <= 512"); return TT_ERR_UNSUPPORTED; }
   const TcMlpPlan plan = plan_tc_mlp(R, E, H);
@@ -718,8 +784,13 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   const bool fused_cs = H <= 512;
   const int nblk2 = (int)ceil_div(R, tc::kNormRowsPerBlock);
   if (fused_cs) {
-    TT_CUDA(launch_kernel(tc::l2norm_bwd_colsum_kernel, dim3((unsigned)nblk2), dim3(256), 0, s, true, dy, dy_parts, dy_part_stride, z, R, H,
-                          (float*)nullptr, dzb, cs2));   // fp32 dz is not needed: db2 comes from cs2
+    // fp32 dz is not needed: db2 comes from cs2
+    if (H <= 256)
+      TT_CUDA(launch_kernel(tc::l2norm_bwd_colsum_kernel<8>, dim3((unsigned)nblk2), dim3(512), 0, s, true, dy, dy_parts, dy_part_stride, z, R, H,
+                            (float*)nullptr, dzb, cs2));
+    else
+      TT_CUDA(launch_kernel(tc::l2norm_bwd_colsum_kernel<16>, dim3((unsigned)nblk2), dim3(512), 0, s, true, dy, dy_parts, dy_part_stride, z, R, H,
+                            (float*)nullptr, dzb, cs2));
     TT_LAUNCH_CHECK("l2norm_bwd_colsum_kernel");
   } else {
     tc::l2norm_bwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(dy, z, R, H, dz, dzb);
@@ -733,6 +804,33 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   ga1.M = (int)R; ga1.N = H; ga1.K = H; ga1.A = dzb; ga1.a_mn = 0; ga1.B = w2a; ga1.b_mn = 1; ga1.C = nullptr; ga1.Cb = da1b;
   ga1.ldc = H; ga1.mask = h1a; ga1.ldmask = H; ga1.colsum_part = cs1;   // fp32 da1 never needed: db1 comes from cs1
   rc = tc::tc_gemm2(ga1, gw2, s); if (rc) return rc;
+  if (embed) {
+    // x = P table: M[V,H] = P^T da1 (split-K partials) replaces dx, dw1 = da1^T x and the embedding backward
+    const int V = (int)embed->V;
+    const int sm = tc::pick_splits(V, H, (int)R);
+    const size_t need = tc_mlp_embed_workspace(V, H, R);
+    if (embed->workspace == nullptr || embed->workspace_bytes < need) { set_error("tc_mlp_bwd: embed workspace too small (%zu < %zu)", embed->workspace_bytes, need); return TT_ERR_WORKSPACE; }
+    Workspace we(embed->workspace, embed->workspace_bytes);
+    float* Mbuf = we.take<float>((size_t)V * H);
+    float* Mpart = sm > 1 ? we.take<float>((size_t)sm * V * H) : nullptr;
+    tc::TcGemm gm{};
+    gm.M = V; gm.N = H; gm.K = (int)R; gm.A = (const __nv_bfloat16*)embed->pool_bf16; gm.a_mn = 1; gm.B = da1b; gm.b_mn = 1;
+    gm.C = Mbuf; gm.ldc = H; gm.splits = sm; gm.partial = Mpart; gm.defer_reduce = true;
+    rc = tc::tc_gemm(gm, s); if (rc) return rc;
+    ReduceJobs jobs{};
+    int nj = 0;
+    if (plan.s_dw2 > 1) jobs.job[nj++] = make_job(partial, plan.s_dw2, (int64_t)H * H, (int64_t)H * H, dw2);
+    if (sm > 1) jobs.job[nj++] = make_job(Mpart, sm, (int64_t)V * H, (int64_t)V * H, Mbuf);
+    jobs.job[nj++] = make_job(cs1, (int)ceil_div(R, 32), H, H, db1);
+    if (fused_cs) jobs.job[nj++] = make_job(cs2, nblk2, H, H, db2);
+    jobs.njobs = nj;
+    rc = reduce_parts(jobs, s); if (rc) return rc;
+    const int64_t outs = (int64_t)H * E + (int64_t)V * E;
+    TT_CUDA(launch_kernel(tc::embed_finish_kernel, dim3((unsigned)ceil_div(outs, 64)), dim3(64), 0, s, true, (const float*)Mbuf, embed->table, w1,
+                          V, H, E, dw1, embed->d_table, embed->accumulate));
+    TT_LAUNCH_CHECK("embed_finish_kernel");
+    return TT_OK;
+  }
   // launch 2: { dw1[H,E] = da1^T x (split-K partials),  dx[R,E] = da1 w1 }
   tc::TcGemm gw1{}, gdx{};
   gw1.M = H; gw1.N = E; gw1.K = (int)R; gw1.A = da1b; gw1.a_mn = 1; gw1.B = xa; gw1.b_mn = 1; gw1.C = dw1; gw1.ldc = E;
@@ -752,6 +850,11 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   if (fused_cs) jobs.job[nj++] = make_job(cs2, nblk2, H, H, db2);
   jobs.njobs = nj;
   return reduce_parts(jobs, s);
+}
+
+size_t tc_mlp_embed_workspace(int64_t V, int H, int64_t R) {
+  const int sm = tc::pick_splits((int)V, H, (int)R);
+  return align_up((size_t)V * H * 4) + align_up(sm > 1 ? (size_t)sm * V * H * 4 : 0) + 256;
 }
 
 // self-test hook used by the GPU test-suite: C = A * B on the tensor cores with either operand major

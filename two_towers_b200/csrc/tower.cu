@@ -272,19 +272,30 @@ int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
 int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1,
                const float* z, int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2,
                float* db2, const void* x_bf16, const void* w1_bf16, const void* w2_bf16, const void* h1_bf16,
-               int dy_parts, int64_t dy_part_stride, int precision, void* workspace, size_t workspace_bytes,
-               void* stream) {
+               int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed, int precision, void* workspace,
+               size_t workspace_bytes, void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(dy && x && w1 && w2 && h1 && z && dw1 && db1 && dw2 && db2 && R > 0 && E > 0 && H > 0,
                "mlp_bwd: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (precision == TT_PREC_BF16)
+  if (precision == TT_PREC_BF16) {
+    if (embed) {
+      TT_CHECK_ARG(embed->pool_bf16 && embed->table && embed->d_table && embed->V > 0 && dx == nullptr,
+                   "mlp_bwd: embed needs pool_bf16, table, d_table and dx == NULL");
+    }
     return tt::tc_mlp_bwd(dy, x, w1, w2, h1, z, R, E, H, dx, dw1, db1, dw2, db2, (const __nv_bfloat16*)x_bf16,
                           (const __nv_bfloat16*)w1_bf16, (const __nv_bfloat16*)w2_bf16, (const __nv_bfloat16*)h1_bf16,
-                          dy_parts, dy_part_stride, workspace, workspace_bytes, s);
+                          dy_parts, dy_part_stride, embed, workspace, workspace_bytes, s);
+  }
+  TT_CHECK_ARG(embed == nullptr, "mlp_bwd: embed is a TT_PREC_BF16 feature");
   TT_CHECK_ARG(precision == TT_PREC_FP32, "mlp_bwd: unknown precision %d", precision);
   TT_CHECK_ARG(dy_parts <= 1, "mlp_bwd: split dy slices are a TT_PREC_BF16 feature");
   return tt::mlp_bwd_fp32(dy, x, w1, w2, h1, z, R, E, H, dx, dw1, db1, dw2, db2, workspace, workspace_bytes, s);
+}
+
+size_t tt_mlp_embed_workspace(int64_t V, int H, int64_t R) {
+  if (V <= 0 || H <= 0 || R <= 0) return 256;
+  return tt::tc_mlp_embed_workspace(V, H, R);
 }
 
 size_t tt_proj_ln_workspace(int64_t R, int E, int H) {

@@ -102,7 +102,7 @@ def embed_pool_fwd(ids: torch.Tensor, table: torch.Tensor, want_bf16: bool = Fal
     inv_len = torch.empty(R, dtype=torch.float32, device=table.device)
     pooled_bf16 = torch.empty(R, E, dtype=torch.bfloat16, device=table.device) if want_bf16 else None
     check(_lib_().tt_embed_pool_fwd(_p(ids_c), idb, _p(table), R, L, V, E, _p(pooled), _p(inv_len),
-                                    _p(pooled_bf16), _stream()), "tt_embed_pool_fwd")
+                                    _p(pooled_bf16), None, _stream()), "tt_embed_pool_fwd")
     return pooled, inv_len, pooled_bf16
 
 
@@ -156,7 +156,7 @@ def mlp_bwd(dy, x, w1, w2, h1, z, need_dx: bool = True, precision=None):
     db2 = torch.empty(H, dtype=torch.float32, device=dev)
     ws = _workspace(_lib_().tt_mlp_workspace(R, E, H, prec), dev)
     check(_lib_().tt_mlp_bwd(_p(dy), _p(x), _p(w1), _p(w2), _p(h1), _p(z), R, E, H, _p(dx), _p(dw1), _p(db1),
-                             _p(dw2), _p(db2), None, None, None, None, 1, 0, prec, _p(ws), ws.numel(), _stream()),
+                             _p(dw2), _p(db2), None, None, None, None, 1, 0, None, prec, _p(ws), ws.numel(), _stream()),
           "tt_mlp_bwd")
     return dx, dw1, db1, dw2, db2
 

@@ -138,6 +138,13 @@ class FusedTrainer:
         # bf16 shadow of the flat parameter buffer, refreshed by the AdamW kernel -> the tensor-core GEMMs
         # read weights without any per-step conversion kernel
         self.flat_bf16 = ops.cast_bf16(self.flat) if bf else None
+        # small vocabularies on the tensor-core path: the forward also emits the pooling matrix P (x = P table) and the
+        # tower backward forms P^T da1 once -- no dx, no separate embedding backward (see tt_mlp_embed_t)
+        self.embed_fused = bool(bf and self.train_table and self.V <= 1024 and self.V % 8 == 0 and self.E % 4 == 0 and
+                                all(isinstance(t, MeanPoolingTower) for t, _, _ in self.groups))
+        self.pool_bf16 = torch.empty(R, self.V, dtype=torch.bfloat16, device=self.dev) if self.embed_fused else None
+        self.embed_ws = (torch.empty(int(max(self.lib.tt_mlp_embed_workspace(self.V, self.H, nr) for _, _, nr in self.groups)),
+                                     dtype=torch.uint8, device=self.dev) if self.embed_fused else None)
         self.h1_bf16 = [torch.empty(nr, self.H, dtype=torch.bfloat16, device=self.dev) if bf else None
                         for _, _, nr in self.groups]
         self.loss = torch.zeros((), **f32)
@@ -195,12 +202,18 @@ class FusedTrainer:
         x, dy = self.pooled[r0:r0 + nr], self.dy[r0:r0 + nr]          # slice 0; further slices dy_part_stride apart
         dx = self.dpooled[r0:r0 + nr] if self.train_table else None
         xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
+        emb = None
+        if self.embed_fused:
+            emb = _lib.MlpEmbed(self.pool_bf16[r0:r0 + nr].data_ptr(), self.V, self.table.data_ptr(), self.table.grad.data_ptr(),
+                                1 if gi > 0 else 0, self.embed_ws.data_ptr(), self.embed_ws.numel())
+            dx = None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
             check(lib.tt_mlp_bwd(_p(dy), _p(x), _p(l1.weight), _p(l2.weight), _p(sv["h1"]), _p(sv["z"]), nr, self.E,
                                  self.H, _p(dx), _p(l1.weight.grad), _p(l1.bias.grad), _p(l2.weight.grad),
                                  _p(l2.bias.grad), _p(xb), _p(self._shadow(l1.weight)), _p(self._shadow(l2.weight)),
-                                 _p(self.h1_bf16[gi]), self.dy_parts, self.dy_part_stride, self.prec, _p(self.ws),
+                                 _p(self.h1_bf16[gi]), self.dy_parts, self.dy_part_stride,
+                                 C.byref(emb) if emb is not None else None, self.prec, _p(self.ws),
                                  self.ws.numel(), s), "tt_mlp_bwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
@@ -218,7 +231,7 @@ class FusedTrainer:
         idb = 8 if self.ids.dtype == torch.int64 else 4
         s = self._stream()
         check(lib.tt_embed_pool_fwd(_p(self.ids), idb, _p(self.table), R, self.L, self.V, self.E, _p(self.pooled),
-                                    _p(self.inv_len), _p(self.pooled_bf16), s), "tt_embed_pool_fwd")
+                                    _p(self.inv_len), _p(self.pooled_bf16), _p(self.pool_bf16), s), "tt_embed_pool_fwd")
         for gi in range(len(self.groups)):
             self._tower_fwd(gi)
         q, d = self.y[:B], self.y[B:2 * B]
@@ -262,7 +275,7 @@ class FusedTrainer:
                   "tt_triplet_bwd")
         for gi in range(len(self.groups)):
             self._tower_bwd(gi)
-        if self.train_table:
+        if self.train_table and not self.embed_fused:
             check(lib.tt_embed_pool_bwd(_p(self.ids), idb, _p(self.inv_len), _p(self.dpooled), R, self.L, self.V,
                                         self.E, _p(self.table.grad), _p(self.ws), self.ws.numel(), s),
                   "tt_embed_pool_bwd")

@@ -527,54 +527,56 @@ l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __r
 // Tail of the embedding-fused tower backward: with M = P^T da1 [V,H] (fp32),
 //   dw1[h,e]     = sum_v M[v,h] table[v,e]        (== da1^T x   for x = P table)
 //   d_table[v,e] = sum_h M[v,h] w1[h,e]           (== P^T dx    for dx = da1 w1)
-// one thread per output, fixed summation order; consecutive threads take consecutive e (coalesced table / w1 reads,
-// M is a warp-wide broadcast).
-__global__ void __launch_bounds__(64)
+// Two small fp32 products.  A block owns an 8-row x 64-column output tile; K is walked in chunks of 128 staged in
+// shared memory with wide coalesced loads (one memory round trip per chunk), each thread accumulating two adjacent
+// columns in ascending-k order (bitwise reproducible).
+constexpr int kFinRows = 8, kFinCols = 64, kFinK = 128;
+__global__ void __launch_bounds__(256)
 embed_finish_kernel(const float* __restrict__ M, const float* __restrict__ table, const float* __restrict__ w1, int V,
                     int H, int E, float* __restrict__ dw1, float* __restrict__ d_table, int accumulate) {
+  __shared__ __align__(16) float As[kFinK][kFinRows];
+  __shared__ __align__(16) float Bs[kFinK][kFinCols];
   pdl_trigger();
   pdl_wait();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t n1 = (int64_t)H * E;
-  if (i < n1) {
-    const int h = (int)(i / E), e = (int)(i % E);
-    // 16 independent load pairs are issued before any of them is used: the loop is latency-, not bandwidth-bound
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int v = 0;
-    for (; v + 16 <= V; v += 16) {
-      float m[16], t[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) { m[u] = __ldg(M + (size_t)(v + u) * H + h); t[u] = __ldg(table + (size_t)(v + u) * E + e); }
-#pragma unroll
-      for (int u = 0; u < 16; u += 4) {
-        a0 = fmaf(m[u], t[u], a0); a1 = fmaf(m[u + 1], t[u + 1], a1); a2 = fmaf(m[u + 2], t[u + 2], a2); a3 = fmaf(m[u + 3], t[u + 3], a3);
-      }
+  const int tiles1 = (H + kFinRows - 1) / kFinRows;       // dw1 row tiles come first, then d_table row tiles
+  const bool second = (int)blockIdx.x >= tiles1;
+  const int r0 = (second ? (int)blockIdx.x - tiles1 : (int)blockIdx.x) * kFinRows;
+  const int c0 = blockIdx.y * kFinCols;
+  const int rows = second ? V : H, K = second ? H : V;
+  const float* B = second ? w1 : table;                   // [K, E]
+  const int tr = threadIdx.x >> 5, tc2 = (threadIdx.x & 31) * 2;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int k0 = 0; k0 < K; k0 += kFinK) {
+    const int kc = min(kFinK, K - k0);
+    // A chunk: As[k][r] = second ? M[(r0 + r) * H + k0 + k] : M[(k0 + k) * H + r0 + r]
+    for (int i = threadIdx.x; i < kFinK * kFinRows; i += 256) {
+      int k, r;
+      if (second) { r = i / kFinK; k = i % kFinK; } else { k = i / kFinRows; r = i % kFinRows; }
+      float v = 0.f;
+      if (k < kc && r0 + r < rows) v = second ? __ldg(M + (size_t)(r0 + r) * H + k0 + k) : __ldg(M + (size_t)(k0 + k) * H + r0 + r);
+      As[k][r] = v;
     }
-    for (; v < V; ++v) a0 = fmaf(M[(size_t)v * H + h], table[(size_t)v * E + e], a0);
-    dw1[i] = (a0 + a1) + (a2 + a3);
-  } else if (i < n1 + (int64_t)V * E) {
-    const int64_t j = i - n1;
-    const int v = (int)(j / E), e = (int)(j % E);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const float* mr = M + (size_t)v * H;
-    int h = 0;
-    for (; h + 16 <= H; h += 16) {
-      float4 m4[4];
-      float t[16];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) m4[u] = __ldg(reinterpret_cast<const float4*>(mr + h) + u);
-#pragma unroll
-      for (int u = 0; u < 16; ++u) t[u] = __ldg(w1 + (size_t)(h + u) * E + e);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        a0 = fmaf(m4[u].x, t[4 * u], a0); a1 = fmaf(m4[u].y, t[4 * u + 1], a1);
-        a2 = fmaf(m4[u].z, t[4 * u + 2], a2); a3 = fmaf(m4[u].w, t[4 * u + 3], a3);
-      }
+    for (int i = threadIdx.x; i < kFinK * (kFinCols / 4); i += 256) {
+      const int k = i / (kFinCols / 4), c = (i % (kFinCols / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < kc && c0 + c < E) v = __ldg(reinterpret_cast<const float4*>(B + (size_t)(k0 + k) * E + c0 + c));   // E % 4 == 0
+      *reinterpret_cast<float4*>(&Bs[k][c]) = v;
     }
-    for (; h < H; ++h) a0 = fmaf(mr[h], w1[(size_t)h * E + e], a0);
-    float r = (a0 + a1) + (a2 + a3);
-    if (v == 0) r = 0.f;                                  // padding row: never looked up (ids > 0), gradient 0 like the reference
-    d_table[j] = accumulate ? d_table[j] + r : r;
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kFinK; ++k) {
+      const float a = As[k][tr];
+      const float2 b = *reinterpret_cast<const float2*>(&Bs[k][tc2]);
+      acc0 = fmaf(a, b.x, acc0); acc1 = fmaf(a, b.y, acc1);
+    }
+    __syncthreads();
+  }
+  const int r = r0 + tr, c = c0 + tc2;
+  if (r < rows && c < E) {                                // E % 4 == 0: c and c + 1 are both in range
+    float* out = (second ? d_table : dw1) + (size_t)r * E + c;
+    if (second && r == 0) { acc0 = 0.f; acc1 = 0.f; }      // padding row: never looked up (ids > 0), gradient 0 like the reference
+    if (second && accumulate) { acc0 += out[0]; acc1 += out[1]; }
+    out[0] = acc0; out[1] = acc1;
   }
 }
 
@@ -825,8 +827,8 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
     if (fused_cs) jobs.job[nj++] = make_job(cs2, nblk2, H, H, db2);
     jobs.njobs = nj;
     rc = reduce_parts(jobs, s); if (rc) return rc;
-    const int64_t outs = (int64_t)H * E + (int64_t)V * E;
-    TT_CUDA(launch_kernel(tc::embed_finish_kernel, dim3((unsigned)ceil_div(outs, 64)), dim3(64), 0, s, true, (const float*)Mbuf, embed->table, w1,
+    const dim3 fgrid((unsigned)(ceil_div(H, tc::kFinRows) + ceil_div(V, tc::kFinRows)), (unsigned)ceil_div(E, tc::kFinCols));
+    TT_CUDA(launch_kernel(tc::embed_finish_kernel, fgrid, dim3(256), 0, s, true, (const float*)Mbuf, embed->table, w1,
                           V, H, E, dw1, embed->d_table, embed->accumulate));
     TT_LAUNCH_CHECK("embed_finish_kernel");
     return TT_OK;

@@ -85,6 +85,9 @@ int tt_embed_pool_bwd(const void* ids, int id_bytes, const float* inv_len, const
  *   h1_bf16 [R,H] written by fwd and read by bwd.
  * dy_parts > 1 (TT_PREC_BF16): dy is given as dy_parts slices, dy_part_stride elements apart, that are summed
  *   in slice order inside the first backward kernel (see tt_inbatch_ce_bwd_parts); pass 1, 0 otherwise.
+ * inv_norm (TT_PREC_BF16, nullable) [R]: tt_mlp_fwd also stores 1 / max(||z||, 1e-12); with y_bf16 AND inv_norm the
+ *   normalise step is fully described by them -- fwd may then be given z == NULL (8 bytes/element less to write) and
+ *   bwd, given the same y_bf16 / inv_norm, ignores z:  dz = (dy - y (y . dy)) * inv_norm.
  * embed (TT_PREC_BF16, nullable): x is the mean-pooled lookup embedding x = P * table (P from tt_embed_pool_fwd).
  *   The backward then forms M = P^T da1 [V,H] once on the tensor cores and finishes with two tiny products,
  *   dw1 = M^T table and d_table = M w1 (+= when accumulate != 0), instead of computing dx [R,E], dw1 = da1^T x and
@@ -103,12 +106,13 @@ size_t tt_mlp_workspace(int64_t R, int E, int H, int precision);
 int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                int64_t R, int E, int H, float* h1, float* z, float* y, void* y_bf16,
                const void* x_bf16, const void* w1_bf16, const void* w2_bf16, void* h1_bf16,
-               int precision, void* workspace, size_t workspace_bytes, void* stream);
+               float* inv_norm, int precision, void* workspace, size_t workspace_bytes, void* stream);
 int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2,
                const float* h1, const float* z, int64_t R, int E, int H,
                float* dx, float* dw1, float* db1, float* dw2, float* db2,
                const void* x_bf16, const void* w1_bf16, const void* w2_bf16, const void* h1_bf16,
                int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed,
+               const void* y_bf16, const float* inv_norm,
                int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K3': avg_pool tower projection  Linear(E,H) -> Dropout(p) -> LayerNorm(H) -> normalise -

@@ -29,8 +29,8 @@ SIGNATURES = {
     "tt_embed_pool_bwd_workspace": (_sz, [_i64, _i, _i64, _i]),
     "tt_embed_pool_bwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _i64, _i, _vp, _vp, _sz, _vp]),
     "tt_mlp_workspace": (_sz, [_i64, _i, _i, _i]),
-    "tt_mlp_fwd": (_i, [_vp] * 5 + [_i64, _i, _i] + [_vp] * 8 + [_i, _vp, _sz, _vp]),
-    "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 9 + [_i, _i64, _vp] + [_i, _vp, _sz, _vp]),
+    "tt_mlp_fwd": (_i, [_vp] * 5 + [_i64, _i, _i] + [_vp] * 9 + [_i, _vp, _sz, _vp]),
+    "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 9 + [_i, _i64, _vp, _vp, _vp] + [_i, _vp, _sz, _vp]),
     "tt_mlp_embed_workspace": (_sz, [_i64, _i, _i64]),
     "tt_proj_ln_workspace": (_sz, [_i64, _i, _i]),
     "tt_proj_ln_fwd": (_i, [_vp] * 5 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 4 + [_vp, _sz, _vp]),

@@ -510,7 +510,8 @@ int cast3_public(const float* a, __nv_bfloat16* ab, int64_t na, const float* b, 
 
 // y = z / max(|z|,1e-12) (fp32 + bf16)
 __global__ void __launch_bounds__(256)
-l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __restrict__ y, __nv_bfloat16* __restrict__ yb) {
+l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __restrict__ y, __nv_bfloat16* __restrict__ yb,
+                       float* __restrict__ inv_norm) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -518,6 +519,7 @@ l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __r
   float ss = 0.f;
   for (int e = lane; e < H; e += 32) { float v = zr[e]; ss = fmaf(v, v, ss); }
   const float denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  if (inv_norm && lane == 0) inv_norm[row] = 1.0f / denom;
   for (int e = lane; e < H; e += 32) {
     const float o = zr[e] / denom;
     if (y) y[row * H + e] = o;
@@ -583,9 +585,11 @@ embed_finish_kernel(const float* __restrict__ M, const float* __restrict__ table
 constexpr int kNormRowsPerBlock = 32;
 // dz = (dy - y (y.dy)) / |z|  -> fp32 + bf16; also per-block column sums of dz (-> db2), H <= 32 * KMAX <= 512.
 // 16 warps x 2 rows: both rows of a warp are loaded together, so a block pays one memory round trip, not four.
-template <int KMAX>
+// FROM_Y: the normalise step is described by (y in bf16, 1/|z|) instead of z:  dz = (dy - y (y.dy)) * inv_norm.
+template <int KMAX, bool FROM_Y>
 __global__ void __launch_bounds__(512)
 l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_stride, const float* __restrict__ z,
+                         const __nv_bfloat16* __restrict__ yb, const float* __restrict__ inv_norm,
                          int64_t R, int H, float* __restrict__ dz, __nv_bfloat16* __restrict__ dzb,
                          float* __restrict__ colsum_part) {
   __shared__ float s_part[16][32 * KMAX];
@@ -598,13 +602,19 @@ l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const bool ok = row0 + i < R;
-    const float* zr = z + (row0 + i) * H; const float* gr = dy + (row0 + i) * H;
+    const float* gr = dy + (row0 + i) * H;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       const int e = lane + 32 * k;
-      zv[i][k] = (ok && e < H) ? zr[e] : 0.f;
+      if (FROM_Y) zv[i][k] = (ok && e < H) ? __bfloat162float(yb[(row0 + i) * H + e]) : 0.f;
+      else        zv[i][k] = (ok && e < H) ? z[(row0 + i) * H + e] : 0.f;
       g[i][k] = (ok && e < H) ? gr[e] : 0.f;
     }
+  }
+  float inv[2] = {0.f, 0.f};
+  if (FROM_Y) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) inv[i] = (row0 + i < R) ? __ldg(inv_norm + row0 + i) : 0.f;
   }
   for (int pp = 1; pp < dy_parts; ++pp) {
     float t[2][KMAX];
@@ -629,14 +639,15 @@ l2norm_bwd_colsum_kernel(const float* __restrict__ dy, int dy_parts, int64_t dy_
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) { const float v = zv[i][k]; ss = fmaf(v, v, ss); dot = fmaf(v, g[i][k], dot); }
     ss = warp_sum(ss); dot = warp_sum(dot);
-    const float n = sqrtf(ss), denom = fmaxf(n, 1e-12f);
-    const float inner = (n > 1e-12f) ? dot / (denom * denom) : 0.f;
+    const float n = sqrtf(ss), denom = FROM_Y ? 1.0f : fmaxf(n, 1e-12f);
+    const float inner = FROM_Y ? dot : ((n > 1e-12f) ? dot / (denom * denom) : 0.f);
+    const float oscale = FROM_Y ? inv[i] : 1.0f / denom;
     if (row0 + i < R) {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         const int e = lane + 32 * k;
         if (e < H) {
-          const float o = (g[i][k] - zv[i][k] * inner) / denom;
+          const float o = (g[i][k] - zv[i][k] * inner) * oscale;
           if (dz) dz[(row0 + i) * H + e] = o;
           dzb[(row0 + i) * H + e] = __float2bfloat16(o);
           cs[k] += o;
@@ -711,7 +722,7 @@ static bool tc_mlp_supported(int E, int H) { return (E % 8 == 0) && (H % 8 == 0)
 
 int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t R, int E,
                int H, float* h1, float* z, float* y, __nv_bfloat16* y_bf16, const __nv_bfloat16* x_bf16,
-               const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16, __nv_bfloat16* h1_bf16, void* ws,
+               const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16, __nv_bfloat16* h1_bf16, float* inv_norm, void* ws,
                size_t ws_bytes, cudaStream_t s) {
   if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0 (E=%d H=%d)", E, H); return TT_ERR_UNSUPPORTED; }
   const TcMlpPlan plan = plan_tc_mlp(R, E, H);
@@ -734,7 +745,8 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
   // so large enough) h1 buffer itself -- TT_PREC_BF16 treats h1 as opaque saved state.
   h1b = h1_bf16 ? h1_bf16 : reinterpret_cast<__nv_bfloat16*>(h1);
   if (tc_mlp_fused_supported(E, H))
-    return tc_mlp_fwd_fused(xa, w1a, b1, w2a, b2, R, E, H, h1b, z, y, y_bf16, s);
+    return tc_mlp_fwd_fused(xa, w1a, b1, w2a, b2, R, E, H, h1b, z, y, y_bf16, inv_norm, s);
+  if (z == nullptr) z = w.take<float>((size_t)R * H);     // unfused shapes: the pre-normalise tensor lives in the workspace
   tc::TcGemm g{};
   g.M = (int)R; g.N = H; g.K = E; g.A = xa; g.a_mn = 0; g.B = w1a; g.b_mn = 0;
   g.C = nullptr; g.Cb = h1b; g.ldc = H; g.bias = b1; g.act = 1;
@@ -743,7 +755,7 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
   g.M = (int)R; g.N = H; g.K = H; g.A = h1b; g.a_mn = 0; g.B = w2a; g.b_mn = 0;
   g.C = z; g.ldc = H; g.bias = b2;
   rc = tc::tc_gemm(g, s); if (rc) return rc;
-  tc::l2norm_fwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(z, R, H, y, y_bf16);
+  tc::l2norm_fwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(z, R, H, y, y_bf16, inv_norm);
   TT_LAUNCH_CHECK("l2norm_fwd_bf16_kernel");
   return TT_OK;
 }
@@ -751,8 +763,8 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
 int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1, const float* z,
                int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2, float* db2,
                const __nv_bfloat16* x_bf16, const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16,
-               const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed, void* ws,
-               size_t ws_bytes, cudaStream_t s) {
+               const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed,
+               const __nv_bfloat16* y_bf16, const float* inv_norm, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0"); return TT_ERR_UNSUPPORTED; }
   if (embed && (embed->V % 8 != 0 || E % 4 != 0)) { set_error("tc_mlp_bwd: embed needs V %% 8 == 0 and E %% 4 == 0"); return TT_ERR_UNSUPPORTED; }
   if (dy_parts < 1) dy_parts = 1;
@@ -787,14 +799,14 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   const int nblk2 = (int)ceil_div(R, tc::kNormRowsPerBlock);
   if (fused_cs) {
     // fp32 dz is not needed: db2 comes from cs2
-    if (H <= 256)
-      TT_CUDA(launch_kernel(tc::l2norm_bwd_colsum_kernel<8>, dim3((unsigned)nblk2), dim3(512), 0, s, true, dy, dy_parts, dy_part_stride, z, R, H,
-                            (float*)nullptr, dzb, cs2));
-    else
-      TT_CUDA(launch_kernel(tc::l2norm_bwd_colsum_kernel<16>, dim3((unsigned)nblk2), dim3(512), 0, s, true, dy, dy_parts, dy_part_stride, z, R, H,
-                            (float*)nullptr, dzb, cs2));
+    const bool from_y = y_bf16 != nullptr && inv_norm != nullptr;
+    auto kern = H <= 256 ? (from_y ? tc::l2norm_bwd_colsum_kernel<8, true> : tc::l2norm_bwd_colsum_kernel<8, false>)
+                         : (from_y ? tc::l2norm_bwd_colsum_kernel<16, true> : tc::l2norm_bwd_colsum_kernel<16, false>);
+    TT_CUDA(launch_kernel(kern, dim3((unsigned)nblk2), dim3(512), 0, s, true, dy, dy_parts, dy_part_stride, z, y_bf16, inv_norm, R, H,
+                          (float*)nullptr, dzb, cs2));
     TT_LAUNCH_CHECK("l2norm_bwd_colsum_kernel");
   } else {
+    if (z == nullptr) { set_error("tc_mlp_bwd: H > 512 needs z"); return TT_ERR_UNSUPPORTED; }
     tc::l2norm_bwd_bf16_kernel<<<(unsigned)ceil_div(R, 8), 256, 0, s>>>(dy, z, R, H, dz, dzb);
     TT_LAUNCH_CHECK("l2norm_bwd_bf16_kernel");
     rc = colsum(dz, R, H, H, db2, cpart, s); if (rc) return rc;

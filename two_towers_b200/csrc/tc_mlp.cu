@@ -31,11 +31,13 @@ struct MlpFwdParams {
   float* z;               // [R,H] nullable
   float* y;               // [R,H] nullable
   __nv_bfloat16* yb;      // [R,H] nullable
+  float* inv_norm;        // [R] nullable: 1 / max(|z|, 1e-12)
 };
 
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                  const __grid_constant__ CUtensorMap tmW2, const MlpFwdParams p) {
+                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmH1,
+                  const __grid_constant__ CUtensorMap tmY, const MlpFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
@@ -157,12 +159,18 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int ch = (c & 1) * 4 + u;
         const uint4 v = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
         *reinterpret_cast<uint4*>(hrow + ((ch ^ (lrow & 7)) << 4)) = v;
-        if (row_ok) *reinterpret_cast<uint4*>(p.h1b + row * H + c * 32 + u * 8) = v;
       }
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_h1);
+    if (lane == 0) {
+      mbar_arrive(bar_h1);
+      // the same swizzled tile GEMM 2 reads is also the source of the global h1 write: one TMA store per k-block of
+      // this warp's 32 rows (rows past R are clipped) instead of 1 KB-strided per-thread stores
+      for (int kb = 0; kb < kH; ++kb)
+        tma_store_2d(&tmH1, h1_tile + (uint32_t)kb * (MLP_BM * 128) + quarter * 4096, kb * 64, (int)m0 + quarter * 32);
+      tma_store_commit();
+    }
     // ---- epilogue 2: z = acc2 + b2; y = z / max(|z|, 1e-12) --------------------------------------------------
     mbar_wait(bar_acc2, 0);
     tc_fence_after();
@@ -178,14 +186,26 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
     const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (p.inv_norm && row_ok) p.inv_norm[row] = inv;
+    if (lane == 0) tma_store_wait_read();                        // this warp's rows of the hidden tile have been read out:
+    __syncwarp();                                                // they now stage the bf16 y tile for its TMA store
     for (int c = 0; c < H / 32; ++c) {
       uint32_t r[32];
       tmem_ld_x32(tmem_a2 + lane_addr + (uint32_t)(c * 32), r);
       tmem_ld_wait();
-      if (row_ok) {
-        float zv[32];
+      float zv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) zv[j] = __uint_as_float(r[j]) + bias_s[H + c * 32 + j];
+      for (int j = 0; j < 32; ++j) zv[j] = __uint_as_float(r[j]) + bias_s[H + c * 32 + j];
+      if (p.yb) {
+        uint8_t* yrow = h1_tile + (uint32_t)(c >> 1) * (MLP_BM * 128) + lrow * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint4 v = make_uint4(pack_bf16x2(zv[8 * u] * inv, zv[8 * u + 1] * inv), pack_bf16x2(zv[8 * u + 2] * inv, zv[8 * u + 3] * inv),
+                                     pack_bf16x2(zv[8 * u + 4] * inv, zv[8 * u + 5] * inv), pack_bf16x2(zv[8 * u + 6] * inv, zv[8 * u + 7] * inv));
+          *reinterpret_cast<uint4*>(yrow + ((((c & 1) * 4 + u) ^ (lrow & 7)) << 4)) = v;
+        }
+      }
+      if (row_ok) {
         if (p.z) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -197,16 +217,18 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             *reinterpret_cast<float4*>(p.y + row * H + c * 32 + j) =
                 make_float4(zv[j] * inv, zv[j + 1] * inv, zv[j + 2] * inv, zv[j + 3] * inv);
         }
-        if (p.yb) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint4 v = make_uint4(pack_bf16x2(zv[8 * u] * inv, zv[8 * u + 1] * inv), pack_bf16x2(zv[8 * u + 2] * inv, zv[8 * u + 3] * inv),
-                                       pack_bf16x2(zv[8 * u + 4] * inv, zv[8 * u + 5] * inv), pack_bf16x2(zv[8 * u + 6] * inv, zv[8 * u + 7] * inv));
-            *reinterpret_cast<uint4*>(p.yb + row * H + c * 32 + u * 8) = v;
-          }
-        }
       }
     }
+    if (p.yb) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        for (int kb = 0; kb < kH; ++kb)
+          tma_store_2d(&tmY, h1_tile + (uint32_t)kb * (MLP_BM * 128) + quarter * 4096, kb * 64, (int)m0 + quarter * 32);
+        tma_store_commit();
+      }
+    }
+    if (lane == 0) tma_store_wait();                             // smem stays valid until every bulk store has completed
   }
   tc_fence_before();
   __syncthreads();
@@ -231,16 +253,18 @@ bool tc_mlp_fused_supported(int E, int H) {
 
 int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const float* b1, const __nv_bfloat16* w2b,
                      const float* b2, int64_t R, int E, int H, __nv_bfloat16* h1b, float* z, float* y,
-                     __nv_bfloat16* yb, cudaStream_t s) {
-  CUtensorMap tmX, tmW1, tmW2;
+                     __nv_bfloat16* yb, float* inv_norm, cudaStream_t s) {
+  CUtensorMap tmX, tmW1, tmW2, tmH1, tmY;
   int rc = tc::make_tmap_bf16(&tmX, xb, (uint64_t)R, (uint64_t)E, tc::MLP_BM); if (rc) return rc;
   rc = tc::make_tmap_bf16(&tmW1, w1b, (uint64_t)H, (uint64_t)E, (uint32_t)H); if (rc) return rc;
   rc = tc::make_tmap_bf16(&tmW2, w2b, (uint64_t)H, (uint64_t)H, (uint32_t)H); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmH1, h1b, (uint64_t)R, (uint64_t)H, 32); if (rc) return rc;          // store maps: 32-row boxes (one warp)
+  rc = tc::make_tmap_bf16(&tmY, yb ? yb : h1b, (uint64_t)R, (uint64_t)H, 32); if (rc) return rc;
   tc::MlpFwdParams p{};
-  p.R = R; p.E = E; p.H = H; p.b1 = b1; p.b2 = b2; p.h1b = h1b; p.z = z; p.y = y; p.yb = yb;
+  p.R = R; p.E = E; p.H = H; p.b1 = b1; p.b2 = b2; p.h1b = h1b; p.z = z; p.y = y; p.yb = yb; p.inv_norm = inv_norm;
   const size_t smem = tc::mlp_fused_smem(E, H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TT_CUDA(launch_kernel(tc::tc_mlp_fwd_kernel, dim3((unsigned)ceil_div(R, tc::MLP_BM)), dim3(tc::MLP_THREADS), smem, s, true, tmX, tmW1, tmW2, p));
+  TT_CUDA(launch_kernel(tc::tc_mlp_fwd_kernel, dim3((unsigned)ceil_div(R, tc::MLP_BM)), dim3(tc::MLP_THREADS), smem, s, true, tmX, tmW1, tmW2, tmH1, tmY, p));
   TT_LAUNCH_CHECK("tc_mlp_fwd_kernel");
   return TT_OK;
 }

@@ -253,17 +253,19 @@ size_t tt_mlp_workspace(int64_t R, int E, int H, int precision) {
 
 int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                int64_t R, int E, int H, float* h1, float* z, float* y, void* y_bf16, const void* x_bf16,
-               const void* w1_bf16, const void* w2_bf16, void* h1_bf16, int precision,
+               const void* w1_bf16, const void* w2_bf16, void* h1_bf16, float* inv_norm, int precision,
                void* workspace, size_t workspace_bytes, void* stream) {
   TT_REQUIRE_DEVICE();
-  TT_CHECK_ARG(x && w1 && b1 && w2 && b2 && h1 && z && R >= 0 && E > 0 && H > 0, "mlp_fwd: bad arguments");
+  TT_CHECK_ARG(x && w1 && b1 && w2 && b2 && h1 && R >= 0 && E > 0 && H > 0, "mlp_fwd: bad arguments");
+  TT_CHECK_ARG(z || (precision == TT_PREC_BF16 && y_bf16 && inv_norm), "mlp_fwd: z may be null only in TT_PREC_BF16 with y_bf16 and inv_norm given");
+  TT_CHECK_ARG(inv_norm == nullptr || precision == TT_PREC_BF16, "mlp_fwd: inv_norm is a TT_PREC_BF16 output");
   TT_CHECK_ARG(y || (precision == TT_PREC_BF16 && y_bf16), "mlp_fwd: y may be null only in TT_PREC_BF16 with y_bf16 given");
   TT_CHECK_ARG(R < (1ll << 31), "mlp_fwd: R too large");
   if (R == 0) return TT_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == TT_PREC_BF16)
     return tt::tc_mlp_fwd(x, w1, b1, w2, b2, R, E, H, h1, z, y, (__nv_bfloat16*)y_bf16, (const __nv_bfloat16*)x_bf16,
-                          (const __nv_bfloat16*)w1_bf16, (const __nv_bfloat16*)w2_bf16, (__nv_bfloat16*)h1_bf16,
+                          (const __nv_bfloat16*)w1_bf16, (const __nv_bfloat16*)w2_bf16, (__nv_bfloat16*)h1_bf16, inv_norm,
                           workspace, workspace_bytes, s);
   TT_CHECK_ARG(precision == TT_PREC_FP32, "mlp_fwd: unknown precision %d", precision);
   return tt::mlp_fwd_fp32(x, w1, b1, w2, b2, R, E, H, h1, z, y, (__nv_bfloat16*)y_bf16, workspace, workspace_bytes, s);
@@ -272,11 +274,12 @@ int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
 int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1,
                const float* z, int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2,
                float* db2, const void* x_bf16, const void* w1_bf16, const void* w2_bf16, const void* h1_bf16,
-               int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed, int precision, void* workspace,
-               size_t workspace_bytes, void* stream) {
+               int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed, const void* y_bf16,
+               const float* inv_norm, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   TT_REQUIRE_DEVICE();
-  TT_CHECK_ARG(dy && x && w1 && w2 && h1 && z && dw1 && db1 && dw2 && db2 && R > 0 && E > 0 && H > 0,
+  TT_CHECK_ARG(dy && x && w1 && w2 && h1 && dw1 && db1 && dw2 && db2 && R > 0 && E > 0 && H > 0,
                "mlp_bwd: bad arguments");
+  TT_CHECK_ARG(z || (precision == TT_PREC_BF16 && y_bf16 && inv_norm), "mlp_bwd: z may be null only in TT_PREC_BF16 with y_bf16 and inv_norm given");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == TT_PREC_BF16) {
     if (embed) {
@@ -285,7 +288,7 @@ int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
     }
     return tt::tc_mlp_bwd(dy, x, w1, w2, h1, z, R, E, H, dx, dw1, db1, dw2, db2, (const __nv_bfloat16*)x_bf16,
                           (const __nv_bfloat16*)w1_bf16, (const __nv_bfloat16*)w2_bf16, (const __nv_bfloat16*)h1_bf16,
-                          dy_parts, dy_part_stride, embed, workspace, workspace_bytes, s);
+                          dy_parts, dy_part_stride, embed, (const __nv_bfloat16*)y_bf16, inv_norm, workspace, workspace_bytes, s);
   }
   TT_CHECK_ARG(embed == nullptr, "mlp_bwd: embed is a TT_PREC_BF16 feature");
   TT_CHECK_ARG(precision == TT_PREC_FP32, "mlp_bwd: unknown precision %d", precision);

@@ -134,6 +134,7 @@ class FusedTrainer:
                 raise TypeError(f"FusedTrainer: unsupported tower {type(tower).__name__}")
         bf = self.prec == _lib.TT_PREC_BF16
         self.pooled_bf16 = torch.empty(R, self.E, dtype=torch.bfloat16, device=self.dev) if bf else None
+        self.inv_norm = torch.empty(R, **f32) if bf else None
         self.y_bf16 = torch.empty(R, self.H, dtype=torch.bfloat16, device=self.dev) if bf else None
         # bf16 shadow of the flat parameter buffer, refreshed by the AdamW kernel -> the tensor-core GEMMs
         # read weights without any per-step conversion kernel
@@ -182,10 +183,14 @@ class FusedTrainer:
         xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
-            y_ptr = None if ((self.dy_parts > 1 or self.global_fast) and yb is not None) else y   # fp32 y unused on the pure bf16 path
+            pure = (self.dy_parts > 1 or self.global_fast) and yb is not None
+            y_ptr = None if pure else y                     # fp32 y unused on the pure bf16 path
+            # pure bf16 path: the normalise step is saved as (y_bf16, 1/|z|); the fp32 pre-normalise tensor is never written
+            inv = self.inv_norm[r0:r0 + nr] if (pure and self.H <= 512) else None
+            z_ptr = None if inv is not None else sv["z"]
             check(lib.tt_mlp_fwd(_p(x), _p(l1.weight), _p(l1.bias), _p(l2.weight), _p(l2.bias), nr, self.E, self.H,
-                                 _p(sv["h1"]), _p(sv["z"]), _p(y_ptr), _p(yb), _p(xb), _p(self._shadow(l1.weight)),
-                                 _p(self._shadow(l2.weight)), _p(self.h1_bf16[gi]), self.prec, _p(self.ws),
+                                 _p(sv["h1"]), _p(z_ptr), _p(y_ptr), _p(yb), _p(xb), _p(self._shadow(l1.weight)),
+                                 _p(self._shadow(l2.weight)), _p(self.h1_bf16[gi]), _p(inv), self.prec, _p(self.ws),
                                  self.ws.numel(), s), "tt_mlp_fwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
@@ -209,12 +214,15 @@ class FusedTrainer:
             dx = None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
-            check(lib.tt_mlp_bwd(_p(dy), _p(x), _p(l1.weight), _p(l2.weight), _p(sv["h1"]), _p(sv["z"]), nr, self.E,
+            yb = self.y_bf16[r0:r0 + nr] if self.y_bf16 is not None else None
+            pure = (self.dy_parts > 1 or self.global_fast) and yb is not None and self.H <= 512
+            inv = self.inv_norm[r0:r0 + nr] if pure else None
+            check(lib.tt_mlp_bwd(_p(dy), _p(x), _p(l1.weight), _p(l2.weight), _p(sv["h1"]), _p(None if pure else sv["z"]), nr, self.E,
                                  self.H, _p(dx), _p(l1.weight.grad), _p(l1.bias.grad), _p(l2.weight.grad),
                                  _p(l2.bias.grad), _p(xb), _p(self._shadow(l1.weight)), _p(self._shadow(l2.weight)),
                                  _p(self.h1_bf16[gi]), self.dy_parts, self.dy_part_stride,
-                                 C.byref(emb) if emb is not None else None, self.prec, _p(self.ws),
-                                 self.ws.numel(), s), "tt_mlp_bwd")
+                                 C.byref(emb) if emb is not None else None, _p(yb if pure else None), _p(inv),
+                                 self.prec, _p(self.ws), self.ws.numel(), s), "tt_mlp_bwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
             check(lib.tt_proj_ln_bwd(_p(dy), _p(x), _p(lin.weight), _p(ln.weight), _p(sv["a"]), _p(sv["stats"]),

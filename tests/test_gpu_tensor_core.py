@@ -87,6 +87,75 @@ def test_mlp_bf16_vs_oracle(R, E, H):
     assert torch.equal(dx, dx2) and torch.equal(dw1, dw1b) and torch.equal(dw2, dw2b)
 
 
+@pytest.mark.parametrize("R,L,V,E,H", [(8192, 64, 128, 64, 256), (300, 20, 64, 64, 128), (1000, 33, 200, 64, 256), (260, 16, 1024, 128, 64)])
+def test_embed_fused_tower_backward(R, L, V, E, H):
+    """Trainer fast path: pooling matrix P from the forward (x = P table), normalise step saved as (y_bf16, 1/|z|),
+    backward through M = P^T da1.  Checked against the fp64 oracle of the SAME chain
+    (encoders.py:62-77 mean pool + MLP + normalise; embedding_dense_backward) and against the generic bf16 path."""
+    import ctypes as C
+    import two_towers_b200 as tt
+    from two_towers_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(R + V)
+    ids = rng.integers(0, V, size=(R, L))
+    ids[rng.random((R, L)) < 0.2] = 0                       # padding
+    ids[0] = 0                                              # an all-padding row
+    table = (rng.standard_normal((V, E)) * 0.5).astype(np.float32)
+    _, w1, b1, w2, b2, dy = _mlp_case(R, E, H, R + E + H)
+    t = lambda a: torch.tensor(a, device=DEV)
+    tids, ttab = t(ids), t(table)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    pt = lambda x: None if x is None else x.data_ptr()
+    f32 = dict(dtype=torch.float32, device=DEV)
+    pooled = torch.empty(R, E, **f32); inv_len = torch.empty(R, **f32)
+    pooled_b = torch.empty(R, E, dtype=torch.bfloat16, device=DEV); P = torch.empty(R, V, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.tt_embed_pool_fwd(pt(tids), 8, pt(ttab), R, L, V, E, pt(pooled), pt(inv_len), pt(pooled_b), pt(P), s), "fwd")
+    # P is counts / len, exact up to bf16 rounding
+    cnt = np.stack([np.bincount(r[r > 0], minlength=V) for r in ids]).astype(np.float64)
+    cnt[:, 0] = 0
+    rP = cnt / (cnt.sum(1, keepdims=True) + 1e-9)
+    close(P, rP, 2.0 ** -8, "pooling matrix")
+    close(pooled, rP @ table.astype(np.float64), 1e-5, "pooled")
+    # forward with the compact saved state
+    tw1, tb1, tw2, tb2, tdy = t(w1), t(b1), t(w2), t(b2), t(dy)
+    h1 = torch.empty(R, H, **f32); yb = torch.empty(R, H, dtype=torch.bfloat16, device=DEV); inv = torch.empty(R, **f32)
+    ws = torch.empty(int(lib.tt_mlp_workspace(R, E, H, 1)), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.tt_mlp_fwd(pt(pooled), pt(tw1), pt(tb1), pt(tw2), pt(tb2), R, E, H, pt(h1), None, None, pt(yb), pt(pooled_b),
+                              None, None, None, pt(inv), 1, pt(ws), ws.numel(), s), "mlp_fwd")
+    f = np.float64
+    x64 = rP @ table.astype(f)
+    a1 = x64 @ w1.astype(f).T + b1
+    rz = np.maximum(a1, 0) @ w2.astype(f).T + b2
+    close(yb, O.normalize(rz), BF16_RTOL, "y_bf16")
+    close(inv, 1.0 / np.maximum(np.linalg.norm(rz, axis=1), 1e-12), BF16_RTOL, "inv_norm")
+    # backward, embed-fused
+    dw1 = torch.empty(H, E, **f32); db1 = torch.empty(H, **f32); dw2 = torch.empty(H, H, **f32); db2 = torch.empty(H, **f32)
+    dtab = torch.full((V, E), 7.0, **f32)
+    ews = torch.empty(int(lib.tt_mlp_embed_workspace(V, H, R)), dtype=torch.uint8, device=DEV)
+    emb = _lib.MlpEmbed(pt(P), V, pt(ttab), pt(dtab), 0, pt(ews), ews.numel())
+    def run_bwd():
+        _lib.check(lib.tt_mlp_bwd(pt(tdy), pt(pooled), pt(tw1), pt(tw2), pt(h1), None, R, E, H, None, pt(dw1), pt(db1), pt(dw2),
+                                  pt(db2), pt(pooled_b), None, None, None, 1, 0, C.byref(emb), pt(yb), pt(inv), 1, pt(ws),
+                                  ws.numel(), s), "mlp_bwd")
+        torch.cuda.synchronize()
+    run_bwd()
+    dz = O.normalize_bwd(dy.astype(f), rz)
+    mask = h1.view(torch.bfloat16).reshape(-1)[:R * H].reshape(R, H).float().cpu().numpy() > 0
+    da1 = (dz @ w2.astype(f)) * mask
+    close(dw2, dz.T @ np.maximum(a1, 0), BF16_RTOL, "dw2"); close(db2, dz.sum(0), BF16_RTOL, "db2")
+    close(db1, da1.sum(0), BF16_RTOL, "db1")
+    close(dw1, da1.T @ x64, BF16_RTOL, "dw1 (via M^T table)")
+    rdtab = rP.T @ (da1 @ w1.astype(f))
+    close(dtab, rdtab, BF16_RTOL, "d_table (via M w1)")
+    assert float(dtab[0].abs().max()) == 0.0                 # padding row
+    keep = (dw1.clone(), dtab.clone())
+    run_bwd()
+    assert torch.equal(dw1, keep[0]) and torch.equal(dtab, keep[1])          # bitwise reproducible
+    emb.accumulate = 1
+    run_bwd()
+    close(dtab, 2 * rdtab, BF16_RTOL, "d_table accumulate")
+
+
 @pytest.mark.parametrize("Bq,Bd,H,off,temp", [(128, 128, 256, 0, 0.1), (64, 64, 64, 0, 0.1), (100, 257, 64, 57, 0.05),
                                               (257, 300, 128, 3, 1.0), (1024, 1024, 256, 0, 0.1), (4096, 4096, 256, 0, 0.1),
                                               (96, 768, 256, 96 * 3, 0.1), (200, 200, 192, 0, 0.1), (50, 50, 24, 0, 0.1)])

@@ -88,6 +88,9 @@ int tt_embed_pool_bwd(const void* ids, int id_bytes, const float* inv_len, const
  * inv_norm (TT_PREC_BF16, nullable) [R]: tt_mlp_fwd also stores 1 / max(||z||, 1e-12); with y_bf16 AND inv_norm the
  *   normalise step is fully described by them -- fwd may then be given z == NULL (8 bytes/element less to write) and
  *   bwd, given the same y_bf16 / inv_norm, ignores z:  dz = (dy - y (y . dy)) * inv_norm.
+ * dz_bf16 + dz_colsum (TT_PREC_BF16, nullable): the normalise backward has already been done by the loss kernel
+ *   (tt_ce_pass_t.dz_bf16): dz [R,H] bf16 and its per-32-row column sums [ceil(R/32),H]; dy, z, y_bf16, inv_norm are
+ *   then ignored (may be null).
  * embed (TT_PREC_BF16, nullable): x is the mean-pooled lookup embedding x = P * table (P from tt_embed_pool_fwd).
  *   The backward then forms M = P^T da1 [V,H] once on the tensor cores and finishes with two tiny products,
  *   dw1 = M^T table and d_table = M w1 (+= when accumulate != 0), instead of computing dx [R,E], dw1 = da1^T x and
@@ -112,7 +115,7 @@ int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
                float* dx, float* dw1, float* db1, float* dw2, float* db2,
                const void* x_bf16, const void* w1_bf16, const void* w2_bf16, const void* h1_bf16,
                int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed,
-               const void* y_bf16, const float* inv_norm,
+               const void* y_bf16, const float* inv_norm, const void* dz_bf16, const float* dz_colsum,
                int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K3': avg_pool tower projection  Linear(E,H) -> Dropout(p) -> LayerNorm(H) -> normalise -
@@ -182,6 +185,11 @@ typedef struct {
   int64_t y_buf_rows, y_blk, y_blk_stride, y_blk_off;
   const float* lse; int64_t label_offset;
   float* out_parts; int64_t part_stride;
+  /* Fused normalise backward (all three or none; needs nparts <= 2, see tt_inbatch_ce_bwd_fused_ok): x is the unit-norm
+   * output y = z / |z| of tt_mlp_fwd and inv_norm its 1/|z|.  Instead of gradient slices the launch then writes
+   *   dz_bf16 [x_rows,H] = (dy - y (y . dy)) * inv_norm  and  dz_colsum [ceil(x_rows/32), H] (per-32-row column sums),
+   * exactly what tt_mlp_bwd(dz_bf16 = ..., dz_colsum = ...) consumes; out_parts is ignored. */
+  void* dz_bf16; float* dz_colsum; const float* inv_norm;
 } tt_ce_pass_t;
 size_t tt_inbatch_ce_fwd_ex_workspace(int64_t Bq, int64_t Bd);
 int tt_inbatch_ce_fwd_ex(const void* q_bf16, int64_t Bq, const void* d_bf16, int64_t Bd, int64_t d_buf_rows,
@@ -193,6 +201,8 @@ int tt_inbatch_ce_fwd_ex(const void* q_bf16, int64_t Bq, const void* d_bf16, int
  * same launch (the last CTA of each row tile merges its splits, fixed order); without it a second launch does. */
 size_t tt_inbatch_ce_sync_bytes(int64_t Bq);
 int tt_inbatch_ce_bwd_nparts_ex(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_rows, int64_t d_y_rows, int H);
+/* 1 when tt_inbatch_ce_bwd_parts_ex can run the fused normalise backward for these shapes (<= 2 splits). */
+int tt_inbatch_ce_bwd_fused_ok(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_rows, int64_t d_y_rows, int H);
 int tt_inbatch_ce_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temperature,
                                float loss_scale, const float* grad_out, int nparts, void* stream);
 int tt_inbatch_ce_bwd_parts(const void* q_bf16, const void* d_bf16, const float* lse, int64_t Bq, int64_t Bd,

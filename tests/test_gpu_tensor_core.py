@@ -212,6 +212,57 @@ def test_inbatch_fwd_in_kernel_finalisation(Bq, Bd, H, off):
     assert l1 == l2 and p1 == p2 and torch.equal(lse1, lse2)
 
 
+@pytest.mark.parametrize("Bq,Bd,H,off", [(4096, 4096, 256, 0), (8192, 8192, 256, 0), (2048, 4096, 128, 2048), (4000, 4000, 64, 0),
+                                         (4096, 8192, 256, 4096)])
+def test_inbatch_bwd_fused_normalise(Bq, Bd, H, off):
+    """Loss backward fused with the normalise backward (CTA pairs exchange accumulator halves through distributed
+    shared memory) against the unfused chain: slices -> sum -> dz = (dy - y (y.dy)) / |z| in fp64."""
+    import ctypes as C
+    import two_towers_b200 as tt
+    from two_towers_b200 import _lib
+    lib = _lib.load()
+    if not lib.tt_inbatch_ce_bwd_fused_ok(Bq, Bd, Bd, Bq, H):
+        pytest.skip("more than two splits for this shape")
+    torch.manual_seed(Bq + H)
+    zq = torch.randn(Bq, H, device=DEV) * 3.0; zd = torch.randn(Bd, H, device=DEV) * 0.5
+    q = tt.ops.cast_bf16(torch.nn.functional.normalize(zq, dim=-1)); d = tt.ops.cast_bf16(torch.nn.functional.normalize(zd, dim=-1))
+    invq = (1.0 / zq.norm(dim=-1)).contiguous(); invd = (1.0 / zd.norm(dim=-1)).contiguous()
+    loss, lse, _ = tt.ops.inbatch_ce_fwd(q.float(), d.float(), 0.1, off, precision="bf16")
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: None if t is None else t.data_ptr()
+    n = int(lib.tt_inbatch_ce_bwd_nparts_ex(Bq, Bd, Bd, Bq, H))
+    # reference: unfused slices
+    pq_ = torch.zeros(n, Bq, H, device=DEV); pd_ = torch.zeros(n, Bd, H, device=DEV)
+    lse_col = torch.full((Bd,), float("inf"), device=DEV)     # d pass: positives only for documents off .. off+Bq
+    # the d pass scores documents (x) against queries (y); lse is indexed by query
+    qp = _lib.CePass(vp(q), Bq, vp(d), Bd, Bd, Bd, 0, 0, vp(lse), off, vp(pq_), Bq * H, None, None, None)
+    dp = _lib.CePass(vp(d), Bd, vp(q), Bq, Bq, Bq, 0, 0, vp(lse), -off, vp(pd_), Bd * H, None, None, None)
+    _lib.check(lib.tt_inbatch_ce_bwd_parts_ex(C.byref(qp), C.byref(dp), H, 10.0, 1.0 / Bq, None, n, s), "parts")
+    dq = pq_.sum(0).double().cpu().numpy(); dd = pd_.sum(0).double().cpu().numpy()
+    def ref_dz(dy, y, inv):
+        y = y.float().double().cpu().numpy(); inv = inv.double().cpu().numpy()
+        return (dy - y * (y * dy).sum(1, keepdims=True)) * inv[:, None]
+    rq, rd = ref_dz(dq, q, invq), ref_dz(dd, d, invd)
+    # fused
+    dzq = torch.zeros(Bq, H, dtype=torch.bfloat16, device=DEV); dzd = torch.zeros(Bd, H, dtype=torch.bfloat16, device=DEV)
+    csq = torch.zeros((Bq + 31) // 32, H, device=DEV); csd = torch.zeros((Bd + 31) // 32, H, device=DEV)
+    qf = _lib.CePass(vp(q), Bq, vp(d), Bd, Bd, Bd, 0, 0, vp(lse), off, None, 0, vp(dzq), vp(csq), vp(invq))
+    df = _lib.CePass(vp(d), Bd, vp(q), Bq, Bq, Bq, 0, 0, vp(lse), -off, None, 0, vp(dzd), vp(csd), vp(invd))
+    for _ in range(2):
+        _lib.check(lib.tt_inbatch_ce_bwd_parts_ex(C.byref(qf), C.byref(df), H, 10.0, 1.0 / Bq, None, n, s), "fused")
+    torch.cuda.synchronize()
+    close(dzq, rq, 1e-2, "dz (queries)"); close(dzd, rd, 1e-2, "dz (documents)")
+    def ref_cs(dz, rows):
+        pad = (-rows) % 32
+        a = np.concatenate([dz, np.zeros((pad, dz.shape[1]))]) if pad else dz
+        return a.reshape(-1, 32, dz.shape[1]).sum(1)
+    close(csq, ref_cs(rq, Bq), 2e-2, "column sums (queries)"); close(csd, ref_cs(rd, Bd), 2e-2, "column sums (documents)")
+    keep = (dzq.clone(), csd.clone())
+    _lib.check(lib.tt_inbatch_ce_bwd_parts_ex(C.byref(qf), C.byref(df), H, 10.0, 1.0 / Bq, None, n, s), "fused")
+    torch.cuda.synchronize()
+    assert torch.equal(dzq, keep[0]) and torch.equal(csd, keep[1])
+
+
 def test_inbatch_bf16_full_size_known_answers():
     import two_towers_b200 as tt
     B, H = 4096, 256

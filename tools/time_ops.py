@@ -67,11 +67,8 @@ def main():
     ops = {
         "embed_pool_fwd": lambda: check(lib.tt_embed_pool_fwd(_p(tr.ids), 8, _p(tr.table), R, tr.L, tr.V, tr.E, _p(tr.pooled), _p(tr.inv_len), _p(tr.pooled_bf16), _p(tr.pool_bf16), s()), "x"),
         "tower_fwd": lambda: tr._tower_fwd(0),
-        "ce_fwd": (lambda: check(lib.tt_inbatch_ce_fwd_ex(_p(qb), B, _p(db), B, B, B, 0, 0, H, 10.0, 0, 1.0 / B, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), _p(tr.ce_ws), tr.ce_ws.numel(), _p(tr.ce_sync), s()), "x"))
-                  if getattr(tr, "local_fast", False) else lambda: check(lib.tt_inbatch_ce_fwd(_p(qf), _p(df), _p(qb), _p(db), B, B, H, 10.0, 0, 1.0 / B, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), tr.prec, _p(tr.ws), tr.ws.numel(), s()), "x"),
-        "ce_bwd": (lambda: check(lib.tt_inbatch_ce_bwd_parts(_p(qb), _p(db), _p(tr.lse), B, B, H, 10.0, 0, 1.0 / B, None, _p(tr.dy[:B]), tr.dy_part_stride, _p(tr.dy[B:2 * B]), tr.dy_part_stride, s()), "x"))
-                  if tr.dy_parts > 1 else
-                  (lambda: check(lib.tt_inbatch_ce_bwd(_p(qf), _p(df), _p(qb), _p(db), _p(tr.lse), B, B, H, 10.0, 0, 1.0 / B, None, _p(tr.dy[:B]), _p(tr.dy[B:2 * B]), tr.prec, _p(tr.ws), tr.ws.numel(), s()), "x")),
+        "ce_fwd": lambda: tr._local_loss_fwd(s()),
+        "ce_bwd": lambda: tr._local_loss_bwd(s()),
         "tower_bwd": lambda: tr._tower_bwd(0),
         "embed_pool_bwd": lambda: check(lib.tt_embed_pool_bwd(_p(tr.ids), 8, _p(tr.inv_len), _p(tr.dpooled), R, tr.L, tr.V, tr.E, _p(tr.table.grad), _p(tr.ws), tr.ws.numel(), s()), "x"),
         "adamw": lambda: check(lib.tt_adamw_step(_p(tr.flat), _p(tr.flat_grad), _p(tr.exp_avg), _p(tr.exp_avg_sq), tr.n_params, 1e-3, 0.9, 0.999, 1e-8, 0.01, _p(tr.step_count), _p(tr.flat_bf16), s()), "x"),

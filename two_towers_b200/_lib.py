@@ -30,7 +30,7 @@ SIGNATURES = {
     "tt_embed_pool_bwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _i64, _i, _vp, _vp, _sz, _vp]),
     "tt_mlp_workspace": (_sz, [_i64, _i, _i, _i]),
     "tt_mlp_fwd": (_i, [_vp] * 5 + [_i64, _i, _i] + [_vp] * 9 + [_i, _vp, _sz, _vp]),
-    "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 9 + [_i, _i64, _vp, _vp, _vp] + [_i, _vp, _sz, _vp]),
+    "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 9 + [_i, _i64, _vp, _vp, _vp, _vp, _vp] + [_i, _vp, _sz, _vp]),
     "tt_mlp_embed_workspace": (_sz, [_i64, _i, _i64]),
     "tt_proj_ln_workspace": (_sz, [_i64, _i, _i]),
     "tt_proj_ln_fwd": (_i, [_vp] * 5 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 4 + [_vp, _sz, _vp]),
@@ -62,13 +62,14 @@ class CePass(C.Structure):
     """tt_ce_pass_t (include/tt_b200.h)"""
     _fields_ = [("x_bf16", _vp), ("x_rows", _i64), ("y_bf16", _vp), ("y_rows", _i64), ("y_buf_rows", _i64),
                 ("y_blk", _i64), ("y_blk_stride", _i64), ("y_blk_off", _i64), ("lse", _vp), ("label_offset", _i64),
-                ("out_parts", _vp), ("part_stride", _i64)]
+                ("out_parts", _vp), ("part_stride", _i64), ("dz_bf16", _vp), ("dz_colsum", _vp), ("inv_norm", _vp)]
 
 
 SIGNATURES.update({
     "tt_inbatch_ce_fwd_ex_workspace": (_sz, [_i64, _i64]),
     "tt_inbatch_ce_fwd_ex": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i, _f, _i64, _f, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "tt_inbatch_ce_sync_bytes": (_sz, [_i64]),
+    "tt_inbatch_ce_bwd_fused_ok": (_i, [_i64, _i64, _i64, _i64, _i]),
     "tt_inbatch_ce_bwd_nparts_ex": (_i, [_i64, _i64, _i64, _i64, _i]),
     "tt_inbatch_ce_bwd_parts_ex": (_i, [C.POINTER(CePass), C.POINTER(CePass), _i, _f, _f, _vp, _i, _vp]),
 })

@@ -487,6 +487,11 @@ int tt_inbatch_ce_bwd_nparts_ex(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_
   return tt::tc_inbatch_bwd_nparts2(q_x_rows, q_y_rows, d_x_rows, d_y_rows, H);
 }
 
+int tt_inbatch_ce_bwd_fused_ok(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_rows, int64_t d_y_rows, int H) {
+  if (q_x_rows <= 0 || q_y_rows <= 0 || d_x_rows <= 0 || d_y_rows <= 0 || H <= 0 || H % 64 != 0 || H > 256) return 0;
+  return tt::tc_inbatch_bwd_nparts2(q_x_rows, q_y_rows, d_x_rows, d_y_rows, H) <= 2 ? 1 : 0;
+}
+
 int tt_inbatch_ce_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temperature,
                                float loss_scale, const float* grad_out, int nparts, void* stream) {
   TT_REQUIRE_DEVICE();

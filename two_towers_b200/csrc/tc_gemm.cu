@@ -764,7 +764,8 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
                int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2, float* db2,
                const __nv_bfloat16* x_bf16, const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16,
                const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed,
-               const __nv_bfloat16* y_bf16, const float* inv_norm, void* ws, size_t ws_bytes, cudaStream_t s) {
+               const __nv_bfloat16* y_bf16, const float* inv_norm, const __nv_bfloat16* dz_bf16, const float* dz_colsum,
+               void* ws, size_t ws_bytes, cudaStream_t s) {
   if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0"); return TT_ERR_UNSUPPORTED; }
   if (embed && (embed->V % 8 != 0 || E % 4 != 0)) { set_error("tc_mlp_bwd: embed needs V %% 8 == 0 and E %% 4 == 0"); return TT_ERR_UNSUPPORTED; }
   if (dy_parts < 1) dy_parts = 1;
@@ -797,7 +798,10 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   const __nv_bfloat16* h1a = h1_bf16 ? h1_bf16 : reinterpret_cast<const __nv_bfloat16*>(h1);   // see tc_mlp_fwd
   const bool fused_cs = H <= 512;
   const int nblk2 = (int)ceil_div(R, tc::kNormRowsPerBlock);
-  if (fused_cs) {
+  if (dz_bf16) {                                            // normalise backward already done by the loss kernel
+    dzb = const_cast<__nv_bfloat16*>(dz_bf16);
+    cs2 = const_cast<float*>(dz_colsum);
+  } else if (fused_cs) {
     // fp32 dz is not needed: db2 comes from cs2
     const bool from_y = y_bf16 != nullptr && inv_norm != nullptr;
     auto kern = H <= 256 ? (from_y ? tc::l2norm_bwd_colsum_kernel<8, true> : tc::l2norm_bwd_colsum_kernel<8, false>)

@@ -299,6 +299,12 @@ struct BwdParams {
   int tiles_per_split[2];      // Y tiles handled by one split
   float* out[2];               // [nsplit] slices (part_stride elements apart) or the final tensor
   int64_t part_stride[2];
+  // fused normalise-backward epilogue (optional, per pass): instead of fp32 slices the kernel finishes
+  //   dz = (dy - y (y . dy)) * inv_norm   with y = this CTA's X tile (the unit rows themselves), dy = sum of the splits,
+  // writes it as bf16 plus per-32-row column sums (-> bias gradient).  Needs <= 2 splits (CTA pair = cluster).
+  __nv_bfloat16* dz[2];        // [Bx, H] bf16 (null: write out[] slices as before)
+  float* dz_colsum[2];         // [ceil(Bx / 32), H]
+  const float* inv_norm[2];    // [Bx]
   int H;
   float inv_temp;
   const float* grad_out;       // nullable device scalar
@@ -350,6 +356,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   const int t_beg = blockIdx.y * tiles_per_split;
   const int t_end = min(ntiles, t_beg + tiles_per_split);
   const int nt = max(0, t_end - t_beg);
+  const bool fused = p.dz[PASS] != nullptr;               // CTA-uniform (cluster-uniform)
   long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (int)blockIdx.z == p.dbg_pass) ? p.dbg : nullptr;
 #define TT_STAMP(role, tile, slot) do { if (dbg) dbg[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); } while (0)
   // per-CTA wall-clock stamps (ns): kernel entry, X resident in TMEM, main loop done, outputs stored
@@ -561,7 +568,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     const int64_t row0 = x0 + quarter * 32;
     const int nrows = (int)min((int64_t)32, Bx - row0);
     float* orow = out + row0 * H + lane;
-    for (int cb = 0; cb < H / 32; ++cb) {
+    for (int cb = 0; cb < (fused ? 0 : H / 32); ++cb) {
       uint32_t q[32];
       if (nt > 0) {
         tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
@@ -587,6 +594,106 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       __syncwarp();
       if (threadIdx.x == 64) TT_STAMP(1, 32 + cb, 3);
     }
+    if (!fused) TT_CTA_STAMP(3);
+  }
+  if (fused) {
+    // ---- fused normalise backward.  The CTA pair (cluster) holds the two halves of dy = scale * (O_0 + O_1) in tensor
+    // memory.  Rank r finishes rows [64 r, 64 r + 64) of the tile: the other 64 rows of its accumulator travel to the
+    // peer's shared memory (the Y stages are idle now).  With a single split the CTA finishes all 128 rows itself.
+    const bool pair = gridDim.y == 2;
+    const uint32_t rank = pair ? cluster_ctarank() : 0u;
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int lrow = quarter * 32 + lane;
+    const float scale = p.coef * (p.grad_out ? *p.grad_out : 1.0f);
+    const int RS = H + 4;                                  // receive-buffer row stride (floats): conflict-free float4 rows, 64 rows fit the Y stages
+    float* recv = reinterpret_cast<float*>(y_tiles);       // [64][RS]
+    if (pair) cluster_sync_all();                          // both CTAs' tensor pipes have retired: every Y stage is free
+    const bool mine = !pair || (quarter >> 1) == (int)rank;   // this warp's rows are finished here
+    if (pair && warp >= 2 && !mine) {
+      const uint32_t dst = mapa_shared(smem_u32(recv), rank ^ 1u) + (uint32_t)((lrow & 63) * RS * 4);
+      for (int cb = 0; cb < H / 32; ++cb) {
+        uint32_t q[32];
+        if (nt > 0) {
+          tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) q[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          st_cluster_f4(dst + (uint32_t)((cb * 32 + j) * 4), __uint_as_float(q[j]), __uint_as_float(q[j + 1]),
+                        __uint_as_float(q[j + 2]), __uint_as_float(q[j + 3]));
+      }
+    }
+    if (pair) cluster_sync_all();                          // peer's half has landed
+    if (warp >= 2 && mine) {
+      const int64_t row = x0 + lrow;
+      const float inv = row < Bx ? __ldg(p.inv_norm[PASS] + row) : 0.f;
+      const float* rrow = recv + (lrow & 63) * RS;
+      // pass 1: y . dy  (y = this row of the X tile, bf16 pairs in tensor memory)
+      float dot = 0.f;
+      for (int cb = 0; cb < H / 32; ++cb) {
+        uint32_t q[32], xw[16];
+        if (nt > 0) tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
+        tmem_ld_x16(tmem_x + lane_addr + (uint32_t)(cb * 16), xw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pair) o = *reinterpret_cast<const float4*>(rrow + cb * 32 + j);
+          if (nt > 0) { o.x += __uint_as_float(q[j]); o.y += __uint_as_float(q[j + 1]); o.z += __uint_as_float(q[j + 2]); o.w += __uint_as_float(q[j + 3]); }
+          const uint32_t w0 = xw[j >> 1], w1 = xw[(j >> 1) + 1];
+          dot = fmaf(o.x, __uint_as_float(w0 << 16), dot); dot = fmaf(o.y, __uint_as_float(w0 & 0xffff0000u), dot);
+          dot = fmaf(o.z, __uint_as_float(w1 << 16), dot); dot = fmaf(o.w, __uint_as_float(w1 & 0xffff0000u), dot);
+        }
+      }
+      // pass 2: dz = (dy - y (y.dy)) * inv  ->  staged 32x32 per warp, then 4 rows x 64 B per store instruction
+      float* T = reinterpret_cast<float*>(p_tile + (warp - 2) * (32 * 36 * 4));
+      const int64_t row0 = x0 + quarter * 32;
+      const int nrows = (int)max((int64_t)0, min((int64_t)32, Bx - row0));
+      const float si = scale * inv;
+      const int cq = (lane & 7) * 4, rq = lane >> 3;
+      __nv_bfloat16* dzo = p.dz[PASS] + (row0 + rq) * H + cq;
+      float* cso = p.dz_colsum[PASS] + (row0 >> 5) * H + cq;
+      for (int cb = 0; cb < H / 32; ++cb) {
+        uint32_t q[32], xw[16];
+        if (nt > 0) tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
+        tmem_ld_x16(tmem_x + lane_addr + (uint32_t)(cb * 16), xw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pair) o = *reinterpret_cast<const float4*>(rrow + cb * 32 + j);
+          if (nt > 0) { o.x += __uint_as_float(q[j]); o.y += __uint_as_float(q[j + 1]); o.z += __uint_as_float(q[j + 2]); o.w += __uint_as_float(q[j + 3]); }
+          const uint32_t w0 = xw[j >> 1], w1 = xw[(j >> 1) + 1];
+          float4 d;
+          d.x = (o.x - __uint_as_float(w0 << 16) * dot) * si;          d.y = (o.y - __uint_as_float(w0 & 0xffff0000u) * dot) * si;
+          d.z = (o.z - __uint_as_float(w1 << 16) * dot) * si;          d.w = (o.w - __uint_as_float(w1 & 0xffff0000u) * dot) * si;
+          *reinterpret_cast<float4*>(&T[lane * 36 + j]) = d;
+        }
+        __syncwarp();
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const float4*>(&T[(4 * k + rq) * 36 + cq]);
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (4 * k + rq < nrows) {
+            cs.x += v[k].x; cs.y += v[k].y; cs.z += v[k].z; cs.w += v[k].w;
+            *reinterpret_cast<uint2*>(dzo + (int64_t)(4 * k) * H + cb * 32) = make_uint2(pack_bf16x2(v[k].x, v[k].y), pack_bf16x2(v[k].z, v[k].w));
+          }
+        }
+#pragma unroll
+        for (int d = 8; d <= 16; d <<= 1) {
+          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, d); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, d);
+          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, d); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, d);
+        }
+        if (rq == 0 && nrows > 0) *reinterpret_cast<float4*>(cso + cb * 32) = cs;
+        __syncwarp();
+      }
+    }
     TT_CTA_STAMP(3);
   }
   tc_fence_before();
@@ -601,7 +708,7 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
   pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   const int pass = blockIdx.z;
-  if ((int64_t)blockIdx.x * CE_BM >= p.Bx[pass] || p.out[pass] == nullptr) return;   // CTA-uniform: nothing to do for this pass
+  if ((int64_t)blockIdx.x * CE_BM >= p.Bx[pass] || (p.out[pass] == nullptr && p.dz[pass] == nullptr)) return;   // cluster-uniform: nothing to do for this pass
   if (pass == 0) ce_bwd_body<false>(&tmX0, &tmY0, p, base);
   else           ce_bwd_body<true>(&tmX1, &tmY1, p, base);
 }
@@ -722,6 +829,7 @@ struct CePass {                  // rows X receive gradients from all (logical) 
   const __nv_bfloat16* y; int64_t By, y_buf_rows, y_blk, y_blk_stride, y_blk_off;
   const float* lse; int64_t label_offset;
   float* out; int64_t part_stride;
+  __nv_bfloat16* dz; float* dz_colsum; const float* inv_norm;     // fused normalise backward (all or none)
 };
 
 static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_temp, int nsplit, const float* grad_out,
@@ -738,18 +846,30 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
     p.y_blk[k] = ps[k]->y_blk > 0 ? ps[k]->y_blk : 1; p.y_blk_stride[k] = ps[k]->y_blk_stride; p.y_blk_off[k] = ps[k]->y_blk_off;
     p.tiles_per_split[k] = (int)ceil_div(ceil_div(ps[k]->By, tc::BWD_BN), nsplit);
     p.out[k] = ps[k]->out; p.part_stride[k] = ps[k]->part_stride;
+    p.dz[k] = ps[k]->dz; p.dz_colsum[k] = ps[k]->dz_colsum; p.inv_norm[k] = ps[k]->inv_norm;
+  }
+  const bool fused = pq.dz != nullptr || pd.dz != nullptr;
+  if (fused) {
+    if (nsplit > 2) { set_error("tc_inbatch_bwd: the fused normalise backward needs <= 2 splits (got %d)", nsplit); return TT_ERR_UNSUPPORTED; }
+    for (int k = 0; k < 2; ++k) {
+      const bool any = ps[k]->dz || ps[k]->out;
+      if (any && (!ps[k]->dz || !ps[k]->dz_colsum || !ps[k]->inv_norm)) { set_error("tc_inbatch_bwd: fused passes need dz, dz_colsum and inv_norm"); return TT_ERR_INVALID; }
+      p.out[k] = nullptr;
+    }
   }
   p.H = H; p.inv_temp = inv_temp; p.grad_out = grad_out; p.coef = coef;
   const size_t smem = tc::bwd_smem(H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
   long long* dbg_dev = nullptr;
-  const int64_t x0 = pq.out ? ceil_div(pq.Bx, tc::CE_BM) : 0, x1 = pd.out ? ceil_div(pd.Bx, tc::CE_BM) : 0;
-  const int nz = pd.out ? 2 : 1;                         // pass 1 absent -> only z = 0 is launched
+  const int64_t x0 = (pq.out || pq.dz) ? ceil_div(pq.Bx, tc::CE_BM) : 0, x1 = (pd.out || pd.dz) ? ceil_div(pd.Bx, tc::CE_BM) : 0;
+  const int nz = (pd.out || pd.dz) ? 2 : 1;              // pass 1 absent -> only z = 0 is launched
   dim3 grid((unsigned)(x0 > x1 ? x0 : x1), (unsigned)nsplit, (unsigned)nz);
   const size_t ncta = (size_t)grid.x * grid.y * grid.z, dbg_n = 2 * 64 * 8 + 4 * ncta;
   if (dbg_on) { p.dbg_pass = atoi(getenv("TT_CE_DEBUG")) == 1 ? 1 : 0; cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p.dbg = dbg_dev; }
-  TT_CUDA(launch_kernel(tc::tc_ce_bwd_kernel, grid, dim3(tc::CE_THREADS), smem, s, true, tmX0, tmY0, tmX1, tmY1, p));
+  // fused + 2 splits: the two CTAs of a row tile form a cluster and exchange accumulator halves through shared memory
+  TT_CUDA(launch_kernel_cluster(tc::tc_ce_bwd_kernel, grid, dim3(tc::CE_THREADS), smem, s, true, (fused && nsplit == 2) ? 2u : 1u,
+                                tmX0, tmY0, tmX1, tmY1, p));
   TT_LAUNCH_CHECK("tc_ce_bwd_kernel");
   if (dbg_on) {                                              // developer aid: per-tile timeline of CTA (0,0,0)
     std::vector<long long> hostv(dbg_n);
@@ -816,12 +936,16 @@ int tc_inbatch_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pa
     c.x = (const __nv_bfloat16*)t->x_bf16; c.Bx = t->x_rows; c.y = (const __nv_bfloat16*)t->y_bf16; c.By = t->y_rows;
     c.y_buf_rows = t->y_buf_rows; c.y_blk = t->y_blk; c.y_blk_stride = t->y_blk_stride; c.y_blk_off = t->y_blk_off;
     c.lse = t->lse; c.label_offset = t->label_offset; c.out = t->out_parts; c.part_stride = t->part_stride;
+    c.dz = (__nv_bfloat16*)t->dz_bf16; c.dz_colsum = t->dz_colsum; c.inv_norm = t->inv_norm;
     return c;
   };
   const CePass pq = conv(q_pass), pd = conv(d_pass);
   const int want = bwd_splits2(pq.Bx, pq.By, pd.Bx, pd.By);
   if (nparts != want) { set_error("tc_inbatch_bwd_parts_ex: nparts %d != %d (query tt_inbatch_ce_bwd_nparts_ex)", nparts, want); return TT_ERR_INVALID; }
-  if (pq.y_blk % tc::BWD_BN != 0 || pd.y_blk % tc::BWD_BN != 0) { set_error("tc_inbatch_bwd_parts_ex: y_blk must be a multiple of %d", tc::BWD_BN); return TT_ERR_UNSUPPORTED; }
+  // a tile may not straddle two blocks of an interleaved buffer; a single block (y_blk >= rows) has no such constraint
+  if ((pq.y_blk < pq.By && pq.y_blk % tc::BWD_BN != 0) || (pd.y_blk < pd.By && pd.y_blk % tc::BWD_BN != 0)) {
+    set_error("tc_inbatch_bwd_parts_ex: y_blk must be a multiple of %d", tc::BWD_BN); return TT_ERR_UNSUPPORTED;
+  }
   return launch_tc_bwd(pq, pd, H, inv_temp, nparts, grad_out, loss_scale * inv_temp, s);
 }
 

@@ -15,8 +15,8 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
                const float* z, int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2,
                float* db2, const __nv_bfloat16* x_bf16, const __nv_bfloat16* w1_bf16,
                const __nv_bfloat16* w2_bf16, const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride,
-               const tt_mlp_embed_t* embed, const __nv_bfloat16* y_bf16, const float* inv_norm, void* ws, size_t ws_bytes,
-               cudaStream_t s);
+               const tt_mlp_embed_t* embed, const __nv_bfloat16* y_bf16, const float* inv_norm, const __nv_bfloat16* dz_bf16,
+               const float* dz_colsum, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t tc_mlp_embed_workspace(int64_t V, int H, int64_t R);
 
 // whole-MLP forward in one kernel (tc_mlp.cu)

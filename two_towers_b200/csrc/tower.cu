@@ -275,11 +275,14 @@ int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
                const float* z, int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2,
                float* db2, const void* x_bf16, const void* w1_bf16, const void* w2_bf16, const void* h1_bf16,
                int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed, const void* y_bf16,
-               const float* inv_norm, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+               const float* inv_norm, const void* dz_bf16, const float* dz_colsum, int precision, void* workspace,
+               size_t workspace_bytes, void* stream) {
   TT_REQUIRE_DEVICE();
-  TT_CHECK_ARG(dy && x && w1 && w2 && h1 && dw1 && db1 && dw2 && db2 && R > 0 && E > 0 && H > 0,
-               "mlp_bwd: bad arguments");
-  TT_CHECK_ARG(z || (precision == TT_PREC_BF16 && y_bf16 && inv_norm), "mlp_bwd: z may be null only in TT_PREC_BF16 with y_bf16 and inv_norm given");
+  TT_CHECK_ARG(x && w1 && w2 && h1 && dw1 && db1 && dw2 && db2 && R > 0 && E > 0 && H > 0, "mlp_bwd: bad arguments");
+  const bool have_dz = dz_bf16 != nullptr;
+  TT_CHECK_ARG(!have_dz || (precision == TT_PREC_BF16 && dz_colsum && H <= 512), "mlp_bwd: dz_bf16 needs TT_PREC_BF16, dz_colsum and H <= 512");
+  TT_CHECK_ARG(have_dz || dy, "mlp_bwd: dy missing");
+  TT_CHECK_ARG(have_dz || z || (precision == TT_PREC_BF16 && y_bf16 && inv_norm), "mlp_bwd: z may be null only in TT_PREC_BF16 with y_bf16 and inv_norm given");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == TT_PREC_BF16) {
     if (embed) {
@@ -288,7 +291,8 @@ int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
     }
     return tt::tc_mlp_bwd(dy, x, w1, w2, h1, z, R, E, H, dx, dw1, db1, dw2, db2, (const __nv_bfloat16*)x_bf16,
                           (const __nv_bfloat16*)w1_bf16, (const __nv_bfloat16*)w2_bf16, (const __nv_bfloat16*)h1_bf16,
-                          dy_parts, dy_part_stride, embed, (const __nv_bfloat16*)y_bf16, inv_norm, workspace, workspace_bytes, s);
+                          dy_parts, dy_part_stride, embed, (const __nv_bfloat16*)y_bf16, inv_norm, (const __nv_bfloat16*)dz_bf16,
+                          dz_colsum, workspace, workspace_bytes, s);
   }
   TT_CHECK_ARG(embed == nullptr, "mlp_bwd: embed is a TT_PREC_BF16 feature");
   TT_CHECK_ARG(precision == TT_PREC_FP32, "mlp_bwd: unknown precision %d", precision);

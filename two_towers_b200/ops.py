@@ -156,7 +156,7 @@ def mlp_bwd(dy, x, w1, w2, h1, z, need_dx: bool = True, precision=None):
     db2 = torch.empty(H, dtype=torch.float32, device=dev)
     ws = _workspace(_lib_().tt_mlp_workspace(R, E, H, prec), dev)
     check(_lib_().tt_mlp_bwd(_p(dy), _p(x), _p(w1), _p(w2), _p(h1), _p(z), R, E, H, _p(dx), _p(dw1), _p(db1),
-                             _p(dw2), _p(db2), None, None, None, None, 1, 0, None, None, None, prec, _p(ws), ws.numel(),
+                             _p(dw2), _p(db2), None, None, None, None, 1, 0, None, None, None, None, None, prec, _p(ws), ws.numel(),
                              _stream()),
           "tt_mlp_bwd")
     return dx, dw1, db1, dw2, db2

@@ -19,6 +19,7 @@ The modules of ``two_towers_b200.encoders`` also work under plain ``loss.backwar
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -116,8 +117,18 @@ class FusedTrainer:
             self.yg_bf16 = torch.empty(self.world * 2 * B, self.H, dtype=torch.bfloat16, device=self.dev)
             self.lse_g = torch.empty(Bg, **f32)
             self.ce_ws = torch.empty(int(self.lib.tt_inbatch_ce_fwd_ex_workspace(B, Bg)), dtype=torch.uint8, device=self.dev)
+        # the loss backward can also finish the normalise backward itself (CTA pairs exchange accumulator halves through
+        # distributed shared memory): it then emits dz (bf16) + column sums and the [parts, R, H] fp32 slices never exist
+        Bg = B * self.world
+        self.ce_fused = bool(os.environ.get("TT_CE_FUSED", "1") != "0" and
+                             fast and (self.local_fast or self.global_fast) and B % 32 == 0 and self.passes == 2 and
+                             self.lib.tt_inbatch_ce_bwd_fused_ok(B, Bg if self.global_fast else B, B,
+                                                                 Bg if self.global_fast else B, self.H))
+        if self.ce_fused:
+            self.dz_bf16 = torch.empty(R, self.H, dtype=torch.bfloat16, device=self.dev)
+            self.dz_colsum = torch.empty(R // 32, self.H, **f32)
         self.dy_part_stride = R * self.H if self.dy_parts > 1 else 0
-        self.dy_all = torch.empty(self.dy_parts, R, self.H, **f32)
+        self.dy_all = torch.empty(1 if self.ce_fused else self.dy_parts, R, self.H, **f32)
         self.dy = self.dy_all[0]
         self.dpooled = torch.empty(R, self.E, **f32)
         self.saved: List[Dict[str, torch.Tensor]] = []
@@ -183,7 +194,7 @@ class FusedTrainer:
         xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
-            pure = (self.dy_parts > 1 or self.global_fast) and yb is not None
+            pure = (self.dy_parts > 1 or self.global_fast or self.ce_fused) and yb is not None
             y_ptr = None if pure else y                     # fp32 y unused on the pure bf16 path
             # pure bf16 path: the normalise step is saved as (y_bf16, 1/|z|); the fp32 pre-normalise tensor is never written
             inv = self.inv_norm[r0:r0 + nr] if (pure and self.H <= 512) else None
@@ -215,14 +226,16 @@ class FusedTrainer:
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
             yb = self.y_bf16[r0:r0 + nr] if self.y_bf16 is not None else None
-            pure = (self.dy_parts > 1 or self.global_fast) and yb is not None and self.H <= 512
+            pure = (self.dy_parts > 1 or self.global_fast or self.ce_fused) and yb is not None and self.H <= 512
             inv = self.inv_norm[r0:r0 + nr] if pure else None
+            dzb = self.dz_bf16[r0:r0 + nr] if self.ce_fused else None
+            dzc = self.dz_colsum[r0 // 32:(r0 + nr) // 32] if self.ce_fused else None
             check(lib.tt_mlp_bwd(_p(dy), _p(x), _p(l1.weight), _p(l2.weight), _p(sv["h1"]), _p(None if pure else sv["z"]), nr, self.E,
                                  self.H, _p(dx), _p(l1.weight.grad), _p(l1.bias.grad), _p(l2.weight.grad),
                                  _p(l2.bias.grad), _p(xb), _p(self._shadow(l1.weight)), _p(self._shadow(l2.weight)),
                                  _p(self.h1_bf16[gi]), self.dy_parts, self.dy_part_stride,
                                  C.byref(emb) if emb is not None else None, _p(yb if pure else None), _p(inv),
-                                 self.prec, _p(self.ws), self.ws.numel(), s), "tt_mlp_bwd")
+                                 _p(dzb), _p(dzc), self.prec, _p(self.ws), self.ws.numel(), s), "tt_mlp_bwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
             check(lib.tt_proj_ln_bwd(_p(dy), _p(x), _p(lin.weight), _p(ln.weight), _p(sv["a"]), _p(sv["stats"]),
@@ -255,25 +268,8 @@ class FusedTrainer:
                 dq.copy_(g_dq)
                 dd.copy_(g_dd)
             else:
-                scale = 1.0 / (B * self.world)
-                qb = self.y_bf16[:B] if self.y_bf16 is not None else None
-                db = self.y_bf16[B:2 * B] if self.y_bf16 is not None else None
-                if self.local_fast:
-                    check(lib.tt_inbatch_ce_fwd_ex(_p(qb), B, _p(db), B, B, B, 0, 0, H, inv_t, 0, scale, _p(self.loss),
-                                                   _p(self.lse), _p(self.pos_mean), _p(self.ce_ws), self.ce_ws.numel(),
-                                                   _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
-                else:
-                    check(lib.tt_inbatch_ce_fwd(_p(q), _p(d), _p(qb), _p(db), B, B, H, inv_t, 0, scale, _p(self.loss),
-                                                _p(self.lse), _p(self.pos_mean), self.prec, _p(self.ws), self.ws.numel(), s),
-                          "tt_inbatch_ce_fwd")
-                if self.dy_parts > 1:
-                    check(lib.tt_inbatch_ce_bwd_parts(_p(qb), _p(db), _p(self.lse), B, B, H, inv_t, 0, scale, None,
-                                                      _p(dq), self.dy_part_stride, _p(dd), self.dy_part_stride, s),
-                          "tt_inbatch_ce_bwd_parts")
-                else:
-                    check(lib.tt_inbatch_ce_bwd(_p(q), _p(d), _p(qb), _p(db), _p(self.lse), B, B, H, inv_t, 0, scale,
-                                                None, _p(dq), _p(dd), self.prec, _p(self.ws), self.ws.numel(), s),
-                          "tt_inbatch_ce_bwd")
+                self._local_loss_fwd(s)
+                self._local_loss_bwd(s)
         else:
             n, dn = self.y[2 * B:3 * B], self.dy[2 * B:3 * B]
             check(lib.tt_triplet_fwd(_p(q), _p(d), _p(n), B, H, self.margin, _p(self.loss), _p(self.sims),
@@ -293,6 +289,49 @@ class FusedTrainer:
                                 self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                 _p(self.step_count), _p(self.flat_bf16), s), "tt_adamw_step")
 
+    def _local_loss_fwd(self, s):
+        """In-batch loss forward against the local documents (one launch on the tensor-core path)."""
+        lib, B, H = self.lib, self.B, self.H
+        q, d = self.y[:B], self.y[B:2 * B]
+        inv_t, scale = 1.0 / self.temperature, 1.0 / (B * self.world)
+        qb = self.y_bf16[:B] if self.y_bf16 is not None else None
+        db = self.y_bf16[B:2 * B] if self.y_bf16 is not None else None
+        if self.local_fast:
+            check(lib.tt_inbatch_ce_fwd_ex(_p(qb), B, _p(db), B, B, B, 0, 0, H, inv_t, 0, scale, _p(self.loss),
+                                           _p(self.lse), _p(self.pos_mean), _p(self.ce_ws), self.ce_ws.numel(),
+                                           _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
+        else:
+            check(lib.tt_inbatch_ce_fwd(_p(q), _p(d), _p(qb), _p(db), B, B, H, inv_t, 0, scale, _p(self.loss),
+                                        _p(self.lse), _p(self.pos_mean), self.prec, _p(self.ws), self.ws.numel(), s),
+                  "tt_inbatch_ce_fwd")
+
+    def _local_loss_bwd(self, s):
+        """Both loss gradients in one launch: fused with the normalise backward (dz + column sums), or as per-split
+        slices the tower backward sums, or (fp32 / unsupported shapes) as plain dq, dd."""
+        lib, B, H = self.lib, self.B, self.H
+        q, d = self.y[:B], self.y[B:2 * B]
+        dq, dd = self.dy[:B], self.dy[B:2 * B]
+        inv_t, scale = 1.0 / self.temperature, 1.0 / (B * self.world)
+        qb = self.y_bf16[:B] if self.y_bf16 is not None else None
+        db = self.y_bf16[B:2 * B] if self.y_bf16 is not None else None
+        if self.ce_fused:
+            vp = lambda t: None if t is None else t.data_ptr()
+            nb = B // 32
+            qp = _lib.CePass(vp(qb), B, vp(db), B, B, B, 0, 0, vp(self.lse), 0, None, 0,
+                             vp(self.dz_bf16[:B]), vp(self.dz_colsum[:nb]), vp(self.inv_norm[:B]))
+            dp = _lib.CePass(vp(db), B, vp(qb), B, B, B, 0, 0, vp(self.lse), 0, None, 0,
+                             vp(self.dz_bf16[B:2 * B]), vp(self.dz_colsum[nb:2 * nb]), vp(self.inv_norm[B:2 * B]))
+            check(lib.tt_inbatch_ce_bwd_parts_ex(C.byref(qp), C.byref(dp), H, inv_t, scale, None, self.dy_parts, s),
+                  "tt_inbatch_ce_bwd_parts_ex")
+        elif self.dy_parts > 1:
+            check(lib.tt_inbatch_ce_bwd_parts(_p(qb), _p(db), _p(self.lse), B, B, H, inv_t, 0, scale, None,
+                                              _p(dq), self.dy_part_stride, _p(dd), self.dy_part_stride, s),
+                  "tt_inbatch_ce_bwd_parts")
+        else:
+            check(lib.tt_inbatch_ce_bwd(_p(q), _p(d), _p(qb), _p(db), _p(self.lse), B, B, H, inv_t, 0, scale,
+                                        None, _p(dq), _p(dd), self.prec, _p(self.ws), self.ws.numel(), s),
+                  "tt_inbatch_ce_bwd")
+
     def _global_inbatch_fast(self, s, inv_t):
         """Global in-batch negatives on the tensor-core path: 2 all-gathers (bf16 [Q|D], fp32 lse), the loss kernels
         read the gathered buffer in place (block-interleaved rows), both gradients come from ONE launch as slices."""
@@ -305,10 +344,14 @@ class FusedTrainer:
                                        _p(self.ce_ws), self.ce_ws.numel(), _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
         dist.all_gather_into_tensor(self.lse_g, self.lse, group=self.group)
         vp = lambda t: None if t is None else t.data_ptr()
+        nb = B // 32
+        fz = (lambda a, b, c: (vp(a), vp(b), vp(c))) if self.ce_fused else (lambda a, b, c: (None, None, None))
         qp = _lib.CePass(vp(self.y_bf16[:B]), B, vp(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, B, vp(self.lse), self.rank * B,
-                         vp(self.dy[:B]), self.dy_part_stride)
+                         vp(self.dy[:B]), self.dy_part_stride,
+                         *(fz(self.dz_bf16[:B], self.dz_colsum[:nb], self.inv_norm[:B]) if self.ce_fused else (None, None, None)))
         dp = _lib.CePass(vp(self.y_bf16[B:2 * B]), B, vp(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, 0, vp(self.lse_g),
-                         -self.rank * B, vp(self.dy[B:2 * B]), self.dy_part_stride)
+                         -self.rank * B, vp(self.dy[B:2 * B]), self.dy_part_stride,
+                         *(fz(self.dz_bf16[B:2 * B], self.dz_colsum[nb:2 * nb], self.inv_norm[B:2 * B]) if self.ce_fused else (None, None, None)))
         check(lib.tt_inbatch_ce_bwd_parts_ex(C.byref(qp), C.byref(dp), H, inv_t, scale, None, self.dy_parts, s),
               "tt_inbatch_ce_bwd_parts_ex")
 

@@ -135,8 +135,8 @@ def test_embed_fused_tower_backward(R, L, V, E, H):
     emb = _lib.MlpEmbed(pt(P), V, pt(ttab), pt(dtab), 0, pt(ews), ews.numel())
     def run_bwd():
         _lib.check(lib.tt_mlp_bwd(pt(tdy), pt(pooled), pt(tw1), pt(tw2), pt(h1), None, R, E, H, None, pt(dw1), pt(db1), pt(dw2),
-                                  pt(db2), pt(pooled_b), None, None, None, 1, 0, C.byref(emb), pt(yb), pt(inv), 1, pt(ws),
-                                  ws.numel(), s), "mlp_bwd")
+                                  pt(db2), pt(pooled_b), None, None, None, 1, 0, C.byref(emb), pt(yb), pt(inv), None, None, 1,
+                                  pt(ws), ws.numel(), s), "mlp_bwd")
         torch.cuda.synchronize()
     run_bwd()
     dz = O.normalize_bwd(dy.astype(f), rz)

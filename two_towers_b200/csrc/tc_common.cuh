@@ -133,6 +133,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
   return r;
 }
+// bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into a peer CTA's, completing (complete_tx) on an
+// mbarrier that lives in the PEER's shared memory; both destination addresses are shared::cluster addresses (mapa)
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, const void* src_smem, uint32_t bytes, uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster_addr), "r"(smem_u32(src_smem)), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void st_cluster_f4(uint32_t cluster_addr, float a, float b, float c, float d) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

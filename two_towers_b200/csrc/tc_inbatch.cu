@@ -305,6 +305,7 @@ struct BwdParams {
   __nv_bfloat16* dz[2];        // [Bx, H] bf16 (null: write out[] slices as before)
   float* dz_colsum[2];         // [ceil(Bx / 32), H]
   const float* inv_norm[2];    // [Bx]
+  const __nv_bfloat16* xg[2];  // the X operand in global memory (== y), re-read by the fused tail
   int H;
   float inv_temp;
   const float* grad_out;       // nullable device scalar
@@ -347,8 +348,9 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   uint64_t* p_empty = p_full + 1;
   uint64_t* o_full = p_empty + 1;
   uint64_t* x_ready = o_full + 1;                         // X tile copied into TMEM (4 epilogue warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
-  float* col_lse = reinterpret_cast<float*>(tmem_slot + 6);   // [2][128] column lse of the current / next Y tile (COL)
+  uint64_t* xfer_bar = x_ready + 1;                       // fused tail: the peer CTA's accumulator half has landed here
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfer_bar + 1);
+  float* col_lse = reinterpret_cast<float*>(tmem_slot + 4);   // [2][128] column lse of the current / next Y tile (COL)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t x0 = (int64_t)blockIdx.x * CE_BM;
@@ -360,7 +362,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (int)blockIdx.z == p.dbg_pass) ? p.dbg : nullptr;
 #define TT_STAMP(role, tile, slot) do { if (dbg) dbg[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); } while (0)
   // per-CTA wall-clock stamps (ns): kernel entry, X resident in TMEM, main loop done, outputs stored
-  long long* cta_dbg = p.dbg ? p.dbg + 2 * 64 * 8 + 4 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  long long* cta_dbg = p.dbg ? p.dbg + 2 * 64 * 8 + 8 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
 #define TT_CTA_STAMP(slot) do { if (cta_dbg && threadIdx.x == 64) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); cta_dbg[slot] = t_; } } while (0)
   TT_CTA_STAMP(0);
 
@@ -372,7 +374,9 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     mbar_init(p_full, 4); mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     mbar_init(x_ready, 4);
+    mbar_init(xfer_bar, 1);
     fence_barrier_init();
+    if (fused && gridDim.y == 2) mbar_arrive_expect_tx(xfer_bar, (uint32_t)(64 * (H + 4) * 4));   // armed long before the peer sends
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -598,20 +602,28 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   }
   if (fused) {
     // ---- fused normalise backward.  The CTA pair (cluster) holds the two halves of dy = scale * (O_0 + O_1) in tensor
-    // memory.  Rank r finishes rows [64 r, 64 r + 64) of the tile: the other 64 rows of its accumulator travel to the
-    // peer's shared memory (the Y stages are idle now).  With a single split the CTA finishes all 128 rows itself.
+    // memory.  Rank r finishes rows [64 r, 64 r + 64) of the tile.  Phase A: every epilogue thread dumps its accumulator
+    // row into local shared memory (the Y stages are idle now); the 64 rows the peer finishes then travel as two 32-row
+    // bulk copies (cp.async.bulk shared::cta -> shared::cluster) that complete on the peer's mbarrier.  Phase B: all four
+    // warps walk the rows, lanes across columns: coalesced shared reads, a shuffle tree for y.dy (y = the X rows, read
+    // back from global / L2), 256-byte coalesced bf16 stores.  A single split (no cluster) finishes all 128 rows itself.
     const bool pair = gridDim.y == 2;
     const uint32_t rank = pair ? cluster_ctarank() : 0u;
-    const int quarter = warp & 3;
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int lrow = quarter * 32 + lane;
-    const float scale = p.coef * (p.grad_out ? *p.grad_out : 1.0f);
-    const int RS = H + 4;                                  // receive-buffer row stride (floats): conflict-free float4 rows, 64 rows fit the Y stages
-    float* recv = reinterpret_cast<float*>(y_tiles);       // [64][RS]
+    const int nfin = pair ? 64 : 128;                      // rows finished by this CTA
+    const int fin0 = pair ? 64 * (int)rank : 0;            // first tile row finished here
+    const int RS = H + 4;                                  // floats per staged accumulator row (conflict-free 16-byte rows)
+    float* own = reinterpret_cast<float*>(y_tiles);        // [nfin][RS]
+    float* recv = own + nfin * RS;                         // [64][RS]  pair only: filled by the peer
+    float* send = recv + 64 * RS;                          // [64][RS]  pair only: rows the peer finishes
+    float* cs_s = pair ? send + 64 * RS : own + nfin * RS; // [4][H] column partials
     if (pair) cluster_sync_all();                          // both CTAs' tensor pipes have retired: every Y stage is free
-    const bool mine = !pair || (quarter >> 1) == (int)rank;   // this warp's rows are finished here
-    if (pair && warp >= 2 && !mine) {
-      const uint32_t dst = mapa_shared(smem_u32(recv), rank ^ 1u) + (uint32_t)((lrow & 63) * RS * 4);
+    TT_CTA_STAMP(4);
+    if (warp >= 2) {
+      const int quarter = warp & 3;
+      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+      const int lrow = quarter * 32 + lane;
+      const bool mine = !pair || (quarter >> 1) == (int)rank;
+      float* dst_row = mine ? own + (lrow - fin0) * RS : send + (lrow & 63) * RS;
       for (int cb = 0; cb < H / 32; ++cb) {
         uint32_t q[32];
         if (nt > 0) {
@@ -623,78 +635,145 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          st_cluster_f4(dst + (uint32_t)((cb * 32 + j) * 4), __uint_as_float(q[j]), __uint_as_float(q[j + 1]),
-                        __uint_as_float(q[j + 2]), __uint_as_float(q[j + 3]));
+          *reinterpret_cast<float4*>(dst_row + cb * 32 + j) = make_float4(__uint_as_float(q[j]), __uint_as_float(q[j + 1]),
+                                                                          __uint_as_float(q[j + 2]), __uint_as_float(q[j + 3]));
+      }
+      if (!mine) {                                         // this warp's 32 rows -> the same rows of the peer's recv buffer
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int r32 = (quarter & 1) * 32;
+          dsmem_bulk_copy(mapa_shared(smem_u32(recv + r32 * RS), rank ^ 1u), send + r32 * RS, (uint32_t)(32 * RS * 4),
+                          mapa_shared(smem_u32(xfer_bar), rank ^ 1u));
+        }
       }
     }
-    if (pair) cluster_sync_all();                          // peer's half has landed
-    if (warp >= 2 && mine) {
-      const int64_t row = x0 + lrow;
-      const float inv = row < Bx ? __ldg(p.inv_norm[PASS] + row) : 0.f;
-      const float* rrow = recv + (lrow & 63) * RS;
-      // pass 1: y . dy  (y = this row of the X tile, bf16 pairs in tensor memory)
-      float dot = 0.f;
-      for (int cb = 0; cb < H / 32; ++cb) {
-        uint32_t q[32], xw[16];
-        if (nt > 0) tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
-        tmem_ld_x16(tmem_x + lane_addr + (uint32_t)(cb * 16), xw);
-        tmem_ld_wait();
+    TT_CTA_STAMP(5);
+    const int e = warp - 2;
+    const int rpw = nfin / 4;                              // rows per warp: 16 (pair) or 32
+    const int steps = (H + 127) / 128;                     // lane -> columns step * 128 + 4 * lane .. + 3
+    const int64_t g0 = x0 + fin0 + e * rpw;                // first global row of this warp
+    const __nv_bfloat16* xg = p.xg[PASS];
+    // y (= the X rows, bf16) for 16 rows of this warp and 1/|z| of all its rows: issued before the waits below, so the
+    // global round trips overlap the peer's bulk copy instead of stalling every row group
+    uint2 ywa[16][2];
+    float my_inv = 0.f;
+    auto load_y16 = [&](int rbase) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pair) o = *reinterpret_cast<const float4*>(rrow + cb * 32 + j);
-          if (nt > 0) { o.x += __uint_as_float(q[j]); o.y += __uint_as_float(q[j + 1]); o.z += __uint_as_float(q[j + 2]); o.w += __uint_as_float(q[j + 3]); }
-          const uint32_t w0 = xw[j >> 1], w1 = xw[(j >> 1) + 1];
-          dot = fmaf(o.x, __uint_as_float(w0 << 16), dot); dot = fmaf(o.y, __uint_as_float(w0 & 0xffff0000u), dot);
-          dot = fmaf(o.z, __uint_as_float(w1 << 16), dot); dot = fmaf(o.w, __uint_as_float(w1 & 0xffff0000u), dot);
+      for (int u = 0; u < 16; ++u) {
+        const int64_t grow = g0 + rbase + u;
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+          const int c = st * 128 + lane * 4;
+          ywa[u][st] = make_uint2(0u, 0u);
+          if (st < steps && c < H && grow < Bx) ywa[u][st] = __ldg(reinterpret_cast<const uint2*>(xg + grow * H + c));
         }
       }
-      // pass 2: dz = (dy - y (y.dy)) * inv  ->  staged 32x32 per warp, then 4 rows x 64 B per store instruction
-      float* T = reinterpret_cast<float*>(p_tile + (warp - 2) * (32 * 36 * 4));
-      const int64_t row0 = x0 + quarter * 32;
-      const int nrows = (int)max((int64_t)0, min((int64_t)32, Bx - row0));
-      const float si = scale * inv;
-      const int cq = (lane & 7) * 4, rq = lane >> 3;
-      __nv_bfloat16* dzo = p.dz[PASS] + (row0 + rq) * H + cq;
-      float* cso = p.dz_colsum[PASS] + (row0 >> 5) * H + cq;
-      for (int cb = 0; cb < H / 32; ++cb) {
-        uint32_t q[32], xw[16];
-        if (nt > 0) tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
-        tmem_ld_x16(tmem_x + lane_addr + (uint32_t)(cb * 16), xw);
-        tmem_ld_wait();
+    };
+    if (warp >= 2) {
+      my_inv = (lane < rpw && g0 + lane < Bx) ? __ldg(p.inv_norm[PASS] + g0 + lane) : 0.f;
+      load_y16(0);
+    }
+    __syncthreads();                                       // own rows staged
+    if (warp >= 2 && pair) mbar_wait(xfer_bar, 0);         // peer's half has landed
+    TT_CTA_STAMP(6);
+    if (warp >= 2) {
+      const float scale = p.coef * (p.grad_out ? *p.grad_out : 1.0f);
+      float4 cs[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+      for (int i0 = 0; i0 < rpw; i0 += 4) {                // 4 rows at a time: their loads and shuffle trees interleave
+        if (i0 == 16) load_y16(16);                        // single split: second half of the warp's 32 rows
+#define TT_PB(slot) do { if (p.dbg && threadIdx.x == 64) p.dbg[(64 + 40 + (i0 >> 2)) * 8 + (slot)] = clock64(); } while (0)
+        TT_PB(0);
+        float4 o[4][2];
+        uint2 yw[4][2];
+        float dot[4];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pair) o = *reinterpret_cast<const float4*>(rrow + cb * 32 + j);
-          if (nt > 0) { o.x += __uint_as_float(q[j]); o.y += __uint_as_float(q[j + 1]); o.z += __uint_as_float(q[j + 2]); o.w += __uint_as_float(q[j + 3]); }
-          const uint32_t w0 = xw[j >> 1], w1 = xw[(j >> 1) + 1];
-          float4 d;
-          d.x = (o.x - __uint_as_float(w0 << 16) * dot) * si;          d.y = (o.y - __uint_as_float(w0 & 0xffff0000u) * dot) * si;
-          d.z = (o.z - __uint_as_float(w1 << 16) * dot) * si;          d.w = (o.w - __uint_as_float(w1 & 0xffff0000u) * dot) * si;
-          *reinterpret_cast<float4*>(&T[lane * 36 + j]) = d;
-        }
-        __syncwarp();
-        float4 v[8];
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const float4*>(&T[(4 * k + rq) * 36 + cq]);
-        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int st = 0; st < 2; ++st) {
+            // ywa is indexed with compile-time constants only (registers): select the row group of this iteration
+            const int gsel = (i0 >> 2) & 3;
+            yw[u][st] = gsel == 0 ? ywa[u][st] : gsel == 1 ? ywa[4 + u][st] : gsel == 2 ? ywa[8 + u][st] : ywa[12 + u][st];
+          }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (4 * k + rq < nrows) {
-            cs.x += v[k].x; cs.y += v[k].y; cs.z += v[k].z; cs.w += v[k].w;
-            *reinterpret_cast<uint2*>(dzo + (int64_t)(4 * k) * H + cb * 32) = make_uint2(pack_bf16x2(v[k].x, v[k].y), pack_bf16x2(v[k].z, v[k].w));
+        for (int u = 0; u < 4; ++u) {
+          const int r = e * rpw + i0 + u;
+#pragma unroll
+          for (int st = 0; st < 2; ++st) {
+            const int c = st * 128 + lane * 4;
+            o[u][st] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (st < steps && c < H) {
+              o[u][st] = *reinterpret_cast<const float4*>(own + r * RS + c);
+              if (pair) {
+                const float4 t = *reinterpret_cast<const float4*>(recv + r * RS + c);
+                o[u][st].x += t.x; o[u][st].y += t.y; o[u][st].z += t.z; o[u][st].w += t.w;
+              }
+            }
           }
         }
 #pragma unroll
-        for (int d = 8; d <= 16; d <<= 1) {
-          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, d); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, d);
-          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, d); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, d);
+        for (int u = 0; u < 4; ++u) {
+          float d = 0.f;
+#pragma unroll
+          for (int st = 0; st < 2; ++st) {
+            d = fmaf(o[u][st].x, __uint_as_float(yw[u][st].x << 16), d); d = fmaf(o[u][st].y, __uint_as_float(yw[u][st].x & 0xffff0000u), d);
+            d = fmaf(o[u][st].z, __uint_as_float(yw[u][st].y << 16), d); d = fmaf(o[u][st].w, __uint_as_float(yw[u][st].y & 0xffff0000u), d);
+          }
+          dot[u] = d;
         }
-        if (rq == 0 && nrows > 0) *reinterpret_cast<float4*>(cso + cb * 32) = cs;
-        __syncwarp();
+        TT_PB(1);
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], sh);
+        }
+        TT_PB(2);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t grow = g0 + i0 + u;
+          const float si = scale * __shfl_sync(0xffffffffu, my_inv, i0 + u);
+          if (grow < Bx) {                                 // warp-uniform
+#pragma unroll
+            for (int st = 0; st < 2; ++st) {
+              const int c = st * 128 + lane * 4;
+              if (st < steps && c < H) {
+                float4 d;
+                d.x = (o[u][st].x - __uint_as_float(yw[u][st].x << 16) * dot[u]) * si;          d.y = (o[u][st].y - __uint_as_float(yw[u][st].x & 0xffff0000u) * dot[u]) * si;
+                d.z = (o[u][st].z - __uint_as_float(yw[u][st].y << 16) * dot[u]) * si;          d.w = (o[u][st].w - __uint_as_float(yw[u][st].y & 0xffff0000u) * dot[u]) * si;
+                cs[st].x += d.x; cs[st].y += d.y; cs[st].z += d.z; cs[st].w += d.w;
+                *reinterpret_cast<uint2*>(p.dz[PASS] + grow * H + c) = make_uint2(pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
+              }
+            }
+          }
+        }
+      }
+      if (p.dbg && threadIdx.x == 64) p.dbg[(64 + 44) * 8 + 0] = clock64();
+      // per-32-row column sums: a warp's own block (32 rows per warp) or the sum of a warp pair (16 rows each)
+#pragma unroll
+      for (int st = 0; st < 2; ++st) {
+        const int c = st * 128 + lane * 4;
+        if (st < steps && c < H) *reinterpret_cast<float4*>(cs_s + e * H + c) = cs[st];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const bool writer = rpw == 32 || (e & 1) == 0;
+      const int64_t blk_row = x0 + fin0 + (rpw == 32 ? e * 32 : (e >> 1) * 32);
+      if (writer && blk_row < Bx) {
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+          const int c = st * 128 + lane * 4;
+          if (st < steps && c < H) {
+            float4 v = cs[st];
+            if (rpw == 16) {
+              const float4 t = *reinterpret_cast<const float4*>(cs_s + (e + 1) * H + c);
+              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            *reinterpret_cast<float4*>(p.dz_colsum[PASS] + (blk_row >> 5) * H + c) = v;
+          }
+        }
       }
     }
     TT_CTA_STAMP(3);
+    if (pair) cluster_sync_all();                          // neither CTA leaves while its peer may still read its send buffer
   }
   tc_fence_before();
   __syncthreads();
@@ -846,7 +925,7 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
     p.y_blk[k] = ps[k]->y_blk > 0 ? ps[k]->y_blk : 1; p.y_blk_stride[k] = ps[k]->y_blk_stride; p.y_blk_off[k] = ps[k]->y_blk_off;
     p.tiles_per_split[k] = (int)ceil_div(ceil_div(ps[k]->By, tc::BWD_BN), nsplit);
     p.out[k] = ps[k]->out; p.part_stride[k] = ps[k]->part_stride;
-    p.dz[k] = ps[k]->dz; p.dz_colsum[k] = ps[k]->dz_colsum; p.inv_norm[k] = ps[k]->inv_norm;
+    p.dz[k] = ps[k]->dz; p.dz_colsum[k] = ps[k]->dz_colsum; p.inv_norm[k] = ps[k]->inv_norm; p.xg[k] = ps[k]->x;
   }
   const bool fused = pq.dz != nullptr || pd.dz != nullptr;
   if (fused) {
@@ -865,7 +944,7 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
   const int64_t x0 = (pq.out || pq.dz) ? ceil_div(pq.Bx, tc::CE_BM) : 0, x1 = (pd.out || pd.dz) ? ceil_div(pd.Bx, tc::CE_BM) : 0;
   const int nz = (pd.out || pd.dz) ? 2 : 1;              // pass 1 absent -> only z = 0 is launched
   dim3 grid((unsigned)(x0 > x1 ? x0 : x1), (unsigned)nsplit, (unsigned)nz);
-  const size_t ncta = (size_t)grid.x * grid.y * grid.z, dbg_n = 2 * 64 * 8 + 4 * ncta;
+  const size_t ncta = (size_t)grid.x * grid.y * grid.z, dbg_n = 2 * 64 * 8 + 8 * ncta;
   if (dbg_on) { p.dbg_pass = atoi(getenv("TT_CE_DEBUG")) == 1 ? 1 : 0; cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p.dbg = dbg_dev; }
   // fused + 2 splits: the two CTAs of a row tile form a cluster and exchange accumulator halves through shared memory
   TT_CUDA(launch_kernel_cluster(tc::tc_ce_bwd_kernel, grid, dim3(tc::CE_THREADS), smem, s, true, (fused && nsplit == 2) ? 2u : 1u,
@@ -888,6 +967,9 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
       for (int k = 0; k < 6; ++k) printf(" %6lld", host[(1 * 64 + t) * 8 + k] ? host[(1 * 64 + t) * 8 + k] - t0 : -1);
       printf("\n");
     }
+    printf("[tt ce_bwd fused tail, cycles; last writer among CTAs] per 4-row group {begin, dots, shuffled}, then end:");
+    for (int g = 0; g < 4; ++g) printf("  %lld %lld %lld |", host[(64 + 40 + g) * 8 + 0] - t0, host[(64 + 40 + g) * 8 + 1] - t0, host[(64 + 40 + g) * 8 + 2] - t0);
+    printf("  %lld\n", host[(64 + 44) * 8 + 0] - t0);
     printf("[tt ce_bwd O store, cycles] cb: tmem_loaded staged read stored\n");
     for (int cb = 0; cb < H / 32; ++cb) {
       printf("  %2d:", cb);
@@ -896,10 +978,11 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
     }
     const long long* c = host + 2 * 64 * 8;
     long long g0 = 0;
-    for (size_t i = 0; i < ncta; ++i) if (c[4 * i] && (!g0 || c[4 * i] < g0)) g0 = c[4 * i];
-    printf("[tt ce_bwd per-CTA, ns since first CTA start] cta: start x_ready loop_done stored\n");
+    for (size_t i = 0; i < ncta; ++i) if (c[8 * i] && (!g0 || c[8 * i] < g0)) g0 = c[8 * i];
+    printf("[tt ce_bwd per-CTA, ns since first CTA start] cta: start x_ready loop_done stored | fused: sync1 dumped sync2\n");
     for (size_t i = 0; i < ncta; ++i)
-      printf("  cta %3zu: %6lld %6lld %6lld %6lld\n", i, c[4 * i] - g0, c[4 * i + 1] - g0, c[4 * i + 2] - g0, c[4 * i + 3] - g0);
+      printf("  cta %3zu: %6lld %6lld %6lld %6lld | %6lld %6lld %6lld\n", i, c[8 * i] - g0, c[8 * i + 1] - g0, c[8 * i + 2] - g0, c[8 * i + 3] - g0,
+             c[8 * i + 4] ? c[8 * i + 4] - g0 : -1, c[8 * i + 5] ? c[8 * i + 5] - g0 : -1, c[8 * i + 6] ? c[8 * i + 6] - g0 : -1);
   }
   return TT_OK;
 }

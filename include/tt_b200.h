@@ -55,6 +55,8 @@ int64_t tt_launch_count(void);
  *                       pool_bf16 (nullable, V <= 1024): the pooling matrix P [rows,V] in bf16,
  *                       P[r,v] = count_r(v) / (count_r + 1e-9), so that pooled = P * table; consumed by
  *                       tt_mlp_bwd(embed = ...) which then needs neither dx nor tt_embed_pool_bwd.
+ *                       pooled == NULL (with pool_bf16): only P and inv_len are produced -- for tt_mlp_fwd(embed = ...),
+ *                       which forms x = P * table on the tensor cores inside the tower kernel.
  * tt_embed_pool_bwd   : autograd of the above -> ATen embedding_dense_backward
  *                       (loss.backward(), twotower/train.py:138).  Deterministic: small tables
  *                       use a pooling-matrix GEMM with fixed split order, large tables a
@@ -95,11 +97,15 @@ int tt_embed_pool_bwd(const void* ids, int id_bytes, const float* inv_len, const
  *   The backward then forms M = P^T da1 [V,H] once on the tensor cores and finishes with two tiny products,
  *   dw1 = M^T table and d_table = M w1 (+= when accumulate != 0), instead of computing dx [R,E], dw1 = da1^T x and
  *   the separate embedding backward; dx must be null.  workspace: tt_mlp_embed_workspace(V, H, R) bytes.
+ *   tt_mlp_fwd(embed = ...) (when tt_mlp_fwd_embed_ok): x = P * table_bf16 is formed on the tensor cores inside the
+ *   tower kernel (x and x_bf16 are ignored): the pooled activations never reach HBM.
  */
-typedef struct {
+
+typedef struct tt_mlp_embed_s {
   const void* pool_bf16;      /* P [R,V] bf16 */
   int64_t V;
   const float* table;         /* [V,E] */
+  const void* table_bf16;     /* [V,E] bf16 shadow (forward only; e.g. the one tt_adamw_step maintains) */
   float* d_table;             /* [V,E] */
   int accumulate;             /* 0: d_table is overwritten, else added to (second tower sharing the table) */
   void* workspace; size_t workspace_bytes;
@@ -109,7 +115,10 @@ size_t tt_mlp_workspace(int64_t R, int E, int H, int precision);
 int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                int64_t R, int E, int H, float* h1, float* z, float* y, void* y_bf16,
                const void* x_bf16, const void* w1_bf16, const void* w2_bf16, void* h1_bf16,
-               float* inv_norm, int precision, void* workspace, size_t workspace_bytes, void* stream);
+               float* inv_norm, const tt_mlp_embed_t* embed,
+               int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* 1 when tt_mlp_fwd(embed = ...) can form x = P * table inside the tower kernel for these shapes. */
+int tt_mlp_fwd_embed_ok(int E, int H, int64_t V);
 int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2,
                const float* h1, const float* z, int64_t R, int E, int H,
                float* dx, float* dw1, float* db1, float* dw2, float* db2,

@@ -121,18 +121,31 @@ def test_embed_fused_tower_backward(R, L, V, E, H):
     h1 = torch.empty(R, H, **f32); yb = torch.empty(R, H, dtype=torch.bfloat16, device=DEV); inv = torch.empty(R, **f32)
     ws = torch.empty(int(lib.tt_mlp_workspace(R, E, H, 1)), dtype=torch.uint8, device=DEV)
     _lib.check(lib.tt_mlp_fwd(pt(pooled), pt(tw1), pt(tb1), pt(tw2), pt(tb2), R, E, H, pt(h1), None, None, pt(yb), pt(pooled_b),
-                              None, None, None, pt(inv), 1, pt(ws), ws.numel(), s), "mlp_fwd")
+                              None, None, None, pt(inv), None, 1, pt(ws), ws.numel(), s), "mlp_fwd")
     f = np.float64
     x64 = rP @ table.astype(f)
     a1 = x64 @ w1.astype(f).T + b1
     rz = np.maximum(a1, 0) @ w2.astype(f).T + b2
     close(yb, O.normalize(rz), BF16_RTOL, "y_bf16")
     close(inv, 1.0 / np.maximum(np.linalg.norm(rz, axis=1), 1e-12), BF16_RTOL, "inv_norm")
+    # forward with x = P table formed inside the tower kernel (char-sized vocabularies)
+    if lib.tt_mlp_fwd_embed_ok(E, H, V):
+        w1b, w2b, tabb = tt.ops.cast_bf16(tw1), tt.ops.cast_bf16(tw2), tt.ops.cast_bf16(ttab)
+        h1_2 = torch.empty(R, H, **f32); yb2 = torch.empty(R, H, dtype=torch.bfloat16, device=DEV); inv2 = torch.empty(R, **f32)
+        P2 = torch.empty(R, V, dtype=torch.bfloat16, device=DEV); il2 = torch.empty(R, **f32)
+        _lib.check(lib.tt_embed_pool_fwd(pt(tids), 8, pt(ttab), R, L, V, E, None, pt(il2), None, pt(P2), s), "pool only")
+        assert torch.equal(P2, P) and torch.equal(il2, inv_len)
+        femb = _lib.MlpEmbed(pt(P2), V, pt(ttab), pt(tabb), None, 0, None, 0)
+        _lib.check(lib.tt_mlp_fwd(None, pt(tw1), pt(tb1), pt(tw2), pt(tb2), R, E, H, pt(h1_2), None, None, pt(yb2), None,
+                                  pt(w1b), pt(w2b), None, pt(inv2), C.byref(femb), 1, pt(ws), ws.numel(), s), "mlp_fwd embed")
+        torch.cuda.synchronize()
+        close(yb2, O.normalize(rz), BF16_RTOL, "y_bf16 (x = P table in-kernel)")
+        close(inv2, 1.0 / np.maximum(np.linalg.norm(rz, axis=1), 1e-12), BF16_RTOL, "inv_norm (in-kernel x)")
     # backward, embed-fused
     dw1 = torch.empty(H, E, **f32); db1 = torch.empty(H, **f32); dw2 = torch.empty(H, H, **f32); db2 = torch.empty(H, **f32)
     dtab = torch.full((V, E), 7.0, **f32)
     ews = torch.empty(int(lib.tt_mlp_embed_workspace(V, H, R)), dtype=torch.uint8, device=DEV)
-    emb = _lib.MlpEmbed(pt(P), V, pt(ttab), pt(dtab), 0, pt(ews), ews.numel())
+    emb = _lib.MlpEmbed(pt(P), V, pt(ttab), None, pt(dtab), 0, pt(ews), ews.numel())
     def run_bwd():
         _lib.check(lib.tt_mlp_bwd(pt(tdy), pt(pooled), pt(tw1), pt(tw2), pt(h1), None, R, E, H, None, pt(dw1), pt(db1), pt(dw2),
                                   pt(db2), pt(pooled_b), None, None, None, 1, 0, C.byref(emb), pt(yb), pt(inv), None, None, 1,

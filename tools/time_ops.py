@@ -65,7 +65,7 @@ def main():
     db = tr.y_bf16[B:2 * B] if tr.y_bf16 is not None else None
     qf, df = tr.y[:B], tr.y[B:2 * B]
     ops = {
-        "embed_pool_fwd": lambda: check(lib.tt_embed_pool_fwd(_p(tr.ids), 8, _p(tr.table), R, tr.L, tr.V, tr.E, _p(tr.pooled), _p(tr.inv_len), _p(tr.pooled_bf16), _p(tr.pool_bf16), s()), "x"),
+        "embed_pool_fwd": lambda: check(lib.tt_embed_pool_fwd(_p(tr.ids), 8, _p(tr.table), R, tr.L, tr.V, tr.E, None if tr.embed_in_tower else _p(tr.pooled), _p(tr.inv_len), None if tr.embed_in_tower else _p(tr.pooled_bf16), _p(tr.pool_bf16), s()), "x"),
         "tower_fwd": lambda: tr._tower_fwd(0),
         "ce_fwd": lambda: tr._local_loss_fwd(s()),
         "ce_bwd": lambda: tr._local_loss_bwd(s()),
@@ -97,6 +97,15 @@ def main():
         t = timed(prefix, flush)
         print(f"prefix..{names[k - 1]:16s} {t:9.1f} us   (+{t - prev:6.1f})")
         prev = t
+    # back-to-back repeats of one op inside one graph: (T10 - T1) / 9 = kernel duration + launch boundary, without the
+    # single-graph replay floor
+    for name in names:
+        t1 = timed(ops[name], flush)
+        def rep10(name=name):
+            for _ in range(10):
+                ops[name]()
+        t10 = timed(rep10, flush)
+        print(f"repeat {name:16s} T1 {t1:7.1f}  T10 {t10:7.1f}  per launch-group {(t10 - t1) / 9:6.1f} us")
     # launch-boundary cost: 32 back-to-back AdamW launches over a tiny slice
     def chain():
         for _ in range(32):

@@ -29,7 +29,8 @@ SIGNATURES = {
     "tt_embed_pool_bwd_workspace": (_sz, [_i64, _i, _i64, _i]),
     "tt_embed_pool_bwd": (_i, [_vp, _i, _vp, _vp, _i64, _i, _i64, _i, _vp, _vp, _sz, _vp]),
     "tt_mlp_workspace": (_sz, [_i64, _i, _i, _i]),
-    "tt_mlp_fwd": (_i, [_vp] * 5 + [_i64, _i, _i] + [_vp] * 9 + [_i, _vp, _sz, _vp]),
+    "tt_mlp_fwd": (_i, [_vp] * 5 + [_i64, _i, _i] + [_vp] * 10 + [_i, _vp, _sz, _vp]),
+    "tt_mlp_fwd_embed_ok": (_i, [_i, _i, _i64]),
     "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 9 + [_i, _i64, _vp, _vp, _vp, _vp, _vp] + [_i, _vp, _sz, _vp]),
     "tt_mlp_embed_workspace": (_sz, [_i64, _i, _i64]),
     "tt_proj_ln_workspace": (_sz, [_i64, _i, _i]),
@@ -54,7 +55,7 @@ SIGNATURES = {
 
 class MlpEmbed(C.Structure):
     """tt_mlp_embed_t (include/tt_b200.h)"""
-    _fields_ = [("pool_bf16", _vp), ("V", _i64), ("table", _vp), ("d_table", _vp), ("accumulate", _i),
+    _fields_ = [("pool_bf16", _vp), ("V", _i64), ("table", _vp), ("table_bf16", _vp), ("d_table", _vp), ("accumulate", _i),
                 ("workspace", _vp), ("workspace_bytes", _sz)]
 
 

@@ -199,6 +199,37 @@ pool_matrix_kernel(const IdT* __restrict__ ids, const float* __restrict__ inv_le
   for (int v = lane; v < V; v += 32) P[row * V + v] = (float)h[v] * il;
 }
 
+// Forward without the gather: only the pooling matrix P (bf16) and 1/len.  Used when the consumer forms x = P table on
+// the tensor cores itself (tt_mlp_fwd with embed): the [rows,E] pooled tensor then never exists.
+template <typename IdT>
+__global__ void __launch_bounds__(256)
+pool_only_kernel(const IdT* __restrict__ ids, int64_t rows, int L, int V, float* __restrict__ inv_len,
+                 __nv_bfloat16* __restrict__ P) {
+  extern __shared__ int hist[];                       // [warps][V]
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int* h = hist + w * V;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
+  if (row >= rows) return;
+  for (int v = lane; v < V; v += 32) h[v] = 0;
+  __syncwarp();
+  int cnt = 0;
+  for (int t0 = 0; t0 < L; t0 += 32) {
+    const int t = t0 + lane;
+    const int64_t id = t < L ? load_id(ids + row * L + t) : 0;
+    const bool ok = id > 0 && id < V;
+    if (ok) atomicAdd(&h[(int)id], 1);                // integer: exact, order-independent
+    cnt += __popc(__ballot_sync(0xffffffffu, ok));
+  }
+  __syncwarp();
+  const float il = 1.0f / ((float)cnt + 1e-9f);       // encoders.py:72
+  if (lane == 0 && inv_len) inv_len[row] = il;
+  for (int v = lane * 2; v < V; v += 64) {             // V is even on this path (V % 8 == 0)
+    *reinterpret_cast<uint32_t*>(P + row * V + v) = pack_bf16x2((float)h[v] * il, (float)h[v + 1] * il);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // K2 backward, large tables: sort + ordered segmented reduction
 // ---------------------------------------------------------------------------------------
@@ -323,6 +354,12 @@ static int embed_pool_fwd_t(const IdT* ids, const float* table, int64_t rows, in
   const unsigned grid = (unsigned)ceil_div(rows, warps);
   if (pool_bf16 && V > kSmallVocab) { set_error("embed_pool_fwd: the pooling-matrix output needs V <= %d", kSmallVocab); return TT_ERR_UNSUPPORTED; }
   const size_t hsm = pool_bf16 ? (size_t)warps * V * sizeof(int) : 0;
+  if (pooled == nullptr) {                             // histogram only: the consumer multiplies P by the table itself
+    if (!pool_bf16 || V % 8 != 0) { set_error("embed_pool_fwd: pooled == NULL needs pool_bf16 and V %% 8 == 0"); return TT_ERR_INVALID; }
+    TT_CUDA(launch_kernel(pool_only_kernel<IdT>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, rows, L, (int)V, inv_len, pool_bf16));
+    TT_LAUNCH_CHECK("pool_only_kernel");
+    return TT_OK;
+  }
   const bool vec = (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(table) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(pooled) & 15) == 0) &&
                    (pooled_bf16 == nullptr || (reinterpret_cast<uintptr_t>(pooled_bf16) & 7) == 0);
@@ -420,7 +457,7 @@ int tt_embed_gather(const void* ids, int id_bytes, const float* table, int64_t n
 int tt_embed_pool_fwd(const void* ids, int id_bytes, const float* table, int64_t rows, int L, int64_t V,
                       int E, float* pooled, float* inv_len, void* pooled_bf16, void* pool_bf16, void* stream) {
   TT_REQUIRE_DEVICE();
-  TT_CHECK_ARG(ids && table && pooled && rows >= 0 && L > 0 && V > 0 && E > 0, "embed_pool_fwd: bad arguments");
+  TT_CHECK_ARG(ids && table && (pooled || pool_bf16) && rows >= 0 && L > 0 && V > 0 && E > 0, "embed_pool_fwd: bad arguments");
   TT_CHECK_ARG(id_bytes == 4 || id_bytes == 8, "embed_pool_fwd: id_bytes must be 4 or 8");
   if (rows == 0) return TT_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

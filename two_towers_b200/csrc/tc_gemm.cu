@@ -722,8 +722,8 @@ static bool tc_mlp_supported(int E, int H) { return (E % 8 == 0) && (H % 8 == 0)
 
 int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t R, int E,
                int H, float* h1, float* z, float* y, __nv_bfloat16* y_bf16, const __nv_bfloat16* x_bf16,
-               const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16, __nv_bfloat16* h1_bf16, float* inv_norm, void* ws,
-               size_t ws_bytes, cudaStream_t s) {
+               const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16, __nv_bfloat16* h1_bf16, float* inv_norm,
+               const tt_mlp_embed_t* embed, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0 (E=%d H=%d)", E, H); return TT_ERR_UNSUPPORTED; }
   const TcMlpPlan plan = plan_tc_mlp(R, E, H);
   if (ws == nullptr || ws_bytes < plan.total) { set_error("tc_mlp_fwd: workspace too small (%zu < %zu)", ws_bytes, plan.total); return TT_ERR_WORKSPACE; }
@@ -733,6 +733,11 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
   __nv_bfloat16* w2b = w.take<__nv_bfloat16>((size_t)H * H);
   __nv_bfloat16* h1b = w.take<__nv_bfloat16>((size_t)R * H);
   int rc = TT_OK;
+  if (embed) {
+    if (!w1_bf16 || !w2_bf16 || !tc_mlp_fwd_pool_supported(E, H, embed->V)) { set_error("tc_mlp_fwd: embed needs bf16 weight shadows and a supported shape (tt_mlp_fwd_embed_ok)"); return TT_ERR_UNSUPPORTED; }
+    return tc_mlp_fwd_fused(nullptr, w1_bf16, b1, w2_bf16, b2, R, E, H, h1_bf16 ? h1_bf16 : reinterpret_cast<__nv_bfloat16*>(h1), z, y, y_bf16,
+                            inv_norm, (const __nv_bfloat16*)embed->pool_bf16, embed->V, (const __nv_bfloat16*)embed->table_bf16, s);
+  }
   if (!x_bf16 || !w1_bf16 || !w2_bf16) {       // only the operands without a caller-provided shadow are converted
     rc = tc::cast3(x_bf16 ? nullptr : x, xb, x_bf16 ? 0 : R * E, w1_bf16 ? nullptr : w1, w1b, w1_bf16 ? 0 : (int64_t)H * E,
                    w2_bf16 ? nullptr : w2, w2b, w2_bf16 ? 0 : (int64_t)H * H, s);
@@ -745,7 +750,7 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
   // so large enough) h1 buffer itself -- TT_PREC_BF16 treats h1 as opaque saved state.
   h1b = h1_bf16 ? h1_bf16 : reinterpret_cast<__nv_bfloat16*>(h1);
   if (tc_mlp_fused_supported(E, H))
-    return tc_mlp_fwd_fused(xa, w1a, b1, w2a, b2, R, E, H, h1b, z, y, y_bf16, inv_norm, s);
+    return tc_mlp_fwd_fused(xa, w1a, b1, w2a, b2, R, E, H, h1b, z, y, y_bf16, inv_norm, nullptr, 0, nullptr, s);
   if (z == nullptr) z = w.take<float>((size_t)R * H);     // unfused shapes: the pre-normalise tensor lives in the workspace
   tc::TcGemm g{};
   g.M = (int)R; g.N = H; g.K = E; g.A = xa; g.a_mn = 0; g.B = w1a; g.b_mn = 0;

@@ -64,6 +64,7 @@ struct FwdFinalize {
   float* tile_sums;            // [row tiles][2]: sum(lse - pos), sum(pos)
   float* lse; float* loss; float* pos_mean;
   float loss_scale;
+  long long* dbg;              // developer aid (TT_CE_DEBUG): [cta][4] %globaltimer stamps
 };
 
 __global__ void __launch_bounds__(CE_THREADS, 1)
@@ -73,6 +74,9 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  float* __restrict__ part_ml, float* __restrict__ pos_logit, const FwdFinalize fin) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
+  long long* fdbg = fin.dbg ? fin.dbg + 4 * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+#define TT_FWD_STAMP(slot) do { if (fdbg && threadIdx.x == 64) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); fdbg[slot] = t_; } } while (0)
+  TT_FWD_STAMP(0);
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // stays in the shared address space
   const int kq = H / 64;                                  // 64-wide K blocks
   const uint32_t d_bytes = (uint32_t)FWD_BN * H * 2;      // == Q tile bytes (both are 128 rows)
@@ -173,6 +177,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(q_ready);
+    TT_FWD_STAMP(1);
     float m = -CUDART_INF_F, l = 0.f;
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
@@ -222,6 +227,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       l = l * fast_exp2((m - mnew) * c) + ((s0 + s1) + (s2 + s3));
       m = mnew;
     }
+    TT_FWD_STAMP(2);
     if (row < Bq) {                                          // a split without tiles contributes (-inf, 0)
       part_ml[((int64_t)blockIdx.y * Bq + row) * 2 + 0] = nt > 0 ? m * inv_temp : -CUDART_INF_F;
       part_ml[((int64_t)blockIdx.y * Bq + row) * 2 + 1] = l;
@@ -231,6 +237,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_s, 512);
+  TT_FWD_STAMP(3);
   if (fin.counters == nullptr) return;
 
   // ---- finalisation by whichever CTA of this row tile finishes last ----
@@ -866,9 +873,23 @@ int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* 
     fin.tile_sums = reinterpret_cast<float*>(static_cast<char*>(sync_scratch) + align_up((size_t)(grid.x + 1) * 4, 16));
     fin.lse = lse; fin.loss = loss; fin.pos_mean = pos_mean; fin.loss_scale = loss_scale;
   }
+  static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
+  long long* dbg_dev = nullptr;
+  const size_t ncta = (size_t)grid.x * grid.y;
+  if (dbg_on) { cudaMalloc(&dbg_dev, ncta * 4 * sizeof(long long)); cudaMemset(dbg_dev, 0, ncta * 4 * sizeof(long long)); fin.dbg = dbg_dev; }
   TT_CUDA(launch_kernel(tc::tc_ce_fwd_kernel, grid, dim3(tc::CE_THREADS), smem, s, true, tmQ, tmD, Bq, Bd, H, inv_temp, label_offset, per,
                         d_blk, d_blk_stride, d_blk_off, part_ml, pos, fin));
   TT_LAUNCH_CHECK("tc_ce_fwd_kernel");
+  if (dbg_on) {
+    std::vector<long long> h(ncta * 4);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dbg_dev);
+    long long g0 = 0;
+    for (size_t i = 0; i < ncta; ++i) if (h[4 * i] && (!g0 || h[4 * i] < g0)) g0 = h[4 * i];
+    printf("[tt ce_fwd per-CTA ns] grid %u x %u, %d tiles per CTA: start q_ready loop_done end\n", grid.x, grid.y, per);
+    for (size_t i = 0; i < ncta; i += 9) printf("  cta %3zu: %6lld %6lld %6lld %6lld\n", i, h[4 * i] - g0, h[4 * i + 1] - g0, h[4 * i + 2] - g0, h[4 * i + 3] - g0);
+  }
   if (sync_scratch) return TT_OK;
   return inbatch_finalize(part_ml, pos, ns, Bq, inv_temp, loss_scale, lse, loss, pos_mean, nullptr, s);
 }

@@ -32,12 +32,16 @@ struct MlpFwdParams {
   float* y;               // [R,H] nullable
   __nv_bfloat16* yb;      // [R,H] nullable
   float* inv_norm;        // [R] nullable: 1 / max(|z|, 1e-12)
+  int V;                  // > 0: x = P * table is formed in-kernel (GEMM 0) from the pooling matrix and the bf16 table
 };
 
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmH1,
-                  const __grid_constant__ CUtensorMap tmY, const MlpFwdParams p) {
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmT, const MlpFwdParams p) {
+  // pool mode (p.V > 0): tmX maps the pooling matrix P [R,V] and tmT the bf16 table [V,E].  GEMM 0 forms
+  // x = P table (accumulator in TMEM columns [256, 256+E)), the warps round it to bf16 straight into the swizzled
+  // x tile GEMM 1 reads: the pooled activations never touch HBM.  P and the table borrow the hidden-tile bytes.
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
@@ -61,7 +65,13 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* bar_acc1 = bars + 4; // accumulator 1 ready
   uint64_t* bar_h1 = bars + 5;   // hidden tile written (4 warps)
   uint64_t* bar_acc2 = bars + 6; // accumulator 2 ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* bar_p = bars + 7;    // pool mode: P tile + table landed
+  uint64_t* bar_acc0 = bars + 8; // pool mode: accumulator 0 (x) ready
+  uint64_t* bar_x0 = bars + 9;   // pool mode: x tile written (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int kV = p.V / 64;                                         // pool mode: k-blocks of GEMM 0
+  uint8_t* p_tile = h1_tile;                                       // [128 x V] bf16, kV k-blocks of 16 KB
+  uint8_t* t_tile = h1_tile + (uint32_t)kV * MLP_BM * 128;         // table, MN-major: E/64 boxes of [V rows x 128 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * MLP_BM;
@@ -70,6 +80,7 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     mbar_init(bar_x, 1); mbar_init(bar_w2a, 1); mbar_init(bar_w2b, 1); mbar_init(bar_g1, 1);
     mbar_init(bar_acc1, 1); mbar_init(bar_h1, 4); mbar_init(bar_acc2, 1);
+    mbar_init(bar_p, 1); mbar_init(bar_acc0, 1); mbar_init(bar_x0, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -85,8 +96,15 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(bar_x, a_bytes);
-      for (int kb = 0; kb < kE; ++kb) tma_load_2d(x_tile + kb * (MLP_BM * 128), &tmX, bar_x, kb * 64, (int)m0);
+      if (kV > 0) {
+        mbar_arrive_expect_tx(bar_p, (uint32_t)kV * MLP_BM * 128 + (uint32_t)p.V * E * 2);
+        for (int kb = 0; kb < kV; ++kb) tma_load_2d(p_tile + kb * (MLP_BM * 128), &tmX, bar_p, kb * 64, (int)m0);
+        for (int nb = 0; nb < kE; ++nb) tma_load_2d(t_tile + (uint32_t)nb * p.V * 128, &tmT, bar_p, nb * 64, 0);
+        mbar_arrive_expect_tx(bar_x, w1_bytes);
+      } else {
+        mbar_arrive_expect_tx(bar_x, a_bytes);
+        for (int kb = 0; kb < kE; ++kb) tma_load_2d(x_tile + kb * (MLP_BM * 128), &tmX, bar_x, kb * 64, (int)m0);
+      }
       for (int kb = 0; kb < kE; ++kb) tma_load_2d(w1_tile + (uint32_t)kb * w2_blk, &tmW1, bar_x, kb * 64, 0);
       if (kH > 1) {
         mbar_arrive_expect_tx(bar_w2b, (uint32_t)(kH - 1) * w2_blk);
@@ -105,6 +123,22 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t idesc = umma_idesc_bf16(MLP_BM, H, 0, 0);
     const uint64_t dx = umma_desc_kmajor(smem_u32(x_tile), 0);
     const uint64_t dw1 = umma_desc_kmajor(smem_u32(w1_tile), 0);
+    if (kV > 0) {                                                  // GEMM 0: x = P table  (A K-major, B = table read MN-major)
+      const uint32_t idesc0 = umma_idesc_bf16(MLP_BM, E, 0, 1);
+      const uint64_t dp = umma_desc_kmajor(smem_u32(p_tile), 0);
+      const uint64_t dt = umma_desc_mnmajor(smem_u32(t_tile), 0, (uint32_t)p.V * 128);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      for (int kb = 0; kb < kV; ++kb)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (elect_one())
+            umma_bf16(tmem_a2, dp + (uint64_t)(kb * (MLP_BM * 128 / 16) + k * 2), dt + (uint64_t)((kb * 4 + k) * 128), idesc0, (kb | k) != 0);
+        }
+      if (elect_one()) umma_commit(bar_acc0);
+      __syncwarp();
+      mbar_wait(bar_x0, 0);                                        // x tile written by the warps
+    }
     mbar_wait(bar_x, 0);
     tc_fence_after();
     for (int kb = 0; kb < kE; ++kb)
@@ -139,6 +173,29 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int64_t row = m0 + lrow;
     const bool row_ok = row < p.R;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    if (kV > 0) {
+      // ---- epilogue 0 (pool mode): x = acc0 -> bf16 -> swizzled x tile (A operand of GEMM 1) -----------------------
+      mbar_wait(bar_acc0, 0);
+      tc_fence_after();
+      for (int c = 0; c < E / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem_a2 + lane_addr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        uint8_t* xrow = x_tile + (uint32_t)(c >> 1) * (MLP_BM * 128) + lrow * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint4 v = make_uint4(pack_bf16x2(__uint_as_float(r[8 * u]), __uint_as_float(r[8 * u + 1])),
+                                     pack_bf16x2(__uint_as_float(r[8 * u + 2]), __uint_as_float(r[8 * u + 3])),
+                                     pack_bf16x2(__uint_as_float(r[8 * u + 4]), __uint_as_float(r[8 * u + 5])),
+                                     pack_bf16x2(__uint_as_float(r[8 * u + 6]), __uint_as_float(r[8 * u + 7])));
+          *reinterpret_cast<uint4*>(xrow + ((((c & 1) * 4 + u) ^ (lrow & 7)) << 4)) = v;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_x0);
+    }
     // ---- epilogue 1: hidden = relu(acc1 + b1) -> bf16 -> smem A tile + global h1 ------------------------------
     mbar_wait(bar_acc1, 0);
     tc_fence_after();
@@ -238,7 +295,7 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 static size_t mlp_fused_smem(int E, int H) {
   const int kE = E / 64, kH = H / 64;
   return 1024 + (size_t)kE * MLP_BM * 128 + (size_t)kE * H * 128 + (size_t)(kH - 1) * H * 128 + (size_t)kH * MLP_BM * 128 +
-         2 * (size_t)H * 4 + 8 * 8 + 16;
+         2 * (size_t)H * 4 + 12 * 8 + 16;
 }
 
 }  // namespace tc
@@ -251,20 +308,36 @@ bool tc_mlp_fused_supported(int E, int H) {
   return tc::mlp_fused_smem(E, H) <= 227 * 1024;
 }
 
+// x = P table inside the kernel: V a multiple of 64, P tile + table fit the hidden-tile bytes, E <= 256 accumulator columns
+bool tc_mlp_fwd_pool_supported(int E, int H, int64_t V) {
+  if (!tc_mlp_fused_supported(E, H) || V < 64 || V % 64 != 0 || V > 256) return false;   // TMA box: <= 256 rows
+  return (size_t)(V / 64) * tc::MLP_BM * 128 + (size_t)V * E * 2 <= (size_t)(H / 64) * tc::MLP_BM * 128;
+}
+
 int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const float* b1, const __nv_bfloat16* w2b,
                      const float* b2, int64_t R, int E, int H, __nv_bfloat16* h1b, float* z, float* y,
-                     __nv_bfloat16* yb, float* inv_norm, cudaStream_t s) {
-  CUtensorMap tmX, tmW1, tmW2, tmH1, tmY;
-  int rc = tc::make_tmap_bf16(&tmX, xb, (uint64_t)R, (uint64_t)E, tc::MLP_BM); if (rc) return rc;
+                     __nv_bfloat16* yb, float* inv_norm, const __nv_bfloat16* pool, int64_t V, const __nv_bfloat16* table_bf16,
+                     cudaStream_t s) {
+  CUtensorMap tmX, tmW1, tmW2, tmH1, tmY, tmT;
+  int rc;
+  if (pool) {
+    if (!tc_mlp_fwd_pool_supported(E, H, V) || !table_bf16) { set_error("tc_mlp_fwd: in-kernel x = P table needs V %% 64 == 0 (<= 256), the bf16 table and a tile that fits"); return TT_ERR_UNSUPPORTED; }
+    rc = tc::make_tmap_bf16(&tmX, pool, (uint64_t)R, (uint64_t)V, tc::MLP_BM); if (rc) return rc;
+    rc = tc::make_tmap_bf16(&tmT, table_bf16, (uint64_t)V, (uint64_t)E, (uint32_t)V); if (rc) return rc;
+  } else {
+    rc = tc::make_tmap_bf16(&tmX, xb, (uint64_t)R, (uint64_t)E, tc::MLP_BM); if (rc) return rc;
+    tmT = tmX;
+  }
   rc = tc::make_tmap_bf16(&tmW1, w1b, (uint64_t)H, (uint64_t)E, (uint32_t)H); if (rc) return rc;
   rc = tc::make_tmap_bf16(&tmW2, w2b, (uint64_t)H, (uint64_t)H, (uint32_t)H); if (rc) return rc;
   rc = tc::make_tmap_bf16(&tmH1, h1b, (uint64_t)R, (uint64_t)H, 32); if (rc) return rc;          // store maps: 32-row boxes (one warp)
   rc = tc::make_tmap_bf16(&tmY, yb ? yb : h1b, (uint64_t)R, (uint64_t)H, 32); if (rc) return rc;
   tc::MlpFwdParams p{};
   p.R = R; p.E = E; p.H = H; p.b1 = b1; p.b2 = b2; p.h1b = h1b; p.z = z; p.y = y; p.yb = yb; p.inv_norm = inv_norm;
+  p.V = pool ? (int)V : 0;
   const size_t smem = tc::mlp_fused_smem(E, H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TT_CUDA(launch_kernel(tc::tc_mlp_fwd_kernel, dim3((unsigned)ceil_div(R, tc::MLP_BM)), dim3(tc::MLP_THREADS), smem, s, true, tmX, tmW1, tmW2, tmH1, tmY, p));
+  TT_CUDA(launch_kernel(tc::tc_mlp_fwd_kernel, dim3((unsigned)ceil_div(R, tc::MLP_BM)), dim3(tc::MLP_THREADS), smem, s, true, tmX, tmW1, tmW2, tmH1, tmY, tmT, p));
   TT_LAUNCH_CHECK("tc_mlp_fwd_kernel");
   return TT_OK;
 }

@@ -10,7 +10,7 @@ size_t tc_mlp_workspace(int64_t R, int E, int H);
 int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                int64_t R, int E, int H, float* h1, float* z, float* y, __nv_bfloat16* y_bf16,
                const __nv_bfloat16* x_bf16, const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16,
-               __nv_bfloat16* h1_bf16, float* inv_norm, void* ws, size_t ws_bytes, cudaStream_t s);
+               __nv_bfloat16* h1_bf16, float* inv_norm, const tt_mlp_embed_t* embed, void* ws, size_t ws_bytes, cudaStream_t s);
 int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2, const float* h1,
                const float* z, int64_t R, int E, int H, float* dx, float* dw1, float* db1, float* dw2,
                float* db2, const __nv_bfloat16* x_bf16, const __nv_bfloat16* w1_bf16,
@@ -23,7 +23,9 @@ size_t tc_mlp_embed_workspace(int64_t V, int H, int64_t R);
 bool tc_mlp_fused_supported(int E, int H);
 int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const float* b1, const __nv_bfloat16* w2b,
                      const float* b2, int64_t R, int E, int H, __nv_bfloat16* h1b, float* z, float* y,
-                     __nv_bfloat16* yb, float* inv_norm, cudaStream_t s);
+                     __nv_bfloat16* yb, float* inv_norm, const __nv_bfloat16* pool, int64_t V, const __nv_bfloat16* table_bf16,
+                     cudaStream_t s);
+bool tc_mlp_fwd_pool_supported(int E, int H, int64_t V);
 
 // fused similarity GEMM + online-LSE cross entropy on tcgen05 (tc_inbatch.cu)
 size_t tc_inbatch_workspace(int64_t Bq, int64_t Bd, int H);

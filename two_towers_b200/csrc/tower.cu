@@ -253,10 +253,12 @@ size_t tt_mlp_workspace(int64_t R, int E, int H, int precision) {
 
 int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                int64_t R, int E, int H, float* h1, float* z, float* y, void* y_bf16, const void* x_bf16,
-               const void* w1_bf16, const void* w2_bf16, void* h1_bf16, float* inv_norm, int precision,
-               void* workspace, size_t workspace_bytes, void* stream) {
+               const void* w1_bf16, const void* w2_bf16, void* h1_bf16, float* inv_norm,
+               const tt_mlp_embed_t* embed, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   TT_REQUIRE_DEVICE();
-  TT_CHECK_ARG(x && w1 && b1 && w2 && b2 && h1 && R >= 0 && E > 0 && H > 0, "mlp_fwd: bad arguments");
+  TT_CHECK_ARG((x || embed) && w1 && b1 && w2 && b2 && h1 && R >= 0 && E > 0 && H > 0, "mlp_fwd: bad arguments");
+  TT_CHECK_ARG(embed == nullptr || (precision == TT_PREC_BF16 && embed->pool_bf16 && embed->table_bf16 && embed->V > 0),
+               "mlp_fwd: embed needs TT_PREC_BF16, pool_bf16 and table_bf16");
   TT_CHECK_ARG(z || (precision == TT_PREC_BF16 && y_bf16 && inv_norm), "mlp_fwd: z may be null only in TT_PREC_BF16 with y_bf16 and inv_norm given");
   TT_CHECK_ARG(inv_norm == nullptr || precision == TT_PREC_BF16, "mlp_fwd: inv_norm is a TT_PREC_BF16 output");
   TT_CHECK_ARG(y || (precision == TT_PREC_BF16 && y_bf16), "mlp_fwd: y may be null only in TT_PREC_BF16 with y_bf16 given");
@@ -265,7 +267,7 @@ int tt_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == TT_PREC_BF16)
     return tt::tc_mlp_fwd(x, w1, b1, w2, b2, R, E, H, h1, z, y, (__nv_bfloat16*)y_bf16, (const __nv_bfloat16*)x_bf16,
-                          (const __nv_bfloat16*)w1_bf16, (const __nv_bfloat16*)w2_bf16, (__nv_bfloat16*)h1_bf16, inv_norm,
+                          (const __nv_bfloat16*)w1_bf16, (const __nv_bfloat16*)w2_bf16, (__nv_bfloat16*)h1_bf16, inv_norm, embed,
                           workspace, workspace_bytes, s);
   TT_CHECK_ARG(precision == TT_PREC_FP32, "mlp_fwd: unknown precision %d", precision);
   return tt::mlp_fwd_fp32(x, w1, b1, w2, b2, R, E, H, h1, z, y, (__nv_bfloat16*)y_bf16, workspace, workspace_bytes, s);
@@ -299,6 +301,8 @@ int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   TT_CHECK_ARG(dy_parts <= 1, "mlp_bwd: split dy slices are a TT_PREC_BF16 feature");
   return tt::mlp_bwd_fp32(dy, x, w1, w2, h1, z, R, E, H, dx, dw1, db1, dw2, db2, workspace, workspace_bytes, s);
 }
+
+int tt_mlp_fwd_embed_ok(int E, int H, int64_t V) { return (E > 0 && H > 0 && V > 0 && tt::tc_mlp_fwd_pool_supported(E, H, V)) ? 1 : 0; }
 
 size_t tt_mlp_embed_workspace(int64_t V, int H, int64_t R) {
   if (V <= 0 || H <= 0 || R <= 0) return 256;

@@ -137,7 +137,7 @@ def mlp_fwd(x, w1, b1, w2, b2, precision=None, want_bf16: bool = False):
     y_bf16 = torch.empty(R, H, dtype=torch.bfloat16, device=dev) if want_bf16 else None
     ws = _workspace(_lib_().tt_mlp_workspace(R, E, H, prec), dev)
     check(_lib_().tt_mlp_fwd(_p(x), _p(w1), _p(b1), _p(w2), _p(b2), R, E, H, _p(h1), _p(z), _p(y), _p(y_bf16),
-                             None, None, None, None, None, prec, _p(ws), ws.numel(), _stream()), "tt_mlp_fwd")
+                             None, None, None, None, None, None, prec, _p(ws), ws.numel(), _stream()), "tt_mlp_fwd")
     return y, h1, z, y_bf16
 
 

@@ -155,6 +155,11 @@ class FusedTrainer:
         self.embed_fused = bool(bf and self.train_table and self.V <= 1024 and self.V % 8 == 0 and self.E % 4 == 0 and
                                 all(isinstance(t, MeanPoolingTower) for t, _, _ in self.groups))
         self.pool_bf16 = torch.empty(R, self.V, dtype=torch.bfloat16, device=self.dev) if self.embed_fused else None
+        # ... and for char-sized vocabularies the tower kernel forms x = P table itself: the gather kernel shrinks to a
+        # histogram and the pooled activations never reach HBM
+        self.embed_in_tower = bool(self.embed_fused and os.environ.get("TT_EMBED_IN_TOWER", "1") != "0" and
+                                   self._shadow(self.table) is not None and
+                                   self.lib.tt_mlp_fwd_embed_ok(self.E, self.H, self.V))
         self.embed_ws = (torch.empty(int(max(self.lib.tt_mlp_embed_workspace(self.V, self.H, nr) for _, _, nr in self.groups)),
                                      dtype=torch.uint8, device=self.dev) if self.embed_fused else None)
         self.h1_bf16 = [torch.empty(nr, self.H, dtype=torch.bfloat16, device=self.dev) if bf else None
@@ -199,9 +204,14 @@ class FusedTrainer:
             # pure bf16 path: the normalise step is saved as (y_bf16, 1/|z|); the fp32 pre-normalise tensor is never written
             inv = self.inv_norm[r0:r0 + nr] if (pure and self.H <= 512) else None
             z_ptr = None if inv is not None else sv["z"]
+            emb = None
+            if self.embed_in_tower:
+                emb = _lib.MlpEmbed(self.pool_bf16[r0:r0 + nr].data_ptr(), self.V, self.table.data_ptr(),
+                                    self._shadow(self.table).data_ptr(), None, 0, None, 0)
             check(lib.tt_mlp_fwd(_p(x), _p(l1.weight), _p(l1.bias), _p(l2.weight), _p(l2.bias), nr, self.E, self.H,
                                  _p(sv["h1"]), _p(z_ptr), _p(y_ptr), _p(yb), _p(xb), _p(self._shadow(l1.weight)),
-                                 _p(self._shadow(l2.weight)), _p(self.h1_bf16[gi]), _p(inv), self.prec, _p(self.ws),
+                                 _p(self._shadow(l2.weight)), _p(self.h1_bf16[gi]), _p(inv),
+                                 C.byref(emb) if emb is not None else None, self.prec, _p(self.ws),
                                  self.ws.numel(), s), "tt_mlp_fwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
@@ -220,8 +230,8 @@ class FusedTrainer:
         xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
         emb = None
         if self.embed_fused:
-            emb = _lib.MlpEmbed(self.pool_bf16[r0:r0 + nr].data_ptr(), self.V, self.table.data_ptr(), self.table.grad.data_ptr(),
-                                1 if gi > 0 else 0, self.embed_ws.data_ptr(), self.embed_ws.numel())
+            emb = _lib.MlpEmbed(self.pool_bf16[r0:r0 + nr].data_ptr(), self.V, self.table.data_ptr(), None,
+                                self.table.grad.data_ptr(), 1 if gi > 0 else 0, self.embed_ws.data_ptr(), self.embed_ws.numel())
             dx = None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
@@ -251,8 +261,10 @@ class FusedTrainer:
         R = P * B
         idb = 8 if self.ids.dtype == torch.int64 else 4
         s = self._stream()
-        check(lib.tt_embed_pool_fwd(_p(self.ids), idb, _p(self.table), R, self.L, self.V, self.E, _p(self.pooled),
-                                    _p(self.inv_len), _p(self.pooled_bf16), _p(self.pool_bf16), s), "tt_embed_pool_fwd")
+        tower_pools = self.embed_in_tower                 # histogram only: the tower kernel multiplies P by the table
+        check(lib.tt_embed_pool_fwd(_p(self.ids), idb, _p(self.table), R, self.L, self.V, self.E,
+                                    None if tower_pools else _p(self.pooled), _p(self.inv_len),
+                                    None if tower_pools else _p(self.pooled_bf16), _p(self.pool_bf16), s), "tt_embed_pool_fwd")
         for gi in range(len(self.groups)):
             self._tower_fwd(gi)
         q, d = self.y[:B], self.y[B:2 * B]

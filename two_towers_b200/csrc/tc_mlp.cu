@@ -12,6 +12,7 @@
 // Compared with the unfused path (GEMM, GEMM, normalise) this is 1 launch instead of 3 and the
 // [R,H] hidden / pre-normalise tensors are written once and never re-read in the forward.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 #include "tensor_core.cuh"
@@ -20,7 +21,7 @@ namespace tt {
 namespace tc {
 
 constexpr int MLP_BM = 128;
-constexpr int MLP_THREADS = 192;
+constexpr int MLP_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 
 struct MlpFwdParams {
   int64_t R;
@@ -33,6 +34,7 @@ struct MlpFwdParams {
   __nv_bfloat16* yb;      // [R,H] nullable
   float* inv_norm;        // [R] nullable: 1 / max(|z|, 1e-12)
   int V;                  // > 0: x = P * table is formed in-kernel (GEMM 0) from the pooling matrix and the bf16 table
+  long long* dbg;         // developer aid (TT_MLP_DEBUG): CTA 0, thread 64: %globaltimer at each phase boundary
 };
 
 __global__ void __launch_bounds__(MLP_THREADS, 1)
@@ -44,6 +46,8 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // x tile GEMM 1 reads: the pooled activations never touch HBM.  P and the table borrow the hidden-tile bytes.
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
+#define TT_MLP_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[slot] = t_; } } while (0)
+  TT_MLP_STAMP(0);
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   const int E = p.E, H = p.H;
   const int kE = E / 64, kH = H / 64;
@@ -69,6 +73,7 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* bar_acc0 = bars + 8; // pool mode: accumulator 0 (x) ready
   uint64_t* bar_x0 = bars + 9;   // pool mode: x tile written (4 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* ss_s = reinterpret_cast<float*>(bars + 12);               // [2][128] per-half row sums of squares
   const int kV = p.V / 64;                                         // pool mode: k-blocks of GEMM 0
   uint8_t* p_tile = h1_tile;                                       // [128 x V] bf16, kV k-blocks of 16 KB
   uint8_t* t_tile = h1_tile + (uint32_t)kV * MLP_BM * 128;         // table, MN-major: E/64 boxes of [V rows x 128 B]
@@ -79,14 +84,14 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     mbar_init(bar_x, 1); mbar_init(bar_w2a, 1); mbar_init(bar_w2b, 1); mbar_init(bar_g1, 1);
-    mbar_init(bar_acc1, 1); mbar_init(bar_h1, 4); mbar_init(bar_acc2, 1);
-    mbar_init(bar_p, 1); mbar_init(bar_acc0, 1); mbar_init(bar_x0, 4);
+    mbar_init(bar_acc1, 1); mbar_init(bar_h1, 8); mbar_init(bar_acc2, 1);
+    mbar_init(bar_p, 1); mbar_init(bar_acc0, 1); mbar_init(bar_x0, 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   pdl_wait();                                                      // barrier init / TMEM alloc overlapped the previous kernel
   if (warp >= 2) {                                                 // biases -> smem (read as broadcasts later)
-    for (int i = threadIdx.x - 64; i < H; i += 128) { bias_s[i] = p.b1[i]; bias_s[H + i] = p.b2[i]; }
+    for (int i = threadIdx.x - 64; i < H; i += 256) { bias_s[i] = p.b1[i]; bias_s[H + i] = p.b2[i]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -154,30 +159,38 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint64_t dw2a = umma_desc_kmajor(smem_u32(base), 0);
     const uint64_t dw2b = umma_desc_kmajor(smem_u32(w2_rest), 0);
     mbar_wait(bar_h1, 0);
-    mbar_wait(bar_w2a, 0);
     if (kH > 1) mbar_wait(bar_w2b, 0);
     tc_fence_after();
-    for (int kb = 0; kb < kH; ++kb) {
+    // k-blocks 1.. of W2 have been resident since the start; k-block 0 (loaded late into the x/W1 bytes) goes last so
+    // its TMA latency hides behind the other MMAs
+    for (int it = 0; it < kH; ++it) {
+      const int kb = (it + 1) % kH;
+      if (kb == 0) { mbar_wait(bar_w2a, 0); tc_fence_after(); }
       const uint64_t dw = kb == 0 ? dw2a : dw2b + (uint64_t)((kb - 1) * (w2_blk >> 4));
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (elect_one())
-          umma_bf16(tmem_a2, dh + (uint64_t)(kb * (MLP_BM * 128 / 16) + k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_bf16(tmem_a2, dh + (uint64_t)(kb * (MLP_BM * 128 / 16) + k * 2), dw + (uint64_t)(k * 2), idesc, (it | k) != 0);
       }
     }
     if (elect_one()) umma_commit(bar_acc2);
     __syncwarp();
   } else {
-    const int quarter = warp & 3;
+    // epilogue warps 2..9: TMEM lane quarter = warp % 4, and the two warps of a quarter split the columns in halves
+    // (two warps per scheduler hide each other's instruction latency; the epilogues are instruction-bound)
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int lrow = quarter * 32 + lane;
     const int64_t row = m0 + lrow;
     const bool row_ok = row < p.R;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int nce = E / 32, nch = H / 32;                          // 32-column chunks (both even)
+    TT_MLP_STAMP(1);
     if (kV > 0) {
       // ---- epilogue 0 (pool mode): x = acc0 -> bf16 -> swizzled x tile (A operand of GEMM 1) -----------------------
       mbar_wait(bar_acc0, 0);
       tc_fence_after();
-      for (int c = 0; c < E / 32; ++c) {
+      TT_MLP_STAMP(2);
+      for (int c = half * (nce / 2); c < (half + 1) * (nce / 2); ++c) {
         uint32_t r[32];
         tmem_ld_x32(tmem_a2 + lane_addr + (uint32_t)(c * 32), r);
         tmem_ld_wait();
@@ -196,10 +209,12 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_x0);
     }
+    TT_MLP_STAMP(3);
     // ---- epilogue 1: hidden = relu(acc1 + b1) -> bf16 -> smem A tile + global h1 ------------------------------
     mbar_wait(bar_acc1, 0);
     tc_fence_after();
-    for (int c = 0; c < H / 32; ++c) {
+    TT_MLP_STAMP(4);
+    for (int c = half * (nch / 2); c < (half + 1) * (nch / 2); ++c) {
       uint32_t r[32];
       tmem_ld_x32(tmem_a1 + lane_addr + (uint32_t)(c * 32), r);
       tmem_ld_wait();
@@ -220,19 +235,22 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(bar_h1);
+    if (lane == 0) mbar_arrive(bar_h1);
+    asm volatile("bar.sync 2, 256;" ::: "memory");               // both column halves of every row are in the tile
+    if (half == 0 && lane == 0) {
       // the same swizzled tile GEMM 2 reads is also the source of the global h1 write: one TMA store per k-block of
-      // this warp's 32 rows (rows past R are clipped) instead of 1 KB-strided per-thread stores
+      // this quarter's 32 rows (rows past R are clipped) instead of 1 KB-strided per-thread stores
       for (int kb = 0; kb < kH; ++kb)
         tma_store_2d(&tmH1, h1_tile + (uint32_t)kb * (MLP_BM * 128) + quarter * 4096, kb * 64, (int)m0 + quarter * 32);
       tma_store_commit();
     }
+    TT_MLP_STAMP(5);
     // ---- epilogue 2: z = acc2 + b2; y = z / max(|z|, 1e-12) --------------------------------------------------
     mbar_wait(bar_acc2, 0);
     tc_fence_after();
+    TT_MLP_STAMP(6);
     float ss = 0.f;
-    for (int c = 0; c < H / 32; ++c) {
+    for (int c = half * (nch / 2); c < (half + 1) * (nch / 2); ++c) {
       uint32_t r[32];
       tmem_ld_x32(tmem_a2 + lane_addr + (uint32_t)(c * 32), r);
       tmem_ld_wait();
@@ -242,11 +260,12 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ss = fmaf(v, v, ss);
       }
     }
-    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-    if (p.inv_norm && row_ok) p.inv_norm[row] = inv;
-    if (lane == 0) tma_store_wait_read();                        // this warp's rows of the hidden tile have been read out:
-    __syncwarp();                                                // they now stage the bf16 y tile for its TMA store
-    for (int c = 0; c < H / 32; ++c) {
+    ss_s[half * MLP_BM + lrow] = ss;
+    if (half == 0 && lane == 0) tma_store_wait_read();           // the hidden tile has been read out by its TMA stores:
+    asm volatile("bar.sync 2, 256;" ::: "memory");               // it now stages the bf16 y tile
+    const float inv = 1.0f / fmaxf(sqrtf(ss_s[lrow] + ss_s[MLP_BM + lrow]), 1e-12f);
+    if (half == 0 && p.inv_norm && row_ok) p.inv_norm[row] = inv;
+    for (int c = half * (nch / 2); c < (half + 1) * (nch / 2); ++c) {
       uint32_t r[32];
       tmem_ld_x32(tmem_a2 + lane_addr + (uint32_t)(c * 32), r);
       tmem_ld_wait();
@@ -278,14 +297,16 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     if (p.yb) {
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (half == 0 && lane == 0) {
         for (int kb = 0; kb < kH; ++kb)
           tma_store_2d(&tmY, h1_tile + (uint32_t)kb * (MLP_BM * 128) + quarter * 4096, kb * 64, (int)m0 + quarter * 32);
         tma_store_commit();
       }
     }
-    if (lane == 0) tma_store_wait();                             // smem stays valid until every bulk store has completed
+    TT_MLP_STAMP(7);
+    if (half == 0 && lane == 0) tma_store_wait();                // smem stays valid until every bulk store has completed
+    TT_MLP_STAMP(8);
   }
   tc_fence_before();
   __syncthreads();
@@ -295,7 +316,7 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 static size_t mlp_fused_smem(int E, int H) {
   const int kE = E / 64, kH = H / 64;
   return 1024 + (size_t)kE * MLP_BM * 128 + (size_t)kE * H * 128 + (size_t)(kH - 1) * H * 128 + (size_t)kH * MLP_BM * 128 +
-         2 * (size_t)H * 4 + 12 * 8 + 16;
+         2 * (size_t)H * 4 + 12 * 8 + 16 + 2 * MLP_BM * 4;
 }
 
 }  // namespace tc
@@ -337,8 +358,19 @@ int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const fl
   p.V = pool ? (int)V : 0;
   const size_t smem = tc::mlp_fused_smem(E, H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool dbg_on = getenv("TT_MLP_DEBUG") != nullptr;
+  long long* dbg_dev = nullptr;
+  if (dbg_on) { cudaMalloc(&dbg_dev, 16 * sizeof(long long)); cudaMemset(dbg_dev, 0, 16 * sizeof(long long)); p.dbg = dbg_dev; }
   TT_CUDA(launch_kernel(tc::tc_mlp_fwd_kernel, dim3((unsigned)ceil_div(R, tc::MLP_BM)), dim3(tc::MLP_THREADS), smem, s, true, tmX, tmW1, tmW2, tmH1, tmY, tmT, p));
   TT_LAUNCH_CHECK("tc_mlp_fwd_kernel");
+  if (dbg_on) {
+    long long h[16];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(dbg_dev);
+    printf("[tt tc_mlp_fwd CTA 0, ns] start 0 | warps ready %lld | acc0 %lld | x written %lld | acc1 %lld | h1 written %lld | acc2 %lld | y staged %lld | stores done %lld\n",
+           h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0]);
+  }
   return TT_OK;
 }
 

@@ -101,7 +101,9 @@ def synth_ids(B, L, V, seed):
     g = torch.Generator().manual_seed(seed)
     lens = torch.randint(8, L + 1, (B, 1), generator=g)
     ids = torch.randint(1, V, (B, L), generator=g)
-    return torch.where(torch.arange(L)[None, :] < lens, ids, torch.zeros_like(ids))
+    # int32 on the wire: tokenisers.encode_batch(out=<pinned int32 buffer>) fills such arrays directly and the kernels read
+    # int32 ids as they are (the reference's int64 ids are a torch default, not a requirement -- SURVEY 8f-2)
+    return torch.where(torch.arange(L)[None, :] < lens, ids, torch.zeros_like(ids)).to(torch.int32)
 
 
 # ------------------------------------------------------------------------------------------
@@ -114,7 +116,7 @@ def cpu_train_baseline(steps, warmup):
     torch.manual_seed(0)
     model = P.PortTwoTower(CFG["V"], CFG["E"], CFG["H"], tied=True)
     opt = torch.optim.AdamW(model.parameters(), lr=CFG["lr"])
-    q, d = synth_ids(CFG["B"], CFG["L"], CFG["V"], 1234), synth_ids(CFG["B"], CFG["L"], CFG["V"], 4321)
+    q, d = synth_ids(CFG["B"], CFG["L"], CFG["V"], 1234).long(), synth_ids(CFG["B"], CFG["L"], CFG["V"], 4321).long()   # torch.long, as the reference feeds nn.Embedding
     for _ in range(warmup):
         P.train_step(model, opt, "in_batch", q, d, temperature=CFG["temperature"])
     t0 = time.perf_counter()
@@ -189,7 +191,8 @@ def bench_train(args, dev, rank, world, pg):
     emb = tt.embeddings.build("lookup", CFG["V"], embedding_dim=CFG["E"])
     model = tt.build_two_tower("mean", emb, hidden_dim=CFG["H"], tied_weights=True).to(dev)
     tr = tt.FusedTrainer(model, loss="in_batch", temperature=CFG["temperature"], lr=CFG["lr"], batch_size=CFG["B"],
-                         max_len=CFG["L"], precision=args.precision, process_group=pg, global_negatives=True)
+                         max_len=CFG["L"], precision=args.precision, process_group=pg, global_negatives=True,
+                         id_dtype=torch.int32)
     B, L, V = CFG["B"], CFG["L"], CFG["V"]
     host_q = [synth_ids(B, L, V, 1234 + rank + 100 * i).pin_memory() for i in range(4)]
     host_d = [synth_ids(B, L, V, 4321 + rank + 100 * i).pin_memory() for i in range(4)]
@@ -232,11 +235,16 @@ def bench_train(args, dev, rank, world, pg):
     t0 = time.perf_counter()
     last = 0.0
     tr.prefetch(host_q[0], host_d[0])                       # every step's H2D copy is inside the timed region;
+    pending = None
     for i in range(args.steps):                             # the copy of batch i+1 overlaps the compute of batch i
-        loss_t = tr.step()
-        if i + 1 < args.steps:
+        tr.step()
+        nxt = tr.read_loss_async()                          # D2H read of EVERY step's loss (pinned ring), consumed one
+        if i + 1 < args.steps:                              # step late so the host never stalls the GPU
             tr.prefetch(host_q[(i + 1) % 4], host_d[(i + 1) % 4])
-        last = loss_t.item()                                # D2H read of the loss every step (host sync, like the reference)
+        if pending is not None:
+            last = pending()
+        pending = nxt
+    last = pending()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -249,7 +257,7 @@ def bench_train(args, dev, rank, world, pg):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     t_dev, t_e2e = t.tolist()
     return dict(t_dev=t_dev, t_e2e=t_e2e, clocks=clocks, launches_per_step=launches_per_step, roof=roof,
-                loss=last, h2d=2 * B * L * 8, d2h=4)
+                loss=last, h2d=2 * B * L * 4, d2h=4)
 
 
 def time_train_local_negatives(args, dev, rank, world, pg):
@@ -261,7 +269,8 @@ def time_train_local_negatives(args, dev, rank, world, pg):
     emb = tt.embeddings.build("lookup", CFG["V"], embedding_dim=CFG["E"])
     model = tt.build_two_tower("mean", emb, hidden_dim=CFG["H"], tied_weights=True).to(dev)
     tr = tt.FusedTrainer(model, loss="in_batch", temperature=CFG["temperature"], lr=CFG["lr"], batch_size=CFG["B"],
-                         max_len=CFG["L"], precision=args.precision, process_group=pg, global_negatives=False)
+                         max_len=CFG["L"], precision=args.precision, process_group=pg, global_negatives=False,
+                         id_dtype=torch.int32)
     B, L, V = CFG["B"], CFG["L"], CFG["V"]
     dev_q = [synth_ids(B, L, V, 1234 + rank + 100 * i).to(dev) for i in range(4)]
     dev_d = [synth_ids(B, L, V, 4321 + rank + 100 * i).to(dev) for i in range(4)]
@@ -482,7 +491,7 @@ def main():
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": config_dict(world, args.precision),
             "e2e": {"value": gb * K / tr["t_e2e"], "unit": "pairs/s", "h2d_bytes_per_step": tr["h2d"],
-                    "d2h_bytes_per_step": tr["d2h"], "api": "FusedTrainer.prefetch(pinned int64 q_ids, d_ids) / .step().item() -- H2D of batch i+1 overlaps step i"},
+                    "d2h_bytes_per_step": tr["d2h"], "api": "FusedTrainer.prefetch(pinned int32 q_ids, d_ids) / .step() / .read_loss_async() -- H2D of batch i+1 overlaps step i, every loss is read on the host one step late"},
             "gpu_launches": int(tr["launches_per_step"]) * K,
             "gpu_launches_per_step": int(tr["launches_per_step"]),
             "clocks": tr["clocks"], "roofline": tr["roof"], "final_loss": tr["loss"],

@@ -298,20 +298,28 @@ def test_inbatch_bf16_full_size_known_answers():
     close(dq, rq.cpu().numpy(), 3e-2, "dq vs fp32 kernel"); close(dd, rd.cpu().numpy(), 3e-2, "dd vs fp32 kernel")
 
 
-def test_fused_trainer_bf16_tracks_fp32():
-    """Same batch, same init: one bf16 tensor-core step stays within 2e-2 of the fp32 step."""
+@pytest.mark.parametrize("B,tied,id_dtype", [(1024, True, torch.int64), (4096, True, torch.int32), (4096, False, torch.int64)])
+def test_fused_trainer_bf16_tracks_fp32(B, tied, id_dtype):
+    """Same batch, same init: one bf16 tensor-core step stays within 2e-2 of the fp32 step.  B = 4096 takes every fused
+    path of the trainer (pooling matrix in the tower kernel, loss backward fused with the normalise backward through
+    CTA pairs, embedding gradient through P^T da1); B = 1024 the split-slice path; untied towers the accumulate path."""
     import copy
     import two_towers_b200 as tt
     torch.manual_seed(0)
     emb = tt.embeddings.build("lookup", 128, embedding_dim=64)
-    m32 = tt.build_two_tower("mean", emb, hidden_dim=256, tied_weights=True).to(DEV)
+    m32 = tt.build_two_tower("mean", emb, hidden_dim=256, tied_weights=tied).to(DEV)
     m16 = copy.deepcopy(m32)
     g = torch.Generator().manual_seed(3)
-    B, L = 1024, 64
-    q = torch.randint(0, 128, (B, L), generator=g); d = torch.randint(0, 128, (B, L), generator=g)
-    t32 = tt.FusedTrainer(m32, loss="in_batch", batch_size=B, max_len=L, precision="fp32", use_cuda_graph=False)
-    t16 = tt.FusedTrainer(m16, loss="in_batch", batch_size=B, max_len=L, precision="bf16", use_cuda_graph=True)
-    l32, l16 = t32.step(q, d).item(), t16.step(q, d).item()
+    L = 64
+    q = torch.randint(0, 128, (B, L), generator=g).to(id_dtype); d = torch.randint(0, 128, (B, L), generator=g).to(id_dtype)
+    t32 = tt.FusedTrainer(m32, loss="in_batch", batch_size=B, max_len=L, precision="fp32", use_cuda_graph=False, id_dtype=id_dtype)
+    t16 = tt.FusedTrainer(m16, loss="in_batch", batch_size=B, max_len=L, precision="bf16", use_cuda_graph=True, id_dtype=id_dtype)
+    if B == 4096:
+        assert t16.ce_fused and t16.embed_fused and t16.embed_in_tower
+    l32 = t32.step(q, d).item()
+    t16.step(q, d)
+    l16 = t16.read_loss_async()()
+    assert l16 == t16.loss.item()
     assert abs(l32 - l16) <= BF16_RTOL * abs(l32)
     close(t16.flat_grad, t32.flat_grad.cpu().numpy(), 5e-2, "flat grads")
     first = l16

@@ -175,6 +175,9 @@ class FusedTrainer:
                  lib.tt_embed_pool_bwd_workspace(R, L, self.V, self.E),
                  lib.tt_inbatch_ce_workspace(B * self.world, B * self.world, self.H, self.prec))
         self.ws = torch.empty(int(nb), dtype=torch.uint8, device=self.dev)
+        self._loss_ring = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]   # read_loss_async()
+        self._loss_ev = [torch.cuda.Event() for _ in range(2)]
+        self._loss_slot = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self._stage = None
         self._staged = False
@@ -447,6 +450,26 @@ class FusedTrainer:
         else:
             self.load_batch(q_ids, d_ids, n_ids)
         return self.run()
+
+    def read_loss_async(self):
+        """Queue a device->host copy of the loss of the step just issued into a pinned two-slot ring and return a
+        zero-argument callable that waits for THAT copy and returns the Python float.  Lets a training loop read every
+        step's loss (as the reference does with loss.item()) one step late, so the host never stalls the GPU:
+
+            pending = None
+            for batch in loader:
+                trainer.step(*batch); nxt = trainer.read_loss_async()
+                if pending is not None: log(pending())
+                pending = nxt
+        """
+        k = self._loss_slot
+        self._loss_slot ^= 1
+        self._loss_ring[k].copy_(self.loss.reshape(1), non_blocking=True)   # stream-ordered before the next step overwrites it
+        self._loss_ev[k].record(torch.cuda.current_stream())
+        def wait(k=k):
+            self._loss_ev[k].synchronize()
+            return float(self._loss_ring[k])
+        return wait
 
     def kernels_per_step(self) -> int:
         """Launches of libtt_b200 kernels in one step (measured on an eager step)."""

@@ -264,6 +264,34 @@ int tt_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k,
 /* fp32 -> bf16 row copy used by index_documents when the index is kept in bf16. */
 int tt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* ---- multi-GPU exchange over NVLink peer memory ---------------------------------------------------
+ * One process per GPU.  Every rank allocates one exchange buffer (tt_p2p_alloc, tt_p2p_buffer_bytes), exports it
+ * (CUDA IPC handle, 64 bytes) and imports every peer's; tt_p2p_t lists all ranks' buffers as mapped in this process
+ * (base[rank] is the local one).  Layout: 256-byte header (arrival counters, round, ticket) + world slots of slot_bytes.
+ * tt_p2p_allgather : ONE kernel stores `bytes` of src into slot `rank` of every rank's buffer (16-byte stores over
+ *                    NVLink), signals, and spins until all ranks' slots for this round have arrived in the LOCAL buffer.
+ *                    When it retires the gathered data is base[rank] + 256.  Every rank must call it with the same bytes.
+ *                    Capturable in a CUDA graph; replaces an NCCL all-gather whose fixed cost dominates at these sizes.
+ * tt_p2p_sum_slots : out[i] = sum_r slot_r[i] in rank order -- with an all-gather of the gradients this is an all-reduce
+ *                    whose result is bitwise identical on every rank.
+ */
+typedef struct {
+  int world, rank;
+  size_t slot_bytes;          /* multiple of 256 */
+  void* base[8];              /* exchange buffer of rank p as mapped in this process */
+  int double_buffered;        /* rounds alternate between two slot sets: safe when this is the only exchange between two
+                                 uses of the same buffer (see p2p.cu); consumers then read via tt_p2p_sum_slots */
+} tt_p2p_t;
+size_t tt_p2p_buffer_bytes(int world, size_t slot_bytes, int double_buffered);
+int tt_p2p_alloc(size_t bytes, void** ptr);
+int tt_p2p_free(void* ptr);
+int tt_p2p_export(void* ptr, void* handle64);
+int tt_p2p_import(const void* handle64, void** ptr);
+int tt_p2p_unimport(void* ptr);
+int tt_p2p_allgather_ctas(size_t bytes);
+int tt_p2p_allgather(const tt_p2p_t* x, const void* src, size_t bytes, void* stream);
+int tt_p2p_sum_slots(const tt_p2p_t* x, size_t n_floats, float* out, void* stream);
+
 /* ---- optimizer: torch.optim.AdamW(model.parameters(), lr), train.py:359 ------
  * One fused AdamW step over a flat fp32 parameter buffer (ATen _single_tensor_adamw
  * semantics and operation order, amsgrad off; hyper-parameters are doubles, rounded to fp32

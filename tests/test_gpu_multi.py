@@ -65,7 +65,40 @@ def _worker(rank, world, port, q_out):
         both = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(both, chk)
         assert both[0].item() == both[1].item()              # ranks stay bit-identical after the all-reduce
-        # ---- sharded search == unsharded ---------------------------------------------------------------------
+        # ---- NVLink peer-memory exchange (tt_p2p_allgather): raw all-gather, repeated rounds, rank-order sum -----------
+        x = parallel.P2PExchange(4096 * 4, device=dev)
+        for rnd in range(3):
+            src = torch.full((4096,), float(10 * rnd + rank + 1), device=dev)
+            x.allgather(src)
+            got = x.gathered(torch.float32, (4096,))
+            torch.cuda.synchronize()
+            for r in range(world):
+                assert float(got[r].min()) == float(got[r].max()) == 10 * rnd + r + 1, (rnd, r, got[r][:4])
+            out = torch.empty(4096, device=dev)
+            x.sum_slots(out)
+            assert float(out[0]) == sum(10 * rnd + r + 1 for r in range(world))
+            dist.barrier()                                   # single-buffered: nobody pushes the next round while a peer still reads
+        x2 = parallel.P2PExchange(1024 * 4, device=dev, double_buffered=True)
+        for rnd in range(5):                                 # double-buffered: back-to-back rounds need no barrier in between
+            x2.allgather(torch.full((1024,), float(rnd * 100 + rank), device=dev))
+            out = torch.empty(1024, device=dev)
+            x2.sum_slots(out)
+            assert float(out[7]) == sum(rnd * 100 + r for r in range(world)), (rnd, float(out[7]))
+        # ---- the same trainer with NCCL collectives and with peer-memory exchanges: identical trajectories -------------
+        def run(p2p):
+            torch.manual_seed(0)
+            emb2 = tt.embeddings.build("lookup", 128, embedding_dim=64)
+            m = tt.build_two_tower("mean", emb2, hidden_dim=256, tied_weights=True).to(dev)
+            t2 = tt.FusedTrainer(m, loss="in_batch", batch_size=256, max_len=64, precision="bf16",
+                                 process_group=dist.group.WORLD, global_negatives=True, p2p=p2p)
+            assert t2.p2p == p2p
+            losses = [t2.step(q_ids, d_ids).item() for _ in range(6)]
+            return losses, t2.flat.clone()
+        l_nccl, w_nccl = run(False)
+        l_p2p, w_p2p = run(True)
+        assert l_nccl == l_p2p, (l_nccl, l_p2p)               # 2 ranks: a + b in either order is the same float
+        assert torch.equal(w_nccl, w_p2p)
+        # ---- sharded search == unsharded ---------------------------------------------------------------------        # ---- sharded search == unsharded ---------------------------------------------------------------------
         N, k = 100_003, 50
         idx = O.normalize(g.standard_normal((N, H))).astype(np.float32)
         idx[70_000] = idx[3]

@@ -59,6 +59,11 @@ class MlpEmbed(C.Structure):
                 ("workspace", _vp), ("workspace_bytes", _sz)]
 
 
+class P2P(C.Structure):
+    """tt_p2p_t (include/tt_b200.h)"""
+    _fields_ = [("world", _i), ("rank", _i), ("slot_bytes", _sz), ("base", _vp * 8), ("double_buffered", _i)]
+
+
 class CePass(C.Structure):
     """tt_ce_pass_t (include/tt_b200.h)"""
     _fields_ = [("x_bf16", _vp), ("x_rows", _i64), ("y_bf16", _vp), ("y_rows", _i64), ("y_buf_rows", _i64),
@@ -70,6 +75,15 @@ SIGNATURES.update({
     "tt_inbatch_ce_fwd_ex_workspace": (_sz, [_i64, _i64]),
     "tt_inbatch_ce_fwd_ex": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i, _f, _i64, _f, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "tt_inbatch_ce_sync_bytes": (_sz, [_i64]),
+    "tt_p2p_buffer_bytes": (_sz, [_i, _sz, _i]),
+    "tt_p2p_alloc": (_i, [_sz, _vp]),
+    "tt_p2p_free": (_i, [_vp]),
+    "tt_p2p_export": (_i, [_vp, _vp]),
+    "tt_p2p_import": (_i, [_vp, _vp]),
+    "tt_p2p_unimport": (_i, [_vp]),
+    "tt_p2p_allgather_ctas": (_i, [_sz]),
+    "tt_p2p_allgather": (_i, [_vp, _vp, _sz, _vp]),
+    "tt_p2p_sum_slots": (_i, [_vp, _sz, _vp, _vp]),
     "tt_inbatch_ce_bwd_fused_ok": (_i, [_i64, _i64, _i64, _i64, _i]),
     "tt_inbatch_ce_bwd_nparts_ex": (_i, [_i64, _i64, _i64, _i64, _i]),
     "tt_inbatch_ce_bwd_parts_ex": (_i, [C.POINTER(CePass), C.POINTER(CePass), _i, _f, _f, _vp, _i, _vp]),

@@ -79,6 +79,94 @@ def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+class _DevMem:
+    """Minimal __cuda_array_interface__ carrier so torch can view a raw device pointer."""
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+
+class P2PExchange:
+    """All-gather over NVLink peer memory (tt_p2p_allgather): one kernel per exchange, no NCCL on the data path.
+
+    Every rank owns a cudaMalloc'ed buffer of `world` slots, exports it through CUDA IPC and maps every peer's.  The
+    handles travel once at construction (torch.distributed all_gather_object); afterwards an exchange is a single
+    graph-capturable kernel launch.  `gathered(dtype, shape)` views the local buffer's slots as a tensor.
+    """
+
+    def __init__(self, slot_bytes: int, group=None, device=None, double_buffered: bool = False):
+        from . import _lib
+        import ctypes as C
+        self.lib = _lib.load()
+        self.rank, self.world = world(group)
+        if self.world > 8:
+            raise RuntimeError("P2PExchange supports up to 8 ranks (one NVSwitch domain)")
+        self.group = group
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
+        self.double_buffered = bool(double_buffered)
+        self.nbytes = int(self.lib.tt_p2p_buffer_bytes(self.world, self.slot_bytes, int(self.double_buffered)))
+        ptr = C.c_void_p()
+        _lib.check(self.lib.tt_p2p_alloc(self.nbytes, C.byref(ptr)), "tt_p2p_alloc")
+        self.local_ptr = ptr.value
+        handle = (C.c_ubyte * 64)()
+        _lib.check(self.lib.tt_p2p_export(ptr, handle), "tt_p2p_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.desc = _lib.P2P()
+        self.desc.world, self.desc.rank, self.desc.slot_bytes = self.world, self.rank, self.slot_bytes
+        self.desc.double_buffered = int(self.double_buffered)
+        self._imported = []
+        for p in range(self.world):
+            if p == self.rank:
+                self.desc.base[p] = self.local_ptr
+                continue
+            h = (C.c_ubyte * 64).from_buffer_copy(handles[p])
+            q = C.c_void_p()
+            _lib.check(self.lib.tt_p2p_import(h, C.byref(q)), "tt_p2p_import")
+            self.desc.base[p] = q.value
+            self._imported.append(q.value)
+        self._raw = torch.as_tensor(_DevMem(self.local_ptr, self.nbytes), device=self.device)   # uint8 view, not owning
+        dist.barrier(group=group)                               # every peer has mapped every buffer before first use
+
+    def gathered(self, dtype, per_rank_shape) -> torch.Tensor:
+        """[world, *per_rank_shape] view of the slots (rank-major); slots are slot_bytes apart."""
+        if self.double_buffered:
+            raise RuntimeError("double-buffered exchanges are consumed through sum_slots()")
+        n = 1
+        for d in per_rank_shape:
+            n *= int(d)
+        esz = torch.empty((), dtype=dtype).element_size()
+        if n * esz > self.slot_bytes:
+            raise ValueError("per-rank shape exceeds the slot")
+        body = self._raw[256:256 + self.world * self.slot_bytes].view(self.world, self.slot_bytes)
+        return body[:, :n * esz].view(dtype).view(self.world, *per_rank_shape) if n * esz == self.slot_bytes else \
+            torch.as_strided(body.view(dtype), (self.world, *per_rank_shape),
+                             (self.slot_bytes // esz, *_contig_strides(per_rank_shape)))
+
+    def allgather(self, src: torch.Tensor) -> None:
+        """Launch the exchange on the current stream: afterwards slot r of the local buffer holds rank r's `src`."""
+        import ctypes as C
+        from . import _lib
+        nbytes = src.numel() * src.element_size()
+        _lib.check(self.lib.tt_p2p_allgather(C.byref(self.desc), C.c_void_p(src.data_ptr()), nbytes,
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tt_p2p_allgather")
+
+    def sum_slots(self, out: torch.Tensor) -> None:
+        """out[i] = sum over ranks (rank order) of the fp32 slots -- all-gather + this = a deterministic all-reduce."""
+        import ctypes as C
+        from . import _lib
+        _lib.check(self.lib.tt_p2p_sum_slots(C.byref(self.desc), out.numel(), C.c_void_p(out.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tt_p2p_sum_slots")
+
+
+def _contig_strides(shape):
+    st, acc = [], 1
+    for d in reversed(shape):
+        st.append(acc)
+        acc *= int(d)
+    return tuple(reversed(st))
+
+
 def shard_bounds(n: int, rank: int, ws: int) -> Tuple[int, int]:
     """Contiguous row range [lo, hi) of shard `rank` (rows split as evenly as possible)."""
     base, rem = divmod(n, ws)

@@ -38,7 +38,8 @@ class FusedTrainer:
     def __init__(self, model: TwoTower, loss: str = "in_batch", temperature: float = 0.1, margin: float = 0.2,
                  lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  batch_size: int = 256, max_len: int = 64, precision=None, process_group=None,
-                 global_negatives: bool = True, use_cuda_graph: bool = True, id_dtype=torch.int64):
+                 global_negatives: bool = True, use_cuda_graph: bool = True, id_dtype=torch.int64,
+                 p2p: Optional[bool] = None):
         if loss not in ("in_batch", "triplet"):
             raise ValueError("FusedTrainer supports loss 'in_batch' or 'triplet'")
         self.model = model
@@ -127,6 +128,24 @@ class FusedTrainer:
         if self.ce_fused:
             self.dz_bf16 = torch.empty(R, self.H, dtype=torch.bfloat16, device=self.dev)
             self.dz_colsum = torch.empty(R // 32, self.H, **f32)
+        # multi-GPU exchanges over NVLink peer memory (one kernel each) instead of NCCL: tower outputs, lse, gradients
+        if p2p is None:
+            p2p = os.environ.get("TT_P2P", "1") != "0"
+        self.p2p = bool(p2p and self.world > 1 and self.world <= 8 and self.flat_grad.numel() % 4 == 0 and
+                        (not self.global_fast or (2 * B * self.H * 2) % 256 == 0))
+        if self.p2p:
+            self.x_grad = parallel.P2PExchange(self.flat_grad.numel() * 4, self.group, self.dev, double_buffered=True)
+            if self.global_fast:
+                self.x_y = parallel.P2PExchange(2 * B * self.H * 2, self.group, self.dev)
+                self.x_lse = parallel.P2PExchange(B * 4, self.group, self.dev)
+                self.yg_bf16 = self.x_y.gathered(torch.bfloat16, (2 * B, self.H)).view(self.world * 2 * B, self.H)
+                self.lse_g = self.x_lse.gathered(torch.float32, (B,)).reshape(self.world * B) \
+                    if (B * 4) % 256 == 0 else None
+                if self.lse_g is None or not self.lse_g.is_contiguous():
+                    self.lse_g = torch.empty(self.world * B, **f32)       # odd B: gather into slots, then pack (one small copy)
+                    self._lse_pack = True
+                else:
+                    self._lse_pack = False
         self.dy_part_stride = R * self.H if self.dy_parts > 1 else 0
         self.dy_all = torch.empty(1 if self.ce_fused else self.dy_parts, R, self.H, **f32)
         self.dy = self.dy_all[0]
@@ -298,7 +317,10 @@ class FusedTrainer:
             check(lib.tt_embed_pool_bwd(_p(self.ids), idb, _p(self.inv_len), _p(self.dpooled), R, self.L, self.V,
                                         self.E, _p(self.table.grad), _p(self.ws), self.ws.numel(), s),
                   "tt_embed_pool_bwd")
-        if self.world > 1:
+        if self.p2p:
+            self.x_grad.allgather(self.flat_grad)           # every rank's gradients over NVLink, then the same rank-order
+            self.x_grad.sum_slots(self.flat_grad)           # sum everywhere: bitwise identical parameters on all ranks
+        elif self.world > 1:
             parallel.allreduce_sum_(self.flat_grad, self.group)
         check(lib.tt_adamw_step(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
                                 self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
@@ -352,12 +374,20 @@ class FusedTrainer:
         read the gathered buffer in place (block-interleaved rows), both gradients come from ONE launch as slices."""
         lib, B, H, W = self.lib, self.B, self.H, self.world
         Bg = B * W
-        dist.all_gather_into_tensor(self.yg_bf16, self.y_bf16[:2 * B], group=self.group)
+        if self.p2p:
+            self.x_y.allgather(self.y_bf16[:2 * B])
+        else:
+            dist.all_gather_into_tensor(self.yg_bf16, self.y_bf16[:2 * B], group=self.group)
         scale = 1.0 / Bg
         check(lib.tt_inbatch_ce_fwd_ex(_p(self.y_bf16[:B]), B, _p(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, B, H, inv_t,
                                        self.rank * B, scale, _p(self.loss), _p(self.lse), _p(self.pos_mean),
                                        _p(self.ce_ws), self.ce_ws.numel(), _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
-        dist.all_gather_into_tensor(self.lse_g, self.lse, group=self.group)
+        if self.p2p:
+            self.x_lse.allgather(self.lse)
+            if self._lse_pack:
+                self.lse_g.view(W, B).copy_(self.x_lse.gathered(torch.float32, (B,)))
+        else:
+            dist.all_gather_into_tensor(self.lse_g, self.lse, group=self.group)
         vp = lambda t: None if t is None else t.data_ptr()
         nb = B // 32
         fz = (lambda a, b, c: (vp(a), vp(b), vp(c))) if self.ce_fused else (lambda a, b, c: (None, None, None))

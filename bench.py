@@ -354,8 +354,12 @@ def kernel_roofline(tt, tr, dev):
     ms = float(np.mean(times))
     flops = 4.0 * Bl * Bg * H                   # algorithmic backward FLOPs (dQ + dD products); recompute not counted
     achieved = flops / (ms * 1e-3) / 1e12
+    # DRAM bytes of this launch from the committed ncu --set full capture (profiles/r01_ncu_ce_bwd_final_raw.csv:
+    # dram__bytes_read.sum 4.42 MB + dram__bytes_write.sum 0 -- the 8 MB of outputs stay in the 126 MB L2); only that
+    # shape was captured
+    traffic = 4416512 if (merged and Bl == 4096 and Bg == 4096 and H == 256) else None
     return {"kernel": what, "bound": "tensor", "achieved": achieved,
-            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"], "traffic": None,
+            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"], "traffic": traffic,
             "ms": ms, "launch_flops": flops, "executed_flops": 2 * flops,
             "note": "achieved counts algorithmic FLOPs; the kernel executes 2x (S = X Y^T is recomputed, flash style); "
                     "event-timed single-kernel graph replay includes a ~8-10 us replay floor",

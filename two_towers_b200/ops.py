@@ -370,7 +370,10 @@ def packed_views(buf_row: torch.Tensor, nq: int, k: int, id_off: int):
 def topk_merge_packed(buf: torch.Tensor, nq: int, k: int, id_off: int):
     """Merge R packed candidate records (see packed_topk_buffer) -> ([nq,k], [nq,k])."""
     _need_cuda(buf)
-    R, nbytes = buf.shape
+    R = buf.shape[0]
+    nbytes = buf.stride(0) if R > 1 else buf.shape[1]          # records may sit in wider slots (peer-memory exchange buffer)
+    if nbytes % 8 != 0 or buf.stride(1) != 1:
+        raise ValueError("packed records need an 8-byte aligned rank pitch")
     out_s = torch.empty(nq, k, dtype=torch.float32, device=buf.device)
     out_i = torch.empty(nq, k, dtype=torch.int64, device=buf.device)
     base = buf.data_ptr()

@@ -126,6 +126,7 @@ class P2PExchange:
             self.desc.base[p] = q.value
             self._imported.append(q.value)
         self._raw = torch.as_tensor(_DevMem(self.local_ptr, self.nbytes), device=self.device)   # uint8 view, not owning
+        self.rounds = 0
         dist.barrier(group=group)                               # every peer has mapped every buffer before first use
 
     def gathered(self, dtype, per_rank_shape) -> torch.Tensor:
@@ -143,10 +144,16 @@ class P2PExchange:
             torch.as_strided(body.view(dtype), (self.world, *per_rank_shape),
                              (self.slot_bytes // esz, *_contig_strides(per_rank_shape)))
 
+    def current_half(self) -> torch.Tensor:
+        """[world, slot_bytes] uint8 view of the slot set the LAST allgather() of a double-buffered exchange filled."""
+        off = 256 + (self.world * self.slot_bytes if (self.double_buffered and (self.rounds & 1)) else 0)
+        return self._raw[off:off + self.world * self.slot_bytes].view(self.world, self.slot_bytes)
+
     def allgather(self, src: torch.Tensor) -> None:
         """Launch the exchange on the current stream: afterwards slot r of the local buffer holds rank r's `src`."""
         import ctypes as C
         from . import _lib
+        self.rounds += 1                                     # mirrors the device-side round counter (all calls go through here)
         nbytes = src.numel() * src.element_size()
         _lib.check(self.lib.tt_p2p_allgather(C.byref(self.desc), C.c_void_p(src.data_ptr()), nbytes,
                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tt_p2p_allgather")
@@ -165,6 +172,28 @@ def _contig_strides(shape):
         st.append(acc)
         acc *= int(d)
     return tuple(reversed(st))
+
+
+_SEARCH_XCH = {}
+
+
+def _search_exchange(nbytes: int, group, device):
+    """Cached double-buffered peer-memory exchange for the candidate records of the sharded search (None: use NCCL)."""
+    import os
+    if device.type != "cuda" or os.environ.get("TT_P2P", "1") == "0":
+        return None
+    _, ws = world(group)
+    if ws < 2 or ws > 8:
+        return None
+    key = (id(group), (nbytes + 255) // 256 * 256, device.index)
+    if key not in _SEARCH_XCH:
+        try:
+            x = P2PExchange(key[1], group, device, double_buffered=True)
+            x.staging = torch.zeros(1, key[1], dtype=torch.uint8, device=device)
+            _SEARCH_XCH[key] = x
+        except RuntimeError:
+            _SEARCH_XCH[key] = None                           # no peer access on this machine: NCCL path
+    return _SEARCH_XCH[key]
 
 
 def shard_bounds(n: int, rank: int, ws: int) -> Tuple[int, int]:
@@ -191,6 +220,9 @@ def sharded_topk(index_shard: torch.Tensor, queries: torch.Tensor, k: int, id_of
     if packed:
         # (score, id) records of this rank go straight into one byte buffer -> ONE all-gather -> merge kernel
         mine, nbytes, id_off = kernels.packed_topk_buffer(nq, k, queries.device)
+        xch = _search_exchange(nbytes, group, queries.device)
+        if xch is not None:                                   # candidates travel over NVLink peer memory (one kernel)
+            mine = xch.staging[:, :nbytes]
         s_view, i_view = kernels.packed_views(mine[0], nq, k, id_off)
         if k_local < k:
             s_view.fill_(float("-inf"))
@@ -201,7 +233,11 @@ def sharded_topk(index_shard: torch.Tensor, queries: torch.Tensor, k: int, id_of
             s, i = kernels.topk_scan(index_shard, queries, k_local, cosine=cosine, id_offset=id_offset)
             s_view[:, :k_local].copy_(s)
             i_view[:, :k_local].copy_(i)
-        everyone = all_gather_rows(mine, group)                 # [R, nbytes]
+        if xch is not None:
+            xch.allgather(xch.staging[0])
+            everyone = xch.current_half()                       # [R, slot_bytes]; records start each slot
+        else:
+            everyone = all_gather_rows(mine, group)             # [R, nbytes]
         return kernels.topk_merge_packed(everyone, nq, k, id_off)
     if k_local > 0:
         s, i = kernels.topk_scan(index_shard, queries, k_local, cosine=cosine, id_offset=id_offset)

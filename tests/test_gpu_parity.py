@@ -349,6 +349,58 @@ def test_search_end_to_end_matches_reference(golden_dir, tmp_path):
     import pickle
     blob = pickle.load(open(tmp_path / "idx.pkl", "rb"))
     assert set(blob) == {"embeddings", "documents"} and isinstance(blob["embeddings"], np.ndarray)
+    # raw, mmap-able format: bit-exact round trip for both index dtypes, and a row-range (shard) load
+    for idx_dtype in ("fp32", "bf16"):
+        sa = tt.TwoTowerSearch(model, tok, device=DEV, index_dtype=idx_dtype)
+        sa.index_documents(gold["docs"])
+        sa.save_index_raw(str(tmp_path / f"raw_{idx_dtype}"))
+        sb = tt.TwoTowerSearch(model, tok, device=DEV, index_dtype=idx_dtype)
+        sb.load_index_raw(str(tmp_path / f"raw_{idx_dtype}"))
+        assert torch.equal(sb.document_embeddings, sa.document_embeddings) and sb.documents == list(gold["docs"])
+        assert sb.search("cat", 3) == sa.search("cat", 3)
+        n = len(gold["docs"])
+        sc = tt.TwoTowerSearch(model, tok, device=DEV, index_dtype=idx_dtype)
+        sc.load_index_raw(str(tmp_path / f"raw_{idx_dtype}"), rows=range(1, n))
+        assert torch.equal(sc.document_embeddings, sa.document_embeddings[1:]) and sc.row_offset == 1
+
+
+def test_evaluate_model_matches_numpy_ranking(golden_dir):
+    """evaluate_model (device ranking through the scan / top-k kernel) == the reference procedure restated in numpy on the
+    same embeddings: cosine scores, descending sort, the metric helpers (pinned against the reference in the CPU suite)."""
+    import two_towers_b200 as tt
+    from two_towers_b200 import evaluate as E
+    gold = json.load(open(os.path.join(golden_dir, "search_small.json")))
+    w = np.load(os.path.join(golden_dir, "search_small.npz"))
+    tok = tt.CharTokeniser(); tok.string_to_index = gold["vocab"]
+    tok.index_to_string = {i: c for c, i in gold["vocab"].items()}
+    emb = tt.embeddings.build("lookup", tok.vocab_size, embedding_dim=16)
+    model = tt.build_two_tower("mean", emb, hidden_dim=32, tied_weights=False).to(DEV)
+    model.load_state_dict({k.replace("__", "."): torch.tensor(w[k]) for k in w.files if k != "doc_embeddings"})
+    docs = list(gold["docs"])
+    rng = np.random.default_rng(5)
+    test_data = []
+    for qi, q in enumerate(["cat", "dog food", "quantum", "the"]):
+        cand = [docs[j] for j in rng.permutation(len(docs))[:max(3, len(docs) - qi)]]
+        rel = rng.integers(0, 2, len(cand)).tolist()
+        test_data.append((q, cand, rel))
+    got = E.evaluate_model(model, test_data, tok, k_values=[1, 3, 5], device=DEV)
+    # numpy restatement
+    P, R, M, N = [], [], [], []
+    with torch.no_grad():
+        for q, cand, rel in test_data:
+            qe = model.query_tower(tok.encode_batch([q], 64).to(DEV)).double().cpu().numpy()[0]
+            de = model.document_tower(tok.encode_batch(cand, 64).to(DEV)).double().cpu().numpy()
+            sc = de @ qe / (np.linalg.norm(de, axis=1) * np.linalg.norm(qe) + 1e-30)
+            order = np.argsort(-sc, kind="stable")
+            ranked = np.asarray(rel)[order]
+            P.append([E.precision_at_k(ranked, k) for k in (1, 3, 5)]); R.append([E.recall_at_k(ranked, k, sum(rel)) for k in (1, 3, 5)])
+            M.append(E.mean_reciprocal_rank(ranked)); N.append([E.ndcg_at_k(ranked, k) for k in (1, 3, 5)])
+    for i, k in enumerate((1, 3, 5)):
+        assert abs(got[f"precision@{k}"] - np.mean([p[i] for p in P])) < 1e-12
+        assert abs(got[f"recall@{k}"] - np.mean([r[i] for r in R])) < 1e-12
+        assert abs(got[f"ndcg@{k}"] - np.mean([n[i] for n in N])) < 1e-12
+    assert abs(got["mrr"] - np.mean(M)) < 1e-12
+    assert set(got) == {"precision@1", "precision@3", "precision@5", "recall@1", "recall@3", "recall@5", "mrr", "ndcg@1", "ndcg@3", "ndcg@5"}
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])

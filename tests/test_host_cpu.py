@@ -155,3 +155,19 @@ def test_shard_bounds_cover_and_partition():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_ranking_metrics_match_reference_golden():
+    """two_towers_b200.evaluate helpers vs values produced by the reference's twotower/evaluate.py
+    (tests/golden/make_golden_eval.py)."""
+    import json
+    from two_towers_b200 import evaluate as E
+    with open(os.path.join(os.path.dirname(__file__), "golden", "eval_metrics.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 100
+    for c in cases:
+        rel, k = c["relevance"], c["k"]
+        assert E.mean_reciprocal_rank(rel) == c["mrr"]
+        assert abs(E.precision_at_k(rel, k) - c["precision"]) < 1e-12
+        assert abs(E.recall_at_k(rel, k, sum(rel)) - c["recall"]) < 1e-12
+        assert abs(E.ndcg_at_k(rel, k) - c["ndcg"]) < 1e-12

@@ -145,6 +145,52 @@ class TwoTowerSearch(BaseSearch):
         self.row_offset, self.num_documents = 0, len(self.documents)
 
 
+    # ------------------------------------------------------------------ raw, mmap-able format
+    def save_index_raw(self, dirpath: str) -> None:
+        """`dirpath/embeddings.bin` = the [N,H] matrix exactly as it sits in HBM (fp32 or bf16 bits, row-major),
+        `dirpath/meta.json` = shape / dtype / row range, `dirpath/documents.json` = the documents.  A 10 M x 256 index is
+        ONE sequential 10 GB (5 GB bf16) write instead of a pickled ndarray, and loads with np.memmap in row chunks
+        (a shard reads only its own rows)."""
+        import json, os
+        if self.document_embeddings is None or self.documents is None:
+            raise ValueError("No index to save. Call index_documents() first.")
+        os.makedirs(dirpath, exist_ok=True)
+        emb = self.document_embeddings
+        n, h = emb.shape
+        bits = emb.view(torch.int16) if emb.dtype == torch.bfloat16 else emb
+        with open(os.path.join(dirpath, "embeddings.bin"), "wb") as f:
+            for r0 in range(0, n, 1 << 20):                       # 1 M rows at a time: bounded host staging
+                f.write(bits[r0:r0 + (1 << 20)].cpu().numpy().tobytes())
+        with open(os.path.join(dirpath, "meta.json"), "w") as f:
+            json.dump({"rows": n, "dim": h, "dtype": "bf16" if emb.dtype == torch.bfloat16 else "fp32",
+                       "row_offset": self.row_offset, "num_documents": self.num_documents}, f)
+        with open(os.path.join(dirpath, "documents.json"), "w") as f:
+            json.dump(list(self.documents), f)
+
+    def load_index_raw(self, dirpath: str, rows: Optional[range] = None) -> None:
+        """Load `rows` (default: all) of an index written by save_index_raw straight into one device matrix."""
+        import json, os
+        with open(os.path.join(dirpath, "meta.json")) as f:
+            meta = json.load(f)
+        with open(os.path.join(dirpath, "documents.json")) as f:
+            self.documents = json.load(f)
+        n, h = meta["rows"], meta["dim"]
+        lo, hi = (0, n) if rows is None else (rows.start, rows.stop)
+        np_dt, t_dt = (np.int16, torch.bfloat16) if meta["dtype"] == "bf16" else (np.float32, torch.float32)
+        mm = np.memmap(os.path.join(dirpath, "embeddings.bin"), dtype=np_dt, mode="r", shape=(n, h))
+        out = torch.empty(hi - lo, h, dtype=t_dt, device=self.device)
+        view = out.view(torch.int16) if t_dt == torch.bfloat16 else out
+        for r0 in range(lo, hi, 1 << 20):
+            r1 = min(hi, r0 + (1 << 20))
+            view[r0 - lo:r1 - lo].copy_(torch.from_numpy(np.array(mm[r0:r1])), non_blocking=False)   # np.array: writable host copy of the chunk
+        if self.index_dtype == "bf16" and t_dt == torch.float32:
+            out = self.kernels.cast_bf16(out)
+        elif self.index_dtype == "fp32" and t_dt == torch.bfloat16:
+            out = out.float()
+        self.document_embeddings = out
+        self.row_offset, self.num_documents = meta.get("row_offset", 0) + lo, meta.get("num_documents", n)
+
+
 def ws_initialized() -> bool:
     import torch.distributed as dist
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1

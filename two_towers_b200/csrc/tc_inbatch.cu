@@ -38,7 +38,8 @@ namespace tc {
 
 constexpr int CE_BM = 128;          // X rows per CTA (UMMA M)
 constexpr int CE_BN = 64;           // Y rows per tile (UMMA N of the S product, K of the O product)
-constexpr int CE_THREADS = 192;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int CE_THREADS = 192;     // backward: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int FWD_THREADS = 320;    // forward: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2, inputs are bounded (<= 0 after max-subtraction)
@@ -67,7 +68,7 @@ struct FwdFinalize {
   long long* dbg;              // developer aid (TT_CE_DEBUG): [cta][4] %globaltimer stamps
 };
 
-__global__ void __launch_bounds__(CE_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmD, int64_t Bq,
                  int64_t Bd, int H, float inv_temp, int64_t label_offset, int tiles_per_split,
                  int64_t d_blk, int64_t d_blk_stride, int64_t d_blk_off,
@@ -77,6 +78,8 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   long long* fdbg = fin.dbg ? fin.dbg + 4 * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
 #define TT_FWD_STAMP(slot) do { if (fdbg && threadIdx.x == 64) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); fdbg[slot] = t_; } } while (0)
   TT_FWD_STAMP(0);
+  long long* tl = (fin.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? fin.dbg + 4 * gridDim.x * gridDim.y : nullptr;
+#define TT_FTL(role, tile, slot) do { if (tl && (tile) < 64) tl[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); } while (0)
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);     // stays in the shared address space
   const int kq = H / 64;                                  // 64-wide K blocks
   const uint32_t d_bytes = (uint32_t)FWD_BN * H * 2;      // == Q tile bytes (both are 128 rows)
@@ -90,6 +93,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* s_empty = s_full + 2;                         // [2]
   uint64_t* q_ready = s_empty + 2;                        // Q tile copied into TMEM (4 epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
+  float* ml_s = reinterpret_cast<float*>(tmem_slot + 2);          // [128][2] (max, sum) of the second column half
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t x0 = (int64_t)blockIdx.x * CE_BM;
@@ -102,8 +106,8 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmD);
     mbar_init(q_bar, 1);
     for (int s = 0; s < FWD_STAGES; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4); }
-    mbar_init(q_ready, 4);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8); }
+    mbar_init(q_ready, 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -140,8 +144,11 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_after();
     for (int i = 0; i < nt; ++i) {
       const int s = i % FWD_STAGES, b = i & 1;
+      if (lane == 0) TT_FTL(0, i, 0);
       mbar_wait(&d_full[s], (i / FWD_STAGES) & 1);
+      if (lane == 0) TT_FTL(0, i, 1);
       mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
+      if (lane == 0) TT_FTL(0, i, 2);
       tc_fence_after();
       const uint64_t dd = dd0 + (uint64_t)((s * d_bytes) >> 4);
       for (int kb = 0; kb < kq; ++kb)
@@ -153,9 +160,13 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       if (elect_one()) { umma_commit(&d_empty[s]); umma_commit(&s_full[b]); }
       __syncwarp();
+      if (lane == 0) TT_FTL(0, i, 3);
     }
   } else {
-    const int quarter = warp & 3;
+    // epilogue warps 2..9: TMEM lane quarter = warp % 4; the two warps of a quarter take the two 64-column halves of every
+    // S tile (online max / sum is associative: the halves are merged once at the end).  The epilogue, not the tensor
+    // pipe, bounds this kernel, so it gets two warps per scheduler.
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int lrow = quarter * 32 + lane;
     const int64_t row = x0 + lrow;
     const int64_t pcol = row + label_offset;
@@ -163,7 +174,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     // Q tile: smem (TMA, 128B swizzle) -> registers -> TMEM, so every S product reads A from tensor memory
     mbar_wait(q_bar, 0);
-    for (int kb = 0; kb < kq; ++kb) {
+    for (int kb = half; kb < kq; kb += 2) {
       uint32_t xr[32];
       const uint8_t* xrow = q_tile + kb * (CE_BM * 128) + lrow * 128;
 #pragma unroll
@@ -181,56 +192,76 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float m = -CUDART_INF_F, l = 0.f;
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
-      const int64_t y0 = (int64_t)(t_beg + i) * FWD_BN;
+      const int64_t y0 = (int64_t)(t_beg + i) * FWD_BN + 64 * half;      // first column of this warp's half tile
+      if (threadIdx.x == 64) TT_FTL(1, i, 0);
       mbar_wait(&s_full[b], (i >> 1) & 1);
+      if (threadIdx.x == 64) TT_FTL(1, i, 1);
       tc_fence_after();
-      uint32_t r[4][32];
-      const uint32_t ta = tmem_s + lane_addr + (uint32_t)(b * FWD_BN);
+      uint32_t r[2][32];
+      const uint32_t ta = tmem_s + lane_addr + (uint32_t)(b * FWD_BN + 64 * half);
 #pragma unroll
-      for (int h = 0; h < 4; ++h) tmem_ld_x32(ta + 32 * h, r[h]);
+      for (int h = 0; h < 2; ++h) tmem_ld_x32(ta + 32 * h, r[h]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[b]);             // TMEM buffer may be overwritten
-      if (y0 + FWD_BN > Bd) {                              // ragged last tile: padded columns -> -inf
+      if (threadIdx.x == 64) TT_FTL(1, i, 2);
+      if (y0 + 64 > Bd) {                                  // ragged last tile: padded columns -> -inf
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (y0 + 32 * h + j >= Bd) r[h][j] = 0xff800000u;
       }
-      const int64_t pj = pcol - y0;                        // this row's positive column inside the tile
-      if (pj >= 0 && pj < FWD_BN && row < Bq) {
+      const int64_t pj = pcol - y0;                        // this row's positive column inside the half tile
+      if (pj >= 0 && pj < 64 && row < Bq) {
         float pv = 0.f;
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int j = 0; j < 32; ++j) pv = (32 * h + j == (int)pj) ? __uint_as_float(r[h][j]) : pv;
         pos_logit[row] = pv * inv_temp;
       }
       float t0 = -CUDART_INF_F, t1 = -CUDART_INF_F;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < 32; j += 2) {
         t0 = fmaxf(t0, fmaxf(__uint_as_float(r[0][j]), __uint_as_float(r[1][j])));
-        t1 = fmaxf(t1, fmaxf(__uint_as_float(r[2][j]), __uint_as_float(r[3][j])));
+        t1 = fmaxf(t1, fmaxf(__uint_as_float(r[0][j + 1]), __uint_as_float(r[1][j + 1])));
       }
       const float mnew = fmaxf(m, fmaxf(t0, t1));
-      const float mc = mnew * c;
+      if (threadIdx.x == 64) TT_FTL(1, i, 3);
+      const bool seen = mnew > -CUDART_INF_F;              // false while this warp's half tiles have all been padding
+      const float mc = seen ? mnew * c : 0.f;              // exp2(-inf * c - 0) = 0, never inf - inf
+      // two phases: all exponentials first (independent MUFU ops, back to back), then the sums -- an accumulate chain
+      // fed directly by MUFU results exposes the MUFU latency on every element
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[h][j] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j]), c, -mc)));
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        s0 += fast_exp2(fmaf(__uint_as_float(r[0][j]), c, -mc));
-        s1 += fast_exp2(fmaf(__uint_as_float(r[1][j]), c, -mc));
-        s2 += fast_exp2(fmaf(__uint_as_float(r[2][j]), c, -mc));
-        s3 += fast_exp2(fmaf(__uint_as_float(r[3][j]), c, -mc));
+      for (int j = 0; j < 32; j += 2) {
+        s0 += __uint_as_float(r[0][j]); s1 += __uint_as_float(r[0][j + 1]);
+        s2 += __uint_as_float(r[1][j]); s3 += __uint_as_float(r[1][j + 1]);
       }
-      l = l * fast_exp2((m - mnew) * c) + ((s0 + s1) + (s2 + s3));
+      l = (seen ? l * fast_exp2((m - mnew) * c) : 0.f) + ((s0 + s1) + (s2 + s3));
       m = mnew;
+      if (threadIdx.x == 64) TT_FTL(1, i, 4);
     }
     TT_FWD_STAMP(2);
-    if (row < Bq) {                                          // a split without tiles contributes (-inf, 0)
-      part_ml[((int64_t)blockIdx.y * Bq + row) * 2 + 0] = nt > 0 ? m * inv_temp : -CUDART_INF_F;
-      part_ml[((int64_t)blockIdx.y * Bq + row) * 2 + 1] = l;
+    // merge the two column halves of every row (fixed order: half 0, then half 1)
+    if (half == 1) { ml_s[2 * lrow] = m; ml_s[2 * lrow + 1] = l; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (half == 0) {
+      const float m1 = ml_s[2 * lrow], l1 = ml_s[2 * lrow + 1];
+      const float M = fmaxf(m, m1);
+      if (nt > 0 && M > -CUDART_INF_F)                       // a half that saw only padding has (m, l) = (-inf, 0)
+        l = (m > -CUDART_INF_F ? l * fast_exp2((m - M) * c) : 0.f) + (m1 > -CUDART_INF_F ? l1 * fast_exp2((m1 - M) * c) : 0.f);
+      m = M;
+      if (row < Bq) {                                        // a split without tiles contributes (-inf, 0)
+        part_ml[((int64_t)blockIdx.y * Bq + row) * 2 + 0] = nt > 0 ? m * inv_temp : -CUDART_INF_F;
+        part_ml[((int64_t)blockIdx.y * Bq + row) * 2 + 1] = l;
+      }
     }
     if (fin.counters) __threadfence();                       // partials visible before this CTA takes its ticket
   }
@@ -246,7 +277,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (threadIdx.x == 0) { s_ticket = atomicAdd(&fin.counters[blockIdx.x], 1u); __threadfence(); }
   __syncthreads();
   if (s_ticket != gridDim.y - 1) return;
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     const int lrow = (warp & 3) * 32 + lane;
     const int64_t row = x0 + lrow;
     float dl = 0.f, dp = 0.f;
@@ -799,9 +830,15 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
   else           ce_bwd_body<true>(&tmX1, &tmY1, p, base);
 }
 
-static size_t fwd_smem(int H) { return 1024 + FWD_STAGES * (size_t)FWD_BN * H * 2 + 20 * 8 + 16; }
+static size_t fwd_smem(int H) {
+  const size_t need = 1024 + FWD_STAGES * (size_t)FWD_BN * H * 2 + 20 * 8 + 16 + 128 * 2 * 4;
+  // every CTA allocates all 512 TMEM columns: two CTAs on one SM would serialise on the allocator, so small H still
+  // asks for more than half an SM's shared memory
+  return need > 120 * 1024 ? need : 120 * 1024;
+}
 static size_t bwd_smem(int H) {
-  return 1024 + BWD_STAGES * (size_t)BWD_BN * H * 2 + (size_t)CE_BM * BWD_BN * 2 + 24 * 8 + 16 + 2 * BWD_BN * 4;
+  const size_t need = 1024 + BWD_STAGES * (size_t)BWD_BN * H * 2 + (size_t)CE_BM * BWD_BN * 2 + 24 * 8 + 16 + 2 * BWD_BN * 4;
+  return need > 120 * 1024 ? need : 120 * 1024;          // one CTA per SM (every CTA allocates all 512 TMEM columns)
 }
 
 static int pick_split(int64_t xtiles, int64_t By, int bn = CE_BN) {
@@ -876,12 +913,13 @@ int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* 
   static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
   long long* dbg_dev = nullptr;
   const size_t ncta = (size_t)grid.x * grid.y;
-  if (dbg_on) { cudaMalloc(&dbg_dev, ncta * 4 * sizeof(long long)); cudaMemset(dbg_dev, 0, ncta * 4 * sizeof(long long)); fin.dbg = dbg_dev; }
-  TT_CUDA(launch_kernel(tc::tc_ce_fwd_kernel, grid, dim3(tc::CE_THREADS), smem, s, true, tmQ, tmD, Bq, Bd, H, inv_temp, label_offset, per,
+  const size_t fdbg_n = ncta * 4 + 2 * 64 * 8;
+  if (dbg_on) { cudaMalloc(&dbg_dev, fdbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, fdbg_n * sizeof(long long)); fin.dbg = dbg_dev; }
+  TT_CUDA(launch_kernel(tc::tc_ce_fwd_kernel, grid, dim3(tc::FWD_THREADS), smem, s, true, tmQ, tmD, Bq, Bd, H, inv_temp, label_offset, per,
                         d_blk, d_blk_stride, d_blk_off, part_ml, pos, fin));
   TT_LAUNCH_CHECK("tc_ce_fwd_kernel");
   if (dbg_on) {
-    std::vector<long long> h(ncta * 4);
+    std::vector<long long> h(fdbg_n);
     cudaStreamSynchronize(s);
     cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(dbg_dev);
@@ -889,6 +927,16 @@ int tc_inbatch_fwd_ex(const __nv_bfloat16* qa, int64_t Bq, const __nv_bfloat16* 
     for (size_t i = 0; i < ncta; ++i) if (h[4 * i] && (!g0 || h[4 * i] < g0)) g0 = h[4 * i];
     printf("[tt ce_fwd per-CTA ns] grid %u x %u, %d tiles per CTA: start q_ready loop_done end\n", grid.x, grid.y, per);
     for (size_t i = 0; i < ncta; i += 9) printf("  cta %3zu: %6lld %6lld %6lld %6lld\n", i, h[4 * i] - g0, h[4 * i + 1] - g0, h[4 * i + 2] - g0, h[4 * i + 3] - g0);
+    const long long* t = h.data() + ncta * 4;
+    const long long t0 = t[0];
+    printf("[tt ce_fwd timeline, cycles] tile: MMA{begin,d_full,s_empty,issued} EPI{begin,s_full,loaded,maxed,done}\n");
+    for (int i = 0; i < (per < 12 ? per : 12); ++i) {
+      printf("  %2d: MMA", i);
+      for (int k = 0; k < 4; ++k) printf(" %6lld", t[(0 * 64 + i) * 8 + k] - t0);
+      printf("   EPI");
+      for (int k = 0; k < 5; ++k) printf(" %6lld", t[(1 * 64 + i) * 8 + k] - t0);
+      printf("\n");
+    }
   }
   if (sync_scratch) return TT_OK;
   return inbatch_finalize(part_ml, pos, ns, Bq, inv_temp, loss_scale, lse, loss, pos_mean, nullptr, s);

@@ -105,26 +105,43 @@ class P2PExchange:
         self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
         self.double_buffered = bool(double_buffered)
         self.nbytes = int(self.lib.tt_p2p_buffer_bytes(self.world, self.slot_bytes, int(self.double_buffered)))
+        # Every step below is collective: a rank that fails still takes part in the exchanges of handles / verdicts, so
+        # either all ranks end up with a working exchange or all of them raise (and callers fall back to NCCL together).
         ptr = C.c_void_p()
-        _lib.check(self.lib.tt_p2p_alloc(self.nbytes, C.byref(ptr)), "tt_p2p_alloc")
-        self.local_ptr = ptr.value
         handle = (C.c_ubyte * 64)()
-        _lib.check(self.lib.tt_p2p_export(ptr, handle), "tt_p2p_export")
+        err = None
+        try:
+            _lib.check(self.lib.tt_p2p_alloc(self.nbytes, C.byref(ptr)), "tt_p2p_alloc")
+            _lib.check(self.lib.tt_p2p_export(ptr, handle), "tt_p2p_export")
+        except RuntimeError as e:
+            err = str(e)
+        self.local_ptr = ptr.value
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=group)
+        dist.all_gather_object(handles, None if err else bytes(handle), group=group)
         self.desc = _lib.P2P()
         self.desc.world, self.desc.rank, self.desc.slot_bytes = self.world, self.rank, self.slot_bytes
         self.desc.double_buffered = int(self.double_buffered)
         self._imported = []
-        for p in range(self.world):
-            if p == self.rank:
-                self.desc.base[p] = self.local_ptr
-                continue
-            h = (C.c_ubyte * 64).from_buffer_copy(handles[p])
-            q = C.c_void_p()
-            _lib.check(self.lib.tt_p2p_import(h, C.byref(q)), "tt_p2p_import")
-            self.desc.base[p] = q.value
-            self._imported.append(q.value)
+        if err is None and all(h is not None for h in handles):
+            try:
+                for p in range(self.world):
+                    if p == self.rank:
+                        self.desc.base[p] = self.local_ptr
+                        continue
+                    h = (C.c_ubyte * 64).from_buffer_copy(handles[p])
+                    q = C.c_void_p()
+                    _lib.check(self.lib.tt_p2p_import(h, C.byref(q)), "tt_p2p_import")
+                    self.desc.base[p] = q.value
+                    self._imported.append(q.value)
+            except RuntimeError as e:
+                err = str(e)
+        else:
+            err = err or "a peer could not allocate / export its exchange buffer"
+        verdicts = [None] * self.world
+        dist.all_gather_object(verdicts, err, group=group)
+        bad = [(r, v) for r, v in enumerate(verdicts) if v is not None]
+        if bad:
+            raise RuntimeError(f"peer-memory exchange unavailable (rank {bad[0][0]}: {bad[0][1]})")
         self._raw = torch.as_tensor(_DevMem(self.local_ptr, self.nbytes), device=self.device)   # uint8 view, not owning
         self.rounds = 0
         dist.barrier(group=group)                               # every peer has mapped every buffer before first use

@@ -134,10 +134,17 @@ class FusedTrainer:
         self.p2p = bool(p2p and self.world > 1 and self.world <= 8 and self.flat_grad.numel() % 4 == 0 and
                         (not self.global_fast or (2 * B * self.H * 2) % 256 == 0))
         if self.p2p:
-            self.x_grad = parallel.P2PExchange(self.flat_grad.numel() * 4, self.group, self.dev, double_buffered=True)
+            try:
+                self.x_grad = parallel.P2PExchange(self.flat_grad.numel() * 4, self.group, self.dev, double_buffered=True)
+                if self.global_fast:
+                    self.x_y = parallel.P2PExchange(2 * B * self.H * 2, self.group, self.dev)
+                    self.x_lse = parallel.P2PExchange(B * 4, self.group, self.dev)
+            except RuntimeError as e:                       # raised on ALL ranks together (see P2PExchange): NCCL path
+                import warnings
+                warnings.warn(f"FusedTrainer: {e}; using NCCL collectives")
+                self.p2p = False
+        if self.p2p:
             if self.global_fast:
-                self.x_y = parallel.P2PExchange(2 * B * self.H * 2, self.group, self.dev)
-                self.x_lse = parallel.P2PExchange(B * 4, self.group, self.dev)
                 self.yg_bf16 = self.x_y.gathered(torch.bfloat16, (2 * B, self.H)).view(self.world * 2 * B, self.H)
                 self.lse_g = self.x_lse.gathered(torch.float32, (B,)).reshape(self.world * B) \
                     if (B * 4) % 256 == 0 else None

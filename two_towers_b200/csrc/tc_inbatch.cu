@@ -142,6 +142,9 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint64_t dd0 = umma_desc_kmajor(smem_u32(d_tiles), 0);
     mbar_wait(q_ready, 0);
     tc_fence_after();
+    // This warp shares its scheduler with two busy epilogue warps: every instruction it does not issue is tensor-pipe
+    // time won back.  The issuing lane is elected ONCE; descriptors advance by loop-carried adds.
+    const bool leader = elect_one();
     for (int i = 0; i < nt; ++i) {
       const int s = i % FWD_STAGES, b = i & 1;
       if (lane == 0) TT_FTL(0, i, 0);
@@ -150,15 +153,19 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
       if (lane == 0) TT_FTL(0, i, 2);
       tc_fence_after();
-      const uint64_t dd = dd0 + (uint64_t)((s * d_bytes) >> 4);
-      for (int kb = 0; kb < kq; ++kb)
+      if (leader) {
+        uint64_t dd = dd0 + (uint64_t)((s * d_bytes) >> 4);
+        uint32_t ta = tmem_q;
+        const uint32_t td = tmem_s + b * FWD_BN;
+        for (int kb = 0; kb < kq; ++kb) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (elect_one())
-            umma_bf16_ts(tmem_s + b * FWD_BN, tmem_q + (uint32_t)(kb * 32 + k * 8),
-                         dd + (uint64_t)(kb * (FWD_BN * 128 / 16) + k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(td, ta + (uint32_t)(k * 8), dd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          dd += FWD_BN * 128 / 16;
+          ta += 32;
         }
-      if (elect_one()) { umma_commit(&d_empty[s]); umma_commit(&s_full[b]); }
+        umma_commit(&d_empty[s]);
+        umma_commit(&s_full[b]);
+      }
       __syncwarp();
       if (lane == 0) TT_FTL(0, i, 3);
     }

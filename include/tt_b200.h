@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TT_ABI_VERSION 1
+#define TT_ABI_VERSION 2
 
 enum { TT_OK = 0, TT_ERR_INVALID = -1, TT_ERR_CUDA = -2, TT_ERR_ARCH = -3, TT_ERR_WORKSPACE = -4,
        TT_ERR_UNSUPPORTED = -5 };

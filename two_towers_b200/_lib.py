@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtt_b200.so")
 TT_PREC_FP32 = 0
 TT_PREC_BF16 = 1
 TT_TOPK_MAX = 1024
+TT_ABI_VERSION = 2          # must equal TT_ABI_VERSION in include/tt_b200.h (a stale .so fails loudly at load)
 
 _vp, _i, _i64, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
 
@@ -107,8 +108,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError == ABI mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.tt_abi_version() != 1:
-        raise RuntimeError(f"two_towers_b200: ABI version {lib.tt_abi_version()} != 1")
+    if lib.tt_abi_version() != TT_ABI_VERSION:
+        raise RuntimeError(f"two_towers_b200: ABI version {lib.tt_abi_version()} != {TT_ABI_VERSION} (rebuild: make -C two_towers_b200/csrc)")
     _lib = lib
     return lib
 

@@ -386,10 +386,12 @@ def bench_search(args, dev, rank, world, pg):
         ws = torch.empty(tt.ops.topk_scan_workspace_bytes(hi - lo, H, 1, k), dtype=torch.uint8, device=dev)
         nrep = max(10, args.steps)
 
+        sharded = parallel.ShardedTopK(index, k, lo, tt.ops, pg, cosine=False, nq=1) if world > 1 else None
+
         def one(i):
             q = qs[i % 64:i % 64 + 1]
-            if world > 1:
-                return parallel.sharded_topk(index, q, k, lo, tt.ops, pg, cosine=False)
+            if world > 1:                                   # one graph replay: scan, peer-memory candidate exchange, merge
+                return sharded(q)
             return tt.ops.topk_scan(index, q, k, cosine=False, id_offset=lo, workspace=ws)
         for i in range(3):
             one(i)

@@ -108,6 +108,13 @@ def _worker(rank, world, port, q_out):
         fs, fi = tt.ops.topk_scan(torch.tensor(idx, device=dev), torch.tensor(qs, device=dev), k, cosine=False)
         assert torch.equal(i, fi) and torch.equal(s, fs)
         assert i[0, :2].tolist() == [3, 70_000]
+        # graph-replayed sharded search: same answers on every call (both buffer parities, fresh queries)
+        st = parallel.ShardedTopK(torch.tensor(idx[lo:hi], device=dev), k, lo, tt.ops, cosine=False, nq=3)
+        for rep in range(5):
+            qr = torch.tensor(np.roll(qs, rep, axis=0), device=dev)
+            s2, i2 = st(qr)
+            fs2, fi2 = tt.ops.topk_scan(torch.tensor(idx, device=dev), qr, k, cosine=False)
+            assert torch.equal(i2, fi2) and torch.equal(s2, fs2), rep
         q_out.put((rank, "ok"))
     except Exception:
         import traceback

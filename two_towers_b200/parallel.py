@@ -161,16 +161,19 @@ class P2PExchange:
             torch.as_strided(body.view(dtype), (self.world, *per_rank_shape),
                              (self.slot_bytes // esz, *_contig_strides(per_rank_shape)))
 
-    def current_half(self) -> torch.Tensor:
-        """[world, slot_bytes] uint8 view of the slot set the LAST allgather() of a double-buffered exchange filled."""
-        off = 256 + (self.world * self.slot_bytes if (self.double_buffered and (self.rounds & 1)) else 0)
+    def current_half(self, round_no=None) -> torch.Tensor:
+        """[world, slot_bytes] uint8 view of the slot set round `round_no` (default: the last allgather()) fills."""
+        r = self.rounds if round_no is None else round_no
+        off = 256 + (self.world * self.slot_bytes if (self.double_buffered and (r & 1)) else 0)
         return self._raw[off:off + self.world * self.slot_bytes].view(self.world, self.slot_bytes)
 
-    def allgather(self, src: torch.Tensor) -> None:
-        """Launch the exchange on the current stream: afterwards slot r of the local buffer holds rank r's `src`."""
+    def allgather(self, src: torch.Tensor, count: bool = True) -> None:
+        """Launch the exchange on the current stream: afterwards slot r of the local buffer holds rank r's `src`.
+        count=False while CAPTURING a CUDA graph (the kernel does not run yet): the caller bumps `rounds` per replay."""
         import ctypes as C
         from . import _lib
-        self.rounds += 1                                     # mirrors the device-side round counter (all calls go through here)
+        if count:
+            self.rounds += 1                                 # mirrors the device-side round counter (all calls go through here)
         nbytes = src.numel() * src.element_size()
         _lib.check(self.lib.tt_p2p_allgather(C.byref(self.desc), C.c_void_p(src.data_ptr()), nbytes,
                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tt_p2p_allgather")
@@ -218,6 +221,49 @@ def shard_bounds(n: int, rank: int, ws: int) -> Tuple[int, int]:
     base, rem = divmod(n, ws)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedTopK:
+    """Row-sharded exact top-k as ONE CUDA-graph replay per call: local scan + top-k, candidate exchange over NVLink peer
+    memory, merge.  At 8 shards the scan of a 10 M x 256 index takes ~0.1-0.2 ms, so the launch / Python overhead of the
+    eager chain (sharded_topk) would be most of a query; the graph removes it.  Collective: every rank calls it in step.
+    The returned tensors are static buffers, valid until the next call.  Falls back to sharded_topk when the
+    peer-memory exchange is unavailable."""
+
+    def __init__(self, index_shard: torch.Tensor, k: int, id_offset: int, kernels, group=None, cosine: bool = True, nq: int = 1):
+        self.index, self.k, self.id_offset, self.kernels, self.group, self.cosine, self.nq = \
+            index_shard, k, id_offset, kernels, group, cosine, nq
+        self.q = torch.zeros(nq, index_shard.shape[1], dtype=torch.float32, device=index_shard.device)
+        self.graphs, self.outs = [None, None], [None, None]
+        self.xch = None
+        if index_shard.is_cuda and hasattr(kernels, "packed_topk_buffer") and index_shard.shape[0] >= k:
+            _, self.nbytes, self.id_off = kernels.packed_topk_buffer(nq, k, index_shard.device)
+            self.xch = _search_exchange(self.nbytes, group, index_shard.device)
+
+    def _body(self, round_no: int, count: bool):
+        x = self.xch
+        s_view, i_view = self.kernels.packed_views(x.staging[0, :self.nbytes], self.nq, self.k, self.id_off)
+        self.kernels.topk_scan(self.index, self.q, self.k, cosine=self.cosine, id_offset=self.id_offset, out=(s_view, i_view))
+        x.allgather(x.staging[0], count=count)
+        return self.kernels.topk_merge_packed(x.current_half(round_no), self.nq, self.k, self.id_off)
+
+    def __call__(self, queries: torch.Tensor):
+        if self.xch is None or queries.shape[0] != self.nq:
+            return sharded_topk(self.index, queries, self.k, self.id_offset, self.kernels, self.group, self.cosine)
+        self.q.copy_(queries)
+        nxt = self.xch.rounds + 1
+        par = nxt & 1
+        if self.graphs[par] is None:
+            out = self._body(nxt, count=True)                  # eager once for this parity (warms every kernel), ...
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                          # ... then record the same chain for later replays
+                self.outs[par] = self._body(nxt, count=False)
+            self.graphs[par] = g
+            return out
+        self.xch.rounds = nxt
+        self.graphs[par].replay()
+        return self.outs[par]
 
 
 def sharded_topk(index_shard: torch.Tensor, queries: torch.Tensor, k: int, id_offset: int, kernels, group=None,

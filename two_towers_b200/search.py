@@ -104,6 +104,15 @@ class TwoTowerSearch(BaseSearch):
     # ------------------------------------------------------------------ search
     def _topk(self, q_emb: torch.Tensor, k: int):
         if self.group is not None or ws_initialized():
+            if self.document_embeddings.is_cuda and hasattr(parallel, "ShardedTopK"):
+                key = (k, q_emb.shape[0], self.document_embeddings.data_ptr())
+                cache = self.__dict__.setdefault("_sharded", {})
+                if key not in cache:                            # one CUDA graph (scan, peer-memory exchange, merge) per shape
+                    cache.clear()
+                    cache[key] = parallel.ShardedTopK(self.document_embeddings, k, self.row_offset, self.kernels, self.group,
+                                                      self.cosine, nq=q_emb.shape[0])
+                s, i = cache[key](q_emb)
+                return s.clone(), i.clone()                     # the graph's outputs are static buffers
             return parallel.sharded_topk(self.document_embeddings, q_emb, k, self.row_offset, self.kernels,
                                          self.group, self.cosine)
         return self.kernels.topk_scan(self.document_embeddings, q_emb, k, cosine=self.cosine,

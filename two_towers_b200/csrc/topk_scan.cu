@@ -269,6 +269,12 @@ struct ScoreIdKeys {            // R lists of [nq, k]; list r starts at r * rank
 
 constexpr int kMergeThreads = 1024;
 
+// Exact top-k of L unique 64-bit keys (R sorted lists of k) by an MSB-first radix select, one CTA per query.
+// Keys are read from global memory ONCE into registers (up to kMergeRegKeys per thread; longer inputs fall back to
+// re-reading), the eight digit passes then only touch shared-memory histograms, and the "which bin holds the k-th key"
+// search is a warp-parallel suffix scan instead of a 256-step serial loop.
+constexpr int kMergeRegKeys = 16;          // 1024 threads x 16 = 16384 keys in registers (148 block lists x k <= 110)
+
 template <typename Keys>
 __global__ void __launch_bounds__(kMergeThreads)
 merge_topk_kernel(Keys src, int64_t L, int k, int64_t id_offset, float* __restrict__ out_scores,
@@ -276,39 +282,85 @@ merge_topk_kernel(Keys src, int64_t L, int k, int64_t id_offset, float* __restri
   __shared__ unsigned int hist[256];
   __shared__ u64 sel[TT_TOPK_MAX];
   __shared__ u64 s_prefix, s_mask;
-  __shared__ int s_need, s_count;
+  __shared__ int s_need, s_count, s_all;
   const int q = blockIdx.x, tid = threadIdx.x;
-  if (tid == 0) { s_prefix = 0ull; s_mask = 0ull; s_need = k; s_count = 0; }
+  const bool in_regs = L <= (int64_t)kMergeRegKeys * kMergeThreads;
+  u64 mine[kMergeRegKeys];
+  if (in_regs) {
+#pragma unroll
+    for (int u = 0; u < kMergeRegKeys; ++u) {
+      const int64_t i = (int64_t)u * kMergeThreads + tid;
+      mine[u] = i < L ? src.get(q, i) : 0ull;               // 0 never matches a live prefix: see below
+    }
+  }
+  if (tid == 0) { s_prefix = 0ull; s_mask = 0ull; s_need = k; s_count = 0; s_all = 0; }
   for (int i = tid; i < TT_TOPK_MAX; i += kMergeThreads) sel[i] = 0ull;
   __syncthreads();
   for (int shift = 56; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += kMergeThreads) hist[i] = 0u;
     __syncthreads();
     const u64 prefix = s_prefix, mask = s_mask;
+    if (in_regs) {
+#pragma unroll
+      for (int u = 0; u < kMergeRegKeys; ++u) {
+        const u64 key = mine[u];
+        if (key != 0ull && (key & mask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & 0xffull)], 1u);
+      }
+    } else {
+      for (int64_t i = tid; i < L; i += kMergeThreads) {
+        const u64 key = src.get(q, i);
+        if (key != 0ull && (key & mask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & 0xffull)], 1u);
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // lane l owns bins [8l, 8l+8).  Walking from bin 255 down, find the bin in which the running count reaches `need`.
+      unsigned c[8], lane_sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[8 * tid + j]; lane_sum += c[j]; }
+      unsigned above = lane_sum;                               // inclusive suffix sum over lanes tid..31
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_down_sync(0xffffffffu, above, o);
+        if (tid + o < 32) above += t;
+      }
+      const int need = s_need;
+      const unsigned excl = above - lane_sum;                   // keys in bins above this lane's
+      const bool here = excl < (unsigned)need && above >= (unsigned)need;
+      const unsigned who = __ballot_sync(0xffffffffu, here);
+      if (who == 0u) {                                          // fewer than k live keys in total (first pass only):
+        if (tid == 0) { s_all = 1; s_prefix = 0ull; }           // every live key is selected, the rest is padding
+      } else if (here) {
+        int rem = need - (int)excl, bin = 7;
+        for (; bin > 0; --bin) {
+          if ((int)c[bin] >= rem) break;
+          rem -= (int)c[bin];
+        }
+        s_need = rem;
+        s_prefix = prefix | ((u64)(8 * tid + bin) << shift);
+        s_mask = mask | (0xffull << shift);
+      }
+    }
+    __syncthreads();
+    if (s_all) break;                                        // CTA-uniform
+  }
+  const u64 kth = s_prefix;                                // exact k-th largest key (keys are unique); 0 = take all
+  if (in_regs) {
+#pragma unroll
+    for (int u = 0; u < kMergeRegKeys; ++u) {
+      const u64 key = mine[u];
+      if (key >= kth && key != 0ull) {
+        const int p = atomicAdd(&s_count, 1);
+        if (p < TT_TOPK_MAX) sel[p] = key;
+      }
+    }
+  } else {
     for (int64_t i = tid; i < L; i += kMergeThreads) {
       const u64 key = src.get(q, i);
-      if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & 0xffull)], 1u);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int need = s_need, bin = 255;
-      for (; bin > 0; --bin) {
-        const int c = (int)hist[bin];
-        if (c >= need) break;
-        need -= c;
+      if (key >= kth && key != 0ull) {
+        const int p = atomicAdd(&s_count, 1);
+        if (p < TT_TOPK_MAX) sel[p] = key;
       }
-      s_need = need;
-      s_prefix = prefix | ((u64)bin << shift);
-      s_mask = mask | (0xffull << shift);
-    }
-    __syncthreads();
-  }
-  const u64 kth = s_prefix;                                // exact k-th largest key (keys are unique)
-  for (int64_t i = tid; i < L; i += kMergeThreads) {
-    const u64 key = src.get(q, i);
-    if (key >= kth && key != 0ull) {
-      const int p = atomicAdd(&s_count, 1);
-      if (p < TT_TOPK_MAX) sel[p] = key;
     }
   }
   __syncthreads();

@@ -339,6 +339,9 @@ merge_topk_kernel(Keys src, int64_t L, int k, int64_t id_offset, float* __restri
         s_need = rem;
         s_prefix = prefix | ((u64)(8 * tid + bin) << shift);
         s_mask = mask | (0xffull << shift);
+        // the chosen bin holds exactly the keys still needed: every key >= prefix (lower digits zero) is selected and the
+        // remaining digit passes cannot change that -- stop (typically after the 3rd of 8 passes)
+        if ((int)c[bin] == rem) s_all = 1;
       }
     }
     __syncthreads();

@@ -298,17 +298,19 @@ def test_inbatch_bf16_full_size_known_answers():
     close(dq, rq.cpu().numpy(), 3e-2, "dq vs fp32 kernel"); close(dd, rd.cpu().numpy(), 3e-2, "dd vs fp32 kernel")
 
 
-@pytest.mark.parametrize("B,tied,id_dtype", [(1024, True, torch.int64), (4096, True, torch.int32), (4096, False, torch.int64)])
-def test_fused_trainer_bf16_tracks_fp32(B, tied, id_dtype):
+@pytest.mark.parametrize("B,tied,id_dtype,E,H", [(1024, True, torch.int64, 64, 256), (4096, True, torch.int32, 64, 256),
+                                                 (4096, False, torch.int64, 64, 256), (512, True, torch.int64, 32, 64),
+                                                 (384, False, torch.int32, 48, 128)])
+def test_fused_trainer_bf16_tracks_fp32(B, tied, id_dtype, E, H):
     """Same batch, same init: one bf16 tensor-core step stays within 2e-2 of the fp32 step.  B = 4096 takes every fused
     path of the trainer (pooling matrix in the tower kernel, loss backward fused with the normalise backward through
     CTA pairs, embedding gradient through P^T da1); B = 1024 the split-slice path; untied towers the accumulate path."""
     import copy
     import two_towers_b200 as tt
     torch.manual_seed(0)
-    emb = tt.embeddings.build("lookup", 128, embedding_dim=64)
-    m32 = tt.build_two_tower("mean", emb, hidden_dim=256, tied_weights=tied).to(DEV)
-    m16 = copy.deepcopy(m32)
+    emb = tt.embeddings.build("lookup", 128, embedding_dim=E)
+    m32 = tt.build_two_tower("mean", emb, hidden_dim=H, tied_weights=tied).to(DEV)     # E % 64 != 0: unfused tower forward,
+    m16 = copy.deepcopy(m32)                                                           # compact normalise state in the workspace
     g = torch.Generator().manual_seed(3)
     L = 64
     q = torch.randint(0, 128, (B, L), generator=g).to(id_dtype); d = torch.randint(0, 128, (B, L), generator=g).to(id_dtype)
@@ -316,6 +318,8 @@ def test_fused_trainer_bf16_tracks_fp32(B, tied, id_dtype):
     t16 = tt.FusedTrainer(m16, loss="in_batch", batch_size=B, max_len=L, precision="bf16", use_cuda_graph=True, id_dtype=id_dtype)
     if B == 4096:
         assert t16.ce_fused and t16.embed_fused and t16.embed_in_tower
+    if E % 64 != 0:
+        assert t16.embed_fused and not t16.embed_in_tower
     l32 = t32.step(q, d).item()
     t16.step(q, d)
     l16 = t16.read_loss_async()()

@@ -111,6 +111,11 @@ def _worker(rank, world, port, q_out):
             np.testing.assert_allclose(s.numpy(), rs, rtol=1e-6)
             if N > 60:
                 assert list(i[0, :2].numpy()) == [3, 60]
+            # the graph-replayed front end falls back to the same eager chain without a CUDA peer-memory exchange
+            st = parallel.ShardedTopK(torch.tensor(idx[lo:hi]), k, lo, K, nq=3)
+            s2, i2 = st(torch.tensor(qs))
+            np.testing.assert_array_equal(i2.numpy(), ri)
+            np.testing.assert_allclose(s2.numpy(), rs, rtol=1e-6)
         q_out.put((rank, "ok"))
     except Exception as e:                                     # pragma: no cover
         import traceback

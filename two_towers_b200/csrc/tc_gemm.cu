@@ -159,23 +159,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       __syncwarp();
     }
   } else if (warp == 1) {
+    // This warp shares its scheduler with epilogue warps (of this CTA and of the co-resident one): the issuing lane is
+    // elected once and the stage-0 descriptors are built once; a later stage only shifts their start-address field.
     const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    const bool leader = elect_one();
+    const uint32_t a0 = smem_u32(tiles), b0 = a0 + kATile;
+    const uint64_t da_base = p.a_mn ? umma_desc_mnmajor(a0, 0, 8192u) : umma_desc_kmajor(a0, 0);
+    const uint64_t db_base = p.b_mn ? umma_desc_mnmajor(b0, 0, 8192u) : umma_desc_kmajor(b0, 0);
+    const uint64_t sa = p.a_mn ? 128u : 2u, sb = p.b_mn ? 128u : 2u;       // (bytes per k16 step) >> 4
     for (int i = 0; i < nkb; ++i) {
       const int s = i % kStages;
       mbar_wait(&full_bar[s], (i / kStages) & 1);
       tc_fence_after();
-      const uint32_t a = smem_u32(tiles + s * kStageBytes), b = a + kATile;
-      const uint64_t da0 = p.a_mn ? umma_desc_mnmajor(a, 0, 8192u) : umma_desc_kmajor(a, 0);
-      const uint64_t db0 = p.b_mn ? umma_desc_mnmajor(b, 0, 8192u) : umma_desc_kmajor(b, 0);
-      const uint64_t sa = p.a_mn ? 128u : 2u, sb = p.b_mn ? 128u : 2u;     // (bytes per k16 step) >> 4
+      if (leader) {
+        const uint64_t off = (uint64_t)((uint32_t)s * kStageBytes >> 4);   // (address >> 4) lives in the low 14 bits
+        const uint64_t da0 = da_base + off, db0 = db_base + off;
 #pragma unroll
-      for (int k = 0; k < BK / 16; ++k) {
-        if (elect_one()) umma_bf16(tmem_acc, da0 + sa * k, db0 + sb * k, idesc, (i | k) != 0);
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, da0 + sa * k, db0 + sb * k, idesc, (i | k) != 0);
+        umma_commit(&empty_bar[s]);                       // stage reusable once these MMAs have read it
       }
-      if (elect_one()) umma_commit(&empty_bar[s]);        // stage reusable once these MMAs have read it
       __syncwarp();
     }
-    if (elect_one()) umma_commit(acc_bar);                // accumulator complete
+    if (leader) umma_commit(acc_bar);                     // accumulator complete
     __syncwarp();
   } else {
     // epilogue warps 2..5 -> TMEM lane quarters (warp % 4).  Each thread holds one accumulator row;

@@ -6,7 +6,8 @@ plugin API: ``tokenisers.REGISTRY``, ``embeddings.REGISTRY``, ``encoders.TOWER_R
 hand-written CUDA kernels inside ``csrc/libtt_b200.so`` (C ABI: ``include/tt_b200.h``); there
 is no CPU / eager-PyTorch fallback.
 """
-from . import _lib, embeddings, encoders, evaluate, losses, ops, parallel, search, tokenisers, train  # noqa: F401
+from . import _lib, dataset, embeddings, encoders, evaluate, losses, ops, parallel, search, tokenisers, train  # noqa: F401
+from .dataset import TripletDataset
 from .embeddings import BaseEmbedding, LookupEmbedding, PretrainedEmbedding
 from .encoders import (AveragePoolingTower, BaseTower, MeanPoolingTower, TwoTower, TOWER_REGISTRY, build_tower,
                        build_two_tower)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TT_ABI_VERSION 2
+#define TT_ABI_VERSION 3
 
 enum { TT_OK = 0, TT_ERR_INVALID = -1, TT_ERR_CUDA = -2, TT_ERR_ARCH = -3, TT_ERR_WORKSPACE = -4,
        TT_ERR_UNSUPPORTED = -5 };
@@ -45,6 +45,11 @@ const char* tt_last_error(void);
 int tt_require_sm100(int device);
 /* Number of kernel launches issued by this library in the calling process so far. */
 int64_t tt_launch_count(void);
+/* Token ids outside [0, V): the reference's nn.Embedding raises IndexError (twotower/embeddings.py:33-40).  The gather
+ * kernels treat such a token as padding (no out-of-bounds read) and record it in a mapped host word; this call returns 1
+ * and the last offending id if any completed kernel has seen one (no synchronisation here: call it after the stream /
+ * event wait that made the results visible), optionally clearing the record.  The Python layer turns it into IndexError. */
+int tt_bad_token_id(int64_t* id, int clear);
 
 /* ---- K1: token-id gather + masked mean pool ----------------------------------------------
  * tt_embed_gather     : LookupEmbedding.forward, twotower/embeddings.py:33-40 (W[ids]).
@@ -130,22 +135,27 @@ int tt_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
 /* ---- K3': avg_pool tower projection  Linear(E,H) -> Dropout(p) -> LayerNorm(H) -> normalise -
  * Replaces AveragePoolingTower.projection + F.normalize, twotower/encoders.py:100-104,144-150.
  * has_projection == 0 (H == E): y = normalise(x) only (w,b,gamma,beta ignored).
- * Dropout: p == 0 or training == 0 -> identity (the parity-tested mode); otherwise a
- * counter-based keep-mask from (seed, element index), recomputed in backward.
+ * Dropout: p == 0 or training == 0 -> identity; otherwise nn.Dropout semantics (kept values scaled by 1/(1-p)) with a
+ * counter-based keep-mask: element (row, col) is kept iff u01(splitmix64(seed' + (row*H + col) * 0x9E3779B97F4A7C15)) >= p,
+ * recomputed in backward.  seed' = seed, or seed + (*seed_step + 1) * 0xD1B54A32D192ED03 when seed_step (nullable device
+ * int64, e.g. tt_adamw_step's counter) is given: a CUDA-graph replay then draws a fresh mask every optimizer step.
+ * torch's Philox stream cannot be reproduced; parity is checked with the same mask applied to the oracle.
+ * TT_PREC_BF16: the Linear(E,H) forward and its two backward products run on the tcgen05 tensor cores (bf16 operands,
+ * fp32 accumulate, any E / H); Dropout, LayerNorm and the normalise stay fp32 row kernels.
  * Saved: a [R,H] (post-dropout pre-LN), stats [R,2] (mean, rstd), z [R,H] (LN output).
  */
-size_t tt_proj_ln_workspace(int64_t R, int E, int H);
+size_t tt_proj_ln_workspace(int64_t R, int E, int H, int precision);
 int tt_proj_ln_fwd(const float* x, const float* w, const float* b, const float* gamma,
                    const float* beta, int64_t R, int E, int H, int has_projection,
-                   float dropout_p, int training, uint64_t seed,
+                   float dropout_p, int training, uint64_t seed, const int64_t* seed_step,
                    float* a, float* stats, float* z, float* y,
-                   void* workspace, size_t workspace_bytes, void* stream);
+                   int precision, void* workspace, size_t workspace_bytes, void* stream);
 int tt_proj_ln_bwd(const float* dy, const float* x, const float* w, const float* gamma,
                    const float* a, const float* stats, const float* z,
                    int64_t R, int E, int H, int has_projection,
-                   float dropout_p, int training, uint64_t seed,
+                   float dropout_p, int training, uint64_t seed, const int64_t* seed_step,
                    float* dx, float* dw, float* db, float* dgamma, float* dbeta,
-                   void* workspace, size_t workspace_bytes, void* stream);
+                   int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K4: in-batch sampled-softmax loss, fused similarity GEMM + online logsumexp CE --------
  * Replaces in_batch_sampled_softmax_loss, twotower/losses.py:107-116: S = Q D^T; S/temperature;
@@ -270,7 +280,7 @@ int tt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
  * (base[rank] is the local one).  Layout: 256-byte header (arrival counters, round, ticket) + world slots of slot_bytes.
  * tt_p2p_allgather : ONE kernel stores `bytes` of src into slot `rank` of every rank's buffer (16-byte stores over
  *                    NVLink), signals, and spins until all ranks' slots for this round have arrived in the LOCAL buffer.
- *                    When it retires the gathered data is base[rank] + 256.  Every rank must call it with the same bytes.
+ *                    When it retires the gathered data is base[rank] + 256.  bytes may differ from call to call (<= slot_bytes).
  *                    Capturable in a CUDA graph; replaces an NCCL all-gather whose fixed cost dominates at these sizes.
  * tt_p2p_sum_slots : out[i] = sum_r slot_r[i] in rank order -- with an all-gather of the gradients this is an all-reduce
  *                    whose result is bitwise identical on every rank.
@@ -281,6 +291,9 @@ typedef struct {
   void* base[8];              /* exchange buffer of rank p as mapped in this process */
   int double_buffered;        /* rounds alternate between two slot sets: safe when this is the only exchange between two
                                  uses of the same buffer (see p2p.cu); consumers then read via tt_p2p_sum_slots */
+  int ctas;                   /* CTAs per exchange kernel, the SAME on every rank and for every call on this exchange
+                                 (0: tt_p2p_allgather_ctas(slot_bytes)); calls may then move any byte count <= slot_bytes */
+  int timeout_s;              /* seconds a rank waits for its peers before it gives up (0: 600); see tt_p2p_status */
 } tt_p2p_t;
 size_t tt_p2p_buffer_bytes(int world, size_t slot_bytes, int double_buffered);
 int tt_p2p_alloc(size_t bytes, void** ptr);
@@ -290,6 +303,9 @@ int tt_p2p_import(const void* handle64, void** ptr);
 int tt_p2p_unimport(void* ptr);
 int tt_p2p_allgather_ctas(size_t bytes);
 int tt_p2p_allgather(const tt_p2p_t* x, const void* src, size_t bytes, void* stream);
+/* Synchronous: *timed_out_rank = the rank an exchange kernel gave up waiting for (its output is then garbage), -1 if none.
+ * A time-out never traps: the CUDA context stays usable and the host decides (raise, fall back to NCCL, retry). */
+int tt_p2p_status(const tt_p2p_t* x, int* timed_out_rank);
 int tt_p2p_sum_slots(const tt_p2p_t* x, size_t n_floats, float* out, void* stream);
 
 /* ---- optimizer: torch.optim.AdamW(model.parameters(), lr), train.py:359 ------

@@ -19,6 +19,88 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _gather_np(t, world):
+    import torch.distributed as dist
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t.contiguous())
+    return torch.cat(parts, 0).cpu().numpy()
+
+
+def _trainer_vs_oracle(rank, world, dev, log):
+    """ONE data-parallel FusedTrainer step on `world` ranks == the single-process reference step on
+    the concatenated batch (twotower/train.py:120-139; losses.py:107-116 in-batch, :28-35 triplet): loss and every
+    parameter gradient, for the paths bench.py runs (bf16, global negatives, peer-memory exchange and NCCL) and for the
+    triplet / local-negatives data-parallel steps."""
+    import torch.distributed as dist
+    import two_towers_b200 as tt
+    from _parity import BF16_RTOL, check, oracle_step, tower_grads, tower_params, trainer_gates
+    B, L, V, E, H = 256, 64, 128, 64, 256
+    gq = torch.Generator().manual_seed(100 + rank)
+    ids = [torch.randint(0, V, (B, L), generator=gq) for _ in range(3)]
+    all_ids = [_gather_np(t.to(dev), world) for t in ids]
+    cases = [("in_batch", True, "bf16", True, True), ("in_batch", True, "bf16", False, True), ("in_batch", True, "bf16", True, False),
+             ("in_batch", False, "bf16", True, True), ("triplet", False, "bf16", True, True), ("triplet", False, "bf16", True, False),
+             ("in_batch", True, "fp32", True, True), ("triplet", False, "fp32", False, True)]
+    for loss, glob, prec, p2p, tied in cases:
+        torch.manual_seed(0)
+        emb = tt.embeddings.build("lookup", V, embedding_dim=E)
+        model = tt.build_two_tower("mean", emb, hidden_dim=H, tied_weights=tied).to(dev)
+        pq0 = tower_params(model.query_tower)
+        pd0 = pq0 if tied else tower_params(model.document_tower)
+        tr = tt.FusedTrainer(model, loss=loss, temperature=0.1, margin=2.5, batch_size=B, max_len=L, precision=prec,
+                             process_group=dist.group.WORLD, global_negatives=glob, p2p=p2p)
+        if loss == "in_batch" and glob and prec == "bf16":
+            assert tr.global_fast and tr.p2p == p2p           # the path bench.py times at N > 1
+        local = tr.step(*ids[:tr.passes]).clone()
+        total = local.clone()
+        dist.all_reduce(total)
+        gates = None
+        if prec == "bf16":
+            gates = tuple(_gather_np(torch.tensor(g, device=dev).to(torch.uint8), world).astype(bool) for g in trainer_gates(tr))
+        groups = None if (loss != "in_batch" or glob) else [(r * B, (r + 1) * B) for r in range(world)]
+        rl, rgq, rgd, flips = oracle_step(pq0, pd0, all_ids[0], all_ids[1], all_ids[2] if loss == "triplet" else None, loss=loss,
+                                          temperature=0.1, margin=2.5, gates=gates, groups=groups)
+        # in-batch: every rank's loss kernel is scaled by 1 / (world * B_local), so the rank values ADD UP to the reference
+        # loss (global negatives) or to the mean of the per-rank losses (local negatives); the triplet kernel reports the
+        # local row mean, whose average over ranks is the reference value on the concatenated batch
+        got_loss = total.item() / world if loss == "triplet" else total.item()
+        tol = BF16_RTOL if prec == "bf16" else 1e-4
+        head = (f"  {world}-rank FusedTrainer loss={loss} global_negatives={glob} {prec} p2p={tr.p2p} tied={tied}: "
+                f"loss {got_loss:.6f} oracle {rl:.6f} gates flipped {flips:.2%}")
+        print(head); log.append(head)
+        assert abs(got_loss - rl) <= tol * abs(rl), (got_loss, rl)
+        assert flips < 0.01
+        got_q = tower_grads(model.query_tower)
+        for k in rgq:
+            check(got_q[k], rgq[k], tol, f"grad query/{k}", log)
+        if not tied:
+            got_d = tower_grads(model.document_tower)
+            for k in ("w1", "b1", "w2", "b2"):
+                check(got_d[k], rgd[k], tol, f"grad document/{k}", log)
+        both = _gather_np(tr.flat.double().sum().reshape(1), world)
+        assert both[0] == both[1]                             # identical parameters on every rank after the step
+        del tr, model
+    # ---- SURVEY 8e row 5: sharded index build -- concat of the shards == the single-GPU matrix, bit for bit ----------
+    torch.manual_seed(0)
+    tok = tt.CharTokeniser().fit(["abcdefghijklmnopqrstuvwxyz 0123456789"])
+    emb = tt.embeddings.build("lookup", tok.vocab_size, embedding_dim=E)
+    model = tt.build_two_tower("mean", emb, hidden_dim=H, tied_weights=True).to(dev)
+    docs = [f"document number {i} about topic {i % 17} and {(i * 7) % 13}" for i in range(1001)]
+    for idt in ("fp32", "bf16"):
+        s = tt.TwoTowerSearch(model, tok, device=dev, index_dtype=idt, process_group=dist.group.WORLD, encode_batch_size=128)
+        s.index_documents(docs)
+        lo, hi = tt.parallel.shard_bounds(len(docs), rank, world)
+        assert s.row_offset == lo and tuple(s.document_embeddings.shape) == (hi - lo, H) and s.num_documents == len(docs)
+        full = s._encode(docs, model.document_tower)          # what a single GPU builds (same tower, same kernels)
+        if idt == "bf16":
+            full = tt.ops.cast_bf16(full)
+        assert torch.equal(s.document_embeddings, full[lo:hi])
+        res = s.search("document number 500 about topic 7 and 3", top_k=5)
+        one = tt.ops.topk_scan(full, s._encode(["document number 500 about topic 7 and 3"], model.query_tower), 5, cosine=True)
+        assert [r["document"] for r in res] == [docs[i] for i in one[1][0].tolist()]
+    log.append("  sharded index_documents: shard rows == single-GPU matrix rows (fp32 and bf16), sharded search == unsharded")
+
+
 def _worker(rank, world, port, q_out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -36,7 +118,7 @@ def _worker(rank, world, port, q_out):
         D = O.normalize(g.standard_normal((world * B, H))).astype(np.float32)
         ql = torch.tensor(Q[rank * B:(rank + 1) * B], device=dev)
         dl = torch.tensor(D[rank * B:(rank + 1) * B], device=dev)
-        for prec, tol in (("fp32", 2e-5), ("bf16", 3e-2)):
+        for prec, tol in (("fp32", 2e-5), ("bf16", 2e-2)):
             loss, lse, dglob = parallel.global_inbatch_fwd(ql, dl, t, tt.ops, precision=prec)
             total = loss.clone()
             dist.all_reduce(total)
@@ -98,7 +180,7 @@ def _worker(rank, world, port, q_out):
         l_p2p, w_p2p = run(True)
         assert l_nccl == l_p2p, (l_nccl, l_p2p)               # 2 ranks: a + b in either order is the same float
         assert torch.equal(w_nccl, w_p2p)
-        # ---- sharded search == unsharded ---------------------------------------------------------------------        # ---- sharded search == unsharded ---------------------------------------------------------------------
+        # ---- sharded search == unsharded ---------------------------------------------------------------------
         N, k = 100_003, 50
         idx = O.normalize(g.standard_normal((N, H))).astype(np.float32)
         idx[70_000] = idx[3]
@@ -115,6 +197,13 @@ def _worker(rank, world, port, q_out):
             s2, i2 = st(qr)
             fs2, fi2 = tt.ops.topk_scan(torch.tensor(idx, device=dev), qr, k, cosine=False)
             assert torch.equal(i2, fi2) and torch.equal(s2, fs2), rep
+        log = []
+        _trainer_vs_oracle(rank, world, dev, log)
+        if rank == 0:
+            out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+            os.makedirs(out_dir, exist_ok=True)
+            with open(os.path.join(out_dir, "multi_parity.log"), "w") as f:
+                f.write("\n".join(log) + "\n")
         q_out.put((rank, "ok"))
     except Exception:
         import traceback
@@ -135,7 +224,7 @@ def test_two_gpu_nccl_equivalence():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in procs]
+    results = [q.get(timeout=900) for _ in procs]
     for p in procs:
         p.join(30)
         if p.is_alive():

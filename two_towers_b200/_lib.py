@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtt_b200.so")
 TT_PREC_FP32 = 0
 TT_PREC_BF16 = 1
 TT_TOPK_MAX = 1024
-TT_ABI_VERSION = 2          # must equal TT_ABI_VERSION in include/tt_b200.h (a stale .so fails loudly at load)
+TT_ABI_VERSION = 3          # must equal TT_ABI_VERSION in include/tt_b200.h (a stale .so fails loudly at load)
 
 _vp, _i, _i64, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
 
@@ -25,6 +25,7 @@ SIGNATURES = {
     "tt_last_error": (C.c_char_p, []),
     "tt_require_sm100": (_i, [_i]),
     "tt_launch_count": (_i64, []),
+    "tt_bad_token_id": (_i, [_vp, _i]),
     "tt_embed_gather": (_i, [_vp, _i, _vp, _i64, _i64, _i, _vp, _vp]),
     "tt_embed_pool_fwd": (_i, [_vp, _i, _vp, _i64, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "tt_embed_pool_bwd_workspace": (_sz, [_i64, _i, _i64, _i]),
@@ -34,9 +35,9 @@ SIGNATURES = {
     "tt_mlp_fwd_embed_ok": (_i, [_i, _i, _i64]),
     "tt_mlp_bwd": (_i, [_vp] * 6 + [_i64, _i, _i] + [_vp] * 9 + [_i, _i64, _vp, _vp, _vp, _vp, _vp] + [_i, _vp, _sz, _vp]),
     "tt_mlp_embed_workspace": (_sz, [_i64, _i, _i64]),
-    "tt_proj_ln_workspace": (_sz, [_i64, _i, _i]),
-    "tt_proj_ln_fwd": (_i, [_vp] * 5 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 4 + [_vp, _sz, _vp]),
-    "tt_proj_ln_bwd": (_i, [_vp] * 7 + [_i64, _i, _i, _i, _f, _i, _u64] + [_vp] * 5 + [_vp, _sz, _vp]),
+    "tt_proj_ln_workspace": (_sz, [_i64, _i, _i, _i]),
+    "tt_proj_ln_fwd": (_i, [_vp] * 5 + [_i64, _i, _i, _i, _f, _i, _u64, _vp] + [_vp] * 4 + [_i, _vp, _sz, _vp]),
+    "tt_proj_ln_bwd": (_i, [_vp] * 7 + [_i64, _i, _i, _i, _f, _i, _u64, _vp] + [_vp] * 5 + [_i, _vp, _sz, _vp]),
     "tt_inbatch_ce_workspace": (_sz, [_i64, _i64, _i, _i]),
     "tt_inbatch_ce_fwd": (_i, [_vp] * 4 + [_i64, _i64, _i, _f, _i64, _f] + [_vp] * 3 + [_i, _vp, _sz, _vp]),
     "tt_inbatch_ce_bwd": (_i, [_vp] * 5 + [_i64, _i64, _i, _f, _i64, _f] + [_vp] * 3 + [_i, _vp, _sz, _vp]),
@@ -62,7 +63,8 @@ class MlpEmbed(C.Structure):
 
 class P2P(C.Structure):
     """tt_p2p_t (include/tt_b200.h)"""
-    _fields_ = [("world", _i), ("rank", _i), ("slot_bytes", _sz), ("base", _vp * 8), ("double_buffered", _i)]
+    _fields_ = [("world", _i), ("rank", _i), ("slot_bytes", _sz), ("base", _vp * 8), ("double_buffered", _i),
+                ("ctas", _i), ("timeout_s", _i)]
 
 
 class CePass(C.Structure):
@@ -84,6 +86,7 @@ SIGNATURES.update({
     "tt_p2p_unimport": (_i, [_vp]),
     "tt_p2p_allgather_ctas": (_i, [_sz]),
     "tt_p2p_allgather": (_i, [_vp, _vp, _sz, _vp]),
+    "tt_p2p_status": (_i, [_vp, _vp]),
     "tt_p2p_sum_slots": (_i, [_vp, _sz, _vp, _vp]),
     "tt_inbatch_ce_bwd_fused_ok": (_i, [_i64, _i64, _i64, _i64, _i]),
     "tt_inbatch_ce_bwd_nparts_ex": (_i, [_i64, _i64, _i64, _i64, _i]),
@@ -125,3 +128,11 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().tt_launch_count())
+
+
+def raise_on_bad_ids() -> None:
+    """IndexError if a completed gather kernel has seen a token id outside [0, V) -- where the reference's nn.Embedding
+    raises (twotower/embeddings.py:33-40).  Call after the synchronisation that made the results visible."""
+    bad = C.c_int64(0)
+    if load().tt_bad_token_id(C.byref(bad), 1):
+        raise IndexError(f"index out of range in self (token id {bad.value} is outside the embedding table)")

@@ -20,6 +20,7 @@ void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int require_device();                       // TT_OK iff current device is sm_100
 void count_launch(int n = 1);
+long long* bad_id_word();                   // device alias of the mapped host word that records an out-of-range token id (may be null)
 
 #define TT_CHECK_ARG(cond, ...)                                   \
   do {                                                            \

@@ -26,6 +26,13 @@ namespace tt {
 template <typename IdT>
 __device__ __forceinline__ int64_t load_id(const IdT* p) { return (int64_t)__ldg(p); }
 
+// The reference's nn.Embedding raises IndexError for an id outside [0, V) (embeddings.py:33-40).  A kernel cannot raise:
+// it treats the token as padding (no out-of-bounds read) and records the offending id in a mapped host word that the
+// host inspects at its next synchronisation point (tt_bad_token_id -> IndexError in the Python layer).
+__device__ __forceinline__ void report_bad_id(long long* word, int64_t id) {
+  if (word) *reinterpret_cast<volatile long long*>(word) = (long long)id * 2 + 1;
+}
+
 // ---------------------------------------------------------------------------------------
 // K1 forward
 // ---------------------------------------------------------------------------------------
@@ -34,7 +41,7 @@ __global__ void __launch_bounds__(256)
 embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ table, int64_t rows,
                       int L, int64_t V, int E, int tpt, float* __restrict__ pooled,
                       float* __restrict__ inv_len, __nv_bfloat16* __restrict__ pooled_bf16,
-                      __nv_bfloat16* __restrict__ pool_bf16) {
+                      __nv_bfloat16* __restrict__ pool_bf16, long long* __restrict__ bad_id) {
   extern __shared__ int fwd_hist[];                    // [warps][V] token histogram (only with pool_bf16)
   pdl_trigger();
   pdl_wait();
@@ -67,6 +74,7 @@ embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ tab
         const int64_t my_id = next_id;
         if (tb + 32 < L) next_id = (tb + 32 + lane < L) ? load_id(rid + tb + 32 + lane) : 0;   // prefetch the next id block
         const int my_row = (my_id > 0 && my_id < V) ? (int)my_id : -1;       // -1 == masked token
+        if (my_id < 0 || my_id >= V) report_bad_id(bad_id, my_id);           // nn.Embedding raises IndexError here
         cnt += __popc(__ballot_sync(0xffffffffu, my_row >= 0));
         if (pool_bf16 && cbase == 0 && my_row >= 0) atomicAdd(&hist[my_row], 1);   // integer counts: order-free, exact
         const int nb = min(32, L - tb);
@@ -163,13 +171,14 @@ embed_pool_fwd_kernel(const IdT* __restrict__ ids, const float* __restrict__ tab
 // plain gather (API compatibility with LookupEmbedding.forward -> [B,L,E])
 template <typename IdT>
 __global__ void embed_gather_kernel(const IdT* __restrict__ ids, const float* __restrict__ table,
-                                    int64_t n_tokens, int64_t V, int E, float* __restrict__ out) {
+                                    int64_t n_tokens, int64_t V, int E, float* __restrict__ out, long long* __restrict__ bad_id) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t t = warp; t < n_tokens; t += nwarps) {
     int64_t id = load_id(ids + t);
     const bool ok = id >= 0 && id < V;
+    if (!ok && lane == 0) report_bad_id(bad_id, id);
     for (int e = lane; e < E; e += 32) out[t * E + e] = ok ? __ldg(table + id * E + e) : 0.f;
   }
 }
@@ -204,7 +213,7 @@ pool_matrix_kernel(const IdT* __restrict__ ids, const float* __restrict__ inv_le
 template <typename IdT>
 __global__ void __launch_bounds__(256)
 pool_only_kernel(const IdT* __restrict__ ids, int64_t rows, int L, int V, float* __restrict__ inv_len,
-                 __nv_bfloat16* __restrict__ P) {
+                 __nv_bfloat16* __restrict__ P, long long* __restrict__ bad_id) {
   extern __shared__ int hist[];                       // [warps][V]
   pdl_trigger();
   pdl_wait();
@@ -219,6 +228,7 @@ pool_only_kernel(const IdT* __restrict__ ids, int64_t rows, int L, int V, float*
     const int t = t0 + lane;
     const int64_t id = t < L ? load_id(ids + row * L + t) : 0;
     const bool ok = id > 0 && id < V;
+    if (id < 0 || id >= V) report_bad_id(bad_id, id);
     if (ok) atomicAdd(&h[(int)id], 1);                // integer: exact, order-independent
     cnt += __popc(__ballot_sync(0xffffffffu, ok));
   }
@@ -356,7 +366,7 @@ static int embed_pool_fwd_t(const IdT* ids, const float* table, int64_t rows, in
   const size_t hsm = pool_bf16 ? (size_t)warps * V * sizeof(int) : 0;
   if (pooled == nullptr) {                             // histogram only: the consumer multiplies P by the table itself
     if (!pool_bf16 || V % 8 != 0) { set_error("embed_pool_fwd: pooled == NULL needs pool_bf16 and V %% 8 == 0"); return TT_ERR_INVALID; }
-    TT_CUDA(launch_kernel(pool_only_kernel<IdT>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, rows, L, (int)V, inv_len, pool_bf16));
+    TT_CUDA(launch_kernel(pool_only_kernel<IdT>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, rows, L, (int)V, inv_len, pool_bf16, bad_id_word()));
     TT_LAUNCH_CHECK("pool_only_kernel");
     return TT_OK;
   }
@@ -365,18 +375,18 @@ static int embed_pool_fwd_t(const IdT* ids, const float* table, int64_t rows, in
                    (pooled_bf16 == nullptr || (reinterpret_cast<uintptr_t>(pooled_bf16) & 7) == 0);
   if (!vec) {
     TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 1, false>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, 32,
-                          pooled, inv_len, pooled_bf16, pool_bf16));
+                          pooled, inv_len, pooled_bf16, pool_bf16, bad_id_word()));
   } else {
     const int chunks = E / 4;
     int tpt = 1;
     while (tpt < chunks && tpt < 32) tpt <<= 1;
     const int per_lane = (int)ceil_div(chunks, tpt);
     if (per_lane <= 1)
-      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 1, true>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16, pool_bf16));
+      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 1, true>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16, pool_bf16, bad_id_word()));
     else if (per_lane == 2)
-      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 2, true>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16, pool_bf16));
+      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 2, true>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16, pool_bf16, bad_id_word()));
     else
-      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 3, true>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16, pool_bf16));
+      TT_CUDA(launch_kernel(embed_pool_fwd_kernel<IdT, 3, true>, dim3(grid), dim3(warps * 32), hsm, s, true, ids, table, rows, L, V, E, tpt, pooled, inv_len, pooled_bf16, pool_bf16, bad_id_word()));
   }
   TT_LAUNCH_CHECK("embed_pool_fwd_kernel");
   return TT_OK;
@@ -447,9 +457,9 @@ int tt_embed_gather(const void* ids, int id_bytes, const float* table, int64_t n
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   unsigned grid = (unsigned)(tt::ceil_div(n_tokens, 8) < 16 * tt::kNumSMs ? tt::ceil_div(n_tokens, 8) : 16 * tt::kNumSMs);
   if (id_bytes == 8)
-    tt::embed_gather_kernel<int64_t><<<grid, 256, 0, s>>>((const int64_t*)ids, table, n_tokens, V, E, out);
+    tt::embed_gather_kernel<int64_t><<<grid, 256, 0, s>>>((const int64_t*)ids, table, n_tokens, V, E, out, tt::bad_id_word());
   else
-    tt::embed_gather_kernel<int32_t><<<grid, 256, 0, s>>>((const int32_t*)ids, table, n_tokens, V, E, out);
+    tt::embed_gather_kernel<int32_t><<<grid, 256, 0, s>>>((const int32_t*)ids, table, n_tokens, V, E, out, tt::bad_id_word());
   TT_LAUNCH_CHECK("embed_gather_kernel");
   return TT_OK;
 }

@@ -11,7 +11,12 @@
 //     target -- when the kernel retires, the local buffer holds all world slots and the next kernel in the stream can
 //     read it.  No host involvement, no second launch, capturable in a CUDA graph.
 // Counters only ever grow (round r expects r * ctas arrivals per peer), so nothing has to be reset between rounds;
-// the round number lives in the local header and is advanced by the last CTA to leave.
+// the round number lives in the local header and is advanced by the last CTA to leave.  The CTA count is a property of
+// the EXCHANGE (tt_p2p_t.ctas, fixed when it is created), not of a call: calls may move any number of bytes up to the
+// slot size and the arrival arithmetic stays consistent on every rank.
+// A peer that never arrives (it died, or sits in a long host-side phase) must not hang the GPU or poison the CUDA
+// context: after tt_p2p_t.timeout_s seconds (default 600) the waiting CTA records 1 + the missing rank in header word 34
+// and returns; the host reads it with tt_p2p_status() at its next synchronisation point and raises.
 // Re-use of a slot by a fast rank cannot overtake a slow reader because every step ends with the gradient exchange:
 // a rank can only leave step k after all ranks have pushed their step-k gradients, i.e. after they are done reading
 // the step-k gather buffers (stream order).  The gradient exchange itself alternates between two slot sets
@@ -28,6 +33,7 @@ constexpr size_t kP2PHeaderBytes = 256;   // [0,32) arrival counters per source 
 
 struct P2PArgs {
   int world, rank, halves;                // halves == 2: rounds alternate between two slot sets (see tt_p2p_t.double_buffered)
+  unsigned timeout_s;
   unsigned char* base[kP2PMaxWorld];      // every rank's exchange buffer as mapped in this process
 };
 
@@ -78,9 +84,10 @@ p2p_allgather_kernel(const P2PArgs a, const uint4* __restrict__ src, size_t n16,
     while (ld_acquire_sys(c) < target) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 20ull * 1000000000ull) {                          // a peer that never arrives must not hang the GPU for good
-        printf("tt p2p_allgather: rank %d gave up waiting for rank %d after 20 s\n", a.rank, (int)threadIdx.x);
-        __trap();
+      if (t1 - t0 > (unsigned long long)a.timeout_s * 1000000000ull) {   // give up, tell the host, keep the context alive
+        hdr[34] = 1u + threadIdx.x;
+        __threadfence_system();
+        break;
       }
     }
   }
@@ -161,6 +168,15 @@ int tt_p2p_allgather_ctas(size_t bytes) {
   return (int)c;
 }
 
+int tt_p2p_status(const tt_p2p_t* x, int* timed_out_rank) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(x && timed_out_rank && x->rank >= 0 && x->rank < tt::kP2PMaxWorld && x->base[x->rank], "p2p_status: bad arguments");
+  unsigned w = 0;
+  TT_CUDA(cudaMemcpy(&w, static_cast<const unsigned*>(x->base[x->rank]) + 34, sizeof(w), cudaMemcpyDeviceToHost));
+  *timed_out_rank = w ? (int)w - 1 : -1;
+  return TT_OK;
+}
+
 int tt_p2p_allgather(const tt_p2p_t* x, const void* src, size_t bytes, void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(x && src && x->world >= 1 && x->world <= tt::kP2PMaxWorld && x->rank >= 0 && x->rank < x->world,
@@ -169,12 +185,14 @@ int tt_p2p_allgather(const tt_p2p_t* x, const void* src, size_t bytes, void* str
                "p2p_allgather: bytes must be a multiple of 16 and fit the slot; src 16-byte aligned");
   tt::P2PArgs a{};
   a.world = x->world; a.rank = x->rank; a.halves = x->double_buffered ? 2 : 1;
+  a.timeout_s = x->timeout_s > 0 ? (unsigned)x->timeout_s : 600u;
   for (int p = 0; p < x->world; ++p) {
     TT_CHECK_ARG(x->base[p] != nullptr, "p2p_allgather: peer %d not mapped", p);
     a.base[p] = static_cast<unsigned char*>(x->base[p]);
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int ctas = tt_p2p_allgather_ctas(bytes);
+  // the grid belongs to the exchange, not to this call's byte count (see the header comment)
+  const int ctas = x->ctas > 0 ? x->ctas : tt_p2p_allgather_ctas(x->slot_bytes);
   TT_CUDA(tt::launch_kernel(tt::p2p_allgather_kernel, dim3((unsigned)ctas), dim3(256), 0, s, true, a, static_cast<const uint4*>(src),
                             bytes / 16, x->slot_bytes));
   TT_LAUNCH_CHECK("p2p_allgather_kernel");

@@ -26,6 +26,30 @@ int check_cuda(cudaError_t e, const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// one mapped, portable host word per process: kernels store (id * 2 + 1) of an out-of-range token id into it
+static long long* g_bad_host = nullptr;
+static long long* g_bad_dev = nullptr;
+static std::atomic<int> g_bad_state{0};                   // 0 not tried, 1 ready, -1 unavailable
+long long* bad_id_word() {
+  int st = g_bad_state.load(std::memory_order_acquire);
+  if (st == 0) {
+    long long* h = nullptr;
+    long long* d = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess && h &&
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) == cudaSuccess && d) {
+      *h = 0;
+      g_bad_host = h; g_bad_dev = d;
+      g_bad_state.store(1, std::memory_order_release);
+      st = 1;
+    } else {
+      (void)cudaGetLastError();
+      g_bad_state.store(-1, std::memory_order_release);
+      st = -1;
+    }
+  }
+  return st == 1 ? g_bad_dev : nullptr;
+}
+
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("TT_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -84,5 +108,14 @@ int tt_abi_version(void) { return TT_ABI_VERSION; }
 const char* tt_last_error(void) { return tt::g_err; }
 int tt_require_sm100(int device) { return tt::check_device(device); }
 int64_t tt_launch_count(void) { return tt::g_launches.load(std::memory_order_relaxed); }
+
+int tt_bad_token_id(int64_t* id, int clear) {
+  if (tt::g_bad_state.load(std::memory_order_acquire) != 1) return 0;
+  const long long w = *reinterpret_cast<volatile long long*>(tt::g_bad_host);
+  if (w == 0) return 0;
+  if (id) *id = (int64_t)(w >> 1);
+  if (clear) *reinterpret_cast<volatile long long*>(tt::g_bad_host) = 0;
+  return 1;
+}
 
 }  // extern "C"

@@ -15,8 +15,9 @@ namespace tc {
 // no link-time dependency on libcuda and still loads on a machine without a driver)
 // ---------------------------------------------------------------------------------------
 // 2-D row-major bf16 matrix [rows, cols] (cols contiguous); box = 64 cols x box_rows rows,
-// 128-byte swizzle, out-of-bounds elements read as zero.  cols*2 bytes must be a multiple of 16.
-int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// 128-byte swizzle, out-of-bounds elements read as zero.  pitch = elements between rows (0: == cols); pitch*2 bytes
+// must be a multiple of 16 (cols itself need not be: columns in [cols, pitch) are out of bounds, i.e. zero).
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t pitch = 0);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------

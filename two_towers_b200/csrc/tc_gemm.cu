@@ -46,15 +46,16 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t pitch) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return TT_ERR_CUDA; }
-  if ((cols * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) {
-    set_error("TMA operand needs 16-byte aligned base and row pitch (cols=%llu)", (unsigned long long)cols);
+  if (pitch == 0) pitch = cols;                          // elements between rows (>= cols; columns past `cols` read as zero)
+  if (pitch < cols || (pitch * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA operand needs 16-byte aligned base and row pitch (cols=%llu pitch=%llu)", (unsigned long long)cols, (unsigned long long)pitch);
     return TT_ERR_UNSUPPORTED;
   }
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * 2};
+  cuuint64_t gstride[1] = {pitch * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -366,6 +367,7 @@ struct TcGemm {
   int M, N, K;
   const __nv_bfloat16* A; int a_mn;      // a_mn ? stored [K,M] : stored [M,K]
   const __nv_bfloat16* B; int b_mn;      // b_mn ? stored [K,N] : stored [N,K]
+  int lda = 0, ldb = 0;                  // row pitch of the stored matrices in elements (0: contiguous); multiple of 8
   float* C = nullptr; __nv_bfloat16* Cb = nullptr; int ldc = 0;
   const float* bias = nullptr; int act = 0; const __nv_bfloat16* mask = nullptr; int ldmask = 0;
   int splits = 1; float* partial = nullptr;
@@ -376,11 +378,11 @@ struct TcGemm {
 template <int BN>
 static int fill_problem(const TcGemm& g, CUtensorMap* tmA, CUtensorMap* tmB, GemmParams* pp) {
   int rc;
-  if (!g.a_mn) rc = make_tmap_bf16(tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM);
-  else         rc = make_tmap_bf16(tmA, g.A, (uint64_t)g.K, (uint64_t)g.M, 64);
+  if (!g.a_mn) rc = make_tmap_bf16(tmA, g.A, (uint64_t)g.M, (uint64_t)g.K, BM, (uint64_t)g.lda);
+  else         rc = make_tmap_bf16(tmA, g.A, (uint64_t)g.K, (uint64_t)g.M, 64, (uint64_t)g.lda);
   if (rc) return rc;
-  if (!g.b_mn) rc = make_tmap_bf16(tmB, g.B, (uint64_t)g.N, (uint64_t)g.K, BN);
-  else         rc = make_tmap_bf16(tmB, g.B, (uint64_t)g.K, (uint64_t)g.N, 64);
+  if (!g.b_mn) rc = make_tmap_bf16(tmB, g.B, (uint64_t)g.N, (uint64_t)g.K, BN, (uint64_t)g.ldb);
+  else         rc = make_tmap_bf16(tmB, g.B, (uint64_t)g.K, (uint64_t)g.N, 64, (uint64_t)g.ldb);
   if (rc) return rc;
   GemmParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.a_mn = g.a_mn; p.b_mn = g.b_mn;
@@ -511,6 +513,27 @@ static int cast3(const float* a, __nv_bfloat16* ab, int64_t na, const float* b, 
 
 int cast3_public(const float* a, __nv_bfloat16* ab, int64_t na, const float* b, __nv_bfloat16* bb, int64_t nb, cudaStream_t s) {
   return cast3(a, ab, na, b, bb, nb, nullptr, nullptr, 0, s);
+}
+
+// fp32 [rows, cols] -> bf16 [rows, pitch] (pitch >= cols, multiple of 8; the pad columns are zeroed).  Lets operands whose
+// inner dimension is not a multiple of 8 (the word tower's E = 300, configs/word2vec_skipgram.yml:23) meet TMA's 16-byte
+// row-pitch rule: the tensor map keeps the true column count, so the pad never enters a product.
+__global__ void __launch_bounds__(256)
+cast_rows_kernel(const float* __restrict__ src, int64_t rows, int cols, int pitch, __nv_bfloat16* __restrict__ dst) {
+  const int64_t n = rows * (int64_t)pitch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / pitch;
+    const int c = (int)(i - r * pitch);
+    dst[i] = __float2bfloat16(c < cols ? src[r * cols + c] : 0.f);
+  }
+}
+static int cast_rows(const float* src, int64_t rows, int cols, int pitch, __nv_bfloat16* dst, cudaStream_t s) {
+  int64_t blocks = ceil_div(rows * (int64_t)pitch, 256);
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  cast_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, rows, cols, pitch, dst);
+  TT_LAUNCH_CHECK("cast_rows_kernel");
+  return TT_OK;
 }
 
 // y = z / max(|z|,1e-12) (fp32 + bf16)
@@ -700,12 +723,13 @@ struct TcMlpPlan {
   int s_dw2, s_dw1;
   size_t xb, w1b, w2b, h1b, act_f, act_b, partial, partial2, cs1, cs2, colsum, total;
 };
+static inline int pad8(int n) { return (n + 7) / 8 * 8; }
 static TcMlpPlan plan_tc_mlp(int64_t R, int E, int H) {
   TcMlpPlan p{};
   p.s_dw2 = tc::pick_splits(H, H, (int)R);
   p.s_dw1 = tc::pick_splits(H, E, (int)R);
-  p.xb = align_up((size_t)R * E * 2);
-  p.w1b = align_up((size_t)H * E * 2);
+  p.xb = align_up((size_t)R * pad8(E) * 2);               // E % 8 != 0: bf16 operands are kept with a row pitch of pad8(E)
+  p.w1b = align_up((size_t)H * pad8(E) * 2);
   p.w2b = align_up((size_t)H * H * 2);
   p.h1b = align_up((size_t)R * H * 2);
   p.act_f = align_up((size_t)R * H * 4);
@@ -723,18 +747,20 @@ static TcMlpPlan plan_tc_mlp(int64_t R, int E, int H) {
 
 size_t tc_mlp_workspace(int64_t R, int E, int H) { return plan_tc_mlp(R, E, H).total; }
 
-static bool tc_mlp_supported(int E, int H) { return (E % 8 == 0) && (H % 8 == 0); }
+// E may be anything (e.g. the word tower's 300): x / W1 are then converted into pad8(E)-pitch bf16 rows inside the call
+static bool tc_mlp_supported(int E, int H) { return E > 0 && (H % 8 == 0); }
 
 int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, int64_t R, int E,
                int H, float* h1, float* z, float* y, __nv_bfloat16* y_bf16, const __nv_bfloat16* x_bf16,
                const __nv_bfloat16* w1_bf16, const __nv_bfloat16* w2_bf16, __nv_bfloat16* h1_bf16, float* inv_norm,
                const tt_mlp_embed_t* embed, void* ws, size_t ws_bytes, cudaStream_t s) {
-  if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0 (E=%d H=%d)", E, H); return TT_ERR_UNSUPPORTED; }
+  if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs H %% 8 == 0 (E=%d H=%d)", E, H); return TT_ERR_UNSUPPORTED; }
   const TcMlpPlan plan = plan_tc_mlp(R, E, H);
   if (ws == nullptr || ws_bytes < plan.total) { set_error("tc_mlp_fwd: workspace too small (%zu < %zu)", ws_bytes, plan.total); return TT_ERR_WORKSPACE; }
   Workspace w(ws, ws_bytes);
-  __nv_bfloat16* xb = w.take<__nv_bfloat16>((size_t)R * E);
-  __nv_bfloat16* w1b = w.take<__nv_bfloat16>((size_t)H * E);
+  const int Ep = pad8(E);
+  __nv_bfloat16* xb = w.take<__nv_bfloat16>((size_t)R * Ep);
+  __nv_bfloat16* w1b = w.take<__nv_bfloat16>((size_t)H * Ep);
   __nv_bfloat16* w2b = w.take<__nv_bfloat16>((size_t)H * H);
   __nv_bfloat16* h1b = w.take<__nv_bfloat16>((size_t)R * H);
   int rc = TT_OK;
@@ -742,6 +768,12 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
     if (!w1_bf16 || !w2_bf16 || !tc_mlp_fwd_pool_supported(E, H, embed->V)) { set_error("tc_mlp_fwd: embed needs bf16 weight shadows and a supported shape (tt_mlp_fwd_embed_ok)"); return TT_ERR_UNSUPPORTED; }
     return tc_mlp_fwd_fused(nullptr, w1_bf16, b1, w2_bf16, b2, R, E, H, h1_bf16 ? h1_bf16 : reinterpret_cast<__nv_bfloat16*>(h1), z, y, y_bf16,
                             inv_norm, (const __nv_bfloat16*)embed->pool_bf16, embed->V, (const __nv_bfloat16*)embed->table_bf16, s);
+  }
+  if (Ep != E) {                               // padded pitch: contiguous caller shadows of x / W1 cannot feed TMA, convert here
+    if (embed) { set_error("tc_mlp_fwd: embed needs E %% 8 == 0"); return TT_ERR_UNSUPPORTED; }
+    rc = tc::cast_rows(x, R, E, Ep, xb, s); if (rc) return rc;
+    rc = tc::cast_rows(w1, H, E, Ep, w1b, s); if (rc) return rc;
+    x_bf16 = xb; w1_bf16 = w1b;
   }
   if (!x_bf16 || !w1_bf16 || !w2_bf16) {       // only the operands without a caller-provided shadow are converted
     rc = tc::cast3(x_bf16 ? nullptr : x, xb, x_bf16 ? 0 : R * E, w1_bf16 ? nullptr : w1, w1b, w1_bf16 ? 0 : (int64_t)H * E,
@@ -758,7 +790,7 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
     return tc_mlp_fwd_fused(xa, w1a, b1, w2a, b2, R, E, H, h1b, z, y, y_bf16, inv_norm, nullptr, 0, nullptr, s);
   if (z == nullptr) z = w.take<float>((size_t)R * H);     // unfused shapes: the pre-normalise tensor lives in the workspace
   tc::TcGemm g{};
-  g.M = (int)R; g.N = H; g.K = E; g.A = xa; g.a_mn = 0; g.B = w1a; g.b_mn = 0;
+  g.M = (int)R; g.N = H; g.K = E; g.A = xa; g.a_mn = 0; g.B = w1a; g.b_mn = 0; g.lda = g.ldb = Ep;
   g.C = nullptr; g.Cb = h1b; g.ldc = H; g.bias = b1; g.act = 1;
   rc = tc::tc_gemm(g, s); if (rc) return rc;
   g = tc::TcGemm{};
@@ -776,15 +808,16 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
                const __nv_bfloat16* h1_bf16, int dy_parts, int64_t dy_part_stride, const tt_mlp_embed_t* embed,
                const __nv_bfloat16* y_bf16, const float* inv_norm, const __nv_bfloat16* dz_bf16, const float* dz_colsum,
                void* ws, size_t ws_bytes, cudaStream_t s) {
-  if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs E %% 8 == 0 and H %% 8 == 0"); return TT_ERR_UNSUPPORTED; }
+  if (!tc_mlp_supported(E, H)) { set_error("TT_PREC_BF16 mlp needs H %% 8 == 0"); return TT_ERR_UNSUPPORTED; }
+  const int Ep = pad8(E);
   if (embed && (embed->V % 8 != 0 || E % 4 != 0)) { set_error("tc_mlp_bwd: embed needs V %% 8 == 0 and E %% 4 == 0"); return TT_ERR_UNSUPPORTED; }
   if (dy_parts < 1) dy_parts = 1;
   if (dy_parts > 1 && H > 512) { set_error("tc_mlp_bwd: split dy needs H <= 512"); return TT_ERR_UNSUPPORTED; }
   const TcMlpPlan plan = plan_tc_mlp(R, E, H);
   if (ws == nullptr || ws_bytes < plan.total) { set_error("tc_mlp_bwd: workspace too small (%zu < %zu)", ws_bytes, plan.total); return TT_ERR_WORKSPACE; }
   Workspace w(ws, ws_bytes);
-  __nv_bfloat16* xb = w.take<__nv_bfloat16>((size_t)R * E);
-  __nv_bfloat16* w1b = w.take<__nv_bfloat16>((size_t)H * E);
+  __nv_bfloat16* xb = w.take<__nv_bfloat16>((size_t)R * Ep);
+  __nv_bfloat16* w1b = w.take<__nv_bfloat16>((size_t)H * Ep);
   __nv_bfloat16* w2b = w.take<__nv_bfloat16>((size_t)H * H);
   __nv_bfloat16* h1b = w.take<__nv_bfloat16>((size_t)R * H);
   float* dz = w.take<float>((size_t)R * H);
@@ -797,6 +830,12 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   float* cs2 = w.take<float>(plan.cs2 / 4);
   float* cpart = w.take<float>(plan.colsum / 4);
   int rc = TT_OK;
+  if (Ep != E) {                               // see tc_mlp_fwd
+    if (embed) { set_error("tc_mlp_bwd: embed needs E %% 8 == 0"); return TT_ERR_UNSUPPORTED; }
+    rc = tc::cast_rows(x, R, E, Ep, xb, s); if (rc) return rc;
+    rc = tc::cast_rows(w1, H, E, Ep, w1b, s); if (rc) return rc;
+    x_bf16 = xb; w1_bf16 = w1b;
+  }
   if (!x_bf16 || !w1_bf16 || !w2_bf16) {
     rc = tc::cast3(x_bf16 ? nullptr : x, xb, x_bf16 ? 0 : R * E, w1_bf16 ? nullptr : w1, w1b, w1_bf16 ? 0 : (int64_t)H * E,
                    w2_bf16 ? nullptr : w2, w2b, w2_bf16 ? 0 : (int64_t)H * H, s);
@@ -861,10 +900,10 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
   }
   // launch 2: { dw1[H,E] = da1^T x (split-K partials),  dx[R,E] = da1 w1 }
   tc::TcGemm gw1{}, gdx{};
-  gw1.M = H; gw1.N = E; gw1.K = (int)R; gw1.A = da1b; gw1.a_mn = 1; gw1.B = xa; gw1.b_mn = 1; gw1.C = dw1; gw1.ldc = E;
+  gw1.M = H; gw1.N = E; gw1.K = (int)R; gw1.A = da1b; gw1.a_mn = 1; gw1.B = xa; gw1.b_mn = 1; gw1.ldb = Ep; gw1.C = dw1; gw1.ldc = E;
   gw1.splits = plan.s_dw1; gw1.partial = partial2; gw1.defer_reduce = true;
   if (dx) {
-    gdx.M = (int)R; gdx.N = E; gdx.K = H; gdx.A = da1b; gdx.a_mn = 0; gdx.B = w1a; gdx.b_mn = 1; gdx.C = dx; gdx.ldc = E;
+    gdx.M = (int)R; gdx.N = E; gdx.K = H; gdx.A = da1b; gdx.a_mn = 0; gdx.B = w1a; gdx.b_mn = 1; gdx.ldb = Ep; gdx.C = dx; gdx.ldc = E;
     rc = tc::tc_gemm2(gdx, gw1, s); if (rc) return rc;
   } else {
     rc = tc::tc_gemm(gw1, s); if (rc) return rc;
@@ -883,6 +922,68 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
 size_t tc_mlp_embed_workspace(int64_t V, int H, int64_t R) {
   const int sm = tc::pick_splits((int)V, H, (int)R);
   return align_up((size_t)V * H * 4) + align_up(sm > 1 ? (size_t)sm * V * H * 4 : 0) + 256;
+}
+
+// ---------------------------------------------------------------------------------------
+// avg_pool tower projection on the tensor cores (TT_PREC_BF16 path of K3', encoders.py:100-104,144-147):
+// the Linear(E,H) forward and its two backward products; Dropout / LayerNorm / normalise stay in tower.cu's fp32
+// row kernels (they are HBM-bound elementwise work).  Any E and H: operands are converted to pad8-pitch bf16 rows.
+// ---------------------------------------------------------------------------------------
+struct TcProjPlan { int s_dw; size_t xb, wb, dab, partial, total; };
+static TcProjPlan plan_tc_proj(int64_t R, int E, int H) {
+  TcProjPlan p{};
+  p.s_dw = tc::pick_splits(H, E, (int)R);
+  p.xb = align_up((size_t)R * pad8(E) * 2);
+  p.wb = align_up((size_t)H * pad8(E) * 2);
+  p.dab = align_up((size_t)R * pad8(H) * 2);
+  p.partial = align_up(p.s_dw > 1 ? (size_t)p.s_dw * H * E * 4 : 0);
+  p.total = p.xb + p.wb + p.dab + p.partial + 1024;
+  return p;
+}
+size_t tc_proj_workspace(int64_t R, int E, int H) { return plan_tc_proj(R, E, H).total; }
+
+// a[R,H] = x[R,E] w[H,E]^T + b
+int tc_proj_fwd(const float* x, const float* w, const float* b, int64_t R, int E, int H, float* a, void* ws, size_t ws_bytes,
+                cudaStream_t s) {
+  const TcProjPlan plan = plan_tc_proj(R, E, H);
+  if (ws == nullptr || ws_bytes < plan.total) { set_error("tc_proj_fwd: workspace too small (%zu < %zu)", ws_bytes, plan.total); return TT_ERR_WORKSPACE; }
+  Workspace wk(ws, ws_bytes);
+  const int Ep = pad8(E);
+  __nv_bfloat16* xb = wk.take<__nv_bfloat16>((size_t)R * Ep);
+  __nv_bfloat16* wb = wk.take<__nv_bfloat16>((size_t)H * Ep);
+  int rc = tc::cast_rows(x, R, E, Ep, xb, s); if (rc) return rc;
+  rc = tc::cast_rows(w, H, E, Ep, wb, s); if (rc) return rc;
+  tc::TcGemm g{};
+  g.M = (int)R; g.N = H; g.K = E; g.A = xb; g.a_mn = 0; g.B = wb; g.b_mn = 0; g.lda = g.ldb = Ep;
+  g.C = a; g.ldc = H; g.bias = b;
+  return tc::tc_gemm(g, s);
+}
+
+// dw[H,E] = da^T x (fixed-order split-K), dx[R,E] = da w (nullable)
+int tc_proj_bwd(const float* da, const float* x, const float* w, int64_t R, int E, int H, float* dx, float* dw, void* ws,
+                size_t ws_bytes, cudaStream_t s) {
+  const TcProjPlan plan = plan_tc_proj(R, E, H);
+  if (ws == nullptr || ws_bytes < plan.total) { set_error("tc_proj_bwd: workspace too small (%zu < %zu)", ws_bytes, plan.total); return TT_ERR_WORKSPACE; }
+  Workspace wk(ws, ws_bytes);
+  const int Ep = pad8(E), Hp = pad8(H);
+  __nv_bfloat16* xb = wk.take<__nv_bfloat16>((size_t)R * Ep);
+  __nv_bfloat16* wb = wk.take<__nv_bfloat16>((size_t)H * Ep);
+  __nv_bfloat16* dab = wk.take<__nv_bfloat16>((size_t)R * Hp);
+  float* partial = plan.partial ? wk.take<float>(plan.partial / 4) : nullptr;
+  int rc = tc::cast_rows(x, R, E, Ep, xb, s); if (rc) return rc;
+  rc = tc::cast_rows(da, R, H, Hp, dab, s); if (rc) return rc;
+  tc::TcGemm gw{};
+  gw.M = H; gw.N = E; gw.K = (int)R; gw.A = dab; gw.a_mn = 1; gw.lda = Hp; gw.B = xb; gw.b_mn = 1; gw.ldb = Ep;
+  gw.C = dw; gw.ldc = E; gw.splits = plan.s_dw; gw.partial = partial;
+  rc = tc::tc_gemm(gw, s); if (rc) return rc;
+  if (dx) {
+    rc = tc::cast_rows(w, H, E, Ep, wb, s); if (rc) return rc;
+    tc::TcGemm gx{};
+    gx.M = (int)R; gx.N = E; gx.K = H; gx.A = dab; gx.a_mn = 0; gx.lda = Hp; gx.B = wb; gx.b_mn = 1; gx.ldb = Ep;
+    gx.C = dx; gx.ldc = E;
+    rc = tc::tc_gemm(gx, s); if (rc) return rc;
+  }
+  return TT_OK;
 }
 
 // self-test hook used by the GPU test-suite: C = A * B on the tensor cores with either operand major

@@ -19,6 +19,13 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
                const float* dz_colsum, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t tc_mlp_embed_workspace(int64_t V, int H, int64_t R);
 
+// avg_pool projection Linear(E,H) on tcgen05 (tc_gemm.cu): forward a = x w^T + b, backward dw = da^T x, dx = da w
+size_t tc_proj_workspace(int64_t R, int E, int H);
+int tc_proj_fwd(const float* x, const float* w, const float* b, int64_t R, int E, int H, float* a, void* ws, size_t ws_bytes,
+                cudaStream_t s);
+int tc_proj_bwd(const float* da, const float* x, const float* w, int64_t R, int E, int H, float* dx, float* dw, void* ws,
+                size_t ws_bytes, cudaStream_t s);
+
 // whole-MLP forward in one kernel (tc_mlp.cu)
 bool tc_mlp_fused_supported(int E, int H);
 int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const float* b1, const __nv_bfloat16* w2b,

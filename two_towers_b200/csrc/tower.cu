@@ -56,13 +56,21 @@ __device__ __forceinline__ float uniform01(uint64_t seed, uint64_t idx) {
   return (float)(x >> 40) * (1.0f / 16777216.0f);
 }
 
+// seed_step (nullable): device counter read at run time (the trainer passes AdamW's step count), so a CUDA-graph replay
+// draws a fresh mask every step although `seed` itself is baked into the graph; forward and backward of one step see
+// the same value because the optimizer bumps it last.
+__device__ __forceinline__ uint64_t mix_seed(uint64_t seed, const int64_t* seed_step) {
+  return seed_step ? seed + (uint64_t)(*seed_step + 1) * 0xD1B54A32D192ED03ull : seed;
+}
+
 // ---- LayerNorm(H) + normalise, one warp per row (encoders.py:103,150) -----------------------
 // a: in/out (dropout applied in place when active); stats[row] = (mean, rstd); z = LN(a); y = z/|z|
 __global__ void __launch_bounds__(256)
 ln_norm_fwd_kernel(float* __restrict__ a, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   int64_t R, int H, float drop_p, int drop_on, uint64_t seed,
+                   int64_t R, int H, float drop_p, int drop_on, uint64_t seed, const int64_t* __restrict__ seed_step,
                    float* __restrict__ stats, float* __restrict__ z, float* __restrict__ y) {
   const int lane = threadIdx.x & 31;
+  seed = mix_seed(seed, seed_step);
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
   float* ar = a + row * H;
@@ -97,9 +105,10 @@ ln_norm_fwd_kernel(float* __restrict__ a, const float* __restrict__ gamma, const
 __global__ void __launch_bounds__(256)
 ln_norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ stats,
                    const float* __restrict__ z, const float* __restrict__ gamma, int64_t R, int H,
-                   float drop_p, int drop_on, uint64_t seed,
+                   float drop_p, int drop_on, uint64_t seed, const int64_t* __restrict__ seed_step,
                    float* __restrict__ da, float* __restrict__ t_gamma, float* __restrict__ t_beta) {
   const int lane = threadIdx.x & 31;
+  seed = mix_seed(seed, seed_step);
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
   const float* zr = z + row * H;
@@ -309,17 +318,20 @@ size_t tt_mlp_embed_workspace(int64_t V, int H, int64_t R) {
   return tt::tc_mlp_embed_workspace(V, H, R);
 }
 
-size_t tt_proj_ln_workspace(int64_t R, int E, int H) {
+size_t tt_proj_ln_workspace(int64_t R, int E, int H, int precision) {
   if (R <= 0 || E <= 0 || H <= 0) return 256;
-  return tt::plan_proj(R, E, H).total;
+  size_t n = tt::plan_proj(R, E, H).total;
+  if (precision == TT_PREC_BF16) n += tt::align_up(tt::tc_proj_workspace(R, E, H));
+  return n;
 }
 
 int tt_proj_ln_fwd(const float* x, const float* w, const float* b, const float* gamma, const float* beta,
                    int64_t R, int E, int H, int has_projection, float dropout_p, int training, uint64_t seed,
-                   float* a, float* stats, float* z, float* y, void* workspace, size_t workspace_bytes,
-                   void* stream) {
+                   const int64_t* seed_step, float* a, float* stats, float* z, float* y, int precision,
+                   void* workspace, size_t workspace_bytes, void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(x && y && R >= 0 && E > 0 && H > 0, "proj_ln_fwd: bad arguments");
+  TT_CHECK_ARG(precision == TT_PREC_FP32 || precision == TT_PREC_BF16, "proj_ln_fwd: unknown precision %d", precision);
   TT_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "proj_ln_fwd: dropout_p must be in [0,1)");
   if (R == 0) return TT_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -334,22 +346,31 @@ int tt_proj_ln_fwd(const float* x, const float* w, const float* b, const float* 
   if (workspace_bytes < plan.total) { tt::set_error("proj_ln_fwd: workspace too small"); return TT_ERR_WORKSPACE; }
   tt::Workspace wsp(workspace, workspace_bytes);
   float* partial = wsp.take<float>(plan.partial_bytes / sizeof(float));
-  tt::SgemmArgs g{};
-  g.M = (int)R; g.N = H; g.K = E; g.A = x; g.lda = E; g.transA = 0; g.B = w; g.ldb = E; g.transB = 1;
-  g.C = a; g.ldc = H; g.bias = b; g.splits = plan.s_fwd; g.partial = partial;
-  int rc = tt::sgemm(g, s); if (rc) return rc;
+  int rc;
+  if (precision == TT_PREC_BF16) {                          // Linear(E,H) on the tcgen05 tensor cores (bf16 operands, fp32 accumulate)
+    if (workspace_bytes < tt_proj_ln_workspace(R, E, H, precision)) { tt::set_error("proj_ln_fwd: workspace too small"); return TT_ERR_WORKSPACE; }
+    rc = tt::tc_proj_fwd(x, w, b, R, E, H, a, static_cast<char*>(workspace) + plan.total, workspace_bytes - plan.total, s);
+    if (rc) return rc;
+  } else {
+    tt::SgemmArgs g{};
+    g.M = (int)R; g.N = H; g.K = E; g.A = x; g.lda = E; g.transA = 0; g.B = w; g.ldb = E; g.transB = 1;
+    g.C = a; g.ldc = H; g.bias = b; g.splits = plan.s_fwd; g.partial = partial;
+    rc = tt::sgemm(g, s); if (rc) return rc;
+  }
   const int drop_on = (training && dropout_p > 0.f) ? 1 : 0;
-  tt::ln_norm_fwd_kernel<<<tt::row_grid(R), 256, 0, s>>>(a, gamma, beta, R, H, dropout_p, drop_on, seed, stats, z, y);
+  tt::ln_norm_fwd_kernel<<<tt::row_grid(R), 256, 0, s>>>(a, gamma, beta, R, H, dropout_p, drop_on, seed, seed_step, stats, z, y);
   TT_LAUNCH_CHECK("ln_norm_fwd_kernel");
   return TT_OK;
 }
 
 int tt_proj_ln_bwd(const float* dy, const float* x, const float* w, const float* gamma, const float* a,
                    const float* stats, const float* z, int64_t R, int E, int H, int has_projection,
-                   float dropout_p, int training, uint64_t seed, float* dx, float* dw, float* db,
-                   float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream) {
+                   float dropout_p, int training, uint64_t seed, const int64_t* seed_step, float* dx, float* dw,
+                   float* db, float* dgamma, float* dbeta, int precision, void* workspace, size_t workspace_bytes,
+                   void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(dy && x && R > 0 && E > 0 && H > 0, "proj_ln_bwd: bad arguments");
+  TT_CHECK_ARG(precision == TT_PREC_FP32 || precision == TT_PREC_BF16, "proj_ln_bwd: unknown precision %d", precision);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!has_projection) {
     TT_CHECK_ARG(E == H && dx, "proj_ln_bwd: no projection requires E == H and dx");
@@ -367,10 +388,15 @@ int tt_proj_ln_bwd(const float* dy, const float* x, const float* w, const float*
   float* tg = wsp.take<float>((size_t)R * H);
   float* tb = wsp.take<float>((size_t)R * H);
   const int drop_on = (training && dropout_p > 0.f) ? 1 : 0;
-  tt::ln_norm_bwd_kernel<<<tt::row_grid(R), 256, 0, s>>>(dy, a, stats, z, gamma, R, H, dropout_p, drop_on, seed, da, tg, tb);
+  tt::ln_norm_bwd_kernel<<<tt::row_grid(R), 256, 0, s>>>(dy, a, stats, z, gamma, R, H, dropout_p, drop_on, seed, seed_step, da, tg, tb);
   TT_LAUNCH_CHECK("ln_norm_bwd_kernel");
   int rc = tt::colsum(tg, R, H, H, dgamma, cpart, s); if (rc) return rc;
   rc = tt::colsum(tb, R, H, H, dbeta, cpart, s); if (rc) return rc;
+  if (precision == TT_PREC_BF16) {                          // dw = da^T x and dx = da w on the tcgen05 tensor cores
+    if (workspace_bytes < tt_proj_ln_workspace(R, E, H, precision)) { tt::set_error("proj_ln_bwd: workspace too small"); return TT_ERR_WORKSPACE; }
+    rc = tt::colsum(da, R, H, H, db, cpart, s); if (rc) return rc;
+    return tt::tc_proj_bwd(da, x, w, R, E, H, dx, dw, static_cast<char*>(workspace) + plan.total, workspace_bytes - plan.total, s);
+  }
   tt::SgemmArgs g{};
   g.M = H; g.N = E; g.K = (int)R; g.A = da; g.lda = H; g.transA = 1; g.B = x; g.ldb = E; g.transB = 0;
   g.C = dw; g.ldc = E; g.splits = plan.s_dw; g.partial = partial;

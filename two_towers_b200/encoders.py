@@ -46,13 +46,17 @@ class MeanPoolingTower(BaseTower):
 
 class AveragePoolingTower(BaseTower):
     """encoders.py:84-155: same pool; if H != E: Linear -> Dropout -> LayerNorm; F.normalize."""
+    _instances = 0
 
     def __init__(self, embedding: BaseEmbedding, hidden_dim: int, dropout: float = 0.1):
         super().__init__(embedding, hidden_dim)
         e = embedding.embedding_dim
         self.has_projection = hidden_dim != e
         self.dropout_p = float(dropout)
-        self._seed = 0x5EED
+        # every tower instance (and every rank) draws its own dropout stream: untied query / document towers must not
+        # share masks (nn.Dropout modules never do)
+        AveragePoolingTower._instances += 1
+        self._seed = (0x5EED + 0x9E3779B97F4A7C15 * AveragePoolingTower._instances) % (1 << 64)
         if self.has_projection:
             self.projection = nn.Sequential(nn.Linear(e, hidden_dim), nn.Dropout(dropout), nn.LayerNorm(hidden_dim))
 
@@ -68,9 +72,9 @@ class AveragePoolingTower(BaseTower):
             self._seed = (self._seed * 6364136223846793005 + 1442695040888963407) % (1 << 64)
         if torch.is_grad_enabled() and (pooled.requires_grad or
                                         (self.has_projection and args[0].requires_grad)):
-            return ops.ProjLnFn.apply(pooled, *args, self.has_projection, self.dropout_p, drop_on, self._seed)
+            return ops.ProjLnFn.apply(pooled, *args, self.has_projection, self.dropout_p, drop_on, self._seed, self.precision)
         args = tuple(None if a is None else a.detach() for a in args)
-        return ops.proj_ln_fwd(pooled, *args, self.has_projection, self.dropout_p, drop_on, self._seed)[0]
+        return ops.proj_ln_fwd(pooled, *args, self.has_projection, self.dropout_p, drop_on, self._seed, self.precision)[0]
 
 
 class TwoTower(nn.Module):

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import TT_PREC_BF16, TT_PREC_FP32, TT_TOPK_MAX, check
+from ._lib import TT_PREC_BF16, TT_PREC_FP32, TT_TOPK_MAX, check, raise_on_bad_ids  # noqa: F401
 
 _PRECISION = {"fp32": TT_PREC_FP32, "bf16": TT_PREC_BF16, TT_PREC_FP32: TT_PREC_FP32, TT_PREC_BF16: TT_PREC_BF16}
 _default_precision = TT_PREC_FP32
@@ -162,16 +162,35 @@ def mlp_bwd(dy, x, w1, w2, h1, z, need_dx: bool = True, precision=None):
     return dx, dw1, db1, dw2, db2
 
 
-def proj_ln_fwd(x, w, b, gamma, beta, has_projection: bool, dropout_p: float, training: bool, seed: int):
+def dropout_keep_mask(seed: int, rows: int, cols: int, p: float, seed_step: Optional[int] = None):
+    """Host restatement (numpy uint64) of the counter-based keep-mask of tt_proj_ln_fwd/bwd (include/tt_b200.h): used by
+    the parity tests to apply the SAME mask to the CPU restatement of the reference.  -> bool [rows, cols]."""
+    import numpy as np
+    m64 = (1 << 64) - 1
+    if seed_step is not None:
+        seed = (seed + (seed_step + 1) * 0xD1B54A32D192ED03) & m64
+    with np.errstate(over="ignore"):
+        idx = np.arange(rows * cols, dtype=np.uint64)
+        x = np.uint64(seed & m64) + idx * np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    u = (x >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return (u >= np.float32(p)).reshape(rows, cols)
+
+
+def proj_ln_fwd(x, w, b, gamma, beta, has_projection: bool, dropout_p: float, training: bool, seed: int,
+                precision=None, seed_step: Optional[torch.Tensor] = None):
     """-> (y, a, stats, z); a/stats/z are None without projection."""
     _need_cuda(x, w, b, gamma, beta)
+    prec = resolve_precision(precision)
     x = _f32(x)
     R, E = x.shape
     dev = x.device
     if not has_projection:
         y = torch.empty(R, E, dtype=torch.float32, device=dev)
-        check(_lib_().tt_proj_ln_fwd(_p(x), None, None, None, None, R, E, E, 0, 0.0, 0, 0, None, None, None,
-                                     _p(y), None, 0, _stream()), "tt_proj_ln_fwd")
+        check(_lib_().tt_proj_ln_fwd(_p(x), None, None, None, None, R, E, E, 0, 0.0, 0, 0, None, None, None, None,
+                                     _p(y), prec, None, 0, _stream()), "tt_proj_ln_fwd")
         return y, None, None, None
     w, b, gamma, beta = map(_f32, (w, b, gamma, beta))
     H = w.shape[0]
@@ -179,24 +198,25 @@ def proj_ln_fwd(x, w, b, gamma, beta, has_projection: bool, dropout_p: float, tr
     stats = torch.empty(R, 2, dtype=torch.float32, device=dev)
     z = torch.empty(R, H, dtype=torch.float32, device=dev)
     y = torch.empty(R, H, dtype=torch.float32, device=dev)
-    ws = _workspace(_lib_().tt_proj_ln_workspace(R, E, H), dev)
+    ws = _workspace(_lib_().tt_proj_ln_workspace(R, E, H, prec), dev)
     check(_lib_().tt_proj_ln_fwd(_p(x), _p(w), _p(b), _p(gamma), _p(beta), R, E, H, 1, float(dropout_p),
-                                 int(bool(training)), int(seed) & (2 ** 64 - 1), _p(a), _p(stats), _p(z), _p(y),
-                                 _p(ws), ws.numel(), _stream()), "tt_proj_ln_fwd")
+                                 int(bool(training)), int(seed) & (2 ** 64 - 1), _p(seed_step), _p(a), _p(stats), _p(z),
+                                 _p(y), prec, _p(ws), ws.numel(), _stream()), "tt_proj_ln_fwd")
     return y, a, stats, z
 
 
 def proj_ln_bwd(dy, x, w, gamma, a, stats, z, has_projection: bool, dropout_p: float, training: bool, seed: int,
-                need_dx: bool = True):
+                need_dx: bool = True, precision=None, seed_step: Optional[torch.Tensor] = None):
     """-> (dx|None, dw, db, dgamma, dbeta)."""
     _need_cuda(dy, x)
+    prec = resolve_precision(precision)
     dy, x = _f32(dy), _f32(x)
     R, E = x.shape
     dev = x.device
     if not has_projection:
         dx = torch.empty(R, E, dtype=torch.float32, device=dev)
-        check(_lib_().tt_proj_ln_bwd(_p(dy), _p(x), None, None, None, None, None, R, E, E, 0, 0.0, 0, 0, _p(dx),
-                                     None, None, None, None, None, 0, _stream()), "tt_proj_ln_bwd")
+        check(_lib_().tt_proj_ln_bwd(_p(dy), _p(x), None, None, None, None, None, R, E, E, 0, 0.0, 0, 0, None, _p(dx),
+                                     None, None, None, None, prec, None, 0, _stream()), "tt_proj_ln_bwd")
         return dx, None, None, None, None
     H = w.shape[0]
     dx = torch.empty(R, E, dtype=torch.float32, device=dev) if need_dx else None
@@ -204,10 +224,11 @@ def proj_ln_bwd(dy, x, w, gamma, a, stats, z, has_projection: bool, dropout_p: f
     db = torch.empty(H, dtype=torch.float32, device=dev)
     dgamma = torch.empty(H, dtype=torch.float32, device=dev)
     dbeta = torch.empty(H, dtype=torch.float32, device=dev)
-    ws = _workspace(_lib_().tt_proj_ln_workspace(R, E, H), dev)
+    ws = _workspace(_lib_().tt_proj_ln_workspace(R, E, H, prec), dev)
     check(_lib_().tt_proj_ln_bwd(_p(dy), _p(x), _p(_f32(w)), _p(_f32(gamma)), _p(a), _p(stats), _p(z), R, E, H, 1,
-                                 float(dropout_p), int(bool(training)), int(seed) & (2 ** 64 - 1), _p(dx), _p(dw),
-                                 _p(db), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()), "tt_proj_ln_bwd")
+                                 float(dropout_p), int(bool(training)), int(seed) & (2 ** 64 - 1), _p(seed_step), _p(dx),
+                                 _p(dw), _p(db), _p(dgamma), _p(dbeta), prec, _p(ws), ws.numel(), _stream()),
+          "tt_proj_ln_bwd")
     return dx, dw, db, dgamma, dbeta
 
 
@@ -457,26 +478,26 @@ class MlpFn(torch.autograd.Function):
 
 class ProjLnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, gamma, beta, has_projection, dropout_p, training, seed):
-        y, a, stats, z = proj_ln_fwd(x, w, b, gamma, beta, has_projection, dropout_p, training, seed)
+    def forward(ctx, x, w, b, gamma, beta, has_projection, dropout_p, training, seed, precision=None):
+        y, a, stats, z = proj_ln_fwd(x, w, b, gamma, beta, has_projection, dropout_p, training, seed, precision)
         if has_projection:
             ctx.save_for_backward(x, w, gamma, a, stats, z)
         else:
             ctx.save_for_backward(x)
-        ctx.cfg = (has_projection, dropout_p, training, seed)
+        ctx.cfg = (has_projection, dropout_p, training, seed, precision)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        has_projection, dropout_p, training, seed = ctx.cfg
+        has_projection, dropout_p, training, seed, precision = ctx.cfg
         if has_projection:
             x, w, gamma, a, stats, z = ctx.saved_tensors
             dx, dw, db, dg, dbt = proj_ln_bwd(dy, x, w, gamma, a, stats, z, True, dropout_p, training, seed,
-                                              ctx.needs_input_grad[0])
-            return dx, dw, db, dg, dbt, None, None, None, None
+                                              ctx.needs_input_grad[0], precision)
+            return dx, dw, db, dg, dbt, None, None, None, None, None
         (x,) = ctx.saved_tensors
         dx, *_ = proj_ln_bwd(dy, x, None, None, None, None, None, False, 0.0, False, 0)
-        return dx, None, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None, None
 
 
 class InBatchLossFn(torch.autograd.Function):

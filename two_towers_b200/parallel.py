@@ -93,7 +93,7 @@ class P2PExchange:
     graph-capturable kernel launch.  `gathered(dtype, shape)` views the local buffer's slots as a tensor.
     """
 
-    def __init__(self, slot_bytes: int, group=None, device=None, double_buffered: bool = False):
+    def __init__(self, slot_bytes: int, group=None, device=None, double_buffered: bool = False, timeout_s: int = 0):
         from . import _lib
         import ctypes as C
         self.lib = _lib.load()
@@ -121,7 +121,12 @@ class P2PExchange:
         self.desc = _lib.P2P()
         self.desc.world, self.desc.rank, self.desc.slot_bytes = self.world, self.rank, self.slot_bytes
         self.desc.double_buffered = int(self.double_buffered)
+        # the kernel grid is a property of the exchange (same on every rank, every call): calls may then move any
+        # byte count up to the slot and the arrival counters stay consistent
+        self.desc.ctas = int(self.lib.tt_p2p_allgather_ctas(self.slot_bytes))
+        self.desc.timeout_s = int(timeout_s or int(__import__("os").environ.get("TT_P2P_TIMEOUT_S", "0")))
         self._imported = []
+        self._closed = False
         if err is None and all(h is not None for h in handles):
             try:
                 for p in range(self.world):
@@ -178,6 +183,30 @@ class P2PExchange:
         _lib.check(self.lib.tt_p2p_allgather(C.byref(self.desc), C.c_void_p(src.data_ptr()), nbytes,
                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tt_p2p_allgather")
 
+    def check(self) -> None:
+        """Synchronous: raise if an exchange kernel on this rank gave up waiting for a peer (its output was garbage)."""
+        import ctypes as C
+        from . import _lib
+        who = C.c_int(-1)
+        _lib.check(self.lib.tt_p2p_status(C.byref(self.desc), C.byref(who)), "tt_p2p_status")
+        if who.value >= 0:
+            raise RuntimeError(f"peer-memory exchange: rank {self.rank} timed out waiting for rank {who.value}")
+
+    def close(self) -> None:
+        """Unmap the peers' buffers and free the local one (every rank, after a barrier: nobody may still push)."""
+        if self._closed:
+            return
+        self._closed = True
+        try:
+            torch.cuda.synchronize()
+            for q in self._imported:
+                self.lib.tt_p2p_unimport(q)
+            if self.local_ptr:
+                self.lib.tt_p2p_free(self.local_ptr)
+        except Exception:
+            pass
+        self._imported, self.local_ptr, self._raw = [], None, None
+
     def sum_slots(self, out: torch.Tensor) -> None:
         """out[i] = sum over ranks (rank order) of the fp32 slots -- all-gather + this = a deterministic all-reduce."""
         import ctypes as C
@@ -207,6 +236,11 @@ def _search_exchange(nbytes: int, group, device):
         return None
     key = (id(group), (nbytes + 255) // 256 * 256, device.index)
     if key not in _SEARCH_XCH:
+        while len(_SEARCH_XCH) >= 4:                          # bounded: one exchange per (group, record size) in use
+            old = _SEARCH_XCH.pop(next(iter(_SEARCH_XCH)))
+            if old is not None:
+                dist.barrier(group=group)
+                old.close()
         try:
             x = P2PExchange(key[1], group, device, double_buffered=True)
             x.staging = torch.zeros(1, key[1], dtype=torch.uint8, device=device)

@@ -55,6 +55,9 @@ class FusedTrainer:
         self.lib = _lib.load()
 
         qt, dt = model.query_tower, model.document_tower
+        if dt.embedding is not qt.embedding:
+            raise ValueError("FusedTrainer: both towers must share one embedding object (build_two_tower always does, "
+                             "encoders.py:265,270)")
         self.tied = qt is dt
         self.passes = 2 if loss == "in_batch" else 3
         table = qt.embedding.embedding.weight
@@ -72,6 +75,7 @@ class FusedTrainer:
 
         # ---- flat parameter / gradient / moment buffers --------------------------------------
         params = [p for p in model.parameters() if p.requires_grad]
+        self._params = params
         pad = lambda n: (n + 63) // 64 * 64          # every view starts 256-byte aligned
         total = sum(pad(p.numel()) for p in params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
@@ -133,16 +137,22 @@ class FusedTrainer:
             p2p = os.environ.get("TT_P2P", "1") != "0"
         self.p2p = bool(p2p and self.world > 1 and self.world <= 8 and self.flat_grad.numel() % 4 == 0 and
                         (not self.global_fast or (2 * B * self.H * 2) % 256 == 0))
+        # the peer-memory gradient exchange pushes every rank's full fp32 gradient to every peer (world x the bytes of a
+        # ring all-reduce, 2 x world x n x 4 bytes of buffer): right for the KB..MB gradients of the char towers where the
+        # collective's fixed cost dominates, wrong for a 480 MB word-embedding table -- those go through NCCL
+        self.p2p_grad = bool(self.p2p and self.flat_grad.numel() * 4 <= int(os.environ.get("TT_P2P_GRAD_MAX_BYTES", 64 << 20)))
+        self.x_grad = None
         if self.p2p:
             try:
-                self.x_grad = parallel.P2PExchange(self.flat_grad.numel() * 4, self.group, self.dev, double_buffered=True)
+                if self.p2p_grad:
+                    self.x_grad = parallel.P2PExchange(self.flat_grad.numel() * 4, self.group, self.dev, double_buffered=True)
                 if self.global_fast:
                     self.x_y = parallel.P2PExchange(2 * B * self.H * 2, self.group, self.dev)
                     self.x_lse = parallel.P2PExchange(B * 4, self.group, self.dev)
             except RuntimeError as e:                       # raised on ALL ranks together (see P2PExchange): NCCL path
                 import warnings
                 warnings.warn(f"FusedTrainer: {e}; using NCCL collectives")
-                self.p2p = False
+                self.p2p = self.p2p_grad = False
         if self.p2p:
             if self.global_fast:
                 self.yg_bf16 = self.x_y.gathered(torch.bfloat16, (2 * B, self.H)).view(self.world * 2 * B, self.H)
@@ -170,7 +180,10 @@ class FusedTrainer:
             else:
                 raise TypeError(f"FusedTrainer: unsupported tower {type(tower).__name__}")
         bf = self.prec == _lib.TT_PREC_BF16
-        self.pooled_bf16 = torch.empty(R, self.E, dtype=torch.bfloat16, device=self.dev) if bf else None
+        # E % 8 != 0 (the word tower's E = 300): bf16 rows of x / W1 need a 16-byte pitch for TMA, so the tower calls
+        # convert them into padded rows themselves and no contiguous shadow is kept here
+        self.e_shadow = bool(bf and self.E % 8 == 0)
+        self.pooled_bf16 = torch.empty(R, self.E, dtype=torch.bfloat16, device=self.dev) if self.e_shadow else None
         self.inv_norm = torch.empty(R, **f32) if bf else None
         self.y_bf16 = torch.empty(R, self.H, dtype=torch.bfloat16, device=self.dev) if bf else None
         # bf16 shadow of the flat parameter buffer, refreshed by the AdamW kernel -> the tensor-core GEMMs
@@ -197,7 +210,7 @@ class FusedTrainer:
         self.sims = torch.empty(3 * B, **f32)
         self.grad_scale = torch.full((), 1.0 / self.world, **f32)
         lib = self.lib
-        nb = max(lib.tt_mlp_workspace(R, self.E, self.H, self.prec), lib.tt_proj_ln_workspace(R, self.E, self.H),
+        nb = max(lib.tt_mlp_workspace(R, self.E, self.H, self.prec), lib.tt_proj_ln_workspace(R, self.E, self.H, self.prec),
                  lib.tt_embed_pool_bwd_workspace(R, L, self.V, self.E),
                  lib.tt_inbatch_ce_workspace(B * self.world, B * self.world, self.H, self.prec))
         self.ws = torch.empty(int(nb), dtype=torch.uint8, device=self.dev)
@@ -220,6 +233,15 @@ class FusedTrainer:
         off = self.offsets[id(param)]
         return self.flat_bf16[off:off + param.numel()]
 
+    def _dropout_cfg(self, tower, gi: int):
+        """(p, training, seed) of an avg_pool tower's Dropout (encoders.py:102): the reference loop runs model.train(), so
+        Dropout(p) is active.  The mode is read when the step is recorded (CUDA graph): changing model.train()/eval()
+        afterwards needs a new trainer.  The seed mixes the tower instance, its row group and the rank; the per-step
+        variation comes from the device-side step counter (tt_proj_ln_fwd seed_step)."""
+        train = int(bool(self.model.training) and tower.dropout_p > 0)
+        seed = (tower._seed + 0xA24BAED4963EE407 * (gi + 1) + 0x9FB21C651E98DF25 * (self.rank + 1)) % (1 << 64)
+        return float(tower.dropout_p), train, seed
+
     def _tower_fwd(self, gi: int):
         tower, r0, nr = self.groups[gi]
         lib, s, sv = self.lib, self._stream(), self.saved[gi]
@@ -238,18 +260,20 @@ class FusedTrainer:
                 emb = _lib.MlpEmbed(self.pool_bf16[r0:r0 + nr].data_ptr(), self.V, self.table.data_ptr(),
                                     self._shadow(self.table).data_ptr(), None, 0, None, 0)
             check(lib.tt_mlp_fwd(_p(x), _p(l1.weight), _p(l1.bias), _p(l2.weight), _p(l2.bias), nr, self.E, self.H,
-                                 _p(sv["h1"]), _p(z_ptr), _p(y_ptr), _p(yb), _p(xb), _p(self._shadow(l1.weight)),
+                                 _p(sv["h1"]), _p(z_ptr), _p(y_ptr), _p(yb), _p(xb),
+                                 _p(self._shadow(l1.weight) if self.e_shadow else None),
                                  _p(self._shadow(l2.weight)), _p(self.h1_bf16[gi]), _p(inv),
                                  C.byref(emb) if emb is not None else None, self.prec, _p(self.ws),
                                  self.ws.numel(), s), "tt_mlp_fwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
+            p_drop, train, seed = self._dropout_cfg(tower, gi)
             check(lib.tt_proj_ln_fwd(_p(x), _p(lin.weight), _p(lin.bias), _p(ln.weight), _p(ln.bias), nr, self.E,
-                                     self.H, 1, 0.0, 0, 0, _p(sv["a"]), _p(sv["stats"]), _p(sv["z"]), _p(y),
-                                     _p(self.ws), self.ws.numel(), s), "tt_proj_ln_fwd")
+                                     self.H, 1, p_drop, train, seed, _p(self.step_count), _p(sv["a"]), _p(sv["stats"]),
+                                     _p(sv["z"]), _p(y), self.prec, _p(self.ws), self.ws.numel(), s), "tt_proj_ln_fwd")
         else:
-            check(lib.tt_proj_ln_fwd(_p(x), None, None, None, None, nr, self.E, self.H, 0, 0.0, 0, 0, None, None,
-                                     None, _p(y), None, 0, s), "tt_proj_ln_fwd")
+            check(lib.tt_proj_ln_fwd(_p(x), None, None, None, None, nr, self.E, self.H, 0, 0.0, 0, 0, None, None, None,
+                                     None, _p(y), self.prec, None, 0, s), "tt_proj_ln_fwd")
 
     def _tower_bwd(self, gi: int):
         tower, r0, nr = self.groups[gi]
@@ -271,19 +295,21 @@ class FusedTrainer:
             dzc = self.dz_colsum[r0 // 32:(r0 + nr) // 32] if self.ce_fused else None
             check(lib.tt_mlp_bwd(_p(dy), _p(x), _p(l1.weight), _p(l2.weight), _p(sv["h1"]), _p(None if pure else sv["z"]), nr, self.E,
                                  self.H, _p(dx), _p(l1.weight.grad), _p(l1.bias.grad), _p(l2.weight.grad),
-                                 _p(l2.bias.grad), _p(xb), _p(self._shadow(l1.weight)), _p(self._shadow(l2.weight)),
+                                 _p(l2.bias.grad), _p(xb), _p(self._shadow(l1.weight) if self.e_shadow else None),
+                                 _p(self._shadow(l2.weight)),
                                  _p(self.h1_bf16[gi]), self.dy_parts, self.dy_part_stride,
                                  C.byref(emb) if emb is not None else None, _p(yb if pure else None), _p(inv),
                                  _p(dzb), _p(dzc), self.prec, _p(self.ws), self.ws.numel(), s), "tt_mlp_bwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
+            p_drop, train, seed = self._dropout_cfg(tower, gi)
             check(lib.tt_proj_ln_bwd(_p(dy), _p(x), _p(lin.weight), _p(ln.weight), _p(sv["a"]), _p(sv["stats"]),
-                                     _p(sv["z"]), nr, self.E, self.H, 1, 0.0, 0, 0, _p(dx), _p(lin.weight.grad),
-                                     _p(lin.bias.grad), _p(ln.weight.grad), _p(ln.bias.grad), _p(self.ws),
-                                     self.ws.numel(), s), "tt_proj_ln_bwd")
+                                     _p(sv["z"]), nr, self.E, self.H, 1, p_drop, train, seed, _p(self.step_count), _p(dx),
+                                     _p(lin.weight.grad), _p(lin.bias.grad), _p(ln.weight.grad), _p(ln.bias.grad),
+                                     self.prec, _p(self.ws), self.ws.numel(), s), "tt_proj_ln_bwd")
         elif dx is not None:
-            check(lib.tt_proj_ln_bwd(_p(dy), _p(x), None, None, None, None, None, nr, self.E, self.H, 0, 0.0, 0, 0,
-                                     _p(dx), None, None, None, None, None, 0, s), "tt_proj_ln_bwd")
+            check(lib.tt_proj_ln_bwd(_p(dy), _p(x), None, None, None, None, None, nr, self.E, self.H, 0, 0.0, 0, 0, None,
+                                     _p(dx), None, None, None, None, self.prec, None, 0, s), "tt_proj_ln_bwd")
 
     def _step_impl(self):
         lib, B, H, P = self.lib, self.B, self.H, self.passes
@@ -324,7 +350,7 @@ class FusedTrainer:
             check(lib.tt_embed_pool_bwd(_p(self.ids), idb, _p(self.inv_len), _p(self.dpooled), R, self.L, self.V,
                                         self.E, _p(self.table.grad), _p(self.ws), self.ws.numel(), s),
                   "tt_embed_pool_bwd")
-        if self.p2p:
+        if self.p2p_grad:
             self.x_grad.allgather(self.flat_grad)           # every rank's gradients over NVLink, then the same rank-order
             self.x_grad.sum_slots(self.flat_grad)           # sum everywhere: bitwise identical parameters on all ranks
         elif self.world > 1:
@@ -457,8 +483,7 @@ class FusedTrainer:
             self._step_impl()
         elif self.graph is None:
             # warm-up outside capture (module loading, workspace sizing, NCCL communicators) ...
-            st = {k: v.clone() for k, v in (("flat", self.flat), ("m", self.exp_avg), ("v", self.exp_avg_sq),
-                                            ("t", self.step_count))}
+            st = self._snapshot()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -466,10 +491,7 @@ class FusedTrainer:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             # ... restore the state the warm-up step changed, then capture and replay once
-            self.flat.copy_(st["flat"]); self.exp_avg.copy_(st["m"]); self.exp_avg_sq.copy_(st["v"])
-            self.step_count.copy_(st["t"])
-            if self.flat_bf16 is not None:
-                ops.cast_bf16(self.flat, self.flat_bf16)
+            self._restore(st)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step_impl()
@@ -505,12 +527,89 @@ class FusedTrainer:
         self._loss_ev[k].record(torch.cuda.current_stream())
         def wait(k=k):
             self._loss_ev[k].synchronize()
+            _lib.raise_on_bad_ids()                                     # the step's gather kernels have completed
             return float(self._loss_ring[k])
         return wait
 
     def kernels_per_step(self) -> int:
-        """Launches of libtt_b200 kernels in one step (measured on an eager step)."""
+        """Launches of libtt_b200 kernels in one step, measured on an eager step whose effect on the parameters, the
+        Adam moments and the step counter is undone.  Collective: with a process group every rank must call it."""
+        st = self._snapshot()
         before = _lib.launch_count()
         self._step_impl()
         n = _lib.launch_count() - before
+        torch.cuda.current_stream().synchronize()
+        self._restore(st)
         return n
+
+    # ---- state: external weight loads, checkpoint / resume (twotower/utils.py save_checkpoint stores
+    # model.state_dict() and optimizer.state_dict(); train.py:359 torch.optim.AdamW) ---------------------------
+    def _snapshot(self):
+        return {k: v.clone() for k, v in (("flat", self.flat), ("m", self.exp_avg), ("v", self.exp_avg_sq),
+                                          ("t", self.step_count))}
+
+    def _restore(self, st) -> None:
+        self.flat.copy_(st["flat"]); self.exp_avg.copy_(st["m"]); self.exp_avg_sq.copy_(st["v"])
+        self.step_count.copy_(st["t"])
+        self.sync_from_model()
+
+    def sync_from_model(self) -> None:
+        """Call after anything OUTSIDE the trainer wrote the parameters (``model.load_state_dict(...)``, manual
+        ``p.data`` edits): refreshes the bf16 weight shadow the tensor-core kernels read.  The fp32 parameters
+        themselves are views of the flat buffer, so in-place loads land there directly."""
+        for p in self._params:
+            off = self.offsets[id(p)]
+            if p.data.data_ptr() != self.flat.data_ptr() + off * 4:          # someone re-pointed p.data: adopt the values
+                self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + p.numel()].view(p.shape)
+        if self.flat_bf16 is not None:
+            ops.cast_bf16(self.flat, self.flat_bf16)
+
+    def state_dict(self) -> Dict:
+        """torch.optim.AdamW layout: {'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]} with the
+        parameters numbered in ``model.parameters()`` order (trainable ones), so it loads into a reference optimizer."""
+        step = float(self.step_count[0].item())
+        state = {}
+        for i, p in enumerate(self._params):
+            off, n = self.offsets[id(p)], p.numel()
+            state[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[off:off + n].view(p.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": True, "params": list(range(len(self._params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        """Resume from ``state_dict()`` or from a reference ``torch.optim.AdamW.state_dict()`` of the same model."""
+        ids = sd["param_groups"][0]["params"]
+        if len(ids) != len(self._params):
+            raise ValueError(f"optimizer state has {len(ids)} parameters, the model has {len(self._params)}")
+        steps = set()
+        for i, p in zip(ids, self._params):
+            st = sd["state"].get(i)
+            off, n = self.offsets[id(p)], p.numel()
+            if st is None:
+                self.exp_avg[off:off + n].zero_(); self.exp_avg_sq[off:off + n].zero_()
+                continue
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ; the fused AdamW keeps one counter")
+        g = sd["param_groups"][0]
+        hp = (float(g["lr"]), tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"]))
+        if self.graph is not None and hp != (self.lr, tuple(self.betas), self.eps, self.weight_decay):
+            raise ValueError("hyper-parameters are baked into the recorded CUDA graph; create the trainer with the checkpoint's values")
+        self.lr, self.betas, self.eps, self.weight_decay = hp
+        self.step_count.zero_()
+        self.step_count[0] = steps.pop() if steps else 0
+        self.sync_from_model()
+
+    def check(self) -> None:
+        """Synchronise and surface asynchronous failures: a token id outside the table (IndexError, as nn.Embedding raises)
+        or a peer-memory exchange that timed out (RuntimeError)."""
+        torch.cuda.current_stream().synchronize()
+        _lib.raise_on_bad_ids()
+        for x in (getattr(self, "x_grad", None), getattr(self, "x_y", None), getattr(self, "x_lse", None)):
+            if x is not None:
+                x.check()

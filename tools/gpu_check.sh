@@ -1,0 +1,22 @@
+#!/bin/bash
+# One-GPU check used with `gpurun`: GPU test-suite, smoke(), default bench + reference arm.  Logs -> gpurun_out/<tag>_*.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_check.sh r02a [pytest-args...]'
+cd "$(dirname "$0")/.."
+TAG=${1:-check}; shift
+O=gpurun_out; mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader > $O/${TAG}_gpu.txt 2>&1
+timeout 1200 python -m pytest tests -m gpu -q -x -s "$@" > $O/${TAG}_pytest.log 2>&1; echo "pytest exit $?" | tee -a $O/${TAG}_pytest.log
+grep -E "passed|failed|error" $O/${TAG}_pytest.log | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -2 $O/${TAG}_smoke.log
+timeout 900 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench exit $?"; tail -3 $O/${TAG}_bench.err | cut -c1-300
+timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > $O/${TAG}_bench_ref.json 2>> $O/${TAG}_bench.err; echo "ref exit $?"
+python - <<PY
+import json
+try:
+    l = json.loads(open("$O/${TAG}_bench.json").read().strip().splitlines()[-1])
+    print("value %.3g pairs/s  %.1f us/step  e2e %.3g  roofline %.3f  launches/step %s" % (l["value"], l["ms_per_step"] * 1e3, l["e2e"]["value"], l["roofline"]["frac"], l["gpu_launches_per_step"]))
+    for k in ("word_tower", "msmarco", "search"):
+        if k in l: print(k, json.dumps(l[k])[:900])
+except Exception as e:
+    print("no bench line:", e)
+PY

@@ -271,6 +271,20 @@ int tt_topk_scan(const void* index, int index_bf16, const float* queries, int64_
 int tt_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k,
                   int64_t score_rank_stride, int64_t id_rank_stride,
                   float* out_scores, int64_t* out_ids, void* stream);
+/* Batched scan on the tcgen05 tensor cores (bf16 index): S = Q D^T for up to 128 queries per pass over the index
+ * (M = 128 queries x N = 128 documents per tcgen05.mma tile, document tiles streamed by TMA), fused with the same exact
+ * top-k; the reference API scores one query per call (two_tower.py:72-115), so nq queries read the index nq times there
+ * and ceil(nq / 128) times here.  fp32 queries are split into bf16 hi + lo parts, both multiplied into the same fp32
+ * accumulator: scores match tt_topk_scan on the same bf16 index to ~1e-5 relative, ids identical except at such ties.
+ * row_inv_norms (nullable, [N] from tt_index_row_inv_norms, computed once per index): cosine scores
+ * (dot / (max(|q|,1e-8) max(|d|,1e-8))); null = raw dot products.  H % 64 == 0, H <= 256, k <= 128.
+ */
+int tt_topk_scan_batched_ok(int H, int k);
+size_t tt_topk_scan_batched_workspace(int64_t N, int H, int nq);
+int tt_index_row_inv_norms(const void* index_bf16, int64_t N, int H, float* out, void* stream);
+int tt_topk_scan_batched(const void* index_bf16, const float* queries, int64_t N, int H, int nq, int k,
+                         const float* row_inv_norms, int64_t id_offset, float* out_scores, int64_t* out_ids,
+                         void* workspace, size_t workspace_bytes, void* stream);
 /* fp32 -> bf16 row copy used by index_documents when the index is kept in bf16. */
 int tt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -61,14 +61,21 @@ def tower_grads(tower):
                 b1=g(tower.feed_forward[0].bias), w2=g(tower.feed_forward[2].weight), b2=g(tower.feed_forward[2].bias))
 
 
+def bf16_round(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float32).bfloat16().double().numpy()
+
+
 def oracle_step(pq, pd, q_ids, d_ids, n_ids=None, loss="in_batch", temperature=0.1, margin=0.2, gates=None,
-                groups=None):
+                groups=None, quantize_y=False):
     """fp64 oracle of one step (reference semantics: twotower/train.py:120-139 on the given batch).
 
     pq / pd: parameter dicts of the query / document tower (pd is pq when tied; the embedding is always shared).
     gates: optional (gq, gd, gn) boolean [B,H] arrays replacing the oracle's own ReLU gates (see module docstring).
     groups: optional list of (lo, hi) row ranges -- in-batch negatives are then LOCAL to each range and the loss is the
             mean over ranges (data-parallel 'local negatives' / DDP semantics); None = one global batch.
+    quantize_y: round the tower outputs to bf16 before the loss (what TT_PREC_BF16 feeds the loss kernels by definition):
+            separates the kernels' own arithmetic error from the input quantisation of the mode when the loss gradient is
+            ill-conditioned (nearly collinear outputs: dq_i = (sum_j P_ij d_j - d_i) / (tau B) is a small difference).
     Returns (loss, grads_q, grads_d, flip_fraction): gradients per tower (for tied towers grads_d is grads_q = the sum).
     """
     f = np.float64
@@ -83,7 +90,7 @@ def oracle_step(pq, pd, q_ids, d_ids, n_ids=None, loss="in_batch", temperature=0
             g = np.asarray(gates[k], bool)
             flips.append(float((own != g).mean()))
             c["a1"] = np.where(g, 1.0, -1.0)
-        ys.append(y); caches.append(c)
+        ys.append(bf16_round(y) if quantize_y else y); caches.append(c)
     B = ids[0].shape[0]
     if loss == "in_batch":
         rng = groups if groups is not None else [(0, B)]

@@ -304,10 +304,20 @@ def test_msmarco_shape_repeated_positives_and_multiple_negatives():
     rl, gq, gd, flips = oracle_step(pq0, pd0, q.numpy(), d.numpy(), loss="in_batch", temperature=0.1, gates=trainer_gates(tr))
     print(f"  msmarco shape, 4x repeated positives, bf16: loss {got:.6f} oracle {rl:.6f} (>= log 4 = {np.log(4):.4f}), gates flipped {flips:.2%}")
     assert abs(got - rl) <= BF16_RTOL * abs(rl) and rl > np.log(4) - 1e-6 and flips < 0.01
-    for k, v in tower_grads(model.query_tower).items():
-        check(v, gq[k], BF16_RTOL, f"grad query/{k}")
+    # At initialisation every tower output is nearly the same unit vector and only 256 of the 1024 rows are distinct, so
+    # the loss gradient dq_i = (sum_j P_ij d_j - d_i) / (tau B) is the small difference of two nearly equal vectors: the
+    # bf16 rounding of the tower outputs (2^-9 relative, what TT_PREC_BF16 feeds the loss kernels BY DEFINITION) is
+    # amplified by that cancellation.  The kernels are therefore held to 2e-2 against the oracle evaluated on the same
+    # bf16-rounded outputs; against the unrounded oracle the measured error is printed and bounded by 5e-2.
+    _, gq_q, gd_q, _ = oracle_step(pq0, pd0, q.numpy(), d.numpy(), loss="in_batch", temperature=0.1, gates=trainer_gates(tr),
+                                   quantize_y=True)
+    got_q, got_d = tower_grads(model.query_tower), tower_grads(model.document_tower)
+    for k in gq:
+        check(got_q[k], gq_q[k], BF16_RTOL, f"grad query/{k} (bf16 y)")
+        check(got_q[k], gq[k], 5e-2, f"grad query/{k} (exact y)")
     for k in ("w1", "b1", "w2", "b2"):
-        check(tower_grads(model.document_tower)[k], gd[k], BF16_RTOL, f"grad document/{k}")
+        check(got_d[k], gd_q[k], BF16_RTOL, f"grad document/{k} (bf16 y)")
+        check(got_d[k], gd[k], 5e-2, f"grad document/{k} (exact y)")
     # multiple negatives, N = 4, on tower outputs of that shape (fp32 row kernels), B = 4096
     rng = np.random.default_rng(1)
     Bm, N = 4096, 4
@@ -322,3 +332,74 @@ def test_msmarco_shape_repeated_positives_and_multiple_negatives():
     dq, dp, dn = tt.ops.multineg_bwd(t(qv), t(pv), t(nv), probs, 0.1)
     rdq, rdp, rdn = O.multiple_negatives_loss_bwd(qv.astype(f), pv.astype(f), nv.astype(f), 0.1)
     check(dq, rdq, 2e-5, "multineg dq"); check(dp, rdp, 2e-5, "multineg dp"); check(dn, rdn, 2e-5, "multineg dnegs")
+
+
+# ------------------------------------------------------------------------------------------
+# batched search on the tensor cores
+# ------------------------------------------------------------------------------------------
+def _ref_topk(index_bf16, queries, k, inv=None):
+    D = index_bf16.float().double().cpu().numpy()
+    q = queries.double().cpu().numpy()
+    sc = q @ D.T
+    if inv is not None:
+        sc = sc * inv.double().cpu().numpy()[None, :] / np.maximum(np.linalg.norm(q, axis=1, keepdims=True), 1e-8)
+    rs, ri = O.topk_lower_index(sc, k)
+    return sc, rs, ri
+
+
+@pytest.mark.parametrize("N,H,k,nq", [(200_003, 256, 100, 16), (200_003, 256, 100, 130), (50_000, 128, 10, 5), (300, 64, 100, 7),
+                                      (100, 256, 100, 4), (500_000, 256, 100, 64), (4099, 192, 128, 33)])
+def test_topk_scan_batched_matches_exact_topk(N, H, k, nq):
+    """tt_topk_scan_batched (tcgen05 Q D^T + fused top-k) vs torch.topk semantics on fp64 scores of the same bf16 index
+    (ids identical except at ties within tolerance, ties -> lower index) and vs the single-query scan kernel."""
+    import two_towers_b200 as tt
+    g = torch.Generator(device=DEV).manual_seed(N + nq)
+    D = tt.ops.cast_bf16(torch.nn.functional.normalize(torch.randn(N, H, device=DEV, generator=g), dim=-1))
+    q = torch.nn.functional.normalize(torch.randn(nq, H, device=DEV, generator=g), dim=-1)
+    if N > 70_000:
+        D[70_000] = D[3]                                       # exact duplicate far away: tie -> lower id first
+        q[0] = D[3].float()
+    assert tt.ops.topk_scan_batched_ok(D, k)
+    s, i = tt.ops.topk_scan_batched(D, q, k, id_offset=1000)
+    sc, rs, ri = _ref_topk(D, q, k)
+    assert O.topk_ids_match(i.cpu().numpy() - 1000, s.cpu().numpy(), ri, rs, sc, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=2e-5, atol=2e-6)
+    if N > 70_000:
+        assert i[0, :2].tolist() == [1003, 71_000]
+    s1, i1 = tt.ops.topk_scan(D, q, k, cosine=False, id_offset=1000)      # the CUDA-core kernel on the same index
+    assert int((i != i1).sum()) <= max(2, int(0.002 * i.numel()))   # identical up to last-ulp score differences at the boundary
+    s2, i2 = tt.ops.topk_scan_batched(D, q, k, id_offset=1000)
+    assert torch.equal(i, i2) and torch.equal(s, s2)           # deterministic
+
+
+def test_topk_scan_batched_cosine_ties_and_api():
+    import two_towers_b200 as tt
+    g = torch.Generator(device=DEV).manual_seed(5)
+    N, H, k = 30_000, 256, 50
+    D = tt.ops.cast_bf16(torch.randn(N, H, device=DEV, generator=g) * (0.5 + torch.rand(N, 1, device=DEV, generator=g)))   # not unit rows
+    q = torch.randn(9, H, device=DEV, generator=g) * 3.0
+    inv = tt.ops.index_row_inv_norms(D)
+    s, i = tt.ops.topk_scan_batched(D, q, k, row_inv_norms=inv)
+    sc, rs, ri = _ref_topk(D, q, k, inv)
+    assert O.topk_ids_match(i.cpu().numpy(), s.cpu().numpy(), ri, rs, sc, rtol=1e-5, atol=1e-6)
+    s1, i1 = tt.ops.topk_scan(D, q, k, cosine=True)
+    assert int((i != i1).sum()) <= 2
+    # every document identical: all scores tie, the answer is rows 0 .. k-1 in order
+    Dsame = D[:1].expand(5000, H).contiguous()
+    s, i = tt.ops.topk_scan_batched(Dsame, q, k)
+    assert torch.equal(i, torch.arange(k, device=DEV).expand(9, k))
+    # through TwoTowerSearch.search_batch: same documents as per-query search on the bf16 index
+    torch.manual_seed(0)
+    tok = tt.CharTokeniser().fit(["abcdefghijklmnopqrstuvwxyz 0123456789"])
+    emb = tt.embeddings.build("lookup", tok.vocab_size, embedding_dim=64)
+    model = tt.build_two_tower("mean", emb, hidden_dim=128, tied_weights=True).to(DEV)
+    docs = [f"document number {i} about topic {i % 17} and {(i * 7) % 13}" for i in range(3000)]
+    srch = tt.TwoTowerSearch(model, tok, device=DEV, index_dtype="bf16")
+    srch.index_documents(docs)
+    queries = [f"topic {j} and {j % 13}" for j in range(12)]
+    batched = srch.search_batch(queries, top_k=20)
+    srch.batched_min_queries = 10 ** 9                          # force the per-query kernel
+    single = srch.search_batch(queries, top_k=20)
+    for a, b in zip(batched, single):
+        assert [r["document"] for r in a] == [r["document"] for r in b]
+        np.testing.assert_allclose([r["score"] for r in a], [r["score"] for r in b], rtol=1e-4)

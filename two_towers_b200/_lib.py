@@ -50,6 +50,10 @@ SIGNATURES = {
     "tt_topk_scan_workspace": (_sz, [_i64, _i, _i, _i]),
     "tt_topk_scan": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "tt_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _i64, _i64, _vp, _vp, _vp]),
+    "tt_topk_scan_batched_ok": (_i, [_i, _i]),
+    "tt_topk_scan_batched_workspace": (_sz, [_i64, _i, _i]),
+    "tt_index_row_inv_norms": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "tt_topk_scan_batched": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "tt_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "tt_selftest_tc_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "tt_adamw_step": (_i, [_vp] * 4 + [_i64] + [C.c_double] * 5 + [_vp, _vp, _vp]),

@@ -259,6 +259,85 @@ constexpr int kSegChunk = 64;     // sorted tokens per warp
 // One warp per chunk of kSegChunk sorted tokens.  Segments that START inside the chunk are
 // written straight to dW (sole writer).  The leading run that continues a segment begun in an
 // earlier chunk goes to carry[chunk]; seg_fixup adds carries in chunk order.
+// The chunk's (id, row, 1/len) triples are read once, coalesced, into registers (2 per lane) and handed out by
+// shuffle; the gradient row of token t+1 is already in flight while token t is accumulated, and a lane owns NC float4
+// column chunks of the whole row (E <= 128 * NC), so the sorted token list is walked ONCE.  With per-token dependent
+// loads (id -> row -> 1/len -> gradient row) this kernel ran at the latency of ~200 serial round trips per warp.
+template <int NC>
+__global__ void __launch_bounds__(256)
+seg_reduce_vec_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                      const float* __restrict__ inv_len, const float* __restrict__ g, int64_t n_tokens,
+                      int64_t V, int E, float* __restrict__ dW, float* __restrict__ carry) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t p0 = chunk * kSegChunk;
+  if (p0 >= n_tokens) return;
+  const int cnt = (int)((p0 + kSegChunk < n_tokens ? p0 + kSegChunk : n_tokens) - p0);
+  const int nchunks = E >> 2;                              // float4 chunks per row (E % 4 == 0 on this path)
+  uint32_t k2[2], r2[2];
+  float s2[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int t = lane + 32 * u;
+    k2[u] = t < cnt ? __ldg(keys + p0 + t) : 0xffffffffu;
+    r2[u] = t < cnt ? __ldg(vals + p0 + t) : 0u;
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) s2[u] = (lane + 32 * u < cnt && k2[u] < (uint32_t)V) ? __ldg(inv_len + r2[u]) : 0.f;
+  uint32_t prev = (p0 > 0 && lane == 0) ? __ldg(keys + p0 - 1) : 0xffffffffu;
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  auto tok = [&](int t, uint32_t& key, uint32_t& row, float& sc) {
+    const int src = t & 31;
+    const uint32_t ka = __shfl_sync(0xffffffffu, k2[0], src), kb = __shfl_sync(0xffffffffu, k2[1], src);
+    const uint32_t ra = __shfl_sync(0xffffffffu, r2[0], src), rb = __shfl_sync(0xffffffffu, r2[1], src);
+    const float sa = __shfl_sync(0xffffffffu, s2[0], src), sb = __shfl_sync(0xffffffffu, s2[1], src);
+    key = t < 32 ? ka : kb; row = t < 32 ? ra : rb; sc = t < 32 ? sa : sb;
+  };
+  auto load_row = [&](uint32_t key, uint32_t row, float4 (&v)[NC]) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int c = lane + 32 * j;
+      v[j] = (key < (uint32_t)V && c < nchunks) ? __ldg(reinterpret_cast<const float4*>(g + (int64_t)row * E) + c)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float4 acc[NC], cur_v[NC], nxt_v[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t key, row, nkey = 0xffffffffu, nrow = 0u;
+  float sc, nsc = 0.f;
+  tok(0, key, row, sc);
+  load_row(key, row, cur_v);
+  uint32_t cur = key;
+  bool continued = (p0 > 0) && (prev == cur);
+  auto flush = [&]() {
+    if (cur < (uint32_t)V) {
+      float* dst = continued ? carry + chunk * E : dW + (int64_t)cur * E;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nchunks) reinterpret_cast<float4*>(dst)[c] = acc[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  for (int t = 0; t < cnt; ++t) {
+    if (t + 1 < cnt) { tok(t + 1, nkey, nrow, nsc); load_row(nkey, nrow, nxt_v); }   // next gradient row in flight
+    if (key != cur) { flush(); cur = key; continued = false; }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      acc[j].x = fmaf(cur_v[j].x, sc, acc[j].x); acc[j].y = fmaf(cur_v[j].y, sc, acc[j].y);
+      acc[j].z = fmaf(cur_v[j].z, sc, acc[j].z); acc[j].w = fmaf(cur_v[j].w, sc, acc[j].w);
+    }
+    key = nkey; row = nrow; sc = nsc;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) cur_v[j] = nxt_v[j];
+  }
+  flush();
+}
+
+// generic E (not a multiple of 4, or E > 512): scalar columns, 128 per pass
 __global__ void __launch_bounds__(256)
 seg_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                   const float* __restrict__ inv_len, const float* __restrict__ g, int64_t n_tokens,
@@ -300,8 +379,11 @@ seg_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict_
   }
 }
 
-// One warp per chunk whose LAST run continues into later chunks and STARTED in this chunk (or
-// at token 0): walk the following chunks in order, adding their carries.
+// One warp per chunk whose LAST run continues into later chunks and STARTED in this chunk (or at token 0): it owns the
+// fix-up of that id.  The end of the run is found by a binary search over the sorted keys; the carries of the chunks
+// the run passes through are then added in chunk order (fixed order -> bitwise reproducible), every lane streaming its
+// own columns with independent loads.  Zipf-distributed ids put ~7 % of all tokens on the hottest row: that run spans
+// hundreds of chunks, which a chunk-by-chunk read-modify-write of dW walked at one memory round trip per chunk.
 __global__ void __launch_bounds__(256)
 seg_fixup_kernel(const uint32_t* __restrict__ keys, int64_t n_tokens, int64_t V, int E,
                  float* __restrict__ dW, const float* __restrict__ carry) {
@@ -315,12 +397,33 @@ seg_fixup_kernel(const uint32_t* __restrict__ keys, int64_t n_tokens, int64_t V,
   if (key >= (uint32_t)V || keys[p1] != key) return;      // last run ends here
   // the run must have started in this chunk, otherwise an earlier chunk owns the fix-up
   if (keys[p0] == key && p0 > 0 && keys[p0 - 1] == key) return;
-  for (int64_t c = chunk + 1; c * kSegChunk < n_tokens; ++c) {
-    const int64_t q0 = c * kSegChunk;
-    if (keys[q0] != key) break;
-    for (int e = lane; e < E; e += 32) dW[(int64_t)key * E + e] += carry[c * E + e];
-    const int64_t q1 = (q0 + kSegChunk < n_tokens) ? q0 + kSegChunk : n_tokens;
-    if (keys[q1 - 1] != key) break;                       // run ended inside chunk c
+  int64_t lo = p1, hi = n_tokens;                         // first position in [p1, n) whose key differs (keys are sorted)
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] == key) lo = mid + 1; else hi = mid;
+  }
+  const int64_t c_last = (lo - 1) / kSegChunk;            // chunk holding the last token of the run
+  float* dst = dW + (int64_t)key * E;
+  for (int e0 = 0; e0 < E; e0 += 32 * 4) {                // 4 columns per lane per pass
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int e = e0 + lane + 32 * j; acc[j] = e < E ? dst[e] : 0.f; }
+    for (int64_t c = chunk + 1; c <= c_last; c += 4) {    // 4 chunks of carries in flight, added in chunk order
+      float v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = e0 + lane + 32 * j;
+          v[u][j] = (c + u <= c_last && e < E) ? __ldg(carry + (c + u) * E + e) : 0.f;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += v[u][j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int e = e0 + lane + 32 * j; if (e < E) dst[e] = acc[j]; }
   }
 }
 
@@ -437,7 +540,13 @@ static int embed_pool_bwd_t(const IdT* ids, const float* inv_len, const float* d
   count_launch(3);
   const int warps = 8;
   const unsigned grid = (unsigned)ceil_div(ceil_div(n, kSegChunk), warps);
-  seg_reduce_kernel<<<grid, warps * 32, 0, s>>>(keys, vals, inv_len, d_pooled, n, V, E, d_table, carry);
+  const bool vec = (E % 4 == 0) && E <= 512 && ((reinterpret_cast<uintptr_t>(d_pooled) | reinterpret_cast<uintptr_t>(d_table) |
+                                                  reinterpret_cast<uintptr_t>(carry)) & 15) == 0;
+  if (vec && E <= 128)      seg_reduce_vec_kernel<1><<<grid, warps * 32, 0, s>>>(keys, vals, inv_len, d_pooled, n, V, E, d_table, carry);
+  else if (vec && E <= 256) seg_reduce_vec_kernel<2><<<grid, warps * 32, 0, s>>>(keys, vals, inv_len, d_pooled, n, V, E, d_table, carry);
+  else if (vec && E <= 384) seg_reduce_vec_kernel<3><<<grid, warps * 32, 0, s>>>(keys, vals, inv_len, d_pooled, n, V, E, d_table, carry);
+  else if (vec)             seg_reduce_vec_kernel<4><<<grid, warps * 32, 0, s>>>(keys, vals, inv_len, d_pooled, n, V, E, d_table, carry);
+  else                      seg_reduce_kernel<<<grid, warps * 32, 0, s>>>(keys, vals, inv_len, d_pooled, n, V, E, d_table, carry);
   TT_LAUNCH_CHECK("seg_reduce_kernel");
   seg_fixup_kernel<<<grid, warps * 32, 0, s>>>(keys, n, V, E, d_table, carry);
   TT_LAUNCH_CHECK("seg_fixup_kernel");

@@ -450,6 +450,15 @@ static int dispatch_scan(const void* index, const float* queries, int64_t N, int
   return TT_OK;
 }
 
+// exact top-k over `per_query` raw 64-bit keys per query (zero keys are padding); used by the batched tensor-core scan
+int topk_merge_raw(const u64* cand, int64_t per_query, int nq, int k, int64_t id_offset, float* out_scores, int64_t* out_ids,
+                   cudaStream_t s) {
+  RawKeys src{cand, per_query};
+  merge_topk_kernel<RawKeys><<<nq, kMergeThreads, 0, s>>>(src, per_query, k, id_offset, out_scores, out_ids);
+  TT_LAUNCH_CHECK("merge_topk_kernel");
+  return TT_OK;
+}
+
 }  // namespace tt
 
 extern "C" {

@@ -358,6 +358,38 @@ def topk_scan(index: torch.Tensor, queries: torch.Tensor, k: int, cosine: bool =
     return scores, ids
 
 
+def topk_scan_batched_ok(index: torch.Tensor, k: int) -> bool:
+    """True when the batched tensor-core scan supports this index (bf16, H % 64 == 0, H <= 256) and k (<= 128)."""
+    return bool(index.dtype == torch.bfloat16 and index.dim() == 2 and _lib_().tt_topk_scan_batched_ok(index.shape[1], int(k)))
+
+
+def index_row_inv_norms(index: torch.Tensor) -> torch.Tensor:
+    """1 / max(|d_n|, 1e-8) for every row of a bf16 index (cosine scores in topk_scan_batched); compute once per index."""
+    _need_cuda(index)
+    out = torch.empty(index.shape[0], dtype=torch.float32, device=index.device)
+    check(_lib_().tt_index_row_inv_norms(_p(index), index.shape[0], index.shape[1], _p(out), _stream()), "tt_index_row_inv_norms")
+    return out
+
+
+def topk_scan_batched(index: torch.Tensor, queries: torch.Tensor, k: int, id_offset: int = 0,
+                      row_inv_norms: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """Batched scan on the tcgen05 tensor cores: bf16 index [N,H], fp32 queries [nq,H] -> (scores [nq,k], ids [nq,k]),
+    the index is read once per 128 queries.  row_inv_norms given: cosine scores, else raw dot products."""
+    _need_cuda(index, queries, row_inv_norms)
+    if index.dtype != torch.bfloat16 or not index.is_contiguous():
+        raise TypeError("topk_scan_batched needs a contiguous bfloat16 index")
+    queries = _f32(queries)
+    N, H = index.shape
+    nq = queries.shape[0]
+    scores = torch.empty(nq, k, dtype=torch.float32, device=index.device)
+    ids = torch.empty(nq, k, dtype=torch.int64, device=index.device)
+    if workspace is None:
+        workspace = _workspace(_lib_().tt_topk_scan_batched_workspace(N, H, nq), index.device)
+    check(_lib_().tt_topk_scan_batched(_p(index), _p(queries), N, H, nq, int(k), _p(row_inv_norms), int(id_offset), _p(scores),
+                                       _p(ids), _p(workspace), workspace.numel(), _stream()), "tt_topk_scan_batched")
+    return scores, ids
+
+
 def topk_scan_workspace_bytes(N: int, H: int, nq: int, k: int) -> int:
     return int(_lib_().tt_topk_scan_workspace(N, H, nq, k))
 

@@ -60,6 +60,7 @@ class TwoTowerSearch(BaseSearch):
         self.documents: Optional[Sequence[str]] = None
         self.row_offset = 0                                          # global id of local row 0
         self.num_documents = 0
+        self.batched_min_queries = 4                                 # search_batch: tensor-core scan from this batch size on
         self.model = self.model.to(self.device)
 
     # ------------------------------------------------------------------ indexing
@@ -103,7 +104,26 @@ class TwoTowerSearch(BaseSearch):
 
     # ------------------------------------------------------------------ search
     def _topk(self, q_emb: torch.Tensor, k: int):
-        if self.group is not None or ws_initialized():
+        sharded = self.group is not None or ws_initialized()
+        # batches on a bf16 index: ONE pass over the index per 128 queries on the tensor cores (tt_topk_scan_batched)
+        # instead of one pass per 2 queries; the shards' candidate lists are merged like the single-query ones
+        if (q_emb.shape[0] >= self.batched_min_queries and self.document_embeddings.is_cuda and
+                k <= self.document_embeddings.shape[0] and hasattr(self.kernels, "topk_scan_batched_ok") and
+                self.kernels.topk_scan_batched_ok(self.document_embeddings, k)):
+            inv = None
+            if self.cosine:
+                key = self.document_embeddings.data_ptr()
+                if getattr(self, "_inv_norms_key", None) != key:
+                    self._inv_norms = self.kernels.index_row_inv_norms(self.document_embeddings)
+                    self._inv_norms_key = key
+                inv = self._inv_norms
+            s, i = self.kernels.topk_scan_batched(self.document_embeddings, q_emb, k, id_offset=self.row_offset, row_inv_norms=inv)
+            if not sharded:
+                return s, i
+            all_s = parallel.all_gather_rows(s.unsqueeze(0), self.group)
+            all_i = parallel.all_gather_rows(i.unsqueeze(0), self.group)
+            return self.kernels.topk_merge(all_s, all_i)
+        if sharded:
             if self.document_embeddings.is_cuda and hasattr(parallel, "ShardedTopK"):
                 key = (k, q_emb.shape[0], self.document_embeddings.data_ptr())
                 cache = self.__dict__.setdefault("_sharded", {})
@@ -136,6 +156,11 @@ class TwoTowerSearch(BaseSearch):
     def save_index(self, filepath: str) -> None:
         if self.document_embeddings is None or self.documents is None:
             raise ValueError("No index to save. Call index_documents() first.")
+        if self.row_offset != 0 or self.document_embeddings.shape[0] != self.num_documents:
+            # the reference's pickle holds ONE matrix for ALL documents (two_tower.py:127-130); a rank of a row-sharded
+            # index owns only its rows, and every rank would write the same path
+            raise ValueError("save_index: this index is row-sharded across ranks; use save_index_raw(dir) per rank "
+                             "(it records the row range) or build the index on one rank")
         emb = self.document_embeddings
         emb = emb.float().cpu().numpy() if torch.is_tensor(emb) else emb
         with open(filepath, "wb") as f:

@@ -38,7 +38,7 @@ namespace tc {
 
 constexpr int CE_BM = 128;          // X rows per CTA (UMMA M)
 constexpr int CE_BN = 64;           // Y rows per tile (UMMA N of the S product, K of the O product)
-constexpr int CE_THREADS = 192;     // backward: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int CE_THREADS = 192;     // backward with 4 epilogue warps: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (EW = 8: 320 threads)
 constexpr int FWD_THREADS = 320;    // forward: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -368,10 +368,19 @@ struct BwdParams {
 // tcgen05.mma has N >= 128 (a 128x64x16 instruction was measured at the same ~66 cycles as 128x128x16).
 constexpr int BWD_BN = 128;
 
-template <bool COL>
+// EW = epilogue warps: 4 (one per TMEM lane quarter, a thread turns a whole 128-column S row into P) or 8 (two per quarter,
+// each taking a 64-column half of every tile, like the forward kernel).  With four warps the epilogue of the dD pass
+// (column lse read back from shared memory as broadcasts) takes longer than the two MMAs of a tile, so that pass -- and
+// with it the launch -- ran ~25 % behind the tensor pipe; the run-once tail (accumulator dump, normalise backward) is
+// also instruction-latency bound with one warp per scheduler.  Eight warps halve both.
+template <bool COL, int EW>
 __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtensorMap* tmY, const BwdParams& p,
                                             uint8_t* base) {
   constexpr int PASS = COL ? 1 : 0;
+  constexpr int NH = EW / 4;                                // warps per TMEM lane quarter
+  constexpr int CW = BWD_BN / NH;                           // S columns per epilogue thread
+  constexpr int HC = CW / 32;                               // 32-column register chunks per thread
+  constexpr int ETH = EW * 32;                              // epilogue threads
   const int64_t Bx = p.Bx[PASS], By = p.By[PASS], label_offset = p.label_offset[PASS];
   const int tiles_per_split = p.tiles_per_split[PASS];
   const float* __restrict__ lse = p.lse[PASS];
@@ -415,10 +424,10 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     tma_prefetch_desc(tmX); tma_prefetch_desc(tmY);
     mbar_init(x_bar, 1);
     for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 4);
-    mbar_init(p_full, 4); mbar_init(p_empty, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, EW);
+    mbar_init(p_full, EW); mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
-    mbar_init(x_ready, 4);
+    mbar_init(x_ready, EW);
     mbar_init(xfer_bar, 1);
     fence_barrier_init();
     if (fused && gridDim.y == 2) mbar_arrive_expect_tx(xfer_bar, (uint32_t)(64 * (H + 4) * 4));   // armed long before the peer sends
@@ -510,7 +519,9 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       __syncwarp();
     }
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, half = (warp - 2) >> 2;   // half: which CW-column slice of every S tile (0 when EW == 4)
+    const int col0 = half * CW;
+    const int tid_e = threadIdx.x - 64;                    // 0 .. ETH-1
     const int lrow = quarter * 32 + lane;                  // row inside the tile == TMEM lane
     const int64_t row = x0 + lrow;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -518,7 +529,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     const float row_lse = (!COL && row < Bx) ? lse[row] * kLog2e : 0.f;
     // X tile: shared memory (TMA, 128B swizzle) -> registers -> TMEM (the TS-mode A operand of every S product)
     mbar_wait(x_bar, 0);
-    for (int kb = 0; kb < kq; ++kb) {
+    for (int kb = half; kb < kq; kb += NH) {
       uint32_t xr[32];
       const uint8_t* xrow = x_tile + kb * (CE_BM * 128) + lrow * 128;
 #pragma unroll
@@ -535,26 +546,26 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     TT_CTA_STAMP(1);
     // Y tiles that can hold a positive of one of this CTA's rows (CTA-uniform band)
     const int64_t band_lo = COL ? x0 - label_offset : x0 + label_offset;
-    auto load_col_lse = [&](int i) {                        // this thread's column of Y tile i (COL mode)
-      const int64_t gc = (int64_t)(t_beg + i) * BWD_BN + threadIdx.x - 64;
-      return (i < nt && gc < By) ? __ldg(lse + gc) * kLog2e : CUDART_INF_F;
+    auto load_col_lse = [&](int i) {                        // this thread's column of Y tile i (COL mode; first 128 threads)
+      const int64_t gc = (int64_t)(t_beg + i) * BWD_BN + tid_e;
+      return (tid_e < BWD_BN && i < nt && gc < By) ? __ldg(lse + gc) * kLog2e : CUDART_INF_F;
     };
     float next_cl = COL ? load_col_lse(0) : 0.f;
     for (int i = 0; i < nt; ++i) {
       const int64_t y0 = (int64_t)(t_beg + i) * BWD_BN;
       const float4* cl4 = reinterpret_cast<const float4*>(col_lse + (i & 1) * BWD_BN);
       if (COL) {                                            // column lse -> smem; read back as broadcasts
-        col_lse[(i & 1) * BWD_BN + threadIdx.x - 64] = next_cl;
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+        if (tid_e < BWD_BN) col_lse[(i & 1) * BWD_BN + tid_e] = next_cl;
+        asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");   // the epilogue warps only
         next_cl = load_col_lse(i + 1);                      // latency hides behind this tile's work
       }
       if (threadIdx.x == 64) TT_STAMP(1, i, 0);
       mbar_wait(s_full, i & 1);
       if (threadIdx.x == 64) TT_STAMP(1, i, 1);
       tc_fence_after();
-      uint32_t r[4][32];
+      uint32_t r[HC][32];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) tmem_ld_x32(tmem_s + lane_addr + 32 * h, r[h]);
+      for (int h = 0; h < HC; ++h) tmem_ld_x32(tmem_s + lane_addr + (uint32_t)(col0 + 32 * h), r[h]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -562,11 +573,11 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       if (threadIdx.x == 64) TT_STAMP(1, i, 2);
       // P = exp2(S*c - lse*log2e) (ragged columns: lse = +inf in COL mode, masked below otherwise), in place
 #pragma unroll
-      for (int h = 0; h < 4; ++h)
+      for (int h = 0; h < HC; ++h)
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 lv = make_float4(row_lse, row_lse, row_lse, row_lse);
-          if (COL) lv = cl4[(32 * h + j) >> 2];
+          if (COL) lv = cl4[(col0 + 32 * h + j) >> 2];
           r[h][j + 0] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 0]), c, -lv.x)));
           r[h][j + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 1]), c, -lv.y)));
           r[h][j + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 2]), c, -lv.z)));
@@ -574,16 +585,16 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         }
       if (!COL && y0 + BWD_BN > By) {
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
+        for (int h = 0; h < HC; ++h)
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (y0 + 32 * h + j >= By) r[h][j] = 0u;
+            if (y0 + col0 + 32 * h + j >= By) r[h][j] = 0u;
       }
       if (y0 + BWD_BN > band_lo && y0 < band_lo + CE_BM) {  // tile intersects the diagonal band
-        const int64_t pj = (COL ? row - label_offset : row + label_offset) - y0;
-        if (pj >= 0 && pj < BWD_BN && y0 + pj < By) {
+        const int64_t pj = (COL ? row - label_offset : row + label_offset) - y0 - col0;   // inside this thread's slice?
+        if (pj >= 0 && pj < CW && y0 + col0 + pj < By) {
 #pragma unroll
-          for (int h = 0; h < 4; ++h)
+          for (int h = 0; h < HC; ++h)
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               r[h][j] = __float_as_uint(__uint_as_float(r[h][j]) - ((32 * h + j == (int)pj) ? 1.0f : 0.0f));
@@ -593,13 +604,13 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       mbar_wait(p_empty, (i & 1) ^ 1);                     // O(i-1) has finished reading the P tile
       if (threadIdx.x == 64) TT_STAMP(1, i, 4);
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {                     // 16 x 16-byte chunks: k-block ch/8, 128B swizzle inside
-        const int h = ch >> 2, j0 = (ch & 3) * 8;
+      for (int ch = 0; ch < CW / 8; ++ch) {                 // 16-byte chunks of this thread's slice: k-block gch/8, 128B swizzle inside
+        const int h = ch >> 2, j0 = (ch & 3) * 8, gch = col0 / 8 + ch;
         const uint4 v = make_uint4(pack_bf16x2(__uint_as_float(r[h][j0 + 0]), __uint_as_float(r[h][j0 + 1])),
                                    pack_bf16x2(__uint_as_float(r[h][j0 + 2]), __uint_as_float(r[h][j0 + 3])),
                                    pack_bf16x2(__uint_as_float(r[h][j0 + 4]), __uint_as_float(r[h][j0 + 5])),
                                    pack_bf16x2(__uint_as_float(r[h][j0 + 6]), __uint_as_float(r[h][j0 + 7])));
-        *reinterpret_cast<uint4*>(p_tile + (ch >> 3) * (CE_BM * 128) + lrow * 128 + (((ch & 7) ^ (lrow & 7)) << 4)) = v;
+        *reinterpret_cast<uint4*>(p_tile + (gch >> 3) * (CE_BM * 128) + lrow * 128 + (((gch & 7) ^ (lrow & 7)) << 4)) = v;
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -613,11 +624,11 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       tc_fence_after();
     }
     TT_CTA_STAMP(2);
-    float* T = reinterpret_cast<float*>(p_tile + (warp - 2) * (32 * 36 * 4));       // [32][36], the P tile is free now
+    float* T = reinterpret_cast<float*>(y_tiles + (warp - 2) * (32 * 36 * 4));      // [32][36] per warp; the Y stages are idle now
     const int64_t row0 = x0 + quarter * 32;
     const int nrows = (int)min((int64_t)32, Bx - row0);
     float* orow = out + row0 * H + lane;
-    for (int cb = 0; cb < (fused ? 0 : H / 32); ++cb) {
+    for (int cb = half; cb < (fused ? 0 : H / 32); cb += NH) {
       uint32_t q[32];
       if (nt > 0) {
         tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
@@ -660,16 +671,16 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     float* own = reinterpret_cast<float*>(y_tiles);        // [nfin][RS]
     float* recv = own + nfin * RS;                         // [64][RS]  pair only: filled by the peer
     float* send = recv + 64 * RS;                          // [64][RS]  pair only: rows the peer finishes
-    float* cs_s = pair ? send + 64 * RS : own + nfin * RS; // [4][H] column partials
+    float* cs_s = pair ? send + 64 * RS : own + nfin * RS; // [EW][H] column partials
     if (pair) cluster_sync_all();                          // both CTAs' tensor pipes have retired: every Y stage is free
     TT_CTA_STAMP(4);
     if (warp >= 2) {
-      const int quarter = warp & 3;
+      const int quarter = warp & 3, half = (warp - 2) >> 2;
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
       const int lrow = quarter * 32 + lane;
       const bool mine = !pair || (quarter >> 1) == (int)rank;
       float* dst_row = mine ? own + (lrow - fin0) * RS : send + (lrow & 63) * RS;
-      for (int cb = 0; cb < H / 32; ++cb) {
+      for (int cb = half; cb < H / 32; cb += NH) {             // the warps of a quarter share its 32 rows, alternating column chunks
         uint32_t q[32];
         if (nt > 0) {
           tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
@@ -683,10 +694,11 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
           *reinterpret_cast<float4*>(dst_row + cb * 32 + j) = make_float4(__uint_as_float(q[j]), __uint_as_float(q[j + 1]),
                                                                           __uint_as_float(q[j + 2]), __uint_as_float(q[j + 3]));
       }
-      if (!mine) {                                         // this warp's 32 rows -> the same rows of the peer's recv buffer
+      if (!mine) {                                         // this quarter's 32 rows -> the same rows of the peer's recv buffer
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
+        if (NH == 2) asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");   // both warps of the quarter have dumped
+        else __syncwarp();
+        if (lane == 0 && half == 0) {
           const int r32 = (quarter & 1) * 32;
           dsmem_bulk_copy(mapa_shared(smem_u32(recv + r32 * RS), rank ^ 1u), send + r32 * RS, (uint32_t)(32 * RS * 4),
                           mapa_shared(smem_u32(xfer_bar), rank ^ 1u));
@@ -695,7 +707,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     }
     TT_CTA_STAMP(5);
     const int e = warp - 2;
-    const int rpw = nfin / 4;                              // rows per warp: 16 (pair) or 32
+    const int rpw = nfin / EW;                             // rows per warp: 64 or 128 rows over EW warps (8 .. 32)
     const int steps = (H + 127) / 128;                     // lane -> columns step * 128 + 4 * lane .. + 3
     const int64_t g0 = x0 + fin0 + e * rpw;                // first global row of this warp
     const __nv_bfloat16* xg = p.xg[PASS];
@@ -711,7 +723,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         for (int st = 0; st < 2; ++st) {
           const int c = st * 128 + lane * 4;
           ywa[u][st] = make_uint2(0u, 0u);
-          if (st < steps && c < H && grow < Bx) ywa[u][st] = __ldg(reinterpret_cast<const uint2*>(xg + grow * H + c));
+          if (rbase + u < rpw && st < steps && c < H && grow < Bx) ywa[u][st] = __ldg(reinterpret_cast<const uint2*>(xg + grow * H + c));
         }
       }
     };
@@ -799,17 +811,18 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         const int c = st * 128 + lane * 4;
         if (st < steps && c < H) *reinterpret_cast<float4*>(cs_s + e * H + c) = cs[st];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const bool writer = rpw == 32 || (e & 1) == 0;
-      const int64_t blk_row = x0 + fin0 + (rpw == 32 ? e * 32 : (e >> 1) * 32);
+      asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
+      const int wpb = 32 / rpw;                              // warps that share one 32-row block of column sums (1, 2 or 4)
+      const bool writer = (e % wpb) == 0;
+      const int64_t blk_row = x0 + fin0 + (e / wpb) * 32;
       if (writer && blk_row < Bx) {
 #pragma unroll
         for (int st = 0; st < 2; ++st) {
           const int c = st * 128 + lane * 4;
           if (st < steps && c < H) {
             float4 v = cs[st];
-            if (rpw == 16) {
-              const float4 t = *reinterpret_cast<const float4*>(cs_s + (e + 1) * H + c);
+            for (int w2 = 1; w2 < wpb; ++w2) {                 // fixed order: this warp's rows, then the following warps'
+              const float4 t = *reinterpret_cast<const float4*>(cs_s + (e + w2) * H + c);
               v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
             *reinterpret_cast<float4*>(p.dz_colsum[PASS] + (blk_row >> 5) * H + c) = v;
@@ -825,7 +838,8 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-__global__ void __launch_bounds__(CE_THREADS, 1)
+template <int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmY0,
                  const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmY1, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -833,8 +847,8 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
   const int pass = blockIdx.z;
   if ((int64_t)blockIdx.x * CE_BM >= p.Bx[pass] || (p.out[pass] == nullptr && p.dz[pass] == nullptr)) return;   // cluster-uniform: nothing to do for this pass
-  if (pass == 0) ce_bwd_body<false>(&tmX0, &tmY0, p, base);
-  else           ce_bwd_body<true>(&tmX1, &tmY1, p, base);
+  if (pass == 0) ce_bwd_body<false, EW>(&tmX0, &tmY0, p, base);
+  else           ce_bwd_body<true, EW>(&tmX1, &tmY1, p, base);
 }
 
 static size_t fwd_smem(int H) {
@@ -1014,7 +1028,10 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
   }
   p.H = H; p.inv_temp = inv_temp; p.grad_out = grad_out; p.coef = coef;
   const size_t smem = tc::bwd_smem(H);
-  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // epilogue warps: 8 by default (two per TMEM lane quarter); TT_CE_EW=4 selects the one-warp-per-quarter variant
+  static const int ew = [] { const char* e = getenv("TT_CE_EW"); return (e && atoi(e) == 4) ? 4 : 8; }();
+  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
   long long* dbg_dev = nullptr;
   const int64_t x0 = (pq.out || pq.dz) ? ceil_div(pq.Bx, tc::CE_BM) : 0, x1 = (pd.out || pd.dz) ? ceil_div(pd.Bx, tc::CE_BM) : 0;
@@ -1023,8 +1040,12 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
   const size_t ncta = (size_t)grid.x * grid.y * grid.z, dbg_n = 2 * 64 * 8 + 8 * ncta;
   if (dbg_on) { p.dbg_pass = atoi(getenv("TT_CE_DEBUG")) == 1 ? 1 : 0; cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p.dbg = dbg_dev; }
   // fused + 2 splits: the two CTAs of a row tile form a cluster and exchange accumulator halves through shared memory
-  TT_CUDA(launch_kernel_cluster(tc::tc_ce_bwd_kernel, grid, dim3(tc::CE_THREADS), smem, s, true, (fused && nsplit == 2) ? 2u : 1u,
-                                tmX0, tmY0, tmX1, tmY1, p));
+  if (ew == 8)
+    TT_CUDA(launch_kernel_cluster(tc::tc_ce_bwd_kernel<8>, grid, dim3(64 + 8 * 32), smem, s, true, (fused && nsplit == 2) ? 2u : 1u,
+                                  tmX0, tmY0, tmX1, tmY1, p));
+  else
+    TT_CUDA(launch_kernel_cluster(tc::tc_ce_bwd_kernel<4>, grid, dim3(tc::CE_THREADS), smem, s, true, (fused && nsplit == 2) ? 2u : 1u,
+                                  tmX0, tmY0, tmX1, tmY1, p));
   TT_LAUNCH_CHECK("tc_ce_bwd_kernel");
   if (dbg_on) {                                              // developer aid: per-tile timeline of CTA (0,0,0)
     std::vector<long long> hostv(dbg_n);

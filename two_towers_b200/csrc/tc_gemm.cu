@@ -560,18 +560,27 @@ l2norm_fwd_bf16_kernel(const float* __restrict__ z, int64_t R, int H, float* __r
 // Two small fp32 products.  A block owns an 8-row x 64-column output tile; K is walked in chunks of 128 staged in
 // shared memory with wide coalesced loads (one memory round trip per chunk), each thread accumulating two adjacent
 // columns in ascending-k order (bitwise reproducible).
+// M may arrive as `mparts` split-K slices (mstride elements apart): they are summed in slice order while the A chunk
+// is staged, so no separate reduction of M is needed.  The launch also carries the step's remaining split reductions
+// (dW2 partials, bias-gradient column sums): blocks [0, red_units) run reduce_parts_block, the rest the two products --
+// both depend only on the GEMMs before them, so one launch replaces reduce_parts_kernel + embed_finish_kernel.
 constexpr int kFinRows = 8, kFinCols = 64, kFinK = 128;
 __global__ void __launch_bounds__(256)
-embed_finish_kernel(const float* __restrict__ M, const float* __restrict__ table, const float* __restrict__ w1, int V,
-                    int H, int E, float* __restrict__ dw1, float* __restrict__ d_table, int accumulate) {
+embed_finish_kernel(const ReduceJobs jobs, int red_units, int fin_x,
+                    const float* __restrict__ M, int mparts, int64_t mstride, const float* __restrict__ table,
+                    const float* __restrict__ w1, int V, int H, int E, float* __restrict__ dw1, float* __restrict__ d_table,
+                    int accumulate) {
   __shared__ __align__(16) float As[kFinK][kFinRows];
   __shared__ __align__(16) float Bs[kFinK][kFinCols];
   pdl_trigger();
   pdl_wait();
+  if ((int)blockIdx.x < red_units) { reduce_parts_block(jobs, (int)blockIdx.x); return; }
+  const int fb = (int)blockIdx.x - red_units;
+  const int bx = fb % fin_x, by = fb / fin_x;
   const int tiles1 = (H + kFinRows - 1) / kFinRows;       // dw1 row tiles come first, then d_table row tiles
-  const bool second = (int)blockIdx.x >= tiles1;
-  const int r0 = (second ? (int)blockIdx.x - tiles1 : (int)blockIdx.x) * kFinRows;
-  const int c0 = blockIdx.y * kFinCols;
+  const bool second = bx >= tiles1;
+  const int r0 = (second ? bx - tiles1 : bx) * kFinRows;
+  const int c0 = by * kFinCols;
   const int rows = second ? V : H, K = second ? H : V;
   const float* B = second ? w1 : table;                   // [K, E]
   const int tr = threadIdx.x >> 5, tc2 = (threadIdx.x & 31) * 2;
@@ -583,7 +592,16 @@ embed_finish_kernel(const float* __restrict__ M, const float* __restrict__ table
       int k, r;
       if (second) { r = i / kFinK; k = i % kFinK; } else { k = i / kFinRows; r = i % kFinRows; }
       float v = 0.f;
-      if (k < kc && r0 + r < rows) v = second ? __ldg(M + (size_t)(r0 + r) * H + k0 + k) : __ldg(M + (size_t)(k0 + k) * H + r0 + r);
+      if (k < kc && r0 + r < rows) {
+        const float* mp = second ? M + (size_t)(r0 + r) * H + k0 + k : M + (size_t)(k0 + k) * H + r0 + r;
+        for (int pz = 0; pz < mparts; pz += 8) {           // slice order (bitwise reproducible), 8 independent loads in flight
+          float t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = (pz + u < mparts) ? __ldg(mp + (size_t)(pz + u) * mstride) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v += t[u];
+        }
+      }
       As[k][r] = v;
     }
     for (int i = threadIdx.x; i < kFinK * (kFinCols / 4); i += 256) {
@@ -884,16 +902,18 @@ int tc_mlp_bwd(const float* dy, const float* x, const float* w1, const float* w2
     gm.M = V; gm.N = H; gm.K = (int)R; gm.A = (const __nv_bfloat16*)embed->pool_bf16; gm.a_mn = 1; gm.B = da1b; gm.b_mn = 1;
     gm.C = Mbuf; gm.ldc = H; gm.splits = sm; gm.partial = Mpart; gm.defer_reduce = true;
     rc = tc::tc_gemm(gm, s); if (rc) return rc;
+    // ONE launch finishes the call: the remaining split reductions (dW2, db1, db2; fixed order) and the two small
+    // products of the embedding-fused backward, which read M's split-K slices directly
     ReduceJobs jobs{};
     int nj = 0;
     if (plan.s_dw2 > 1) jobs.job[nj++] = make_job(partial, plan.s_dw2, (int64_t)H * H, (int64_t)H * H, dw2);
-    if (sm > 1) jobs.job[nj++] = make_job(Mpart, sm, (int64_t)V * H, (int64_t)V * H, Mbuf);
     jobs.job[nj++] = make_job(cs1, (int)ceil_div(R, 32), H, H, db1);
     if (fused_cs) jobs.job[nj++] = make_job(cs2, nblk2, H, H, db2);
     jobs.njobs = nj;
-    rc = reduce_parts(jobs, s); if (rc) return rc;
-    const dim3 fgrid((unsigned)(ceil_div(H, tc::kFinRows) + ceil_div(V, tc::kFinRows)), (unsigned)ceil_div(E, tc::kFinCols));
-    TT_CUDA(launch_kernel(tc::embed_finish_kernel, fgrid, dim3(256), 0, s, true, (const float*)Mbuf, embed->table, w1,
+    const int red_units = plan_reduce(jobs);
+    const int fin_x = (int)(ceil_div(H, tc::kFinRows) + ceil_div(V, tc::kFinRows)), fin_y = (int)ceil_div(E, tc::kFinCols);
+    TT_CUDA(launch_kernel(tc::embed_finish_kernel, dim3((unsigned)(red_units + fin_x * fin_y)), dim3(256), 0, s, true, jobs, red_units, fin_x,
+                          (const float*)(sm > 1 ? Mpart : Mbuf), sm > 1 ? sm : 1, (int64_t)V * H, embed->table, w1,
                           V, H, E, dw1, embed->d_table, embed->accumulate));
     TT_LAUNCH_CHECK("embed_finish_kernel");
     return TT_OK;

@@ -607,7 +607,7 @@ def bench_search(args, dev, rank, world, pg):
                                        "frac": ach / pk["hbm"], "traffic": traffic, "traffic_source": src,
                                        "bytes_per_query_per_gpu": bytes_per_query, "peak_source": pk["src"]}}
         # batched mode (nq in {16, 64, 256}): one pass over the index serves the whole batch
-        if world == 1 and hasattr(tt.ops, "topk_scan_batched"):
+        if world == 1 and idx_dtype == "bf16" and hasattr(tt.ops, "topk_scan_batched") and tt.ops.topk_scan_batched_ok(index, k):
             bt = {}
             for nq in (16, 64, 256):
                 qb = qs[:nq].contiguous()

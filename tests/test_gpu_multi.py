@@ -76,7 +76,10 @@ def _trainer_vs_oracle(rank, world, dev, log):
         if not tied:
             got_d = tower_grads(model.document_tower)
             for k in ("w1", "b1", "w2", "b2"):
-                check(got_d[k], rgd[k], tol, f"grad document/{k}", log)
+                # in-batch, untied: db2 of the document tower is a cancellation residue (sum_j dL/dd_j = 0), see
+                # tests/test_gpu_tensor_core.py::test_fused_trainer_bf16_tracks_fp32
+                kt = 5e-2 if (k == "b2" and loss == "in_batch" and prec == "bf16") else tol
+                check(got_d[k], rgd[k], kt, f"grad document/{k}", log)
         both = _gather_np(tr.flat.double().sum().reshape(1), world)
         assert both[0] == both[1]                             # identical parameters on every rank after the step
         del tr, model

@@ -337,9 +337,13 @@ def test_fused_trainer_bf16_tracks_fp32(B, tied, id_dtype, E, H):
     for k in gq:
         check(got_q[k], gq[k], BF16_RTOL, f"grad query/{k}")
     if not tied:
+        # The softmax rows sum to one, so sum_j dL/dd_j = sum_i q_i (sum_j P_ij - 1) / (tau B) = 0 IDENTICALLY: the bias
+        # gradient of an untied document tower (the column sum of its dz rows) is a pure cancellation residue, and the
+        # bf16 rounding of P (row sums off by ~2^-9) shows up in it at 2-3 % although every row of dz holds 2e-2
+        # (test_inbatch_bwd_fused_normalise) -- db2 of the document tower is bounded at 5e-2 for that reason.
         got_d = tower_grads(m16.document_tower)
         for k in ("w1", "b1", "w2", "b2"):
-            check(got_d[k], gd[k], BF16_RTOL, f"grad document/{k}")
+            check(got_d[k], gd[k], 5e-2 if k == "b2" else BF16_RTOL, f"grad document/{k}")
     first = l16
     for _ in range(30):
         last = t16.step(q, d).item()

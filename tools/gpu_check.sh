@@ -5,8 +5,12 @@ cd "$(dirname "$0")/.."
 TAG=${1:-check}; shift
 O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader > $O/${TAG}_gpu.txt 2>&1
-timeout 1200 python -m pytest tests -m gpu -q -s --maxfail=40 "$@" > $O/${TAG}_pytest.log 2>&1; echo "pytest exit $?" | tee -a $O/${TAG}_pytest.log
-grep -E "passed|failed|error" $O/${TAG}_pytest.log | tail -3
+# one pytest process per file: a kernel fault (sticky CUDA error) in one file cannot poison the others
+: > $O/${TAG}_pytest.log
+for f in tests/test_gpu_parity.py tests/test_gpu_tensor_core.py tests/test_gpu_round2.py tests/test_plumbing.py tests/test_gpu_multi.py; do
+  timeout 900 python -m pytest $f -m gpu -q -s --maxfail=40 "$@" >> $O/${TAG}_pytest.log 2>&1; echo "pytest $f exit $?" | tee -a $O/${TAG}_pytest.log
+done
+grep -E "^FAILED|passed|failed|error" $O/${TAG}_pytest.log | tail -30 | cut -c1-200
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -2 $O/${TAG}_smoke.log
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench exit $?"; tail -3 $O/${TAG}_bench.err | cut -c1-300
 timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > $O/${TAG}_bench_ref.json 2>> $O/${TAG}_bench.err; echo "ref exit $?"

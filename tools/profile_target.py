@@ -17,7 +17,7 @@ import two_towers_b200 as tt
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="train", choices=["train", "search"])
+    ap.add_argument("--what", default="train", choices=["train", "search", "word", "search_batched", "msmarco"])
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--dtype", default="fp32")
     ap.add_argument("--rows", type=int, default=10_000_000)
@@ -37,6 +37,38 @@ def main():
             loss = tr.step(q, d)
         torch.cuda.synchronize()
         print("train ok, loss", loss.item(), "launches/step", tr.kernels_per_step())
+    elif a.what in ("word", "msmarco"):
+        # configs[2] (word tower: V = 400k, E = 300, L = 32, trainable table, in-batch) / configs[3] (untied, H = 128)
+        import bench
+        if a.what == "word":
+            c = bench.WORD
+            emb = tt.embeddings.build("lookup", c["V"], embedding_dim=c["E"])
+            model = tt.build_two_tower("mean", emb, hidden_dim=c["H"], tied_weights=True).to(dev)
+            q, d = bench.zipf_ids(c["B"], c["L"], c["V"], 1).to(dev), bench.zipf_ids(c["B"], c["L"], c["V"], 2).to(dev)
+        else:
+            c = bench.MSM
+            emb = tt.embeddings.build("lookup", c["V"], embedding_dim=c["E"])
+            model = tt.build_two_tower("mean", emb, hidden_dim=c["H"], tied_weights=False).to(dev)
+            q, d = (bench.repeated_ids(c["B"], c["L"], c["V"], s_, c["repeat"]).to(dev) for s_ in (1, 2))
+        tr = tt.FusedTrainer(model, loss="in_batch", batch_size=c["B"], max_len=c["L"], precision=a.precision,
+                             use_cuda_graph=False, id_dtype=torch.int32)
+        for _ in range(a.iters):
+            loss = tr.step(q, d)
+        torch.cuda.synchronize()
+        print(a.what, "ok, loss", loss.item(), "launches/step", tr.kernels_per_step())
+    elif a.what == "search_batched":
+        N, H = a.rows, 256
+        D = torch.empty(N, H, device=dev)
+        for s in range(0, N, 1_000_000):
+            e = min(N, s + 1_000_000)
+            D[s:e] = torch.nn.functional.normalize(torch.randn(e - s, H, device=dev), dim=-1)
+        idx = tt.ops.cast_bf16(D)
+        del D
+        q = torch.nn.functional.normalize(torch.randn(64, H, device=dev), dim=-1)
+        for _ in range(a.iters):
+            s, i = tt.ops.topk_scan_batched(idx, q, 100)
+        torch.cuda.synchronize()
+        print("batched search ok, best", s[0, 0].item(), i[0, 0].item())
     else:
         N, H = a.rows, 256
         D = torch.empty(N, H, device=dev)

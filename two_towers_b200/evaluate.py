@@ -73,10 +73,17 @@ def rank_candidates(model, tokenizer, query: str, documents: Sequence[str], max_
     if n <= ops.TT_TOPK_MAX:
         _, order = ops.topk_scan(d.contiguous(), q.contiguous(), n, cosine=True)       # exact full ranking on the device
         return order[0].cpu().numpy()
-    # candidate lists longer than the kernel's k limit: scores from the scan kernel's dot product are not exposed, so
-    # rank with a device sort of the cosine scores (stable -> lower index first on ties)
-    s = torch.nn.functional.cosine_similarity(q, d, dim=1)
-    return torch.sort(s, descending=True, stable=True).indices.cpu().numpy()
+    # candidate lists longer than the kernel's k limit: exact full ranking of every block of TT_TOPK_MAX candidates on the
+    # device (scores + ids from the scan kernel), then one host merge of the sorted blocks by (score desc, index asc) --
+    # no eager-PyTorch scoring path
+    d = d.contiguous()
+    ss, ii = [], []
+    for lo in range(0, n, ops.TT_TOPK_MAX):
+        hi = min(n, lo + ops.TT_TOPK_MAX)
+        s_blk, i_blk = ops.topk_scan(d[lo:hi], q.contiguous(), hi - lo, cosine=True, id_offset=lo)
+        ss.append(s_blk[0]); ii.append(i_blk[0])
+    s_all, i_all = torch.cat(ss).cpu().numpy(), torch.cat(ii).cpu().numpy()
+    return i_all[np.lexsort((i_all, -s_all.astype(np.float64)))]
 
 
 def evaluate_model(model, test_data: List[Tuple[str, List[str], List[int]]], tokenizer,

@@ -288,15 +288,27 @@ def test_fused_trainer_checkpoint_resume_and_external_loads():
 def test_msmarco_shape_repeated_positives_and_multiple_negatives():
     """configs/msmarco_gpu.yml:24-31 (untied mean towers, E = 64, H = 128) on a batch where every positive appears 4 times
     (presets/multi_pos_multi_neg.yml:12 negatives_per_pos: 4 -> duplicated (q, d+) rows; the reference applies no
-    false-negative masking): in-batch step vs the fp64 oracle, and multiple_negatives_loss with N = 4 (losses.py:47-85)."""
+    false-negative masking): in-batch step vs the fp64 oracle, and multiple_negatives_loss with N = 4 (losses.py:47-85).
+
+    Conditioning.  With 64 random characters per row every mean-pooled input -- hence every hidden activation h1_r -- is
+    nearly the same vector at initialisation, and sum_r dz_r = 0 for a uniform softmax, so the weight gradients
+    dW = sum_r dz_r (x) h1_r are small residues of cancelling terms: the bf16 rounding of the GEMM operands (2^-9 per
+    element, the definition of TT_PREC_BF16) is amplified by |h_mean| / |h_r - h_mean| and reaches 2-6 % there (measured,
+    gpurun_out r02c; the oracle on bf16-rounded tower outputs alone moves the gradients by only 0.4 %).  Rows of 1-6
+    tokens keep the activations apart; on them every gradient holds the stated 2e-2 (document-tower db2: see
+    test_fused_trainer_bf16_tracks_fp32)."""
     import two_towers_b200 as tt
     torch.manual_seed(0)
     V, E, H, B, L = 128, 64, 128, 1024, 64
     emb = tt.embeddings.build("lookup", V, embedding_dim=E)
     model = tt.build_two_tower("mean", emb, hidden_dim=H, tied_weights=False).to(DEV)
     g = torch.Generator().manual_seed(2)
-    q = torch.randint(0, V, (B // 4, L), generator=g).repeat_interleave(4, 0)
-    d = torch.randint(0, V, (B // 4, L), generator=g).repeat_interleave(4, 0)
+
+    def ids():
+        x = torch.randint(1, V, (B // 4, L), generator=g)
+        lens = torch.randint(1, 7, (B // 4, 1), generator=g)
+        return torch.where(torch.arange(L)[None, :] < lens, x, torch.zeros_like(x)).repeat_interleave(4, 0)
+    q, d = ids(), ids()
     pq0, pd0 = tower_params(model.query_tower), tower_params(model.document_tower)
     tr = tt.FusedTrainer(model, loss="in_batch", temperature=0.1, batch_size=B, max_len=L, precision="bf16")
     assert tr.local_fast and not tr.tied
@@ -304,23 +316,11 @@ def test_msmarco_shape_repeated_positives_and_multiple_negatives():
     rl, gq, gd, flips = oracle_step(pq0, pd0, q.numpy(), d.numpy(), loss="in_batch", temperature=0.1, gates=trainer_gates(tr))
     print(f"  msmarco shape, 4x repeated positives, bf16: loss {got:.6f} oracle {rl:.6f} (>= log 4 = {np.log(4):.4f}), gates flipped {flips:.2%}")
     assert abs(got - rl) <= BF16_RTOL * abs(rl) and rl > np.log(4) - 1e-6 and flips < 0.01
-    # At initialisation every tower output is nearly the same unit vector and only 256 of the 1024 rows are distinct, so
-    # the loss gradient dq_i = (sum_j P_ij d_j - d_i) / (tau B) is the small difference of two nearly equal vectors: the
-    # bf16 rounding of the tower outputs (2^-9 relative, what TT_PREC_BF16 feeds the loss kernels BY DEFINITION) is
-    # amplified by that cancellation.  The kernels are therefore held to 2e-2 against the oracle evaluated on the same
-    # bf16-rounded outputs; against the unrounded oracle the measured error is printed and bounded by 5e-2.
-    _, gq_q, gd_q, _ = oracle_step(pq0, pd0, q.numpy(), d.numpy(), loss="in_batch", temperature=0.1, gates=trainer_gates(tr),
-                                   quantize_y=True)
     got_q, got_d = tower_grads(model.query_tower), tower_grads(model.document_tower)
-    # The same cancellation makes the sums over rows ill-conditioned as well (sum_j dL/dd_j = 0 identically; with 4 copies
-    # of every row the first-layer sums are residues of residues): measured 1-4 %, bounded at 5e-2; the kernels behind
-    # them hold 2e-2 per row (test_inbatch_bwd_fused_normalise, test_embed_fused_tower_backward).
     for k in gq:
-        check(got_q[k], gq_q[k], 5e-2, f"grad query/{k} (bf16 y)")
-        check(got_q[k], gq[k], 5e-2, f"grad query/{k} (exact y)")
+        check(got_q[k], gq[k], BF16_RTOL, f"grad query/{k}")
     for k in ("w1", "b1", "w2", "b2"):
-        check(got_d[k], gd_q[k], 5e-2, f"grad document/{k} (bf16 y)")
-        check(got_d[k], gd[k], 5e-2, f"grad document/{k} (exact y)")
+        check(got_d[k], gd[k], 5e-2 if k == "b2" else BF16_RTOL, f"grad document/{k}")
     # multiple negatives, N = 4, on tower outputs of that shape (fp32 row kernels), B = 4096
     rng = np.random.default_rng(1)
     Bm, N = 4096, 4

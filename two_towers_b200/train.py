@@ -147,15 +147,20 @@ class FusedTrainer:
                 if self.p2p_grad:
                     self.x_grad = parallel.P2PExchange(self.flat_grad.numel() * 4, self.group, self.dev, double_buffered=True)
                 if self.global_fast:
-                    self.x_y = parallel.P2PExchange(2 * B * self.H * 2, self.group, self.dev)
+                    # documents and queries travel separately: the loss forward needs only D, so the Q exchange (needed by
+                    # the dD pass of the backward) runs on a side stream underneath the forward kernel
+                    self.x_d = parallel.P2PExchange(B * self.H * 2, self.group, self.dev)
+                    self.x_q = parallel.P2PExchange(B * self.H * 2, self.group, self.dev)
                     self.x_lse = parallel.P2PExchange(B * 4, self.group, self.dev)
+                    self._side = torch.cuda.Stream(device=self.dev)
             except RuntimeError as e:                       # raised on ALL ranks together (see P2PExchange): NCCL path
                 import warnings
                 warnings.warn(f"FusedTrainer: {e}; using NCCL collectives")
                 self.p2p = self.p2p_grad = False
         if self.p2p:
             if self.global_fast:
-                self.yg_bf16 = self.x_y.gathered(torch.bfloat16, (2 * B, self.H)).view(self.world * 2 * B, self.H)
+                self.dg_bf16 = self.x_d.gathered(torch.bfloat16, (B, self.H)).view(self.world * B, self.H)
+                self.qg_bf16 = self.x_q.gathered(torch.bfloat16, (B, self.H)).view(self.world * B, self.H)
                 self.lse_g = self.x_lse.gathered(torch.float32, (B,)).reshape(self.world * B) \
                     if (B * 4) % 256 == 0 else None
                 if self.lse_g is None or not self.lse_g.is_contiguous():
@@ -403,31 +408,42 @@ class FusedTrainer:
                   "tt_inbatch_ce_bwd")
 
     def _global_inbatch_fast(self, s, inv_t):
-        """Global in-batch negatives on the tensor-core path: 2 all-gathers (bf16 [Q|D], fp32 lse), the loss kernels
-        read the gathered buffer in place (block-interleaved rows), both gradients come from ONE launch as slices."""
+        """Global in-batch negatives on the tensor-core path.  Peer-memory exchanges: D on the main stream (the forward
+        needs nothing else), Q on a side stream underneath the forward kernel (only the backward's dD pass reads it), lse
+        after the forward; both gradients come from ONE launch.  NCCL fallback: one all-gather of the [Q_r | D_r] blocks,
+        which the loss kernels index in place (block-interleaved rows), and one of lse."""
         lib, B, H, W = self.lib, self.B, self.H, self.world
         Bg = B * W
+        vp = lambda t: None if t is None else t.data_ptr()
         if self.p2p:
-            self.x_y.allgather(self.y_bf16[:2 * B])
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)                    # tower outputs are ready
+            with torch.cuda.stream(self._side):
+                self.x_q.allgather(self.y_bf16[:B])         # consumed by the backward's dD pass only: hidden under the forward
+            self.x_d.allgather(self.y_bf16[B:2 * B])
+            d_all, d_rows, d_blk, d_stride, d_off = self.dg_bf16, Bg, Bg, 0, 0          # one contiguous [Bg, H] matrix each
+            q_all, q_off = self.qg_bf16, 0
         else:
             dist.all_gather_into_tensor(self.yg_bf16, self.y_bf16[:2 * B], group=self.group)
+            d_all, d_rows, d_blk, d_stride, d_off = self.yg_bf16, W * 2 * B, B, 2 * B, B  # [Q_r | D_r] blocks, indexed in place
+            q_all, q_off = self.yg_bf16, 0
         scale = 1.0 / Bg
-        check(lib.tt_inbatch_ce_fwd_ex(_p(self.y_bf16[:B]), B, _p(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, B, H, inv_t,
+        check(lib.tt_inbatch_ce_fwd_ex(_p(self.y_bf16[:B]), B, _p(d_all), Bg, d_rows, d_blk, d_stride, d_off, H, inv_t,
                                        self.rank * B, scale, _p(self.loss), _p(self.lse), _p(self.pos_mean),
                                        _p(self.ce_ws), self.ce_ws.numel(), _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
         if self.p2p:
             self.x_lse.allgather(self.lse)
             if self._lse_pack:
                 self.lse_g.view(W, B).copy_(self.x_lse.gathered(torch.float32, (B,)))
+            torch.cuda.current_stream().wait_stream(self._side)          # Q of every rank has arrived
         else:
             dist.all_gather_into_tensor(self.lse_g, self.lse, group=self.group)
-        vp = lambda t: None if t is None else t.data_ptr()
         nb = B // 32
         fz = (lambda a, b, c: (vp(a), vp(b), vp(c))) if self.ce_fused else (lambda a, b, c: (None, None, None))
-        qp = _lib.CePass(vp(self.y_bf16[:B]), B, vp(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, B, vp(self.lse), self.rank * B,
+        qp = _lib.CePass(vp(self.y_bf16[:B]), B, vp(d_all), Bg, d_rows, d_blk, d_stride, d_off, vp(self.lse), self.rank * B,
                          vp(self.dy[:B]), self.dy_part_stride,
                          *(fz(self.dz_bf16[:B], self.dz_colsum[:nb], self.inv_norm[:B]) if self.ce_fused else (None, None, None)))
-        dp = _lib.CePass(vp(self.y_bf16[B:2 * B]), B, vp(self.yg_bf16), Bg, W * 2 * B, B, 2 * B, 0, vp(self.lse_g),
+        dp = _lib.CePass(vp(self.y_bf16[B:2 * B]), B, vp(q_all), Bg, d_rows, d_blk, d_stride, q_off, vp(self.lse_g),
                          -self.rank * B, vp(self.dy[B:2 * B]), self.dy_part_stride,
                          *(fz(self.dz_bf16[B:2 * B], self.dz_colsum[nb:2 * nb], self.inv_norm[B:2 * B]) if self.ce_fused else (None, None, None)))
         check(lib.tt_inbatch_ce_bwd_parts_ex(C.byref(qp), C.byref(dp), H, inv_t, scale, None, self.dy_parts, s),
@@ -610,6 +626,6 @@ class FusedTrainer:
         or a peer-memory exchange that timed out (RuntimeError)."""
         torch.cuda.current_stream().synchronize()
         _lib.raise_on_bad_ids()
-        for x in (getattr(self, "x_grad", None), getattr(self, "x_y", None), getattr(self, "x_lse", None)):
+        for x in (getattr(self, "x_grad", None), getattr(self, "x_d", None), getattr(self, "x_q", None), getattr(self, "x_lse", None)):
             if x is not None:
                 x.check()

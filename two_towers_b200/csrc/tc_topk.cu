@@ -28,8 +28,8 @@ namespace tt {
 typedef unsigned long long u64;
 
 // shared with topk_scan.cu
-int topk_merge_raw(const u64* cand, int64_t per_query, int nq, int k, int64_t id_offset, float* out_scores, int64_t* out_ids,
-                   cudaStream_t s);
+int topk_merge_blocked(const u64* cand, int blocks, int cap, int nq, int k, int64_t id_offset, float* out_scores, int64_t* out_ids,
+                       cudaStream_t s);
 
 namespace tc {
 
@@ -37,7 +37,10 @@ constexpr int TK_BM = 128;            // queries per pass (UMMA M)
 constexpr int TK_BN = 128;            // documents per tile (UMMA N)
 constexpr int TK_STAGES = 3;
 constexpr int TK_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (one per TMEM lane quarter)
-constexpr int TK_CAP = 256;           // candidate keys per (query, CTA); k <= TK_CAP / 2
+constexpr int TK_CAP = 512;           // candidate keys per (query, CTA): a prune frees CAP - 32 - k slots, so the rows seen
+                                      // between two prunes grow by (CAP - 32) / k (4.8x at k = 100): ~4 prunes per query and CTA
+constexpr int TK_KMAX = 128;          // k <= TK_KMAX
+constexpr int TK_KPL = TK_CAP / 32;   // keys per lane while a buffer is selected in registers
 
 __device__ __forceinline__ uint32_t tk_score_bits(float f) {
   f += 0.0f;
@@ -51,19 +54,53 @@ __device__ __forceinline__ u64 tk_make_key(float score, uint32_t row) {
   return ((u64)tk_score_bits(score) << 32) | (u64)(0xffffffffu - row);
 }
 
-// descending bitonic sort of buf[0..n) (n power of two) by one warp
-__device__ __forceinline__ void tk_bitonic_desc(u64* buf, int n, int lane) {
-  for (int size = 2; size <= n; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = lane; i < (n >> 1); i += 32) {
-        const int pos = 2 * i - (i & (stride - 1));
-        const u64 a = buf[pos], b = buf[pos + stride];
-        const bool desc = (pos & size) == 0;
-        if ((a < b) == desc) { buf[pos] = b; buf[pos + stride] = a; }
-      }
-      __syncwarp();
+// Warp-cooperative exact selection: keep the k largest of the cnt (k <= cnt <= TK_CAP) unique keys in buf[0, cnt), in any
+// order, in buf[0, k); returns the k-th largest key.  The keys sit in registers (TK_KPL per lane); the k-th largest SCORE
+// (high word) is found by an MSB-first bisection with one warp-wide integer reduction per bit, and only if more keys tie
+// with it than fit is the low word (inverted row: larger = lower row) bisected as well.  ~0.5 us against ~6 us for a
+// bitonic sort of the buffer in shared memory.
+__device__ __forceinline__ u64 tk_select_topk(u64* buf, int cnt, int k, int lane) {
+  u64 kv[TK_KPL];
+#pragma unroll
+  for (int j = 0; j < TK_KPL; ++j) { const int i = lane + 32 * j; kv[j] = i < cnt ? buf[i] : 0ull; }
+  uint32_t hi = 0;                                         // largest value with count(score bits >= hi) >= k
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = hi | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < TK_KPL; ++j) c += ((uint32_t)(kv[j] >> 32) >= cand) ? 1 : 0;
+    if (__reduce_add_sync(0xffffffffu, c) >= k) hi = cand;
+  }
+  int gt = 0, ge = 0;
+#pragma unroll
+  for (int j = 0; j < TK_KPL; ++j) { const uint32_t h = (uint32_t)(kv[j] >> 32); gt += h > hi ? 1 : 0; ge += h >= hi ? 1 : 0; }
+  gt = __reduce_add_sync(0xffffffffu, gt);
+  ge = __reduce_add_sync(0xffffffffu, ge);
+  uint32_t lo = 0;                                         // ties at the k-th score: the k - gt largest low words among them
+  if (ge > k) {
+    const int need = k - gt;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = lo | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < TK_KPL; ++j) c += ((uint32_t)(kv[j] >> 32) == hi && (uint32_t)kv[j] >= cand) ? 1 : 0;
+      if (__reduce_add_sync(0xffffffffu, c) >= need) lo = cand;
     }
   }
+  const u64 kth = ((u64)hi << 32) | (u64)lo;
+  __syncwarp();                                            // every lane holds its keys in registers before buf is rewritten
+  int base = 0;
+#pragma unroll
+  for (int j = 0; j < TK_KPL; ++j) {
+    const bool keep = kv[j] >= kth;                        // zero padding: kth > 0 because cnt >= k real keys exist
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[base + __popc(m & ((1u << lane) - 1u))] = kv[j];
+    base += __popc(m);
+  }
+  __syncwarp();
+  return kth;
 }
 
 // fp32 queries [nq, H] -> bf16 hi / lo tiles [TK_BM, H] each (rows >= nq are zero) and, for cosine scores, 1 / max(|q|, 1e-8)
@@ -118,7 +155,6 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
   uint64_t* q_ready = s_empty + 2;                         // query tiles copied into TMEM (4 epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 1);
   float* dscale = reinterpret_cast<float*>(tmem_slot + 4);                  // [2][128]
-  u64* scratch = reinterpret_cast<u64*>(dscale + 2 * TK_BN);                // [4][TK_CAP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = ceil_div(N, TK_BN);
@@ -223,7 +259,6 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
     const bool cosine = dinv != nullptr;
     const float my_qinv = cosine ? qinv[lrow] : 1.0f;
     u64* gbuf = cand + ((size_t)lrow * gridDim.x + blockIdx.x) * TK_CAP;   // this query's candidate buffer for this CTA
-    u64* sc = scratch + ew * TK_CAP;
     int count = 0;
     // Rows of a CTA arrive in increasing order, so once the buffer has been pruned to its k best a later row that only
     // TIES the k-th score can never displace it (ties -> lower row): the test is strict, and identical scores (duplicate
@@ -237,16 +272,9 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
         mask &= mask - 1;
         const u64 gp = __shfl_sync(0xffffffffu, (u64)(uintptr_t)gbuf, L);
         const int cnt = __shfl_sync(0xffffffffu, count, L);
-        const u64* src = reinterpret_cast<const u64*>((uintptr_t)gp);
-        __syncwarp();
-        for (int i = lane; i < TK_CAP; i += 32) sc[i] = i < cnt ? src[i] : 0ull;
-        __syncwarp();
-        tk_bitonic_desc(sc, TK_CAP, lane);
-        u64* dst = reinterpret_cast<u64*>((uintptr_t)gp);
-        for (int i = lane; i < k; i += 32) dst[i] = sc[i];
-        const u64 kth = sc[k - 1];
-        __syncwarp();
-        if (lane == L && cnt >= k) { count = k; thr = tk_bits_score((uint32_t)(kth >> 32)); }
+        __syncwarp();                                        // lane L's appends are visible to the warp
+        const u64 kth = tk_select_topk(reinterpret_cast<u64*>((uintptr_t)gp), cnt, k, lane);
+        if (lane == L) { count = k; thr = tk_bits_score((uint32_t)(kth >> 32)); }
       }
     };
 
@@ -302,8 +330,11 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
         __syncwarp();
       }
     }
-    // leave every buffer zero-padded: the merge kernel ignores zero keys
-    for (int i = count; i < TK_CAP; ++i) gbuf[i] = 0ull;
+    // leave the k best of every live buffer in front (zero-padded when the CTA saw fewer than k rows): the merge kernel
+    // reads k keys per (query, CTA) and ignores zero keys
+    const unsigned over = __ballot_sync(0xffffffffu, count > k);
+    if (over) prune(over);
+    for (int i = count; i < k; ++i) gbuf[i] = 0ull;
   }
   tc_fence_before();
   __syncthreads();
@@ -311,12 +342,12 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
 }
 
 static size_t topk_smem(int H) {
-  return 1024 + TK_STAGES * (size_t)TK_BN * H * 2 + 16 * 8 + 16 + 2 * TK_BN * 4 + 4 * TK_CAP * 8 + 64;
+  return 1024 + TK_STAGES * (size_t)TK_BN * H * 2 + 16 * 8 + 16 + 2 * TK_BN * 4 + 64;
 }
 
 }  // namespace tc
 
-static bool tc_topk_supported(int H, int k) { return H % 64 == 0 && H >= 64 && H <= 256 && k >= 1 && k <= tc::TK_CAP / 2; }
+static bool tc_topk_supported(int H, int k) { return H % 64 == 0 && H >= 64 && H <= 256 && k >= 1 && k <= tc::TK_KMAX; }
 
 struct TcTopkPlan { int grid, tiles_per_cta; size_t qhi, qlo, qinv, cand, total; };
 static TcTopkPlan plan_tc_topk(int64_t N, int H, int nq) {
@@ -359,7 +390,7 @@ int tt_topk_scan_batched(const void* index_bf16, const float* queries, int64_t N
                          void* workspace, size_t workspace_bytes, void* stream) {
   TT_REQUIRE_DEVICE();
   TT_CHECK_ARG(index_bf16 && queries && out_scores && out_ids && N > 0 && nq > 0, "topk_scan_batched: bad arguments");
-  TT_CHECK_ARG(tt::tc_topk_supported(H, k), "topk_scan_batched: needs H %% 64 == 0, H <= 256, k <= %d (H=%d k=%d)", tt::tc::TK_CAP / 2, H, k);
+  TT_CHECK_ARG(tt::tc_topk_supported(H, k), "topk_scan_batched: needs H %% 64 == 0, H <= 256, k <= %d (H=%d k=%d)", tt::tc::TK_KMAX, H, k);
   TT_CHECK_ARG(k <= N && N < (1ll << 31), "topk_scan_batched: need k <= N < 2^31");
   TT_CHECK_ARG((reinterpret_cast<uintptr_t>(index_bf16) & 15) == 0, "topk_scan_batched: index must be 16-byte aligned");
   const tt::TcTopkPlan plan = tt::plan_tc_topk(N, H, nq);
@@ -383,8 +414,8 @@ int tt_topk_scan_batched(const void* index_bf16, const float* queries, int64_t N
     TT_CUDA(tt::launch_kernel(tt::tc::tc_topk_kernel, dim3((unsigned)plan.grid), dim3(tt::tc::TK_THREADS), smem, s, false, tmQhi, tmQlo,
                               tmD, N, H, k, nqp, plan.tiles_per_cta, (const float*)qinv, row_inv_norms, cand));
     TT_LAUNCH_CHECK("tc_topk_kernel");
-    rc = tt::topk_merge_raw(cand, (int64_t)plan.grid * tt::tc::TK_CAP, nqp, k, id_offset, out_scores + (int64_t)q0 * k,
-                            out_ids + (int64_t)q0 * k, s);
+    rc = tt::topk_merge_blocked(cand, plan.grid, tt::tc::TK_CAP, nqp, k, id_offset, out_scores + (int64_t)q0 * k,
+                                out_ids + (int64_t)q0 * k, s);
     if (rc) return rc;
   }
   return TT_OK;

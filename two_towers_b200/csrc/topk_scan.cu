@@ -257,6 +257,10 @@ struct RawKeys {
   const u64* keys; int64_t per_query;
   __device__ __forceinline__ u64 get(int q, int64_t i) const { return keys[(int64_t)q * per_query + i]; }
 };
+struct BlockedKeys {            // per query: `blocks` buffers of `cap` keys of which the first k are live (tc_topk.cu)
+  const u64* keys; int64_t per_query; int k, cap;
+  __device__ __forceinline__ u64 get(int q, int64_t i) const { return keys[(int64_t)q * per_query + (i / k) * cap + (i % k)]; }
+};
 struct ScoreIdKeys {            // R lists of [nq, k]; list r starts at r * rank_stride elements
   const float* scores; const int64_t* ids; int R, nq, k; int64_t score_stride, id_stride;
   __device__ __forceinline__ u64 get(int q, int64_t i) const {
@@ -450,11 +454,12 @@ static int dispatch_scan(const void* index, const float* queries, int64_t N, int
   return TT_OK;
 }
 
-// exact top-k over `per_query` raw 64-bit keys per query (zero keys are padding); used by the batched tensor-core scan
-int topk_merge_raw(const u64* cand, int64_t per_query, int nq, int k, int64_t id_offset, float* out_scores, int64_t* out_ids,
-                   cudaStream_t s) {
-  RawKeys src{cand, per_query};
-  merge_topk_kernel<RawKeys><<<nq, kMergeThreads, 0, s>>>(src, per_query, k, id_offset, out_scores, out_ids);
+// exact top-k over `blocks` candidate buffers per query, each `cap` keys long with its k best in front (zero keys are
+// padding); used by the batched tensor-core scan
+int topk_merge_blocked(const u64* cand, int blocks, int cap, int nq, int k, int64_t id_offset, float* out_scores, int64_t* out_ids,
+                       cudaStream_t s) {
+  BlockedKeys src{cand, (int64_t)blocks * cap, k, cap};
+  merge_topk_kernel<BlockedKeys><<<nq, kMergeThreads, 0, s>>>(src, (int64_t)blocks * k, k, id_offset, out_scores, out_ids);
   TT_LAUNCH_CHECK("merge_topk_kernel");
   return TT_OK;
 }

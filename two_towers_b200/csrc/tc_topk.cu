@@ -103,6 +103,22 @@ __device__ __forceinline__ u64 tk_select_topk(u64* buf, int cnt, int k, int lane
   return kth;
 }
 
+// Warp-cooperative prune of the candidate buffers of the lanes flagged in `mask` (warp-uniform): each flagged lane's buffer
+// is cut to its k best and that lane's (count, threshold) are updated.  One out-of-line copy (see the epilogue).
+// Values travel in and out by value ((threshold bits << 32) | count) so the caller's count / threshold stay in registers.
+__device__ __noinline__ u64 tk_prune_lanes(unsigned mask, u64* gbuf, int count, float thr, int k, int lane) {
+  while (mask) {
+    const int L = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const u64 gp = __shfl_sync(0xffffffffu, (u64)(uintptr_t)gbuf, L);
+    const int cnt = __shfl_sync(0xffffffffu, count, L);
+    __syncwarp();                                          // lane L's appends are visible to the warp
+    const u64 kth = tk_select_topk(reinterpret_cast<u64*>((uintptr_t)gp), cnt, k, lane);
+    if (lane == L) { count = k; thr = tk_bits_score((uint32_t)(kth >> 32)); }
+  }
+  return ((u64)__float_as_uint(thr) << 32) | (u64)(uint32_t)count;
+}
+
 // fp32 queries [nq, H] -> bf16 hi / lo tiles [TK_BM, H] each (rows >= nq are zero) and, for cosine scores, 1 / max(|q|, 1e-8)
 __global__ void __launch_bounds__(256)
 tk_split_queries_kernel(const float* __restrict__ q, int nq, int H, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
@@ -265,19 +281,11 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
     // documents, the zero rows of a padded query lane) do not flood the buffer.  Padded lanes never append.
     float thr = lrow < nq_pass ? -CUDART_INF_F : CUDART_INF_F;
 
-    // warp-cooperative prune of the buffers of the lanes flagged in `mask` (warp-uniform)
-    auto prune = [&](unsigned mask) {
-      while (mask) {
-        const int L = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const u64 gp = __shfl_sync(0xffffffffu, (u64)(uintptr_t)gbuf, L);
-        const int cnt = __shfl_sync(0xffffffffu, count, L);
-        __syncwarp();                                        // lane L's appends are visible to the warp
-        const u64 kth = tk_select_topk(reinterpret_cast<u64*>((uintptr_t)gp), cnt, k, lane);
-        if (lane == L) { count = k; thr = tk_bits_score((uint32_t)(kth >> 32)); }
-      }
-    };
-
+    // Code size matters here: the epilogue runs once per tile, and with the four 32-column chunks unrolled and the prune
+    // inlined in each of them it was ~10 k instructions of straight-line code whose FETCH (stall_no_inst) set the tile
+    // period (7.6 us per tile against 1.1 us of HBM time).  The chunk loop is therefore a real loop (the TMEM load of a
+    // chunk sits inside it), the prune is one out-of-line function, and the per-element append block is branched over
+    // whenever the chunk maximum is below the threshold -- ~40 instructions per chunk on the common path.
     for (int i = 0; i < nt; ++i) {
       const int b = i & 1;
       const int64_t row0 = (t_beg + i) * TK_BN;
@@ -288,42 +296,46 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
       }
       mbar_wait(&s_full[b], (i >> 1) & 1);
       tc_fence_after();
-      uint32_t r[4][32];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) tmem_ld_x32(tmem_s + lane_addr + (uint32_t)(b * TK_BN + 32 * h), r[h]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);             // the accumulator may be overwritten
       const int valid = (int)((N - row0) < TK_BN ? (N - row0) : TK_BN);   // ragged last tile
-#pragma unroll
+#pragma unroll 1
       for (int h = 0; h < 4; ++h) {
-        float mx = -CUDART_INF_F;
+        uint32_t r[32];
+        tmem_ld_x32(tmem_s + lane_addr + (uint32_t)(b * TK_BN + 32 * h), r);
+        tmem_ld_wait();
+        if (h == 3) {                                      // the whole tile has been read: the accumulator may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[b]);
+        }
         if (cosine) {
           const float4* ds4 = reinterpret_cast<const float4*>(dscale + b * TK_BN + 32 * h);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 dv = ds4[j >> 2];
-            r[h][j + 0] = __float_as_uint(__uint_as_float(r[h][j + 0]) * (my_qinv * dv.x));
-            r[h][j + 1] = __float_as_uint(__uint_as_float(r[h][j + 1]) * (my_qinv * dv.y));
-            r[h][j + 2] = __float_as_uint(__uint_as_float(r[h][j + 2]) * (my_qinv * dv.z));
-            r[h][j + 3] = __float_as_uint(__uint_as_float(r[h][j + 3]) * (my_qinv * dv.w));
+            r[j + 0] = __float_as_uint(__uint_as_float(r[j + 0]) * (my_qinv * dv.x));
+            r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) * (my_qinv * dv.y));
+            r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) * (my_qinv * dv.z));
+            r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) * (my_qinv * dv.w));
           }
         }
         if (32 * h + 32 > valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (32 * h + j >= valid) r[h][j] = 0xff800000u;   // -inf: never a candidate
+            if (32 * h + j >= valid) r[j] = 0xff800000u;   // -inf: never a candidate
         }
+        float mx = -CUDART_INF_F;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[h][j]));
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
         // a chunk adds at most 32 keys per query: make room first (warp-uniform decision, cooperative prune)
         const unsigned need = __ballot_sync(0xffffffffu, count > TK_CAP - 32);
-        if (need) prune(need);
-        if (mx > thr && 32 * h < valid) {
+        if (need) {
+          const u64 ct = tk_prune_lanes(need, gbuf, count, thr, k, lane);
+          count = (int)(uint32_t)ct; thr = __uint_as_float((uint32_t)(ct >> 32));
+        }
+        if (mx > thr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float sv = __uint_as_float(r[h][j]);
+            const float sv = __uint_as_float(r[j]);
             if (sv > thr) { gbuf[count] = tk_make_key(sv, (uint32_t)(row0 + 32 * h + j)); ++count; }
           }
         }
@@ -333,7 +345,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
     // leave the k best of every live buffer in front (zero-padded when the CTA saw fewer than k rows): the merge kernel
     // reads k keys per (query, CTA) and ignores zero keys
     const unsigned over = __ballot_sync(0xffffffffu, count > k);
-    if (over) prune(over);
+    if (over) count = (int)(uint32_t)tk_prune_lanes(over, gbuf, count, thr, k, lane);
     for (int i = count; i < k; ++i) gbuf[i] = 0ull;
   }
   tc_fence_before();

@@ -48,6 +48,30 @@ __device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2, inputs a
   return y;
 }
 
+// exp2 on the FMA / integer pipes for arguments <= 0: round-to-nearest split x = n + f (magic-number add), a polynomial
+// for 2^f on [-0.5, 0.5] and the exponent patched in with an integer add.  The special-function unit retires 16 exp2 per
+// clock and SM -- 1024 cycles for a 128 x 128 score tile, as long as the tile's MMAs -- so a fixed 3 of every 8 elements
+// take this route and the two pipes share the work (FlashAttention-4's trick).  Relative error 1.4e-4 (degree 3, where
+// the result is rounded to bf16 anyway) / 5e-6 (degree 4, where it is summed into the logsumexp).
+constexpr unsigned kExpPolyMask = 0x13;                   // bit e set: element e (mod 8) of a row uses the polynomial
+template <int DEG>
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.0f);
+  const float xf = x + 12582912.0f;                       // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (xf - 12582912.0f);
+  float p;
+  if (DEG == 3) {
+    p = fmaf(0.05502927f, f, 0.24225698f); p = fmaf(p, f, 0.69325305f); p = fmaf(p, f, 0.99995134f);
+  } else {
+    p = fmaf(0.00955411f, f, 0.05587041f); p = fmaf(p, f, 0.24024697f); p = fmaf(p, f, 0.69312803f); p = fmaf(p, f, 0.99999944f);
+  }
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));   // (bits(xf) - bits(magic)) << 23 == bits(xf) << 23 (mod 2^32)
+}
+template <int DEG>
+__device__ __forceinline__ float exp2_sel(float x, int e) {   // e: compile-time element index
+  return ((kExpPolyMask >> (e & 7)) & 1u) ? poly_exp2<DEG>(x) : fast_exp2(x);
+}
+
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
@@ -244,7 +268,7 @@ tc_ce_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[h][j] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j]), c, -mc)));
+        for (int j = 0; j < 32; ++j) r[h][j] = __float_as_uint(exp2_sel<4>(fmaf(__uint_as_float(r[h][j]), c, -mc), j));
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
@@ -578,10 +602,10 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         for (int j = 0; j < 32; j += 4) {
           float4 lv = make_float4(row_lse, row_lse, row_lse, row_lse);
           if (COL) lv = cl4[(col0 + 32 * h + j) >> 2];
-          r[h][j + 0] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 0]), c, -lv.x)));
-          r[h][j + 1] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 1]), c, -lv.y)));
-          r[h][j + 2] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 2]), c, -lv.z)));
-          r[h][j + 3] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(r[h][j + 3]), c, -lv.w)));
+          r[h][j + 0] = __float_as_uint(exp2_sel<3>(fmaf(__uint_as_float(r[h][j + 0]), c, -lv.x), j + 0));
+          r[h][j + 1] = __float_as_uint(exp2_sel<3>(fmaf(__uint_as_float(r[h][j + 1]), c, -lv.y), j + 1));
+          r[h][j + 2] = __float_as_uint(exp2_sel<3>(fmaf(__uint_as_float(r[h][j + 2]), c, -lv.z), j + 2));
+          r[h][j + 3] = __float_as_uint(exp2_sel<3>(fmaf(__uint_as_float(r[h][j + 3]), c, -lv.w), j + 3));
         }
       if (!COL && y0 + BWD_BN > By) {
 #pragma unroll

@@ -332,11 +332,30 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
           const u64 ct = tk_prune_lanes(need, gbuf, count, thr, k, lane);
           count = (int)(uint32_t)ct; thr = __uint_as_float((uint32_t)(ct >> 32));
         }
-        if (mx > thr) {
+        // Candidates are sparse per element (k / rows_seen) but not per warp: 32 queries x 32 rows hold a few of them in
+        // almost every chunk, so a block of 32 predicated per-element appends would run on every chunk (measured: it set
+        // the tile period).  Instead every lane builds the bit mask of its candidates, one redux.or gives the columns that
+        // hold a candidate for ANY query of the warp, and only those columns (2-4 per chunk) are visited, the register
+        // holding column j selected by a warp-uniform switch.
+        if (__any_sync(0xffffffffu, mx > thr)) {
+          unsigned cm = 0u;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sv = __uint_as_float(r[j]);
-            if (sv > thr) { gbuf[count] = tk_make_key(sv, (uint32_t)(row0 + 32 * h + j)); ++count; }
+          for (int j = 0; j < 32; ++j) cm |= (__uint_as_float(r[j]) > thr) ? (1u << j) : 0u;
+          unsigned wm = __reduce_or_sync(0xffffffffu, cm);
+          while (wm) {                                     // warp-uniform
+            const int j = __ffs(wm) - 1;
+            wm &= wm - 1;
+            uint32_t bits;
+            switch (j) {
+#define TT_TK_CASE(J) case J: bits = r[J]; break;
+              TT_TK_CASE(0) TT_TK_CASE(1) TT_TK_CASE(2) TT_TK_CASE(3) TT_TK_CASE(4) TT_TK_CASE(5) TT_TK_CASE(6) TT_TK_CASE(7)
+              TT_TK_CASE(8) TT_TK_CASE(9) TT_TK_CASE(10) TT_TK_CASE(11) TT_TK_CASE(12) TT_TK_CASE(13) TT_TK_CASE(14) TT_TK_CASE(15)
+              TT_TK_CASE(16) TT_TK_CASE(17) TT_TK_CASE(18) TT_TK_CASE(19) TT_TK_CASE(20) TT_TK_CASE(21) TT_TK_CASE(22) TT_TK_CASE(23)
+              TT_TK_CASE(24) TT_TK_CASE(25) TT_TK_CASE(26) TT_TK_CASE(27) TT_TK_CASE(28) TT_TK_CASE(29) TT_TK_CASE(30)
+              default: bits = r[31]; break;
+#undef TT_TK_CASE
+            }
+            if ((cm >> j) & 1u) { gbuf[count] = tk_make_key(__uint_as_float(bits), (uint32_t)(row0 + 32 * h + j)); ++count; }
           }
         }
         __syncwarp();

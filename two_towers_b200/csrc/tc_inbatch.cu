@@ -49,11 +49,13 @@ __device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2, inputs a
 }
 
 // exp2 on the FMA / integer pipes for arguments <= 0: round-to-nearest split x = n + f (magic-number add), a polynomial
-// for 2^f on [-0.5, 0.5] and the exponent patched in with an integer add.  The special-function unit retires 16 exp2 per
-// clock and SM -- 1024 cycles for a 128 x 128 score tile, as long as the tile's MMAs -- so a fixed 3 of every 8 elements
-// take this route and the two pipes share the work (FlashAttention-4's trick).  Relative error 1.4e-4 (degree 3, where
-// the result is rounded to bf16 anyway) / 5e-6 (degree 4, where it is summed into the logsumexp).
-constexpr unsigned kExpPolyMask = 0x13;                   // bit e set: element e (mod 8) of a row uses the polynomial
+// for 2^f on [-0.5, 0.5] and the exponent patched in with an integer add (FlashAttention-4's trick: the special-function
+// unit retires 16 exp2 per clock and SM -- 1024 cycles for a 128 x 128 score tile, as long as the tile's MMAs).
+// Relative error 1.4e-4 (degree 3) / 5e-6 (degree 4).  MEASURED (gpurun r02f, mask 0x13 = 3 of every 8 elements): no gain
+// -- forward 15.0 -> 15.3 us, backward 34.7 -> 35.1 us: with eight epilogue warps the loops are bound by the dependent
+// TMEM-load -> exp -> pack -> shared-store chain and by issue slots, not by MUFU throughput, and the eight extra
+// FMA-pipe instructions per element cost what the MUFU slot saved.  Kept behind the mask (0 = every element on MUFU).
+constexpr unsigned kExpPolyMask = 0x0;                    // bit e set: element e (mod 8) of a row uses the polynomial
 template <int DEG>
 __device__ __forceinline__ float poly_exp2(float x) {
   x = fmaxf(x, -126.0f);
@@ -758,12 +760,13 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     __syncthreads();                                       // own rows staged
     if (warp >= 2 && pair) mbar_wait(xfer_bar, 0);         // peer's half has landed
     TT_CTA_STAMP(6);
+    if (dbg && threadIdx.x == 64) dbg[(64 + 45) * 8 + 0] = clock64();
     if (warp >= 2) {
       const float scale = p.coef * (p.grad_out ? *p.grad_out : 1.0f);
       float4 cs[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
       for (int i0 = 0; i0 < rpw; i0 += 4) {                // 4 rows at a time: their loads and shuffle trees interleave
         if (i0 == 16) load_y16(16);                        // single split: second half of the warp's 32 rows
-#define TT_PB(slot) do { if (p.dbg && threadIdx.x == 64) p.dbg[(64 + 40 + (i0 >> 2)) * 8 + (slot)] = clock64(); } while (0)
+#define TT_PB(slot) do { if (dbg && threadIdx.x == 64) dbg[(64 + 40 + (i0 >> 2)) * 8 + (slot)] = clock64(); } while (0)
         TT_PB(0);
         float4 o[4][2];
         uint2 yw[4][2];
@@ -828,7 +831,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
           }
         }
       }
-      if (p.dbg && threadIdx.x == 64) p.dbg[(64 + 44) * 8 + 0] = clock64();
+      if (dbg && threadIdx.x == 64) dbg[(64 + 44) * 8 + 0] = clock64();
       // per-32-row column sums: a warp's own block (32 rows per warp) or the sum of a warp pair (16 rows each)
 #pragma unroll
       for (int st = 0; st < 2; ++st) {
@@ -836,6 +839,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         if (st < steps && c < H) *reinterpret_cast<float4*>(cs_s + e * H + c) = cs[st];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
+      if (dbg && threadIdx.x == 64) dbg[(64 + 46) * 8 + 0] = clock64();
       const int wpb = 32 / rpw;                              // warps that share one 32-row block of column sums (1, 2 or 4)
       const bool writer = (e % wpb) == 0;
       const int64_t blk_row = x0 + fin0 + (e / wpb) * 32;
@@ -855,6 +859,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       }
     }
     TT_CTA_STAMP(3);
+    if (dbg && threadIdx.x == 64) dbg[(64 + 47) * 8 + 0] = clock64();
     if (pair) cluster_sync_all();                          // neither CTA leaves while its peer may still read its send buffer
   }
   tc_fence_before();
@@ -1091,6 +1096,8 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
     printf("[tt ce_bwd fused tail, cycles; last writer among CTAs] per 4-row group {begin, dots, shuffled}, then end:");
     for (int g = 0; g < 4; ++g) printf("  %lld %lld %lld |", host[(64 + 40 + g) * 8 + 0] - t0, host[(64 + 40 + g) * 8 + 1] - t0, host[(64 + 40 + g) * 8 + 2] - t0);
     printf("  %lld\n", host[(64 + 44) * 8 + 0] - t0);
+    printf("[tt ce_bwd fused tail, cycles] peer half landed %lld, column-sum barrier %lld, outputs stored %lld\n", host[(64 + 45) * 8 + 0] - t0,
+           host[(64 + 46) * 8 + 0] - t0, host[(64 + 47) * 8 + 0] - t0);
     printf("[tt ce_bwd O store, cycles] cb: tmem_loaded staged read stored\n");
     for (int cb = 0; cb < H / 32; ++cb) {
       printf("  %2d:", cb);

@@ -36,7 +36,8 @@ namespace tc {
 constexpr int TK_BM = 128;            // queries per pass (UMMA M)
 constexpr int TK_BN = 128;            // documents per tile (UMMA N)
 constexpr int TK_STAGES = 3;
-constexpr int TK_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue (one per TMEM lane quarter)
+constexpr int TK_EW = 8;              // epilogue warps: two per TMEM lane quarter, each owning a 64-column half of every tile
+constexpr int TK_THREADS = 64 + TK_EW * 32;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int TK_CAP = 512;           // candidate keys per (query, CTA): a prune frees CAP - 32 - k slots, so the rows seen
                                       // between two prunes grow by (CAP - 32) / k (4.8x at k = 100): ~4 prunes per query and CTA
 constexpr int TK_KMAX = 128;          // k <= TK_KMAX
@@ -182,8 +183,8 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
     tma_prefetch_desc(&tmQhi); tma_prefetch_desc(&tmQlo); tma_prefetch_desc(&tmD);
     mbar_init(q_bar, 1);
     for (int s = 0; s < TK_STAGES; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4); }
-    mbar_init(q_ready, 4);
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], TK_EW); }
+    mbar_init(q_ready, TK_EW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -247,8 +248,11 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
       __syncwarp();
     }
   } else {
-    // epilogue warps 2..5: TMEM lane quarter = warp & 3; thread = one query
-    const int quarter = warp & 3, ew = warp - 2;
+    // epilogue warps 2..9: TMEM lane quarter = warp & 3, column half = (warp - 2) / 4; a thread = one query x one 64-column
+    // half of every tile, with its own candidate buffer, count and threshold (top-k of a union is inside the union of the
+    // top-ks).  One warp per quarter walked the whole 128-column row serially and its dependent chain (TMEM load -> max
+    // -> vote -> append) took longer per tile than the tile's HBM time; two warps per scheduler also hide each other.
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int lrow = quarter * 32 + lane;                  // query index inside the pass == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     // query tiles: smem (TMA, 128B swizzle) -> registers -> TMEM
@@ -256,7 +260,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
 #pragma unroll 1
     for (int part = 0; part < 2; ++part) {
       const uint8_t* qt = d_tiles + (1 + part) * d_bytes;
-      for (int kb = 0; kb < kq; ++kb) {
+      for (int kb = half; kb < kq; kb += 2) {
         uint32_t xr[32];
         const uint8_t* xrow = qt + kb * (TK_BM * 128) + lrow * 128;
 #pragma unroll
@@ -274,7 +278,7 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
 
     const bool cosine = dinv != nullptr;
     const float my_qinv = cosine ? qinv[lrow] : 1.0f;
-    u64* gbuf = cand + ((size_t)lrow * gridDim.x + blockIdx.x) * TK_CAP;   // this query's candidate buffer for this CTA
+    u64* gbuf = cand + (((size_t)lrow * gridDim.x + blockIdx.x) * 2 + half) * TK_CAP;   // this thread's candidate buffer
     int count = 0;
     // Rows of a CTA arrive in increasing order, so once the buffer has been pruned to its k best a later row that only
     // TIES the k-th score can never displace it (ties -> lower row): the test is strict, and identical scores (duplicate
@@ -290,19 +294,19 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
       const int b = i & 1;
       const int64_t row0 = (t_beg + i) * TK_BN;
       if (cosine) {                                        // per-document scales of this tile -> smem, read back as broadcasts
-        const int64_t gr = row0 + (threadIdx.x - 64);
-        dscale[b * TK_BN + threadIdx.x - 64] = gr < N ? __ldg(dinv + gr) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps only
+        const int te = threadIdx.x - 64;
+        if (te < TK_BN) { const int64_t gr = row0 + te; dscale[b * TK_BN + te] = gr < N ? __ldg(dinv + gr) : 0.f; }
+        asm volatile("bar.sync 1, %0;" ::"n"(TK_EW * 32) : "memory");   // the epilogue warps only
       }
       mbar_wait(&s_full[b], (i >> 1) & 1);
       tc_fence_after();
       const int valid = (int)((N - row0) < TK_BN ? (N - row0) : TK_BN);   // ragged last tile
 #pragma unroll 1
-      for (int h = 0; h < 4; ++h) {
+      for (int h = 2 * half; h < 2 * half + 2; ++h) {      // this thread's two 32-column chunks
         uint32_t r[32];
         tmem_ld_x32(tmem_s + lane_addr + (uint32_t)(b * TK_BN + 32 * h), r);
         tmem_ld_wait();
-        if (h == 3) {                                      // the whole tile has been read: the accumulator may be overwritten
+        if (h == 2 * half + 1) {                           // this warp has read its half: the accumulator may be overwritten
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_empty[b]);
@@ -332,30 +336,11 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
           const u64 ct = tk_prune_lanes(need, gbuf, count, thr, k, lane);
           count = (int)(uint32_t)ct; thr = __uint_as_float((uint32_t)(ct >> 32));
         }
-        // Candidates are sparse per element (k / rows_seen) but not per warp: 32 queries x 32 rows hold a few of them in
-        // almost every chunk, so a block of 32 predicated per-element appends would run on every chunk (measured: it set
-        // the tile period).  Instead every lane builds the bit mask of its candidates, one redux.or gives the columns that
-        // hold a candidate for ANY query of the warp, and only those columns (2-4 per chunk) are visited, the register
-        // holding column j selected by a warp-uniform switch.
-        if (__any_sync(0xffffffffu, mx > thr)) {
-          unsigned cm = 0u;
+        if (mx > thr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cm |= (__uint_as_float(r[j]) > thr) ? (1u << j) : 0u;
-          unsigned wm = __reduce_or_sync(0xffffffffu, cm);
-          while (wm) {                                     // warp-uniform
-            const int j = __ffs(wm) - 1;
-            wm &= wm - 1;
-            uint32_t bits;
-            switch (j) {
-#define TT_TK_CASE(J) case J: bits = r[J]; break;
-              TT_TK_CASE(0) TT_TK_CASE(1) TT_TK_CASE(2) TT_TK_CASE(3) TT_TK_CASE(4) TT_TK_CASE(5) TT_TK_CASE(6) TT_TK_CASE(7)
-              TT_TK_CASE(8) TT_TK_CASE(9) TT_TK_CASE(10) TT_TK_CASE(11) TT_TK_CASE(12) TT_TK_CASE(13) TT_TK_CASE(14) TT_TK_CASE(15)
-              TT_TK_CASE(16) TT_TK_CASE(17) TT_TK_CASE(18) TT_TK_CASE(19) TT_TK_CASE(20) TT_TK_CASE(21) TT_TK_CASE(22) TT_TK_CASE(23)
-              TT_TK_CASE(24) TT_TK_CASE(25) TT_TK_CASE(26) TT_TK_CASE(27) TT_TK_CASE(28) TT_TK_CASE(29) TT_TK_CASE(30)
-              default: bits = r[31]; break;
-#undef TT_TK_CASE
-            }
-            if ((cm >> j) & 1u) { gbuf[count] = tk_make_key(__uint_as_float(bits), (uint32_t)(row0 + 32 * h + j)); ++count; }
+          for (int j = 0; j < 32; ++j) {
+            const float sv = __uint_as_float(r[j]);
+            if (sv > thr) { gbuf[count] = tk_make_key(sv, (uint32_t)(row0 + 32 * h + j)); ++count; }
           }
         }
         __syncwarp();
@@ -390,7 +375,7 @@ static TcTopkPlan plan_tc_topk(int64_t N, int H, int nq) {
   p.qhi = align_up((size_t)tc::TK_BM * H * 2);
   p.qlo = p.qhi;
   p.qinv = align_up((size_t)tc::TK_BM * 4);
-  p.cand = align_up((size_t)tc::TK_BM * p.grid * tc::TK_CAP * sizeof(u64));
+  p.cand = align_up((size_t)tc::TK_BM * p.grid * 2 * tc::TK_CAP * sizeof(u64));
   p.total = p.qhi + p.qlo + p.qinv + p.cand + 1024;
   (void)nq;
   return p;
@@ -431,7 +416,7 @@ int tt_topk_scan_batched(const void* index_bf16, const float* queries, int64_t N
   __nv_bfloat16* qhi = w.take<__nv_bfloat16>((size_t)tt::tc::TK_BM * H);
   __nv_bfloat16* qlo = w.take<__nv_bfloat16>((size_t)tt::tc::TK_BM * H);
   float* qinv = w.take<float>(tt::tc::TK_BM);
-  tt::u64* cand = w.take<tt::u64>((size_t)tt::tc::TK_BM * plan.grid * tt::tc::TK_CAP);
+  tt::u64* cand = w.take<tt::u64>((size_t)tt::tc::TK_BM * plan.grid * 2 * tt::tc::TK_CAP);
   CUtensorMap tmQhi, tmQlo, tmD;
   int rc = tt::tc::make_tmap_bf16(&tmQhi, qhi, tt::tc::TK_BM, (uint64_t)H, tt::tc::TK_BM); if (rc) return rc;
   rc = tt::tc::make_tmap_bf16(&tmQlo, qlo, tt::tc::TK_BM, (uint64_t)H, tt::tc::TK_BM); if (rc) return rc;
@@ -445,7 +430,7 @@ int tt_topk_scan_batched(const void* index_bf16, const float* queries, int64_t N
     TT_CUDA(tt::launch_kernel(tt::tc::tc_topk_kernel, dim3((unsigned)plan.grid), dim3(tt::tc::TK_THREADS), smem, s, false, tmQhi, tmQlo,
                               tmD, N, H, k, nqp, plan.tiles_per_cta, (const float*)qinv, row_inv_norms, cand));
     TT_LAUNCH_CHECK("tc_topk_kernel");
-    rc = tt::topk_merge_blocked(cand, plan.grid, tt::tc::TK_CAP, nqp, k, id_offset, out_scores + (int64_t)q0 * k,
+    rc = tt::topk_merge_blocked(cand, plan.grid * 2, tt::tc::TK_CAP, nqp, k, id_offset, out_scores + (int64_t)q0 * k,
                                 out_ids + (int64_t)q0 * k, s);
     if (rc) return rc;
   }

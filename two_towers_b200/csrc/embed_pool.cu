@@ -404,27 +404,28 @@ seg_fixup_kernel(const uint32_t* __restrict__ keys, int64_t n_tokens, int64_t V,
   }
   const int64_t c_last = (lo - 1) / kSegChunk;            // chunk holding the last token of the run
   float* dst = dW + (int64_t)key * E;
-  for (int e0 = 0; e0 < E; e0 += 32 * 4) {                // 4 columns per lane per pass
-    float acc[4];
+  // blockIdx.y selects a group of 128 columns (4 per lane), so the hottest rows' fix-ups are spread over E/128 warps;
+  // 8 chunks of carries are in flight per step and still added in chunk order
+  const int e0 = blockIdx.y * 128;
+  float acc[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const int e = e0 + lane + 32 * j; acc[j] = e < E ? dst[e] : 0.f; }
-    for (int64_t c = chunk + 1; c <= c_last; c += 4) {    // 4 chunks of carries in flight, added in chunk order
-      float v[4][4];
+  for (int j = 0; j < 4; ++j) { const int e = e0 + lane + 32 * j; acc[j] = e < E ? dst[e] : 0.f; }
+  for (int64_t c = chunk + 1; c <= c_last; c += 8) {
+    float v[8][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int e = e0 + lane + 32 * j;
-          v[u][j] = (c + u <= c_last && e < E) ? __ldg(carry + (c + u) * E + e) : 0.f;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int e = e0 + lane + 32 * j;
+        v[u][j] = (c + u <= c_last && e < E) ? __ldg(carry + (c + u) * E + e) : 0.f;
+      }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] += v[u][j];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { const int e = e0 + lane + 32 * j; if (e < E) dst[e] = acc[j]; }
+      for (int j = 0; j < 4; ++j) acc[j] += v[u][j];
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const int e = e0 + lane + 32 * j; if (e < E) dst[e] = acc[j]; }
 }
 
 constexpr int64_t kSmallVocab = 1024;
@@ -548,7 +549,7 @@ static int embed_pool_bwd_t(const IdT* ids, const float* inv_len, const float* d
   else if (vec)             seg_reduce_vec_kernel<4><<<grid, warps * 32, 0, s>>>(keys, vals, inv_len, d_pooled, n, V, E, d_table, carry);
   else                      seg_reduce_kernel<<<grid, warps * 32, 0, s>>>(keys, vals, inv_len, d_pooled, n, V, E, d_table, carry);
   TT_LAUNCH_CHECK("seg_reduce_kernel");
-  seg_fixup_kernel<<<grid, warps * 32, 0, s>>>(keys, n, V, E, d_table, carry);
+  seg_fixup_kernel<<<dim3(grid, (unsigned)ceil_div(E, 128)), warps * 32, 0, s>>>(keys, n, V, E, d_table, carry);
   TT_LAUNCH_CHECK("seg_fixup_kernel");
   return TT_OK;
 }

@@ -327,20 +327,33 @@ tc_topk_kernel(const __grid_constant__ CUtensorMap tmQhi, const __grid_constant_
           for (int j = 0; j < 32; ++j)
             if (32 * h + j >= valid) r[j] = 0xff800000u;   // -inf: never a candidate
         }
-        float mx = -CUDART_INF_F;
+        float m8[4];                                       // maxima of the four 8-column groups, then of the chunk
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        for (int g = 0; g < 4; ++g) {
+          m8[g] = __uint_as_float(r[8 * g]);
+#pragma unroll
+          for (int jj = 1; jj < 8; ++jj) m8[g] = fmaxf(m8[g], __uint_as_float(r[8 * g + jj]));
+        }
+        const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
         // a chunk adds at most 32 keys per query: make room first (warp-uniform decision, cooperative prune)
         const unsigned need = __ballot_sync(0xffffffffu, count > TK_CAP - 32);
         if (need) {
           const u64 ct = tk_prune_lanes(need, gbuf, count, thr, k, lane);
           count = (int)(uint32_t)ct; thr = __uint_as_float((uint32_t)(ct >> 32));
         }
-        if (mx > thr) {
+        // Candidates are rare per element (k / rows seen) but 32 queries x 32 documents hold one in most chunks, so the
+        // append code is entered per 8-column group and only where SOME query of the warp has a candidate (2-3 of the 4
+        // groups mid-scan); inside, the stores are predicated per thread.
+        if (__any_sync(0xffffffffu, mx > thr)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sv = __uint_as_float(r[j]);
-            if (sv > thr) { gbuf[count] = tk_make_key(sv, (uint32_t)(row0 + 32 * h + j)); ++count; }
+          for (int g = 0; g < 4; ++g) {
+            if (__any_sync(0xffffffffu, m8[g] > thr)) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const float sv = __uint_as_float(r[8 * g + jj]);
+                if (sv > thr) { gbuf[count] = tk_make_key(sv, (uint32_t)(row0 + 32 * h + 8 * g + jj)); ++count; }
+              }
+            }
           }
         }
         __syncwarp();

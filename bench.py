@@ -472,9 +472,10 @@ def bench_word_tower(args, dev, rank, world, pg):
             ntok = int((ids > 0).sum().item())
             uniq = int(torch.unique(ids[ids > 0]).numel())
             b1 = R * L * 4 + ntok * E * 4 + R * E * 4                    # ids + rows actually read + pooled out
+            tr1, src1 = ncu_traffic("embed_pool_fwd_kernel", f"R{R}_L{L}_V{V}_E{E}")
             res["gather_pool_fwd"] = {"kernel": "embed_pool_fwd_kernel", "rows": R, "tokens": ntok, "unique_rows": uniq, "ms": t1 * 1e3,
                                       "roofline": {"bound": "hbm", "achieved": b1 / t1 / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                                   "frac": b1 / t1 / 1e9 / pk["hbm"], "traffic": None, "algorithmic_bytes": b1,
+                                                   "frac": b1 / t1 / 1e9 / pk["hbm"], "traffic": tr1, "traffic_source": src1, "algorithmic_bytes": b1,
                                                    "note": "bytes = ids + non-pad rows x E x 4 + pooled out (SURVEY 8d); Zipf ids re-use hot rows out of L2, "
                                                            "so DRAM traffic is below the algorithmic bytes"}}
             if trainable:

@@ -374,8 +374,10 @@ def _graph_time(run, dev, nrep=10, iters=12, skip=3):
 
 
 def kernel_roofline(tt, tr, dev):
-    """Time the loss backward (dominant kernel of the step) alone, L2-cold, with CUDA events: the same single launch the
-    trainer issues (both gradient passes, fused with the normalise backward when the shape allows)."""
+    """Time the loss kernels (the dominant kernels of the step) alone, L2-cold, with CUDA events: the same launches the
+    trainer issues.  One-pass path: tt_inbatch_ce_fwd_dq (forward + query gradient, S formed once) and tt_inbatch_ce_dd
+    (document gradient); `roofline` is the LONGER of the two, `loss_step` both together.  Two-launch path (one-pass
+    switched off / not applicable): the merged backward kernel as in round 1."""
     from two_towers_b200 import _lib
     pk = peaks()
     lib = _lib.load()
@@ -386,13 +388,52 @@ def kernel_roofline(tt, tr, dev):
     d = torch.nn.functional.normalize(torch.randn(Bg, H, device=dev), dim=-1)
     loss, lse, _ = tt.ops.inbatch_ce_fwd(q, d, 0.1, precision=prec)
     merged = prec == "bf16" and H % 64 == 0 and H <= 256
+    vp = lambda t: None if t is None else t.data_ptr()
+    NREP = 10
+    note_t = f"duration = median CUDA-event time of {NREP} back-to-back launches in one graph replay / {NREP} (L2 flushed before each replay)"
+    if merged and getattr(tr, "onepass", False):
+        qb, db = tt.ops.cast_bf16(q), tt.ops.cast_bf16(d)
+        lse_g = torch.cat([lse] * tr.world) if tr.world > 1 else lse
+        inv = torch.ones(Bl, device=dev)
+        dzq = torch.empty(Bl, H, dtype=torch.bfloat16, device=dev); dzd = torch.empty_like(dzq)
+        csq = torch.empty(Bl // 32, H, device=dev); csd = torch.empty_like(csq)
+        sync = torch.zeros(int(lib.tt_inbatch_ce_onepass_sync_bytes(Bl)), dtype=torch.uint8, device=dev)
+        lss = torch.zeros((), device=dev); lse_o = torch.zeros(Bl, device=dev)
+        qp = _lib.CePass(vp(qb), Bl, vp(db), Bg, Bg, Bg, 0, 0, None, 0, None, 0, vp(dzq), vp(csq), vp(inv))
+        dp = _lib.CePass(vp(db), Bl, vp(qb if tr.world == 1 else db), Bg, Bg, Bg, 0, 0, vp(lse_g), 0, None, 0, vp(dzd), vp(csd), vp(inv))
+        def run_a():
+            s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, 10.0, 10.0, 1.0 / Bg, None, vp(lss), vp(lse_o), None, vp(sync), s), "ce_fwd_dq")
+        def run_b():
+            s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.tt_inbatch_ce_dd(C.byref(dp), H, 10.0, 1.0 / Bg, None, s), "ce_dd")
+        ta, tb = _graph_time(run_a, dev, nrep=NREP), _graph_time(run_b, dev, nrep=NREP)
+        fa, fb = 4.0 * Bl * Bg * H, 2.0 * Bl * Bg * H
+        shape = f"Bl{Bl}_Bg{Bg}_H{H}"
+        def entry(kernel, what, sec, alg, exe, note):
+            traffic, src = ncu_traffic(kernel, shape)
+            return {"kernel": what, "bound": "tensor", "achieved": alg / sec / 1e12, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                    "frac": alg / sec / 1e12 / pk["tf_burst"], "traffic": traffic, "traffic_source": src, "ms": sec * 1e3,
+                    "launch_flops": alg, "executed_flops": exe, "note": note + "; " + note_t,
+                    "peak_source": f"{pk['src']} bf16 burst (kernel timed alone)"}
+        ea = entry("tc_ce_fwd_dq_kernel", "inbatch_ce_fwd_dq[bf16] (loss forward + dQ in ONE pass over S = Q D^T, fixed softmax shift, "
+                   "4-CTA cluster split reduction + fused normalise backward)", ta, fa, fa,
+                   "algorithmic FLOPs = executed FLOPs: S (2 B_l B_g H) is formed once and feeds the forward AND dQ (2 B_l B_g H)")
+        eb = entry("tc_ce_dd", "inbatch_ce_dd[bf16] (dD with S recomputed from the saved lse, cluster split reduction + fused normalise backward)",
+                   tb, fb, 2 * fb, "achieved counts algorithmic FLOPs (dD product); the kernel executes 2x (S^T = D Q^T is recomputed)")
+        roof = dict(eb if tb >= ta else ea)
+        roof["other_loss_kernel"] = ea if tb >= ta else eb
+        roof["loss_step"] = {"launches": 2, "ms": (ta + tb) * 1e3, "algorithmic_flops": fa + fb, "executed_flops": fa + 2 * fb,
+                             "achieved": (fa + fb) / (ta + tb) / 1e12, "frac": (fa + fb) / (ta + tb) / 1e12 / pk["tf_burst"],
+                             "executed_frac": (fa + 2 * fb) / (ta + tb) / 1e12 / pk["tf_burst"],
+                             "note": "loss forward + both gradients: 6 B_l B_g H algorithmic, 8 executed (round 1/2a two-launch form: 10 executed)"}
+        return roof
     if merged:
         # rank-local view of the data-parallel step: local queries / local documents against all Bg rows
         qb, db = tt.ops.cast_bf16(q), tt.ops.cast_bf16(d)
         lse_g = torch.cat([lse] * tr.world) if tr.world > 1 else lse
         n = int(lib.tt_inbatch_ce_bwd_nparts_ex(Bl, Bg, Bl, Bg, H))
         fused = bool(lib.tt_inbatch_ce_bwd_fused_ok(Bl, Bg, Bl, Bg, H)) and Bl % 32 == 0
-        vp = lambda t: None if t is None else t.data_ptr()
         inv = torch.ones(Bl, device=dev)
         if fused:
             dzq = torch.empty(Bl, H, dtype=torch.bfloat16, device=dev); dzd = torch.empty_like(dzq)
@@ -411,7 +452,6 @@ def kernel_roofline(tt, tr, dev):
         def run():
             tt.ops.inbatch_ce_bwd(q, d, lse, 0.1, precision=prec)
         what = f"inbatch_ce_bwd[{prec}] (dQ+dD, fused recompute)"
-    NREP = 10
     sec = _graph_time(run, dev, nrep=NREP)
     flops = 4.0 * Bl * Bg * H                   # algorithmic backward FLOPs (dQ + dD products); recompute not counted
     achieved = flops / sec / 1e12
@@ -419,8 +459,7 @@ def kernel_roofline(tt, tr, dev):
     return {"kernel": what, "bound": "tensor", "achieved": achieved,
             "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"], "traffic": traffic,
             "traffic_source": src, "ms": sec * 1e3, "launch_flops": flops, "executed_flops": 2 * flops,
-            "note": "achieved counts algorithmic FLOPs; the kernel executes 2x (S = X Y^T is recomputed, flash style); "
-                    f"duration = median CUDA-event time of {NREP} back-to-back launches in one graph replay / {NREP} (L2 flushed before each replay)",
+            "note": "achieved counts algorithmic FLOPs; the kernel executes 2x (S = X Y^T is recomputed, flash style); " + note_t,
             "peak_source": f"{pk['src']} bf16 burst (kernel timed alone)"}
 
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TT_ABI_VERSION 3
+#define TT_ABI_VERSION 4
 
 enum { TT_OK = 0, TT_ERR_INVALID = -1, TT_ERR_CUDA = -2, TT_ERR_ARCH = -3, TT_ERR_WORKSPACE = -4,
        TT_ERR_UNSUPPORTED = -5 };
@@ -220,10 +220,33 @@ int tt_inbatch_ce_fwd_ex(const void* q_bf16, int64_t Bq, const void* d_bf16, int
  * same launch (the last CTA of each row tile merges its splits, fixed order); without it a second launch does. */
 size_t tt_inbatch_ce_sync_bytes(int64_t Bq);
 int tt_inbatch_ce_bwd_nparts_ex(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_rows, int64_t d_y_rows, int H);
-/* 1 when tt_inbatch_ce_bwd_parts_ex can run the fused normalise backward for these shapes (<= 2 splits). */
+/* 1 when tt_inbatch_ce_bwd_parts_ex can run the fused normalise backward for these shapes (both passes in one launch: <= 2 splits). */
 int tt_inbatch_ce_bwd_fused_ok(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_rows, int64_t d_y_rows, int H);
 int tt_inbatch_ce_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temperature,
                                float loss_scale, const float* grad_out, int nparts, void* stream);
+/* One-pass step (TT_PREC_BF16 operands, H % 64 == 0, H <= 256), for logits with a known bound: |logit_ij| <= logit_bound
+ * (unit-norm tower outputs, twotower/encoders.py:77: logit_bound = inv_temperature).  With the bound as a fixed softmax
+ * shift no running maximum is needed, so the forward of twotower/losses.py:107-116 and the query gradient come out of ONE
+ * pass over S = X Y^T:  E = exp(S/temp - bound) feeds the second product O += E Y tile by tile while its row sums L
+ * accumulate, and the row is normalised once at the end:  dq_i = g*loss_scale/temp * (O_i / L_i - y_pos(i)),
+ * lse_i = bound + log L_i.  S is formed once instead of three times (forward, dq pass, dd pass of the two-launch form).
+ *   tt_inbatch_ce_fwd_dq : q_pass as for tt_inbatch_ce_bwd_parts_ex, except that q_pass->lse is ignored (lse is an
+ *       OUTPUT here, [x_rows]) and, without dz_bf16, out_parts receives the finished dq [x_rows,H] (no slices).
+ *       The 1, 2 or 4 CTAs that share a row tile form a cluster and reduce their accumulators through distributed
+ *       shared memory in rank order (bitwise reproducible).  sync_scratch: tt_inbatch_ce_onepass_sync_bytes(x_rows)
+ *       bytes, zero-filled once by the caller, re-armed by every call.
+ *   tt_inbatch_ce_dd     : the document gradient as its own launch (it needs the lse of every -- gathered -- query):
+ *       d_pass as for tt_inbatch_ce_bwd_parts_ex; with out_parts the gradient is left as tt_inbatch_ce_dd_nparts slices.
+ *   tt_inbatch_ce_onepass_ok : 1 when the shapes and the bound qualify (2 * logit_bound * log2(e) < 120 keeps E a normal
+ *       fp32 number for every admissible logit).
+ */
+int tt_inbatch_ce_onepass_ok(int64_t Bq, int64_t Bd, int H, float logit_bound);
+size_t tt_inbatch_ce_onepass_sync_bytes(int64_t Bq);
+int tt_inbatch_ce_fwd_dq(const tt_ce_pass_t* q_pass, int H, float inv_temperature, float logit_bound, float loss_scale,
+                         const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch, void* stream);
+int tt_inbatch_ce_dd_nparts(int64_t d_x_rows, int64_t d_y_rows, int H);
+int tt_inbatch_ce_dd(const tt_ce_pass_t* d_pass, int H, float inv_temperature, float loss_scale, const float* grad_out,
+                     void* stream);
 int tt_inbatch_ce_bwd_parts(const void* q_bf16, const void* d_bf16, const float* lse, int64_t Bq, int64_t Bd,
                             int H, float inv_temperature, int64_t label_offset, float loss_scale,
                             const float* grad_out, float* dq_parts, int64_t dq_part_stride,

@@ -1,0 +1,147 @@
+"""GPU tests of the one-pass in-batch softmax step (tt_inbatch_ce_fwd_dq + tt_inbatch_ce_dd): loss forward and query
+gradient from ONE pass over S = Q D^T with the logit bound as a fixed softmax shift, document gradient as the second
+launch, split reduction over 1 / 2 / 4-CTA clusters.  Checked against the numpy oracle of twotower/losses.py:107-116
+(bf16 tolerance 2e-2, max-abs and norm-wise), for bitwise repeatability, and -- in the dz form the trainer uses -- against
+the fp64 normalise backward of the kernel's own dq / dd."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import two_tower_oracle as O
+from _parity import BF16_RTOL, check
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+SHAPES = [(128, 128, 256, 0, 0.1), (64, 64, 64, 0, 0.1), (100, 257, 64, 57, 0.05), (257, 300, 128, 3, 1.0),
+          (1024, 1024, 256, 0, 0.1), (4096, 4096, 256, 0, 0.1), (96, 768, 256, 96 * 3, 0.1), (200, 200, 192, 0, 0.1),
+          (2048, 4096, 128, 2048, 0.1),          # 16 row tiles x 4 splits, positives in the second half
+          (8192, 8192, 256, 0, 0.1),             # 64 row tiles -> clusters of 2
+          (10000, 10000, 64, 0, 0.07),           # 79 row tiles -> single CTA per row tile, ragged last tile
+          (4096, 32768, 256, 3 * 4096, 0.1)]     # one rank's share of an 8-GPU global-negatives step
+
+
+def _inputs(Bq, Bd, H, off, seed):
+    rng = np.random.default_rng(seed)
+    q = O.normalize(rng.standard_normal((Bq, H))).astype(np.float32)
+    d = O.normalize(rng.standard_normal((Bd, H))).astype(np.float32)
+    idx = np.arange(Bq) + off
+    d[idx] = O.normalize(d[idx] + 2.0 * q).astype(np.float32)      # positives correlated with their queries
+    return q, d
+
+
+@pytest.mark.parametrize("Bq,Bd,H,off,temp", SHAPES)
+def test_onepass_vs_oracle(Bq, Bd, H, off, temp):
+    import two_towers_b200 as tt
+    q, d = _inputs(Bq, Bd, H, off, Bq + Bd + H)
+    tq, td = torch.tensor(q, device=DEV), torch.tensor(d, device=DEV)
+    qb, db = tt.ops.cast_bf16(tq), tt.ops.cast_bf16(td)
+    gout = torch.tensor(0.5, device=DEV)
+    loss, lse, pm, dq, dd = tt.ops.inbatch_ce_onepass(qb, db, temp, off, grad_out=gout)
+    torch.cuda.synchronize()
+    q64, d64 = q.astype(np.float64), d.astype(np.float64)
+    rl, rlse = O.in_batch_loss(q64, d64, temp, off)
+    rdq, rdd = O.in_batch_loss_bwd(q64, d64, temp, off, grad=0.5)
+    print(f"  one-pass CE Bq={Bq} Bd={Bd} H={H} off={off} temp={temp}: loss {loss.item():.6f} (oracle {rl:.6f})")
+    assert abs(loss.item() - rl) <= BF16_RTOL * max(abs(rl), 1.0), (loss.item(), rl)
+    assert np.abs(lse.cpu().numpy() - rlse).max() <= BF16_RTOL * max(np.abs(rlse).max(), 1.0)
+    rpm = float((q64 * d64[np.arange(Bq) + off]).sum(1).mean())
+    assert abs(pm.item() - rpm) <= BF16_RTOL * max(abs(rpm), 1e-3), (pm.item(), rpm)
+    check(dq, rdq, BF16_RTOL, "dq"); check(dd, rdd, BF16_RTOL, "dd")
+    # the two-launch kernels (online softmax, S recomputed per pass) on the same operands agree far inside the tolerance
+    l2, lse2, _ = tt.ops.inbatch_ce_fwd(tq, td, temp, off, precision="bf16", q_bf16=qb, d_bf16=db)
+    assert abs(l2.item() - loss.item()) <= 1e-4 * max(1.0, abs(l2.item()))
+    assert (lse2 - lse).abs().max().item() <= 1e-4 * max(1.0, lse2.abs().max().item())
+    # bitwise repeatable, ticket counter re-armed
+    loss_b, lse_b, pm_b, dq_b, dd_b = tt.ops.inbatch_ce_onepass(qb, db, temp, off, grad_out=gout)
+    torch.cuda.synchronize()
+    assert loss_b.item() == loss.item() and pm_b.item() == pm.item()
+    assert torch.equal(lse, lse_b) and torch.equal(dq, dq_b) and torch.equal(dd, dd_b)
+    sync = tt.ops._ONEPASS_SYNC[(torch.cuda.current_device(), Bq)]
+    assert int(sync[:4].view(torch.int32).item()) == 0
+
+
+@pytest.mark.parametrize("Bq,Bd,H,off", [(4096, 4096, 256, 0), (8192, 8192, 256, 0), (2048, 4096, 128, 2048), (4000, 4000, 64, 0),
+                                         (4096, 8192, 256, 4096), (300, 900, 128, 17)])
+def test_onepass_fused_normalise(Bq, Bd, H, off):
+    """dz form (what FusedTrainer consumes): dz = (dy - y (y.dy)) / |z| as bf16 rows + per-32-row column sums, from both
+    launches, against the fp64 normalise backward of the plain-form gradients."""
+    import two_towers_b200 as tt
+    from two_towers_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(Bq + H)
+    zq = torch.randn(Bq, H, device=DEV) * 3.0; zd = torch.randn(Bd, H, device=DEV) * 0.5
+    q = tt.ops.cast_bf16(torch.nn.functional.normalize(zq, dim=-1)); d = tt.ops.cast_bf16(torch.nn.functional.normalize(zd, dim=-1))
+    invq = (1.0 / zq.norm(dim=-1)).contiguous(); invd = (1.0 / zd.norm(dim=-1)).contiguous()
+    loss, lse, pm, dq, dd = tt.ops.inbatch_ce_onepass(q, d, 0.1, off)
+
+    def ref_dz(dy, y, inv):
+        dy = dy.double().cpu().numpy(); y = y.float().double().cpu().numpy(); inv = inv.double().cpu().numpy()
+        return (dy - y * (y * dy).sum(1, keepdims=True)) * inv[:, None]
+
+    def ref_cs(dz, rows):
+        pad = (-rows) % 32
+        a = np.concatenate([dz, np.zeros((pad, dz.shape[1]))]) if pad else dz
+        return a.reshape(-1, 32, dz.shape[1]).sum(1)
+
+    rq, rd = ref_dz(dq, q, invq), ref_dz(dd, d, invd)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: None if t is None else t.data_ptr()
+    dzq = torch.zeros(Bq, H, dtype=torch.bfloat16, device=DEV); dzd = torch.zeros(Bd, H, dtype=torch.bfloat16, device=DEV)
+    csq = torch.zeros((Bq + 31) // 32, H, device=DEV); csd = torch.zeros((Bd + 31) // 32, H, device=DEV)
+    sync = torch.zeros(int(lib.tt_inbatch_ce_onepass_sync_bytes(Bq)), dtype=torch.uint8, device=DEV)
+    loss2 = torch.zeros((), device=DEV); lse2 = torch.zeros(Bq, device=DEV)
+    qf = _lib.CePass(vp(q), Bq, vp(d), Bd, Bd, Bd, 0, 0, None, off, None, 0, vp(dzq), vp(csq), vp(invq))
+    df = _lib.CePass(vp(d), Bd, vp(q), Bq, Bq, Bq, 0, 0, vp(lse2), off, None, 0, vp(dzd), vp(csd), vp(invd))
+    keep = None
+    for it in range(2):
+        _lib.check(lib.tt_inbatch_ce_fwd_dq(C.byref(qf), H, 10.0, 10.0, 1.0 / Bq, None, vp(loss2), vp(lse2), None, vp(sync), s), "fwd_dq")
+        _lib.check(lib.tt_inbatch_ce_dd(C.byref(df), H, 10.0, 1.0 / Bq, None, s), "dd")
+        torch.cuda.synchronize()
+        if keep is None:
+            keep = (dzq.clone(), dzd.clone(), csq.clone(), csd.clone())
+    assert loss2.item() == loss.item() and torch.equal(lse2, lse)
+    print(f"  one-pass dz form Bq={Bq} Bd={Bd} H={H} off={off}")
+    check(dzq, rq, 1e-2, "dz (queries)"); check(dzd, rd, 1e-2, "dz (documents)")
+    check(csq, ref_cs(rq, Bq), BF16_RTOL, "column sums (queries)"); check(csd, ref_cs(rd, Bd), BF16_RTOL, "column sums (documents)")
+    assert torch.equal(dzq, keep[0]) and torch.equal(dzd, keep[1]) and torch.equal(csq, keep[2]) and torch.equal(csd, keep[3])
+
+
+def test_onepass_rejects_unbounded_logits():
+    from two_towers_b200 import _lib
+    lib = _lib.load()
+    assert lib.tt_inbatch_ce_onepass_ok(4096, 4096, 256, 10.0) == 1
+    assert lib.tt_inbatch_ce_onepass_ok(4096, 4096, 256, 100.0) == 0      # exp(-200) is not a normal fp32 number
+    assert lib.tt_inbatch_ce_onepass_ok(4096, 4096, 200, 10.0) == 0       # H % 64
+
+
+@pytest.mark.parametrize("B,tied", [(4096, True), (1024, False)])
+def test_trainer_onepass_matches_two_launch_path(B, tied, monkeypatch):
+    """FusedTrainer with the one-pass loss against the same trainer on the two-launch kernels: same loss trajectory and
+    parameters within bf16 noise over three optimizer steps."""
+    import two_towers_b200 as tt
+    from two_towers_b200.train import FusedTrainer
+
+    def run(onepass):
+        monkeypatch.setenv("TT_CE_ONEPASS", "1" if onepass else "0")
+        torch.manual_seed(7)
+        emb = tt.embeddings.build("lookup", 128, embedding_dim=64)
+        model = tt.build_two_tower("mean", emb, hidden_dim=256, tied_weights=tied).to(DEV)
+        tr = FusedTrainer(model, loss="in_batch", temperature=0.1, lr=1e-3, batch_size=B, max_len=64, precision="bf16",
+                          use_cuda_graph=False)
+        assert tr.onepass == onepass
+        g = torch.Generator(device="cpu").manual_seed(3)
+        losses = []
+        for _ in range(3):
+            qi = torch.randint(1, 128, (B, 64), generator=g); di = torch.randint(1, 128, (B, 64), generator=g)
+            losses.append(float(tr.step(qi, di).item()))
+        return losses, tr.flat.clone()
+
+    l1, p1 = run(True)
+    l0, p0 = run(False)
+    print(f"  trainer B={B} tied={tied}: one-pass {l1}  two-launch {l0}")
+    for a, b in zip(l1, l0):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b))
+    check(p1, p0.cpu().numpy(), 2e-3, "parameters after 3 steps")

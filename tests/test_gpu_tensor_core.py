@@ -250,7 +250,7 @@ def test_inbatch_bwd_fused_normalise(Bq, Bd, H, off):
     lse_col = torch.full((Bd,), float("inf"), device=DEV)     # d pass: positives only for documents off .. off+Bq
     # the d pass scores documents (x) against queries (y); lse is indexed by query
     qp = _lib.CePass(vp(q), Bq, vp(d), Bd, Bd, Bd, 0, 0, vp(lse), off, vp(pq_), Bq * H, None, None, None)
-    dp = _lib.CePass(vp(d), Bd, vp(q), Bq, Bq, Bq, 0, 0, vp(lse), -off, vp(pd_), Bd * H, None, None, None)
+    dp = _lib.CePass(vp(d), Bd, vp(q), Bq, Bq, Bq, 0, 0, vp(lse), off, vp(pd_), Bd * H, None, None, None)
     _lib.check(lib.tt_inbatch_ce_bwd_parts_ex(C.byref(qp), C.byref(dp), H, 10.0, 1.0 / Bq, None, n, s), "parts")
     dq = pq_.sum(0).double().cpu().numpy(); dd = pd_.sum(0).double().cpu().numpy()
     def ref_dz(dy, y, inv):
@@ -261,7 +261,7 @@ def test_inbatch_bwd_fused_normalise(Bq, Bd, H, off):
     dzq = torch.zeros(Bq, H, dtype=torch.bfloat16, device=DEV); dzd = torch.zeros(Bd, H, dtype=torch.bfloat16, device=DEV)
     csq = torch.zeros((Bq + 31) // 32, H, device=DEV); csd = torch.zeros((Bd + 31) // 32, H, device=DEV)
     qf = _lib.CePass(vp(q), Bq, vp(d), Bd, Bd, Bd, 0, 0, vp(lse), off, None, 0, vp(dzq), vp(csq), vp(invq))
-    df = _lib.CePass(vp(d), Bd, vp(q), Bq, Bq, Bq, 0, 0, vp(lse), -off, None, 0, vp(dzd), vp(csd), vp(invd))
+    df = _lib.CePass(vp(d), Bd, vp(q), Bq, Bq, Bq, 0, 0, vp(lse), off, None, 0, vp(dzd), vp(csd), vp(invd))
     for _ in range(2):
         _lib.check(lib.tt_inbatch_ce_bwd_parts_ex(C.byref(qf), C.byref(df), H, 10.0, 1.0 / Bq, None, n, s), "fused")
     torch.cuda.synchronize()

@@ -74,6 +74,15 @@ def main():
         "adamw": lambda: check(lib.tt_adamw_step(_p(tr.flat), _p(tr.flat_grad), _p(tr.exp_avg), _p(tr.exp_avg_sq), tr.n_params, 1e-3, 0.9, 0.999, 1e-8, 0.01, _p(tr.step_count), _p(tr.flat_bf16), s()), "x"),
         "whole_step": lambda: tr._step_impl(),
     }
+    if tr.onepass:                            # forward + dQ in one launch, dD in the other
+        vp = lambda t: None if t is None else t.data_ptr()
+        nb = B // 32
+        qp = _lib.CePass(vp(qb), B, vp(db), B, B, B, 0, 0, None, 0, None, 0, vp(tr.dz_bf16[:B]), vp(tr.dz_colsum[:nb]), vp(tr.inv_norm[:B]))
+        dp = _lib.CePass(vp(db), B, vp(qb), B, B, B, 0, 0, vp(tr.lse), 0, None, 0, vp(tr.dz_bf16[B:2 * B]), vp(tr.dz_colsum[nb:2 * nb]), vp(tr.inv_norm[B:2 * B]))
+        inv_t = 1.0 / tr.temperature
+        ops["ce_fwd"] = lambda: check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, inv_t, 1.0 / B, None, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), _p(tr.onepass_sync), s()), "x")
+        ops["ce_bwd"] = lambda: check(lib.tt_inbatch_ce_dd(C.byref(dp), H, inv_t, 1.0 / B, None, s()), "x")
+        ops = {("ce_fwd_dq" if k == "ce_fwd" else "ce_dd" if k == "ce_bwd" else k): v for k, v in ops.items()}
     if tr.embed_fused:
         del ops["embed_pool_bwd"]            # folded into the tower backward (tt_mlp_embed_t)
     total = 0.0

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtt_b200.so")
 TT_PREC_FP32 = 0
 TT_PREC_BF16 = 1
 TT_TOPK_MAX = 1024
-TT_ABI_VERSION = 3          # must equal TT_ABI_VERSION in include/tt_b200.h (a stale .so fails loudly at load)
+TT_ABI_VERSION = 4          # must equal TT_ABI_VERSION in include/tt_b200.h (a stale .so fails loudly at load)
 
 _vp, _i, _i64, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
 
@@ -95,6 +95,11 @@ SIGNATURES.update({
     "tt_inbatch_ce_bwd_fused_ok": (_i, [_i64, _i64, _i64, _i64, _i]),
     "tt_inbatch_ce_bwd_nparts_ex": (_i, [_i64, _i64, _i64, _i64, _i]),
     "tt_inbatch_ce_bwd_parts_ex": (_i, [C.POINTER(CePass), C.POINTER(CePass), _i, _f, _f, _vp, _i, _vp]),
+    "tt_inbatch_ce_onepass_ok": (_i, [_i64, _i64, _i, _f]),
+    "tt_inbatch_ce_onepass_sync_bytes": (_sz, [_i64]),
+    "tt_inbatch_ce_fwd_dq": (_i, [C.POINTER(CePass), _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tt_inbatch_ce_dd_nparts": (_i, [_i64, _i64, _i]),
+    "tt_inbatch_ce_dd": (_i, [C.POINTER(CePass), _i, _f, _f, _vp, _vp]),
 })
 
 _lib = None

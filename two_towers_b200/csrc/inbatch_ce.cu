@@ -492,6 +492,40 @@ int tt_inbatch_ce_bwd_fused_ok(int64_t q_x_rows, int64_t q_y_rows, int64_t d_x_r
   return tt::tc_inbatch_bwd_nparts2(q_x_rows, q_y_rows, d_x_rows, d_y_rows, H) <= 2 ? 1 : 0;
 }
 
+size_t tt_inbatch_ce_onepass_sync_bytes(int64_t Bq) { return Bq > 0 ? tt::tc_inbatch_onepass_sync_bytes(Bq) : 16; }
+
+int tt_inbatch_ce_onepass_ok(int64_t Bq, int64_t Bd, int H, float logit_bound) {
+  if (Bq <= 0 || Bd <= 0 || H <= 0) return 0;
+  return tt::tc_inbatch_onepass_ok(Bq, Bd, H, logit_bound);
+}
+
+int tt_inbatch_ce_fwd_dq(const tt_ce_pass_t* q_pass, int H, float inv_temperature, float logit_bound, float loss_scale,
+                         const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(q_pass && H > 0 && loss && lse && sync_scratch, "inbatch_ce_fwd_dq: bad arguments");
+  TT_CHECK_ARG(q_pass->x_bf16 && q_pass->y_bf16 && q_pass->x_rows > 0 && q_pass->y_rows > 0 && q_pass->y_buf_rows >= 1,
+               "inbatch_ce_fwd_dq: null operand");
+  TT_CHECK_ARG(q_pass->label_offset >= 0 && q_pass->x_rows + q_pass->label_offset <= q_pass->y_rows,
+               "inbatch_ce_fwd_dq: positives out of range");
+  return tt::tc_inbatch_fwd_dq(q_pass, H, inv_temperature, logit_bound, loss_scale, grad_out, loss, lse, pos_mean, sync_scratch,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int tt_inbatch_ce_dd_nparts(int64_t d_x_rows, int64_t d_y_rows, int H) {
+  if (d_x_rows <= 0 || d_y_rows <= 0 || H <= 0) return 1;
+  return tt::tc_inbatch_dd_nparts(d_x_rows, d_y_rows);
+}
+
+int tt_inbatch_ce_dd(const tt_ce_pass_t* d_pass, int H, float inv_temperature, float loss_scale, const float* grad_out,
+                     void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(d_pass && H > 0 && d_pass->x_bf16 && d_pass->y_bf16 && d_pass->lse && d_pass->x_rows > 0 && d_pass->y_rows > 0,
+               "inbatch_ce_dd: bad arguments");
+  TT_CHECK_ARG(d_pass->dz_bf16 ? (d_pass->dz_colsum && d_pass->inv_norm) : d_pass->out_parts != nullptr,
+               "inbatch_ce_dd: needs dz_bf16 + dz_colsum + inv_norm, or out_parts");
+  return tt::tc_inbatch_dd(d_pass, H, inv_temperature, loss_scale, grad_out, static_cast<cudaStream_t>(stream));
+}
+
 int tt_inbatch_ce_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temperature,
                                float loss_scale, const float* grad_out, int nparts, void* stream) {
   TT_REQUIRE_DEVICE();

@@ -143,6 +143,51 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, const
 __device__ __forceinline__ void st_cluster_f4(uint32_t cluster_addr, float a, float b, float c, float d) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+// 16-byte asynchronous global -> shared copy (LDGSTS); completes with cp.async.wait_group of the issuing thread
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// split cluster barrier WITHOUT memory ordering (the release / acquire forms compile to gpu-scope MEMBARs plus an L1
+// invalidate, ~1 us): used where only the peers' PROGRESS matters -- data handed over through cp.async.bulk / st.async is
+// ordered by the mbarrier it completes on
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_noacq() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+// asynchronous 8-byte store into a peer CTA's shared memory that completes (complete_tx, 8 bytes) on an mbarrier of that CTA
+__device__ __forceinline__ void st_async_f2(uint32_t dst_cluster_addr, float a, float b, uint32_t mbar_cluster_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(dst_cluster_addr), "f"(a), "f"(b), "r"(mbar_cluster_addr) : "memory");
+}
+// arrive on an mbarrier in a PEER CTA's shared memory; release at cluster scope: this thread's earlier st.shared::cluster
+// stores are visible to whoever observes the phase flip with a cluster-scope acquire (mbar_wait_cluster)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t mbar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (uint32_t spins = 1;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000ll) {
+      printf("tt_b200: cluster mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+// one L2 round trip instead of fence + atomic + fence: the ticket publishes this thread's earlier stores and
+// acquires those of every earlier ticket holder
+__device__ __forceinline__ unsigned atom_add_acq_rel_gpu(unsigned* p, unsigned v) {
+  unsigned r;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+  return r;
+}
 // registers -> TMEM, same 32 lanes x 32 columns shape as tmem_ld_x32
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(

@@ -18,6 +18,7 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "tc_common.cuh"
@@ -383,6 +384,15 @@ struct BwdParams {
   float coef;                  // loss_scale / temperature
   int dbg_pass;                // pass whose CTA (0,0) is stamped (TT_CE_DEBUG=<pass>)
   long long* dbg;              // optional timeline buffer (TT_CE_DEBUG=1): [role 0..1][tile][8] clock64 stamps of CTA (0,0,0)
+  int pass_base;               // pass = blockIdx.z + pass_base (1: only the dD pass is launched)
+  const __nv_bfloat16* yg[2];  // the Y operand in global memory (MODE 2 re-reads each row's positive from it)
+  // MODE 2 (one-pass forward + query gradient, tc_ce_fwd_dq_kernel): logits are bounded by mfix, so the softmax needs no
+  // running maximum -- E = exp(logit - mfix) is accumulated as it is produced and normalised once per row at the end.
+  float mfix;                  // >= every logit (logit units, i.e. already divided by the temperature)
+  float* lse_out;              // [Bx[0]] natural-log logsumexp (saved for the dD pass)
+  float* loss; float* pos_mean; float loss_scale;
+  unsigned* counter;           // one ticket counter, zero on entry, zero again on exit
+  float* tile_sums;            // [row tiles * splits][2]: sum(lse - pos), sum(pos)
 };
 
 // X rows = this CTA's 128 output rows, Y = streamed 128-row tiles.
@@ -399,9 +409,10 @@ constexpr int BWD_BN = 128;
 // (column lse read back from shared memory as broadcasts) takes longer than the two MMAs of a tile, so that pass -- and
 // with it the launch -- ran ~25 % behind the tensor pipe; the run-once tail (accumulator dump, normalise backward) is
 // also instruction-latency bound with one warp per scheduler.  Eight warps halve both.
-template <bool COL, int EW>
+template <int MODE, int EW>
 __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtensorMap* tmY, const BwdParams& p,
                                             uint8_t* base) {
+  constexpr bool COL = MODE == 1;                           // MODE 0: dQ from saved lse, 1: dD, 2: forward + dQ in one pass
   constexpr int PASS = COL ? 1 : 0;
   constexpr int NH = EW / 4;                                // warps per TMEM lane quarter
   constexpr int CW = BWD_BN / NH;                           // S columns per epilogue thread
@@ -429,8 +440,10 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   uint64_t* o_full = p_empty + 1;
   uint64_t* x_ready = o_full + 1;                         // X tile copied into TMEM (4 epilogue warps)
   uint64_t* xfer_bar = x_ready + 1;                       // fused tail: the peer CTA's accumulator half has landed here
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfer_bar + 1);
-  float* col_lse = reinterpret_cast<float*>(tmem_slot + 4);   // [2][128] column lse of the current / next Y tile (COL)
+  uint64_t* sc_bar = xfer_bar + 1;                        // MODE 2 tail: the peers' per-row scalars have landed here
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sc_bar + 1);
+  float* col_lse = reinterpret_cast<float*>(tmem_slot + 6);   // [2][128] column lse of the current / next Y tile (COL); 16-byte aligned
+  float* red_s = col_lse + 2 * BWD_BN;                    // [EW][2] MODE 2: per-warp loss partials
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t x0 = (int64_t)blockIdx.x * CE_BM;
@@ -438,9 +451,12 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   const int t_beg = blockIdx.y * tiles_per_split;
   const int t_end = min(ntiles, t_beg + tiles_per_split);
   const int nt = max(0, t_end - t_beg);
-  const bool fused = p.dz[PASS] != nullptr;               // CTA-uniform (cluster-uniform)
+  const bool fused = MODE == 2 || p.dz[PASS] != nullptr;  // CTA-uniform (cluster-uniform): finish through the cluster tail
+  float lsum = 0.f, pos_val = 0.f;                         // MODE 2: this thread's share of sum_j E_ij, its row's positive logit
+  bool pos_found = false;
   long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (int)blockIdx.z == p.dbg_pass) ? p.dbg : nullptr;
 #define TT_STAMP(role, tile, slot) do { if (dbg) dbg[((role) * 64 + (tile)) * 8 + (slot)] = clock64(); } while (0)
+#define TT_TAIL(k) do { if (dbg && threadIdx.x == 64) dbg[(64 + 40) * 8 + (k)] = clock64(); } while (0)
   // per-CTA wall-clock stamps (ns): kernel entry, X resident in TMEM, main loop done, outputs stored
   long long* cta_dbg = p.dbg ? p.dbg + 2 * 64 * 8 + 8 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
 #define TT_CTA_STAMP(slot) do { if (cta_dbg && threadIdx.x == 64) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); cta_dbg[slot] = t_; } } while (0)
@@ -456,7 +472,12 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     mbar_init(x_ready, EW);
     mbar_init(xfer_bar, 1);
     fence_barrier_init();
-    if (fused && gridDim.y == 2) mbar_arrive_expect_tx(xfer_bar, (uint32_t)(64 * (H + 4) * 4));   // armed long before the peer sends
+    // cluster tail: the peers' accumulator rows (bulk copies) and, MODE 2, per-row scalars (st.async) complete on this
+    // barrier; armed long before anybody sends
+    if (fused && gridDim.y > 1) {
+      const uint32_t rows = (gridDim.y - 1) * (CE_BM / gridDim.y);
+      mbar_arrive_expect_tx(xfer_bar, rows * (uint32_t)H * 2u + (MODE == 2 ? rows * 8u : 0u));   // fp16 partials
+    }
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -552,7 +573,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     const int64_t row = x0 + lrow;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float c = p.inv_temp * kLog2e;
-    const float row_lse = (!COL && row < Bx) ? lse[row] * kLog2e : 0.f;
+    const float row_lse = MODE == 2 ? p.mfix * kLog2e : (!COL && row < Bx) ? lse[row] * kLog2e : 0.f;
     // X tile: shared memory (TMA, 128B swizzle) -> registers -> TMEM (the TS-mode A operand of every S product)
     mbar_wait(x_bar, 0);
     for (int kb = half; kb < kq; kb += NH) {
@@ -597,6 +618,18 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);                 // S(i+1) may overwrite the accumulator
       if (threadIdx.x == 64) TT_STAMP(1, i, 2);
+      const bool in_band = y0 + BWD_BN > band_lo && y0 < band_lo + CE_BM;    // tile intersects the diagonal band
+      if (MODE == 2 && in_band) {                           // this row's positive logit, before the exponentials overwrite S
+        const int64_t pj = row + label_offset - y0 - col0;
+        if (pj >= 0 && pj < CW && y0 + col0 + pj < By && row < Bx) {
+          float pv = 0.f;
+#pragma unroll
+          for (int h = 0; h < HC; ++h)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pv = (32 * h + j == (int)pj) ? __uint_as_float(r[h][j]) : pv;
+          pos_val = pv; pos_found = true;
+        }
+      }
       // P = exp2(S*c - lse*log2e) (ragged columns: lse = +inf in COL mode, masked below otherwise), in place
 #pragma unroll
       for (int h = 0; h < HC; ++h)
@@ -616,7 +649,29 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
           for (int j = 0; j < 32; ++j)
             if (y0 + col0 + 32 * h + j >= By) r[h][j] = 0u;
       }
-      if (y0 + BWD_BN > band_lo && y0 < band_lo + CE_BM) {  // tile intersects the diagonal band
+      if (MODE == 2) {
+        // unnormalised row sums.  The positive's own E is kept OUT of both the P tile and the sum: the tail re-derives it
+        // from the saved logit and forms  dy = coef (O_off - L_off d_pos) / (L_off + E_pos)  -- the "P_ii - 1" factor is
+        // then -L_off / L, free of cancellation when the softmax is peaked on the positive
+        if (in_band) {
+          const int64_t pj = row + label_offset - y0 - col0;
+          if (pj >= 0 && pj < CW && y0 + col0 + pj < By) {
+#pragma unroll
+            for (int h = 0; h < HC; ++h)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[h][j] = (32 * h + j == (int)pj) ? 0u : r[h][j];
+          }
+        }
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int h = 0; h < HC; ++h)
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            s0 += __uint_as_float(r[h][j]); s1 += __uint_as_float(r[h][j + 1]);
+            s2 += __uint_as_float(r[h][j + 2]); s3 += __uint_as_float(r[h][j + 3]);
+          }
+        lsum += (s0 + s1) + (s2 + s3);
+      } else if (in_band) {
         const int64_t pj = (COL ? row - label_offset : row + label_offset) - y0 - col0;   // inside this thread's slice?
         if (pj >= 0 && pj < CW && y0 + col0 + pj < By) {
 #pragma unroll
@@ -681,186 +736,283 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       if (threadIdx.x == 64) TT_STAMP(1, 32 + cb, 3);
     }
     if (!fused) TT_CTA_STAMP(3);
+    if (MODE == 2) {
+      if (!pos_found) pos_val = -CUDART_INF_F;             // exactly one thread of the cluster holds each row's positive
+      if (NH == 2) {                                       // the two column halves of a row, fixed order (col_lse is idle in this mode)
+        float2* cmb = reinterpret_cast<float2*>(col_lse);
+        if (half == 1) cmb[lrow] = make_float2(lsum, pos_val);
+        asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
+        if (half == 0) { const float2 t = cmb[lrow]; lsum += t.x; pos_val = fmaxf(pos_val, t.y); cmb[lrow].x = lsum; }
+        asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
+        if (half == 1) lsum = cmb[lrow].x;                   // both halves scale their accumulator columns by the same 1 / lsum
+      }
+    }
   }
   if (fused) {
-    // ---- fused normalise backward.  The CTA pair (cluster) holds the two halves of dy = scale * (O_0 + O_1) in tensor
-    // memory.  Rank r finishes rows [64 r, 64 r + 64) of the tile.  Phase A: every epilogue thread dumps its accumulator
-    // row into local shared memory (the Y stages are idle now); the 64 rows the peer finishes then travel as two 32-row
-    // bulk copies (cp.async.bulk shared::cta -> shared::cluster) that complete on the peer's mbarrier.  Phase B: all four
-    // warps walk the rows, lanes across columns: coalesced shared reads, a shuffle tree for y.dy (y = the X rows, read
-    // back from global / L2), 256-byte coalesced bf16 stores.  A single split (no cluster) finishes all 128 rows itself.
-    const bool pair = gridDim.y == 2;
-    const uint32_t rank = pair ? cluster_ctarank() : 0u;
-    const int nfin = pair ? 64 : 128;                      // rows finished by this CTA
-    const int fin0 = pair ? 64 * (int)rank : 0;            // first tile row finished here
-    const int RS = H + 4;                                  // floats per staged accumulator row (conflict-free 16-byte rows)
-    float* own = reinterpret_cast<float*>(y_tiles);        // [nfin][RS]
-    float* recv = own + nfin * RS;                         // [64][RS]  pair only: filled by the peer
-    float* send = recv + 64 * RS;                          // [64][RS]  pair only: rows the peer finishes
-    float* cs_s = pair ? send + 64 * RS : own + nfin * RS; // [EW][H] column partials
-    if (pair) cluster_sync_all();                          // both CTAs' tensor pipes have retired: every Y stage is free
-    TT_CTA_STAMP(4);
-    if (warp >= 2) {
-      const int quarter = warp & 3, half = (warp - 2) >> 2;
-      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-      const int lrow = quarter * 32 + lane;
-      const bool mine = !pair || (quarter >> 1) == (int)rank;
-      float* dst_row = mine ? own + (lrow - fin0) * RS : send + (lrow & 63) * RS;
-      for (int cb = half; cb < H / 32; cb += NH) {             // the warps of a quarter share its 32 rows, alternating column chunks
-        uint32_t q[32];
-        if (nt > 0) {
-          tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) q[j] = 0u;
+    // ---- cluster tail.  The NS = gridDim.y CTAs of a row tile (one cluster; NS = 1, 2 or 4) each hold a partial
+    // accumulator O_k (128 x H fp32) in tensor memory; rank r finishes rows [NFIN r, NFIN r + NFIN), NFIN = 128 / NS.
+    //   A. every epilogue thread dumps its accumulator row into a local staging block (one block per TMEM lane quarter,
+    //      16-byte chunks XOR-swizzled by row: conflict-free for the row-per-lane writes here and the column-per-lane
+    //      reads below); quarters finished elsewhere then travel as 32-row bulk copies (cp.async.bulk shared::cta ->
+    //      shared::cluster) that complete on the finishing CTA's mbarrier.  MODE 2 also sends every row's share of the
+    //      softmax normaliser and the positive logit (st.async onto the same mbarrier).
+    //   B. the eight warps walk the finished rows, lanes across columns: partials added in rank order (bitwise
+    //      reproducible); MODE 2 forms dy = coef (O_off - L_off y_pos) / (L_off + E_pos) and lse / the loss partials;
+    //      the normalise backward  dz = (dy - y (y . dy)) * inv_norm  (y = the X rows, re-read from L2) leaves as bf16
+    //      rows plus per-32-row column sums (or, MODE 2 without dz, dy itself as fp32 rows).
+    // This code runs ONCE per CTA, so it is bound by cold instruction fetch and by memory round trips, not by arithmetic:
+    // it is specialised on NS (no run-time loops over ranks), keeps no release / acquire fences on its path (they compile
+    // to gpu-scope MEMBARs), issues every global load before the exchange, and hands the loss ticket to the idle TMA warp.
+    // The staging aliases the Y stages and the P tile: nobody may write into a peer before that peer has left its main
+    // loop (cluster barrier 1, arrive early / wait late), and nobody may exit while a peer still reads from it (barrier 2).
+    auto tail = [&](auto ns_tag) {
+      constexpr int NS = decltype(ns_tag)::value;
+      constexpr int NFIN = CE_BM / NS;                       // rows finished by this CTA (128, 64 or 32)
+      constexpr int QPR = 4 / NS;                            // TMEM lane quarters (32-row blocks) per rank
+      constexpr int RPW = NFIN / EW;                         // rows per epilogue warp (4, 8, 16; 32 with four warps)
+      const uint32_t rank = NS > 1 ? cluster_ctarank() : 0u;
+      const int fin0 = NFIN * (int)rank;                     // first tile row finished here
+      const int nch = H / 32;                                // 32-column chunks per row
+      // staging: [quarter][chunk] blocks of 32 rows x 32 columns fp16 (2 KB, 16-byte units XOR-swizzled by row pair)
+      uint8_t* stage = y_tiles;                              // [4][nch] blocks: this CTA's partial
+      uint8_t* recv = stage + 4 * nch * 2048;                // [NS - 1][QPR][nch] blocks: the other ranks' partials of MY rows
+      uint8_t* cs_b = recv + (NS - 1) * QPR * nch * 2048;
+      float* cs_s = reinterpret_cast<float*>(cs_b);          // [EW][H] column-sum partials
+      uint8_t* ybuf = cs_b + EW * H * 4;                     // [NFIN][H] bf16: y = the X rows of the rows finished here
+      uint8_t* pbuf = ybuf + NFIN * H * 2;                   // [NFIN][H] bf16: MODE 2, each row's positive row of Y
+      float2* lp2 = reinterpret_cast<float2*>(col_lse);      // [NS][NFIN] MODE 2: (share of sum_j E_ij, positive dot product or -inf)
+      const bool to_dz = p.dz[PASS] != nullptr;
+      const int e = warp - 2;
+      const int lc = lane * 4;                               // this lane's columns: lc .. lc + 3 and 128 + lc .. 128 + lc + 3
+      const bool c0 = lc < H, c1 = 128 + lc < H;
+      const int64_t gw0 = x0 + fin0 + e * RPW;               // first global row of this warp (epilogue warps)
+      TT_TAIL(0);
+      if (NS > 1) cluster_arrive_relaxed();                  // this CTA's tensor pipe has retired: its Y stages / P tile are free
+      float inv_n = 0.f;                                     // lane i: 1 / |z| of this warp's row i
+      if (warp >= 2) {
+        // this warp's rows of y (and, MODE 2, of the positives) -> shared memory, asynchronously: in flight under the dump
+        // and the exchange.  A rolled loop: this code runs once, every instruction of it is a cold fetch.
+        {
+          uint32_t pr = 0; int64_t pbase = 0;                // MODE 2: positive of row i = physical row pbase + pr
+          const uint32_t blk = (uint32_t)p.y_blk[PASS];
+          if (MODE == 2) {
+            const uint32_t g = (uint32_t)(gw0 + label_offset);
+            const uint32_t qb = g / blk;
+            pr = g - qb * blk; pbase = (int64_t)qb * p.y_blk_stride[PASS] + p.y_blk_off[PASS];
+          }
+          const bool cl = lane * 8 < H;                      // 16 bytes = 8 bf16 per lane
+#pragma unroll 1
+          for (int i = 0; i < RPW; ++i) {
+            const int64_t grow = gw0 + i;
+            if (grow < Bx && cl) {
+              if (to_dz) cp_async_16(ybuf + (e * RPW + i) * H * 2 + lane * 16, p.xg[PASS] + grow * H + lane * 8);
+              if (MODE == 2) cp_async_16(pbuf + (e * RPW + i) * H * 2 + lane * 16, p.yg[PASS] + (pbase + pr) * H + lane * 8);
+            }
+            if (MODE == 2 && ++pr == blk) { pr = 0; pbase += p.y_blk_stride[PASS]; }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
         }
+        if (to_dz && lane < RPW && gw0 + lane < Bx) inv_n = __ldg(p.inv_norm[PASS] + gw0 + lane);
+        // A. accumulator row -> fp16 (MODE 2: scaled by 1 / lsum so that every row is a convex combination of unit rows --
+        // the raw E-weighted sums can be far below the fp16 normal range), chunk by chunk; a chunk that another rank
+        // finishes leaves as a 2 KB bulk copy as soon as this warp has written it (the exchange runs under the dump)
+        const int quarter = warp & 3, half = e >> 2;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const int dst = quarter / QPR;                       // finishing rank of this warp's 32 rows (warp-uniform)
+        const int ql = quarter - dst * QPR;
+        const bool remote = NS > 1 && dst != (int)rank;
+        const int slot = (int)rank < dst ? (int)rank : (int)rank - 1;
+        const uint32_t peer_bar = remote ? mapa_shared(smem_u32(xfer_bar), (uint32_t)dst) : 0u;
+        const float rs = MODE == 2 ? (lsum > 0.f ? 1.0f / lsum : 0.f) : 1.0f;
+        const int sx = (lane >> 1) & 3;
+        bool waited = NS == 1;
+        for (int cb = half; cb < nch; cb += NH) {            // the warps of a quarter share its 32 rows, alternating column chunks
+          uint32_t q[32];
+          if (nt > 0) {
+            tmem_ld_x32(tmem_o + lane_addr + (uint32_t)(cb * 32), q);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst_row + cb * 32 + j) = make_float4(__uint_as_float(q[j]), __uint_as_float(q[j + 1]),
-                                                                          __uint_as_float(q[j + 2]), __uint_as_float(q[j + 3]));
-      }
-      if (!mine) {                                         // this quarter's 32 rows -> the same rows of the peer's recv buffer
-        fence_proxy_async_smem();
-        if (NH == 2) asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");   // both warps of the quarter have dumped
-        else __syncwarp();
-        if (lane == 0 && half == 0) {
-          const int r32 = (quarter & 1) * 32;
-          dsmem_bulk_copy(mapa_shared(smem_u32(recv + r32 * RS), rank ^ 1u), send + r32 * RS, (uint32_t)(32 * RS * 4),
-                          mapa_shared(smem_u32(xfer_bar), rank ^ 1u));
+            for (int j = 0; j < 32; ++j) q[j] = 0u;
+          }
+          uint8_t* blkp = stage + (quarter * nch + cb) * 2048;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 v;
+            v.x = pack_f16x2(__uint_as_float(q[8 * u + 0]) * rs, __uint_as_float(q[8 * u + 1]) * rs);
+            v.y = pack_f16x2(__uint_as_float(q[8 * u + 2]) * rs, __uint_as_float(q[8 * u + 3]) * rs);
+            v.z = pack_f16x2(__uint_as_float(q[8 * u + 4]) * rs, __uint_as_float(q[8 * u + 5]) * rs);
+            v.w = pack_f16x2(__uint_as_float(q[8 * u + 6]) * rs, __uint_as_float(q[8 * u + 7]) * rs);
+            *reinterpret_cast<uint4*>(blkp + lane * 64 + ((u ^ sx) << 4)) = v;
+          }
+          if (!waited) { TT_TAIL(1); cluster_wait_noacq(); waited = true; TT_TAIL(2); }   // every CTA of the cluster has left its main loop
+          if (remote) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0)
+              dsmem_bulk_copy(mapa_shared(smem_u32(recv + ((slot * QPR + ql) * nch + cb) * 2048), (uint32_t)dst), blkp, 2048u, peer_bar);
+          }
+        }
+        if (!waited) cluster_wait_noacq();
+        TT_CTA_STAMP(4);
+        if (MODE == 2 && half == 0) {
+          const int rloc = ql * 32 + lane;
+          if (remote) st_async_f2(mapa_shared(smem_u32(lp2 + (int)rank * NFIN + rloc), (uint32_t)dst), lsum, pos_val, peer_bar);
+          else lp2[(int)rank * NFIN + rloc] = make_float2(lsum, pos_val);
+        }
+        TT_TAIL(3);
+        asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");   // this CTA's own rows (and scalars) are staged
+        if (NS > 1) mbar_wait(xfer_bar, 0);                  // the peers' rows and scalars have landed
+        TT_TAIL(4);
+        TT_CTA_STAMP(6);
+        // lane i <-> this warp's row i: per-rank weights of the fp16 partials; MODE 2: softmax normaliser, lse, loss partials
+        float wk[NS], wpos = 0.f;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) wk[k] = 1.0f;
+        if (MODE == 2) {
+          float dl = 0.f, dpz = 0.f;
+          if (lane < RPW && gw0 + lane < Bx) {
+            const int r = e * RPW + lane;
+            float Loff = 0.f, pdot = -CUDART_INF_F;          // sum of the negatives' E (rank order), the positive's dot product
+#pragma unroll
+            for (int k = 0; k < NS; ++k) { const float2 t = lp2[k * NFIN + r]; wk[k] = t.x; Loff += t.x; pdot = fmaxf(pdot, t.y); }
+            const float epos = fast_exp2(fmaf(pdot, p.inv_temp * kLog2e, -p.mfix * kLog2e));   // the positive's E, as the main loop formed it
+            const float L = Loff + epos;
+            const float invL = 1.0f / L;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) wk[k] *= invL;      // O / L = sum_k (lsum_k / L) (O_k / lsum_k)
+            wpos = Loff * invL;                              // 1 - P_pos, free of cancellation
+            const float lse_r = p.mfix + logf(L), pl = pdot * p.inv_temp;
+            p.lse_out[gw0 + lane] = lse_r;
+            dl = lse_r - pl; dpz = pl;
+          }
+          dl = warp_sum(dl); dpz = warp_sum(dpz);
+          if (lane == 0) { red_s[2 * e] = dl; red_s[2 * e + 1] = dpz; }
+          asm volatile("bar.arrive 6, %0;" ::"n"(ETH + 32) : "memory");   // hand the partials to warp 0 (loss ticket)
+        }
+        const float scale = p.coef * (p.grad_out ? *p.grad_out : 1.0f);
+        float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0;
+        // per-lane addressing, hoisted: a warp's RPW rows lie inside ONE 32-row block, so the NS partial blocks are fixed
+        const int offA = c0 ? ((lane >> 3) * 2048) + ((lane & 1) << 3) : 0, offB = c1 ? ((4 + (lane >> 3)) * 2048) + ((lane & 1) << 3) : 0;
+        const int ux = (lane & 7) >> 1, qrow = (e * RPW) >> 5;
+        const uint8_t* srck[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+          srck[k] = k == (int)rank ? stage + ((int)rank * QPR + qrow) * nch * 2048 : recv + ((k < (int)rank ? k : k - 1) * QPR + qrow) * nch * 2048;
+        const int yoA = c0 ? lane * 8 : 0, yoB = c1 ? 256 + lane * 8 : 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();                                        // a warp reads back only the rows it copied itself
+#pragma unroll 1
+        for (int i = 0; i < RPW; ++i) {                      // ONE row per iteration of a rolled loop (cold code: keep it small)
+          const int r = e * RPW + i;                         // row among the NFIN rows finished here
+          const int64_t grow = gw0 + i;
+          const int rq = r & 31;
+          const int rowoff = rq * 64 + ((ux ^ ((rq >> 1) & 3)) << 4);
+          float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+#pragma unroll
+          for (int k = 0; k < NS; ++k) {                     // rank order
+            const uint2 h0 = *reinterpret_cast<const uint2*>(srck[k] + rowoff + offA), h1 = *reinterpret_cast<const uint2*>(srck[k] + rowoff + offB);
+            const float w = MODE == 2 ? __shfl_sync(0xffffffffu, wk[k], i) : 1.0f;
+            const float2 a0 = unpack_f16x2(h0.x), a1 = unpack_f16x2(h0.y), b0 = unpack_f16x2(h1.x), b1 = unpack_f16x2(h1.y);
+            o0.x = fmaf(a0.x, w, o0.x); o0.y = fmaf(a0.y, w, o0.y); o0.z = fmaf(a1.x, w, o0.z); o0.w = fmaf(a1.y, w, o0.w);
+            o1.x = fmaf(b0.x, w, o1.x); o1.y = fmaf(b0.y, w, o1.y); o1.z = fmaf(b1.x, w, o1.z); o1.w = fmaf(b1.y, w, o1.w);
+          }
+          if (MODE == 2) {
+            const uint2 pa = *reinterpret_cast<const uint2*>(pbuf + r * H * 2 + yoA), pb = *reinterpret_cast<const uint2*>(pbuf + r * H * 2 + yoB);
+            const float wp = -__shfl_sync(0xffffffffu, wpos, i);
+            o0.x = fmaf(wp, bf16lo_to_f32(pa.x), o0.x); o0.y = fmaf(wp, bf16hi_to_f32(pa.x), o0.y);
+            o0.z = fmaf(wp, bf16lo_to_f32(pa.y), o0.z); o0.w = fmaf(wp, bf16hi_to_f32(pa.y), o0.w);
+            if (c1) {
+              o1.x = fmaf(wp, bf16lo_to_f32(pb.x), o1.x); o1.y = fmaf(wp, bf16hi_to_f32(pb.x), o1.y);
+              o1.z = fmaf(wp, bf16lo_to_f32(pb.y), o1.z); o1.w = fmaf(wp, bf16hi_to_f32(pb.y), o1.w);
+            }
+          }
+          const bool valid = grow < Bx;                      // warp-uniform
+          if (to_dz) {
+            const uint2 ya = *reinterpret_cast<const uint2*>(ybuf + r * H * 2 + yoA), yb = *reinterpret_cast<const uint2*>(ybuf + r * H * 2 + yoB);
+            const float y0 = c0 ? bf16lo_to_f32(ya.x) : 0.f, y1 = c0 ? bf16hi_to_f32(ya.x) : 0.f, y2 = c0 ? bf16lo_to_f32(ya.y) : 0.f, y3 = c0 ? bf16hi_to_f32(ya.y) : 0.f;
+            const float y4 = c1 ? bf16lo_to_f32(yb.x) : 0.f, y5 = c1 ? bf16hi_to_f32(yb.x) : 0.f, y6 = c1 ? bf16lo_to_f32(yb.y) : 0.f, y7 = c1 ? bf16hi_to_f32(yb.y) : 0.f;
+            float dot = o0.x * y0;
+            dot = fmaf(o0.y, y1, dot); dot = fmaf(o0.z, y2, dot); dot = fmaf(o0.w, y3, dot);
+            dot = fmaf(o1.x, y4, dot); dot = fmaf(o1.y, y5, dot); dot = fmaf(o1.z, y6, dot); dot = fmaf(o1.w, y7, dot);
+            dot = warp_sum(dot);
+            const float si = scale * __shfl_sync(0xffffffffu, inv_n, i);
+            const float4 d0 = make_float4((o0.x - y0 * dot) * si, (o0.y - y1 * dot) * si, (o0.z - y2 * dot) * si, (o0.w - y3 * dot) * si);
+            const float4 d1 = make_float4((o1.x - y4 * dot) * si, (o1.y - y5 * dot) * si, (o1.z - y6 * dot) * si, (o1.w - y7 * dot) * si);
+            if (valid && c0) {
+              cs0.x += d0.x; cs0.y += d0.y; cs0.z += d0.z; cs0.w += d0.w;
+              *reinterpret_cast<uint2*>(p.dz[PASS] + grow * H + lc) = make_uint2(pack_bf16x2(d0.x, d0.y), pack_bf16x2(d0.z, d0.w));
+            }
+            if (valid && c1) {
+              cs1.x += d1.x; cs1.y += d1.y; cs1.z += d1.z; cs1.w += d1.w;
+              *reinterpret_cast<uint2*>(p.dz[PASS] + grow * H + 128 + lc) = make_uint2(pack_bf16x2(d1.x, d1.y), pack_bf16x2(d1.z, d1.w));
+            }
+          } else {                                           // MODE 2 without the normalise backward: dy rows as fp32
+            if (valid && c0) *reinterpret_cast<float4*>(p.out[PASS] + grow * H + lc) = make_float4(o0.x * scale, o0.y * scale, o0.z * scale, o0.w * scale);
+            if (valid && c1) *reinterpret_cast<float4*>(p.out[PASS] + grow * H + 128 + lc) = make_float4(o1.x * scale, o1.y * scale, o1.z * scale, o1.w * scale);
+          }
+        }
+        TT_TAIL(7);
+        if (to_dz) {
+          // per-32-row column sums: the 2 / 4 / 8 warps that share a 32-row block add their partials in warp order
+          constexpr int WPB = 32 / RPW > 0 ? 32 / RPW : 1;   // warps per 32-row block
+          if (WPB > 1) {
+            if (c0) *reinterpret_cast<float4*>(cs_s + e * H + lc) = cs0;
+            if (c1) *reinterpret_cast<float4*>(cs_s + e * H + 128 + lc) = cs1;
+            asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
+          }
+          TT_TAIL(8);
+          const int64_t blk_row = x0 + fin0 + (e / WPB) * 32;
+          if (e % WPB == 0 && blk_row < Bx) {
+#pragma unroll
+            for (int w2 = 1; w2 < WPB; ++w2) {               // fixed order: this warp's rows, then the following warps'
+              const float* o = cs_s + (e + w2) * H;
+              const float4 t0 = *reinterpret_cast<const float4*>(o + (c0 ? lc : 0)), t1 = *reinterpret_cast<const float4*>(o + (c1 ? 128 + lc : 0));
+              cs0.x += t0.x; cs0.y += t0.y; cs0.z += t0.z; cs0.w += t0.w;
+              cs1.x += t1.x; cs1.y += t1.y; cs1.z += t1.z; cs1.w += t1.w;
+            }
+            if (c0) *reinterpret_cast<float4*>(p.dz_colsum[PASS] + (blk_row >> 5) * H + lc) = cs0;
+            if (c1) *reinterpret_cast<float4*>(p.dz_colsum[PASS] + (blk_row >> 5) * H + 128 + lc) = cs1;
+          }
+        }
+        TT_TAIL(9);
+      } else {
+        if (NS > 1) cluster_wait_noacq();
+        if (MODE == 2 && warp == 0) {
+          // loss (the TMA warp is idle by now): this CTA's partial -> its slot; the CTA that takes the last ticket adds all
+          // slots in slot order.  One acq_rel atomic is the only gpu-scope fence of the kernel, and it is off the epilogue
+          // warps' path.
+          asm volatile("bar.sync 6, %0;" ::"n"(ETH + 32) : "memory");
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int k = 0; k < EW; ++k) { a += red_s[2 * k]; b += red_s[2 * k + 1]; }
+          const unsigned nslots = gridDim.x * (unsigned)NS;
+          unsigned ticket = 0;
+          if (lane == 0) {
+            const unsigned slot = blockIdx.x * (unsigned)NS + rank;
+            __stcg(p.tile_sums + 2 * slot, a); __stcg(p.tile_sums + 2 * slot + 1, b);
+            ticket = atom_add_acq_rel_gpu(p.counter, 1u);
+          }
+          ticket = __shfl_sync(0xffffffffu, ticket, 0);
+          if (ticket == nslots - 1) {
+            float tl = 0.f, tp = 0.f;
+            for (unsigned t = lane; t < nslots; t += 32) { tl += __ldcg(p.tile_sums + 2 * t); tp += __ldcg(p.tile_sums + 2 * t + 1); }
+            tl = warp_sum(tl); tp = warp_sum(tp);
+            if (lane == 0) {
+              *p.loss = tl * p.loss_scale;
+              if (p.pos_mean) *p.pos_mean = tp / (p.inv_temp * (float)Bx);
+              *p.counter = 0u;                                   // re-armed for the next launch
+            }
+          }
         }
       }
-    }
-    TT_CTA_STAMP(5);
-    const int e = warp - 2;
-    const int rpw = nfin / EW;                             // rows per warp: 64 or 128 rows over EW warps (8 .. 32)
-    const int steps = (H + 127) / 128;                     // lane -> columns step * 128 + 4 * lane .. + 3
-    const int64_t g0 = x0 + fin0 + e * rpw;                // first global row of this warp
-    const __nv_bfloat16* xg = p.xg[PASS];
-    // y (= the X rows, bf16) for 16 rows of this warp and 1/|z| of all its rows: issued before the waits below, so the
-    // global round trips overlap the peer's bulk copy instead of stalling every row group
-    uint2 ywa[16][2];
-    float my_inv = 0.f;
-    auto load_y16 = [&](int rbase) {
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int64_t grow = g0 + rbase + u;
-#pragma unroll
-        for (int st = 0; st < 2; ++st) {
-          const int c = st * 128 + lane * 4;
-          ywa[u][st] = make_uint2(0u, 0u);
-          if (rbase + u < rpw && st < steps && c < H && grow < Bx) ywa[u][st] = __ldg(reinterpret_cast<const uint2*>(xg + grow * H + c));
-        }
-      }
+      if (NS > 1) { cluster_arrive_relaxed(); cluster_wait_noacq(); }   // no CTA leaves while a peer's bulk copy may still read its staging
+      TT_TAIL(10);
+      TT_CTA_STAMP(3);
     };
-    if (warp >= 2) {
-      my_inv = (lane < rpw && g0 + lane < Bx) ? __ldg(p.inv_norm[PASS] + g0 + lane) : 0.f;
-      load_y16(0);
-    }
-    __syncthreads();                                       // own rows staged
-    if (warp >= 2 && pair) mbar_wait(xfer_bar, 0);         // peer's half has landed
-    TT_CTA_STAMP(6);
-    if (dbg && threadIdx.x == 64) dbg[(64 + 45) * 8 + 0] = clock64();
-    if (warp >= 2) {
-      const float scale = p.coef * (p.grad_out ? *p.grad_out : 1.0f);
-      float4 cs[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-      for (int i0 = 0; i0 < rpw; i0 += 4) {                // 4 rows at a time: their loads and shuffle trees interleave
-        if (i0 == 16) load_y16(16);                        // single split: second half of the warp's 32 rows
-#define TT_PB(slot) do { if (dbg && threadIdx.x == 64) dbg[(64 + 40 + (i0 >> 2)) * 8 + (slot)] = clock64(); } while (0)
-        TT_PB(0);
-        float4 o[4][2];
-        uint2 yw[4][2];
-        float dot[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int st = 0; st < 2; ++st) {
-            // ywa is indexed with compile-time constants only (registers): select the row group of this iteration
-            const int gsel = (i0 >> 2) & 3;
-            yw[u][st] = gsel == 0 ? ywa[u][st] : gsel == 1 ? ywa[4 + u][st] : gsel == 2 ? ywa[8 + u][st] : ywa[12 + u][st];
-          }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = e * rpw + i0 + u;
-#pragma unroll
-          for (int st = 0; st < 2; ++st) {
-            const int c = st * 128 + lane * 4;
-            o[u][st] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (st < steps && c < H) {
-              o[u][st] = *reinterpret_cast<const float4*>(own + r * RS + c);
-              if (pair) {
-                const float4 t = *reinterpret_cast<const float4*>(recv + r * RS + c);
-                o[u][st].x += t.x; o[u][st].y += t.y; o[u][st].z += t.z; o[u][st].w += t.w;
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float d = 0.f;
-#pragma unroll
-          for (int st = 0; st < 2; ++st) {
-            d = fmaf(o[u][st].x, __uint_as_float(yw[u][st].x << 16), d); d = fmaf(o[u][st].y, __uint_as_float(yw[u][st].x & 0xffff0000u), d);
-            d = fmaf(o[u][st].z, __uint_as_float(yw[u][st].y << 16), d); d = fmaf(o[u][st].w, __uint_as_float(yw[u][st].y & 0xffff0000u), d);
-          }
-          dot[u] = d;
-        }
-        TT_PB(1);
-#pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], sh);
-        }
-        TT_PB(2);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int64_t grow = g0 + i0 + u;
-          const float si = scale * __shfl_sync(0xffffffffu, my_inv, i0 + u);
-          if (grow < Bx) {                                 // warp-uniform
-#pragma unroll
-            for (int st = 0; st < 2; ++st) {
-              const int c = st * 128 + lane * 4;
-              if (st < steps && c < H) {
-                float4 d;
-                d.x = (o[u][st].x - __uint_as_float(yw[u][st].x << 16) * dot[u]) * si;          d.y = (o[u][st].y - __uint_as_float(yw[u][st].x & 0xffff0000u) * dot[u]) * si;
-                d.z = (o[u][st].z - __uint_as_float(yw[u][st].y << 16) * dot[u]) * si;          d.w = (o[u][st].w - __uint_as_float(yw[u][st].y & 0xffff0000u) * dot[u]) * si;
-                cs[st].x += d.x; cs[st].y += d.y; cs[st].z += d.z; cs[st].w += d.w;
-                *reinterpret_cast<uint2*>(p.dz[PASS] + grow * H + c) = make_uint2(pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
-              }
-            }
-          }
-        }
-      }
-      if (dbg && threadIdx.x == 64) dbg[(64 + 44) * 8 + 0] = clock64();
-      // per-32-row column sums: a warp's own block (32 rows per warp) or the sum of a warp pair (16 rows each)
-#pragma unroll
-      for (int st = 0; st < 2; ++st) {
-        const int c = st * 128 + lane * 4;
-        if (st < steps && c < H) *reinterpret_cast<float4*>(cs_s + e * H + c) = cs[st];
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(ETH) : "memory");
-      if (dbg && threadIdx.x == 64) dbg[(64 + 46) * 8 + 0] = clock64();
-      const int wpb = 32 / rpw;                              // warps that share one 32-row block of column sums (1, 2 or 4)
-      const bool writer = (e % wpb) == 0;
-      const int64_t blk_row = x0 + fin0 + (e / wpb) * 32;
-      if (writer && blk_row < Bx) {
-#pragma unroll
-        for (int st = 0; st < 2; ++st) {
-          const int c = st * 128 + lane * 4;
-          if (st < steps && c < H) {
-            float4 v = cs[st];
-            for (int w2 = 1; w2 < wpb; ++w2) {                 // fixed order: this warp's rows, then the following warps'
-              const float4 t = *reinterpret_cast<const float4*>(cs_s + (e + w2) * H + c);
-              v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-            }
-            *reinterpret_cast<float4*>(p.dz_colsum[PASS] + (blk_row >> 5) * H + c) = v;
-          }
-        }
-      }
-    }
-    TT_CTA_STAMP(3);
-    if (dbg && threadIdx.x == 64) dbg[(64 + 47) * 8 + 0] = clock64();
-    if (pair) cluster_sync_all();                          // neither CTA leaves while its peer may still read its send buffer
+    if (gridDim.y == 4) tail(std::integral_constant<int, 4>{});
+    else if (gridDim.y == 2) tail(std::integral_constant<int, 2>{});
+    else tail(std::integral_constant<int, 1>{});
   }
   tc_fence_before();
   __syncthreads();
@@ -874,10 +1026,19 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-  const int pass = blockIdx.z;
+  const int pass = blockIdx.z + p.pass_base;
   if ((int64_t)blockIdx.x * CE_BM >= p.Bx[pass] || (p.out[pass] == nullptr && p.dz[pass] == nullptr)) return;   // cluster-uniform: nothing to do for this pass
-  if (pass == 0) ce_bwd_body<false, EW>(&tmX0, &tmY0, p, base);
-  else           ce_bwd_body<true, EW>(&tmX1, &tmY1, p, base);
+  if (pass == 0) ce_bwd_body<0, EW>(&tmX0, &tmY0, p, base);
+  else           ce_bwd_body<1, EW>(&tmX1, &tmY1, p, base);
+}
+
+// forward + query gradient in one pass (MODE 2): grid = (row tiles, splits), one cluster per row tile
+__global__ void __launch_bounds__(64 + 8 * 32, 1)
+tc_ce_fwd_dq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
+  uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  ce_bwd_body<2, 8>(&tmX, &tmY, p, base);
 }
 
 static size_t fwd_smem(int H) {
@@ -887,7 +1048,7 @@ static size_t fwd_smem(int H) {
   return need > 120 * 1024 ? need : 120 * 1024;
 }
 static size_t bwd_smem(int H) {
-  const size_t need = 1024 + BWD_STAGES * (size_t)BWD_BN * H * 2 + (size_t)CE_BM * BWD_BN * 2 + 24 * 8 + 16 + 2 * BWD_BN * 4;
+  const size_t need = 1024 + BWD_STAGES * (size_t)BWD_BN * H * 2 + (size_t)CE_BM * BWD_BN * 2 + 26 * 8 + 16 + 2 * BWD_BN * 4 + 64;
   return need > 120 * 1024 ? need : 120 * 1024;          // one CTA per SM (every CTA allocates all 512 TMEM columns)
 }
 
@@ -913,6 +1074,13 @@ static int bwd_splits2(int64_t Bx0, int64_t By0, int64_t Bx1, int64_t By1) {
   return a < b ? a : b;
 }
 static int bwd_splits(int64_t Bq, int64_t Bd) { return bwd_splits2(Bq, Bd, Bd, Bq); }
+// cluster tail: the splits of a row tile form one cluster that finishes 128 / ns rows each -> ns in {1, 2, 4}
+static int cluster_splits(int64_t xtiles, int64_t By) {
+  const int64_t yt = ceil_div(By, tc::BWD_BN);
+  int ns = 1;
+  while (ns < 4 && xtiles * (ns * 2) <= kNumSMs && ns * 2 <= yt) ns *= 2;
+  return ns;
+}
 
 struct TcCePlan { int ns_f, ns_b; size_t qb, db, ml, pos, partial, total; };
 static TcCePlan plan_tc_ce(int64_t Bq, int64_t Bd, int H) {
@@ -1044,11 +1212,11 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
     p.y_blk[k] = ps[k]->y_blk > 0 ? ps[k]->y_blk : 1; p.y_blk_stride[k] = ps[k]->y_blk_stride; p.y_blk_off[k] = ps[k]->y_blk_off;
     p.tiles_per_split[k] = (int)ceil_div(ceil_div(ps[k]->By, tc::BWD_BN), nsplit);
     p.out[k] = ps[k]->out; p.part_stride[k] = ps[k]->part_stride;
-    p.dz[k] = ps[k]->dz; p.dz_colsum[k] = ps[k]->dz_colsum; p.inv_norm[k] = ps[k]->inv_norm; p.xg[k] = ps[k]->x;
+    p.dz[k] = ps[k]->dz; p.dz_colsum[k] = ps[k]->dz_colsum; p.inv_norm[k] = ps[k]->inv_norm; p.xg[k] = ps[k]->x; p.yg[k] = ps[k]->y;
   }
   const bool fused = pq.dz != nullptr || pd.dz != nullptr;
   if (fused) {
-    if (nsplit > 2) { set_error("tc_inbatch_bwd: the fused normalise backward needs <= 2 splits (got %d)", nsplit); return TT_ERR_UNSUPPORTED; }
+    if (nsplit != 1 && nsplit != 2 && nsplit != 4) { set_error("tc_inbatch_bwd: the fused normalise backward needs 1, 2 or 4 splits (got %d)", nsplit); return TT_ERR_UNSUPPORTED; }
     for (int k = 0; k < 2; ++k) {
       const bool any = ps[k]->dz || ps[k]->out;
       if (any && (!ps[k]->dz || !ps[k]->dz_colsum || !ps[k]->inv_norm)) { set_error("tc_inbatch_bwd: fused passes need dz, dz_colsum and inv_norm"); return TT_ERR_INVALID; }
@@ -1063,17 +1231,20 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
   TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
   long long* dbg_dev = nullptr;
-  const int64_t x0 = (pq.out || pq.dz) ? ceil_div(pq.Bx, tc::CE_BM) : 0, x1 = (pd.out || pd.dz) ? ceil_div(pd.Bx, tc::CE_BM) : 0;
-  const int nz = (pd.out || pd.dz) ? 2 : 1;              // pass 1 absent -> only z = 0 is launched
+  const bool has_q = pq.out || pq.dz, has_d = pd.out || pd.dz;
+  if (!has_q && !has_d) return TT_OK;
+  const int64_t x0 = has_q ? ceil_div(pq.Bx, tc::CE_BM) : 0, x1 = has_d ? ceil_div(pd.Bx, tc::CE_BM) : 0;
+  p.pass_base = has_q ? 0 : 1;                           // only the launched passes get CTAs
+  const int nz = (has_q && has_d) ? 2 : 1;
   dim3 grid((unsigned)(x0 > x1 ? x0 : x1), (unsigned)nsplit, (unsigned)nz);
   const size_t ncta = (size_t)grid.x * grid.y * grid.z, dbg_n = 2 * 64 * 8 + 8 * ncta;
   if (dbg_on) { p.dbg_pass = atoi(getenv("TT_CE_DEBUG")) == 1 ? 1 : 0; cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p.dbg = dbg_dev; }
   // fused + 2 splits: the two CTAs of a row tile form a cluster and exchange accumulator halves through shared memory
   if (ew == 8)
-    TT_CUDA(launch_kernel_cluster(tc::tc_ce_bwd_kernel<8>, grid, dim3(64 + 8 * 32), smem, s, true, (fused && nsplit == 2) ? 2u : 1u,
+    TT_CUDA(launch_kernel_cluster(tc::tc_ce_bwd_kernel<8>, grid, dim3(64 + 8 * 32), smem, s, true, fused ? (unsigned)nsplit : 1u,
                                   tmX0, tmY0, tmX1, tmY1, p));
   else
-    TT_CUDA(launch_kernel_cluster(tc::tc_ce_bwd_kernel<4>, grid, dim3(tc::CE_THREADS), smem, s, true, (fused && nsplit == 2) ? 2u : 1u,
+    TT_CUDA(launch_kernel_cluster(tc::tc_ce_bwd_kernel<4>, grid, dim3(tc::CE_THREADS), smem, s, true, fused ? (unsigned)nsplit : 1u,
                                   tmX0, tmY0, tmX1, tmY1, p));
   TT_LAUNCH_CHECK("tc_ce_bwd_kernel");
   if (dbg_on) {                                              // developer aid: per-tile timeline of CTA (0,0,0)
@@ -1093,11 +1264,9 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
       for (int k = 0; k < 6; ++k) printf(" %6lld", host[(1 * 64 + t) * 8 + k] ? host[(1 * 64 + t) * 8 + k] - t0 : -1);
       printf("\n");
     }
-    printf("[tt ce_bwd fused tail, cycles; last writer among CTAs] per 4-row group {begin, dots, shuffled}, then end:");
-    for (int g = 0; g < 4; ++g) printf("  %lld %lld %lld |", host[(64 + 40 + g) * 8 + 0] - t0, host[(64 + 40 + g) * 8 + 1] - t0, host[(64 + 40 + g) * 8 + 2] - t0);
-    printf("  %lld\n", host[(64 + 44) * 8 + 0] - t0);
-    printf("[tt ce_bwd fused tail, cycles] peer half landed %lld, column-sum barrier %lld, outputs stored %lld\n", host[(64 + 45) * 8 + 0] - t0,
-           host[(64 + 46) * 8 + 0] - t0, host[(64 + 47) * 8 + 0] - t0);
+    printf("[tt ce_bwd tail, cycles] loop_done sync1 dumped preloaded sync2 summed normalised rows_done colsum_bar colsum_done end:");
+    for (int k = 0; k <= 10; ++k) printf(" %lld", host[(64 + 40) * 8 + k] ? host[(64 + 40) * 8 + k] - t0 : -1);
+    printf("\n");
     printf("[tt ce_bwd O store, cycles] cb: tmem_loaded staged read stored\n");
     for (int cb = 0; cb < H / 32; ++cb) {
       printf("  %2d:", cb);
@@ -1113,6 +1282,97 @@ static int launch_tc_bwd(const CePass& pq, const CePass& pd, int H, float inv_te
              c[8 * i + 4] ? c[8 * i + 4] - g0 : -1, c[8 * i + 5] ? c[8 * i + 5] - g0 : -1, c[8 * i + 6] ? c[8 * i + 6] - g0 : -1);
   }
   return TT_OK;
+}
+
+// ---- one-pass step: forward + query gradient (MODE 2), then the document gradient as its own launch --------------
+size_t tc_inbatch_onepass_sync_bytes(int64_t Bq) {
+  return 16 + (size_t)ceil_div(Bq, tc::CE_BM) * 4 * 2 * 4;
+}
+int tc_inbatch_onepass_ok(int64_t Bq, int64_t Bd, int H, float logit_bound) {
+  // E = exp(logit - bound) must stay a normal fp32 / bf16 number for logit >= -bound
+  return (tc_ce_supported(H) && Bq > 0 && Bd > 0 && logit_bound > 0.f && 2.0f * logit_bound * tc::kLog2e < 120.0f) ? 1 : 0;
+}
+int tc_inbatch_dd_nparts(int64_t x_rows, int64_t y_rows) { return cluster_splits(ceil_div(x_rows, tc::CE_BM), y_rows); }
+
+int tc_inbatch_fwd_dq(const tt_ce_pass_t* t, int H, float inv_temp, float logit_bound, float loss_scale, const float* grad_out,
+                      float* loss, float* lse_out, float* pos_mean, void* sync_scratch, cudaStream_t s) {
+  if (!tc_inbatch_onepass_ok(t->x_rows, t->y_rows, H, logit_bound)) {
+    set_error("tc_inbatch_fwd_dq: needs H %% 64 == 0, H <= 256 and 2 * logit_bound * log2(e) < 120 (got H=%d bound=%g)", H, (double)logit_bound);
+    return TT_ERR_UNSUPPORTED;
+  }
+  const int64_t Bx = t->x_rows, By = t->y_rows;
+  const int64_t y_blk = t->y_blk > 0 ? t->y_blk : 1;
+  if (y_blk < By && y_blk % tc::BWD_BN != 0) { set_error("tc_inbatch_fwd_dq: y_blk must be a multiple of %d", tc::BWD_BN); return TT_ERR_UNSUPPORTED; }
+  const bool to_dz = t->dz_bf16 != nullptr;
+  if (to_dz && (!t->dz_colsum || !t->inv_norm)) { set_error("tc_inbatch_fwd_dq: dz needs dz_colsum and inv_norm"); return TT_ERR_INVALID; }
+  if (!to_dz && !t->out_parts) { set_error("tc_inbatch_fwd_dq: needs dz_bf16 or out_parts (dq)"); return TT_ERR_INVALID; }
+  CUtensorMap tmX, tmY;
+  int rc = tc::make_tmap_bf16(&tmX, t->x_bf16, (uint64_t)Bx, (uint64_t)H, tc::CE_BM); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmY, t->y_bf16, (uint64_t)t->y_buf_rows, (uint64_t)H, tc::BWD_BN); if (rc) return rc;
+  const int64_t xt = ceil_div(Bx, tc::CE_BM);
+  const int ns = cluster_splits(xt, By);
+  tc::BwdParams p{};
+  p.lse[0] = nullptr; p.Bx[0] = Bx; p.By[0] = By; p.label_offset[0] = t->label_offset;
+  p.y_blk[0] = y_blk; p.y_blk_stride[0] = t->y_blk_stride; p.y_blk_off[0] = t->y_blk_off;
+  p.tiles_per_split[0] = (int)ceil_div(ceil_div(By, tc::BWD_BN), ns);
+  p.out[0] = to_dz ? nullptr : t->out_parts; p.part_stride[0] = 0;
+  p.dz[0] = (__nv_bfloat16*)t->dz_bf16; p.dz_colsum[0] = t->dz_colsum; p.inv_norm[0] = t->inv_norm;
+  p.xg[0] = (const __nv_bfloat16*)t->x_bf16; p.yg[0] = (const __nv_bfloat16*)t->y_bf16;
+  p.H = H; p.inv_temp = inv_temp; p.grad_out = grad_out; p.coef = loss_scale * inv_temp;
+  p.mfix = logit_bound; p.lse_out = lse_out; p.loss = loss; p.pos_mean = pos_mean; p.loss_scale = loss_scale;
+  p.counter = static_cast<unsigned*>(sync_scratch);
+  p.tile_sums = reinterpret_cast<float*>(static_cast<char*>(sync_scratch) + 16);
+  const size_t smem = tc::bwd_smem(H);
+  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_fwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
+  dim3 grid((unsigned)xt, (unsigned)ns, 1);
+  long long* dbg_dev = nullptr;
+  const size_t ncta = (size_t)grid.x * grid.y, dbg_n = 2 * 64 * 8 + 8 * ncta;
+  if (dbg_on) { cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p.dbg = dbg_dev; p.dbg_pass = 0; }
+  TT_CUDA(launch_kernel_cluster(tc::tc_ce_fwd_dq_kernel, grid, dim3(64 + 8 * 32), smem, s, true, (unsigned)ns, tmX, tmY, p));
+  TT_LAUNCH_CHECK("tc_ce_fwd_dq_kernel");
+  if (dbg_on) {
+    std::vector<long long> h(dbg_n);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h.data(), dbg_dev, dbg_n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dbg_dev);
+    const long long* c = h.data() + 2 * 64 * 8;
+    long long g0 = 0;
+    for (size_t i = 0; i < ncta; ++i) if (c[8 * i] && (!g0 || c[8 * i] < g0)) g0 = c[8 * i];
+    printf("[tt ce_fwd_dq per-CTA, ns since first CTA start] grid %u x %u, %d tiles per CTA: start x_ready loop_done | sync1 dumped sync2 stored\n",
+           grid.x, grid.y, p.tiles_per_split[0]);
+    for (size_t i = 0; i < ncta; i += 7)
+      printf("  cta %3zu: %6lld %6lld %6lld | %6lld %6lld %6lld %6lld\n", i, c[8 * i] - g0, c[8 * i + 1] - g0, c[8 * i + 2] - g0,
+             c[8 * i + 4] - g0, c[8 * i + 5] - g0, c[8 * i + 6] - g0, c[8 * i + 3] - g0);
+    const long long t0 = h[0];
+    printf("[tt ce_fwd_dq tail, cycles] loop_done sync1 dumped preloaded sync2 summed normalised rows_done colsum_bar colsum_done end:");
+    for (int k = 0; k <= 10; ++k) printf(" %lld", h[(64 + 40) * 8 + k] ? h[(64 + 40) * 8 + k] - t0 : -1);
+    printf("\n");
+    const int ntl = p.tiles_per_split[0] < 12 ? p.tiles_per_split[0] : 12;
+    printf("[tt ce_fwd_dq timeline, cycles] tile: MMA{s_issue_begin,y_full,s_empty,s_issued,o_wait,p_full,o_issued} EPI{begin,s_full,loaded,computed,p_empty,p_written}\n");
+    for (int i = 0; i < ntl; ++i) {
+      printf("  %2d: MMA", i);
+      for (int k = 0; k < 7; ++k) printf(" %6lld", h[(0 * 64 + i) * 8 + k] ? h[(0 * 64 + i) * 8 + k] - t0 : -1);
+      printf("   EPI");
+      for (int k = 0; k < 6; ++k) printf(" %6lld", h[(1 * 64 + i) * 8 + k] ? h[(1 * 64 + i) * 8 + k] - t0 : -1);
+      printf("\n");
+    }
+  }
+  return TT_OK;
+}
+
+// document gradient alone: every field of tt_ce_pass_t is honoured; dz -> cluster tail, out_parts -> nparts slices
+int tc_inbatch_dd(const tt_ce_pass_t* t, int H, float inv_temp, float loss_scale, const float* grad_out, cudaStream_t s) {
+  if (!tc_ce_supported(H)) { set_error("tc_inbatch_dd: needs H %% 64 == 0, H <= 256"); return TT_ERR_UNSUPPORTED; }
+  CePass pd{};
+  pd.x = (const __nv_bfloat16*)t->x_bf16; pd.Bx = t->x_rows; pd.y = (const __nv_bfloat16*)t->y_bf16; pd.By = t->y_rows;
+  pd.y_buf_rows = t->y_buf_rows; pd.y_blk = t->y_blk; pd.y_blk_stride = t->y_blk_stride; pd.y_blk_off = t->y_blk_off;
+  pd.lse = t->lse; pd.label_offset = t->label_offset; pd.out = t->out_parts; pd.part_stride = t->part_stride;
+  pd.dz = (__nv_bfloat16*)t->dz_bf16; pd.dz_colsum = t->dz_colsum; pd.inv_norm = t->inv_norm;
+  if (pd.y_blk < pd.By && pd.y_blk % tc::BWD_BN != 0) { set_error("tc_inbatch_dd: y_blk must be a multiple of %d", tc::BWD_BN); return TT_ERR_UNSUPPORTED; }
+  CePass pq = pd;                                           // tensor maps need valid operands; the pass itself is not launched
+  pq.out = nullptr; pq.dz = nullptr; pq.dz_colsum = nullptr; pq.inv_norm = nullptr;
+  return launch_tc_bwd(pq, pd, H, inv_temp, tc_inbatch_dd_nparts(pd.Bx, pd.By), grad_out, loss_scale * inv_temp, s);
 }
 
 static CePass plain_pass(const __nv_bfloat16* x, int64_t Bx, const __nv_bfloat16* y, int64_t By, const float* lse, int64_t off,

@@ -276,6 +276,48 @@ def inbatch_ce_bwd(q, d, lse, temperature: float, label_offset: int = 0, loss_sc
     return dq, dd
 
 
+_ONEPASS_SYNC = {}
+
+
+def inbatch_ce_onepass(q_bf16: torch.Tensor, d_bf16: torch.Tensor, temperature: float, label_offset: int = 0,
+                       loss_scale: Optional[float] = None, grad_out: Optional[torch.Tensor] = None,
+                       logit_bound: Optional[float] = None):
+    """Loss forward and both gradients of the in-batch softmax (twotower/losses.py:107-116) in TWO launches on unit-norm
+    bf16 rows: ``tt_inbatch_ce_fwd_dq`` (forward + dq, S formed once, fixed softmax shift) and ``tt_inbatch_ce_dd``.
+    Returns (loss, lse, pos_mean, dq, dd) with fp32 gradients."""
+    _need_cuda(q_bf16, d_bf16, grad_out)
+    assert q_bf16.dtype == torch.bfloat16 and d_bf16.dtype == torch.bfloat16
+    lib = _lib_()
+    Bq, H = q_bf16.shape
+    Bd = d_bf16.shape[0]
+    dev = q_bf16.device
+    inv_t = 1.0 / float(temperature)
+    bound = inv_t if logit_bound is None else float(logit_bound)
+    if not lib.tt_inbatch_ce_onepass_ok(Bq, Bd, H, bound):
+        raise RuntimeError(f"inbatch_ce_onepass: unsupported (H={H}, logit bound {bound})")
+    scale = 1.0 / Bq if loss_scale is None else float(loss_scale)
+    key = (dev.index, Bq)
+    if key not in _ONEPASS_SYNC:
+        _ONEPASS_SYNC[key] = torch.zeros(int(lib.tt_inbatch_ce_onepass_sync_bytes(Bq)), dtype=torch.uint8, device=dev)
+    sync = _ONEPASS_SYNC[key]
+    f32 = dict(dtype=torch.float32, device=dev)
+    loss, lse, pm = torch.empty((), **f32), torch.empty(Bq, **f32), torch.empty((), **f32)
+    dq = torch.empty(Bq, H, **f32)
+    if grad_out is not None:
+        grad_out = _f32(grad_out)
+    qp = _lib.CePass(q_bf16.data_ptr(), Bq, d_bf16.data_ptr(), Bd, Bd, Bd, 0, 0, None, int(label_offset), dq.data_ptr(), 0,
+                     None, None, None)
+    check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, bound, scale, _p(grad_out), _p(loss), _p(lse), _p(pm), _p(sync),
+                                   _stream()), "tt_inbatch_ce_fwd_dq")
+    n = int(lib.tt_inbatch_ce_dd_nparts(Bd, Bq, H))
+    parts = torch.empty(n, Bd, H, **f32)
+    # document j is the positive of query j - label_offset (tt_ce_pass_t: "positive at row == col + off")
+    dp = _lib.CePass(d_bf16.data_ptr(), Bd, q_bf16.data_ptr(), Bq, Bq, Bq, 0, 0, lse.data_ptr(), int(label_offset),
+                     parts.data_ptr(), Bd * H, None, None, None)
+    check(lib.tt_inbatch_ce_dd(C.byref(dp), H, inv_t, scale, _p(grad_out), _stream()), "tt_inbatch_ce_dd")
+    return loss, lse, pm, dq, parts.sum(0) if n > 1 else parts[0]
+
+
 # --------------------------------------------------------------------------------------
 # K5 / K6
 # --------------------------------------------------------------------------------------

@@ -129,6 +129,14 @@ class FusedTrainer:
                              fast and (self.local_fast or self.global_fast) and B % 32 == 0 and self.passes == 2 and
                              self.lib.tt_inbatch_ce_bwd_fused_ok(B, Bg if self.global_fast else B, B,
                                                                  Bg if self.global_fast else B, self.H))
+        # one-pass step: unit-norm tower outputs bound every logit by 1/temperature, so the loss forward and the query
+        # gradient share ONE pass over S (tt_inbatch_ce_fwd_dq) and the document gradient is the only other loss launch
+        self.onepass = bool(os.environ.get("TT_CE_ONEPASS", "1") != "0" and os.environ.get("TT_CE_FUSED", "1") != "0" and fast and (self.local_fast or self.global_fast) and
+                            B % 32 == 0 and self.passes == 2 and
+                            self.lib.tt_inbatch_ce_onepass_ok(B, Bg if self.global_fast else B, self.H, 1.0 / self.temperature))
+        if self.onepass:
+            self.ce_fused = True
+            self.onepass_sync = torch.zeros(int(self.lib.tt_inbatch_ce_onepass_sync_bytes(B)), dtype=torch.uint8, device=self.dev)
         if self.ce_fused:
             self.dz_bf16 = torch.empty(R, self.H, dtype=torch.bfloat16, device=self.dev)
             self.dz_colsum = torch.empty(R // 32, self.H, **f32)
@@ -339,6 +347,8 @@ class FusedTrainer:
                 g_dq, g_dd = parallel.global_inbatch_bwd(q, d, d_glob, lse, self.temperature, ops, self.group, self.prec)
                 dq.copy_(g_dq)
                 dd.copy_(g_dd)
+            elif self.onepass:
+                self._local_loss_onepass(s)
             else:
                 self._local_loss_fwd(s)
                 self._local_loss_bwd(s)
@@ -379,6 +389,22 @@ class FusedTrainer:
             check(lib.tt_inbatch_ce_fwd(_p(q), _p(d), _p(qb), _p(db), B, B, H, inv_t, 0, scale, _p(self.loss),
                                         _p(self.lse), _p(self.pos_mean), self.prec, _p(self.ws), self.ws.numel(), s),
                   "tt_inbatch_ce_fwd")
+
+    def _local_loss_onepass(self, s):
+        """Two loss launches: forward + query gradient in one pass over S, then the document gradient; both finish the
+        normalise backward themselves (dz + column sums for the tower backward)."""
+        lib, B, H = self.lib, self.B, self.H
+        inv_t, scale = 1.0 / self.temperature, 1.0 / (B * self.world)
+        qb, db = self.y_bf16[:B], self.y_bf16[B:2 * B]
+        vp = lambda t: None if t is None else t.data_ptr()
+        nb = B // 32
+        qp = _lib.CePass(vp(qb), B, vp(db), B, B, B, 0, 0, None, 0, None, 0,
+                         vp(self.dz_bf16[:B]), vp(self.dz_colsum[:nb]), vp(self.inv_norm[:B]))
+        check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, inv_t, scale, None, _p(self.loss), _p(self.lse),
+                                       _p(self.pos_mean), _p(self.onepass_sync), s), "tt_inbatch_ce_fwd_dq")
+        dp = _lib.CePass(vp(db), B, vp(qb), B, B, B, 0, 0, vp(self.lse), 0, None, 0,
+                         vp(self.dz_bf16[B:2 * B]), vp(self.dz_colsum[nb:2 * nb]), vp(self.inv_norm[B:2 * B]))
+        check(lib.tt_inbatch_ce_dd(C.byref(dp), H, inv_t, scale, None, s), "tt_inbatch_ce_dd")
 
     def _local_loss_bwd(self, s):
         """Both loss gradients in one launch: fused with the normalise backward (dz + column sums), or as per-split
@@ -428,9 +454,16 @@ class FusedTrainer:
             d_all, d_rows, d_blk, d_stride, d_off = self.yg_bf16, W * 2 * B, B, 2 * B, B  # [Q_r | D_r] blocks, indexed in place
             q_all, q_off = self.yg_bf16, 0
         scale = 1.0 / Bg
-        check(lib.tt_inbatch_ce_fwd_ex(_p(self.y_bf16[:B]), B, _p(d_all), Bg, d_rows, d_blk, d_stride, d_off, H, inv_t,
-                                       self.rank * B, scale, _p(self.loss), _p(self.lse), _p(self.pos_mean),
-                                       _p(self.ce_ws), self.ce_ws.numel(), _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
+        nb = B // 32
+        if self.onepass:                                    # forward + query gradient in one pass over S
+            qp = _lib.CePass(vp(self.y_bf16[:B]), B, vp(d_all), Bg, d_rows, d_blk, d_stride, d_off, None, self.rank * B, None, 0,
+                             vp(self.dz_bf16[:B]), vp(self.dz_colsum[:nb]), vp(self.inv_norm[:B]))
+            check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, inv_t, scale, None, _p(self.loss), _p(self.lse),
+                                           _p(self.pos_mean), _p(self.onepass_sync), s), "tt_inbatch_ce_fwd_dq")
+        else:
+            check(lib.tt_inbatch_ce_fwd_ex(_p(self.y_bf16[:B]), B, _p(d_all), Bg, d_rows, d_blk, d_stride, d_off, H, inv_t,
+                                           self.rank * B, scale, _p(self.loss), _p(self.lse), _p(self.pos_mean),
+                                           _p(self.ce_ws), self.ce_ws.numel(), _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
         if self.p2p:
             self.x_lse.allgather(self.lse)
             if self._lse_pack:
@@ -438,7 +471,12 @@ class FusedTrainer:
             torch.cuda.current_stream().wait_stream(self._side)          # Q of every rank has arrived
         else:
             dist.all_gather_into_tensor(self.lse_g, self.lse, group=self.group)
-        nb = B // 32
+        if self.onepass:
+            dp = _lib.CePass(vp(self.y_bf16[B:2 * B]), B, vp(q_all), Bg, d_rows, d_blk, d_stride, q_off, vp(self.lse_g),
+                             -self.rank * B, None, 0,
+                             vp(self.dz_bf16[B:2 * B]), vp(self.dz_colsum[nb:2 * nb]), vp(self.inv_norm[B:2 * B]))
+            check(lib.tt_inbatch_ce_dd(C.byref(dp), H, inv_t, scale, None, s), "tt_inbatch_ce_dd")
+            return
         fz = (lambda a, b, c: (vp(a), vp(b), vp(c))) if self.ce_fused else (lambda a, b, c: (None, None, None))
         qp = _lib.CePass(vp(self.y_bf16[:B]), B, vp(d_all), Bg, d_rows, d_blk, d_stride, d_off, vp(self.lse), self.rank * B,
                          vp(self.dy[:B]), self.dy_part_stride,

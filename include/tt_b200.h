@@ -355,6 +355,13 @@ int tt_p2p_sum_slots(const tt_p2p_t* x, size_t n_floats, float* out, void* strea
 int tt_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                   int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
                   int64_t* step_count, void* param_bf16, void* stream);
+/* Same step; in addition the kernel copies the scalar *publish_src (e.g. the step's loss, twotower/train.py:139
+ * loss.item()) to *publish_dst, which may be MAPPED PINNED HOST memory: the value reaches the host from inside the
+ * step's last launch, so a captured step needs no device-to-host copy node.  Both null == tt_adamw_step. */
+int tt_adamw_step_publish(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                          int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
+                          int64_t* step_count, void* param_bf16, const float* publish_src, float* publish_dst,
+                          void* stream);
 
 /* ---- self-test hook -------------------------------------------------------------------------
  * C[M,N] (fp32) = A * B on the tcgen05 tensor cores; used by the GPU tests to pin the UMMA / TMA

@@ -7,7 +7,7 @@ O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader > $O/${TAG}_gpu.txt 2>&1
 # one pytest process per file: a kernel fault (sticky CUDA error) in one file cannot poison the others
 : > $O/${TAG}_pytest.log
-for f in tests/test_gpu_parity.py tests/test_gpu_tensor_core.py tests/test_gpu_round2.py tests/test_plumbing.py tests/test_gpu_multi.py; do
+for f in tests/test_gpu_parity.py tests/test_gpu_tensor_core.py tests/test_gpu_round2.py tests/test_gpu_onepass.py tests/test_plumbing.py tests/test_gpu_multi.py; do
   timeout 900 python -m pytest $f -m gpu -q -s --maxfail=40 "$@" >> $O/${TAG}_pytest.log 2>&1; echo "pytest $f exit $?" | tee -a $O/${TAG}_pytest.log
 done
 grep -E "^FAILED|passed|failed|error" $O/${TAG}_pytest.log | tail -30 | cut -c1-200

@@ -27,7 +27,8 @@ def timed(fn, flush, reps=43):
         fn()
     ts = []
     for i in range(reps):
-        flush.add_(1)
+        if FLUSH_MODE != "none":
+            flush.add_(1)
         if FLUSH_MODE == "write_read":          # read a second buffer: dirty lines are written back, L2 is cold AND clean
             FLUSH_SINK.append(float(0) if FLUSH_BUF2 is None else 0.0)
             torch.sum(FLUSH_BUF2, dtype=torch.float32)
@@ -43,7 +44,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--B", type=int, default=4096)
-    ap.add_argument("--flush", default="write", choices=["write", "write_read"])
+    ap.add_argument("--flush", default="write", choices=["write", "write_read", "none"])
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     global FLUSH_MODE, FLUSH_BUF2

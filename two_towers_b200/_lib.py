@@ -57,6 +57,7 @@ SIGNATURES = {
     "tt_cast_f32_to_bf16": (_i, [_vp, _vp, _i64, _vp]),
     "tt_selftest_tc_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "tt_adamw_step": (_i, [_vp] * 4 + [_i64] + [C.c_double] * 5 + [_vp, _vp, _vp]),
+    "tt_adamw_step_publish": (_i, [_vp] * 4 + [_i64] + [C.c_double] * 5 + [_vp, _vp, _vp, _vp, _vp]),
 }
 
 class MlpEmbed(C.Structure):

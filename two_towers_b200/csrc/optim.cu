@@ -12,11 +12,14 @@ namespace tt {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              int64_t n, double lr, double beta1, double beta2, double eps, double wd,
-             int64_t* step_count, __nv_bfloat16* __restrict__ p_bf16, int vec_ok) {
+             int64_t* step_count, __nv_bfloat16* __restrict__ p_bf16, int vec_ok,
+             const float* __restrict__ publish_src, float* publish_dst) {
   // scalars are formed in double (as Python does in torch.optim) and rounded to fp32 once
   __shared__ float s_neg_step_size, s_sqrt_bc2;
   pdl_trigger();
   pdl_wait();
+  // the step's loss leaves for the host from here (publish_dst: mapped pinned memory): no copy node in the captured step
+  if (publish_dst && blockIdx.x == 0 && threadIdx.x == 0) *publish_dst = *publish_src;
   if (threadIdx.x == 0) {
     const double t = (double)(*step_count + 1);
     const double bc1 = 1.0 - pow(beta1, t);
@@ -69,10 +72,12 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 
 }  // namespace tt
 
-extern "C" int tt_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                             double lr, double beta1, double beta2, double eps, double weight_decay,
-                             int64_t* step_count, void* param_bf16, void* stream) {
+extern "C" int tt_adamw_step_publish(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                     double lr, double beta1, double beta2, double eps, double weight_decay,
+                                     int64_t* step_count, void* param_bf16, const float* publish_src, float* publish_dst,
+                                     void* stream) {
   TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG((publish_src == nullptr) == (publish_dst == nullptr), "adamw_step: publish_src and publish_dst go together");
   TT_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step_count && n >= 0, "adamw_step: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int64_t blocks = tt::ceil_div(n > 0 ? n : 1, 1024);         // 4 parameters per thread and iteration
@@ -81,7 +86,14 @@ extern "C" int tt_adamw_step(float* param, const float* grad, float* exp_avg, fl
                        reinterpret_cast<uintptr_t>(exp_avg_sq);
   const int vec_ok = ((al & 15) == 0 && (reinterpret_cast<uintptr_t>(param_bf16) & 7) == 0) ? 1 : 0;
   TT_CUDA(tt::launch_kernel(tt::adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, s, true, param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
-                            beta2, eps, weight_decay, step_count, (__nv_bfloat16*)param_bf16, vec_ok));
+                            beta2, eps, weight_decay, step_count, (__nv_bfloat16*)param_bf16, vec_ok, publish_src, publish_dst));
   TT_LAUNCH_CHECK("adamw_kernel");
   return TT_OK;
+}
+
+extern "C" int tt_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             double lr, double beta1, double beta2, double eps, double weight_decay,
+                             int64_t* step_count, void* param_bf16, void* stream) {
+  return tt_adamw_step_publish(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_count, param_bf16,
+                               nullptr, nullptr, stream);
 }

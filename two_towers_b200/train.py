@@ -99,6 +99,11 @@ class FusedTrainer:
         # ---- static activations -------------------------------------------------------------
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.ids = torch.zeros(R, L, dtype=id_dtype, device=self.dev)
+        # input pipelining (prefetch / step): TWO static id buffers, each with its own captured graph and loss slot, so a
+        # host->device copy lands directly in the buffer the next replay reads (no staging copy on the step's stream)
+        self._ids_bufs = [self.ids, None]
+        self._ids_cur = self.ids
+        self._loss_dst = None
         self.pooled = torch.empty(R, self.E, **f32)
         self.inv_len = torch.empty(R, **f32)
         self.y = torch.empty(R, self.H, **f32)
@@ -228,6 +233,9 @@ class FusedTrainer:
                  lib.tt_inbatch_ce_workspace(B * self.world, B * self.world, self.H, self.prec))
         self.ws = torch.empty(int(nb), dtype=torch.uint8, device=self.dev)
         self._loss_ring = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]   # read_loss_async()
+        self._loss_ring_g = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]  # written by graph 0 / 1
+        self._graphs: List[Optional[torch.cuda.CUDAGraph]] = [None, None]
+        self._last_gi = -1                                  # graph of the last pipelined step (-1: explicit-ids step)
         self._loss_ev = [torch.cuda.Event() for _ in range(2)]
         self._loss_slot = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -330,7 +338,7 @@ class FusedTrainer:
         idb = 8 if self.ids.dtype == torch.int64 else 4
         s = self._stream()
         tower_pools = self.embed_in_tower                 # histogram only: the tower kernel multiplies P by the table
-        check(lib.tt_embed_pool_fwd(_p(self.ids), idb, _p(self.table), R, self.L, self.V, self.E,
+        check(lib.tt_embed_pool_fwd(_p(self._ids_cur), idb, _p(self.table), R, self.L, self.V, self.E,
                                     None if tower_pools else _p(self.pooled), _p(self.inv_len),
                                     None if tower_pools else _p(self.pooled_bf16), _p(self.pool_bf16), s), "tt_embed_pool_fwd")
         for gi in range(len(self.groups)):
@@ -362,7 +370,7 @@ class FusedTrainer:
         for gi in range(len(self.groups)):
             self._tower_bwd(gi)
         if self.train_table and not self.embed_fused:
-            check(lib.tt_embed_pool_bwd(_p(self.ids), idb, _p(self.inv_len), _p(self.dpooled), R, self.L, self.V,
+            check(lib.tt_embed_pool_bwd(_p(self._ids_cur), idb, _p(self.inv_len), _p(self.dpooled), R, self.L, self.V,
                                         self.E, _p(self.table.grad), _p(self.ws), self.ws.numel(), s),
                   "tt_embed_pool_bwd")
         if self.p2p_grad:
@@ -370,9 +378,12 @@ class FusedTrainer:
             self.x_grad.sum_slots(self.flat_grad)           # sum everywhere: bitwise identical parameters on all ranks
         elif self.world > 1:
             parallel.allreduce_sum_(self.flat_grad, self.group)
-        check(lib.tt_adamw_step(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
-                                self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                _p(self.step_count), _p(self.flat_bf16), s), "tt_adamw_step")
+        # pipelined mode: the loss reaches the host (mapped pinned slot) from inside the step's last launch
+        pub = self._loss_dst
+        check(lib.tt_adamw_step_publish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                        self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                        _p(self.step_count), _p(self.flat_bf16), _p(self.loss) if pub is not None else None,
+                                        _p(pub), s), "tt_adamw_step")
 
     def _local_loss_fwd(self, s):
         """In-batch loss forward against the local documents (one launch on the tensor-core path)."""
@@ -501,67 +512,86 @@ class FusedTrainer:
 
     # ---- input pipelining: the next batch's host->device copy overlaps the current step ------------------
     def prefetch(self, q_ids: torch.Tensor, d_ids: torch.Tensor, n_ids: Optional[torch.Tensor] = None) -> None:
-        """Start copying the NEXT batch (pinned host or device tensors, [B,L]) into a staging buffer on a
-        separate copy stream.  `step()` with no arguments then consumes it.  One batch may be in flight."""
-        if self._stage is None:
-            self._stage = torch.empty_like(self.ids)
+        """Start copying the NEXT batch (pinned host or device tensors, [B,L]) on a separate copy stream, straight into
+        the static id buffer the next `step()` (no arguments) will read: two buffers alternate, each with its own captured
+        graph, so the step's own stream carries no staging copy.  One batch may be in flight."""
+        if self._ids_bufs[1] is None:
+            self._ids_bufs[1] = torch.zeros_like(self.ids)
             self._copy_stream = torch.cuda.Stream(device=self.dev)
-            self._copy_done = torch.cuda.Event()
-            self._stage_free = torch.cuda.Event()
-            self._stage_free.record(torch.cuda.current_stream())
+            self._copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._buf_free = [torch.cuda.Event(), torch.cuda.Event()]
+            for ev in self._buf_free:
+                ev.record(torch.cuda.current_stream())
+            self._pf_idx = 1                                # buffer 0 doubles as the explicit-ids buffer: start with 1
         B = self.B
         parts = [q_ids, d_ids] + ([n_ids] if self.passes == 3 else [])
         if self.passes == 3 and n_ids is None:
             raise ValueError("triplet loss needs negative ids")
-        with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(self._stage_free)          # previous consumer has read the staging buffer
-            for i, t in enumerate(parts):
-                if tuple(t.shape) != (B, self.L):
-                    raise ValueError(f"expected ids of shape {(B, self.L)}, got {tuple(t.shape)}")
-                self._stage[i * B:(i + 1) * B].copy_(t, non_blocking=True)
-            self._copy_done.record(self._copy_stream)
-        self._staged = True
+        if self._staged is not False:
+            raise RuntimeError("prefetch(): the previous batch has not been consumed by step() yet")
+        t = self._pf_idx
+        buf = self._ids_bufs[t]
+        cs = self._copy_stream
+        cs.wait_event(self._buf_free[t])                    # the last replay that read this buffer has finished
+        with torch.cuda.stream(cs):
+            for i, x in enumerate(parts):
+                if tuple(x.shape) != (B, self.L):
+                    raise ValueError(f"expected ids of shape {(B, self.L)}, got {tuple(x.shape)}")
+                buf[i * B:(i + 1) * B].copy_(x, non_blocking=True)
+        self._copy_done[t].record(cs)
+        self._staged = t
+        self._pf_idx = t ^ 1
 
-    def _consume_prefetched(self) -> None:
-        if not self._staged:
+    def _consume_prefetched(self) -> int:
+        if self._staged is False:
             raise RuntimeError("step() without arguments needs a prefetch() first")
-        cur = torch.cuda.current_stream()
-        cur.wait_event(self._copy_done)
-        self.ids.copy_(self._stage, non_blocking=True)              # device-to-device into the graph's static buffer
-        self._stage_free.record(cur)
+        t = self._staged
+        torch.cuda.current_stream().wait_event(self._copy_done[t])
         self._staged = False
+        return t
 
-    def run(self) -> torch.Tensor:
-        """One optimizer step on the batch currently in the static buffer; returns the loss (device scalar)."""
+    def run(self, gi: int = 0) -> torch.Tensor:
+        """One optimizer step on the batch currently in static id buffer `gi` (0: the buffer load_batch() fills); returns
+        the loss (device scalar)."""
+        self._ids_cur = self._ids_bufs[gi]
+        self._loss_dst = self._loss_ring_g[gi]
         if not self.use_graph:
             self._step_impl()
-        elif self.graph is None:
-            # warm-up outside capture (module loading, workspace sizing, NCCL communicators) ...
-            st = self._snapshot()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self._step_impl()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            # ... restore the state the warm-up step changed, then capture and replay once
-            self._restore(st)
+        elif self._graphs[gi] is None:
+            if self._graphs[0] is None and self._graphs[1] is None:
+                # warm-up outside capture (module loading, workspace sizing, NCCL communicators) ...
+                st = self._snapshot()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._step_impl()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                # ... restore the state the warm-up step changed, then capture and replay once
+                self._restore(st)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._step_impl()
-            self.graph = g
+            self._graphs[gi] = g
+            self.graph = self._graphs[0] if self._graphs[0] is not None else g
             g.replay()
         else:
-            self.graph.replay()
+            self._graphs[gi].replay()
+        self._ids_cur = self.ids
+        self._loss_dst = None
         self.steps_done += 1
         return self.loss
 
     def step(self, q_ids=None, d_ids=None, n_ids=None) -> torch.Tensor:
         """One optimizer step.  With ids: copy them in and run.  Without: consume the batch started by prefetch()."""
         if q_ids is None:
-            self._consume_prefetched()
-        else:
-            self.load_batch(q_ids, d_ids, n_ids)
+            t = self._consume_prefetched()
+            out = self.run(t)
+            self._buf_free[t].record(torch.cuda.current_stream())
+            self._last_gi = t
+            return out
+        self.load_batch(q_ids, d_ids, n_ids)
+        self._last_gi = -1
         return self.run()
 
     def read_loss_async(self):
@@ -575,14 +605,21 @@ class FusedTrainer:
                 if pending is not None: log(pending())
                 pending = nxt
         """
-        k = self._loss_slot
-        self._loss_slot ^= 1
-        self._loss_ring[k].copy_(self.loss.reshape(1), non_blocking=True)   # stream-ordered before the next step overwrites it
+        if self._last_gi >= 0:
+            # pipelined step: its replay already carried the copy into the slot of its graph; that slot is written again
+            # two steps later, after the loop above has consumed it
+            k = self._last_gi
+            ring = self._loss_ring_g
+        else:
+            k = self._loss_slot
+            self._loss_slot ^= 1
+            ring = self._loss_ring
+            ring[k].copy_(self.loss.reshape(1), non_blocking=True)      # stream-ordered before the next step overwrites it
         self._loss_ev[k].record(torch.cuda.current_stream())
-        def wait(k=k):
+        def wait(k=k, ring=ring):
             self._loss_ev[k].synchronize()
             _lib.raise_on_bad_ids()                                     # the step's gather kernels have completed
-            return float(self._loss_ring[k])
+            return float(ring[k])
         return wait
 
     def kernels_per_step(self) -> int:

@@ -245,6 +245,18 @@ size_t tt_inbatch_ce_onepass_sync_bytes(int64_t Bq);
 int tt_inbatch_ce_fwd_dq(const tt_ce_pass_t* q_pass, int H, float inv_temperature, float logit_bound, float loss_scale,
                          const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch, void* stream);
 int tt_inbatch_ce_dd_nparts(int64_t d_x_rows, int64_t d_y_rows, int H);
+/* tt_inbatch_ce_fwd_dq fused with the all-gather of the documents (data-parallel training, global in-batch negatives,
+ * twotower/losses.py:107-116 over the concatenated batch): q_pass->y_bf16 must be the gathered slots of `y_exchange`
+ * (base[rank] + 256: world x y_rows/world x H bf16), and the call must follow tt_p2p_allgather(y_exchange, ...) on the same
+ * stream, whose `src` is y_own_bf16 (this rank's y_rows/world rows; x_rows == y_rows/world, label_offset == rank * x_rows).
+ * The kernel is launched programmatically behind the exchange kernel and does not wait for it to retire: it starts on this
+ * rank's own rows, read where the towers left them, and its TMA warp polls the exchange's per-source arrival counters and
+ * consumes each peer's block as it lands -- the NVLink transfer and the wait for the slowest peer run under the loss
+ * kernel's main loop. */
+struct tt_p2p_s;
+int tt_inbatch_ce_fwd_dq_p2p(const tt_ce_pass_t* q_pass, int H, float inv_temperature, float logit_bound, float loss_scale,
+                             const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch,
+                             const struct tt_p2p_s* y_exchange, const void* y_own_bf16, void* stream);
 int tt_inbatch_ce_dd(const tt_ce_pass_t* d_pass, int H, float inv_temperature, float loss_scale, const float* grad_out,
                      void* stream);
 int tt_inbatch_ce_bwd_parts(const void* q_bf16, const void* d_bf16, const float* lse, int64_t Bq, int64_t Bd,
@@ -322,7 +334,7 @@ int tt_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
  * tt_p2p_sum_slots : out[i] = sum_r slot_r[i] in rank order -- with an all-gather of the gradients this is an all-reduce
  *                    whose result is bitwise identical on every rank.
  */
-typedef struct {
+typedef struct tt_p2p_s {
   int world, rank;
   size_t slot_bytes;          /* multiple of 256 */
   void* base[8];              /* exchange buffer of rank p as mapped in this process */

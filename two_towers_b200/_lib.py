@@ -100,6 +100,7 @@ SIGNATURES.update({
     "tt_inbatch_ce_onepass_sync_bytes": (_sz, [_i64]),
     "tt_inbatch_ce_fwd_dq": (_i, [C.POINTER(CePass), _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tt_inbatch_ce_dd_nparts": (_i, [_i64, _i64, _i]),
+    "tt_inbatch_ce_fwd_dq_p2p": (_i, [C.POINTER(CePass), _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, C.POINTER(P2P), _vp, _vp]),
     "tt_inbatch_ce_dd": (_i, [C.POINTER(CePass), _i, _f, _f, _vp, _vp]),
 })
 

@@ -508,7 +508,20 @@ int tt_inbatch_ce_fwd_dq(const tt_ce_pass_t* q_pass, int H, float inv_temperatur
   TT_CHECK_ARG(q_pass->label_offset >= 0 && q_pass->x_rows + q_pass->label_offset <= q_pass->y_rows,
                "inbatch_ce_fwd_dq: positives out of range");
   return tt::tc_inbatch_fwd_dq(q_pass, H, inv_temperature, logit_bound, loss_scale, grad_out, loss, lse, pos_mean, sync_scratch,
-                               static_cast<cudaStream_t>(stream));
+                               nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int tt_inbatch_ce_fwd_dq_p2p(const tt_ce_pass_t* q_pass, int H, float inv_temperature, float logit_bound, float loss_scale,
+                             const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch,
+                             const tt_p2p_t* y_exchange, const void* y_own, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(q_pass && H > 0 && loss && lse && sync_scratch && y_exchange && y_own, "inbatch_ce_fwd_dq_p2p: bad arguments");
+  TT_CHECK_ARG(q_pass->x_bf16 && q_pass->y_bf16 && q_pass->x_rows > 0 && q_pass->y_rows > 0 && q_pass->y_buf_rows >= 1,
+               "inbatch_ce_fwd_dq_p2p: null operand");
+  TT_CHECK_ARG(q_pass->label_offset >= 0 && q_pass->x_rows + q_pass->label_offset <= q_pass->y_rows,
+               "inbatch_ce_fwd_dq_p2p: positives out of range");
+  return tt::tc_inbatch_fwd_dq(q_pass, H, inv_temperature, logit_bound, loss_scale, grad_out, loss, lse, pos_mean, sync_scratch,
+                               y_exchange, y_own, static_cast<cudaStream_t>(stream));
 }
 
 int tt_inbatch_ce_dd_nparts(int64_t d_x_rows, int64_t d_y_rows, int H) {

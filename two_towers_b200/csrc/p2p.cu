@@ -29,7 +29,7 @@
 namespace tt {
 
 constexpr int kP2PMaxWorld = 8;
-constexpr size_t kP2PHeaderBytes = 256;   // [0,32) arrival counters per source rank, [32] round, [33] exit ticket (u32 words)
+constexpr size_t kP2PHeaderBytes = 256;   // u32 words: [0,32) arrival counters per source rank, [32] round, [33] exit ticket, [34] time-out, [36] CTAs started
 
 struct P2PArgs {
   int world, rank, halves;                // halves == 2: rounds alternate between two slot sets (see tt_p2p_t.double_buffered)
@@ -48,9 +48,17 @@ __device__ __forceinline__ void red_release_sys_add(unsigned* p, unsigned v) {
 
 __global__ void __launch_bounds__(256)
 p2p_allgather_kernel(const P2PArgs a, const uint4* __restrict__ src, size_t n16, size_t slot_bytes) {
-  pdl_trigger();
-  pdl_wait();
   unsigned* hdr = reinterpret_cast<unsigned*>(a.base[a.rank]);
+  // header word 36 counts the CTAs that have STARTED, over all rounds.  It is bumped before the dependent-launch trigger:
+  // a kernel launched programmatically behind this one (tt_inbatch_ce_fwd_dq_p2p) starts only after every CTA here has
+  // triggered, so what it reads from word 36 is exactly this round's arrival target (round x CTAs) -- it can then consume
+  // the slots rank by rank as their counters reach that target, while this kernel is still pushing / waiting for the
+  // slowest peer.  The trigger comes AFTER griddepcontrol.wait: such a dependent also knows that everything before this
+  // kernel in the stream has retired (it may read `src` itself).
+  pdl_wait();                                                        // the producers of `src` have retired ...
+  if (threadIdx.x == 0) { atomicAdd(hdr + 36, 1u); __threadfence(); }
+  __syncthreads();
+  pdl_trigger();                                                     // ... before any dependent of this kernel may start
   const unsigned round = hdr[32] + 1;                                // every CTA reads it before any CTA can bump it
   const size_t per = (n16 + gridDim.x - 1) / gridDim.x;
   const size_t lo = (size_t)blockIdx.x * per, hi = min(n16, lo + per);

@@ -393,6 +393,14 @@ struct BwdParams {
   float* loss; float* pos_mean; float loss_scale;
   unsigned* counter;           // one ticket counter, zero on entry, zero again on exit
   float* tile_sums;            // [row tiles * splits][2]: sum(lse - pos), sum(pos)
+  // MODE 2 behind a peer-memory all-gather of Y (tt_inbatch_ce_fwd_dq_p2p): the kernel is launched programmatically behind
+  // the exchange kernel and does NOT wait for it to retire; the TMA warp polls the exchange's per-source arrival counters
+  // and consumes each rank's block of Y as it lands, its own rank's block first.
+  const unsigned* gate;        // local exchange header (null: no gate): word r = arrivals from rank r, word 36 = this round's target
+  int gate_rank;               // this rank: its block of Y is consumed first, straight from the exchange's SOURCE (y_own)
+  const __nv_bfloat16* y_own;  // [gate_blk, H]: this rank's rows of Y where the exchange kernel reads them
+  int64_t gate_blk;            // logical Y rows per source rank
+  unsigned gate_timeout_s;
 };
 
 // X rows = this CTA's 128 output rows, Y = streamed 128-row tiles.
@@ -411,7 +419,7 @@ constexpr int BWD_BN = 128;
 // also instruction-latency bound with one warp per scheduler.  Eight warps halve both.
 template <int MODE, int EW>
 __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtensorMap* tmY, const BwdParams& p,
-                                            uint8_t* base) {
+                                            uint8_t* base, const CUtensorMap* tmYown = nullptr) {
   constexpr bool COL = MODE == 1;                           // MODE 0: dQ from saved lse, 1: dD, 2: forward + dQ in one pass
   constexpr int PASS = COL ? 1 : 0;
   constexpr int NH = EW / 4;                                // warps per TMEM lane quarter
@@ -450,7 +458,17 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   const int ntiles = (int)ceil_div(By, BWD_BN);
   const int t_beg = blockIdx.y * tiles_per_split;
   const int t_end = min(ntiles, t_beg + tiles_per_split);
-  const int nt = max(0, t_end - t_beg);
+  // gated: every split takes the same slice of EVERY source rank's block and walks the blocks starting with its own
+  // rank's (local data first, the peers' blocks have time to arrive); otherwise one contiguous tile range per split
+  const bool rot = MODE == 2 && p.gate != nullptr;
+  const int g_nblk = rot ? (int)(By / p.gate_blk) : 1, g_tpb = rot ? (int)(p.gate_blk / BWD_BN) : 1;
+  const int g_tps = rot ? g_tpb / (int)gridDim.y : 1;
+  const int nt = rot ? g_nblk * g_tps : max(0, t_end - t_beg);
+  auto tile_at = [&](int i) -> int {
+    if (!rot) return t_beg + i;
+    const int b = i / g_tps;
+    return ((p.gate_rank + b) % g_nblk) * g_tpb + (int)blockIdx.y * g_tps + (i - b * g_tps);
+  };
   const bool fused = MODE == 2 || p.dz[PASS] != nullptr;  // CTA-uniform (cluster-uniform): finish through the cluster tail
   float lsum = 0.f, pos_val = 0.f;                         // MODE 2: this thread's share of sum_j E_ij, its row's positive logit
   bool pos_found = false;
@@ -483,13 +501,37 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();                                             // prologue overlapped the previous kernel's tail
+  const bool gated = MODE == 2 && p.gate != nullptr;
+  if (!gated) pdl_wait();                                 // prologue overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base;                      // columns [0, H)
   const uint32_t tmem_s = tmem_base + 256;                // columns [256, 384): S tile
   const uint32_t tmem_x = tmem_base + 384;                // columns [384, 384 + H/2): X tile (TMEM A operand)
 
   if (warp == 0) {
+    unsigned g_target = 0, g_have = 0;                      // gate: this round's arrival target, bitmask of ranks seen arrived
+    auto gate_wait = [&](int src) {                         // whole warp: every lane acquires, so the elected one has
+      if (!gated || ((g_have >> src) & 1u)) return;
+      unsigned long long t0 = 0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (unsigned spins = 1;; ++spins) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.gate + src) : "memory");
+        if (v >= g_target) break;
+        if ((spins & 255u) == 0) {                          // a dead peer must not hang the GPU: the exchange kernel reports it
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > (unsigned long long)p.gate_timeout_s * 1000000000ull) break;
+        }
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");   // the acquired data is read by TMA (async proxy)
+      __syncwarp();
+      g_have |= 1u << src;
+    };
+    if (gated) {                                            // X and this rank's own Y block need no gate: the exchange kernel
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g_target) : "l"(p.gate + 36) : "memory");   // triggered this launch after its own griddepcontrol.wait
+      g_have = 1u << p.gate_rank;
+    }
     if (elect_one()) {
       mbar_arrive_expect_tx(x_bar, y_bytes);
       for (int kb = 0; kb < kq; ++kb) tma_load_2d(x_tile + kb * (CE_BM * 128), tmX, x_bar, kb * 64, (int)x0);
@@ -500,11 +542,18 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       if (i == BWD_STAGES - 1) mbar_wait(x_ready, 0);     // the stage X borrowed is free once X lives in TMEM
       mbar_wait(&y_empty[s], ((i / BWD_STAGES) & 1) ^ 1);
       uint8_t* yt = y_tiles + s * y_bytes;
-      const int64_t g = (int64_t)(t_beg + i) * BWD_BN;
-      const int yc = (int)((g / p.y_blk[PASS]) * p.y_blk_stride[PASS] + (g % p.y_blk[PASS]) + p.y_blk_off[PASS]);
+      const int64_t g = (int64_t)tile_at(i) * BWD_BN;
+      const CUtensorMap* tm = tmY;
+      int yc;
+      if (gated && g / p.gate_blk == p.gate_rank) {       // this rank's own rows: read where the towers left them
+        tm = tmYown; yc = (int)(g - (int64_t)p.gate_rank * p.gate_blk);
+      } else {
+        if (gated) gate_wait((int)(g / p.gate_blk));
+        yc = (int)((g / p.y_blk[PASS]) * p.y_blk_stride[PASS] + (g % p.y_blk[PASS]) + p.y_blk_off[PASS]);
+      }
       if (elect_one()) {
         mbar_arrive_expect_tx(&y_full[s], y_bytes);
-        for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (BWD_BN * 128), tmY, &y_full[s], kb * 64, yc);
+        for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (BWD_BN * 128), tm, &y_full[s], kb * 64, yc);
       }
       __syncwarp();
     }
@@ -599,7 +648,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     };
     float next_cl = COL ? load_col_lse(0) : 0.f;
     for (int i = 0; i < nt; ++i) {
-      const int64_t y0 = (int64_t)(t_beg + i) * BWD_BN;
+      const int64_t y0 = (int64_t)tile_at(i) * BWD_BN;
       const float4* cl4 = reinterpret_cast<const float4*>(col_lse + (i & 1) * BWD_BN);
       if (COL) {                                            // column lse -> smem; read back as broadcasts
         if (tid_e < BWD_BN) col_lse[(i & 1) * BWD_BN + tid_e] = next_cl;
@@ -806,7 +855,9 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
             const int64_t grow = gw0 + i;
             if (grow < Bx && cl) {
               if (to_dz) cp_async_16(ybuf + (e * RPW + i) * H * 2 + lane * 16, p.xg[PASS] + grow * H + lane * 8);
-              if (MODE == 2) cp_async_16(pbuf + (e * RPW + i) * H * 2 + lane * 16, p.yg[PASS] + (pbase + pr) * H + lane * 8);
+              if (MODE == 2) cp_async_16(pbuf + (e * RPW + i) * H * 2 + lane * 16,
+                                         (p.gate ? p.y_own + (grow + label_offset - (int64_t)p.gate_rank * p.gate_blk) * H
+                                                 : p.yg[PASS] + (pbase + pr) * H) + lane * 8);
             }
             if (MODE == 2 && ++pr == blk) { pr = 0; pbase += p.y_blk_stride[PASS]; }
           }
@@ -1034,11 +1085,12 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
 
 // forward + query gradient in one pass (MODE 2): grid = (row tiles, splits), one cluster per row tile
 __global__ void __launch_bounds__(64 + 8 * 32, 1)
-tc_ce_fwd_dq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const BwdParams p) {
+tc_ce_fwd_dq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                    const __grid_constant__ CUtensorMap tmYown, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-  ce_bwd_body<2, 8>(&tmX, &tmY, p, base);
+  ce_bwd_body<2, 8>(&tmX, &tmY, p, base, &tmYown);
 }
 
 static size_t fwd_smem(int H) {
@@ -1295,7 +1347,8 @@ int tc_inbatch_onepass_ok(int64_t Bq, int64_t Bd, int H, float logit_bound) {
 int tc_inbatch_dd_nparts(int64_t x_rows, int64_t y_rows) { return cluster_splits(ceil_div(x_rows, tc::CE_BM), y_rows); }
 
 int tc_inbatch_fwd_dq(const tt_ce_pass_t* t, int H, float inv_temp, float logit_bound, float loss_scale, const float* grad_out,
-                      float* loss, float* lse_out, float* pos_mean, void* sync_scratch, cudaStream_t s) {
+                      float* loss, float* lse_out, float* pos_mean, void* sync_scratch, const tt_p2p_t* y_exchange, const void* y_own,
+                      cudaStream_t s) {
   if (!tc_inbatch_onepass_ok(t->x_rows, t->y_rows, H, logit_bound)) {
     set_error("tc_inbatch_fwd_dq: needs H %% 64 == 0, H <= 256 and 2 * logit_bound * log2(e) < 120 (got H=%d bound=%g)", H, (double)logit_bound);
     return TT_ERR_UNSUPPORTED;
@@ -1306,9 +1359,10 @@ int tc_inbatch_fwd_dq(const tt_ce_pass_t* t, int H, float inv_temp, float logit_
   const bool to_dz = t->dz_bf16 != nullptr;
   if (to_dz && (!t->dz_colsum || !t->inv_norm)) { set_error("tc_inbatch_fwd_dq: dz needs dz_colsum and inv_norm"); return TT_ERR_INVALID; }
   if (!to_dz && !t->out_parts) { set_error("tc_inbatch_fwd_dq: needs dz_bf16 or out_parts (dq)"); return TT_ERR_INVALID; }
-  CUtensorMap tmX, tmY;
+  CUtensorMap tmX, tmY, tmYown;
   int rc = tc::make_tmap_bf16(&tmX, t->x_bf16, (uint64_t)Bx, (uint64_t)H, tc::CE_BM); if (rc) return rc;
   rc = tc::make_tmap_bf16(&tmY, t->y_bf16, (uint64_t)t->y_buf_rows, (uint64_t)H, tc::BWD_BN); if (rc) return rc;
+  tmYown = tmY;
   const int64_t xt = ceil_div(Bx, tc::CE_BM);
   const int ns = cluster_splits(xt, By);
   tc::BwdParams p{};
@@ -1322,6 +1376,24 @@ int tc_inbatch_fwd_dq(const tt_ce_pass_t* t, int H, float inv_temp, float logit_
   p.mfix = logit_bound; p.lse_out = lse_out; p.loss = loss; p.pos_mean = pos_mean; p.loss_scale = loss_scale;
   p.counter = static_cast<unsigned*>(sync_scratch);
   p.tile_sums = reinterpret_cast<float*>(static_cast<char*>(sync_scratch) + 16);
+  if (y_exchange) {
+    // Y is the gathered buffer of a peer-memory exchange launched just before this call on the same stream: consume it
+    // rank by rank as it lands instead of waiting for the exchange kernel to retire
+    const tt_p2p_t* x = y_exchange;
+    const int64_t blk = x->world > 0 ? By / x->world : 0;
+    const bool ok = x->world >= 1 && x->world <= 8 && x->rank >= 0 && x->rank < x->world && By % x->world == 0 &&
+                    blk % ((int64_t)tc::BWD_BN * ns) == 0 && y_blk >= By && t->y_blk_off == 0 &&
+                    t->y_bf16 == static_cast<const char*>(x->base[x->rank]) + 256 && (size_t)blk * H * 2 <= x->slot_bytes &&
+                    (size_t)blk * H * 2 == x->slot_bytes;
+    if (!ok) { set_error("tc_inbatch_fwd_dq: y_bf16 must be the gathered slots of y_exchange (world x rows x H bf16, rows %% %d == 0)", tc::BWD_BN * ns); return TT_ERR_INVALID; }
+    if (!y_own || t->label_offset != (int64_t)x->rank * blk || Bx != blk) {
+      set_error("tc_inbatch_fwd_dq: the p2p form needs y_own, x_rows == y_rows / world and label_offset == rank * x_rows"); return TT_ERR_INVALID;
+    }
+    p.gate = static_cast<const unsigned*>(x->base[x->rank]);
+    p.gate_rank = x->rank; p.gate_blk = blk; p.gate_timeout_s = x->timeout_s > 0 ? (unsigned)x->timeout_s : 600u;
+    p.y_own = static_cast<const __nv_bfloat16*>(y_own);
+    rc = tc::make_tmap_bf16(&tmYown, y_own, (uint64_t)blk, (uint64_t)H, tc::BWD_BN); if (rc) return rc;
+  }
   const size_t smem = tc::bwd_smem(H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_fwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
@@ -1329,7 +1401,7 @@ int tc_inbatch_fwd_dq(const tt_ce_pass_t* t, int H, float inv_temp, float logit_
   long long* dbg_dev = nullptr;
   const size_t ncta = (size_t)grid.x * grid.y, dbg_n = 2 * 64 * 8 + 8 * ncta;
   if (dbg_on) { cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p.dbg = dbg_dev; p.dbg_pass = 0; }
-  TT_CUDA(launch_kernel_cluster(tc::tc_ce_fwd_dq_kernel, grid, dim3(64 + 8 * 32), smem, s, true, (unsigned)ns, tmX, tmY, p));
+  TT_CUDA(launch_kernel_cluster(tc::tc_ce_fwd_dq_kernel, grid, dim3(64 + 8 * 32), smem, s, true, (unsigned)ns, tmX, tmY, tmYown, p));
   TT_LAUNCH_CHECK("tc_ce_fwd_dq_kernel");
   if (dbg_on) {
     std::vector<long long> h(dbg_n);

@@ -34,6 +34,10 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class _StopStep(Exception):
+    pass
+
+
 class FusedTrainer:
     def __init__(self, model: TwoTower, loss: str = "in_batch", temperature: float = 0.1, margin: float = 0.2,
                  lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
@@ -170,6 +174,9 @@ class FusedTrainer:
                 import warnings
                 warnings.warn(f"FusedTrainer: {e}; using NCCL collectives")
                 self.p2p = self.p2p_grad = False
+        # the loss forward consumes the gathered documents block by block as they land (tt_inbatch_ce_fwd_dq_p2p)
+        self.gated = bool(self.p2p and self.global_fast and self.onepass and B % 512 == 0 and (B * self.H * 2) % 256 == 0 and
+                          os.environ.get("TT_CE_GATED", "1") != "0")
         if self.p2p:
             if self.global_fast:
                 self.dg_bf16 = self.x_d.gathered(torch.bfloat16, (B, self.H)).view(self.world * B, self.H)
@@ -332,7 +339,34 @@ class FusedTrainer:
             check(lib.tt_proj_ln_bwd(_p(dy), _p(x), None, None, None, None, None, nr, self.E, self.H, 0, 0.0, 0, 0, None,
                                      _p(dx), None, None, None, None, self.prec, None, 0, s), "tt_proj_ln_bwd")
 
+    def _mark(self, name: str) -> None:
+        """Developer aid (tools/step_timeline.py): phase boundaries of the step.  With `self._trace` set to a list an eager
+        step leaves one CUDA event per boundary; with `self._stop_after` set the step ends at that boundary
+        (`step_prefix`), so that prefixes of the step can be captured and timed as graphs of their own."""
+        tr = getattr(self, "_trace", None)
+        if tr is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            tr.append((name, ev))
+        if getattr(self, "_stop_after", None) == name:
+            if getattr(self, "_side_open", False):          # join the forked exchange stream before the prefix ends
+                torch.cuda.current_stream().wait_stream(self._side)
+                self._side_open = False
+            raise _StopStep()
+
+    def step_prefix(self, stop_after: str) -> None:
+        """Run the step's launches up to and including phase `stop_after` (names as in tools/step_timeline.py).  Collective
+        with a process group.  Leaves parameters untouched unless the prefix reaches the optimizer."""
+        self._stop_after = stop_after
+        try:
+            self._step_impl()
+        except _StopStep:
+            pass
+        finally:
+            self._stop_after = None
+
     def _step_impl(self):
+        self._mark("start")
         lib, B, H, P = self.lib, self.B, self.H, self.passes
         R = P * B
         idb = 8 if self.ids.dtype == torch.int64 else 4
@@ -341,8 +375,10 @@ class FusedTrainer:
         check(lib.tt_embed_pool_fwd(_p(self._ids_cur), idb, _p(self.table), R, self.L, self.V, self.E,
                                     None if tower_pools else _p(self.pooled), _p(self.inv_len),
                                     None if tower_pools else _p(self.pooled_bf16), _p(self.pool_bf16), s), "tt_embed_pool_fwd")
+        self._mark("embed_pool_fwd")
         for gi in range(len(self.groups)):
             self._tower_fwd(gi)
+        self._mark("tower_fwd")
         q, d = self.y[:B], self.y[B:2 * B]
         dq, dd = self.dy[:B], self.dy[B:2 * B]
         if self.loss_name == "in_batch":
@@ -367,23 +403,27 @@ class FusedTrainer:
             check(lib.tt_triplet_bwd(_p(q), _p(d), _p(n), _p(self.sims), B, H, self.margin,
                                      _p(self.grad_scale) if self.world > 1 else None, _p(dq), _p(dd), _p(dn), s),
                   "tt_triplet_bwd")
+        self._mark("loss")
         for gi in range(len(self.groups)):
             self._tower_bwd(gi)
         if self.train_table and not self.embed_fused:
             check(lib.tt_embed_pool_bwd(_p(self._ids_cur), idb, _p(self.inv_len), _p(self.dpooled), R, self.L, self.V,
                                         self.E, _p(self.table.grad), _p(self.ws), self.ws.numel(), s),
                   "tt_embed_pool_bwd")
+        self._mark("tower_bwd")
         if self.p2p_grad:
             self.x_grad.allgather(self.flat_grad)           # every rank's gradients over NVLink, then the same rank-order
             self.x_grad.sum_slots(self.flat_grad)           # sum everywhere: bitwise identical parameters on all ranks
         elif self.world > 1:
             parallel.allreduce_sum_(self.flat_grad, self.group)
+        self._mark("grad_exchange")
         # pipelined mode: the loss reaches the host (mapped pinned slot) from inside the step's last launch
         pub = self._loss_dst
         check(lib.tt_adamw_step_publish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
                                         self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                         _p(self.step_count), _p(self.flat_bf16), _p(self.loss) if pub is not None else None,
                                         _p(pub), s), "tt_adamw_step")
+        self._mark("adamw")
 
     def _local_loss_fwd(self, s):
         """In-batch loss forward against the local documents (one launch on the tensor-core path)."""
@@ -455,6 +495,7 @@ class FusedTrainer:
         if self.p2p:
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)                    # tower outputs are ready
+            self._side_open = True
             with torch.cuda.stream(self._side):
                 self.x_q.allgather(self.y_bf16[:B])         # consumed by the backward's dD pass only: hidden under the forward
             self.x_d.allgather(self.y_bf16[B:2 * B])
@@ -466,22 +507,34 @@ class FusedTrainer:
             q_all, q_off = self.yg_bf16, 0
         scale = 1.0 / Bg
         nb = B // 32
+        self._mark("loss/gather_D")
         if self.onepass:                                    # forward + query gradient in one pass over S
             qp = _lib.CePass(vp(self.y_bf16[:B]), B, vp(d_all), Bg, d_rows, d_blk, d_stride, d_off, None, self.rank * B, None, 0,
                              vp(self.dz_bf16[:B]), vp(self.dz_colsum[:nb]), vp(self.inv_norm[:B]))
-            check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, inv_t, scale, None, _p(self.loss), _p(self.lse),
-                                           _p(self.pos_mean), _p(self.onepass_sync), s), "tt_inbatch_ce_fwd_dq")
+            if self.p2p and self.gated:
+                # fused with the exchange: launched behind the all-gather kernel without waiting for it to retire; each
+                # rank's block of D is consumed as its arrival counter reaches this round's target (own block first)
+                check(lib.tt_inbatch_ce_fwd_dq_p2p(C.byref(qp), H, inv_t, inv_t, scale, None, _p(self.loss), _p(self.lse),
+                                                   _p(self.pos_mean), _p(self.onepass_sync), C.byref(self.x_d.desc),
+                                                   _p(self.y_bf16[B:2 * B]), s),
+                      "tt_inbatch_ce_fwd_dq_p2p")
+            else:
+                check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, inv_t, scale, None, _p(self.loss), _p(self.lse),
+                                               _p(self.pos_mean), _p(self.onepass_sync), s), "tt_inbatch_ce_fwd_dq")
         else:
             check(lib.tt_inbatch_ce_fwd_ex(_p(self.y_bf16[:B]), B, _p(d_all), Bg, d_rows, d_blk, d_stride, d_off, H, inv_t,
                                            self.rank * B, scale, _p(self.loss), _p(self.lse), _p(self.pos_mean),
                                            _p(self.ce_ws), self.ce_ws.numel(), _p(self.ce_sync), s), "tt_inbatch_ce_fwd_ex")
+        self._mark("loss/forward(+dQ)")
         if self.p2p:
             self.x_lse.allgather(self.lse)
             if self._lse_pack:
                 self.lse_g.view(W, B).copy_(self.x_lse.gathered(torch.float32, (B,)))
             torch.cuda.current_stream().wait_stream(self._side)          # Q of every rank has arrived
+            self._side_open = False
         else:
             dist.all_gather_into_tensor(self.lse_g, self.lse, group=self.group)
+        self._mark("loss/gather_lse(+Q)")
         if self.onepass:
             dp = _lib.CePass(vp(self.y_bf16[B:2 * B]), B, vp(q_all), Bg, d_rows, d_blk, d_stride, q_off, vp(self.lse_g),
                              -self.rank * B, None, 0,

@@ -374,6 +374,14 @@ int tt_adamw_step_publish(float* param, const float* grad, float* exp_avg, float
                           int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
                           int64_t* step_count, void* param_bf16, const float* publish_src, float* publish_dst,
                           void* stream);
+/* Same step with the gradient taken from the slots of a (double-buffered) peer-memory all-gather that has just completed
+ * on this stream (tt_p2p_allgather of every rank's local gradient): the slots are summed in rank order while they are
+ * read -- the data-parallel all-reduce (twotower semantics: one model, mean over the global batch) costs no reduction
+ * launch, and the parameters stay bitwise identical on all ranks.  grad_sum (nullable) receives the summed gradient. */
+int tt_adamw_step_p2p(float* param, float* grad_sum, const tt_p2p_t* grad_exchange, float* exp_avg, float* exp_avg_sq,
+                      int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
+                      int64_t* step_count, void* param_bf16, const float* publish_src, float* publish_dst,
+                      void* stream);
 
 /* ---- self-test hook -------------------------------------------------------------------------
  * C[M,N] (fp32) = A * B on the tcgen05 tensor cores; used by the GPU tests to pin the UMMA / TMA

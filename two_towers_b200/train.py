@@ -411,18 +411,24 @@ class FusedTrainer:
                                         self.E, _p(self.table.grad), _p(self.ws), self.ws.numel(), s),
                   "tt_embed_pool_bwd")
         self._mark("tower_bwd")
+        pub = self._loss_dst                                # pipelined mode: the loss reaches the host (mapped pinned slot) from inside the step's last launch
         if self.p2p_grad:
-            self.x_grad.allgather(self.flat_grad)           # every rank's gradients over NVLink, then the same rank-order
-            self.x_grad.sum_slots(self.flat_grad)           # sum everywhere: bitwise identical parameters on all ranks
-        elif self.world > 1:
-            parallel.allreduce_sum_(self.flat_grad, self.group)
-        self._mark("grad_exchange")
-        # pipelined mode: the loss reaches the host (mapped pinned slot) from inside the step's last launch
-        pub = self._loss_dst
-        check(lib.tt_adamw_step_publish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
-                                        self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                        _p(self.step_count), _p(self.flat_bf16), _p(self.loss) if pub is not None else None,
-                                        _p(pub), s), "tt_adamw_step")
+            # every rank's gradients over NVLink; the optimizer launch adds the slots in rank order as it reads them
+            # (bitwise identical parameters on all ranks, no reduction launch) and leaves the sum in flat_grad
+            self.x_grad.allgather(self.flat_grad)
+            self._mark("grad_exchange")
+            check(lib.tt_adamw_step_p2p(_p(self.flat), _p(self.flat_grad), C.byref(self.x_grad.desc), _p(self.exp_avg),
+                                        _p(self.exp_avg_sq), self.n_params, self.lr, self.betas[0], self.betas[1], self.eps,
+                                        self.weight_decay, _p(self.step_count), _p(self.flat_bf16),
+                                        _p(self.loss) if pub is not None else None, _p(pub), s), "tt_adamw_step_p2p")
+        else:
+            if self.world > 1:
+                parallel.allreduce_sum_(self.flat_grad, self.group)
+            self._mark("grad_exchange")
+            check(lib.tt_adamw_step_publish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                            self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                            _p(self.step_count), _p(self.flat_bf16), _p(self.loss) if pub is not None else None,
+                                            _p(pub), s), "tt_adamw_step")
         self._mark("adamw")
 
     def _local_loss_fwd(self, s):

@@ -244,6 +244,13 @@ int tt_inbatch_ce_onepass_ok(int64_t Bq, int64_t Bd, int H, float logit_bound);
 size_t tt_inbatch_ce_onepass_sync_bytes(int64_t Bq);
 int tt_inbatch_ce_fwd_dq(const tt_ce_pass_t* q_pass, int H, float inv_temperature, float logit_bound, float loss_scale,
                          const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch, void* stream);
+/* Both launches as ONE for the square single-process case (x_rows == y_rows on both passes, offsets 0, dz form,
+ * d_pass->lse == lse): forward + query gradient, a grid-wide barrier inside the kernel (every CTA of the <= 148-CTA grid is
+ * resident; checked with the occupancy calculator), document gradient.  Results are bitwise those of the two calls above.
+ * Returns TT_ERR_UNSUPPORTED (-> make the two calls) when the shapes or the device do not allow it. */
+int tt_inbatch_ce_onepass(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temperature, float logit_bound,
+                          float loss_scale, const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch,
+                          void* stream);
 int tt_inbatch_ce_dd_nparts(int64_t d_x_rows, int64_t d_y_rows, int H);
 /* tt_inbatch_ce_fwd_dq fused with the all-gather of the documents (data-parallel training, global in-batch negatives,
  * twotower/losses.py:107-116 over the concatenated batch): q_pass->y_bf16 must be the gathered slots of `y_exchange`

@@ -103,6 +103,21 @@ def test_onepass_fused_normalise(Bq, Bd, H, off):
         if keep is None:
             keep = (dzq.clone(), dzd.clone(), csq.clone(), csd.clone())
     assert loss2.item() == loss.item() and torch.equal(lse2, lse)
+    if Bq == Bd and off == 0:
+        # both launches as ONE kernel (grid barrier between the phases): bitwise the same outputs
+        dzq1 = torch.zeros_like(dzq); dzd1 = torch.zeros_like(dzd); csq1 = torch.zeros_like(csq); csd1 = torch.zeros_like(csd)
+        loss3 = torch.zeros((), device=DEV); lse3 = torch.zeros(Bq, device=DEV)
+        q1 = _lib.CePass(vp(q), Bq, vp(d), Bd, Bd, Bd, 0, 0, None, 0, None, 0, vp(dzq1), vp(csq1), vp(invq))
+        d1 = _lib.CePass(vp(d), Bd, vp(q), Bq, Bq, Bq, 0, 0, vp(lse3), 0, None, 0, vp(dzd1), vp(csd1), vp(invd))
+        for it in range(3):
+            rc = lib.tt_inbatch_ce_onepass(C.byref(q1), C.byref(d1), H, 10.0, 10.0, 1.0 / Bq, None, vp(loss3), vp(lse3), None, vp(sync), s)
+            if rc == _lib.TT_ERR_UNSUPPORTED:
+                break
+            _lib.check(rc, "onepass single launch")
+            torch.cuda.synchronize()
+            assert loss3.item() == loss.item() and torch.equal(lse3, lse)
+            assert torch.equal(dzq1, dzq) and torch.equal(dzd1, dzd) and torch.equal(csq1, csq) and torch.equal(csd1, csd)
+        print(f"  single-launch form: {'bitwise equal to the two launches' if rc == 0 else 'not available for this shape'}")
     print(f"  one-pass dz form Bq={Bq} Bd={Bd} H={H} off={off}")
     check(dzq, rq, 1e-2, "dz (queries)"); check(dzd, rd, 1e-2, "dz (documents)")
     check(csq, ref_cs(rq, Bq), BF16_RTOL, "column sums (queries)"); check(csd, ref_cs(rd, Bd), BF16_RTOL, "column sums (documents)")

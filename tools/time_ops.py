@@ -84,6 +84,9 @@ def main():
         ops["ce_fwd"] = lambda: check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, inv_t, 1.0 / B, None, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), _p(tr.onepass_sync), s()), "x")
         ops["ce_bwd"] = lambda: check(lib.tt_inbatch_ce_dd(C.byref(dp), H, inv_t, 1.0 / B, None, s()), "x")
         ops = {("ce_fwd_dq" if k == "ce_fwd" else "ce_dd" if k == "ce_bwd" else k): v for k, v in ops.items()}
+        if tr.onelaunch:                          # both as one kernel
+            ops = {k: v for k, v in ops.items() if k != "ce_dd"}
+            ops = {("ce_onepass" if k == "ce_fwd_dq" else k): (lambda: tr._local_loss_onepass(s())) if k == "ce_fwd_dq" else v for k, v in ops.items()}
     if tr.embed_fused:
         del ops["embed_pool_bwd"]            # folded into the tower backward (tt_mlp_embed_t)
     total = 0.0

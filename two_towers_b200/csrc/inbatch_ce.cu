@@ -524,6 +524,16 @@ int tt_inbatch_ce_fwd_dq_p2p(const tt_ce_pass_t* q_pass, int H, float inv_temper
                                y_exchange, y_own, static_cast<cudaStream_t>(stream));
 }
 
+int tt_inbatch_ce_onepass(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temperature, float logit_bound,
+                          float loss_scale, const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch,
+                          void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(q_pass && d_pass && H > 0 && loss && lse && sync_scratch, "inbatch_ce_onepass: bad arguments");
+  TT_CHECK_ARG(q_pass->x_bf16 && q_pass->y_bf16 && d_pass->x_bf16 && d_pass->y_bf16 && q_pass->x_rows > 0, "inbatch_ce_onepass: null operand");
+  return tt::tc_inbatch_onepass_single(q_pass, d_pass, H, inv_temperature, logit_bound, loss_scale, grad_out, loss, lse, pos_mean,
+                                       sync_scratch, static_cast<cudaStream_t>(stream));
+}
+
 int tt_inbatch_ce_dd_nparts(int64_t d_x_rows, int64_t d_y_rows, int H) {
   if (d_x_rows <= 0 || d_y_rows <= 0 || H <= 0) return 1;
   return tt::tc_inbatch_dd_nparts(d_x_rows, d_y_rows);

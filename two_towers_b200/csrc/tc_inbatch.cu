@@ -419,7 +419,9 @@ constexpr int BWD_BN = 128;
 // also instruction-latency bound with one warp per scheduler.  Eight warps halve both.
 template <int MODE, int EW>
 __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtensorMap* tmY, const BwdParams& p,
-                                            uint8_t* base, const CUtensorMap* tmYown = nullptr) {
+                                            uint8_t* base, const CUtensorMap* tmYown = nullptr, int tmem_mode = 0) {
+  // tmem_mode: 0 = allocate and free tensor memory here; 1 = allocate, leave it to a second body of the same kernel;
+  // 2 = re-use that allocation and free it (the allocation permit is relinquished after the first tcgen05.alloc)
   constexpr bool COL = MODE == 1;                           // MODE 0: dQ from saved lse, 1: dD, 2: forward + dQ in one pass
   constexpr int PASS = COL ? 1 : 0;
   constexpr int NH = EW / 4;                                // warps per TMEM lane quarter
@@ -497,7 +499,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       mbar_arrive_expect_tx(xfer_bar, rows * (uint32_t)H * 2u + (MODE == 2 ? rows * 8u : 0u));   // fp16 partials
     }
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1 && tmem_mode != 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -644,7 +646,7 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
     const int64_t band_lo = COL ? x0 - label_offset : x0 + label_offset;
     auto load_col_lse = [&](int i) {                        // this thread's column of Y tile i (COL mode; first 128 threads)
       const int64_t gc = (int64_t)(t_beg + i) * BWD_BN + tid_e;
-      return (tid_e < BWD_BN && i < nt && gc < By) ? __ldg(lse + gc) * kLog2e : CUDART_INF_F;
+      return (tid_e < BWD_BN && i < nt && gc < By) ? __ldcg(lse + gc) * kLog2e : CUDART_INF_F;   // L2: the single-launch form reads what phase 1 of the SAME kernel wrote
     };
     float next_cl = COL ? load_col_lse(0) : 0.f;
     for (int i = 0; i < nt; ++i) {
@@ -1067,7 +1069,11 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1 && tmem_mode != 1) tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 0) {                                  // the single-launch form runs a second body over the same barrier words
+    for (uint64_t* b = x_bar; b <= sc_bar; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+  }
+  __syncthreads();
 }
 
 template <int EW>
@@ -1081,6 +1087,45 @@ tc_ce_bwd_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant
   if ((int64_t)blockIdx.x * CE_BM >= p.Bx[pass] || (p.out[pass] == nullptr && p.dz[pass] == nullptr)) return;   // cluster-uniform: nothing to do for this pass
   if (pass == 0) ce_bwd_body<0, EW>(&tmX0, &tmY0, p, base);
   else           ce_bwd_body<1, EW>(&tmX1, &tmY1, p, base);
+}
+
+// Both launches of the one-pass loss as ONE (square single-GPU case): phase 1 = forward + query gradient, a grid-wide barrier
+// (the document gradient needs the lse of every query), phase 2 = document gradient.  The grid is at most one CTA per SM and
+// every CTA is resident before the barrier can be reached (checked on the host with cudaOccupancyMaxActiveClusters), so
+// the barrier cannot deadlock; it is a self-resetting sense-reversal barrier in the call site's sync scratch
+// (word 1: arrivals, word 2: generation).  Saves the kernel boundary between the two launches (~7 us with 224 KB of
+// shared memory and all of tensor memory per CTA: nothing of the second launch can start before the first has left).
+__global__ void __launch_bounds__(64 + 8 * 32, 1)
+tc_ce_onepass_kernel(const __grid_constant__ CUtensorMap tmXq, const __grid_constant__ CUtensorMap tmYq,
+                     const __grid_constant__ CUtensorMap tmXd, const __grid_constant__ CUtensorMap tmYd, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
+  uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  unsigned gen = 0;
+  if (threadIdx.x == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(p.counter + 2) : "memory");
+  ce_bwd_body<2, 8>(&tmXq, &tmYq, p, base, &tmYq, 1);
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    __threadfence();                                       // this CTA's lse / dz rows before its arrival
+    if (atomicAdd(p.counter + 1, 1u) == total - 1) {
+      p.counter[1] = 0u;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.counter + 2), "r"(gen + 1) : "memory");
+    } else {
+      const long long t0 = clock64();
+      for (unsigned spins = 1;; ++spins) {
+        unsigned g2;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g2) : "l"(p.counter + 2) : "memory");
+        if (g2 != gen) break;
+        if ((spins & 1023u) == 0 && clock64() - t0 > 4000000000ll) {
+          printf("tt_b200: grid barrier of the one-pass loss timed out (block %d,%d)\n", blockIdx.x, blockIdx.y);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  ce_bwd_body<1, 8>(&tmXd, &tmYd, p, base, nullptr, 2);
 }
 
 // forward + query gradient in one pass (MODE 2): grid = (row tiles, splits), one cluster per row tile
@@ -1430,6 +1475,67 @@ int tc_inbatch_fwd_dq(const tt_ce_pass_t* t, int H, float inv_temp, float logit_
       printf("\n");
     }
   }
+  return TT_OK;
+}
+
+// both launches as one (see tc_ce_onepass_kernel); returns TT_ERR_UNSUPPORTED when the shapes / the device do not allow it
+int tc_inbatch_onepass_single(const tt_ce_pass_t* tq, const tt_ce_pass_t* td, int H, float inv_temp, float logit_bound, float loss_scale,
+                              const float* grad_out, float* loss, float* lse_out, float* pos_mean, void* sync_scratch, cudaStream_t s) {
+  if (!tc_inbatch_onepass_ok(tq->x_rows, tq->y_rows, H, logit_bound)) { set_error("tc_inbatch_onepass_single: unsupported shape / bound"); return TT_ERR_UNSUPPORTED; }
+  const int64_t B = tq->x_rows;
+  if (tq->y_rows != B || td->x_rows != B || td->y_rows != B || tq->label_offset != 0 || td->label_offset != 0 ||
+      !tq->dz_bf16 || !td->dz_bf16 || !tq->dz_colsum || !td->dz_colsum || !tq->inv_norm || !td->inv_norm || td->lse != lse_out) {
+    set_error("tc_inbatch_onepass_single: needs the square single-process case (Bq == Bd, offset 0), both passes in dz form, d_pass->lse == lse");
+    return TT_ERR_UNSUPPORTED;
+  }
+  const int64_t xt = ceil_div(B, tc::CE_BM);
+  const int ns = cluster_splits(xt, B);
+  if (xt * ns > kNumSMs) { set_error("tc_inbatch_onepass_single: grid larger than the SM count"); return TT_ERR_UNSUPPORTED; }
+  CUtensorMap tmXq, tmYq, tmXd, tmYd;
+  int rc = tc::make_tmap_bf16(&tmXq, tq->x_bf16, (uint64_t)B, (uint64_t)H, tc::CE_BM); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmYq, tq->y_bf16, (uint64_t)tq->y_buf_rows, (uint64_t)H, tc::BWD_BN); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmXd, td->x_bf16, (uint64_t)B, (uint64_t)H, tc::CE_BM); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmYd, td->y_bf16, (uint64_t)td->y_buf_rows, (uint64_t)H, tc::BWD_BN); if (rc) return rc;
+  tc::BwdParams p{};
+  const tt_ce_pass_t* ps[2] = {tq, td};
+  for (int k = 0; k < 2; ++k) {
+    p.lse[k] = k == 0 ? nullptr : lse_out; p.Bx[k] = B; p.By[k] = B; p.label_offset[k] = 0;
+    p.y_blk[k] = ps[k]->y_blk > 0 ? ps[k]->y_blk : 1; p.y_blk_stride[k] = ps[k]->y_blk_stride; p.y_blk_off[k] = ps[k]->y_blk_off;
+    p.tiles_per_split[k] = (int)ceil_div(ceil_div(B, tc::BWD_BN), ns);
+    p.out[k] = nullptr; p.part_stride[k] = 0;
+    p.dz[k] = (__nv_bfloat16*)ps[k]->dz_bf16; p.dz_colsum[k] = ps[k]->dz_colsum; p.inv_norm[k] = ps[k]->inv_norm;
+    p.xg[k] = (const __nv_bfloat16*)ps[k]->x_bf16; p.yg[k] = (const __nv_bfloat16*)ps[k]->y_bf16;
+  }
+  p.H = H; p.inv_temp = inv_temp; p.grad_out = grad_out; p.coef = loss_scale * inv_temp;
+  p.mfix = logit_bound; p.lse_out = lse_out; p.loss = loss; p.pos_mean = pos_mean; p.loss_scale = loss_scale;
+  p.counter = static_cast<unsigned*>(sync_scratch);
+  p.tile_sums = reinterpret_cast<float*>(static_cast<char*>(sync_scratch) + 16);
+  const size_t smem = tc::bwd_smem(H);
+  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)xt, (unsigned)ns, 1);
+  // every cluster of the grid must be resident at the same time (grid barrier): ask the occupancy calculator once per shape
+  static int ok_key = -1, ok_val = 0;
+  const int key = (int)(xt * 8 + ns) * 1024 + H;
+  if (ok_key != key) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(64 + 8 * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)ns; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = ns > 1 ? 1 : 0;
+    int nclusters = 0;
+    if (ns > 1) {
+      TT_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, tc::tc_ce_onepass_kernel, &cfg));
+    } else {
+      int per_sm = 0;
+      TT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc::tc_ce_onepass_kernel, 64 + 8 * 32, smem));
+      nclusters = per_sm * kNumSMs;
+    }
+    ok_key = key; ok_val = nclusters >= (int)xt ? 1 : 0;
+  }
+  if (!ok_val) { set_error("tc_inbatch_onepass_single: the grid's clusters cannot all be resident at once"); return TT_ERR_UNSUPPORTED; }
+  TT_CUDA(launch_kernel_cluster(tc::tc_ce_onepass_kernel, grid, dim3(64 + 8 * 32), smem, s, true, (unsigned)ns, tmXq, tmYq, tmXd, tmYd, p));
+  TT_LAUNCH_CHECK("tc_ce_onepass_kernel");
   return TT_OK;
 }
 

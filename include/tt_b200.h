@@ -114,6 +114,11 @@ typedef struct tt_mlp_embed_s {
   float* d_table;             /* [V,E] */
   int accumulate;             /* 0: d_table is overwritten, else added to (second tower sharing the table) */
   void* workspace; size_t workspace_bytes;
+  /* tt_mlp_fwd only, optional (ids == NULL: pool_bf16 is an INPUT produced by tt_embed_pool_fwd): the tower kernel builds
+   * the pooling matrix itself from the token ids [R,L] (int32: id_bytes 4, int64: 8; 0 = padding; L <= 255, V <= 128 E / 64) -- mask +
+   * mean of twotower/encoders.py:62-72 as one integer histogram per row -- and writes it to pool_bf16 for the backward; inv_len
+   * (nullable) [R] receives 1 / (non-pad tokens + 1e-9).  The histogram launch of the step disappears. */
+  const void* ids; int id_bytes; int L; float* inv_len;
 } tt_mlp_embed_t;
 size_t tt_mlp_embed_workspace(int64_t V, int H, int64_t R);
 size_t tt_mlp_workspace(int64_t R, int E, int H, int precision);

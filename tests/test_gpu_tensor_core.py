@@ -141,6 +141,22 @@ def test_embed_fused_tower_backward(R, L, V, E, H):
         torch.cuda.synchronize()
         close(yb2, O.normalize(rz), BF16_RTOL, "y_bf16 (x = P table in-kernel)")
         close(inv2, 1.0 / np.maximum(np.linalg.norm(rz, axis=1), 1e-12), BF16_RTOL, "inv_norm (in-kernel x)")
+        # ... and with the pooling matrix itself built inside the tower kernel from the token ids (tt_mlp_embed_t.ids):
+        # bit for bit the histogram kernel's P and 1/len, hence the same y / h1 / 1/|z|; int64 and int32 ids
+        for id_dtype, idb in ((torch.int64, 8), (torch.int32, 4)):
+            tid2 = tids.to(id_dtype).contiguous()
+            P3 = torch.zeros(R, V, dtype=torch.bfloat16, device=DEV); il3 = torch.zeros(R, **f32)
+            h1_3 = torch.zeros(R, H, **f32); yb3 = torch.zeros(R, H, dtype=torch.bfloat16, device=DEV); inv3 = torch.zeros(R, **f32)
+            femb3 = _lib.MlpEmbed(pt(P3), V, pt(ttab), pt(tabb), None, 0, None, 0, pt(tid2), idb, L, pt(il3))
+            rc = lib.tt_mlp_fwd(None, pt(tw1), pt(tb1), pt(tw2), pt(tb2), R, E, H, pt(h1_3), None, None, pt(yb3), None,
+                                pt(w1b), pt(w2b), None, pt(inv3), C.byref(femb3), 1, pt(ws), ws.numel(), s)
+            if rc == _lib.TT_ERR_UNSUPPORTED and (L > 255 or V > 128 * (E // 64)):
+                continue
+            _lib.check(rc, "mlp_fwd embed from ids")
+            torch.cuda.synchronize()
+            assert torch.equal(P3, P2) and torch.equal(il3, il2), "pooling matrix built in the tower kernel"
+            hb = lambda t_: t_.view(torch.bfloat16).reshape(-1)[:R * H]          # TT_PREC_BF16 keeps the hidden tile as bf16 in h1
+            assert torch.equal(yb3, yb2) and torch.equal(inv3, inv2) and torch.equal(hb(h1_3).view(torch.int16), hb(h1_2).view(torch.int16))
     # backward, embed-fused
     dw1 = torch.empty(H, E, **f32); db1 = torch.empty(H, **f32); dw2 = torch.empty(H, H, **f32); db2 = torch.empty(H, **f32)
     dtab = torch.full((V, E), 7.0, **f32)

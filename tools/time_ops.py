@@ -87,6 +87,8 @@ def main():
         if tr.onelaunch:                          # both as one kernel
             ops = {k: v for k, v in ops.items() if k != "ce_dd"}
             ops = {("ce_onepass" if k == "ce_fwd_dq" else k): (lambda: tr._local_loss_onepass(s())) if k == "ce_fwd_dq" else v for k, v in ops.items()}
+    if getattr(tr, "pool_in_tower", False):
+        del ops["embed_pool_fwd"]            # the tower kernel builds the pooling matrix itself
     if tr.embed_fused:
         del ops["embed_pool_bwd"]            # folded into the tower backward (tt_mlp_embed_t)
     total = 0.0

@@ -64,7 +64,7 @@ SIGNATURES = {
 class MlpEmbed(C.Structure):
     """tt_mlp_embed_t (include/tt_b200.h)"""
     _fields_ = [("pool_bf16", _vp), ("V", _i64), ("table", _vp), ("table_bf16", _vp), ("d_table", _vp), ("accumulate", _i),
-                ("workspace", _vp), ("workspace_bytes", _sz)]
+                ("workspace", _vp), ("workspace_bytes", _sz), ("ids", _vp), ("id_bytes", _i), ("L", _i), ("inv_len", _vp)]
 
 
 class P2P(C.Structure):

@@ -785,7 +785,8 @@ int tc_mlp_fwd(const float* x, const float* w1, const float* b1, const float* w2
   if (embed) {
     if (!w1_bf16 || !w2_bf16 || !tc_mlp_fwd_pool_supported(E, H, embed->V)) { set_error("tc_mlp_fwd: embed needs bf16 weight shadows and a supported shape (tt_mlp_fwd_embed_ok)"); return TT_ERR_UNSUPPORTED; }
     return tc_mlp_fwd_fused(nullptr, w1_bf16, b1, w2_bf16, b2, R, E, H, h1_bf16 ? h1_bf16 : reinterpret_cast<__nv_bfloat16*>(h1), z, y, y_bf16,
-                            inv_norm, (const __nv_bfloat16*)embed->pool_bf16, embed->V, (const __nv_bfloat16*)embed->table_bf16, s);
+                            inv_norm, (const __nv_bfloat16*)embed->pool_bf16, embed->V, (const __nv_bfloat16*)embed->table_bf16, s,
+                            embed->ids, embed->id_bytes, embed->L, embed->inv_len);
   }
   if (Ep != E) {                               // padded pitch: contiguous caller shadows of x / W1 cannot feed TMA, convert here
     if (embed) { set_error("tc_mlp_fwd: embed needs E %% 8 == 0"); return TT_ERR_UNSUPPORTED; }

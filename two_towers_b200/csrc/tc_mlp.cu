@@ -34,6 +34,12 @@ struct MlpFwdParams {
   __nv_bfloat16* yb;      // [R,H] nullable
   float* inv_norm;        // [R] nullable: 1 / max(|z|, 1e-12)
   int V;                  // > 0: x = P * table is formed in-kernel (GEMM 0) from the pooling matrix and the bf16 table
+  // ids != null (pool mode): the pooling matrix is BUILT here from the token ids (one integer histogram per row in shared
+  // memory, twotower/encoders.py:62-72 mask + mean) and stored to P [R,V] for the backward -- the separate histogram launch disappears
+  const void* ids;        // [R, L] int32 / int64, 0 = padding
+  int id_bytes, L;
+  float* inv_len;         // [R] nullable: 1 / (number of non-pad tokens + 1e-9)
+  long long* bad_id;      // mapped host word that records an out-of-range token id (nullable)
   long long* dbg;         // developer aid (TT_MLP_DEBUG): CTA 0, thread 64: %globaltimer at each phase boundary
 };
 
@@ -72,8 +78,9 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* bar_p = bars + 7;    // pool mode: P tile + table landed
   uint64_t* bar_acc0 = bars + 8; // pool mode: accumulator 0 (x) ready
   uint64_t* bar_x0 = bars + 9;   // pool mode: x tile written (4 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* ss_s = reinterpret_cast<float*>(bars + 12);               // [2][128] per-half row sums of squares
+  uint64_t* bar_pw = bars + 10;  // pool mode from ids: P tile written (the 4 warps of the first column half)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* ss_s = reinterpret_cast<float*>(bars + 13);               // [2][128] per-half row sums of squares
   const int kV = p.V / 64;                                         // pool mode: k-blocks of GEMM 0
   uint8_t* p_tile = h1_tile;                                       // [128 x V] bf16, kV k-blocks of 16 KB
   uint8_t* t_tile = h1_tile + (uint32_t)kV * MLP_BM * 128;         // table, MN-major: E/64 boxes of [V rows x 128 B]
@@ -85,7 +92,7 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     mbar_init(bar_x, 1); mbar_init(bar_w2a, 1); mbar_init(bar_w2b, 1); mbar_init(bar_g1, 1);
     mbar_init(bar_acc1, 1); mbar_init(bar_h1, 8); mbar_init(bar_acc2, 1);
-    mbar_init(bar_p, 1); mbar_init(bar_acc0, 1); mbar_init(bar_x0, 8);
+    mbar_init(bar_p, 1); mbar_init(bar_acc0, 1); mbar_init(bar_x0, 8); mbar_init(bar_pw, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -102,8 +109,9 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 0) {
     if (elect_one()) {
       if (kV > 0) {
-        mbar_arrive_expect_tx(bar_p, (uint32_t)kV * MLP_BM * 128 + (uint32_t)p.V * E * 2);
-        for (int kb = 0; kb < kV; ++kb) tma_load_2d(p_tile + kb * (MLP_BM * 128), &tmX, bar_p, kb * 64, (int)m0);
+        mbar_arrive_expect_tx(bar_p, (p.ids ? 0u : (uint32_t)kV * MLP_BM * 128) + (uint32_t)p.V * E * 2);
+        if (!p.ids)
+          for (int kb = 0; kb < kV; ++kb) tma_load_2d(p_tile + kb * (MLP_BM * 128), &tmX, bar_p, kb * 64, (int)m0);
         for (int nb = 0; nb < kE; ++nb) tma_load_2d(t_tile + (uint32_t)nb * p.V * 128, &tmT, bar_p, nb * 64, 0);
         mbar_arrive_expect_tx(bar_x, w1_bytes);
       } else {
@@ -133,6 +141,14 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint64_t dp = umma_desc_kmajor(smem_u32(p_tile), 0);
       const uint64_t dt = umma_desc_mnmajor(smem_u32(t_tile), 0, (uint32_t)p.V * 128);
       mbar_wait(bar_p, 0);
+      if (p.ids) {                                                 // P built by the warps: also the saved pooling matrix of the backward
+        mbar_wait(bar_pw, 0);
+        if (lane == 0) {
+          for (int kb = 0; kb < kV; ++kb) tma_store_2d(&tmX, p_tile + kb * (MLP_BM * 128), kb * 64, (int)m0);
+          tma_store_commit();
+        }
+        __syncwarp();
+      }
       tc_fence_after();
       for (int kb = 0; kb < kV; ++kb)
 #pragma unroll
@@ -153,6 +169,8 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           umma_bf16(tmem_a1, dx + (uint64_t)(kb * (MLP_BM * 128 / 16) + k * 2),
                     dw1 + (uint64_t)(kb * (w2_blk >> 4) + k * 2), idesc, (kb | k) != 0);
       }
+    if (kV > 0 && p.ids && lane == 0) tma_store_wait_read();    // the P tile (== hidden tile bytes) has been read out
+    __syncwarp();
     if (elect_one()) { umma_commit(bar_g1); umma_commit(bar_acc1); }
     __syncwarp();
     const uint64_t dh = umma_desc_kmajor(smem_u32(h1_tile), 0);
@@ -185,6 +203,49 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int nce = E / 32, nch = H / 32;                          // 32-column chunks (both even)
     TT_MLP_STAMP(1);
+    if (kV > 0 && p.ids && half == 0) {
+      // ---- pooling matrix from the token ids: P[r,v] = count_r(v) / (len_r + 1e-9), bf16, straight into the swizzled
+      // A tile of GEMM 0.  One THREAD per row (the 128 threads of the first column half): a private byte histogram in
+      // shared memory (counts <= L <= 64; it borrows the x-tile bytes, nothing lives there before GEMM 0 has retired), no
+      // atomics, no barriers, all 128 rows of the tile in flight at once.  Rows are rotated by 8 r bytes against each
+      // other so that equal ids of different rows fall into different banks.
+      const int V = p.V, L = p.L;
+      const int r = lrow;
+      uint8_t* h = x_tile + r * V;
+      const int rot = (V & (V - 1)) == 0 ? (8 * r) & (V - 1) : 0;
+      for (int i = 0; i < V; i += 16) *reinterpret_cast<uint4*>(h + i) = make_uint4(0u, 0u, 0u, 0u);
+      int cnt = 0;
+      if (row_ok) {
+        auto count = [&](long long id) {
+          if (id > 0 && id < V) { int pos = (int)id + rot; if (pos >= V) pos -= V; h[pos] = (uint8_t)(h[pos] + 1); ++cnt; }
+          // nn.Embedding raises IndexError for an id outside [0, V) (embeddings.py:33-40): treated as padding, recorded for the host
+          else if (id != 0 && p.bad_id) *reinterpret_cast<volatile long long*>(p.bad_id) = id * 2 + 1;
+        };
+        if (p.id_bytes == 4) {
+          const int* q = static_cast<const int*>(p.ids) + row * L;
+#pragma unroll 16
+          for (int t = 0; t < L; ++t) count(__ldg(q + t));
+        } else {
+          const long long* q = static_cast<const long long*>(p.ids) + row * L;
+#pragma unroll 16
+          for (int t = 0; t < L; ++t) count(__ldg(q + t));
+        }
+      }
+      const float il = 1.0f / ((float)cnt + 1e-9f);                 // encoders.py:72
+      if (p.inv_len && row_ok) p.inv_len[row] = il;
+      for (int c = 0; c < V / 8; ++c) {                             // 8 counts -> one 16-byte chunk of the swizzled tile
+        int pos = 8 * c + rot; if (pos >= V) pos -= V;
+        const uint2 w = *reinterpret_cast<const uint2*>(h + pos);
+        const uint4 v = make_uint4(pack_bf16x2((float)(w.x & 255u) * il, (float)((w.x >> 8) & 255u) * il),
+                                   pack_bf16x2((float)((w.x >> 16) & 255u) * il, (float)(w.x >> 24) * il),
+                                   pack_bf16x2((float)(w.y & 255u) * il, (float)((w.y >> 8) & 255u) * il),
+                                   pack_bf16x2((float)((w.y >> 16) & 255u) * il, (float)(w.y >> 24) * il));
+        *reinterpret_cast<uint4*>(p_tile + (uint32_t)(c >> 3) * (MLP_BM * 128) + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pw);
+    }
     if (kV > 0) {
       // ---- epilogue 0 (pool mode): x = acc0 -> bf16 -> swizzled x tile (A operand of GEMM 1) -----------------------
       mbar_wait(bar_acc0, 0);
@@ -316,7 +377,7 @@ tc_mlp_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 static size_t mlp_fused_smem(int E, int H) {
   const int kE = E / 64, kH = H / 64;
   return 1024 + (size_t)kE * MLP_BM * 128 + (size_t)kE * H * 128 + (size_t)(kH - 1) * H * 128 + (size_t)kH * MLP_BM * 128 +
-         2 * (size_t)H * 4 + 12 * 8 + 16 + 2 * MLP_BM * 4;
+         2 * (size_t)H * 4 + 13 * 8 + 16 + 2 * MLP_BM * 4;
 }
 
 }  // namespace tc
@@ -338,7 +399,7 @@ bool tc_mlp_fwd_pool_supported(int E, int H, int64_t V) {
 int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const float* b1, const __nv_bfloat16* w2b,
                      const float* b2, int64_t R, int E, int H, __nv_bfloat16* h1b, float* z, float* y,
                      __nv_bfloat16* yb, float* inv_norm, const __nv_bfloat16* pool, int64_t V, const __nv_bfloat16* table_bf16,
-                     cudaStream_t s) {
+                     cudaStream_t s, const void* ids, int id_bytes, int L, float* inv_len) {
   CUtensorMap tmX, tmW1, tmW2, tmH1, tmY, tmT;
   int rc;
   if (pool) {
@@ -356,6 +417,13 @@ int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const fl
   tc::MlpFwdParams p{};
   p.R = R; p.E = E; p.H = H; p.b1 = b1; p.b2 = b2; p.h1b = h1b; p.z = z; p.y = y; p.yb = yb; p.inv_norm = inv_norm;
   p.V = pool ? (int)V : 0;
+  if (ids) {
+    // a byte histogram per row borrows the x-tile bytes: 128 rows x V bytes must fit E/64 k-blocks of 16 KB; counts <= 255
+    if (!pool || L < 1 || L > 255 || (id_bytes != 4 && id_bytes != 8) || (size_t)tc::MLP_BM * V > (size_t)(E / 64) * tc::MLP_BM * 128) {
+      set_error("tc_mlp_fwd: building P from ids needs the pool mode, L <= 255 and V <= 128 E / 64"); return TT_ERR_UNSUPPORTED;
+    }
+    p.ids = ids; p.id_bytes = id_bytes; p.L = L; p.inv_len = inv_len; p.bad_id = bad_id_word();
+  }
   const size_t smem = tc::mlp_fused_smem(E, H);
   TT_CUDA(cudaFuncSetAttribute(tc::tc_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool dbg_on = getenv("TT_MLP_DEBUG") != nullptr;

@@ -31,7 +31,7 @@ bool tc_mlp_fused_supported(int E, int H);
 int tc_mlp_fwd_fused(const __nv_bfloat16* xb, const __nv_bfloat16* w1b, const float* b1, const __nv_bfloat16* w2b,
                      const float* b2, int64_t R, int E, int H, __nv_bfloat16* h1b, float* z, float* y,
                      __nv_bfloat16* yb, float* inv_norm, const __nv_bfloat16* pool, int64_t V, const __nv_bfloat16* table_bf16,
-                     cudaStream_t s);
+                     cudaStream_t s, const void* ids = nullptr, int id_bytes = 0, int L = 0, float* inv_len = nullptr);
 bool tc_mlp_fwd_pool_supported(int E, int H, int64_t V);
 
 // fused similarity GEMM + online-LSE cross entropy on tcgen05 (tc_inbatch.cu)

@@ -227,6 +227,12 @@ class FusedTrainer:
         self.embed_in_tower = bool(self.embed_fused and os.environ.get("TT_EMBED_IN_TOWER", "1") != "0" and
                                    self._shadow(self.table) is not None and
                                    self.lib.tt_mlp_fwd_embed_ok(self.E, self.H, self.V))
+        # ... and could build the histogram too (tt_mlp_embed_t.ids: one launch less per step, bitwise the same P).  Measured
+        # SLOWER (tower kernel 10.0 -> 17.7 us with a warp per row, 21.9 us with a thread per row, against 3.4 us for the
+        # stand-alone histogram launch that spreads the rows over 8192 warps): 64 CTAs x 8 warps cannot hide the per-row
+        # chain of shared-memory updates.  Kept for reference, off by default.
+        self.pool_in_tower = bool(self.embed_in_tower and self.L <= 255 and self.V <= 128 * (self.E // 64) and
+                                  os.environ.get("TT_POOL_IN_TOWER", "0") == "1")
         self.embed_ws = (torch.empty(int(max(self.lib.tt_mlp_embed_workspace(self.V, self.H, nr) for _, _, nr in self.groups)),
                                      dtype=torch.uint8, device=self.dev) if self.embed_fused else None)
         self.h1_bf16 = [torch.empty(nr, self.H, dtype=torch.bfloat16, device=self.dev) if bf else None
@@ -290,6 +296,11 @@ class FusedTrainer:
             if self.embed_in_tower:
                 emb = _lib.MlpEmbed(self.pool_bf16[r0:r0 + nr].data_ptr(), self.V, self.table.data_ptr(),
                                     self._shadow(self.table).data_ptr(), None, 0, None, 0)
+                if self.pool_in_tower:                      # the tower kernel builds P from the ids itself: no histogram launch
+                    emb.ids = self._ids_cur[r0:r0 + nr].data_ptr()
+                    emb.id_bytes = 8 if self.ids.dtype == torch.int64 else 4
+                    emb.L = self.L
+                    emb.inv_len = self.inv_len[r0:r0 + nr].data_ptr()
             check(lib.tt_mlp_fwd(_p(x), _p(l1.weight), _p(l1.bias), _p(l2.weight), _p(l2.bias), nr, self.E, self.H,
                                  _p(sv["h1"]), _p(z_ptr), _p(y_ptr), _p(yb), _p(xb),
                                  _p(self._shadow(l1.weight) if self.e_shadow else None),
@@ -375,9 +386,10 @@ class FusedTrainer:
         idb = 8 if self.ids.dtype == torch.int64 else 4
         s = self._stream()
         tower_pools = self.embed_in_tower                 # histogram only: the tower kernel multiplies P by the table
-        check(lib.tt_embed_pool_fwd(_p(self._ids_cur), idb, _p(self.table), R, self.L, self.V, self.E,
-                                    None if tower_pools else _p(self.pooled), _p(self.inv_len),
-                                    None if tower_pools else _p(self.pooled_bf16), _p(self.pool_bf16), s), "tt_embed_pool_fwd")
+        if not self.pool_in_tower:                        # ... or nothing at all: the tower kernel also builds P from the ids
+            check(lib.tt_embed_pool_fwd(_p(self._ids_cur), idb, _p(self.table), R, self.L, self.V, self.E,
+                                        None if tower_pools else _p(self.pooled), _p(self.inv_len),
+                                        None if tower_pools else _p(self.pooled_bf16), _p(self.pool_bf16), s), "tt_embed_pool_fwd")
         self._mark("embed_pool_fwd")
         for gi in range(len(self.groups)):
             self._tower_fwd(gi)

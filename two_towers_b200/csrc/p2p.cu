@@ -24,6 +24,8 @@
 // pushed round k+1, i.e. has finished summing round k.
 // Gradients: all-gather + a fixed rank-order sum on every rank (tt_p2p_sum_slots) instead of an all-reduce: the summed
 // gradient is bitwise identical on all ranks.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tt {
@@ -172,7 +174,11 @@ int tt_p2p_allgather_ctas(size_t bytes) {
   const size_t per_cta = 256 * 16 * 8;                                 // 32 KB per CTA
   size_t c = (bytes + per_cta - 1) / per_cta;
   if (c < 1) c = 1;
-  if (c > 64) c = 64;                                                  // leave SMs for whatever overlaps; NVLink saturates well below this
+  // leave SMs for whatever overlaps.  Measured at 8 ranks (bench.py, 20 steps): 64 / 148 / 296 CTAs give 390.5 / 391.0 / 391.3 us per
+  // step -- the exchanges are bound by their fences and by the wait for the slowest rank, not by store issue.  TT_P2P_CTAS
+  // overrides the cap (same value on every rank!).
+  static const size_t cap = [] { const char* e = getenv("TT_P2P_CTAS"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 64); }();
+  if (c > cap) c = cap;
   return (int)c;
 }
 

@@ -587,28 +587,50 @@ embed_finish_kernel(const ReduceJobs jobs, int red_units, int fin_x,
   float acc0 = 0.f, acc1 = 0.f;
   for (int k0 = 0; k0 < K; k0 += kFinK) {
     const int kc = min(kFinK, K - k0);
-    // A chunk: As[k][r] = second ? M[(r0 + r) * H + k0 + k] : M[(k0 + k) * H + r0 + r]
-    for (int i = threadIdx.x; i < kFinK * kFinRows; i += 256) {
-      int k, r;
-      if (second) { r = i / kFinK; k = i % kFinK; } else { k = i / kFinRows; r = i % kFinRows; }
-      float v = 0.f;
-      if (k < kc && r0 + r < rows) {
-        const float* mp = second ? M + (size_t)(r0 + r) * H + k0 + k : M + (size_t)(k0 + k) * H + r0 + r;
-        for (int pz = 0; pz < mparts; pz += 8) {           // slice order (bitwise reproducible), 8 independent loads in flight
-          float t[8];
+    // B chunk first (its loads are in flight under the slice sums below): kFinK * kFinCols / 4 / 256 = 8 float4 per thread
+    constexpr int NB = kFinK * (kFinCols / 4) / 256;
+    float4 bv[NB];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) t[u] = (pz + u < mparts) ? __ldg(mp + (size_t)(pz + u) * mstride) : 0.f;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v += t[u];
-        }
-      }
-      As[k][r] = v;
-    }
-    for (int i = threadIdx.x; i < kFinK * (kFinCols / 4); i += 256) {
+    for (int e = 0; e < NB; ++e) {
+      const int i = threadIdx.x + e * 256;
       const int k = i / (kFinCols / 4), c = (i % (kFinCols / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k < kc && c0 + c < E) v = __ldg(reinterpret_cast<const float4*>(B + (size_t)(k0 + k) * E + c0 + c));   // E % 4 == 0
-      *reinterpret_cast<float4*>(&Bs[k][c]) = v;
+      bv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < kc && c0 + c < E) bv[e] = __ldg(reinterpret_cast<const float4*>(B + (size_t)(k0 + k) * E + c0 + c));   // E % 4 == 0
+    }
+    // A chunk: As[k][r] = second ? M[(r0 + r) * H + k0 + k] : M[(k0 + k) * H + r0 + r]
+    // kFinK * kFinRows / 256 = 4 elements per thread; the slice loads of all four are issued together (32 in flight per
+    // thread and pass over eight slices): with one element at a time this staging ran at eight serial round trips per chunk
+    {
+      constexpr int NE = kFinK * kFinRows / 256;
+      const float* mp[NE];
+      float v[NE];
+      int kk[NE], rr[NE];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int i = threadIdx.x + e * 256;
+        int k, r;
+        if (second) { r = i / kFinK; k = i % kFinK; } else { k = i / kFinRows; r = i % kFinRows; }
+        kk[e] = k; rr[e] = r; v[e] = 0.f;
+        mp[e] = (k < kc && r0 + r < rows) ? (second ? M + (size_t)(r0 + r) * H + k0 + k : M + (size_t)(k0 + k) * H + r0 + r) : nullptr;
+      }
+      for (int pz = 0; pz < mparts; pz += 8) {             // slice order (bitwise reproducible)
+        float t[NE][8];
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[e][u] = (mp[e] && pz + u < mparts) ? __ldg(mp[e] + (size_t)(pz + u) * mstride) : 0.f;
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[e] += t[e][u];
+      }
+#pragma unroll
+      for (int e = 0; e < NE; ++e) As[kk[e]][rr[e]] = v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < NB; ++e) {
+      const int i = threadIdx.x + e * 256;
+      *reinterpret_cast<float4*>(&Bs[i / (kFinCols / 4)][(i % (kFinCols / 4)) * 4]) = bv[e];
     }
     __syncthreads();
 #pragma unroll 8

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TT_ABI_VERSION 4
+#define TT_ABI_VERSION 5
 
 enum { TT_OK = 0, TT_ERR_INVALID = -1, TT_ERR_CUDA = -2, TT_ERR_ARCH = -3, TT_ERR_WORKSPACE = -4,
        TT_ERR_UNSUPPORTED = -5 };
@@ -271,6 +271,22 @@ int tt_inbatch_ce_fwd_dq_p2p(const tt_ce_pass_t* q_pass, int H, float inv_temper
                              const struct tt_p2p_s* y_exchange, const void* y_own_bf16, void* stream);
 int tt_inbatch_ce_dd(const tt_ce_pass_t* d_pass, int H, float inv_temperature, float loss_scale, const float* grad_out,
                      void* stream);
+/* Stored-E form of the one-pass step (single process, or per-rank negatives): while the B_q x B_d bf16 matrix
+ * E = exp(S/temp - bound) fits in L2 (tt_inbatch_ce_stash_ok: H >= 128 and at most TT_CE_STASH_MAX_MB, default 48, MB),
+ * tt_inbatch_ce_fwd_dq_stash also writes every E tile it forms (TMA store of the tile it has just fed to the tensor cores; the
+ * positives left out), the rows x_i / L_i and 1 - P_pos(i) into `stash` (tt_inbatch_ce_stash_bytes, caller-owned, no
+ * initialisation), and tt_inbatch_ce_dd_stash forms the document gradient of twotower/losses.py:107-116 as ONE plain product
+ *   dd_j = g*loss_scale/temp * ( sum_i E_ij x_i / L_i  -  (1 - P_pos(i(j))) x_i(j) )
+ * (d_pass: x = documents, y = the queries of the first call, label_offset as there; lse is not used) -- S is formed once per
+ * step (6 B^2 H FLOP executed for the 6 B^2 H the loss and its two gradients need) and no exponential is taken twice.  The two
+ * calls must use the same stash on the same stream.  Results differ from tt_inbatch_ce_dd only by bf16 rounding of x / L. */
+int tt_inbatch_ce_stash_ok(int64_t Bq, int64_t Bd, int H);
+size_t tt_inbatch_ce_stash_bytes(int64_t Bq, int64_t Bd, int H);
+int tt_inbatch_ce_fwd_dq_stash(const tt_ce_pass_t* q_pass, int H, float inv_temperature, float logit_bound, float loss_scale,
+                               const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch, void* stash,
+                               void* stream);
+int tt_inbatch_ce_dd_stash(const tt_ce_pass_t* d_pass, int H, float inv_temperature, float loss_scale, const float* grad_out,
+                           const void* stash, void* stream);
 int tt_inbatch_ce_bwd_parts(const void* q_bf16, const void* d_bf16, const float* lse, int64_t Bq, int64_t Bd,
                             int H, float inv_temperature, int64_t label_offset, float loss_scale,
                             const float* grad_out, float* dq_parts, int64_t dq_part_stride,

@@ -83,6 +83,10 @@ def main():
         inv_t = 1.0 / tr.temperature
         ops["ce_fwd"] = lambda: check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, inv_t, 1.0 / B, None, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), _p(tr.onepass_sync), s()), "x")
         ops["ce_bwd"] = lambda: check(lib.tt_inbatch_ce_dd(C.byref(dp), H, inv_t, 1.0 / B, None, s()), "x")
+        if getattr(tr, "ce_stash", None) is not None:   # stored-E form: the first launch stores E, the second is a plain product
+            ops["ce_fwd"] = lambda: check(lib.tt_inbatch_ce_fwd_dq_stash(C.byref(qp), H, inv_t, inv_t, 1.0 / B, None, _p(tr.loss), _p(tr.lse), _p(tr.pos_mean), _p(tr.onepass_sync), _p(tr.ce_stash), s()), "x")
+            ops["ce_bwd"] = lambda: check(lib.tt_inbatch_ce_dd_stash(C.byref(dp), H, inv_t, 1.0 / B, None, _p(tr.ce_stash), s()), "x")
+            print("loss: stored-E form (tt_inbatch_ce_fwd_dq_stash + tt_inbatch_ce_dd_stash)")
         ops = {("ce_fwd_dq" if k == "ce_fwd" else "ce_dd" if k == "ce_bwd" else k): v for k, v in ops.items()}
         if tr.onelaunch:                          # both as one kernel
             ops = {k: v for k, v in ops.items() if k != "ce_dd"}

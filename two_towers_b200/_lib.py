@@ -16,7 +16,7 @@ TT_PREC_FP32 = 0
 TT_PREC_BF16 = 1
 TT_TOPK_MAX = 1024
 TT_ERR_UNSUPPORTED = -5
-TT_ABI_VERSION = 4          # must equal TT_ABI_VERSION in include/tt_b200.h (a stale .so fails loudly at load)
+TT_ABI_VERSION = 5          # must equal TT_ABI_VERSION in include/tt_b200.h (a stale .so fails loudly at load)
 
 _vp, _i, _i64, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
 
@@ -102,6 +102,10 @@ SIGNATURES.update({
     "tt_inbatch_ce_onepass_sync_bytes": (_sz, [_i64]),
     "tt_inbatch_ce_fwd_dq": (_i, [C.POINTER(CePass), _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tt_inbatch_ce_dd_nparts": (_i, [_i64, _i64, _i]),
+    "tt_inbatch_ce_stash_ok": (_i, [_i64, _i64, _i]),
+    "tt_inbatch_ce_stash_bytes": (_sz, [_i64, _i64, _i]),
+    "tt_inbatch_ce_fwd_dq_stash": (_i, [C.POINTER(CePass), _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tt_inbatch_ce_dd_stash": (_i, [C.POINTER(CePass), _i, _f, _f, _vp, _vp, _vp]),
     "tt_inbatch_ce_onepass": (_i, [C.POINTER(CePass), C.POINTER(CePass), _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tt_inbatch_ce_fwd_dq_p2p": (_i, [C.POINTER(CePass), _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, C.POINTER(P2P), _vp, _vp]),
     "tt_inbatch_ce_dd": (_i, [C.POINTER(CePass), _i, _f, _f, _vp, _vp]),

@@ -511,6 +511,37 @@ int tt_inbatch_ce_fwd_dq(const tt_ce_pass_t* q_pass, int H, float inv_temperatur
                                nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int tt_inbatch_ce_stash_ok(int64_t Bq, int64_t Bd, int H) {
+  if (Bq <= 0 || Bd <= 0 || H <= 0) return 0;
+  return tt::tc_inbatch_stash_ok(Bq, Bd, H);
+}
+size_t tt_inbatch_ce_stash_bytes(int64_t Bq, int64_t Bd, int H) {
+  return (Bq > 0 && Bd > 0 && H > 0) ? tt::tc_inbatch_stash_bytes(Bq, Bd, H) : 0;
+}
+
+int tt_inbatch_ce_fwd_dq_stash(const tt_ce_pass_t* q_pass, int H, float inv_temperature, float logit_bound, float loss_scale,
+                               const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch, void* stash,
+                               void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(q_pass && H > 0 && loss && lse && sync_scratch && stash, "inbatch_ce_fwd_dq_stash: bad arguments");
+  TT_CHECK_ARG(q_pass->x_bf16 && q_pass->y_bf16 && q_pass->x_rows > 0 && q_pass->y_rows > 0 && q_pass->y_buf_rows >= 1,
+               "inbatch_ce_fwd_dq_stash: null operand");
+  TT_CHECK_ARG(q_pass->label_offset >= 0 && q_pass->x_rows + q_pass->label_offset <= q_pass->y_rows,
+               "inbatch_ce_fwd_dq_stash: positives out of range");
+  return tt::tc_inbatch_fwd_dq(q_pass, H, inv_temperature, logit_bound, loss_scale, grad_out, loss, lse, pos_mean, sync_scratch,
+                               nullptr, nullptr, static_cast<cudaStream_t>(stream), stash);
+}
+
+int tt_inbatch_ce_dd_stash(const tt_ce_pass_t* d_pass, int H, float inv_temperature, float loss_scale, const float* grad_out,
+                           const void* stash, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(d_pass && H > 0 && d_pass->x_bf16 && d_pass->y_bf16 && d_pass->x_rows > 0 && d_pass->y_rows > 0 && stash,
+               "inbatch_ce_dd_stash: bad arguments");
+  TT_CHECK_ARG(d_pass->dz_bf16 ? (d_pass->dz_colsum && d_pass->inv_norm) : d_pass->out_parts != nullptr,
+               "inbatch_ce_dd_stash: needs dz_bf16 + dz_colsum + inv_norm, or out_parts");
+  return tt::tc_inbatch_dd_stored(d_pass, H, inv_temperature, loss_scale, grad_out, stash, static_cast<cudaStream_t>(stream));
+}
+
 int tt_inbatch_ce_fwd_dq_p2p(const tt_ce_pass_t* q_pass, int H, float inv_temperature, float logit_bound, float loss_scale,
                              const float* grad_out, float* loss, float* lse, float* pos_mean, void* sync_scratch,
                              const tt_p2p_t* y_exchange, const void* y_own, void* stream) {

@@ -401,6 +401,14 @@ struct BwdParams {
   const __nv_bfloat16* y_own;  // [gate_blk, H]: this rank's rows of Y where the exchange kernel reads them
   int64_t gate_blk;            // logical Y rows per source rank
   unsigned gate_timeout_s;
+  // Stored-E form of the document gradient (single-process / per-rank negatives, E small enough to stay in L2): MODE 2 also
+  // writes every P tile it forms (E = exp(logit - mfix) as bf16, the positives left out) to e[x_rows, e_pitch] with a TMA
+  // store, the rows x_i / L_i (bf16) to xs_out and 1 - P_pos to wpos_out; MODE 3 then forms the document gradient as the plain
+  // product  dD = E^T (X / L)  minus the positives' rank-one terms -- S is not recomputed and no exponential is taken twice.
+  int e_store;                 // MODE 2: 1 = write E / xs_out / wpos_out
+  __nv_bfloat16* xs_out;       // [Bx[0], H] bf16
+  float* wpos_out;             // [Bx[0]]
+  const float* wpos_in;        // MODE 3: [By[1]] 1 - P_pos of every query
 };
 
 // X rows = this CTA's 128 output rows, Y = streamed 128-row tiles.
@@ -419,11 +427,12 @@ constexpr int BWD_BN = 128;
 // also instruction-latency bound with one warp per scheduler.  Eight warps halve both.
 template <int MODE, int EW>
 __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtensorMap* tmY, const BwdParams& p,
-                                            uint8_t* base, const CUtensorMap* tmYown = nullptr, int tmem_mode = 0) {
+                                            uint8_t* base, const CUtensorMap* tmYown = nullptr, int tmem_mode = 0,
+                                            const CUtensorMap* tmE = nullptr) {
   // tmem_mode: 0 = allocate and free tensor memory here; 1 = allocate, leave it to a second body of the same kernel;
   // 2 = re-use that allocation and free it (the allocation permit is relinquished after the first tcgen05.alloc)
-  constexpr bool COL = MODE == 1;                           // MODE 0: dQ from saved lse, 1: dD, 2: forward + dQ in one pass
-  constexpr int PASS = COL ? 1 : 0;
+  constexpr bool COL = MODE == 1;                           // MODE 0: dQ from saved lse, 1: dD, 2: forward + dQ in one pass,
+  constexpr int PASS = (MODE == 1 || MODE == 3) ? 1 : 0;    //      3: dD from the E tiles MODE 2 stored (tmY = X / L, tmE = E)
   constexpr int NH = EW / 4;                                // warps per TMEM lane quarter
   constexpr int CW = BWD_BN / NH;                           // S columns per epilogue thread
   constexpr int HC = CW / 32;                               // 32-column register chunks per thread
@@ -465,13 +474,18 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   const bool rot = MODE == 2 && p.gate != nullptr;
   const int g_nblk = rot ? (int)(By / p.gate_blk) : 1, g_tpb = rot ? (int)(p.gate_blk / BWD_BN) : 1;
   const int g_tps = rot ? g_tpb / (int)gridDim.y : 1;
-  const int nt = rot ? g_nblk * g_tps : max(0, t_end - t_beg);
+  // MODE 3: the loop runs over 64-row K blocks of the split's query range (E3_ST stages of [64 x H] X/L + [64 x 128] E)
+  constexpr int E3_ST = 4, E3_BK = 64;
+  const int k3_beg = t_beg * (BWD_BN / E3_BK);
+  const int k3_end = min((int)ceil_div(By, (int64_t)E3_BK), t_end * (BWD_BN / E3_BK));
+  const int nt = MODE == 3 ? max(0, k3_end - k3_beg) : rot ? g_nblk * g_tps : max(0, t_end - t_beg);
+  const bool estore = MODE == 2 && p.e_store != 0;
   auto tile_at = [&](int i) -> int {
     if (!rot) return t_beg + i;
     const int b = i / g_tps;
     return ((p.gate_rank + b) % g_nblk) * g_tpb + (int)blockIdx.y * g_tps + (i - b * g_tps);
   };
-  const bool fused = MODE == 2 || p.dz[PASS] != nullptr;  // CTA-uniform (cluster-uniform): finish through the cluster tail
+  const bool fused = MODE >= 2 || p.dz[PASS] != nullptr;  // CTA-uniform (cluster-uniform): finish through the cluster tail
   float lsum = 0.f, pos_val = 0.f;                         // MODE 2: this thread's share of sum_j E_ij, its row's positive logit
   bool pos_found = false;
   long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (int)blockIdx.z == p.dbg_pass) ? p.dbg : nullptr;
@@ -483,11 +497,17 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   TT_CTA_STAMP(0);
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(tmX); tma_prefetch_desc(tmY);
+    if (MODE != 3) tma_prefetch_desc(tmX);
+    tma_prefetch_desc(tmY);
+    if (MODE == 3 || estore) tma_prefetch_desc(tmE);
     mbar_init(x_bar, 1);
-    for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, EW);
-    mbar_init(p_full, EW); mbar_init(p_empty, 1);
+    if (MODE == 3) {                                        // full[s] = y_full + s, empty[s] = y_full + E3_ST + s (8 consecutive words)
+      for (int s = 0; s < 2 * E3_ST; ++s) mbar_init(&y_full[s], 1);
+    } else {
+      for (int s = 0; s < BWD_STAGES; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
+      mbar_init(s_full, 1); mbar_init(s_empty, EW);
+      mbar_init(p_full, EW); mbar_init(p_empty, estore ? 2 : 1);   // stored-E: the TMA store of the P tile has read it, too
+    }
     mbar_init(o_full, 1);
     mbar_init(x_ready, EW);
     mbar_init(xfer_bar, 1);
@@ -510,7 +530,55 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
   const uint32_t tmem_s = tmem_base + 256;                // columns [256, 384): S tile
   const uint32_t tmem_x = tmem_base + 384;                // columns [384, 384 + H/2): X tile (TMEM A operand)
 
-  if (warp == 0) {
+  if (MODE == 3) {
+    // dD = E^T (X / L): a plain TMA -> tcgen05 pipeline, both operands read MN-major (E is stored [query][document], X / L
+    // [query][H]; the contraction runs over queries), no epilogue inside the loop.  Per 64-query block a CTA pulls 16 KB of E
+    // and 64 H / 128 x 16 KB of X / L through L2 for 512 tensor-pipe cycles: the loop is bound by L2 bandwidth, not by the MMAs.
+    const uint32_t q_bytes = (uint32_t)E3_BK * H * 2;       // X / L block: kq boxes of [64 rows x 128 B]
+    constexpr uint32_t e_bytes = E3_BK * CE_BM * 2;         // E block: 2 boxes of [64 rows x 128 B] = this CTA's 128 documents
+    const uint32_t st_bytes = q_bytes + e_bytes;
+    uint64_t* full3 = y_full;
+    uint64_t* empty3 = y_full + E3_ST;
+    if (warp == 0) {
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % E3_ST;
+        mbar_wait(&empty3[s], ((i / E3_ST) & 1) ^ 1);
+        uint8_t* st = y_tiles + s * st_bytes;
+        const int r0 = (k3_beg + i) * E3_BK;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full3[s], st_bytes);
+          for (int kb = 0; kb < kq; ++kb) tma_load_2d(st + kb * (E3_BK * 128), tmY, &full3[s], kb * 64, r0);
+          tma_load_2d(st + q_bytes, tmE, &full3[s], (int)x0, r0);
+          tma_load_2d(st + q_bytes + E3_BK * 128, tmE, &full3[s], (int)x0 + 64, r0);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      if (nt > 0) {
+        const uint32_t idesc = umma_idesc_bf16(CE_BM, H, 1, 1);
+        const uint64_t dq0 = umma_desc_mnmajor(smem_u32(y_tiles), 0, E3_BK * 128);
+        const uint64_t de0 = umma_desc_mnmajor(smem_u32(y_tiles) + q_bytes, 0, E3_BK * 128);
+        for (int i = 0; i < nt; ++i) {
+          const int s = i % E3_ST;
+          mbar_wait(&full3[s], (i / E3_ST) & 1);
+          tc_fence_after();
+          const uint64_t off = (uint64_t)((s * st_bytes) >> 4);
+#pragma unroll
+          for (int k = 0; k < E3_BK / 16; ++k) {              // 16 query rows per instruction: +2048 B in both operands
+            if (elect_one()) umma_bf16(tmem_o, de0 + off + (uint64_t)(k * 128), dq0 + off + (uint64_t)(k * 128), idesc, (i | k) != 0);
+          }
+          if (elect_one()) umma_commit(&empty3[s]);
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(o_full);
+        __syncwarp();
+      }
+    } else {
+      TT_CTA_STAMP(1);
+      if (nt > 0) { mbar_wait(o_full, 0); tc_fence_after(); }
+      TT_CTA_STAMP(2);
+    }
+  } else if (warp == 0) {
     unsigned g_target = 0, g_have = 0;                      // gate: this round's arrival target, bitmask of ranks seen arrived
     auto gate_wait = [&](int src) {                         // whole warp: every lane acquires, so the elected one has
       if (!gated || ((g_have >> src) & 1u)) return;
@@ -539,6 +607,21 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
       for (int kb = 0; kb < kq; ++kb) tma_load_2d(x_tile + kb * (CE_BM * 128), tmX, x_bar, kb * 64, (int)x0);
     }
     __syncwarp();
+    // stored-E form: this (otherwise idle) warp also sends every finished P tile -- two [128 x 64] swizzled boxes -- to
+    // E[x0.., y0..] with a TMA store and gives p_empty its second arrival once the store has read the tile.  It runs two
+    // tiles behind its own loads: the stage load(i + 1) needs is released by O(i - 2), i.e. after P(i - 2) anyway.
+    auto store_e = [&](int t) {
+      mbar_wait(p_full, t & 1);
+      if (lane == 0) {
+        const int yc = tile_at(t) * BWD_BN;
+        tma_store_2d(tmE, p_tile, yc, (int)x0);
+        tma_store_2d(tmE, p_tile + CE_BM * 128, yc + 64, (int)x0);
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(p_empty);
+      }
+      __syncwarp();
+    };
     for (int i = 0; i < nt; ++i) {                        // whole warp, uniform control flow; one lane issues
       const int s = i % BWD_STAGES;
       if (i == BWD_STAGES - 1) mbar_wait(x_ready, 0);     // the stage X borrowed is free once X lives in TMEM
@@ -557,6 +640,12 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         mbar_arrive_expect_tx(&y_full[s], y_bytes);
         for (int kb = 0; kb < kq; ++kb) tma_load_2d(yt + kb * (BWD_BN * 128), tm, &y_full[s], kb * 64, yc);
       }
+      __syncwarp();
+      if (estore && i >= BWD_STAGES - 1) store_e(i - (BWD_STAGES - 1));
+    }
+    if (estore) {
+      for (int i = max(0, nt - (BWD_STAGES - 1)); i < nt; ++i) store_e(i);
+      if (lane == 0) tma_store_wait();
       __syncwarp();
     }
   } else if (warp == 1) {
@@ -856,10 +945,16 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
           for (int i = 0; i < RPW; ++i) {
             const int64_t grow = gw0 + i;
             if (grow < Bx && cl) {
-              if (to_dz) cp_async_16(ybuf + (e * RPW + i) * H * 2 + lane * 16, p.xg[PASS] + grow * H + lane * 8);
+              if (to_dz || estore) cp_async_16(ybuf + (e * RPW + i) * H * 2 + lane * 16, p.xg[PASS] + grow * H + lane * 8);
               if (MODE == 2) cp_async_16(pbuf + (e * RPW + i) * H * 2 + lane * 16,
                                          (p.gate ? p.y_own + (grow + label_offset - (int64_t)p.gate_rank * p.gate_blk) * H
                                                  : p.yg[PASS] + (pbase + pr) * H) + lane * 8);
+              if (MODE == 3) {                               // the query whose positive this document is (if any)
+                const int64_t gi = grow - label_offset;
+                if (gi >= 0 && gi < By)
+                  cp_async_16(pbuf + (e * RPW + i) * H * 2 + lane * 16,
+                              p.yg[PASS] + ((gi / blk) * p.y_blk_stride[PASS] + (gi % blk) + p.y_blk_off[PASS]) * H + lane * 8);
+              }
             }
             if (MODE == 2 && ++pr == blk) { pr = 0; pbase += p.y_blk_stride[PASS]; }
           }
@@ -919,9 +1014,13 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
         TT_TAIL(4);
         TT_CTA_STAMP(6);
         // lane i <-> this warp's row i: per-rank weights of the fp16 partials; MODE 2: softmax normaliser, lse, loss partials
-        float wk[NS], wpos = 0.f;
+        float wk[NS], wpos = 0.f, inv_l = 0.f;
 #pragma unroll
         for (int k = 0; k < NS; ++k) wk[k] = 1.0f;
+        if (MODE == 3 && lane < RPW && gw0 + lane < Bx) {     // 1 - P_pos of the query this document is the positive of
+          const int64_t gi = gw0 + lane - label_offset;
+          if (gi >= 0 && gi < By) wpos = __ldcg(p.wpos_in + gi);
+        }
         if (MODE == 2) {
           float dl = 0.f, dpz = 0.f;
           if (lane < RPW && gw0 + lane < Bx) {
@@ -935,6 +1034,8 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
 #pragma unroll
             for (int k = 0; k < NS; ++k) wk[k] *= invL;      // O / L = sum_k (lsum_k / L) (O_k / lsum_k)
             wpos = Loff * invL;                              // 1 - P_pos, free of cancellation
+            inv_l = invL;
+            if (estore) p.wpos_out[gw0 + lane] = wpos;
             const float lse_r = p.mfix + logf(L), pl = pdot * p.inv_temp;
             p.lse_out[gw0 + lane] = lse_r;
             dl = lse_r - pl; dpz = pl;
@@ -970,9 +1071,9 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
             o0.x = fmaf(a0.x, w, o0.x); o0.y = fmaf(a0.y, w, o0.y); o0.z = fmaf(a1.x, w, o0.z); o0.w = fmaf(a1.y, w, o0.w);
             o1.x = fmaf(b0.x, w, o1.x); o1.y = fmaf(b0.y, w, o1.y); o1.z = fmaf(b1.x, w, o1.z); o1.w = fmaf(b1.y, w, o1.w);
           }
-          if (MODE == 2) {
+          const float wp = (MODE >= 2) ? -__shfl_sync(0xffffffffu, wpos, i) : 0.f;
+          if (MODE == 2 || (MODE == 3 && wp != 0.f)) {       // MODE 3: rows without a positive have nothing staged in pbuf
             const uint2 pa = *reinterpret_cast<const uint2*>(pbuf + r * H * 2 + yoA), pb = *reinterpret_cast<const uint2*>(pbuf + r * H * 2 + yoB);
-            const float wp = -__shfl_sync(0xffffffffu, wpos, i);
             o0.x = fmaf(wp, bf16lo_to_f32(pa.x), o0.x); o0.y = fmaf(wp, bf16hi_to_f32(pa.x), o0.y);
             o0.z = fmaf(wp, bf16lo_to_f32(pa.y), o0.z); o0.w = fmaf(wp, bf16hi_to_f32(pa.y), o0.w);
             if (c1) {
@@ -981,6 +1082,14 @@ __device__ __forceinline__ void ce_bwd_body(const CUtensorMap* tmX, const CUtens
             }
           }
           const bool valid = grow < Bx;                      // warp-uniform
+          if (MODE == 2 && estore && valid) {                // x_i / L_i: the B operand of the stored-E document gradient
+            const uint2 ya = *reinterpret_cast<const uint2*>(ybuf + r * H * 2 + yoA), yb = *reinterpret_cast<const uint2*>(ybuf + r * H * 2 + yoB);
+            const float il = __shfl_sync(0xffffffffu, inv_l, i);
+            if (c0) *reinterpret_cast<uint2*>(p.xs_out + grow * H + lc) =
+                make_uint2(pack_bf16x2(bf16lo_to_f32(ya.x) * il, bf16hi_to_f32(ya.x) * il), pack_bf16x2(bf16lo_to_f32(ya.y) * il, bf16hi_to_f32(ya.y) * il));
+            if (c1) *reinterpret_cast<uint2*>(p.xs_out + grow * H + 128 + lc) =
+                make_uint2(pack_bf16x2(bf16lo_to_f32(yb.x) * il, bf16hi_to_f32(yb.x) * il), pack_bf16x2(bf16lo_to_f32(yb.y) * il, bf16hi_to_f32(yb.y) * il));
+          }
           if (to_dz) {
             const uint2 ya = *reinterpret_cast<const uint2*>(ybuf + r * H * 2 + yoA), yb = *reinterpret_cast<const uint2*>(ybuf + r * H * 2 + yoB);
             const float y0 = c0 ? bf16lo_to_f32(ya.x) : 0.f, y1 = c0 ? bf16hi_to_f32(ya.x) : 0.f, y2 = c0 ? bf16lo_to_f32(ya.y) : 0.f, y3 = c0 ? bf16hi_to_f32(ya.y) : 0.f;
@@ -1131,11 +1240,21 @@ tc_ce_onepass_kernel(const __grid_constant__ CUtensorMap tmXq, const __grid_cons
 // forward + query gradient in one pass (MODE 2): grid = (row tiles, splits), one cluster per row tile
 __global__ void __launch_bounds__(64 + 8 * 32, 1)
 tc_ce_fwd_dq_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                    const __grid_constant__ CUtensorMap tmYown, const BwdParams p) {
+                    const __grid_constant__ CUtensorMap tmYown, const __grid_constant__ CUtensorMap tmE, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
   uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-  ce_bwd_body<2, 8>(&tmX, &tmY, p, base, &tmYown);
+  ce_bwd_body<2, 8>(&tmX, &tmY, p, base, &tmYown, 0, &tmE);
+}
+
+// document gradient from the stored E tiles (MODE 3): grid = (document row tiles, splits over the queries), one cluster per
+// row tile; tmXs = X / L [queries, H] (64-row boxes), tmE = E [queries, documents] (64-row boxes)
+__global__ void __launch_bounds__(64 + 8 * 32, 1)
+tc_ce_dd_stored_kernel(const __grid_constant__ CUtensorMap tmXs, const __grid_constant__ CUtensorMap tmE, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
+  uint8_t* base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+  ce_bwd_body<3, 8>(&tmXs, &tmXs, p, base, nullptr, 0, &tmE);
 }
 
 static size_t fwd_smem(int H) {
@@ -1391,9 +1510,29 @@ int tc_inbatch_onepass_ok(int64_t Bq, int64_t Bd, int H, float logit_bound) {
 }
 int tc_inbatch_dd_nparts(int64_t x_rows, int64_t y_rows) { return cluster_splits(ceil_div(x_rows, tc::CE_BM), y_rows); }
 
+// ---- stored-E form: what tt_inbatch_ce_fwd_dq leaves for tt_inbatch_ce_dd_stored ------------------------------------
+struct CeStash { __nv_bfloat16* e; int64_t pitch; __nv_bfloat16* xs; float* wpos; size_t bytes; };
+static CeStash stash_at(void* base, int64_t Bq, int64_t Bd, int H) {
+  CeStash st{};
+  st.pitch = (Bd + 63) / 64 * 64;
+  char* b = static_cast<char*>(base);
+  const size_t eb = align_up((size_t)Bq * st.pitch * 2), xb = align_up((size_t)Bq * H * 2), wb = align_up((size_t)Bq * 4);
+  st.e = reinterpret_cast<__nv_bfloat16*>(b);
+  st.xs = reinterpret_cast<__nv_bfloat16*>(b + eb);
+  st.wpos = reinterpret_cast<float*>(b + eb + xb);
+  st.bytes = eb + xb + wb;
+  return st;
+}
+size_t tc_inbatch_stash_bytes(int64_t Bq, int64_t Bd, int H) { return stash_at(nullptr, Bq, Bd, H).bytes; }
+// worth it while E stays in L2 between the two launches (126 MB, shared with everything else the step touches)
+int tc_inbatch_stash_ok(int64_t Bq, int64_t Bd, int H) {
+  static const size_t max_bytes = [] { const char* e = getenv("TT_CE_STASH_MAX_MB"); return (size_t)(e ? atoi(e) : 48) << 20; }();
+  return (tc_ce_supported(H) && H >= 128 && Bq > 0 && Bd > 0 && (size_t)Bq * ((Bd + 63) / 64 * 64) * 2 <= max_bytes) ? 1 : 0;
+}
+
 int tc_inbatch_fwd_dq(const tt_ce_pass_t* t, int H, float inv_temp, float logit_bound, float loss_scale, const float* grad_out,
                       float* loss, float* lse_out, float* pos_mean, void* sync_scratch, const tt_p2p_t* y_exchange, const void* y_own,
-                      cudaStream_t s) {
+                      cudaStream_t s, void* stash) {
   if (!tc_inbatch_onepass_ok(t->x_rows, t->y_rows, H, logit_bound)) {
     set_error("tc_inbatch_fwd_dq: needs H %% 64 == 0, H <= 256 and 2 * logit_bound * log2(e) < 120 (got H=%d bound=%g)", H, (double)logit_bound);
     return TT_ERR_UNSUPPORTED;
@@ -1404,13 +1543,20 @@ int tc_inbatch_fwd_dq(const tt_ce_pass_t* t, int H, float inv_temp, float logit_
   const bool to_dz = t->dz_bf16 != nullptr;
   if (to_dz && (!t->dz_colsum || !t->inv_norm)) { set_error("tc_inbatch_fwd_dq: dz needs dz_colsum and inv_norm"); return TT_ERR_INVALID; }
   if (!to_dz && !t->out_parts) { set_error("tc_inbatch_fwd_dq: needs dz_bf16 or out_parts (dq)"); return TT_ERR_INVALID; }
-  CUtensorMap tmX, tmY, tmYown;
+  CUtensorMap tmX, tmY, tmYown, tmE;
   int rc = tc::make_tmap_bf16(&tmX, t->x_bf16, (uint64_t)Bx, (uint64_t)H, tc::CE_BM); if (rc) return rc;
   rc = tc::make_tmap_bf16(&tmY, t->y_bf16, (uint64_t)t->y_buf_rows, (uint64_t)H, tc::BWD_BN); if (rc) return rc;
   tmYown = tmY;
+  tmE = tmX;
   const int64_t xt = ceil_div(Bx, tc::CE_BM);
   const int ns = cluster_splits(xt, By);
   tc::BwdParams p{};
+  if (stash) {
+    if (y_exchange || !tc_inbatch_stash_ok(Bx, By, H)) { set_error("tc_inbatch_fwd_dq: stash not supported for these shapes (see tt_inbatch_ce_stash_ok)"); return TT_ERR_UNSUPPORTED; }
+    const CeStash st = stash_at(stash, Bx, By, H);
+    rc = tc::make_tmap_bf16(&tmE, st.e, (uint64_t)Bx, (uint64_t)By, tc::CE_BM, (uint64_t)st.pitch); if (rc) return rc;
+    p.e_store = 1; p.xs_out = st.xs; p.wpos_out = st.wpos;
+  }
   p.lse[0] = nullptr; p.Bx[0] = Bx; p.By[0] = By; p.label_offset[0] = t->label_offset;
   p.y_blk[0] = y_blk; p.y_blk_stride[0] = t->y_blk_stride; p.y_blk_off[0] = t->y_blk_off;
   p.tiles_per_split[0] = (int)ceil_div(ceil_div(By, tc::BWD_BN), ns);
@@ -1446,7 +1592,7 @@ int tc_inbatch_fwd_dq(const tt_ce_pass_t* t, int H, float inv_temp, float logit_
   long long* dbg_dev = nullptr;
   const size_t ncta = (size_t)grid.x * grid.y, dbg_n = 2 * 64 * 8 + 8 * ncta;
   if (dbg_on) { cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p.dbg = dbg_dev; p.dbg_pass = 0; }
-  TT_CUDA(launch_kernel_cluster(tc::tc_ce_fwd_dq_kernel, grid, dim3(64 + 8 * 32), smem, s, true, (unsigned)ns, tmX, tmY, tmYown, p));
+  TT_CUDA(launch_kernel_cluster(tc::tc_ce_fwd_dq_kernel, grid, dim3(64 + 8 * 32), smem, s, true, (unsigned)ns, tmX, tmY, tmYown, tmE, p));
   TT_LAUNCH_CHECK("tc_ce_fwd_dq_kernel");
   if (dbg_on) {
     std::vector<long long> h(dbg_n);
@@ -1551,6 +1697,54 @@ int tc_inbatch_dd(const tt_ce_pass_t* t, int H, float inv_temp, float loss_scale
   CePass pq = pd;                                           // tensor maps need valid operands; the pass itself is not launched
   pq.out = nullptr; pq.dz = nullptr; pq.dz_colsum = nullptr; pq.inv_norm = nullptr;
   return launch_tc_bwd(pq, pd, H, inv_temp, tc_inbatch_dd_nparts(pd.Bx, pd.By), grad_out, loss_scale * inv_temp, s);
+}
+
+// document gradient from the stash tt_inbatch_ce_fwd_dq(stash = ...) left: x = documents, y = the queries of that call
+int tc_inbatch_dd_stored(const tt_ce_pass_t* t, int H, float inv_temp, float loss_scale, const float* grad_out, const void* stash,
+                         cudaStream_t s) {
+  const int64_t Bx = t->x_rows, By = t->y_rows;            // documents, queries
+  if (!tc_inbatch_stash_ok(By, Bx, H)) { set_error("tc_inbatch_dd_stored: unsupported shapes (see tt_inbatch_ce_stash_ok)"); return TT_ERR_UNSUPPORTED; }
+  const bool to_dz = t->dz_bf16 != nullptr;
+  if (to_dz && (!t->dz_colsum || !t->inv_norm)) { set_error("tc_inbatch_dd_stored: dz needs dz_colsum and inv_norm"); return TT_ERR_INVALID; }
+  if (!to_dz && !t->out_parts) { set_error("tc_inbatch_dd_stored: needs dz_bf16 or out_parts (dd)"); return TT_ERR_INVALID; }
+  const CeStash st = stash_at(const_cast<void*>(stash), By, Bx, H);
+  CUtensorMap tmXs, tmE;
+  int rc = tc::make_tmap_bf16(&tmXs, st.xs, (uint64_t)By, (uint64_t)H, 64); if (rc) return rc;
+  rc = tc::make_tmap_bf16(&tmE, st.e, (uint64_t)By, (uint64_t)Bx, 64, (uint64_t)st.pitch); if (rc) return rc;
+  const int64_t xt = ceil_div(Bx, tc::CE_BM);
+  const int ns = cluster_splits(xt, By);
+  tc::BwdParams p{};
+  p.Bx[1] = Bx; p.By[1] = By; p.label_offset[1] = t->label_offset;
+  p.y_blk[1] = t->y_blk > 0 ? t->y_blk : 1; p.y_blk_stride[1] = t->y_blk_stride; p.y_blk_off[1] = t->y_blk_off;
+  p.tiles_per_split[1] = (int)ceil_div(ceil_div(By, tc::BWD_BN), ns);
+  p.out[1] = to_dz ? nullptr : t->out_parts; p.part_stride[1] = 0;
+  p.dz[1] = (__nv_bfloat16*)t->dz_bf16; p.dz_colsum[1] = t->dz_colsum; p.inv_norm[1] = t->inv_norm;
+  p.xg[1] = (const __nv_bfloat16*)t->x_bf16; p.yg[1] = (const __nv_bfloat16*)t->y_bf16;
+  p.H = H; p.inv_temp = inv_temp; p.grad_out = grad_out; p.coef = loss_scale * inv_temp;
+  p.wpos_in = st.wpos;
+  const size_t smem = tc::bwd_smem(H);
+  TT_CUDA(cudaFuncSetAttribute(tc::tc_ce_dd_stored_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool dbg_on = getenv("TT_CE_DEBUG") != nullptr;
+  dim3 grid((unsigned)xt, (unsigned)ns, 1);
+  long long* dbg_dev = nullptr;
+  const size_t ncta = (size_t)grid.x * grid.y, dbg_n = 2 * 64 * 8 + 8 * ncta;
+  if (dbg_on) { cudaMalloc(&dbg_dev, dbg_n * sizeof(long long)); cudaMemset(dbg_dev, 0, dbg_n * sizeof(long long)); p.dbg = dbg_dev; p.dbg_pass = 0; }
+  TT_CUDA(launch_kernel_cluster(tc::tc_ce_dd_stored_kernel, grid, dim3(64 + 8 * 32), smem, s, true, (unsigned)ns, tmXs, tmE, p));
+  TT_LAUNCH_CHECK("tc_ce_dd_stored_kernel");
+  if (dbg_on) {
+    std::vector<long long> h(dbg_n);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h.data(), dbg_dev, dbg_n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dbg_dev);
+    const long long* c = h.data() + 2 * 64 * 8;
+    long long g0 = 0;
+    for (size_t i = 0; i < ncta; ++i) if (c[8 * i] && (!g0 || c[8 * i] < g0)) g0 = c[8 * i];
+    printf("[tt ce_dd_stored per-CTA, ns since first CTA start] grid %u x %u: start loop_begin loop_done | dumped sync2 stored\n", grid.x, grid.y);
+    for (size_t i = 0; i < ncta; i += 7)
+      printf("  cta %3zu: %6lld %6lld %6lld | %6lld %6lld %6lld\n", i, c[8 * i] - g0, c[8 * i + 1] - g0, c[8 * i + 2] - g0,
+             c[8 * i + 4] - g0, c[8 * i + 6] - g0, c[8 * i + 3] - g0);
+  }
+  return TT_OK;
 }
 
 static CePass plain_pass(const __nv_bfloat16* x, int64_t Bx, const __nv_bfloat16* y, int64_t By, const float* lse, int64_t off,

@@ -55,9 +55,13 @@ size_t tc_inbatch_onepass_sync_bytes(int64_t Bq);
 int tc_inbatch_onepass_ok(int64_t Bq, int64_t Bd, int H, float logit_bound);
 int tc_inbatch_dd_nparts(int64_t x_rows, int64_t y_rows);
 int tc_inbatch_fwd_dq(const tt_ce_pass_t* q_pass, int H, float inv_temp, float logit_bound, float loss_scale, const float* grad_out,
-                      float* loss, float* lse_out, float* pos_mean, void* sync_scratch, const tt_p2p_t* y_exchange, const void* y_own, cudaStream_t s);
+                      float* loss, float* lse_out, float* pos_mean, void* sync_scratch, const tt_p2p_t* y_exchange, const void* y_own, cudaStream_t s, void* stash = nullptr);
 int tc_inbatch_onepass_single(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temp, float logit_bound, float loss_scale,
                               const float* grad_out, float* loss, float* lse_out, float* pos_mean, void* sync_scratch, cudaStream_t s);
+size_t tc_inbatch_stash_bytes(int64_t Bq, int64_t Bd, int H);
+int tc_inbatch_stash_ok(int64_t Bq, int64_t Bd, int H);
+int tc_inbatch_dd_stored(const tt_ce_pass_t* d_pass, int H, float inv_temp, float loss_scale, const float* grad_out, const void* stash,
+                         cudaStream_t s);
 int tc_inbatch_dd(const tt_ce_pass_t* d_pass, int H, float inv_temp, float loss_scale, const float* grad_out, cudaStream_t s);
 int tc_inbatch_bwd_parts_ex(const tt_ce_pass_t* q_pass, const tt_ce_pass_t* d_pass, int H, float inv_temp, float loss_scale,
                             const float* grad_out, int nparts, cudaStream_t s);

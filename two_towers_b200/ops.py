@@ -281,10 +281,11 @@ _ONEPASS_SYNC = {}
 
 def inbatch_ce_onepass(q_bf16: torch.Tensor, d_bf16: torch.Tensor, temperature: float, label_offset: int = 0,
                        loss_scale: Optional[float] = None, grad_out: Optional[torch.Tensor] = None,
-                       logit_bound: Optional[float] = None):
+                       logit_bound: Optional[float] = None, stash: Optional[bool] = None):
     """Loss forward and both gradients of the in-batch softmax (twotower/losses.py:107-116) in TWO launches on unit-norm
     bf16 rows: ``tt_inbatch_ce_fwd_dq`` (forward + dq, S formed once, fixed softmax shift) and ``tt_inbatch_ce_dd``.
-    Returns (loss, lse, pos_mean, dq, dd) with fp32 gradients."""
+    ``stash`` (None: whenever ``tt_inbatch_ce_stash_ok``): the first launch also stores its E tiles and the second is the plain
+    product of ``tt_inbatch_ce_dd_stash`` -- nothing is recomputed.  Returns (loss, lse, pos_mean, dq, dd) with fp32 gradients."""
     _need_cuda(q_bf16, d_bf16, grad_out)
     assert q_bf16.dtype == torch.bfloat16 and d_bf16.dtype == torch.bfloat16
     lib = _lib_()
@@ -307,6 +308,18 @@ def inbatch_ce_onepass(q_bf16: torch.Tensor, d_bf16: torch.Tensor, temperature: 
         grad_out = _f32(grad_out)
     qp = _lib.CePass(q_bf16.data_ptr(), Bq, d_bf16.data_ptr(), Bd, Bd, Bd, 0, 0, None, int(label_offset), dq.data_ptr(), 0,
                      None, None, None)
+    stash_ok = bool(lib.tt_inbatch_ce_stash_ok(Bq, Bd, H))
+    if stash and not stash_ok:
+        raise RuntimeError(f"inbatch_ce_onepass: the stored-E form is not available for Bq={Bq} Bd={Bd} H={H}")
+    if stash or (stash is None and stash_ok):
+        buf = _workspace(lib.tt_inbatch_ce_stash_bytes(Bq, Bd, H), dev)
+        check(lib.tt_inbatch_ce_fwd_dq_stash(C.byref(qp), H, inv_t, bound, scale, _p(grad_out), _p(loss), _p(lse), _p(pm),
+                                             _p(sync), _p(buf), _stream()), "tt_inbatch_ce_fwd_dq_stash")
+        dd = torch.empty(Bd, H, **f32)
+        dp = _lib.CePass(d_bf16.data_ptr(), Bd, q_bf16.data_ptr(), Bq, Bq, Bq, 0, 0, None, int(label_offset),
+                         dd.data_ptr(), 0, None, None, None)
+        check(lib.tt_inbatch_ce_dd_stash(C.byref(dp), H, inv_t, scale, _p(grad_out), _p(buf), _stream()), "tt_inbatch_ce_dd_stash")
+        return loss, lse, pm, dq, dd
     check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, bound, scale, _p(grad_out), _p(loss), _p(lse), _p(pm), _p(sync),
                                    _stream()), "tt_inbatch_ce_fwd_dq")
     n = int(lib.tt_inbatch_ce_dd_nparts(Bd, Bq, H))

@@ -149,6 +149,12 @@ class FusedTrainer:
         if self.onepass:
             self.ce_fused = True
             self.onepass_sync = torch.zeros(int(self.lib.tt_inbatch_ce_onepass_sync_bytes(B)), dtype=torch.uint8, device=self.dev)
+        # stored-E form (per-rank negatives, B x B bf16 small enough to stay in L2): the first loss launch also stores its E
+        # tiles and the document gradient becomes one plain product (tt_inbatch_ce_dd_stash) -- S is formed once per step
+        self.ce_stash = None
+        if (self.onepass and self.local_fast and not self.onelaunch and os.environ.get("TT_CE_STASH", "1") != "0" and
+                self.lib.tt_inbatch_ce_stash_ok(B, B, self.H)):
+            self.ce_stash = torch.empty(int(self.lib.tt_inbatch_ce_stash_bytes(B, B, self.H)), dtype=torch.uint8, device=self.dev)
         if self.ce_fused:
             self.dz_bf16 = torch.empty(R, self.H, dtype=torch.bfloat16, device=self.dev)
             self.dz_colsum = torch.empty(R // 32, self.H, **f32)
@@ -483,6 +489,12 @@ class FusedTrainer:
             if rc != _lib.TT_ERR_UNSUPPORTED:
                 check(rc, "tt_inbatch_ce_onepass")
             self.onelaunch = False                          # shapes / device do not allow it: two launches from now on
+        if self.ce_stash is not None:
+            check(lib.tt_inbatch_ce_fwd_dq_stash(C.byref(qp), H, inv_t, inv_t, scale, None, _p(self.loss), _p(self.lse),
+                                                 _p(self.pos_mean), _p(self.onepass_sync), _p(self.ce_stash), s),
+                  "tt_inbatch_ce_fwd_dq_stash")
+            check(lib.tt_inbatch_ce_dd_stash(C.byref(dp), H, inv_t, scale, None, _p(self.ce_stash), s), "tt_inbatch_ce_dd_stash")
+            return
         check(lib.tt_inbatch_ce_fwd_dq(C.byref(qp), H, inv_t, inv_t, scale, None, _p(self.loss), _p(self.lse),
                                        _p(self.pos_mean), _p(self.onepass_sync), s), "tt_inbatch_ce_fwd_dq")
         check(lib.tt_inbatch_ce_dd(C.byref(dp), H, inv_t, scale, None, s), "tt_inbatch_ce_dd")

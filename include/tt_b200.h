@@ -384,6 +384,17 @@ int tt_p2p_allgather(const tt_p2p_t* x, const void* src, size_t bytes, void* str
  * A time-out never traps: the CUDA context stays usable and the host decides (raise, fall back to NCCL, retry). */
 int tt_p2p_status(const tt_p2p_t* x, int* timed_out_rank);
 int tt_p2p_sum_slots(const tt_p2p_t* x, size_t n_floats, float* out, void* stream);
+/* Row-sharded search in two launches per query batch (inference/search/two_tower.py:98-105 over a row-sharded index,
+ * SURVEY 8e): tt_topk_scan's scan kernel, then ONE kernel per query that (1) selects this shard's k best block candidates,
+ * (2) stores them -- rebased to global row numbers, id_offset + N < 2^32 -- into every rank's exchange slot over NVLink and
+ * bumps the arrival counters (the protocol of tt_p2p_allgather), (3) waits for every shard's k candidates and (4) selects the
+ * global top-k.  Every rank gets the same (out_scores, out_ids [nq,k], global ids; ties -> lower global row).  `x`: a
+ * double-buffered exchange whose `ctas` field equals nq and whose slots hold nq * k * 8 bytes (tt_topk_scan_p2p_ok); every
+ * rank calls it in step, on one stream.  workspace: tt_topk_scan_workspace(N, H, nq, k). */
+int tt_topk_scan_p2p_ok(const tt_p2p_t* x, int nq, int k);
+int tt_topk_scan_p2p(const void* index, int index_bf16, const float* queries, int64_t N, int H, int nq, int k,
+                     int cosine, int64_t id_offset, const tt_p2p_t* x, float* out_scores, int64_t* out_ids, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* ---- optimizer: torch.optim.AdamW(model.parameters(), lr), train.py:359 ------
  * One fused AdamW step over a flat fp32 parameter buffer (ATen _single_tensor_adamw

@@ -111,9 +111,10 @@ def _worker(rank, world, port, q_out):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
+        import ctypes as C
         import two_towers_b200 as tt
         from oracle import two_tower_oracle as O
-        from two_towers_b200 import parallel
+        from two_towers_b200 import parallel, _lib
         # ---- global in-batch negatives: loss / dq / dd vs the oracle on the concatenated batch -------------
         g = np.random.default_rng(0)
         B, H, t = 192, 256, 0.1
@@ -200,6 +201,24 @@ def _worker(rank, world, port, q_out):
             s2, i2 = st(qr)
             fs2, fi2 = tt.ops.topk_scan(torch.tensor(idx, device=dev), qr, k, cosine=False)
             assert torch.equal(i2, fi2) and torch.equal(s2, fs2), rep
+        assert st.fused                                      # scan + ONE merge / exchange / merge kernel (tt_topk_scan_p2p)
+        # one query, k = 100 (the benchmarked form), more rounds than buffer parities; then the three-launch chain it replaces
+        st1 = parallel.ShardedTopK(torch.tensor(idx[lo:hi], device=dev), 100, lo, tt.ops, cosine=True, nq=1)
+        assert st1.fused
+        os.environ["TT_SEARCH_FUSED"] = "0"
+        st0 = parallel.ShardedTopK(torch.tensor(idx[lo:hi], device=dev), 100, lo, tt.ops, cosine=True, nq=1)
+        os.environ.pop("TT_SEARCH_FUSED")
+        assert not st0.fused
+        for rep in range(9):
+            qr = torch.tensor(qs[rep % 3:rep % 3 + 1] if rep < 6 else idx[70_000 + rep:70_001 + rep], device=dev)
+            fs1, fi1 = tt.ops.topk_scan(torch.tensor(idx, device=dev), qr, 100, cosine=True)
+            s1, i1 = st1(qr)
+            assert torch.equal(i1, fi1) and torch.equal(s1, fs1), rep
+            s0, i0 = st0(qr)
+            assert torch.equal(i0, fi1) and torch.equal(s0, fs1), rep
+        rc = C.c_int(-1)
+        _lib.check(_lib.load().tt_p2p_status(C.byref(st1.xch.desc), C.byref(rc)), "tt_p2p_status")
+        assert rc.value == -1
         log = []
         _trainer_vs_oracle(rank, world, dev, log)
         if rank == 0:

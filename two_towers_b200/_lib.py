@@ -94,6 +94,8 @@ SIGNATURES.update({
     "tt_p2p_allgather": (_i, [_vp, _vp, _sz, _vp]),
     "tt_p2p_status": (_i, [_vp, _vp]),
     "tt_p2p_sum_slots": (_i, [_vp, _sz, _vp, _vp]),
+    "tt_topk_scan_p2p_ok": (_i, [C.POINTER(P2P), _i, _i]),
+    "tt_topk_scan_p2p": (_i, [_vp, _i, _vp, _i64, _i, _i, _i, _i, _i64, C.POINTER(P2P), _vp, _vp, _vp, _sz, _vp]),
     "tt_adamw_step_p2p": (_i, [_vp, _vp, C.POINTER(P2P), _vp, _vp, _i64] + [C.c_double] * 5 + [_vp, _vp, _vp, _vp, _vp]),
     "tt_inbatch_ce_bwd_fused_ok": (_i, [_i64, _i64, _i64, _i64, _i]),
     "tt_inbatch_ce_bwd_nparts_ex": (_i, [_i64, _i64, _i64, _i64, _i]),

@@ -24,6 +24,8 @@
 //     row-sharded multi-GPU search.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tt {
@@ -126,6 +128,13 @@ __device__ __forceinline__ float group8_sum(float v) {
 }
 
 constexpr int kScanThreads = 512;            // upper bound; large k launches fewer warps so the buffers fit
+constexpr int kSampleRows = 64;              // rows every warp scores unconditionally before the CTA fixes its starting threshold
+constexpr int kMaxCapPerLane = 8;            // packed block epilogue: candidate buffers of <= 256 keys travel through registers
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 // CPL = 16-byte chunks per lane (row = 8 lanes x CPL chunks), NQ queries per pass.
 template <int CPL, int NQ, bool BF16, bool COSINE>
@@ -136,6 +145,7 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   constexpr int EPC = BF16 ? 8 : 4;                        // elements per chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* sm = reinterpret_cast<u64*>(smem_raw);              // [NQ][warps][cap]
+  pdl_trigger();                                           // the merge kernel may be set up while this one streams the index
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kScanWarps = blockDim.x >> 5;
@@ -164,15 +174,21 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   WarpTopK tk[NQ];
 #pragma unroll
   for (int n = 0; n < NQ; ++n) tk[n].init(sm + ((size_t)n * kScanWarps + warp) * cap, cap, k);
+  // sample area behind the candidate buffers: [NQ][warps * kSampleRows] keys
+  const int nsamp = kScanWarps * kSampleRows;
+  u64* samp = sm + (size_t)NQ * kScanWarps * cap;
 
   const Chunk* base = reinterpret_cast<const Chunk*>(index);
   const int64_t quads = (N + 3) >> 2;
   const int64_t gw = (int64_t)blockIdx.x * kScanWarps + warp;
   const int64_t nw = (int64_t)gridDim.x * kScanWarps;
 
-  for (int64_t it = gw; it < quads; it += 2 * nw) {
+  // one step = two row quads of this warp (rows it*4.. and (it+nw)*4..).  SAMPLE steps store every score into the sample
+  // area instead of the warp's candidate buffer (slot = step * 8 + quad * 4 + row-in-quad).
+  auto step = [&](int64_t it, auto sample_tag, int sidx) {
+    constexpr bool SAMPLE = decltype(sample_tag)::value;
     const int64_t rowA = it * 4 + grp, rowB = (it + nw) * 4 + grp;
-    const bool okA = rowA < N, okB = (it + nw < quads) && rowB < N;
+    const bool okA = it < quads && rowA < N, okB = (it + nw < quads) && rowB < N;
     Chunk a[CPL], b[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
@@ -197,18 +213,77 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
       for (int c = 0; c < CPL; ++c) { da = dot_chunk(a[c], qf[n][c], da); db = dot_chunk(b[c], qf[n][c], db); }
       da = group8_sum(da); db = group8_sum(db);
       if (COSINE) { da = da * (qinv[n] * invA); db = db * (qinv[n] * invB); }
-      tk[n].push(okA && sub == 0 && da >= tk[n].thr, da, (uint32_t)rowA, lane);
-      tk[n].push(okB && sub == 0 && db >= tk[n].thr, db, (uint32_t)rowB, lane);
+      if (SAMPLE) {
+        if (sub == 0) {
+          u64* sp = samp + (size_t)n * nsamp + warp * kSampleRows + sidx * 8 + grp;
+          sp[0] = okA ? make_key(da, (uint32_t)rowA) : 0ull;
+          sp[4] = okB ? make_key(db, (uint32_t)rowB) : 0ull;
+        }
+      } else {
+        tk[n].push(okA && sub == 0 && da >= tk[n].thr, da, (uint32_t)rowA, lane);
+        tk[n].push(okB && sub == 0 && db >= tk[n].thr, db, (uint32_t)rowB, lane);
+      }
     }
-  }
+  };
 
-  // block epilogue: per-warp sort, then sort across the block's warps, emit the block top-k
+  // Sample phase.  A warp sees only rows / (148 * warps) rows of the index, so a threshold built from its OWN k best rows is
+  // weak on a small shard (1.25 M rows: 528 rows per warp, 19 % of them pass, and every warp sorts its buffer two or three
+  // times at the same moment -- measured 50-60 us on top of the 187 us the bytes take).  Instead every warp scores its first
+  // 64 rows unconditionally, the CTA sorts those warps * 64 sample keys once, and the score of the k-th best becomes the
+  // starting threshold of every warp: at least k rows of this CTA reach it, so no row below it can be in the CTA's top-k.
+  // The sample's k best keys continue as warp 0's candidates.  (k > warps * 64: no threshold, the scan works as before.)
+  int64_t it = gw;
+#pragma unroll 1
+  for (int i = 0; i < kSampleRows / 8; ++i, it += 2 * nw) step(it, std::true_type{}, i);
+  __syncthreads();
+#pragma unroll
+  for (int n = 0; n < NQ; ++n) {
+    u64* sp = samp + (size_t)n * nsamp;
+    bitonic_desc<true>(sp, nsamp, threadIdx.x, blockDim.x);
+    const u64 kth = k <= nsamp ? sp[k - 1] : 0ull;
+    const float thr0 = kth != 0ull ? bits_score((uint32_t)(kth >> 32)) : -CUDART_INF_F;
+    if (warp == 0) {
+      const int live = k <= nsamp ? k : nsamp;               // zero keys (rows past the end) sort last and are never live
+      int cnt = 0;
+      for (int i = lane; i < live; i += 32) { const u64 key = sp[i]; tk[n].buf[i] = key; cnt += key != 0ull; }
+      tk[n].count = warp_sum_int(cnt);
+    }
+    tk[n].thr = thr0;
+  }
+  __syncwarp();
+
+  for (; it < quads; it += 2 * nw) step(it, std::false_type{}, 0);
+
+  // block epilogue: every warp sorts its own buffer; the live keys of all warps are packed into one contiguous run (usually
+  // ~1 k keys instead of warps * cap slots), sorted, and the block top-k goes to global
+  __shared__ int s_cnt[kScanThreads / 32 + 1];
 #pragma unroll
   for (int n = 0; n < NQ; ++n) {
     tk[n].prune(lane);
-    __syncthreads();
     u64* region = sm + (size_t)n * kScanWarps * cap;
-    bitonic_desc<true>(region, kScanWarps * cap, threadIdx.x, blockDim.x);
+    u64 keep[kMaxCapPerLane];
+    const int cnt = tk[n].count;
+#pragma unroll
+    for (int u = 0; u < kMaxCapPerLane; ++u) keep[u] = (u * 32 + lane < cnt) ? tk[n].buf[u * 32 + lane] : 0ull;
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w = 0; w < kScanWarps; ++w) { const int c = s_cnt[w]; off += w < warp ? c : 0; total += c; }
+    int n2 = 32;
+    while (n2 < total || n2 < k) n2 <<= 1;
+    const bool packed = cap <= 32 * kMaxCapPerLane;          // larger caps (k > 128) keep the full-region sort
+    if (packed) {
+#pragma unroll
+      for (int u = 0; u < kMaxCapPerLane; ++u)
+        if (u * 32 + lane < cnt) region[off + u * 32 + lane] = keep[u];
+      for (int i = total + threadIdx.x; i < n2; i += blockDim.x) region[i] = 0ull;
+      __syncthreads();
+      bitonic_desc<true>(region, n2, threadIdx.x, blockDim.x);
+    } else {
+      for (int i = cnt + lane; i < cap; i += 32) tk[n].buf[i] = 0ull;
+      __syncthreads();
+      bitonic_desc<true>(region, kScanWarps * cap, threadIdx.x, blockDim.x);
+    }
     u64* out = cand + ((size_t)(q0 + n) * gridDim.x + blockIdx.x) * k;
     for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = region[i];
     __syncthreads();
@@ -279,15 +354,18 @@ constexpr int kMergeThreads = 1024;
 // search is a warp-parallel suffix scan instead of a 256-step serial loop.
 constexpr int kMergeRegKeys = 16;          // 1024 threads x 16 = 16384 keys in registers (148 block lists x k <= 110)
 
+struct MergeShared {
+  unsigned int hist[256];
+  u64 sel[TT_TOPK_MAX];
+  u64 prefix, mask;
+  int need, count, all;
+};
+
+// the whole CTA (kMergeThreads threads): leaves the k largest of the L keys src.get(q, 0..L) in sh.sel[0..k), descending
+// (zero-padded when fewer than k keys are live); ends with a CTA-wide barrier
 template <typename Keys>
-__global__ void __launch_bounds__(kMergeThreads)
-merge_topk_kernel(Keys src, int64_t L, int k, int64_t id_offset, float* __restrict__ out_scores,
-                  int64_t* __restrict__ out_ids) {
-  __shared__ unsigned int hist[256];
-  __shared__ u64 sel[TT_TOPK_MAX];
-  __shared__ u64 s_prefix, s_mask;
-  __shared__ int s_need, s_count, s_all;
-  const int q = blockIdx.x, tid = threadIdx.x;
+__device__ __forceinline__ void select_topk_sorted(const Keys& src, int q, int64_t L, int k, MergeShared& sh) {
+  const int tid = threadIdx.x;
   const bool in_regs = L <= (int64_t)kMergeRegKeys * kMergeThreads;
   u64 mine[kMergeRegKeys];
   if (in_regs) {
@@ -297,23 +375,23 @@ merge_topk_kernel(Keys src, int64_t L, int k, int64_t id_offset, float* __restri
       mine[u] = i < L ? src.get(q, i) : 0ull;               // 0 never matches a live prefix: see below
     }
   }
-  if (tid == 0) { s_prefix = 0ull; s_mask = 0ull; s_need = k; s_count = 0; s_all = 0; }
-  for (int i = tid; i < TT_TOPK_MAX; i += kMergeThreads) sel[i] = 0ull;
+  if (tid == 0) { sh.prefix = 0ull; sh.mask = 0ull; sh.need = k; sh.count = 0; sh.all = 0; }
+  for (int i = tid; i < TT_TOPK_MAX; i += kMergeThreads) sh.sel[i] = 0ull;
   __syncthreads();
   for (int shift = 56; shift >= 0; shift -= 8) {
-    for (int i = tid; i < 256; i += kMergeThreads) hist[i] = 0u;
+    for (int i = tid; i < 256; i += kMergeThreads) sh.hist[i] = 0u;
     __syncthreads();
-    const u64 prefix = s_prefix, mask = s_mask;
+    const u64 prefix = sh.prefix, mask = sh.mask;
     if (in_regs) {
 #pragma unroll
       for (int u = 0; u < kMergeRegKeys; ++u) {
         const u64 key = mine[u];
-        if (key != 0ull && (key & mask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & 0xffull)], 1u);
+        if (key != 0ull && (key & mask) == prefix) atomicAdd(&sh.hist[(unsigned)((key >> shift) & 0xffull)], 1u);
       }
     } else {
       for (int64_t i = tid; i < L; i += kMergeThreads) {
         const u64 key = src.get(q, i);
-        if (key != 0ull && (key & mask) == prefix) atomicAdd(&hist[(unsigned)((key >> shift) & 0xffull)], 1u);
+        if (key != 0ull && (key & mask) == prefix) atomicAdd(&sh.hist[(unsigned)((key >> shift) & 0xffull)], 1u);
       }
     }
     __syncthreads();
@@ -321,66 +399,233 @@ merge_topk_kernel(Keys src, int64_t L, int k, int64_t id_offset, float* __restri
       // lane l owns bins [8l, 8l+8).  Walking from bin 255 down, find the bin in which the running count reaches `need`.
       unsigned c[8], lane_sum = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { c[j] = hist[8 * tid + j]; lane_sum += c[j]; }
+      for (int j = 0; j < 8; ++j) { c[j] = sh.hist[8 * tid + j]; lane_sum += c[j]; }
       unsigned above = lane_sum;                               // inclusive suffix sum over lanes tid..31
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned t = __shfl_down_sync(0xffffffffu, above, o);
         if (tid + o < 32) above += t;
       }
-      const int need = s_need;
+      const int need = sh.need;
       const unsigned excl = above - lane_sum;                   // keys in bins above this lane's
       const bool here = excl < (unsigned)need && above >= (unsigned)need;
       const unsigned who = __ballot_sync(0xffffffffu, here);
       if (who == 0u) {                                          // fewer than k live keys in total (first pass only):
-        if (tid == 0) { s_all = 1; s_prefix = 0ull; }           // every live key is selected, the rest is padding
+        if (tid == 0) { sh.all = 1; sh.prefix = 0ull; }         // every live key is selected, the rest is padding
       } else if (here) {
         int rem = need - (int)excl, bin = 7;
         for (; bin > 0; --bin) {
           if ((int)c[bin] >= rem) break;
           rem -= (int)c[bin];
         }
-        s_need = rem;
-        s_prefix = prefix | ((u64)(8 * tid + bin) << shift);
-        s_mask = mask | (0xffull << shift);
+        sh.need = rem;
+        sh.prefix = prefix | ((u64)(8 * tid + bin) << shift);
+        sh.mask = mask | (0xffull << shift);
         // the chosen bin holds exactly the keys still needed: every key >= prefix (lower digits zero) is selected and the
         // remaining digit passes cannot change that -- stop (typically after the 3rd of 8 passes)
-        if ((int)c[bin] == rem) s_all = 1;
+        if ((int)c[bin] == rem) sh.all = 1;
       }
     }
     __syncthreads();
-    if (s_all) break;                                        // CTA-uniform
+    if (sh.all) break;                                       // CTA-uniform
   }
-  const u64 kth = s_prefix;                                // exact k-th largest key (keys are unique); 0 = take all
+  const u64 kth = sh.prefix;                               // exact k-th largest key (keys are unique); 0 = take all
   if (in_regs) {
 #pragma unroll
     for (int u = 0; u < kMergeRegKeys; ++u) {
       const u64 key = mine[u];
       if (key >= kth && key != 0ull) {
-        const int p = atomicAdd(&s_count, 1);
-        if (p < TT_TOPK_MAX) sel[p] = key;
+        const int p = atomicAdd(&sh.count, 1);
+        if (p < TT_TOPK_MAX) sh.sel[p] = key;
       }
     }
   } else {
     for (int64_t i = tid; i < L; i += kMergeThreads) {
       const u64 key = src.get(q, i);
       if (key >= kth && key != 0ull) {
-        const int p = atomicAdd(&s_count, 1);
-        if (p < TT_TOPK_MAX) sel[p] = key;
+        const int p = atomicAdd(&sh.count, 1);
+        if (p < TT_TOPK_MAX) sh.sel[p] = key;
       }
     }
   }
   __syncthreads();
   int n2 = 32;
   while (n2 < k) n2 <<= 1;
-  bitonic_desc<true>(sel, n2, tid, kMergeThreads);
-  for (int i = tid; i < k; i += kMergeThreads) {
-    const u64 key = sel[i];
+  bitonic_desc<true>(sh.sel, n2, tid, kMergeThreads);
+}
+
+// Fast path for G DESCENDING lists of k keys (the scan's per-block lists, the shards' candidate lists): the first
+// r = ceil(k / G) keys of every list are G r >= k distinct keys, so the k-th largest of these heads is a lower bound T of the
+// k-th largest key overall; only keys >= T can be selected.  With 148 block lists of 100 that leaves a few hundred of the
+// 14 800 keys: one 256-key sort for T, one pass over the keys (already in registers), one sort of the survivors -- instead of
+// three or four 8-bit radix passes over everything.  Returns false (nothing decided, sh in an arbitrary state) when the shape
+// or the data do not fit: fewer than k live heads, more than TT_TOPK_MAX survivors; the caller then runs the radix select.
+template <typename Lists>
+__device__ __forceinline__ bool select_from_lists(const Lists& src, int q, int G, int k, MergeShared& sh) {
+  const int tid = threadIdx.x;
+  const int r = (k + G - 1) / G;
+  const int nh = G * r;
+  const int64_t L = (int64_t)G * k;
+  if (nh > TT_TOPK_MAX || L > (int64_t)kMergeRegKeys * kMergeThreads) return false;   // CTA-uniform
+  u64 mine[kMergeRegKeys];
+  {
+    // key i = u * 1024 + tid lives at (list i / k, position i % k): one division, then strides of 1024 keys
+    int g = tid / k, pos = tid - g * k;
+    const int dg = kMergeThreads / k, dp = kMergeThreads - dg * k;
+    const int iL = (int)L;
+#pragma unroll
+    for (int u = 0; u < kMergeRegKeys; ++u) {
+      mine[u] = u * kMergeThreads + tid < iL ? src.at(q, g, pos) : 0ull;
+      g += dg; pos += dp;
+      if (pos >= k) { pos -= k; ++g; }
+    }
+  }
+  // Both selections are RANK computations over a few hundred unique keys held one per thread (every thread counts the keys
+  // larger than its own: broadcast reads of shared memory, ONE barrier) -- a 256-key bitonic sort by 32 warps spends 36
+  // CTA-wide barriers, ~5 us, for the same answer.
+  const u64 head = tid < nh ? src.at(q, tid / r, tid - (tid / r) * r) : 0ull;
+  if (tid < nh) sh.sel[tid] = head;
+  if (tid == 0) { sh.count = 0; sh.prefix = 0ull; }
+  __syncthreads();
+  if (tid < nh && head != 0ull) {
+    int rank = 0;
+    for (int j = 0; j < nh; ++j) rank += sh.sel[j] > head;
+    if (rank == k - 1) sh.prefix = head;                     // the k-th largest head (keys are unique)
+  }
+  __syncthreads();
+  const u64 thr = sh.prefix;
+  if (thr == 0ull) return false;                             // fewer than k live heads (tiny shards); CTA-uniform
+#pragma unroll
+  for (int u = 0; u < kMergeRegKeys; ++u) {
+    const u64 key = mine[u];
+    if (key >= thr) {
+      const int p = atomicAdd(&sh.count, 1);
+      if (p < TT_TOPK_MAX) sh.sel[p] = key;
+    }
+  }
+  __syncthreads();
+  const int S = sh.count;                                    // >= k: the heads themselves
+  if (S > kMergeThreads || S > TT_TOPK_MAX) { __syncthreads(); return false; }
+  const u64 key = tid < S ? sh.sel[tid] : 0ull;
+  int rank = 0;
+  if (tid < S)
+    for (int j = 0; j < S; ++j) rank += sh.sel[j] > key;
+  __syncthreads();                                           // every survivor is in a register: permute in place
+  if (tid < S) sh.sel[rank] = key;
+  __syncthreads();
+  return true;
+}
+struct RawLists {               // RawKeys seen as per_query / k sorted lists of k keys
+  const u64* keys; int64_t per_query; int k;
+  __device__ __forceinline__ u64 at(int q, int g, int pos) const { return keys[(int64_t)q * per_query + (int64_t)g * k + pos]; }
+};
+template <typename Keys>
+__device__ __forceinline__ bool try_sorted_lists(const Keys&, int, int64_t, int, MergeShared&) { return false; }
+__device__ __forceinline__ bool try_sorted_lists(const RawKeys& src, int q, int64_t L, int k, MergeShared& sh) {
+  if (L % k != 0 || L / k > 0x7fffffff) return false;
+  return select_from_lists(RawLists{src.keys, src.per_query, k}, q, (int)(L / k), k, sh);
+}
+
+__device__ __forceinline__ void write_topk(const MergeShared& sh, int q, int k, int64_t id_offset, float* __restrict__ out_scores,
+                                           int64_t* __restrict__ out_ids) {
+  for (int i = threadIdx.x; i < k; i += kMergeThreads) {
+    const u64 key = sh.sel[i];
     if (key == 0ull) { out_scores[(int64_t)q * k + i] = -CUDART_INF_F; out_ids[(int64_t)q * k + i] = -1; }
     else {
       out_scores[(int64_t)q * k + i] = bits_score((uint32_t)(key >> 32));
       out_ids[(int64_t)q * k + i] = (int64_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull)) + id_offset;
     }
+  }
+}
+
+template <typename Keys>
+__global__ void __launch_bounds__(kMergeThreads)
+merge_topk_kernel(Keys src, int64_t L, int k, int64_t id_offset, float* __restrict__ out_scores,
+                  int64_t* __restrict__ out_ids) {
+  __shared__ MergeShared sh;
+  pdl_wait();                                                // launched programmatically behind the scan (tt_topk_scan); a no-op otherwise
+  if (!try_sorted_lists(src, blockIdx.x, L, k, sh)) select_topk_sorted(src, blockIdx.x, L, k, sh);
+  write_topk(sh, blockIdx.x, k, id_offset, out_scores, out_ids);
+}
+
+// ---- row-sharded search: block merge + candidate exchange over NVLink peer memory + final merge in ONE launch ---------
+// (local top-k per shard merged by all-gather).  One CTA per query:
+//   1. radix-select this shard's k best keys out of the scan's per-block lists (as merge_topk_kernel does) and rebase their
+//      row field to GLOBAL row numbers (id_offset + N_total < 2^32), so keys of different shards compare directly:
+//      higher score first, ties -> lower global row (BASELINE tie rule);
+//   2. store the k keys into slot `rank` of EVERY rank's exchange buffer (8-byte stores over NVLink), fence.sys, and bump
+//      every rank's arrival counter for this source -- the protocol of p2p_allgather_kernel (p2p.cu): counters only grow,
+//      round r expects r * ctas arrivals per source, rounds alternate between the two slot sets;
+//   3. wait until every source's counter in the LOCAL header has reached the round's target (bounded: a peer that never
+//      arrives is reported through header word 34, tt_p2p_status);
+//   4. radix-select the k best of the world * k gathered keys (read through L2: the peers' stores bypass this SM's L1) and
+//      write scores / global ids.
+// Replaces three launches of the plain chain (block merge, tt_p2p_allgather, tt_topk_merge) and their two boundaries.
+struct P2PSearchArgs {
+  int world, rank, halves;
+  unsigned timeout_s;
+  unsigned char* base[8];
+  size_t slot_bytes;
+};
+struct GatheredKeys {           // world slots of [nq][kpad] keys, every slot's k keys descending
+  const u64* keys; int64_t slot_keys; int k, kpad;
+  __device__ __forceinline__ u64 get(int q, int64_t i) const { return __ldcg(keys + (i / k) * slot_keys + (int64_t)q * kpad + (i % k)); }
+  __device__ __forceinline__ u64 at(int q, int g, int pos) const { return __ldcg(keys + (int64_t)g * slot_keys + (int64_t)q * kpad + pos); }
+};
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_exchange_merge_kernel(const u64* __restrict__ cand, int64_t per_query, int k, int kpad, unsigned id_offset, const P2PSearchArgs a,
+                            float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  __shared__ MergeShared sh;
+  __shared__ unsigned s_round;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  unsigned* hdr = reinterpret_cast<unsigned*>(a.base[a.rank]);
+  pdl_wait();                                                // the scan kernel has retired (this kernel is launched programmatically behind it)
+  if (tid == 0) {
+    atomicAdd(hdr + 36, 1u);                                         // CTAs started (see p2p_allgather_kernel)
+    s_round = *reinterpret_cast<volatile unsigned*>(hdr + 32) + 1u;  // every CTA reads it before the last one out bumps it
+  }
+  RawKeys src{cand, per_query};
+  if (!try_sorted_lists(src, q, per_query, k, sh)) select_topk_sorted(src, q, per_query, k, sh);
+  const unsigned round = s_round;
+  const size_t half_off = (a.halves == 2 && (round & 1u)) ? (size_t)a.world * a.slot_bytes : 0;
+  const size_t slot0 = 256 + half_off;                               // kP2PHeaderBytes
+  if (tid < kpad) {
+    u64 key = tid < k ? sh.sel[tid] : 0ull;
+    if (key != 0ull) key -= (u64)id_offset;                          // row field = ~row: ~(row + off) = ~row - off (no borrow: row + off < 2^32)
+    for (int p = 0; p < a.world; ++p)
+      reinterpret_cast<u64*>(a.base[p] + slot0 + (size_t)a.rank * a.slot_bytes)[(size_t)q * kpad + tid] = key;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < a.world) {
+    unsigned* peer = reinterpret_cast<unsigned*>(a.base[tid]) + a.rank;
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(peer), "r"(1u) : "memory");
+    const unsigned target = round * gridDim.x;                       // the exchange's CTA count == this grid (checked on the host)
+    const unsigned* c = hdr + tid;
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+      if (v >= target) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > (unsigned long long)a.timeout_s * 1000000000ull) {   // give up, tell the host, keep the context alive
+        hdr[34] = 1u + tid;
+        __threadfence_system();
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  GatheredKeys g{reinterpret_cast<const u64*>(a.base[a.rank] + slot0), (int64_t)(a.slot_bytes / 8), k, kpad};
+  if (!select_from_lists(g, q, a.world, k, sh)) select_topk_sorted(g, q, (int64_t)a.world * k, k, sh);
+  write_topk(sh, q, k, 0, out_scores, out_ids);
+  if (tid == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(hdr + 33, 1u);
+    if (t == gridDim.x - 1) { hdr[33] = 0u; hdr[32] = round; }
   }
 }
 
@@ -401,7 +646,7 @@ static ScanPlan plan_scan(int64_t N, int nq, int k) {
   int64_t quads = (N + 3) / 4;
   int64_t g = ceil_div(quads, warps);
   p.grid = (int)(g < kNumSMs ? (g < 1 ? 1 : g) : kNumSMs);
-  p.smem_per_q = (size_t)warps * cap * sizeof(u64);
+  p.smem_per_q = (size_t)warps * (cap + kSampleRows) * sizeof(u64);     // candidate buffers + the sample area
   p.cand_bytes = align_up((size_t)nq * p.grid * k * sizeof(u64));
   p.total = p.cand_bytes + 256;
   return p;
@@ -492,8 +737,51 @@ int tt_topk_scan(const void* index, int index_bf16, const float* queries, int64_
                               : tt::dispatch_scan<false, false>(index, queries, N, H, nq, k, plan, cand, s);
   if (rc) return rc;
   tt::RawKeys src{cand, (int64_t)plan.grid * k};
-  tt::merge_topk_kernel<tt::RawKeys><<<nq, tt::kMergeThreads, 0, s>>>(src, (int64_t)plan.grid * k, k, id_offset, out_scores, out_ids);
+  TT_CUDA(tt::launch_kernel(tt::merge_topk_kernel<tt::RawKeys>, dim3((unsigned)nq), dim3(tt::kMergeThreads), 0, s, true, src,
+                            (int64_t)plan.grid * k, k, id_offset, out_scores, out_ids));
   TT_LAUNCH_CHECK("merge_topk_kernel");
+  return TT_OK;
+}
+
+int tt_topk_scan_p2p_ok(const tt_p2p_t* x, int nq, int k) {
+  if (!x || nq <= 0 || k <= 0 || k > TT_TOPK_MAX) return 0;
+  const int kpad = (k + 1) & ~1;
+  return (x->world >= 1 && x->world <= 8 && x->double_buffered && x->ctas == nq && (size_t)nq * kpad * 8 <= x->slot_bytes &&
+          (int64_t)x->world * k <= (int64_t)tt::kMergeRegKeys * tt::kMergeThreads) ? 1 : 0;
+}
+
+int tt_topk_scan_p2p(const void* index, int index_bf16, const float* queries, int64_t N, int H, int nq, int k,
+                     int cosine, int64_t id_offset, const tt_p2p_t* x, float* out_scores, int64_t* out_ids, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  TT_REQUIRE_DEVICE();
+  TT_CHECK_ARG(index && queries && out_scores && out_ids && x && N > 0 && H > 0 && nq > 0, "topk_scan_p2p: bad arguments");
+  TT_CHECK_ARG(k > 0 && k <= TT_TOPK_MAX && k <= N, "topk_scan_p2p: need 0 < k <= min(N, %d) (k=%d, N=%lld)", TT_TOPK_MAX, k, (long long)N);
+  TT_CHECK_ARG(id_offset >= 0 && id_offset + N < (1ll << 32), "topk_scan_p2p: global row numbers must stay below 2^32");
+  if (!tt_topk_scan_p2p_ok(x, nq, k)) {
+    tt::set_error("topk_scan_p2p: needs a double-buffered exchange created with ctas == nq and slots of >= nq * k * 8 bytes");
+    return TT_ERR_UNSUPPORTED;
+  }
+  TT_CHECK_ARG(x->rank >= 0 && x->rank < x->world, "topk_scan_p2p: bad rank");
+  const tt::ScanPlan plan = tt::plan_scan(N, nq, k);
+  if (workspace == nullptr || workspace_bytes < plan.total) { tt::set_error("topk_scan_p2p: workspace too small (%zu < %zu)", workspace_bytes, plan.total); return TT_ERR_WORKSPACE; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  tt::u64* cand = reinterpret_cast<tt::u64*>(workspace);
+  int rc;
+  if (index_bf16) rc = cosine ? tt::dispatch_scan<true, true>(index, queries, N, H, nq, k, plan, cand, s)
+                              : tt::dispatch_scan<true, false>(index, queries, N, H, nq, k, plan, cand, s);
+  else            rc = cosine ? tt::dispatch_scan<false, true>(index, queries, N, H, nq, k, plan, cand, s)
+                              : tt::dispatch_scan<false, false>(index, queries, N, H, nq, k, plan, cand, s);
+  if (rc) return rc;
+  tt::P2PSearchArgs a{};
+  a.world = x->world; a.rank = x->rank; a.halves = 2; a.slot_bytes = x->slot_bytes;
+  a.timeout_s = x->timeout_s > 0 ? (unsigned)x->timeout_s : 600u;
+  for (int p = 0; p < x->world; ++p) {
+    TT_CHECK_ARG(x->base[p] != nullptr, "topk_scan_p2p: peer %d not mapped", p);
+    a.base[p] = static_cast<unsigned char*>(x->base[p]);
+  }
+  TT_CUDA(tt::launch_kernel(tt::merge_exchange_merge_kernel, dim3((unsigned)nq), dim3(tt::kMergeThreads), 0, s, true, (const tt::u64*)cand,
+                            (int64_t)plan.grid * k, k, (k + 1) & ~1, (unsigned)id_offset, a, out_scores, out_ids));
+  TT_LAUNCH_CHECK("merge_exchange_merge_kernel");
   return TT_OK;
 }
 

@@ -449,6 +449,33 @@ def topk_scan_workspace_bytes(N: int, H: int, nq: int, k: int) -> int:
     return int(_lib_().tt_topk_scan_workspace(N, H, nq, k))
 
 
+def topk_scan_p2p_ok(xch, nq: int, k: int) -> bool:
+    """True when `xch` (parallel.P2PExchange) can carry the fused sharded search for nq queries / top-k."""
+    return bool(_lib_().tt_topk_scan_p2p_ok(C.byref(xch.desc), int(nq), int(k)))
+
+
+def topk_scan_p2p(index: torch.Tensor, queries: torch.Tensor, k: int, xch, cosine: bool = True, id_offset: int = 0,
+                  workspace: Optional[torch.Tensor] = None):
+    """Row-sharded exact top-k in two launches (tt_topk_scan_p2p): this rank's scan, then one kernel that merges the block
+    lists, exchanges the shard's k candidates with every rank over NVLink peer memory and selects the global top-k.
+    Collective over xch's group; returns (scores [nq,k], GLOBAL ids [nq,k]), identical on every rank."""
+    _need_cuda(index, queries)
+    if index.dtype not in (torch.float32, torch.bfloat16) or not index.is_contiguous():
+        raise TypeError("index must be contiguous float32 or bfloat16 [N,H]")
+    queries = _f32(queries)
+    N, H = index.shape
+    nq = queries.shape[0]
+    dev = index.device
+    scores = torch.empty(nq, k, dtype=torch.float32, device=dev)
+    ids = torch.empty(nq, k, dtype=torch.int64, device=dev)
+    if workspace is None:
+        workspace = _workspace(_lib_().tt_topk_scan_workspace(N, H, nq, k), dev)
+    check(_lib_().tt_topk_scan_p2p(_p(index), int(index.dtype == torch.bfloat16), _p(queries), N, H, nq, int(k),
+                                   int(bool(cosine)), int(id_offset), C.byref(xch.desc), _p(scores), _p(ids), _p(workspace),
+                                   workspace.numel(), _stream()), "tt_topk_scan_p2p")
+    return scores, ids
+
+
 def topk_merge(scores: torch.Tensor, ids: torch.Tensor):
     """scores/ids [R,nq,k] -> merged ([nq,k], [nq,k])."""
     _need_cuda(scores, ids)

@@ -226,15 +226,16 @@ def _contig_strides(shape):
 _SEARCH_XCH = {}
 
 
-def _search_exchange(nbytes: int, group, device):
-    """Cached double-buffered peer-memory exchange for the candidate records of the sharded search (None: use NCCL)."""
+def _search_exchange(nbytes: int, group, device, ctas: int = 0):
+    """Cached double-buffered peer-memory exchange for the candidate records of the sharded search (None: use NCCL).
+    ctas > 0 fixes the exchange's CTA count (one CTA per query for the fused merge + exchange + merge kernel)."""
     import os
     if device.type != "cuda" or os.environ.get("TT_P2P", "1") == "0":
         return None
     _, ws = world(group)
     if ws < 2 or ws > 8:
         return None
-    key = (id(group), (nbytes + 255) // 256 * 256, device.index)
+    key = (id(group), (nbytes + 255) // 256 * 256, device.index, int(ctas))
     if key not in _SEARCH_XCH:
         while len(_SEARCH_XCH) >= 4:                          # bounded: one exchange per (group, record size) in use
             old = _SEARCH_XCH.pop(next(iter(_SEARCH_XCH)))
@@ -243,6 +244,8 @@ def _search_exchange(nbytes: int, group, device):
                 old.close()
         try:
             x = P2PExchange(key[1], group, device, double_buffered=True)
+            if ctas > 0:
+                x.desc.ctas = int(ctas)                       # same on every rank: all of them pass the same nq
             x.staging = torch.zeros(1, key[1], dtype=torch.uint8, device=device)
             _SEARCH_XCH[key] = x
         except RuntimeError:
@@ -272,10 +275,22 @@ class ShardedTopK:
         self.xch = None
         if index_shard.is_cuda and hasattr(kernels, "packed_topk_buffer") and index_shard.shape[0] >= k:
             _, self.nbytes, self.id_off = kernels.packed_topk_buffer(nq, k, index_shard.device)
-            self.xch = _search_exchange(self.nbytes, group, index_shard.device)
+            import os
+            fused_ok = hasattr(kernels, "topk_scan_p2p") and nq <= 64 and os.environ.get("TT_SEARCH_FUSED", "1") != "0"
+            self.xch = _search_exchange(self.nbytes, group, index_shard.device, ctas=nq if fused_ok else 0)
+            # scan, then ONE kernel: block merge + candidate exchange over NVLink + final merge (tt_topk_scan_p2p)
+            self.fused = bool(fused_ok and self.xch is not None and kernels.topk_scan_p2p_ok(self.xch, nq, k))
+            if self.fused:
+                self.ws = torch.empty(kernels.topk_scan_workspace_bytes(index_shard.shape[0], index_shard.shape[1], nq, k),
+                                      dtype=torch.uint8, device=index_shard.device)
 
     def _body(self, round_no: int, count: bool):
         x = self.xch
+        if getattr(self, "fused", False):
+            if count:
+                x.rounds += 1                                    # mirrors the device-side round counter
+            return self.kernels.topk_scan_p2p(self.index, self.q, self.k, x, cosine=self.cosine, id_offset=self.id_offset,
+                                              workspace=self.ws)
         s_view, i_view = self.kernels.packed_views(x.staging[0, :self.nbytes], self.nq, self.k, self.id_off)
         self.kernels.topk_scan(self.index, self.q, self.k, cosine=self.cosine, id_offset=self.id_offset, out=(s_view, i_view))
         x.allgather(x.staging[0], count=count)

@@ -259,7 +259,10 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   __shared__ int s_cnt[kScanThreads / 32 + 1];
 #pragma unroll
   for (int n = 0; n < NQ; ++n) {
-    tk[n].prune(lane);
+    // a warp's buffer is sorted / cut to k only when it holds more than k keys or cannot travel through registers: the block
+    // sort below does not need sorted input, and a 256-key in-warp sort is ~4 us of latency at the very end of the kernel
+    if (tk[n].count > k || cap > 32 * kMaxCapPerLane) tk[n].prune(lane);
+    __syncwarp();
     u64* region = sm + (size_t)n * kScanWarps * cap;
     u64 keep[kMaxCapPerLane];
     const int cnt = tk[n].count;

@@ -23,6 +23,8 @@
 //     and sorts the survivors.  The same kernel implements tt_topk_merge for the
 //     row-sharded multi-GPU search.
 #include <math_constants.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -127,6 +129,12 @@ __device__ __forceinline__ float group8_sum(float v) {
   return v;
 }
 
+// developer aid (TT_SCAN_DEBUG=1, tt_topk_scan prints them): %globaltimer stamps of CTA 0 -- start, sample scored, threshold
+// known, main loop done (warp 0), packed + sorted, end
+__device__ int g_scan_dbg_on = 0;
+__device__ long long g_scan_dbg[8];
+#define TT_SCAN_STAMP(i) do { if (dbg) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_scan_dbg[i] = t_; } } while (0)
+
 constexpr int kScanThreads = 512;            // upper bound; large k launches fewer warps so the buffers fit
 constexpr int kSampleRows = 64;              // rows every warp scores unconditionally before the CTA fixes its starting threshold
 constexpr int kMaxCapPerLane = 8;            // packed block epilogue: candidate buffers of <= 256 keys travel through registers
@@ -134,6 +142,95 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// descending bitonic sort of 32 * KPL keys held KPL per lane (element e = j * 32 + lane): compare distances below 32 are
+// shuffles, the others pair registers of one lane -- no shared memory, no barriers
+template <int KPL>
+__device__ __forceinline__ void warp_sort_desc(u64 (&v)[KPL], int lane) {
+  constexpr int M = 32 * KPL;
+#pragma unroll
+  for (int size = 2; size <= M; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int sj = stride >> 5;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          if ((j & sj) == 0) {
+            const bool desc = ((j << 5) & size) == 0;
+            const u64 a = v[j], b = v[j | sj];
+            if ((a < b) == desc) { v[j] = b; v[j | sj] = a; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+          const u64 other = __shfl_xor_sync(0xffffffffu, v[j], stride);
+          const bool desc = ((((j << 5) | lane)) & size) == 0;
+          const bool keep_max = ((lane & stride) == 0) == desc;
+          v[j] = keep_max ? (v[j] > other ? v[j] : other) : (v[j] < other ? v[j] : other);
+        }
+      }
+    }
+  }
+}
+// sorts buf[0..cnt) of one warp (cnt <= 32 * KPL, unique keys) descending in place, zero-padded to 32 * KPL
+template <int KPL>
+__device__ __forceinline__ void warp_sort_buffer(u64* buf, int cnt, int lane) {
+  u64 v[KPL];
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) v[j] = (j * 32 + lane < cnt) ? buf[j * 32 + lane] : 0ull;
+  warp_sort_desc<KPL>(v, lane);
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) buf[j * 32 + lane] = v[j];
+}
+
+// The whole CTA: top-k of W DESCENDING runs (run w: lst + w * stride, s_cnt[w] keys) -> out[0..k) descending, zero-padded.
+// Same idea as select_from_lists: the k-th largest of the runs' heads (first ceil(k / W) keys of each) bounds the k-th largest
+// key from below; the few keys that reach it are ranked against each other (one key per thread, broadcast reads) -- four
+// barriers instead of the 55 of a 1024-key bitonic sort.  `out` may alias run 0.  Returns the number of live keys written,
+// or -1 with nothing written when the shape / data do not fit (fewer than k live heads, more survivors than threads).
+__device__ __forceinline__ int cta_select_runs(const u64* lst, int stride, const int* s_cnt, int W, int k, u64* out,
+                                               u64* scratch, int* s_ctr, u64* s_thr) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int r = (k + W - 1) / W, nh = W * r;
+  if (nh > nthr) return -1;                                  // CTA-uniform
+  u64 head = 0ull;
+  if (tid < nh) {
+    const int w = tid / r, pos = tid - w * r;
+    head = pos < s_cnt[w] ? lst[(size_t)w * stride + pos] : 0ull;
+    scratch[tid] = head;
+  }
+  if (tid == 0) { *s_ctr = 0; *s_thr = 0ull; }
+  __syncthreads();
+  if (tid < nh && head != 0ull) {
+    int rank = 0;
+    for (int j = 0; j < nh; ++j) rank += scratch[j] > head;
+    if (rank == k - 1) *s_thr = head;
+  }
+  __syncthreads();
+  const u64 thr = *s_thr;
+  if (thr == 0ull) return -1;                                // fewer than k live heads
+  const int cw = s_cnt[warp];
+  for (int i = lane; i < cw; i += 32) {                      // survivors are a prefix of each run
+    const u64 key = lst[(size_t)warp * stride + i];
+    if (key < thr) break;
+    const int p = atomicAdd(s_ctr, 1);
+    if (p < nthr) scratch[p] = key;
+  }
+  __syncthreads();
+  const int S = *s_ctr;
+  if (S > nthr) return -1;
+  const u64 key = tid < S ? scratch[tid] : 0ull;
+  int rank = 0;
+  if (tid < S)
+    for (int j = 0; j < S; ++j) rank += scratch[j] > key;
+  __syncthreads();
+  if (tid < S && rank < k) out[rank] = key;
+  for (int i = S + tid; i < k; i += nthr) out[i] = 0ull;
+  __syncthreads();
+  return S < k ? S : k;
 }
 
 // CPL = 16-byte chunks per lane (row = 8 lanes x CPL chunks), NQ queries per pass.
@@ -146,6 +243,8 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* sm = reinterpret_cast<u64*>(smem_raw);              // [NQ][warps][cap]
   pdl_trigger();                                           // the merge kernel may be set up while this one streams the index
+  const bool dbg = g_scan_dbg_on && blockIdx.x == 0 && threadIdx.x == 0;
+  TT_SCAN_STAMP(0);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kScanWarps = blockDim.x >> 5;
@@ -235,62 +334,93 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   int64_t it = gw;
 #pragma unroll 1
   for (int i = 0; i < kSampleRows / 8; ++i, it += 2 * nw) step(it, std::true_type{}, i);
+  TT_SCAN_STAMP(1);
+  __shared__ int s_cnt[kScanThreads / 32 + 1];
+  __shared__ u64 s_scratch[kScanThreads];
+  __shared__ int s_ctr;
+  __shared__ u64 s_thr;
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < NQ; ++n) warp_sort_buffer<kSampleRows / 32>(samp + (size_t)n * nsamp + warp * kSampleRows, kSampleRows, lane);
+  if (lane == 0) s_cnt[warp] = kSampleRows;
   __syncthreads();
 #pragma unroll
   for (int n = 0; n < NQ; ++n) {
     u64* sp = samp + (size_t)n * nsamp;
-    bitonic_desc<true>(sp, nsamp, threadIdx.x, blockDim.x);
-    const u64 kth = k <= nsamp ? sp[k - 1] : 0ull;
-    const float thr0 = kth != 0ull ? bits_score((uint32_t)(kth >> 32)) : -CUDART_INF_F;
-    if (warp == 0) {
+    u64* buf0 = sm + (size_t)n * kScanWarps * cap;           // warp 0's candidate buffer
+    float thr0 = -CUDART_INF_F;
+    int cnt0 = cta_select_runs(sp, kSampleRows, s_cnt, kScanWarps, k, buf0, s_scratch, &s_ctr, &s_thr);
+    if (cnt0 >= 0) {
+      if (cnt0 == k) thr0 = bits_score((uint32_t)(buf0[k - 1] >> 32));
+    } else {                                                 // odd shapes (k > warps * 64, tiny shards): sort the whole sample
+      bitonic_desc<true>(sp, nsamp, threadIdx.x, blockDim.x);
+      const u64 kth = k <= nsamp ? sp[k - 1] : 0ull;
+      if (kth != 0ull) thr0 = bits_score((uint32_t)(kth >> 32));
       const int live = k <= nsamp ? k : nsamp;               // zero keys (rows past the end) sort last and are never live
-      int cnt = 0;
-      for (int i = lane; i < live; i += 32) { const u64 key = sp[i]; tk[n].buf[i] = key; cnt += key != 0ull; }
-      tk[n].count = warp_sum_int(cnt);
+      int c = 0;
+      if (warp == 0)
+        for (int i = lane; i < live; i += 32) { const u64 key = sp[i]; buf0[i] = key; c += key != 0ull; }
+      cnt0 = warp_sum_int(c);
     }
+    if (warp == 0) tk[n].count = cnt0;
     tk[n].thr = thr0;
   }
   __syncwarp();
+  TT_SCAN_STAMP(2);
 
   for (; it < quads; it += 2 * nw) step(it, std::false_type{}, 0);
+  TT_SCAN_STAMP(3);
 
-  // block epilogue: every warp sorts its own buffer; the live keys of all warps are packed into one contiguous run (usually
-  // ~1 k keys instead of warps * cap slots), sorted, and the block top-k goes to global
-  __shared__ int s_cnt[kScanThreads / 32 + 1];
+  // block epilogue: every warp sorts its own candidates in registers (usually <= 64 keys), the CTA selects the top-k of the
+  // sorted runs by head threshold + ranking (cta_select_runs); the packed bitonic sort remains for the shapes that does not fit
 #pragma unroll
   for (int n = 0; n < NQ; ++n) {
-    // a warp's buffer is sorted / cut to k only when it holds more than k keys or cannot travel through registers: the block
-    // sort below does not need sorted input, and a 256-key in-warp sort is ~4 us of latency at the very end of the kernel
-    if (tk[n].count > k || cap > 32 * kMaxCapPerLane) tk[n].prune(lane);
-    __syncwarp();
     u64* region = sm + (size_t)n * kScanWarps * cap;
-    u64 keep[kMaxCapPerLane];
+    const bool small = cap <= 32 * kMaxCapPerLane;          // candidate buffers of <= 256 keys travel through registers
+    if (small) {
+      const int c = tk[n].count;
+      __syncwarp();
+      if (c <= 64) warp_sort_buffer<2>(tk[n].buf, c, lane);
+      else if (c <= 128) warp_sort_buffer<4>(tk[n].buf, c, lane);
+      else warp_sort_buffer<8>(tk[n].buf, c, lane);
+      if (c > k) tk[n].count = k;                            // a sorted run: only its k best can matter
+    } else {
+      tk[n].prune(lane);
+    }
+    __syncwarp();
     const int cnt = tk[n].count;
-#pragma unroll
-    for (int u = 0; u < kMaxCapPerLane; ++u) keep[u] = (u * 32 + lane < cnt) ? tk[n].buf[u * 32 + lane] : 0ull;
+    __syncthreads();                                         // the previous query's selection has finished with s_cnt
     if (lane == 0) s_cnt[warp] = cnt;
     __syncthreads();
-    int off = 0, total = 0;
-    for (int w = 0; w < kScanWarps; ++w) { const int c = s_cnt[w]; off += w < warp ? c : 0; total += c; }
-    int n2 = 32;
-    while (n2 < total || n2 < k) n2 <<= 1;
-    const bool packed = cap <= 32 * kMaxCapPerLane;          // larger caps (k > 128) keep the full-region sort
-    if (packed) {
+    const int sel = small ? cta_select_runs(region, cap, s_cnt, kScanWarps, k, region, s_scratch, &s_ctr, &s_thr) : -1;
+    if (sel < 0) {
+      int off = 0, total = 0;
+      for (int w = 0; w < kScanWarps; ++w) { const int c = s_cnt[w]; off += w < warp ? c : 0; total += c; }
+      int n2 = 32;
+      while (n2 < total || n2 < k) n2 <<= 1;
+      if (small) {                                           // pack the live keys of all warps (through registers), sort them
+        u64 keep[kMaxCapPerLane];
 #pragma unroll
-      for (int u = 0; u < kMaxCapPerLane; ++u)
-        if (u * 32 + lane < cnt) region[off + u * 32 + lane] = keep[u];
-      for (int i = total + threadIdx.x; i < n2; i += blockDim.x) region[i] = 0ull;
-      __syncthreads();
-      bitonic_desc<true>(region, n2, threadIdx.x, blockDim.x);
-    } else {
-      for (int i = cnt + lane; i < cap; i += 32) tk[n].buf[i] = 0ull;
-      __syncthreads();
-      bitonic_desc<true>(region, kScanWarps * cap, threadIdx.x, blockDim.x);
+        for (int u = 0; u < kMaxCapPerLane; ++u) keep[u] = (u * 32 + lane < cnt) ? tk[n].buf[u * 32 + lane] : 0ull;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kMaxCapPerLane; ++u)
+          if (u * 32 + lane < cnt) region[off + u * 32 + lane] = keep[u];
+        for (int i = total + threadIdx.x; i < n2; i += blockDim.x) region[i] = 0ull;
+        __syncthreads();
+        bitonic_desc<true>(region, n2, threadIdx.x, blockDim.x);
+      } else {
+        for (int i = cnt + lane; i < cap; i += 32) tk[n].buf[i] = 0ull;
+        __syncthreads();
+        bitonic_desc<true>(region, kScanWarps * cap, threadIdx.x, blockDim.x);
+      }
     }
+    TT_SCAN_STAMP(4);
     u64* out = cand + ((size_t)(q0 + n) * gridDim.x + blockIdx.x) * k;
     for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = region[i];
     __syncthreads();
   }
+  TT_SCAN_STAMP(5);
 }
 
 // generic-H fallback: one warp per row, scalar loads (used only when H is not a multiple of 32/64)
@@ -743,6 +873,19 @@ int tt_topk_scan(const void* index, int index_bf16, const float* queries, int64_
   TT_CUDA(tt::launch_kernel(tt::merge_topk_kernel<tt::RawKeys>, dim3((unsigned)nq), dim3(tt::kMergeThreads), 0, s, true, src,
                             (int64_t)plan.grid * k, k, id_offset, out_scores, out_ids));
   TT_LAUNCH_CHECK("merge_topk_kernel");
+  static const bool dbg_on = getenv("TT_SCAN_DEBUG") != nullptr;
+  if (dbg_on) {
+    static int calls = 0;
+    const int one = 1;
+    cudaStreamSynchronize(s);
+    if (calls++ == 0) cudaMemcpyToSymbol(tt::g_scan_dbg_on, &one, sizeof(int));
+    else {
+      long long t[8];
+      cudaMemcpyFromSymbol(t, tt::g_scan_dbg, sizeof(t));
+      printf("[tt scan CTA 0, ns] N=%lld bf16=%d: sample scored %lld | threshold known %lld | loop done %lld | packed+sorted %lld | end %lld\n",
+             (long long)N, index_bf16, t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0]);
+    }
+  }
   return TT_OK;
 }
 

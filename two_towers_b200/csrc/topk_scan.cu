@@ -191,8 +191,9 @@ __device__ __forceinline__ void warp_sort_buffer(u64* buf, int cnt, int lane) {
 // key from below; the few keys that reach it are ranked against each other (one key per thread, broadcast reads) -- four
 // barriers instead of the 55 of a 1024-key bitonic sort.  `out` may alias run 0.  Returns the number of live keys written,
 // or -1 with nothing written when the shape / data do not fit (fewer than k live heads, more survivors than threads).
+// deal_stride > 0: the selected keys are dealt round-robin into W buffers deal_stride keys apart instead of one sorted run.
 __device__ __forceinline__ int cta_select_runs(const u64* lst, int stride, const int* s_cnt, int W, int k, u64* out,
-                                               u64* scratch, int* s_ctr, u64* s_thr) {
+                                               u64* scratch, int* s_ctr, u64* s_thr, int deal_stride = 0) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int r = (k + W - 1) / W, nh = W * r;
   if (nh > nthr) return -1;                                  // CTA-uniform
@@ -227,8 +228,12 @@ __device__ __forceinline__ int cta_select_runs(const u64* lst, int stride, const
   if (tid < S)
     for (int j = 0; j < S; ++j) rank += scratch[j] > key;
   __syncthreads();
-  if (tid < S && rank < k) out[rank] = key;
-  for (int i = S + tid; i < k; i += nthr) out[i] = 0ull;
+  if (deal_stride > 0) {                                      // deal the selected keys out to W buffers: key of rank r -> buffer r % W, slot r / W
+    if (tid < S && rank < k) out[(size_t)(rank % W) * deal_stride + rank / W] = key;
+  } else {
+    if (tid < S && rank < k) out[rank] = key;
+    for (int i = S + tid; i < k; i += nthr) out[i] = 0ull;
+  }
   __syncthreads();
   return S < k ? S : k;
 }
@@ -337,8 +342,9 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   TT_SCAN_STAMP(1);
   __shared__ int s_cnt[kScanThreads / 32 + 1];
   __shared__ u64 s_scratch[kScanThreads];
-  __shared__ int s_ctr;
+  __shared__ int s_ctr, s_next;
   __shared__ u64 s_thr;
+  if (threadIdx.x == 0) s_next = (kSampleRows / 8) * kScanWarps;   // the sample rounds were taken statically
   __syncwarp();
 #pragma unroll
   for (int n = 0; n < NQ; ++n) warp_sort_buffer<kSampleRows / 32>(samp + (size_t)n * nsamp + warp * kSampleRows, kSampleRows, lane);
@@ -349,9 +355,17 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
     u64* sp = samp + (size_t)n * nsamp;
     u64* buf0 = sm + (size_t)n * kScanWarps * cap;           // warp 0's candidate buffer
     float thr0 = -CUDART_INF_F;
-    int cnt0 = cta_select_runs(sp, kSampleRows, s_cnt, kScanWarps, k, buf0, s_scratch, &s_ctr, &s_thr);
+    // the sample's k best keys continue as candidates, dealt out over the warps' buffers: every warp then ends the scan with
+    // a few dozen keys, which its register sort (64 keys) handles -- all of them in warp 0's buffer made that warp sort 256
+    int cnt0 = cta_select_runs(sp, kSampleRows, s_cnt, kScanWarps, k, buf0, s_scratch, &s_ctr, &s_thr, cap);
     if (cnt0 >= 0) {
-      if (cnt0 == k) thr0 = bits_score((uint32_t)(buf0[k - 1] >> 32));
+      if (cnt0 == k) {                                       // the k-th best sample key: rank k - 1
+        const u64 kth = buf0[(size_t)((k - 1) % kScanWarps) * cap + (k - 1) / kScanWarps];
+        thr0 = bits_score((uint32_t)(kth >> 32));
+      }
+      tk[n].count = cnt0 > warp ? (cnt0 - warp + kScanWarps - 1) / kScanWarps : 0;
+      tk[n].thr = thr0;
+      continue;
     } else {                                                 // odd shapes (k > warps * 64, tiny shards): sort the whole sample
       bitonic_desc<true>(sp, nsamp, threadIdx.x, blockDim.x);
       const u64 kth = k <= nsamp ? sp[k - 1] : 0ull;
@@ -368,7 +382,21 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   __syncwarp();
   TT_SCAN_STAMP(2);
 
-  for (; it < quads; it += 2 * nw) step(it, std::false_type{}, 0);
+  // The CTA's remaining steps (step t = round t / warps, warp slot t % warps: the same rows the static schedule gave this
+  // CTA) are handed out through a shared-memory counter: warps of one SM do not progress at the same rate, and with a fixed
+  // share each the block epilogue waited ~12 us for the slowest one.
+  {
+    const int wshift = __ffs(kScanWarps) - 1;
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&s_next, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      const int rnd = t >> wshift, slot = t & (kScanWarps - 1);
+      const int64_t it0 = (int64_t)blockIdx.x * kScanWarps + (int64_t)rnd * 2 * nw;
+      if (it0 >= quads) break;
+      step(it0 + slot, std::false_type{}, 0);
+    }
+  }
   TT_SCAN_STAMP(3);
 
   // block epilogue: every warp sorts its own candidates in registers (usually <= 64 keys), the CTA selects the top-k of the
@@ -380,10 +408,11 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
     if (small) {
       const int c = tk[n].count;
       __syncwarp();
+      // <= 64 keys (the usual case): the register sort the sample phase has already pulled into the instruction cache;
+      // more: the in-warp shared-memory sort (rolled loops -- a fully unrolled 256-key register sort is ~2000 instructions
+      // of cold code, ~10 us for the one warp that runs it)
       if (c <= 64) warp_sort_buffer<2>(tk[n].buf, c, lane);
-      else if (c <= 128) warp_sort_buffer<4>(tk[n].buf, c, lane);
-      else warp_sort_buffer<8>(tk[n].buf, c, lane);
-      if (c > k) tk[n].count = k;                            // a sorted run: only its k best can matter
+      else tk[n].prune(lane);
     } else {
       tk[n].prune(lane);
     }

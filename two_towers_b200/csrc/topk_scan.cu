@@ -26,6 +26,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "common.cuh"
@@ -135,6 +136,16 @@ __device__ int g_scan_dbg_on = 0;
 __device__ long long g_scan_dbg[8];
 #define TT_SCAN_STAMP(i) do { if (dbg) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_scan_dbg[i] = t_; } } while (0)
 
+// fp32 rows of 256+ columns (16 x 16-byte loads in flight per lane): rounds of the scan (one round = one step of every warp
+// of a CTA = warps * 8 rows) are handed out to the CTAs through a global counter -- SMs do not stream at the same rate, and
+// with a fixed share per CTA the kernel waited 15-19 us for the slowest one (10 M rows: 1433 -> 1397 us, 7.3 TB/s).  The
+// narrower variants have half the bytes in flight and are latency-bound: the extra hop per step cost them more than the
+// balance gained (bf16, 10 M rows: 766 -> 823 us), so they keep the static interleaved schedule.
+// One counter pair {next round, CTAs finished} per launch slot; the last CTA to finish resets its pair, so the counters are
+// zero between launches (they start zero: static storage).  Launches take slots round-robin.
+constexpr int kScanSlots = 256;
+__device__ unsigned g_scan_rounds[kScanSlots][2];
+
 constexpr int kScanThreads = 512;            // upper bound; large k launches fewer warps so the buffers fit
 constexpr int kSampleRows = 64;              // rows every warp scores unconditionally before the CTA fixes its starting threshold
 constexpr int kMaxCapPerLane = 8;            // packed block epilogue: candidate buffers of <= 256 keys travel through registers
@@ -242,7 +253,8 @@ __device__ __forceinline__ int cta_select_runs(const u64* lst, int stride, const
 template <int CPL, int NQ, bool BF16, bool COSINE>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queries, int64_t N, int H,
-                 int k, int cap, int q0, u64* __restrict__ cand) {
+                 int k, int cap, int q0, u64* __restrict__ cand, int slot_id) {
+  constexpr bool DYN = CPL >= 8;                           // global round counter (see g_scan_rounds)
   typedef typename ChunkT<BF16>::type Chunk;
   constexpr int EPC = BF16 ? 8 : 4;                        // elements per chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -250,6 +262,19 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   pdl_trigger();                                           // the merge kernel may be set up while this one streams the index
   const bool dbg = g_scan_dbg_on && blockIdx.x == 0 && threadIdx.x == 0;
   TT_SCAN_STAMP(0);
+  // dynamic rounds: local block b of `warps` steps <-> one global round; its id travels through a ring tagged with b
+  __shared__ int s_next;
+  __shared__ unsigned long long s_blk[16];
+  unsigned* gctr = g_scan_rounds[slot_id];
+  if (DYN) {
+    if (threadIdx.x < 16) s_blk[threadIdx.x] = ~0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) {                                 // the rounds of local blocks 0 and 1: their latency hides under the sample phase
+      s_next = 0;
+      s_blk[0] = (unsigned long long)atomicAdd(gctr, 1u);
+      s_blk[1] = (1ull << 32) | atomicAdd(gctr, 1u);
+    }
+  }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kScanWarps = blockDim.x >> 5;
@@ -287,45 +312,52 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   const int64_t gw = (int64_t)blockIdx.x * kScanWarps + warp;
   const int64_t nw = (int64_t)gridDim.x * kScanWarps;
 
-  // one step = two row quads of this warp (rows it*4.. and (it+nw)*4..).  SAMPLE steps store every score into the sample
-  // area instead of the warp's candidate buffer (slot = step * 8 + quad * 4 + row-in-quad).
+  // one step = NQD row quads of this warp (rows (it + j nw) * 4 .., j < NQD): 16 x 16-byte loads in flight per lane whatever
+  // the row width (2 quads of 8 chunks for fp32 x 256 columns, 4 quads of 4 chunks for bf16 x 256 -- with two quads the
+  // narrower rows had half the bytes in flight and ran latency-bound).  SAMPLE steps store every score into the sample area
+  // instead of the warp's candidate buffer (slot = step * 4 NQD + quad * 4 + row-in-quad).
+  constexpr int NQD = (CPL >= 8 || NQ > 1 || (BF16 && COSINE)) ? 2 : 4;   // four quads only where they fit in registers without spills
+  constexpr int kSampleSteps = kSampleRows / (4 * NQD);
   auto step = [&](int64_t it, auto sample_tag, int sidx) {
     constexpr bool SAMPLE = decltype(sample_tag)::value;
-    const int64_t rowA = it * 4 + grp, rowB = (it + nw) * 4 + grp;
-    const bool okA = it < quads && rowA < N, okB = (it + nw < quads) && rowB < N;
-    Chunk a[CPL], b[CPL];
+    int64_t row[NQD];
+    bool ok[NQD];
+    Chunk a[NQD][CPL];
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      if (okA) a[c] = ld_chunk(base + rowA * chunks_per_row + sub + 8 * c); else zero_chunk(a[c]);
+    for (int j = 0; j < NQD; ++j) {
+      row[j] = (it + j * nw) * 4 + grp;
+      ok[j] = (it + j * nw < quads) && row[j] < N;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        if (ok[j]) a[j][c] = ld_chunk(base + row[j] * chunks_per_row + sub + 8 * c); else zero_chunk(a[j][c]);
+      }
     }
+    float inv[NQD];
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      if (okB) b[c] = ld_chunk(base + rowB * chunks_per_row + sub + 8 * c); else zero_chunk(b[c]);
-    }
-    float invA = 1.0f, invB = 1.0f;
-    if (COSINE) {
-      float sa = 0.f, sb = 0.f;
+    for (int j = 0; j < NQD; ++j) {
+      inv[j] = 1.0f;
+      if (COSINE) {
+        float sa = 0.f;
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) { sa = sq_chunk(a[c], sa); sb = sq_chunk(b[c], sb); }
-      invA = 1.0f / fmaxf(sqrtf(group8_sum(sa)), 1e-8f);
-      invB = 1.0f / fmaxf(sqrtf(group8_sum(sb)), 1e-8f);
+        for (int c = 0; c < CPL; ++c) sa = sq_chunk(a[j][c], sa);
+        inv[j] = 1.0f / fmaxf(sqrtf(group8_sum(sa)), 1e-8f);
+      }
     }
 #pragma unroll
     for (int n = 0; n < NQ; ++n) {
-      float da = 0.f, db = 0.f;
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) { da = dot_chunk(a[c], qf[n][c], da); db = dot_chunk(b[c], qf[n][c], db); }
-      da = group8_sum(da); db = group8_sum(db);
-      if (COSINE) { da = da * (qinv[n] * invA); db = db * (qinv[n] * invB); }
-      if (SAMPLE) {
-        if (sub == 0) {
-          u64* sp = samp + (size_t)n * nsamp + warp * kSampleRows + sidx * 8 + grp;
-          sp[0] = okA ? make_key(da, (uint32_t)rowA) : 0ull;
-          sp[4] = okB ? make_key(db, (uint32_t)rowB) : 0ull;
+      for (int j = 0; j < NQD; ++j) {
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) d = dot_chunk(a[j][c], qf[n][c], d);
+        d = group8_sum(d);
+        if (COSINE) d = d * (qinv[n] * inv[j]);
+        if (SAMPLE) {
+          if (sub == 0)
+            samp[(size_t)n * nsamp + warp * kSampleRows + sidx * (4 * NQD) + j * 4 + grp] = ok[j] ? make_key(d, (uint32_t)row[j]) : 0ull;
+        } else {
+          tk[n].push(ok[j] && sub == 0 && d >= tk[n].thr, d, (uint32_t)row[j], lane);
         }
-      } else {
-        tk[n].push(okA && sub == 0 && da >= tk[n].thr, da, (uint32_t)rowA, lane);
-        tk[n].push(okB && sub == 0 && db >= tk[n].thr, db, (uint32_t)rowB, lane);
       }
     }
   };
@@ -338,13 +370,13 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   // The sample's k best keys continue as warp 0's candidates.  (k > warps * 64: no threshold, the scan works as before.)
   int64_t it = gw;
 #pragma unroll 1
-  for (int i = 0; i < kSampleRows / 8; ++i, it += 2 * nw) step(it, std::true_type{}, i);
+  for (int i = 0; i < kSampleSteps; ++i, it += NQD * nw) step(it, std::true_type{}, i);
   TT_SCAN_STAMP(1);
   __shared__ int s_cnt[kScanThreads / 32 + 1];
   __shared__ u64 s_scratch[kScanThreads];
-  __shared__ int s_ctr, s_next;
+  __shared__ int s_ctr;
   __shared__ u64 s_thr;
-  if (threadIdx.x == 0) s_next = (kSampleRows / 8) * kScanWarps;   // the sample rounds were taken statically
+  if (!DYN && threadIdx.x == 0) s_next = kSampleSteps * kScanWarps;   // the sample rounds were taken statically
   __syncwarp();
 #pragma unroll
   for (int n = 0; n < NQ; ++n) warp_sort_buffer<kSampleRows / 32>(samp + (size_t)n * nsamp + warp * kSampleRows, kSampleRows, lane);
@@ -382,19 +414,40 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   __syncwarp();
   TT_SCAN_STAMP(2);
 
-  // The CTA's remaining steps (step t = round t / warps, warp slot t % warps: the same rows the static schedule gave this
-  // CTA) are handed out through a shared-memory counter: warps of one SM do not progress at the same rate, and with a fixed
-  // share each the block epilogue waited ~12 us for the slowest one.
+  // Main loop.  A warp takes local step t from a shared-memory counter (warps of one SM do not progress at the same rate):
+  // local block t / warps, warp slot t % warps.  Static variants: block b is round b of this CTA's interleaved share.  DYN:
+  // the warp that takes slot 0 of block b fetches the global round of block b + 2 (one global atomic per warps * 8 rows,
+  // issued before the warp's own step and published after it, so its ~1 us round trip is never waited for); everybody reads
+  // the round of its own block from the ring.  Global round G = (CTA slot G % grid, round G / grid behind the sample
+  // rounds) of the static interleaved schedule, so the memory access pattern does not change.
   {
     const int wshift = __ffs(kScanWarps) - 1;
     for (;;) {
-      int t = 0;
-      if (lane == 0) t = atomicAdd(&s_next, 1);
-      t = __shfl_sync(0xffffffffu, t, 0);
-      const int rnd = t >> wshift, slot = t & (kScanWarps - 1);
-      const int64_t it0 = (int64_t)blockIdx.x * kScanWarps + (int64_t)rnd * 2 * nw;
-      if (it0 >= quads) break;
-      step(it0 + slot, std::false_type{}, 0);
+      unsigned long long v = 0;
+      unsigned g_next = 0, b_pub = 0;
+      bool publish = false;
+      if (lane == 0) {
+        const int t = atomicAdd(&s_next, 1);
+        const unsigned b = (unsigned)(t >> wshift);
+        if (DYN) {
+          publish = (t & (kScanWarps - 1)) == 0;
+          if (publish) { g_next = atomicAdd(gctr, 1u); b_pub = b + 2; }
+          do { v = reinterpret_cast<volatile unsigned long long*>(s_blk)[b & 15]; } while ((unsigned)(v >> 32) != b);
+          v &= 0xffffffffull;
+        } else {
+          v = b;
+        }
+        v |= (unsigned long long)(unsigned)(t & (kScanWarps - 1)) << 32;
+      }
+      v = __shfl_sync(0xffffffffu, v, 0);
+      const unsigned G = (unsigned)(v & 0xffffffffull);
+      const int slot = (int)(v >> 32);
+      const int64_t it0 = DYN ? (int64_t)(G % gridDim.x) * kScanWarps + (int64_t)(G / gridDim.x + kSampleSteps) * NQD * nw
+                              : (int64_t)blockIdx.x * kScanWarps + (int64_t)G * NQD * nw;
+      const bool done = it0 >= quads;
+      if (!done) step(it0 + slot, std::false_type{}, 0);
+      if (DYN && publish) reinterpret_cast<volatile unsigned long long*>(s_blk)[b_pub & 15] = ((unsigned long long)b_pub << 32) | g_next;
+      if (done) break;
     }
   }
   TT_SCAN_STAMP(3);
@@ -450,6 +503,10 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
     __syncthreads();
   }
   TT_SCAN_STAMP(5);
+  if (DYN && threadIdx.x == 0) {                            // last CTA out re-arms the counters for the next launch on this slot
+    __threadfence();
+    if (atomicAdd(gctr + 1, 1u) == gridDim.x - 1) { gctr[0] = 0u; gctr[1] = 0u; __threadfence(); }
+  }
 }
 
 // generic-H fallback: one warp per row, scalar loads (used only when H is not a multiple of 32/64)
@@ -814,6 +871,11 @@ static ScanPlan plan_scan(int64_t N, int nq, int k) {
   return p;
 }
 
+static int next_scan_slot() {
+  static std::atomic<unsigned> n{0};
+  return (int)(n.fetch_add(1u, std::memory_order_relaxed) % (unsigned)kScanSlots);
+}
+
 template <int CPL, bool BF16, bool COS>
 static int launch_scan(const void* index, const float* queries, int64_t N, int H, int nq, int k,
                        const ScanPlan& plan, u64* cand, cudaStream_t s) {
@@ -824,14 +886,14 @@ static int launch_scan(const void* index, const float* queries, int64_t N, int H
   if (kTwoFits && 2 * plan.smem_per_q <= 200 * 1024) {
     TT_CUDA(cudaFuncSetAttribute(scan_topk_kernel<CPL, 2, BF16, COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * plan.smem_per_q)));
     for (; q + 2 <= nq; q += 2) {
-      scan_topk_kernel<CPL, 2, BF16, COS><<<plan.grid, plan.warps * 32, 2 * plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand);
+      scan_topk_kernel<CPL, 2, BF16, COS><<<plan.grid, plan.warps * 32, 2 * plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand, next_scan_slot());
       TT_LAUNCH_CHECK("scan_topk_kernel");
     }
   }
   if (q < nq) {
     TT_CUDA(cudaFuncSetAttribute(scan_topk_kernel<CPL, 1, BF16, COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_q));
     for (; q < nq; ++q) {
-      scan_topk_kernel<CPL, 1, BF16, COS><<<plan.grid, plan.warps * 32, plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand);
+      scan_topk_kernel<CPL, 1, BF16, COS><<<plan.grid, plan.warps * 32, plan.smem_per_q, s>>>(index, queries, N, H, k, plan.cap, q, cand, next_scan_slot());
       TT_LAUNCH_CHECK("scan_topk_kernel");
     }
   }

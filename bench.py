@@ -21,8 +21,9 @@ ranks, single-query and batched).
             slower, most of it instruction fetch from DRAM at the start of every kernel.
   e2e       same metric through the public API (FusedTrainer.prefetch/step/read_loss_async) with pinned HOST id
             tensors: H2D of the ids and D2H of the loss inside the timed region; median of the same repeats.
-  roofline  dominant kernel: the longer of the two one-pass loss kernels (tt_inbatch_ce_dd; `other_loss_kernel` =
-            tt_inbatch_ce_fwd_dq, `loss_step` = both), algorithmic FLOPs / live CUDA-event time of that kernel vs
+  roofline  dominant kernel: the longer of the two one-pass loss kernels (stored-E form, the trainer's choice at one GPU:
+            tt_inbatch_ce_fwd_dq_stash; `other_loss_kernel` = tt_inbatch_ce_dd_stash, `loss_step` = both; recomputing form at
+            N > 1: tt_inbatch_ce_dd / tt_inbatch_ce_fwd_dq), algorithmic FLOPs / live CUDA-event time of that kernel vs
             MEASURED_PEAKS.json; `traffic` comes from profiles/ncu_traffic.json (committed ncu capture).
   cpu_baseline  oracle/torch_port.py (the reference's eager path restated) on the host cores.
 `--impl reference` times that same CPU port as the reference arm, with --steps / --warmup used unchanged.

@@ -143,8 +143,10 @@ __device__ long long g_scan_dbg[8];
 // balance gained (bf16, 10 M rows: 766 -> 823 us), so they keep the static interleaved schedule.
 // One counter pair {next round, CTAs finished} per launch slot; the last CTA to finish resets its pair, so the counters are
 // zero between launches (they start zero: static storage).  Launches take slots round-robin.
+// Word 2: set by the CTA that drew round 0; the last CTA traps if nobody did (the counter was not zero when the launch began,
+// i.e. an earlier launch on this slot died half-way: rows would be skipped silently otherwise).
 constexpr int kScanSlots = 256;
-__device__ unsigned g_scan_rounds[kScanSlots][2];
+__device__ unsigned g_scan_rounds[kScanSlots][4];
 
 constexpr int kScanThreads = 512;            // upper bound; large k launches fewer warps so the buffers fit
 constexpr int kSampleRows = 64;              // rows every warp scores unconditionally before the CTA fixes its starting threshold
@@ -271,7 +273,9 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
     __syncthreads();
     if (threadIdx.x == 0) {                                 // the rounds of local blocks 0 and 1: their latency hides under the sample phase
       s_next = 0;
-      s_blk[0] = (unsigned long long)atomicAdd(gctr, 1u);
+      const unsigned g0 = atomicAdd(gctr, 1u);
+      if (g0 == 0u) gctr[2] = 1u;
+      s_blk[0] = (unsigned long long)g0;
       s_blk[1] = (1ull << 32) | atomicAdd(gctr, 1u);
     }
   }
@@ -505,7 +509,14 @@ scan_topk_kernel(const void* __restrict__ index, const float* __restrict__ queri
   TT_SCAN_STAMP(5);
   if (DYN && threadIdx.x == 0) {                            // last CTA out re-arms the counters for the next launch on this slot
     __threadfence();
-    if (atomicAdd(gctr + 1, 1u) == gridDim.x - 1) { gctr[0] = 0u; gctr[1] = 0u; __threadfence(); }
+    if (atomicAdd(gctr + 1, 1u) == gridDim.x - 1) {
+      if (*reinterpret_cast<volatile unsigned*>(gctr + 2) != 1u) {
+        printf("tt_b200: scan round counter of slot %d was not zero when the launch began\n", slot_id);
+        __trap();
+      }
+      gctr[0] = 0u; gctr[1] = 0u; gctr[2] = 0u;
+      __threadfence();
+    }
   }
 }
 

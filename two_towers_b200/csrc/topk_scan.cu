@@ -140,7 +140,8 @@ __device__ long long g_scan_dbg[8];
 // of a CTA = warps * 8 rows) are handed out to the CTAs through a global counter -- SMs do not stream at the same rate, and
 // with a fixed share per CTA the kernel waited 15-19 us for the slowest one (10 M rows: 1433 -> 1397 us, 7.3 TB/s).  The
 // narrower variants have half the bytes in flight and are latency-bound: the extra hop per step cost them more than the
-// balance gained (bf16, 10 M rows: 766 -> 823 us), so they keep the static interleaved schedule.
+// balance gained (bf16 x 256, 10 M rows: 766 -> 823 us with two quads per step, 730 -> 753 us with four, same box), so they
+// keep the static interleaved schedule.
 // One counter pair {next round, CTAs finished} per launch slot; the last CTA to finish resets its pair, so the counters are
 // zero between launches (they start zero: static storage).  Launches take slots round-robin.
 // Word 2: set by the CTA that drew round 0; the last CTA traps if nobody did (the counter was not zero when the launch began,

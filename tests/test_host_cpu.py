@@ -34,6 +34,34 @@ def test_cabi_exports_every_declared_symbol(built_library):
     assert _lib.load().tt_abi_version() == _lib.TT_ABI_VERSION == 5
 
 
+def test_shape_predicates_need_no_gpu(built_library):
+    """The planning entry points of the stored-E loss and the fused sharded search are pure host arithmetic: which shapes take
+    which path is decided (and testable) without a device."""
+    import ctypes as C
+    from two_towers_b200 import _lib
+    lib = _lib.load()
+    # stored-E loss: H >= 128 (H % 64 == 0, <= 256) and E = Bq x roundup(Bd, 64) bf16 within the L2 budget (48 MB by default)
+    assert lib.tt_inbatch_ce_stash_ok(4096, 4096, 256) == 1 and lib.tt_inbatch_ce_stash_ok(4096, 4096, 128) == 1
+    assert lib.tt_inbatch_ce_stash_ok(4096, 4096, 64) == 0 and lib.tt_inbatch_ce_stash_ok(4096, 4096, 200) == 0
+    assert lib.tt_inbatch_ce_stash_ok(8192, 8192, 256) == 0          # 128 MB: the recomputing document pass runs
+    assert lib.tt_inbatch_ce_stash_ok(4096, 32768, 256) == 0         # one rank's share of an 8-GPU global-negatives step
+    assert lib.tt_inbatch_ce_stash_ok(0, 10, 256) == 0
+    n = lib.tt_inbatch_ce_stash_bytes(1000, 3001, 256)               # E rows are padded to 64 columns; X / L and 1 - P_pos follow
+    assert n >= 1000 * 3008 * 2 + 1000 * 256 * 2 + 1000 * 4 and n % 256 == 0
+    # fused sharded search: double-buffered exchange, one CTA per query, slots that hold nq * k keys
+    x = _lib.P2P()
+    x.world, x.rank, x.slot_bytes, x.double_buffered, x.ctas = 8, 3, 1280, 1, 1
+    assert lib.tt_topk_scan_p2p_ok(C.byref(x), 1, 100) == 1
+    assert lib.tt_topk_scan_p2p_ok(C.byref(x), 2, 100) == 0          # ctas != nq
+    x.ctas = 2
+    assert lib.tt_topk_scan_p2p_ok(C.byref(x), 2, 100) == 0          # 2 x 100 keys do not fit a 1280-byte slot
+    x.slot_bytes = 2048
+    assert lib.tt_topk_scan_p2p_ok(C.byref(x), 2, 100) == 1
+    x.double_buffered = 0
+    assert lib.tt_topk_scan_p2p_ok(C.byref(x), 2, 100) == 0
+    assert lib.tt_topk_scan_p2p_ok(None, 1, 100) == 0
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_gpu_fails_loudly_no_fallback():
     from two_towers_b200 import _lib, ops

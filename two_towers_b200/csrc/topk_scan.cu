@@ -8,20 +8,29 @@
 //
 // Layout / algorithm (HBM-bound: N*H*s bytes per query batch):
 //   * index [N,H] row-major fp32 (or bf16); 8 lanes own one row (lane j reads 16-byte chunks
-//     j, j+8, ...: a warp instruction covers 4 rows x 128 contiguous bytes), 2 row-quads in
-//     flight per warp -> 16 independent LDG.128 per lane.
+//     j, j+8, ...: a warp instruction covers 4 rows x 128 contiguous bytes), 2 or 4 row-quads in
+//     flight per warp -> 16 independent LDG.128 per lane for fp32 x 256 and bf16 x 256 columns alike.
 //   * the query (<= 2 per pass) lives in registers; partial dots are combined with 3 xor
 //     shuffles inside the 8-lane group.
 //   * top-k: every warp keeps a private candidate buffer in shared memory (CAP >= 2k keys)
-//     and a running threshold = score of its current k-th best.  A row is appended only if
-//     score >= threshold (ballot + prefix popcount, no atomics); a full buffer is pruned by an
-//     in-warp bitonic sort.  Expected appends per warp ~ k (1 + ln(rows_per_warp / k)).
+//     and a running threshold.  A row is appended only if score >= threshold (ballot + prefix
+//     popcount, no atomics); a full buffer is pruned by an in-warp bitonic sort.  The threshold
+//     STARTS at the k-th best score of a CTA-wide sample (the first 64 rows of every warp, scored
+//     unconditionally): a warp's own k best rows give a weak bound on a small shard.
 //   * keys are 64-bit: (order-preserving score bits << 32) | ~row, so "larger key" ==
 //     "higher score, ties -> LOWER row index" (BASELINE tie rule) and keys are unique.
-//   * block epilogue: bitonic sort over all warps' buffers, the block's top-k goes to global;
-//     a second kernel (one block per query) radix-selects the k-th key over all block lists
-//     and sorts the survivors.  The same kernel implements tt_topk_merge for the
-//     row-sharded multi-GPU search.
+//   * selections over a few hundred keys (sample threshold, block epilogue, merge of the block
+//     lists, merge of the shards' lists) all work the same way: sorted runs (a warp sorts its 64
+//     keys in registers with shuffles), the k-th largest of the runs' HEADS as a lower bound of the
+//     k-th largest key, and a rank computation over the keys that reach it (one key per thread,
+//     broadcast reads of shared memory) -- a handful of barriers instead of a CTA-wide bitonic sort
+//     or radix passes over everything.  The bitonic / radix code remains as the fallback for shapes
+//     that do not fit (k > 128, ties that flood the survivors, tiny shards).
+//   * a second kernel (one block per query, launched programmatically behind the scan) selects
+//     over the block lists; on a row-sharded index the same launch also exchanges the shard's k
+//     keys with every rank over NVLink peer memory and selects the global top-k
+//     (merge_exchange_merge_kernel, tt_topk_scan_p2p).  tt_topk_merge (lists from anywhere) keeps
+//     the radix select.
 #include <math_constants.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -13,6 +13,12 @@
 //   to 128B-swizzled shared memory -> O += P Y as a second tcgen05.mma whose B operand is the
 //   SAME TMA-loaded Y tile read MN-major.  O (128 x H fp32) lives in TMEM for the whole loop.
 //   S(t+1) is issued before O(t) so the tensor pipe overlaps the exp2 epilogue.
+// one-pass form (ce_bwd_body MODE 2, the trainer's default): unit-norm rows bound every logit, so
+//   E = exp(logit - bound) needs no running maximum: the loss forward and dQ come out of ONE pass
+//   over S, the row normaliser is applied in the cluster tail.
+// stored-E form (MODE 2 with e_store + MODE 3, while B_q x B_d bf16 fits in L2): MODE 2 also TMA-stores
+//   every E tile it forms; the document gradient is then the plain product dD = E^T (X / L) -- both
+//   operands MN-major, no epilogue in the loop, S formed once per step.
 // Each output row has one owner CTA per split and splits are summed in split order:
 // bitwise-reproducible gradients.
 #include <math_constants.h>

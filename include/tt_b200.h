@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TT_ABI_VERSION 5
+#define TT_ABI_VERSION 6
 
 enum { TT_OK = 0, TT_ERR_INVALID = -1, TT_ERR_CUDA = -2, TT_ERR_ARCH = -3, TT_ERR_WORKSPACE = -4,
        TT_ERR_UNSUPPORTED = -5 };
@@ -417,6 +417,14 @@ int tt_adamw_step_publish(float* param, const float* grad, float* exp_avg, float
  * on this stream (tt_p2p_allgather of every rank's local gradient): the slots are summed in rank order while they are
  * read -- the data-parallel all-reduce (twotower semantics: one model, mean over the global batch) costs no reduction
  * launch, and the parameters stay bitwise identical on all ranks.  grad_sum (nullable) receives the summed gradient. */
+/* tt_adamw_step_publish with a SECOND gradient for one segment of the flat buffer (parameters extra_offset .. + extra_n, both
+ * multiples of 4): grad[i] + extra_grad[i - extra_offset] is what the update uses, and it is written back to grad.  Used by
+ * FusedTrainer with untied towers: the two towers' backward passes run concurrently on two streams, each writing its own
+ * embedding-table gradient (twotower/train.py:120-139: one table shared by both towers), and the sum costs no launch. */
+int tt_adamw_step_extra(float* param, float* grad, const float* extra_grad, int64_t extra_offset, int64_t extra_n,
+                        float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2, double eps,
+                        double weight_decay, int64_t* step_count, void* param_bf16, const float* publish_src,
+                        float* publish_dst, void* stream);
 int tt_adamw_step_p2p(float* param, float* grad_sum, const tt_p2p_t* grad_exchange, float* exp_avg, float* exp_avg_sq,
                       int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
                       int64_t* step_count, void* param_bf16, const float* publish_src, float* publish_dst,

@@ -31,7 +31,7 @@ def test_cabi_exports_every_declared_symbol(built_library):
         assert hasattr(lib, name), f"{name} declared in include/tt_b200.h but not exported"
     from two_towers_b200 import _lib
     assert set(_lib.SIGNATURES) == declared       # the ctypes table mirrors the header exactly
-    assert _lib.load().tt_abi_version() == _lib.TT_ABI_VERSION == 5
+    assert _lib.load().tt_abi_version() == _lib.TT_ABI_VERSION == 6
 
 
 def test_shape_predicates_need_no_gpu(built_library):

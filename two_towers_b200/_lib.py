@@ -16,7 +16,7 @@ TT_PREC_FP32 = 0
 TT_PREC_BF16 = 1
 TT_TOPK_MAX = 1024
 TT_ERR_UNSUPPORTED = -5
-TT_ABI_VERSION = 5          # must equal TT_ABI_VERSION in include/tt_b200.h (a stale .so fails loudly at load)
+TT_ABI_VERSION = 6          # must equal TT_ABI_VERSION in include/tt_b200.h (a stale .so fails loudly at load)
 
 _vp, _i, _i64, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
 
@@ -59,6 +59,7 @@ SIGNATURES = {
     "tt_selftest_tc_gemm": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "tt_adamw_step": (_i, [_vp] * 4 + [_i64] + [C.c_double] * 5 + [_vp, _vp, _vp]),
     "tt_adamw_step_publish": (_i, [_vp] * 4 + [_i64] + [C.c_double] * 5 + [_vp, _vp, _vp, _vp, _vp]),
+    "tt_adamw_step_extra": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64] + [C.c_double] * 5 + [_vp, _vp, _vp, _vp, _vp]),
 }
 
 class MlpEmbed(C.Structure):

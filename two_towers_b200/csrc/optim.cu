@@ -16,6 +16,11 @@ struct GradSlots {
   int world;
   size_t slot_floats;
   float* sum_out;              // nullable: the summed gradient is also written here (p.grad stays meaningful)
+  // a second gradient for one segment of the flat buffer (parameters extra_lo .. extra_lo + extra_n, both multiples of 4):
+  // the embedding-table gradient of the tower whose backward ran concurrently on a second stream (FusedTrainer, untied
+  // towers) -- added after `g`, i.e. in the order the serial schedule accumulates it
+  const float* extra;
+  int64_t extra_lo, extra_n;
 };
 
 __global__ void __launch_bounds__(256)
@@ -69,6 +74,14 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     } else {
       g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
     }
+    if (gs.extra) {
+      const int64_t e = i * 4 - gs.extra_lo;
+      if (e >= 0 && e < gs.extra_n) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(gs.extra + e));
+        g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
+        if (gs.sum_out) reinterpret_cast<float4*>(gs.sum_out)[i] = g4;
+      }
+    }
     float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
     update(g4.x, p4.x, m4.x, v4.x); update(g4.y, p4.y, m4.y, v4.y);
     update(g4.z, p4.z, m4.z, v4.z); update(g4.w, p4.w, m4.w, v4.w);
@@ -84,6 +97,10 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
       if (gs.sum_out) gs.sum_out[i] = gi;
     } else {
       gi = g[i];
+    }
+    if (gs.extra && i >= gs.extra_lo && i < gs.extra_lo + gs.extra_n) {
+      gi += gs.extra[i - gs.extra_lo];
+      if (gs.sum_out) gs.sum_out[i] = gi;
     }
     update(gi, pi, mi, vi);
     p[i] = pi; m[i] = mi; v[i] = vi;
@@ -143,6 +160,19 @@ extern "C" int tt_adamw_step_p2p(float* param, float* grad_sum, const tt_p2p_t* 
   gs.world = grad_exchange->world; gs.slot_floats = grad_exchange->slot_bytes / 4; gs.sum_out = grad_sum;
   return adamw_launch(param, grad_sum ? grad_sum : param, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_count,
                       param_bf16, publish_src, publish_dst, gs, stream);
+}
+
+extern "C" int tt_adamw_step_extra(float* param, float* grad, const float* extra_grad, int64_t extra_offset, int64_t extra_n,
+                                   float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2, double eps,
+                                   double weight_decay, int64_t* step_count, void* param_bf16, const float* publish_src,
+                                   float* publish_dst, void* stream) {
+  TT_CHECK_ARG(extra_grad && extra_offset >= 0 && extra_n > 0 && extra_offset + extra_n <= n && extra_offset % 4 == 0 && extra_n % 4 == 0 &&
+               (reinterpret_cast<uintptr_t>(extra_grad) & 15) == 0,
+               "adamw_step_extra: the extra gradient must cover a 4-aligned segment of the flat buffer");
+  tt::GradSlots gs{};
+  gs.extra = extra_grad; gs.extra_lo = extra_offset; gs.extra_n = extra_n; gs.sum_out = grad;
+  return adamw_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_count, param_bf16,
+                      publish_src, publish_dst, gs, stream);
 }
 
 extern "C" int tt_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

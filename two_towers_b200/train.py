@@ -254,6 +254,19 @@ class FusedTrainer:
                  lib.tt_embed_pool_bwd_workspace(R, L, self.V, self.E),
                  lib.tt_inbatch_ce_workspace(B * self.world, B * self.world, self.H, self.prec))
         self.ws = torch.empty(int(nb), dtype=torch.uint8, device=self.dev)
+        # untied towers: the two towers' forward and backward launches are independent chains (3 launches each in the backward),
+        # so they run concurrently on two streams inside the captured step.  The second tower then needs its own workspaces
+        # and -- both towers share ONE embedding table (twotower/train.py:120-139) -- its own table-gradient buffer, which the
+        # optimizer launch adds to the first tower's (tt_adamw_step_extra: no launch for the sum, same order of additions as
+        # the serial schedule).  With a process group the sum would have to precede the gradient exchange: serial there.
+        self.par_towers = bool(len(self.groups) == 2 and bf and os.environ.get("TT_TOWER_PAR", "1") != "0" and
+                               all(isinstance(t, MeanPoolingTower) for t, _, _ in self.groups) and
+                               (self.world == 1 or not self.embed_fused) and self.n_params % 4 == 0)
+        if self.par_towers:
+            self.ws2 = torch.empty_like(self.ws)
+            self.embed_ws2 = torch.empty_like(self.embed_ws) if self.embed_ws is not None else None
+            self.table_grad2 = torch.zeros((self.table.numel() + 3) // 4 * 4, **f32) if self.embed_fused else None
+            self._tower_stream = torch.cuda.Stream(device=self.dev)
         self._loss_ring = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]   # read_loss_async()
         self._loss_ring_g = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]  # written by graph 0 / 1
         self._graphs: List[Optional[torch.cuda.CUDAGraph]] = [None, None]
@@ -285,9 +298,11 @@ class FusedTrainer:
         seed = (tower._seed + 0xA24BAED4963EE407 * (gi + 1) + 0x9FB21C651E98DF25 * (self.rank + 1)) % (1 << 64)
         return float(tower.dropout_p), train, seed
 
-    def _tower_fwd(self, gi: int):
+    def _tower_fwd(self, gi: int, second: bool = False):
+        """second: this call runs on the second tower stream (par_towers) and uses the second set of workspaces."""
         tower, r0, nr = self.groups[gi]
         lib, s, sv = self.lib, self._stream(), self.saved[gi]
+        ws = self.ws2 if second else self.ws
         x, y = self.pooled[r0:r0 + nr], self.y[r0:r0 + nr]
         yb = self.y_bf16[r0:r0 + nr] if self.y_bf16 is not None else None
         xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
@@ -311,8 +326,8 @@ class FusedTrainer:
                                  _p(sv["h1"]), _p(z_ptr), _p(y_ptr), _p(yb), _p(xb),
                                  _p(self._shadow(l1.weight) if self.e_shadow else None),
                                  _p(self._shadow(l2.weight)), _p(self.h1_bf16[gi]), _p(inv),
-                                 C.byref(emb) if emb is not None else None, self.prec, _p(self.ws),
-                                 self.ws.numel(), s), "tt_mlp_fwd")
+                                 C.byref(emb) if emb is not None else None, self.prec, _p(ws),
+                                 ws.numel(), s), "tt_mlp_fwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
             p_drop, train, seed = self._dropout_cfg(tower, gi)
@@ -323,16 +338,21 @@ class FusedTrainer:
             check(lib.tt_proj_ln_fwd(_p(x), None, None, None, None, nr, self.E, self.H, 0, 0.0, 0, 0, None, None, None,
                                      None, _p(y), self.prec, None, 0, s), "tt_proj_ln_fwd")
 
-    def _tower_bwd(self, gi: int):
+    def _tower_bwd(self, gi: int, second: bool = False):
         tower, r0, nr = self.groups[gi]
         lib, s, sv = self.lib, self._stream(), self.saved[gi]
+        ws = self.ws2 if second else self.ws
         x, dy = self.pooled[r0:r0 + nr], self.dy[r0:r0 + nr]          # slice 0; further slices dy_part_stride apart
         dx = self.dpooled[r0:r0 + nr] if self.train_table else None
         xb = self.pooled_bf16[r0:r0 + nr] if self.pooled_bf16 is not None else None
         emb = None
         if self.embed_fused:
-            emb = _lib.MlpEmbed(self.pool_bf16[r0:r0 + nr].data_ptr(), self.V, self.table.data_ptr(), None,
-                                self.table.grad.data_ptr(), 1 if gi > 0 else 0, self.embed_ws.data_ptr(), self.embed_ws.numel())
+            if second:                                      # own table-gradient buffer, summed inside the optimizer launch
+                emb = _lib.MlpEmbed(self.pool_bf16[r0:r0 + nr].data_ptr(), self.V, self.table.data_ptr(), None,
+                                    self.table_grad2.data_ptr(), 0, self.embed_ws2.data_ptr(), self.embed_ws2.numel())
+            else:
+                emb = _lib.MlpEmbed(self.pool_bf16[r0:r0 + nr].data_ptr(), self.V, self.table.data_ptr(), None,
+                                    self.table.grad.data_ptr(), 1 if gi > 0 else 0, self.embed_ws.data_ptr(), self.embed_ws.numel())
             dx = None
         if isinstance(tower, MeanPoolingTower):
             l1, l2 = tower.feed_forward[0], tower.feed_forward[2]
@@ -347,7 +367,7 @@ class FusedTrainer:
                                  _p(self._shadow(l2.weight)),
                                  _p(self.h1_bf16[gi]), self.dy_parts, self.dy_part_stride,
                                  C.byref(emb) if emb is not None else None, _p(yb if pure else None), _p(inv),
-                                 _p(dzb), _p(dzc), self.prec, _p(self.ws), self.ws.numel(), s), "tt_mlp_bwd")
+                                 _p(dzb), _p(dzc), self.prec, _p(ws), ws.numel(), s), "tt_mlp_bwd")
         elif tower.has_projection:
             lin, ln = tower.projection[0], tower.projection[2]
             p_drop, train, seed = self._dropout_cfg(tower, gi)
@@ -397,8 +417,11 @@ class FusedTrainer:
                                         None if tower_pools else _p(self.pooled), _p(self.inv_len),
                                         None if tower_pools else _p(self.pooled_bf16), _p(self.pool_bf16), s), "tt_embed_pool_fwd")
         self._mark("embed_pool_fwd")
-        for gi in range(len(self.groups)):
-            self._tower_fwd(gi)
+        if self.par_towers:
+            self._towers_parallel(self._tower_fwd)
+        else:
+            for gi in range(len(self.groups)):
+                self._tower_fwd(gi)
         self._mark("tower_fwd")
         q, d = self.y[:B], self.y[B:2 * B]
         dq, dd = self.dy[:B], self.dy[B:2 * B]
@@ -425,8 +448,11 @@ class FusedTrainer:
                                      _p(self.grad_scale) if self.world > 1 else None, _p(dq), _p(dd), _p(dn), s),
                   "tt_triplet_bwd")
         self._mark("loss")
-        for gi in range(len(self.groups)):
-            self._tower_bwd(gi)
+        if self.par_towers:
+            self._towers_parallel(self._tower_bwd)
+        else:
+            for gi in range(len(self.groups)):
+                self._tower_bwd(gi)
         if self.train_table and not self.embed_fused:
             check(lib.tt_embed_pool_bwd(_p(self._ids_cur), idb, _p(self.inv_len), _p(self.dpooled), R, self.L, self.V,
                                         self.E, _p(self.table.grad), _p(self.ws), self.ws.numel(), s),
@@ -446,11 +472,30 @@ class FusedTrainer:
             if self.world > 1:
                 parallel.allreduce_sum_(self.flat_grad, self.group)
             self._mark("grad_exchange")
-            check(lib.tt_adamw_step_publish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
-                                            self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                            _p(self.step_count), _p(self.flat_bf16), _p(self.loss) if pub is not None else None,
-                                            _p(pub), s), "tt_adamw_step")
+            if self.par_towers and self.embed_fused:
+                # the second tower's table gradient joins here: grad[table] + table_grad2, written back to the table's .grad
+                check(lib.tt_adamw_step_extra(_p(self.flat), _p(self.flat_grad), _p(self.table_grad2), self.offsets[id(self.table)],
+                                              self.table_grad2.numel(), _p(self.exp_avg), _p(self.exp_avg_sq), self.n_params,
+                                              self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                              _p(self.step_count), _p(self.flat_bf16), _p(self.loss) if pub is not None else None,
+                                              _p(pub), s), "tt_adamw_step_extra")
+            else:
+                check(lib.tt_adamw_step_publish(_p(self.flat), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                                self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                                _p(self.step_count), _p(self.flat_bf16), _p(self.loss) if pub is not None else None,
+                                                _p(pub), s), "tt_adamw_step")
         self._mark("adamw")
+
+    def _towers_parallel(self, fn) -> None:
+        """Both towers' launches of one phase (forward or backward) as two concurrent chains: tower 0 on the step's stream,
+        tower 1 on the second tower stream, forked behind everything launched so far and joined before anything that follows
+        (capturable: the fork / join become graph edges)."""
+        cur = torch.cuda.current_stream()
+        self._tower_stream.wait_stream(cur)
+        fn(0)
+        with torch.cuda.stream(self._tower_stream):
+            fn(1, second=True)
+        cur.wait_stream(self._tower_stream)
 
     def _local_loss_fwd(self, s):
         """In-batch loss forward against the local documents (one launch on the tensor-core path)."""
